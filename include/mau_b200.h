@@ -1,0 +1,157 @@
+/*
+ * mau_b200.h -- C ABI of the B200-native hot path of the Metadata-Augmented U-Net.
+ *
+ * This is the drop-in boundary for the forward/backward of the reference's
+ * `UrbanPredictor` (reference src/model.py:295-329).  The reference has no FFI of its
+ * own (it is pure Python on top of PyTorch/ATen), so each entry point below cites the
+ * reference *call* it replaces.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; mau_last_error() returns
+ *     a thread-local, NUL-terminated description of the last failure.  Nothing throws
+ *     across the ABI.
+ *   - all pointers named *_dev are device pointers on the plan's device; the caller owns
+ *     parameters, buffers, inputs, outputs and gradients; the plan owns only its
+ *     workspace, packed weights and TMA descriptors.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing is
+ *     synchronised (the plan is stateful: one forward/backward in flight per plan).
+ *   - tensors crossing the ABI are contiguous fp32 NCHW exactly as the reference's
+ *     callers hold them (src/dataset.py:99-106); counters are int64.
+ */
+#ifndef MAU_B200_H_
+#define MAU_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAU_MODEL_UNET   0   /* UrbanPredictor_unet,   src/model.py:195-292 */
+#define MAU_MODEL_UNETPP 1   /* UrbanPredictor_unetpp, src/model.py:51-193  */
+
+#define MAU_PRECISION_BF16 0 /* NHWC bf16 activations, tcgen05 implicit GEMM, fp32 accumulate */
+#define MAU_PRECISION_FP32 1 /* NHWC fp32 activations, FFMA convolutions (1e-5 parity mode)   */
+
+typedef struct mau_config {
+  int32_t model_type;           /* MAU_MODEL_* (src/model.py:299,311)                         */
+  int32_t spatial_channels;     /* ctor arg, 23 in conf/config.yaml:18                         */
+  int32_t temporal_dim;         /* TemporalEncoder out_dim, src/model.py:27                    */
+  int32_t meta_features;        /* MetadataEncoder in_features (4 or 8), src/model.py:42       */
+  int32_t meta_dim;             /* MetadataEncoder out_dim, src/model.py:44                    */
+  int32_t lstm_dim;             /* LSTM hidden size, src/model.py:26                           */
+  int32_t out_channels;         /* 1x1 head, src/model.py:241 / :96                            */
+  int32_t filters[5];           /* nb_filter, src/model.py:322 / :54                           */
+  int32_t temporal_embeddings;  /* U-Net only flag, src/model.py:198; U-Net++ always 1         */
+  int32_t metadata_embeddings;  /* U-Net only flag, src/model.py:199; U-Net++ always 1         */
+  int32_t deep_supervision;     /* U-Net++ only, src/model.py:52,180                           */
+  int32_t batch, height, width; /* maps [B, spatial_channels, H, W]                            */
+  int32_t seq_len;              /* T of temp_series [B, T] (runtime length, src/model.py:29)   */
+  int32_t training;             /* nn.Module.training: batch-stat BN + saved activations        */
+  int32_t precision;            /* MAU_PRECISION_*                                             */
+  int32_t device;               /* CUDA device ordinal                                         */
+  int32_t flags;                /* MAU_FLAG_* bit set                                          */
+} mau_config;
+
+#define MAU_FLAG_SHARED_MAPS   1  /* all B rows share maps and series (metadata_sensitivity sweep,
+                                     test/metadata_sensitivity.py:294-311): encoder computed once */
+#define MAU_FLAG_CONV_TAPLOAD  2  /* debug: force the 9-box-loads-per-chunk conv main loop        */
+#define MAU_FLAG_CONV_FFMA     4  /* debug: run bf16 plans on the FFMA convolution kernels         */
+
+typedef struct mau_plan mau_plan; /* opaque */
+
+/* library / error plumbing */
+const char* mau_last_error(void);
+int         mau_version(void);
+/* number of CUDA kernels this library has launched in the calling process (bench gpu_launches) */
+int64_t     mau_launch_count(void);
+
+/* --- the plan: replaces nn.Module construction + .to(device) (src/train.py:194-206) ------- */
+int    mau_plan_create(const mau_config* cfg, mau_plan** out);
+int    mau_plan_destroy(mau_plan* plan);
+size_t mau_plan_workspace_bytes(const mau_plan* plan);
+/* number of state tensors (state_dict order: parameters and buffers) the plan expects */
+int    mau_plan_num_state(const mau_plan* plan);
+/* element count of state tensor i, and its role: 0 = trainable fp32 parameter used by this
+ * configuration, 1 = fp32 parameter present but unused (flag-disabled encoder: grad stays
+ * None, src/model.py:263-264), 2 = fp32 running statistic, 3 = int64 num_batches_tracked */
+int    mau_plan_state_info(const mau_plan* plan, int i, int64_t* numel, int* role);
+/* a human-readable description of the layer graph (JSON), for tests and tooling; works
+ * without a GPU when created through mau_plan_describe_config */
+int    mau_plan_describe_config(const mau_config* cfg, char* buf, size_t buflen);
+/* algorithmic work of one forward over the whole batch (dense reference graph) */
+int    mau_plan_flops(const mau_plan* plan, double* fwd_flops, double* bwd_flops);
+
+/* --- forward: replaces `model(maps, temp_series, metadata)` (src/model.py:328,
+ *     called at src/train.py:245, test/evaluate.py:186, test/metadata_sensitivity.py:310) ---
+ * state_dev[i]: device pointer of state tensor i (state_dict order).  In training mode the
+ * running_mean / running_var / num_batches_tracked entries are updated in place exactly like
+ * nn.BatchNorm2d does.  out_dev: [B, out_channels, H, W] fp32 (deep supervision:
+ * [4, B, out_channels, H, W]). */
+int mau_plan_forward(mau_plan* plan, void* const* state_dev, const float* maps_dev,
+                     const float* temp_series_dev, const float* metadata_dev, float* out_dev,
+                     void* stream);
+
+/* --- backward: replaces `loss.backward()` through the model (src/train.py:252) -------------
+ * grad_out_dev: dL/d out, same shape as out.  grads_dev[i]: where to write dL/d state[i]
+ * (fp32, same shape), or NULL to skip; entries for unused / non-parameter state must be NULL.
+ * Gradients are written (not accumulated). Must follow a training-mode forward on the plan. */
+int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* grads_dev,
+                      void* stream);
+
+/* optional: called from inside backward as soon as all gradients up to (and including) the
+ * given state index are final on `stream` -- the hook a data-parallel caller uses to launch a
+ * bucketed all-reduce that overlaps the rest of backward (new capability; the reference is
+ * single-GPU, src/train.py:99).  first_index..last_index is a contiguous state-index range. */
+typedef void (*mau_grad_ready_fn)(void* user, int first_index, int last_index);
+int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user);
+
+/* per-layer device timings of the last forward/backward (ms, CUDA events on `stream`);
+ * enable, run, then read.  names: '\n'-separated, same order as ms[]. */
+int mau_plan_profile(mau_plan* plan, int enable);
+int mau_plan_profile_read(mau_plan* plan, char* names, size_t names_len, float* ms, int max_n, int* n);
+
+/* --- training loss terms: replaces F.l1_loss / F.mse_loss / gradient_loss
+ *     (src/utils/losses.py:5-25,33,67-70); SSIM (piq) is out of scope.
+ * kind: 0 = L1 + lambda*grad, 1 = MSE + lambda*grad.  losses_dev[4] = {total, pixel, gradient, 0}.
+ * grad_dev (nullable): dL_total/d pred, same shape as pred. */
+int mau_loss_forward_backward(int kind, const float* pred_dev, const float* target_dev, int B, int C,
+                              int H, int W, float lambda_grad, float* losses_dev, float* grad_dev,
+                              void* stream);
+
+/* --- evaluation metrics: replaces the NumPy loop of test/evaluate.py:210-275 ---------------
+ * dw_map_dev [B,H,W] int64 = argmax_c(maps[b,c]*c, c<9) (ties -> lowest index, bit-exact);
+ * temperature channel (index 1) is un-normalised by *temp_std + temp_mean (test/evaluate.py:33-36)
+ * unless temp_std == 0.  sums_dev [B, C, 10, 3] float64: for class slot k (0 = overall, 1..9 = DW
+ * class k-1): {count, sum |p-g|, sum (p-g)^2}. */
+int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred_dev,
+                     const float* target_dev, int B, int C, int H, int W, float temp_mean,
+                     float temp_std, int64_t* dw_map_dev, double* sums_dev, void* stream);
+
+/* --- single operators on raw NHWC device buffers (used by the kernel-level parity tests) ----
+ * dtype: 0 = bf16, 1 = fp32.  x [B,H,W,Cin_stride], w OIHW fp32 [Cout,Cin,3,3],
+ * y [B,H,W,Cout_stride]; y = relu?(conv(x,w)*scale + shift).  impl: 0 = tcgen05 halo main loop,
+ * 1 = tcgen05 tap-load main loop, 2 = FFMA. */
+int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
+                   const float* w_oihw_dev, const float* scale_dev, const float* shift_dev, int relu,
+                   int Cout, void* y_dev, int Cout_stride, void* stream);
+/* dW [Cout,Cin,3,3] fp32 = sum_pixels dy (x) x ; impl 0 = tcgen05, 2 = FFMA */
+int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_dev, int B, int H, int W,
+                         int Cin, int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev,
+                         void* stream);
+int mau_op_maxpool2x2(int dtype, const void* x_dev, int B, int H, int W, int C, void* y_dev, void* stream);
+int mau_op_bilinear(int dtype, const void* x_dev, int B, int Hin, int Win, int C, int Hout, int Wout,
+                    void* y_dev, void* stream);
+int mau_op_nchw_to_nhwc(int dtype, const float* x_dev, int B, int C, int H, int W, int Cstride,
+                        void* y_dev, void* stream);
+int mau_op_nhwc_to_nchw(int dtype, const void* x_dev, int B, int C, int H, int W, int Cstride,
+                        float* y_dev, void* stream);
+int mau_op_lstm_last_hidden(const float* series_dev, int B, int T, int hidden, const float* w_ih,
+                            const float* w_hh, const float* b_ih, const float* b_hh, float* h_out_dev,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAU_B200_H_ */

@@ -1,0 +1,9 @@
+"""B200-native hot path of the Metadata-Augmented U-Net (import name: ``mau_b200``).
+
+Public surface mirrors reference ``src/model.py``: :class:`UrbanPredictor` (same
+constructor, ``forward(maps, temp_series, metadata)`` and ``state_dict`` layout).
+"""
+from .model import UrbanPredictor, UrbanPredictor_unet, UrbanPredictor_unetpp  # noqa: F401
+from . import engine  # noqa: F401
+
+__all__ = ["UrbanPredictor", "UrbanPredictor_unet", "UrbanPredictor_unetpp", "engine"]

@@ -1,0 +1,325 @@
+"""ctypes binding of the C-ABI library (include/mau_b200.h) + the autograd bridge.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every
+kernel that runs belongs to ``libmau_b200.so``.  If the library is missing the import of
+this module still succeeds (so CPU-only tooling can introspect the package) but any attempt
+to build a plan raises ``RuntimeError`` -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import threading
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmau_b200.so")
+
+MODEL_UNET, MODEL_UNETPP = 0, 1
+PRECISIONS = {"bf16": 0, "fp32": 1}
+FLAG_SHARED_MAPS, FLAG_CONV_TAPLOAD, FLAG_CONV_FFMA = 1, 2, 4
+ROLE_PARAM, ROLE_UNUSED_PARAM, ROLE_RUNNING_STAT, ROLE_COUNTER = 0, 1, 2, 3
+
+
+def default_precision() -> str:
+    p = os.environ.get("MAU_PRECISION", "bf16")
+    return p if p in PRECISIONS else "bf16"
+
+
+class MauConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "model_type", "spatial_channels", "temporal_dim", "meta_features", "meta_dim", "lstm_dim",
+        "out_channels")] + [("filters", C.c_int32 * 5)] + [(n, C.c_int32) for n in (
+        "temporal_embeddings", "metadata_embeddings", "deep_supervision", "batch", "height", "width",
+        "seq_len", "training", "precision", "device", "flags")]
+
+
+GRAD_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+# every symbol include/mau_b200.h declares (tests check the .so exports all of them)
+EXPORTS = (
+    "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
+    "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
+    "mau_plan_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook",
+    "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics",
+    "mau_op_conv3x3", "mau_op_conv3x3_wgrad", "mau_op_maxpool2x2", "mau_op_bilinear",
+    "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
+)
+
+
+def lib():
+    """Load libmau_b200.so once; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"mau_b200: CUDA library not built ({LIB_PATH} missing). Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` -- there is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.mau_last_error.restype = C.c_char_p
+        L.mau_version.restype = C.c_int
+        L.mau_launch_count.restype = C.c_int64
+        L.mau_plan_create.argtypes = [C.POINTER(MauConfig), C.POINTER(C.c_void_p)]
+        L.mau_plan_destroy.argtypes = [C.c_void_p]
+        L.mau_plan_workspace_bytes.argtypes = [C.c_void_p]
+        L.mau_plan_workspace_bytes.restype = C.c_size_t
+        L.mau_plan_num_state.argtypes = [C.c_void_p]
+        L.mau_plan_state_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.mau_plan_describe_config.argtypes = [C.POINTER(MauConfig), C.c_char_p, C.c_size_t]
+        L.mau_plan_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.mau_plan_forward.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mau_plan_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+        L.mau_plan_set_grad_hook.argtypes = [C.c_void_p, GRAD_HOOK, C.c_void_p]
+        L.mau_plan_profile.argtypes = [C.c_void_p, C.c_int]
+        L.mau_plan_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_float),
+                                            C.c_int, C.POINTER(C.c_int)]
+        L.mau_loss_forward_backward.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mau_eval_metrics.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+        L.mau_op_conv3x3.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_void_p]
+        L.mau_op_conv3x3_wgrad.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p]
+        L.mau_op_maxpool2x2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]
+        L.mau_op_bilinear.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_void_p, C.c_void_p]
+        L.mau_op_nchw_to_nhwc.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p]
+        L.mau_op_nhwc_to_nchw.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p]
+        L.mau_op_lstm_last_hidden.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().mau_last_error()
+        raise RuntimeError(f"mau_b200 {what}: {msg.decode() if msg else 'error'} (code {rc})")
+
+
+def _stream_ptr() -> C.c_void_p:
+    # the *calling thread's* current stream (backward runs on the autograd worker thread)
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_config(cfg: Dict) -> MauConfig:
+    c = MauConfig()
+    for k, v in cfg.items():
+        if k == "filters":
+            c.filters = (C.c_int32 * 5)(*[int(x) for x in v])
+        else:
+            setattr(c, k, int(v))
+    return c
+
+
+def describe(cfg: Dict) -> Dict:
+    """Layer graph of a configuration as a dict (host logic only; needs no GPU)."""
+    c = make_config(cfg)
+    buf = C.create_string_buffer(1 << 20)
+    check(lib().mau_plan_describe_config(C.byref(c), buf, len(buf)), "describe")
+    return json.loads(buf.value.decode())
+
+
+class Plan:
+    """One (variant, B, H, W, T, mode, precision) instance of the engine."""
+
+    def __init__(self, cfg: Dict):
+        self.cfg = dict(cfg)
+        self._c = make_config(cfg)
+        self._h = C.c_void_p()
+        self.device = torch.device("cuda", int(cfg.get("device", 0)))
+        with torch.cuda.device(self.device):
+            check(lib().mau_plan_create(C.byref(self._c), C.byref(self._h)), "plan_create")
+        L = lib()
+        self.num_state = L.mau_plan_num_state(self._h)
+        self.roles: List[int] = []
+        self.numels: List[int] = []
+        for i in range(self.num_state):
+            n, r = C.c_int64(), C.c_int()
+            check(L.mau_plan_state_info(self._h, i, C.byref(n), C.byref(r)), "state_info")
+            self.roles.append(r.value)
+            self.numels.append(n.value)
+        self.uses_metadata = bool(cfg.get("metadata_embeddings", 1))
+        self.uses_series = bool(cfg.get("temporal_embeddings", 1))
+        self._hook_ref = None
+        B, H, W = cfg["batch"], cfg["height"], cfg["width"]
+        self.out_shape = ((4,) if cfg.get("deep_supervision") else ()) + (B, cfg["out_channels"], H, W)
+
+    # ------------------------------------------------------------------ #
+    def close(self):
+        if self._h:
+            lib().mau_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(lib().mau_plan_workspace_bytes(self._h))
+
+    def flops(self):
+        f, b = C.c_double(), C.c_double()
+        check(lib().mau_plan_flops(self._h, C.byref(f), C.byref(b)), "flops")
+        return f.value, b.value
+
+    def used_state_indices(self) -> List[int]:
+        return [i for i, r in enumerate(self.roles) if r == ROLE_PARAM]
+
+    def _ptr_array(self, tensors: Sequence[Optional[torch.Tensor]]):
+        arr = (C.c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            arr[i] = None if t is None else t.data_ptr()
+        return arr
+
+    def _check_state(self, state: Sequence[torch.Tensor]):
+        if len(state) != self.num_state:
+            raise RuntimeError(f"mau_b200: plan expects {self.num_state} state tensors, got {len(state)}")
+        for i, t in enumerate(state):
+            if t.numel() != self.numels[i] or t.device != self.device or not t.is_contiguous():
+                raise RuntimeError(f"mau_b200: state tensor {i} mismatch: numel {t.numel()} vs "
+                                   f"{self.numels[i]}, device {t.device} vs {self.device}")
+            want = torch.int64 if self.roles[i] == ROLE_COUNTER else torch.float32
+            if t.dtype != want:
+                raise RuntimeError(f"mau_b200: state tensor {i} must be {want}, got {t.dtype} "
+                                   "(keep the module in fp32; precision is chosen by set_precision)")
+
+    def forward(self, state, maps, series, md, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._check_state(state)
+        if out is None:
+            out = torch.empty(self.out_shape, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().mau_plan_forward(self._h, self._ptr_array(state), maps.data_ptr(),
+                                         series.data_ptr() if series.numel() else None,
+                                         md.data_ptr() if md.numel() else None, out.data_ptr(),
+                                         _stream_ptr()), "forward")
+        return out
+
+    def backward(self, grad_out: torch.Tensor, grads: Sequence[Optional[torch.Tensor]]):
+        with torch.cuda.device(self.device):
+            check(lib().mau_plan_backward(self._h, grad_out.data_ptr(), self._ptr_array(grads),
+                                          _stream_ptr()), "backward")
+
+    def set_grad_hook(self, fn):
+        """fn(first_index, last_index) is called from inside backward when those state
+        gradients are final on the stream (data-parallel bucket launch point)."""
+        if fn is None:
+            self._hook_ref = None
+            check(lib().mau_plan_set_grad_hook(self._h, C.cast(None, GRAD_HOOK), None), "set_grad_hook")
+            return
+        self._hook_ref = GRAD_HOOK(lambda _u, a, b: fn(a, b))
+        check(lib().mau_plan_set_grad_hook(self._h, self._hook_ref, None), "set_grad_hook")
+
+    def profile(self, enable=True):
+        check(lib().mau_plan_profile(self._h, int(enable)), "profile")
+
+    def profile_read(self):
+        names = C.create_string_buffer(1 << 16)
+        ms = (C.c_float * 1024)()
+        n = C.c_int()
+        check(lib().mau_plan_profile_read(self._h, names, len(names), ms, 1024, C.byref(n)), "profile_read")
+        nm = names.value.decode().split("\n")[: n.value]
+        return list(zip(nm, [ms[i] for i in range(n.value)]))
+
+
+class HotPathFn(torch.autograd.Function):
+    """The single autograd node of the model (reference: the whole nn.Module graph of
+    src/model.py:261-292 / :123-193 as recorded by PyTorch autograd)."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, state, diff_idx, maps, series, md, *diff_params):
+        out = plan.forward(state, maps, series, md)
+        ctx.plan, ctx.diff_idx, ctx.n_state = plan, diff_idx, len(state)
+        ctx.shapes = [p.shape for p in diff_params]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        plan: Plan = ctx.plan
+        grad_out = grad_out.contiguous().float()
+        grads_full: List[Optional[torch.Tensor]] = [None] * ctx.n_state
+        outs = []
+        for i, shp in zip(ctx.diff_idx, ctx.shapes):
+            g = torch.empty(shp, device=plan.device, dtype=torch.float32)
+            grads_full[i] = g
+            outs.append(g)
+        plan.backward(grad_out, grads_full)
+        return (None, None, None, None, None, None, *outs)
+
+
+# ---------------------------------------------------------------------- #
+# stand-alone operators of the path (loss terms, evaluation metrics)
+# ---------------------------------------------------------------------- #
+def loss_terms(pred: torch.Tensor, target: torch.Tensor, kind: str = "l1", lambda_grad: float = 0.1,
+               need_grad: bool = True):
+    """L1|MSE + lambda * gradient-difference loss and its gradient w.r.t. pred in one pass
+    (reference src/utils/losses.py:5-25,33,67-70).  Returns (losses[4] tensor, grad or None)."""
+    B, Cc, H, W = pred.shape
+    losses = torch.zeros(4, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if need_grad else None
+    with torch.cuda.device(pred.device):
+        check(lib().mau_loss_forward_backward({"l1": 0, "mse": 1}[kind], pred.data_ptr(), target.data_ptr(),
+                                              B, Cc, H, W, lambda_grad, losses.data_ptr(),
+                                              grad.data_ptr() if need_grad else None, _stream_ptr()), "loss")
+    return losses, grad
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, kind, lambda_grad):
+        losses, grad = loss_terms(pred.contiguous(), target.contiguous(), kind, lambda_grad, True)
+        ctx.save_for_backward(grad)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g[0], None, None, None      # d total / d pred
+
+
+def compute_loss_l1_grad(outputs, targets, lambda_grad=0.1):
+    """{'total','pixel','gradient'} like the L1+gradient part of the reference's
+    compute_loss_l1_grad_ssim (src/utils/losses.py:59-99); 'total' carries the gradient."""
+    l = _LossFn.apply(outputs, targets, "l1", lambda_grad)
+    return {"total": l[0], "pixel": l[1].detach(), "gradient": l[2].detach()}
+
+
+def compute_loss_mse_gradient(outputs, targets, lambda_grad=0.1):
+    """src/utils/losses.py:41-57."""
+    l = _LossFn.apply(outputs, targets, "mse", lambda_grad)
+    return {"total": l[0], "mse": l[1].detach(), "gradient": l[2].detach()}
+
+
+def eval_metrics(maps: torch.Tensor, pred: torch.Tensor, target: torch.Tensor,
+                 temp_mean: float = 0.0, temp_std: float = 0.0):
+    """Device version of test/evaluate.py:210-275.  Returns (dw_map int64 [B,H,W],
+    sums float64 [B,C,10,3] = {count, sum|d|, sum d^2} for overall + 9 DW classes)."""
+    B, Cc, H, W = pred.shape
+    dw = torch.empty(B, H, W, device=pred.device, dtype=torch.int64)
+    sums = torch.zeros(B, Cc, 10, 3, device=pred.device, dtype=torch.float64)
+    with torch.cuda.device(pred.device):
+        check(lib().mau_eval_metrics(maps.data_ptr(), maps.shape[1], pred.data_ptr(), target.data_ptr(),
+                                     B, Cc, H, W, temp_mean, temp_std, dw.data_ptr(), sums.data_ptr(),
+                                     _stream_ptr()), "eval_metrics")
+    return dw, sums

@@ -1,0 +1,234 @@
+"""Drop-in ``UrbanPredictor`` whose forward/backward run on the B200 engine.
+
+Boundary mirrored: reference ``src/model.py:295-329`` (``UrbanPredictor``), with the
+constructor signature, sub-module names, parameter registration order and buffers of
+``UrbanPredictor_unet`` (``src/model.py:195-241``) and ``UrbanPredictor_unetpp``
+(``src/model.py:51-96``), so ``state_dict()`` is key-for-key / shape-for-shape equal and
+``optimizer.state_dict()`` parameter indices line up.
+
+The ``torch.nn`` layers below are *parameter containers only* (they give the reference's
+default initialisation and key names); none of their ``forward`` methods is ever called.
+All arithmetic happens in the C-ABI library (``csrc/``) through ``engine.Plan``.
+There is no CPU / eager fallback: tensors must live on a CUDA device and the library must
+be built, otherwise a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import engine
+
+try:  # the reference logs its embedding flags at construction (src/model.py:202)
+    from loguru import logger as _log
+except Exception:  # pragma: no cover - loguru is optional here
+    _log = None
+
+
+class _ConvPair(nn.Module):
+    """Parameter holder for one reference ``VGGBlock`` (src/model.py:9-16):
+    conv1/bn1/conv2/bn2, 3x3 convolutions with bias, BatchNorm2d with running stats."""
+
+    def __init__(self, cin: int, cmid: int, cout: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cmid, 3, padding=1)
+        self.bn1 = nn.BatchNorm2d(cmid)
+        self.conv2 = nn.Conv2d(cmid, cout, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(cout)
+
+
+class _SeriesParams(nn.Module):
+    """Holder for ``TemporalEncoder`` (src/model.py:23-27): lstm(1->hidden) + fc."""
+
+    def __init__(self, hidden: int, out_dim: int):
+        super().__init__()
+        self.lstm = nn.LSTM(input_size=1, hidden_size=hidden, batch_first=True)
+        self.fc = nn.Linear(hidden, out_dim)
+
+
+class _MetaParams(nn.Module):
+    """Holder for ``MetadataEncoder`` (src/model.py:38-45): fc.0 (in->32), fc.2 (32->out)."""
+
+    def __init__(self, in_features: int, out_dim: int):
+        super().__init__()
+        self.fc = nn.Sequential(nn.Linear(in_features, 32), nn.ReLU(), nn.Linear(32, out_dim))
+
+
+class _EngineNet(nn.Module):
+    """Common machinery: plan cache + dispatch into the C-ABI engine."""
+
+    _variant = -1
+
+    def _engine_config(self) -> Dict[str, int]:
+        raise NotImplementedError
+
+    def _init_engine_state(self):
+        # not registered as parameters/buffers -> invisible to state_dict()
+        object.__setattr__(self, "_plans", {})
+        object.__setattr__(self, "precision", engine.default_precision())
+
+    # ------------------------------------------------------------------ #
+    def _state_tensors(self) -> List[torch.Tensor]:
+        # state_dict order == registration order (parameters and buffers interleaved per module)
+        return list(self.state_dict(keep_vars=True).values())
+
+    def _plan_for(self, B: int, H: int, W: int, T: int, training: bool, device: torch.device):
+        key = (B, H, W, T, bool(training), self.precision, device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            cfg = dict(self._engine_config())
+            cfg.update(batch=B, height=H, width=W, seq_len=T, training=int(training),
+                       precision=engine.PRECISIONS[self.precision],
+                       device=device.index if device.index is not None else torch.cuda.current_device())
+            plan = engine.Plan(cfg)
+            if len(self._plans) >= 8:           # bound the workspace held by stale shapes
+                self._plans.pop(next(iter(self._plans))).close()
+            self._plans[key] = plan
+        return plan
+
+    def release_plans(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans.clear()
+
+    def forward(self, maps, temp_series, metadata):
+        if not maps.is_cuda:
+            raise RuntimeError("mau_b200: the hot path runs on a CUDA device only (no CPU fallback); "
+                               "move the model and its inputs to cuda")
+        if maps.dim() != 4 or maps.shape[1] != self._cfg["spatial_channels"]:
+            raise RuntimeError(f"maps must be [B,{self._cfg['spatial_channels']},H,W], got {tuple(maps.shape)}")
+        B, _, H, W = maps.shape
+        if min(H, W) < 16:
+            raise RuntimeError("tile edge must be >= 16 (four 2x2 poolings)")
+        T = int(temp_series.shape[1]) if temp_series.dim() == 2 else 0
+        plan = self._plan_for(B, H, W, T, self.training, maps.device)
+        maps = maps.contiguous().float()
+        temp_series = temp_series.contiguous().float()
+        metadata = metadata.contiguous().float()
+        uses_meta = plan.uses_metadata
+        if uses_meta and (metadata.dim() != 2 or metadata.shape[1] != self._cfg["meta_features"]):
+            raise RuntimeError(f"metadata must be [B,{self._cfg['meta_features']}], got {tuple(metadata.shape)}")
+        state = self._state_tensors()
+        need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in state)
+        if not need_grad:
+            return self._finish(plan.forward(state, maps, temp_series, metadata))
+        if not self.training:
+            raise RuntimeError("mau_b200: backward through an eval()-mode forward is not supported; "
+                               "call model.train() or wrap inference in torch.no_grad()")
+        used = plan.used_state_indices()
+        diff = [i for i in used if state[i].requires_grad]
+        out = engine.HotPathFn.apply(plan, state, diff, maps, temp_series, metadata,
+                                     *[state[i] for i in diff])
+        return self._finish(out)
+
+    def _finish(self, out):
+        if self._cfg.get("deep_supervision"):
+            return [out[i] for i in range(out.shape[0])]
+        return out
+
+
+class UrbanPredictor_unet(_EngineNet):
+    """State layout of reference ``UrbanPredictor_unet`` (src/model.py:195-241)."""
+
+    def __init__(self, spatial_channels, seq_len, temporal_dim, meta_features, meta_dim, lstm_dim,
+                 out_channels, nb_filter=None, temporal_embeddings=True, metadata_embeddings=True):
+        super().__init__()
+        if _log is not None:
+            _log.info(f"UrbanPredictor_unet[b200] temporal_embeddings={temporal_embeddings}, "
+                      f"metadata_embeddings={metadata_embeddings}")
+        f = list(nb_filter) if nb_filter is not None else [32, 64, 128, 256, 512]
+        self.temporal_dim, self.meta_dim = temporal_dim, meta_dim
+        self.temporal_embeddings, self.metadata_embeddings = temporal_embeddings, metadata_embeddings
+        # registration order is the contract (optimizer state indexes parameters by it)
+        self.temporal_encoder = _SeriesParams(lstm_dim, temporal_dim)
+        self.meta_encoder = _MetaParams(meta_features, meta_dim)
+        self.conv0_0 = _ConvPair(spatial_channels, f[0], f[0])
+        self.conv1_0 = _ConvPair(f[0], f[1], f[1])
+        self.conv2_0 = _ConvPair(f[1], f[2], f[2])
+        self.conv3_0 = _ConvPair(f[2], f[3], f[3])
+        fused = f[3] + (temporal_dim if temporal_embeddings else 0) + (meta_dim if metadata_embeddings else 0)
+        self.conv4_0 = _ConvPair(fused, f[4], f[4])
+        self.conv3_1 = _ConvPair(f[3] + f[4], f[3], f[3])
+        self.conv2_1 = _ConvPair(f[2] + f[3], f[2], f[2])
+        self.conv1_1 = _ConvPair(f[1] + f[2], f[1], f[1])
+        self.conv0_1 = _ConvPair(f[0] + f[1], f[0], f[0])
+        self.final = nn.Conv2d(f[0], out_channels, kernel_size=1)
+        object.__setattr__(self, "_cfg", dict(
+            model_type=engine.MODEL_UNET, spatial_channels=spatial_channels, temporal_dim=temporal_dim,
+            meta_features=meta_features, meta_dim=meta_dim, lstm_dim=lstm_dim, out_channels=out_channels,
+            filters=f, temporal_embeddings=int(bool(temporal_embeddings)),
+            metadata_embeddings=int(bool(metadata_embeddings)), deep_supervision=0))
+        self._init_engine_state()
+
+    def _engine_config(self):
+        return self._cfg
+
+
+class UrbanPredictor_unetpp(_EngineNet):
+    """State layout of reference ``UrbanPredictor_unetpp`` (src/model.py:51-96).  Unknown
+    keyword arguments are swallowed like the reference does (src/model.py:52-53), so both
+    embeddings are always on."""
+
+    def __init__(self, spatial_channels, seq_len, temporal_dim, meta_features, meta_dim, lstm_dim,
+                 out_channels, base_filters=32, deep_supervision=False, **kwargs):
+        super().__init__()
+        f = [base_filters * m for m in (1, 2, 4, 8, 16)]
+        e = temporal_dim + meta_dim
+        self.deep_supervision = deep_supervision
+        self.embed_dim = e
+        for lvl in range(5):                                   # encoders conv0_0 .. conv4_0
+            cin = spatial_channels if lvl == 0 else f[lvl - 1]
+            setattr(self, f"conv{lvl}_0", _ConvPair(cin, f[lvl], f[lvl]))
+        for depth in (1, 2, 3, 4):                             # conv0_1..conv3_1, conv0_2.., conv0_4
+            for lvl in range(0, 5 - depth):
+                setattr(self, f"conv{lvl}_{depth}", _ConvPair(f[lvl] * depth + f[lvl + 1] + e, f[lvl], f[lvl]))
+        self.temporal_encoder = _SeriesParams(lstm_dim, temporal_dim)
+        self.meta_encoder = _MetaParams(meta_features, meta_dim)
+        if deep_supervision:
+            for i in (1, 2, 3, 4):
+                setattr(self, f"final{i}", nn.Conv2d(f[0], out_channels, kernel_size=1))
+        else:
+            self.final = nn.Conv2d(f[0], out_channels, kernel_size=1)
+        object.__setattr__(self, "_cfg", dict(
+            model_type=engine.MODEL_UNETPP, spatial_channels=spatial_channels, temporal_dim=temporal_dim,
+            meta_features=meta_features, meta_dim=meta_dim, lstm_dim=lstm_dim, out_channels=out_channels,
+            filters=f, temporal_embeddings=1, metadata_embeddings=1,
+            deep_supervision=int(bool(deep_supervision))))
+        self._init_engine_state()
+
+    def _engine_config(self):
+        return self._cfg
+
+
+class UrbanPredictor(nn.Module):
+    """Same constructor / forward / state_dict surface as reference ``UrbanPredictor``
+    (src/model.py:295-329).  ``model_type`` in {'unet', 'unet++'}; anything else raises
+    ``ValueError`` (src/model.py:326)."""
+
+    def __init__(self, model_type, spatial_channels, seq_len, temporal_dim, meta_features, meta_dim,
+                 lstm_dim, out_channels, base_filters=64, deep_supervision=False, **kwargs):
+        super().__init__()
+        common = dict(spatial_channels=spatial_channels, seq_len=seq_len, temporal_dim=temporal_dim,
+                      meta_features=meta_features, meta_dim=meta_dim, lstm_dim=lstm_dim,
+                      out_channels=out_channels)
+        if model_type == "unet++":
+            self.model = UrbanPredictor_unetpp(base_filters=base_filters,
+                                               deep_supervision=deep_supervision, **common, **kwargs)
+        elif model_type == "unet":
+            self.model = UrbanPredictor_unet(nb_filter=[base_filters * m for m in (1, 2, 4, 8, 16)],
+                                             **common, **kwargs)
+        else:
+            raise ValueError(f"Unsupported model_type: {model_type}")
+
+    def forward(self, maps, temp_series, metadata):
+        return self.model(maps, temp_series, metadata)
+
+    # convenience (not part of the reference surface)
+    def set_precision(self, precision: str):
+        """'bf16' (tcgen05 tensor-core path, default) or 'fp32' (FFMA path, 1e-5 parity mode)."""
+        if precision not in engine.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(engine.PRECISIONS)}")
+        self.model.precision = precision
+        return self

@@ -1,0 +1,106 @@
+"""CPU: the oracle restatement (oracle/unet_oracle.py) against the golden vectors written
+by the real reference (oracle/gen_golden.py) -- this is what pins the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mau_b200
+from oracle import unet_oracle as O
+
+VARIANTS = {
+    "unet_noemb": ("unet", 828, dict(temporal_embeddings=False, metadata_embeddings=False)),
+    "unet_metaemb": ("unet", 828, dict(temporal_embeddings=False, metadata_embeddings=True)),
+    "unet_emb": ("unet", 60, dict(temporal_embeddings=True, metadata_embeddings=True)),
+    "unetpp_emb": ("unet++", 60, dict()),
+}
+
+
+def _small(name):
+    mt, _, kw = VARIANTS[name]
+    torch.manual_seed(123)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 23, 37, 45, generator=g)
+    ts = torch.randn(3, 40, generator=g)
+    md = torch.randn(3, 8, generator=g)
+    return mt, kw, m, x, ts, md
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_oracle_small_eval_matches_reference(name, golden_dir):
+    mt, kw, m, x, ts, md = _small(name)
+    want = np.load(os.path.join(golden_dir, f"small_{name}.npz"))["y_eval"]
+    got = O.forward(m.state_dict(), mt, x, ts, md, training=False, **kw).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6)
+
+
+def test_oracle_deep_supervision(golden_dir):
+    torch.manual_seed(123)
+    m = mau_b200.UrbanPredictor("unet++", 23, 828, 16, 8, 8, 32, 2, base_filters=8, deep_supervision=True)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 23, 37, 45, generator=g); ts = torch.randn(3, 40, generator=g); md = torch.randn(3, 8, generator=g)
+    want = np.load(os.path.join(golden_dir, "small_unetpp_ds.npz"))["y_eval"]
+    got = O.forward(m.state_dict(), "unet++", x, ts, md, deep_supervision=True)
+    np.testing.assert_allclose(np.stack([t.numpy() for t in got]), want, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["unet_metaemb", "unetpp_emb"])
+def test_oracle_full_width_kat(name, golden_dir):
+    """Full 64-filter model at 50x50 (two-stage 12->24->25 resize), eval + one train step."""
+    mt, T, kw = VARIANTS[name]
+    kat = np.load(os.path.join(golden_dir, f"kat_{name}.npz"))
+    torch.manual_seed(42)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 64, 8, 64, 96, 2, **kw)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 23, 50, 50, generator=g); ts = torch.randn(2, T, generator=g); md = torch.randn(2, 8, generator=g)
+    sd = m.state_dict()
+    y = O.forward(sd, mt, x, ts, md, training=False, **kw).numpy()
+    np.testing.assert_allclose(y, kat["y_eval"], rtol=1e-4, atol=1e-5)
+    out, loss, grads, new_stats = O.train_step_grads(sd, mt, x, ts, md, None, loss="abs_mean", **kw)
+    np.testing.assert_allclose(out.numpy(), kat["y_train"], rtol=1e-4, atol=1e-5)
+    assert abs(float(loss) - float(kat["loss"])) < 1e-5
+    np.testing.assert_allclose(new_stats["model.conv0_0.bn1.running_mean"].numpy(), kat["bn_rm"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(new_stats["model.conv0_0.bn1.running_var"].numpy(), kat["bn_rv"], rtol=1e-4, atol=1e-6)
+    assert int(new_stats["model.conv0_0.bn1.num_batches_tracked"]) == int(kat["bn_count"]) == 1
+    want_norms = json.loads(str(kat["grad_norms"]))
+    for k, wn in want_norms.items():
+        if wn is None:
+            assert grads[k] is None, k          # flag-disabled encoders: grad stays None
+        else:
+            assert abs(float(grads[k].norm()) - wn) <= 1e-3 * max(wn, 1e-3) + 1e-6, k
+    for k in kat.files:
+        if k.startswith("g::"):
+            np.testing.assert_allclose(grads[k[3:]].numpy(), kat[k], rtol=2e-3, atol=2e-5)
+
+
+def test_oracle_loss_terms(golden_dir):
+    z = np.load(os.path.join(golden_dir, "loss_terms.npz"))
+    pred = torch.tensor(z["pred"], requires_grad=True)
+    tgt = torch.tensor(z["tgt"])
+    d = O.loss_l1_gradient(pred, tgt, 0.1)
+    assert abs(float(d["pixel"]) - float(z["l1"])) < 1e-6
+    assert abs(float(d["gradient"]) - float(z["grad"])) < 1e-6
+    (g,) = torch.autograd.grad(d["total"], pred)
+    np.testing.assert_allclose(g.numpy(), z["dpred_l1"], rtol=1e-5, atol=1e-8)
+    d2 = O.loss_mse_gradient(pred, tgt, 0.1)
+    assert abs(float(d2["total"]) - float(z["total_mse"])) < 1e-6
+
+
+def test_oracle_dw_map_known_answers():
+    """test/evaluate.py:212-217: channel 0 is multiplied by 0, so class 0 wins only when all
+    of channels 1..8 are <= 0; ties resolve to the lowest index."""
+    x = np.zeros((1, 23, 2, 3), np.float32)
+    x[0, 0, 0, 0] = 1.0                  # class 0 one-hot -> all products 0 -> argmax 0
+    x[0, 5, 0, 1] = 1.0                  # class 5
+    x[0, 3, 0, 2] = 1.0; x[0, 6, 0, 2] = 0.5   # 3*1 == 6*0.5 -> tie -> lowest index 3
+    x[0, 8, 1, 0] = 1.0; x[0, 2, 1, 0] = 1.0   # 8 beats 2
+    x[0, 4, 1, 1] = -1.0                 # negative product loses to zeros -> 0
+    dw, rows = O.eval_metrics(x, np.zeros((1, 2, 2, 3), np.float32), np.ones((1, 2, 2, 3), np.float32))
+    assert dw.dtype == np.int64
+    assert dw[0].tolist() == [[0, 5, 3], [8, 0, 0]]
+    overall = [r for r in rows if r[2] == -1]
+    assert all(abs(r[4] - 1.0) < 1e-7 and abs(r[5] - 1.0) < 1e-7 for r in overall)
+    assert sorted({r[2] for r in rows}) == [-1, 0, 3, 5, 8]
