@@ -58,6 +58,8 @@ typedef struct mau_config {
                                      test/metadata_sensitivity.py:294-311): encoder computed once */
 #define MAU_FLAG_CONV_TAPLOAD  2  /* debug: force the 9-box-loads-per-chunk conv main loop        */
 #define MAU_FLAG_CONV_FFMA     4  /* debug: run bf16 plans on the FFMA convolution kernels         */
+#define MAU_FLAG_HALO_BASEOFF  256 /* debug: halo main loop fills the UMMA descriptor base_offset   */
+#define MAU_FLAG_CONV_HALO     512 /* single-halo-box conv main loop (1 A load per 64-channel chunk) */
 
 typedef struct mau_plan mau_plan; /* opaque */
 

@@ -1,0 +1,234 @@
+// api.cu -- the extern "C" surface declared in include/mau_b200.h
+#include <cstring>
+#include <new>
+#include "plan.h"
+
+using namespace mau;
+
+struct mau_plan {
+  Plan impl;
+};
+
+extern "C" {
+
+const char* mau_last_error(void) { return last_error().c_str(); }
+int mau_version(void) { return 100; }
+int64_t mau_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int mau_plan_create(const mau_config* cfg, mau_plan** out) {
+  if (!cfg || !out) return fail("mau_plan_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available: this library has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d devices)", cfg->device, ndev);
+  MAU_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  MAU_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail("sm_100a kernels only: device %d is sm_%d%d", cfg->device, prop.major, prop.minor);
+  mau_plan* p = new (std::nothrow) mau_plan();
+  if (!p) return fail("out of host memory");
+  p->impl.cfg = *cfg;
+  int rc = p->impl.build();
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return 0;
+}
+
+int mau_plan_destroy(mau_plan* plan) {
+  delete plan;
+  return 0;
+}
+
+size_t mau_plan_workspace_bytes(const mau_plan* plan) { return plan ? plan->impl.ws_bytes : 0; }
+int mau_plan_num_state(const mau_plan* plan) { return plan ? (int)plan->impl.state.size() : 0; }
+
+int mau_plan_state_info(const mau_plan* plan, int i, int64_t* numel, int* role) {
+  if (!plan || i < 0 || i >= (int)plan->impl.state.size()) return fail("state index out of range");
+  if (numel) *numel = plan->impl.state[i].numel;
+  if (role) *role = plan->impl.state[i].role;
+  return 0;
+}
+
+int mau_plan_describe_config(const mau_config* cfg, char* buf, size_t buflen) {
+  if (!cfg || !buf) return fail("null argument");
+  Plan p;
+  p.cfg = *cfg;
+  p.dry = true;
+  int rc = p.build();
+  if (rc) return rc;
+  if (p.describe_json.size() + 1 > buflen) return fail("describe buffer too small (%zu needed)", p.describe_json.size() + 1);
+  memcpy(buf, p.describe_json.c_str(), p.describe_json.size() + 1);
+  return 0;
+}
+
+int mau_plan_flops(const mau_plan* plan, double* fwd_flops, double* bwd_flops) {
+  if (!plan) return fail("null plan");
+  if (fwd_flops) *fwd_flops = plan->impl.fwd_flops;
+  if (bwd_flops) *bwd_flops = plan->impl.bwd_flops;
+  return 0;
+}
+
+int mau_plan_forward(mau_plan* plan, void* const* state_dev, const float* maps_dev, const float* temp_series_dev,
+                     const float* metadata_dev, float* out_dev, void* stream) {
+  if (!plan || !state_dev || !maps_dev || !out_dev) return fail("mau_plan_forward: null argument");
+  Ctx c;
+  c.state = state_dev; c.maps = maps_dev; c.series = temp_series_dev; c.md = metadata_dev; c.out = out_dev;
+  c.st = static_cast<cudaStream_t>(stream);
+  plan->impl.last_state.assign(state_dev, state_dev + plan->impl.state.size());
+  plan->impl.last_series = temp_series_dev; plan->impl.last_md = metadata_dev;
+  return plan->impl.run_forward(c);
+}
+
+int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* grads_dev, void* stream) {
+  if (!plan || !grad_out_dev || !grads_dev) return fail("mau_plan_backward: null argument");
+  Ctx c;
+  c.grads = grads_dev; c.gout = grad_out_dev; c.st = static_cast<cudaStream_t>(stream);
+  // parameters are read again in backward (dgrad weight pack, BN gamma): reuse the forward's pointers
+  c.state = plan->impl.last_state.data();
+  c.series = plan->impl.last_series; c.md = plan->impl.last_md;
+  return plan->impl.run_backward(c);
+}
+
+int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user) {
+  if (!plan) return fail("null plan");
+  plan->impl.hook = fn; plan->impl.hook_user = user;
+  return 0;
+}
+
+int mau_plan_profile(mau_plan* plan, int enable) {
+  if (!plan) return fail("null plan");
+  plan->impl.profiling = enable != 0;
+  plan->impl.prof.clear();
+  return 0;
+}
+
+int mau_plan_profile_read(mau_plan* plan, char* names, size_t names_len, float* ms, int max_n, int* n) {
+  if (!plan || !names || !ms || !n) return fail("null argument");
+  std::string s;
+  int k = 0;
+  for (auto& e : plan->impl.prof) {
+    if (k >= max_n || s.size() + e.first.size() + 2 > names_len) break;
+    s += e.first; s += "\n";
+    ms[k++] = e.second;
+  }
+  memcpy(names, s.c_str(), s.size() + 1);
+  *n = k;
+  return 0;
+}
+
+int mau_loss_forward_backward(int kind, const float* pred_dev, const float* target_dev, int B, int C, int H, int W,
+                              float lambda_grad, float* losses_dev, float* grad_dev, void* stream) {
+  if (!pred_dev || !target_dev || !losses_dev) return fail("loss: null argument");
+  return op_loss(kind, pred_dev, target_dev, B, C, H, W, lambda_grad, losses_dev, grad_dev,
+                 static_cast<cudaStream_t>(stream));
+}
+
+int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred_dev, const float* target_dev, int B,
+                     int C, int H, int W, float temp_mean, float temp_std, int64_t* dw_map_dev, double* sums_dev,
+                     void* stream) {
+  if (!maps_dev || !pred_dev || !target_dev || !dw_map_dev || !sums_dev) return fail("eval_metrics: null argument");
+  return op_eval_metrics(maps_dev, maps_channels, pred_dev, target_dev, B, C, H, W, temp_mean, temp_std,
+                         reinterpret_cast<long long*>(dw_map_dev), sums_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------- single operators (parity tests)
+static View mkview(const void* p, int B, int H, int W, int C, int cs) {
+  View v; v.ptr = const_cast<void*>(p); v.B = B; v.H = H; v.W = W; v.C = C; v.cs = cs; v.c0 = 0;
+  return v;
+}
+
+int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
+                   const float* w_oihw_dev, const float* scale_dev, const float* shift_dev, int relu, int Cout,
+                   void* y_dev, int Cout_stride, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Kp = round_up(Cin, 64);
+  std::vector<int> kmap(Kp);
+  for (int i = 0; i < Kp; ++i) kmap[i] = i < Cin ? i : -1;
+  int* kmap_dev = nullptr; void* wp = nullptr;
+  MAU_CUDA(cudaMalloc(&kmap_dev, sizeof(int) * Kp));
+  MAU_CUDA(cudaMemcpy(kmap_dev, kmap.data(), sizeof(int) * Kp, cudaMemcpyHostToDevice));
+  const View x = mkview(x_dev, B, H, W, Cin, Cin_stride), y = mkview(y_dev, B, H, W, Cout, Cout_stride);
+  const int zero = 0;
+  int rc = 0;
+  if (impl == 2) {
+    MAU_CUDA(cudaMalloc(&wp, sizeof(float) * 9 * Kp * Cout));
+    ConvFfmaParams p;
+    rc = conv_ffma_pack_fwd(w_oihw_dev, Cout, Cin, kmap_dev, Kp, static_cast<float*>(wp), st);
+    if (!rc) rc = conv_ffma_prepare(&p, x, 1, &zero, &Cin, static_cast<float*>(wp), Kp, Cout, y, scale_dev, shift_dev, relu, 0);
+    if (!rc) rc = conv_ffma_launch(dtype, p, B, st);
+  } else {
+    if (dtype != DT_BF16) { rc = fail("tcgen05 convolution is bf16 only"); }
+    else {
+      MAU_CUDA(cudaMalloc(&wp, (size_t)2 * 9 * Kp * Cout));
+      ConvTcOp op;
+      const int mode = (impl & 3) == 0 ? MODE_ROW3 : ((impl & 3) == 1 ? MODE_TAP : MODE_HALO);
+      rc = conv_tc_pack_fwd(w_oihw_dev, Cout, Cin, kmap_dev, Kp, wp, st);
+      if (!rc) rc = conv_tc_prepare(&op, x, 1, &zero, &Cin, wp, Kp, Cout, y, mode, scale_dev, shift_dev, relu, 0, (impl >> 2) & 1);
+      if (!rc) rc = conv_tc_launch(op, st);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(kmap_dev); cudaFree(wp);
+  if (!rc && e != cudaSuccess) rc = fail("conv3x3 execution failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_dev, int B, int H, int W, int Cin,
+                         int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const View x = mkview(x_dev, B, H, W, Cin, Cin_stride), dy = mkview(dy_dev, B, H, W, Cout, Cout_stride);
+  MAU_CUDA(cudaMemsetAsync(dw_oihw_dev, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
+  if (impl == 2) return wgrad_ffma_launch(dtype, x, dy, 0, Cin, dw_oihw_dev, 1, st);
+  if (dtype != DT_BF16) return fail("tcgen05 wgrad is bf16 only");
+  WgradTcOp op;
+  MAU_TRY(wgrad_tc_prepare(&op, x, dy, 0, Cin));
+  return wgrad_tc_launch(op, dw_oihw_dev, st);
+}
+
+int mau_op_maxpool2x2(int dtype, const void* x_dev, int B, int H, int W, int C, void* y_dev, void* stream) {
+  return op_maxpool(dtype, mkview(x_dev, B, H, W, C, C), mkview(y_dev, B, H / 2, W / 2, C, C),
+                    static_cast<cudaStream_t>(stream));
+}
+
+int mau_op_bilinear(int dtype, const void* x_dev, int B, int Hin, int Win, int C, int Hout, int Wout, void* y_dev,
+                    void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BilinearHost hy, hx;
+  bilinear_axis_tables(Hin, Hout, &hy);
+  bilinear_axis_tables(Win, Wout, &hx);
+  BilinearTables t;
+  t.Hin = Hin; t.Win = Win; t.Hout = Hout; t.Wout = Wout;
+  std::vector<void*> tmp;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(bytes, 4)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    tmp.push_back(d);
+    return d;
+  };
+  t.y0 = (int*)up(hy.i0.data(), 4 * hy.i0.size()); t.y1 = (int*)up(hy.i1.data(), 4 * hy.i1.size());
+  t.ly = (float*)up(hy.l.data(), 4 * hy.l.size());
+  t.x0 = (int*)up(hx.i0.data(), 4 * hx.i0.size()); t.x1 = (int*)up(hx.i1.data(), 4 * hx.i1.size());
+  t.lx = (float*)up(hx.l.data(), 4 * hx.l.size());
+  int rc = op_bilinear(dtype, mkview(x_dev, B, Hin, Win, C, C), mkview(y_dev, B, Hout, Wout, C, C), t, st);
+  cudaStreamSynchronize(st);
+  for (void* p : tmp) cudaFree(p);
+  return rc;
+}
+
+int mau_op_nchw_to_nhwc(int dtype, const float* x_dev, int B, int C, int H, int W, int Cstride, void* y_dev,
+                        void* stream) {
+  return op_nchw_to_nhwc(dtype, x_dev, B, C, H, W, mkview(y_dev, B, H, W, C, Cstride), static_cast<cudaStream_t>(stream));
+}
+int mau_op_nhwc_to_nchw(int dtype, const void* x_dev, int B, int C, int H, int W, int Cstride, float* y_dev,
+                        void* stream) {
+  return op_nhwc_to_nchw(dtype, mkview(x_dev, B, H, W, C, Cstride), y_dev, static_cast<cudaStream_t>(stream));
+}
+int mau_op_lstm_last_hidden(const float* series_dev, int B, int T, int hidden, const float* w_ih, const float* w_hh,
+                            const float* b_ih, const float* b_hh, float* h_out_dev, void* stream) {
+  return op_lstm_fwd(series_dev, B, T, hidden, w_ih, w_hh, b_ih, b_hh, h_out_dev, nullptr,
+                     static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

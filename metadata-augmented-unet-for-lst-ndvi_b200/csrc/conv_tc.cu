@@ -1,0 +1,385 @@
+// conv_tc.cu -- 3x3 / pad 1 / stride 1 convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+// Replaces: nn.Conv2d(cin, cout, 3, padding=1) forward (reference src/model.py:12,14) and, with a
+// transposed + spatially flipped weight pack, its data gradient (the autograd of the same lines).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + d(tap), cin] * W[cout, cin, tap]
+//   GEMM view: M = 128 output pixels (a TH x TW spatial box of one image), N = BN output channels,
+//              K = 9 taps x Cin, consumed in chunks of 64 channels of one tap.
+//
+// Data movement: activations are NHWC bf16.  A-operand tiles are fetched by TMA as *shifted boxes*
+// of the 4-D tensor {C, W, H, B}; out-of-image coordinates are zero-filled by the TMA unit, which is
+// the convolution's zero padding, and partial tiles at the right/bottom edge are clipped by the TMA
+// store.  Three main-loop variants trade L2->SMEM traffic for descriptor tricks:
+//   MODE_TAP  : one {64, TW, TH} box per tap                (9 A loads per 64-channel chunk)
+//   MODE_ROW3 : three {64, 8, TH+2} boxes (one per horizontal shift); the three vertical taps are
+//               1024-byte-aligned sub-windows of a box     (3 A loads per chunk)
+//   MODE_HALO : one {64, 10, TH+2} halo box; all nine taps are sub-windows addressed through the
+//               UMMA descriptor (start offset + 1280-byte group stride)   (1 A load per chunk)
+// B-operand tiles ({64 k, BN cout} of one tap) come from a packed bf16 weight tensor [9][Cout][Kp].
+// Accumulation is fp32 in TMEM (tcgen05.mma kind::f16); the epilogue applies a per-channel affine
+// (+ReLU) -- folded eval-mode BatchNorm, or the plain bias in training -- converts to bf16 and
+// leaves through a swizzled SMEM staging tile and a TMA store (or TMA reduce-add for gradients
+// that accumulate into a concat buffer).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+#include "conv_tc.h"
+#include "ptx.cuh"
+#include "tma.h"
+
+namespace mau {
+using namespace ptx;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int MODE> struct ATile;
+template <> struct ATile<MODE_TAP>  { static constexpr int kStage = 16384; static constexpr int kTx = 16384; };
+template <> struct ATile<MODE_ROW3> { static constexpr int kStage = 3 * 18432; static constexpr int kTx = 3 * 18432; };
+template <> struct ATile<MODE_HALO> { static constexpr int kStage = 23552; static constexpr int kTx = 23040; };
+
+struct Ring {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) { stage = 0; phase ^= 1; }
+  }
+};
+
+template <int BN, int MODE, int NA, int NB>
+__global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmY,
+                                                              const ConvTcParams p) {
+  constexpr int A_STAGE = ATile<MODE>::kStage;
+  constexpr int B_STAGE = BN * 128;
+  static_assert((BN / 64) * 16384 <= NA * A_STAGE + NB * B_STAGE, "epilogue staging does not fit");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NA * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NB * B_STAGE);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + NA;
+  uint64_t* fullB = bars + 2 * NA;
+  uint64_t* emptyB = bars + 2 * NA + NB;
+  uint64_t* tmem_full = bars + 2 * NA + 2 * NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_shift = s_scale + BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int b = blockIdx.x / tiles_per_img;
+  const int trem = blockIdx.x - b * tiles_per_img;
+  const int th = trem / p.tiles_w;
+  const int h0 = th * p.TH;
+  const int w0 = (trem - th * p.tiles_w) * p.TW;
+  const int n0 = blockIdx.y * BN;
+
+  // ---- one-time setup
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    prefetch_tensormap(&tmY);
+    for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int total_chunks = 0;
+  for (int s = 0; s < p.nseg; ++s) total_chunks += p.seg_chunks[s];
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      Ring ra, rb;
+      int kB = 0;  // packed K offset (elements)
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        for (int kc = 0; kc < p.seg_chunks[sg]; ++kc, kB += 64) {
+          const int cA = p.seg_start[sg] + kc * 64;
+          if (MODE == MODE_ROW3) {
+            mbar_wait(&emptyA[ra.stage], ra.phase ^ 1);
+            mbar_expect_tx(&fullA[ra.stage], ATile<MODE>::kTx);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+              tma_load_4d(sA + ra.stage * A_STAGE + s * 18432, &tmA, &fullA[ra.stage], cA, w0 + s - 1, h0 - 1, b);
+            ra.advance(NA);
+          } else if (MODE == MODE_HALO) {
+            mbar_wait(&emptyA[ra.stage], ra.phase ^ 1);
+            mbar_expect_tx(&fullA[ra.stage], ATile<MODE>::kTx);
+            tma_load_4d(sA + ra.stage * A_STAGE, &tmA, &fullA[ra.stage], cA, w0 - 1, h0 - 1, b);
+            ra.advance(NA);
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            if (MODE == MODE_TAP) {
+              const int r = tap / 3, s = tap - r * 3;
+              mbar_wait(&emptyA[ra.stage], ra.phase ^ 1);
+              mbar_expect_tx(&fullA[ra.stage], ATile<MODE>::kTx);
+              tma_load_4d(sA + ra.stage * A_STAGE, &tmA, &fullA[ra.stage], cA, w0 + s - 1, h0 + r - 1, b);
+              ra.advance(NA);
+            }
+            mbar_wait(&emptyB[rb.stage], rb.phase ^ 1);
+            mbar_expect_tx(&fullB[rb.stage], B_STAGE);
+            tma_load_3d(sB + rb.stage * B_STAGE, &tmB, &fullB[rb.stage], kB, n0, tap);
+            rb.advance(NB);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 0, 0);
+      Ring ra, rb;
+      uint32_t acc = 0;
+      for (int chunk = 0; chunk < total_chunks; ++chunk) {
+        if (MODE != MODE_TAP) {
+          mbar_wait(&fullA[ra.stage], ra.phase);
+        }
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, s = tap - r * 3;
+          if (MODE == MODE_TAP) mbar_wait(&fullA[ra.stage], ra.phase);
+          mbar_wait(&fullB[rb.stage], rb.phase);
+          tc_fence_after();
+          uint32_t a_addr = smem_u32(sA + ra.stage * A_STAGE);
+          uint32_t sbo = 1024;
+          if (MODE == MODE_ROW3) a_addr += s * 18432 + r * 1024;
+          if (MODE == MODE_HALO) { a_addr += (r * 10 + s) * 128; sbo = 1280; }
+          const uint32_t b_addr = smem_u32(sB + rb.stage * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t aa = a_addr + k * 32;
+            const uint32_t bo = (MODE == MODE_HALO && p.halo_base_offset) ? ((aa >> 7) & 7) : 0;
+            const uint64_t da = smem_desc_sw128(aa, 16, sbo, bo);
+            const uint64_t db = smem_desc_sw128(b_addr + k * 32, 16, 1024, 0);
+            umma_bf16(tmem_base, da, db, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(&emptyB[rb.stage]);
+          rb.advance(NB);
+          if (MODE == MODE_TAP) {
+            umma_commit(&emptyA[ra.stage]);
+            ra.advance(NA);
+          }
+        }
+        if (MODE != MODE_TAP) {
+          umma_commit(&emptyA[ra.stage]);
+          ra.advance(NA);
+        }
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int et = threadIdx.x - 128;  // 0..127
+    for (int i = et; i < BN; i += 128) {
+      const int c = n0 + i;
+      const bool ok = c < p.Cout;
+      s_scale[i] = ok ? (p.scale ? p.scale[c] : 1.f) : 0.f;
+      s_shift[i] = ok ? (p.shift ? p.shift[c] : 0.f) : 0.f;
+    }
+    named_bar_sync(1, 128);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // accumulator row == TMEM lane == pixel index inside the tile
+    uint8_t* stg = smem;          // pipeline buffers are idle now: reuse as the store staging tile
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = cb * 32 + 2 * j;
+        float y0 = __uint_as_float(v[2 * j]) * s_scale[c] + s_shift[c];
+        float y1 = __uint_as_float(v[2 * j + 1]) * s_scale[c + 1] + s_shift[c + 1];
+        if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      uint8_t* rowp = stg + (cb >> 1) * 16384 + m * 128;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int chunk16 = (cb & 1) * 4 + jj;
+        uint4 val = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+        *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (m & 7)) << 4)) = val;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (et == 0) {
+#pragma unroll 1
+      for (int g = 0; g < BN / 64; ++g) {
+        if (n0 + g * 64 < p.Cout) {
+          if (p.accumulate) tma_reduce_add_4d(&tmY, stg + g * 16384, n0 + g * 64, w0, h0, b);
+          else              tma_store_4d(&tmY, stg + g * 16384, n0 + g * 64, w0, h0, b);
+        }
+      }
+      tma_commit_group();
+      tma_wait_group0();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 -> [9][N][Kp] bf16
+// fwd : out[t][n][kp] = W[n][kmap[kp]][t]            (kmap = -1 -> 0)
+// dgrad: out[t][n][kp] = W[kp][ci0 + n][8 - t]       (kp >= Cout -> 0)
+__global__ void pack_w_fwd_kernel(const float* __restrict__ w, int Cout, int Cin, const int* __restrict__ kmap,
+                                  int Kp, __nv_bfloat16* __restrict__ out) {
+  const long long total = 9LL * Cout * Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(i % Kp);
+    const long long r = i / Kp;
+    const int n = (int)(r % Cout);
+    const int t = (int)(r / Cout);
+    const int ci = kmap[kp];
+    const float v = ci >= 0 ? w[((long long)n * Cin + ci) * 9 + t] : 0.f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int ci0, int N, int Kp,
+                                    __nv_bfloat16* __restrict__ out) {
+  const long long total = 9LL * N * Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(i % Kp);
+    const long long r = i / Kp;
+    const int n = (int)(r % N);
+    const int t = (int)(r / N);
+    const float v = kp < Cout ? w[((long long)kp * Cin + (ci0 + n)) * 9 + (8 - t)] : 0.f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int BN, int MODE, int NA, int NB>
+int launch_inst(const ConvTcOp& op, cudaStream_t st) {
+  constexpr size_t smem = 1024 + NA * ATile<MODE>::kStage + NB * BN * 128 + 8 * (2 * NA + 2 * NB + 1) + 16 +
+                          2 * BN * sizeof(float);
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = conv3x3_tc_kernel<BN, MODE, NA, NB>;
+  if (!attr_done[dev & 15]) {
+    MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 15] = true;
+  }
+  kern<<<op.grid, kThreads, smem, st>>>(op.tmA, op.tmB, op.tmY, op.p);
+  MAU_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+int conv_tc_pick_bn(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
+
+int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
+                    const void* wpacked, int Kp, int n_rows, const View& y, int mode, const float* scale,
+                    const float* shift, int relu, int accumulate, int halo_base_offset) {
+  if (nseg < 1 || nseg > 4) return fail("conv_tc: 1..4 input segments supported, got %d", nseg);
+  if (xbuf.cs % 8 || y.cs % 8 || y.c0 % 8 || Kp % 64)
+    return fail("conv_tc: channel strides/offsets must be multiples of 8 (cs=%d, ycs=%d, yc0=%d, Kp=%d)", xbuf.cs,
+                y.cs, y.c0, Kp);
+  if (xbuf.B != y.B || xbuf.H != y.H || xbuf.W != y.W) return fail("conv_tc: input/output geometry mismatch");
+  ConvTcParams& p = op->p;
+  p = ConvTcParams();
+  op->mode = mode;
+  op->bn = conv_tc_pick_bn(y.C);
+  p.TW = (mode == MODE_TAP) ? 16 : 8;
+  p.TH = 128 / p.TW;
+  p.tiles_w = ceil_div(y.W, p.TW);
+  p.tiles_h = ceil_div(y.H, p.TH);
+  p.Cout = y.C;
+  p.nseg = nseg;
+  int chunks = 0;
+  for (int i = 0; i < nseg; ++i) {
+    if (seg_start[i] % 8) return fail("conv_tc: segment start %d not a multiple of 8", seg_start[i]);
+    p.seg_start[i] = seg_start[i];
+    p.seg_chunks[i] = ceil_div(seg_len[i], 64);
+    chunks += p.seg_chunks[i];
+  }
+  if (chunks * 64 != Kp) return fail("conv_tc: packed K %d does not match segments (%d chunks)", Kp, chunks);
+  p.relu = relu;
+  p.accumulate = accumulate;
+  p.halo_base_offset = halo_base_offset;
+  p.scale = scale;
+  p.shift = shift;
+  op->grid = dim3((unsigned)(y.B * p.tiles_w * p.tiles_h), (unsigned)ceil_div(y.C, op->bn), 1);
+  // A: whole input buffer {C, W, H, B}
+  View xa = xbuf;
+  int bw = p.TW, bh = p.TH;
+  if (mode == MODE_ROW3) { bw = 8; bh = p.TH + 2; }
+  if (mode == MODE_HALO) { bw = 10; bh = p.TH + 2; }
+  MAU_TRY(make_nhwc_map(&op->tmA, DT_BF16, xa, 64, bw, bh));
+  // B: packed weights {Kp, n_rows, 9}
+  {
+    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)n_rows, 9};
+    uint64_t str[2] = {(uint64_t)Kp * 2, (uint64_t)Kp * 2 * (uint64_t)n_rows};
+    uint32_t box[3] = {64, (uint32_t)op->bn, 1};
+    MAU_TRY(make_tensor_map(&op->tmB, DT_BF16, 3, const_cast<void*>(wpacked), dims, str, box, true));
+  }
+  // Y: the output *view* {Cout, W, H, B} (channel clipping at the view end, not the buffer end)
+  MAU_TRY(make_nhwc_map(&op->tmY, DT_BF16, y, 64, p.TW, p.TH));
+  return 0;
+}
+
+int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
+#define MAU_INST(BN_, MODE_, NA_, NB_) \
+  if (op.bn == BN_ && op.mode == MODE_) return launch_inst<BN_, MODE_, NA_, NB_>(op, st);
+  MAU_INST(64, MODE_TAP, 4, 4)
+  MAU_INST(128, MODE_TAP, 3, 3)
+  MAU_INST(256, MODE_TAP, 4, 4)
+  MAU_INST(64, MODE_ROW3, 2, 6)
+  MAU_INST(128, MODE_ROW3, 2, 4)
+  MAU_INST(256, MODE_ROW3, 2, 3)
+  MAU_INST(64, MODE_HALO, 2, 6)
+  MAU_INST(128, MODE_HALO, 2, 4)
+  MAU_INST(256, MODE_HALO, 2, 4)
+#undef MAU_INST
+  return fail("conv_tc: no kernel instance for BN=%d mode=%d", op.bn, op.mode);
+}
+
+int conv_tc_pack_fwd(const float* w_oihw, int Cout, int Cin, const int* kmap_dev, int Kp, void* out,
+                     cudaStream_t st) {
+  const long long total = 9LL * Cout * Kp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_w_fwd_kernel<<<blocks, 256, 0, st>>>(w_oihw, Cout, Cin, kmap_dev, Kp, static_cast<__nv_bfloat16*>(out));
+  MAU_LAUNCHED();
+  return 0;
+}
+int conv_tc_pack_dgrad(const float* w_oihw, int Cout, int Cin, int ci0, int N, int Kp, void* out,
+                       cudaStream_t st) {
+  const long long total = 9LL * N * Kp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_w_dgrad_kernel<<<blocks, 256, 0, st>>>(w_oihw, Cout, Cin, ci0, N, Kp, static_cast<__nv_bfloat16*>(out));
+  MAU_LAUNCHED();
+  return 0;
+}
+
+}  // namespace mau

@@ -1,0 +1,60 @@
+// conv_tc.h -- host interface of the tcgen05 implicit-GEMM 3x3 convolution (conv_tc.cu) and the
+// tcgen05 weight-gradient kernel (wgrad_tc.cu)
+#pragma once
+#include <cuda.h>
+#include "common.h"
+
+namespace mau {
+
+enum ConvMode : int { MODE_TAP = 0, MODE_ROW3 = 1, MODE_HALO = 2 };
+
+struct ConvTcParams {
+  int tiles_w = 0, tiles_h = 0;  // spatial tiles per image
+  int TW = 16, TH = 8;           // tile = TH x TW = 128 output pixels
+  int Cout = 0;                  // valid output channels (N extent of the view)
+  int nseg = 0;                  // channel segments of the input buffer feeding K
+  int seg_start[4] = {0, 0, 0, 0};
+  int seg_chunks[4] = {0, 0, 0, 0};  // 64-channel chunks per segment
+  int relu = 0;
+  int accumulate = 0;            // TMA reduce-add instead of store
+  int halo_base_offset = 0;      // MODE_HALO: fill the descriptor base_offset field from the address
+  const float* scale = nullptr;  // per output channel (nullptr -> 1)
+  const float* shift = nullptr;  // per output channel (nullptr -> 0)
+};
+
+struct ConvTcOp {
+  CUtensorMap tmA, tmB, tmY;
+  ConvTcParams p;
+  dim3 grid;
+  int bn = 0;
+  int mode = 0;
+};
+
+int conv_tc_pick_bn(int Cout);
+// xbuf: the *whole* input buffer (c0 = 0, C = valid channels); segments select the K channels.
+// wpacked: bf16 [9][n_rows][Kp]; y: output view (its C is the GEMM N extent).
+int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
+                    const void* wpacked, int Kp, int n_rows, const View& y, int mode, const float* scale,
+                    const float* shift, int relu, int accumulate, int halo_base_offset);
+int conv_tc_launch(const ConvTcOp& op, cudaStream_t st);
+int conv_tc_pack_fwd(const float* w_oihw, int Cout, int Cin, const int* kmap_dev, int Kp, void* out,
+                     cudaStream_t st);
+int conv_tc_pack_dgrad(const float* w_oihw, int Cout, int Cin, int ci0, int N, int Kp, void* out,
+                       cudaStream_t st);
+
+// ---- weight gradient (wgrad_tc.cu): dW[co][ci][tap] = sum_pixels dY[p][co] * X[p + d(tap)][ci]
+struct WgradTcOp {
+  CUtensorMap tmDy, tmX;
+  int B = 0, H = 0, W = 0;
+  int Cout = 0, Cin = 0;         // extents of this launch (Cin = one input segment)
+  int ci_w0 = 0;                 // first weight input-channel index of this segment
+  int Cin_w = 0;                 // Cin of the full OIHW weight tensor
+  int m_tiles = 0, n_tiles = 0, splits = 0, tiles_per_split = 0;
+  int bn = 0;
+  dim3 grid;
+};
+int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0, int Cin_w);
+// accumulates into dw (fp32 OIHW, must be zeroed by the caller before the first segment)
+int wgrad_tc_launch(const WgradTcOp& op, float* dw_oihw, cudaStream_t st);
+
+}  // namespace mau

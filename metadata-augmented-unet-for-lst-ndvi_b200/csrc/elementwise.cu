@@ -1,0 +1,523 @@
+// elementwise.cu -- bandwidth-bound NHWC kernels: layout transposes, 2x2 max-pool (+backward),
+// bilinear align_corners resize (+backward), embedding broadcast / reduction, slice copies and the
+// 1x1 output head.  All of them move 8 channels (16 B bf16 / 32 B fp32) per thread access so that a
+// warp touches whole 128-byte lines; grids are sized in multiples of the SM count and grid-stride.
+#include "ops.h"
+#include "vec.cuh"
+
+namespace mau {
+namespace {
+
+constexpr int kSMs = 148;
+inline int grid_for(long long work_items, int threads = 256, int max_waves = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)kSMs * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+inline DView dv(const View& v) { return DView{v.ptr, v.B, v.H, v.W, v.cs, v.c0, v.C}; }
+
+template <typename T>
+__device__ __forceinline__ T* at(const DView& v, long long pix, int c) {
+  return static_cast<T*>(v.ptr) + pix * v.cs + v.c0 + c;
+}
+
+// ------------------------------------------------------------------ layout
+// x [B][C][P] fp32 -> y [B][P][cs] (T), P = H*W.  32x32 smem transpose tiles.
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int P, DView y) {
+  __shared__ float tile[32][33];
+  const int p_tiles = (P + 31) / 32, c_tiles = (C + 31) / 32;
+  const long long total = (long long)B * p_tiles * c_tiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = (int)(t % c_tiles);
+    const long long r = t / c_tiles;
+    const int pt = (int)(r % p_tiles);
+    const int b = (int)(r / p_tiles);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int c = ct * 32 + j, p = pt * 32 + tx;
+      tile[j][tx] = (c < C && p < P) ? x[((long long)b * C + c) * P + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int p = pt * 32 + j, c = ct * 32 + tx;
+      if (p < P && c < C) {
+        T* dst = at<T>(y, (long long)b * P + p, c);
+        if constexpr (sizeof(T) == 2) *dst = __float2bfloat16_rn(tile[tx][j]);
+        else *dst = tile[tx][j];
+      }
+    }
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(DView x, float* __restrict__ y, int P) {
+  __shared__ float tile[32][33];
+  const int C = x.C, B = x.B;
+  const int p_tiles = (P + 31) / 32, c_tiles = (C + 31) / 32;
+  const long long total = (long long)B * p_tiles * c_tiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = (int)(t % c_tiles);
+    const long long r = t / c_tiles;
+    const int pt = (int)(r % p_tiles);
+    const int b = (int)(r / p_tiles);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int p = pt * 32 + j, c = ct * 32 + tx;
+      float v = 0.f;
+      if (p < P && c < C) {
+        const T* src = at<T>(x, (long long)b * P + p, c);
+        if constexpr (sizeof(T) == 2) v = __bfloat162float(*src); else v = *src;
+      }
+      tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int c = ct * 32 + j, p = pt * 32 + tx;
+      if (c < C && p < P) y[((long long)b * C + c) * P + p] = tile[tx][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ max-pool
+template <typename T>
+__global__ void maxpool_kernel(DView x, DView y) {
+  const int G = y.C / 8;
+  const long long total = (long long)y.B * y.H * y.W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int ow = (int)(r % y.W); r /= y.W;
+    const int oh = (int)(r % y.H);
+    const int b = (int)(r / y.H);
+    const long long p00 = ((long long)b * x.H + 2 * oh) * x.W + 2 * ow;
+    float a[8], bb[8], c[8], d[8], o[8];
+    V8<T>::load(at<T>(x, p00, g * 8), a);
+    V8<T>::load(at<T>(x, p00 + 1, g * 8), bb);
+    V8<T>::load(at<T>(x, p00 + x.W, g * 8), c);
+    V8<T>::load(at<T>(x, p00 + x.W + 1, g * 8), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaxf(a[k], bb[k]), fmaxf(c[k], d[k]));
+    V8<T>::store(at<T>(y, ((long long)b * y.H + oh) * y.W + ow, g * 8), o);
+  }
+}
+
+// one thread per 2x2 window (windows also cover the odd trailing row/col, which get no gradient)
+template <typename T>
+__global__ void maxpool_bwd_kernel(DView x, DView gy, DView add, int has_add, DView gx) {
+  const int G = x.C / 8;
+  const int WH = (x.H + 1) / 2, WW = (x.W + 1) / 2;
+  const long long total = (long long)x.B * WH * WW * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int ow = (int)(r % WW); r /= WW;
+    const int oh = (int)(r % WH);
+    const int b = (int)(r / WH);
+    const bool full = (2 * oh + 1 < x.H) && (2 * ow + 1 < x.W);   // a real pooling window
+    float gv[8];
+    float xv[4][8];
+    int best[8];
+    if (full) {
+      V8<T>::load(at<T>(gy, ((long long)b * gy.H + oh) * gy.W + ow, g * 8), gv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        V8<T>::load(at<T>(x, ((long long)b * x.H + 2 * oh + (q >> 1)) * x.W + 2 * ow + (q & 1), g * 8), xv[q]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int bi = 0; float bv = xv[0][k];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) if (xv[q][k] > bv) { bv = xv[q][k]; bi = q; }
+        best[k] = bi;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int h = 2 * oh + (q >> 1), w = 2 * ow + (q & 1);
+      if (h >= x.H || w >= x.W) continue;
+      const long long pix = ((long long)b * x.H + h) * x.W + w;
+      float o[8];
+      if (has_add) V8<T>::load(at<T>(add, pix, g * 8), o);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      }
+      if (full) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (best[k] == q) o[k] += gv[k];
+      }
+      V8<T>::store(at<T>(gx, pix, g * 8), o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bilinear
+template <typename T>
+__global__ void bilinear_kernel(DView x, DView y, BilinearTables t) {
+  const int G = y.C / 8;
+  const long long total = (long long)y.B * y.H * y.W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int ow = (int)(r % y.W); r /= y.W;
+    const int oh = (int)(r % y.H);
+    const int b = (int)(r / y.H);
+    const int y0 = t.y0[oh], y1 = t.y1[oh], x0 = t.x0[ow], x1 = t.x1[ow];
+    const float ly = t.ly[oh], lx = t.lx[ow];
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const long long base = (long long)b * x.H;
+    float a[8], bb[8], c[8], d[8], o[8];
+    V8<T>::load(at<T>(x, (base + y0) * x.W + x0, g * 8), a);
+    V8<T>::load(at<T>(x, (base + y0) * x.W + x1, g * 8), bb);
+    V8<T>::load(at<T>(x, (base + y1) * x.W + x0, g * 8), c);
+    V8<T>::load(at<T>(x, (base + y1) * x.W + x1, g * 8), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * bb[k]) + ly * (hx * c[k] + lx * d[k]);
+    V8<T>::store(at<T>(y, ((long long)b * y.H + oh) * y.W + ow, g * 8), o);
+  }
+}
+// gather form: gx[ih,iw] = sum_{(oh,wy) in rows(ih)} sum_{(ow,wx) in cols(iw)} wy*wx*gy[oh,ow]
+template <typename T>
+__global__ void bilinear_bwd_kernel(DView gy, DView gx, BilinearTables t, int accumulate) {
+  const int G = gx.C / 8;
+  const long long total = (long long)gx.B * gx.H * gx.W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int iw = (int)(r % gx.W); r /= gx.W;
+    const int ih = (int)(r % gx.H);
+    const int b = (int)(r / gx.H);
+    float o[8];
+    const long long opix = ((long long)b * gx.H + ih) * gx.W + iw;
+    if (accumulate) V8<T>::load(at<T>(gx, opix, g * 8), o);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    }
+    for (int a = t.ty_off[ih]; a < t.ty_off[ih + 1]; ++a) {
+      const int oh = t.ty_idx[a];
+      const float wy = t.ty_w[a];
+      for (int c = t.tx_off[iw]; c < t.tx_off[iw + 1]; ++c) {
+        const int ow = t.tx_idx[c];
+        const float wgt = wy * t.tx_w[c];
+        float v[8];
+        V8<T>::load(at<T>(gy, ((long long)b * gy.H + oh) * gy.W + ow, g * 8), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(wgt, v[k], o[k]);
+      }
+    }
+    V8<T>::store(at<T>(gx, opix, g * 8), o);
+  }
+}
+
+// ------------------------------------------------------------------ embeddings
+template <typename T>
+__global__ void embed_broadcast_kernel(const float* __restrict__ emb, int stride, DView y) {
+  const int G = y.C / 8;
+  const long long HW = (long long)y.H * y.W;
+  const long long total = (long long)y.B * HW * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    const int b = (int)(pix / HW);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = emb[(long long)b * stride + g * 8 + k];
+    V8<T>::store(at<T>(y, pix, g * 8), o);
+  }
+}
+// grid (chunks, B); block 256 = (C/8 groups) x (256 / groups pixel lanes)
+template <typename T>
+__global__ void embed_reduce_kernel(DView g, float* __restrict__ demb, int stride, int chunks) {
+  extern __shared__ float red[];   // [256][8]
+  const int G = g.C / 8;
+  const int lanes = 256 / G;
+  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
+  const int b = blockIdx.y;
+  const long long HW = (long long)g.H * g.W;
+  const long long per = (HW + chunks - 1) / chunks;
+  const long long p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (pl < lanes)
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      float v[8];
+      V8<T>::load(at<T>(g, b * HW + p, gi * 8), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < g.C) {
+    const int c = threadIdx.x;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(l * G + c / 8) * 8 + (c & 7)];
+    atomicAdd(&demb[(long long)b * stride + c], s);
+  }
+}
+
+template <typename T>
+__global__ void copy_slice_kernel(DView src, DView dst, int accumulate) {
+  const int G = src.C / 8;
+  const long long total = (long long)src.B * src.H * src.W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    float v[8];
+    V8<T>::load(at<T>(src, pix, g * 8), v);
+    if (accumulate) {
+      float o[8];
+      V8<T>::load(at<T>(dst, pix, g * 8), o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += o[k];
+    }
+    V8<T>::store(at<T>(dst, pix, g * 8), v);
+  }
+}
+
+// ------------------------------------------------------------------ 1x1 head
+// 8 lanes per pixel (each 8 channels of up to 64), shuffle-reduce, lane 0 of the group writes NCHW.
+constexpr int kMaxOC = 8;
+template <typename T>
+__global__ void head_kernel(DView x, const float* __restrict__ w, const float* __restrict__ bias, int OC,
+                            int apply_tanh, float* __restrict__ out) {
+  extern __shared__ float sw[];  // [OC][C]
+  for (int i = threadIdx.x; i < OC * x.C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int G = x.C / 8;           // lanes per pixel (power of two <= 32 assumed by the host)
+  const long long P = (long long)x.H * x.W;
+  const long long npix = (long long)x.B * P;
+  const int per_block = blockDim.x / G;
+  const int sub = threadIdx.x % G, slot = threadIdx.x / G;
+  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += (long long)gridDim.x * per_block) {
+    const long long pix = base + slot;
+    float acc[kMaxOC];
+#pragma unroll
+    for (int o = 0; o < kMaxOC; ++o) acc[o] = 0.f;
+    if (pix < npix) {
+      float v[8];
+      V8<T>::load(at<T>(x, pix, sub * 8), v);
+#pragma unroll
+      for (int o = 0; o < kMaxOC; ++o)
+        if (o < OC) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[o] = fmaf(v[k], sw[o * x.C + sub * 8 + k], acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < kMaxOC; ++o)
+      if (o < OC)
+        for (int off = G >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+    if (pix < npix && sub == 0) {
+      const int b = (int)(pix / P);
+      const long long p = pix - (long long)b * P;
+#pragma unroll
+      for (int o = 0; o < kMaxOC; ++o)
+        if (o < OC) {
+          float v = acc[o] + bias[o];
+          if (apply_tanh && o == 0) v = tanhf(v);
+          out[((long long)b * OC + o) * P + p] = v;
+        }
+    }
+  }
+}
+
+// backward of the head: per pixel g_o = gout_o * (o==0 && tanh ? 1 - out_0^2 : 1);
+// gx[c] = sum_o g_o W[o][c];  dW[o][c] += g_o x[c];  db[o] += g_o
+template <typename T>
+__global__ void head_bwd_kernel(DView x, const float* __restrict__ w, int OC, int apply_tanh,
+                                const float* __restrict__ out, const float* __restrict__ gout, DView gx,
+                                float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float sm[];      // sw [OC][C] | sdw [OC][C] | sdb [OC]
+  float* sw = sm;
+  float* sdw = sm + OC * x.C;
+  float* sdb = sdw + OC * x.C;
+  for (int i = threadIdx.x; i < OC * x.C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+  if (threadIdx.x < OC) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int G = x.C / 8;
+  const long long P = (long long)x.H * x.W;
+  const long long npix = (long long)x.B * P;
+  const int per_block = blockDim.x / G;
+  const int sub = threadIdx.x % G, slot = threadIdx.x / G;
+  float dwl[kMaxOC][8];
+  float dbl[kMaxOC];
+#pragma unroll
+  for (int o = 0; o < kMaxOC; ++o) {
+    dbl[o] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dwl[o][k] = 0.f;
+  }
+  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += (long long)gridDim.x * per_block) {
+    const long long pix = base + slot;
+    if (pix >= npix) continue;
+    const int b = (int)(pix / P);
+    const long long p = pix - (long long)b * P;
+    float go[kMaxOC];
+#pragma unroll
+    for (int o = 0; o < kMaxOC; ++o)
+      if (o < OC) {
+        float gval = gout[((long long)b * OC + o) * P + p];
+        if (apply_tanh && o == 0) {
+          const float y = out[((long long)b * OC) * P + p];
+          gval *= (1.f - y * y);
+        }
+        go[o] = gval;
+      } else go[o] = 0.f;
+    float v[8], r[8];
+    V8<T>::load(at<T>(x, pix, sub * 8), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = 0.f;
+#pragma unroll
+    for (int o = 0; o < kMaxOC; ++o)
+      if (o < OC) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          r[k] = fmaf(go[o], sw[o * x.C + sub * 8 + k], r[k]);
+          dwl[o][k] = fmaf(go[o], v[k], dwl[o][k]);
+        }
+        if (sub == 0) dbl[o] += go[o];
+      }
+    V8<T>::store(at<T>(gx, pix, sub * 8), r);
+  }
+#pragma unroll
+  for (int o = 0; o < kMaxOC; ++o)
+    if (o < OC) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&sdw[o * x.C + sub * 8 + k], dwl[o][k]);
+      if (sub == 0) atomicAdd(&sdb[o], dbl[o]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < OC * x.C; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+  if (threadIdx.x < OC) atomicAdd(&db[threadIdx.x], sdb[threadIdx.x]);
+}
+
+inline bool vec_ok(const View& v) { return v.cs % 8 == 0 && v.c0 % 8 == 0 && v.C % 8 == 0; }
+
+}  // namespace
+
+#define MAU_DISPATCH(dt, KERNEL, GRID, BLOCK, SMEM, ST, ...)                            \
+  do {                                                                                  \
+    if ((dt) == DT_BF16) KERNEL<__nv_bfloat16><<<GRID, BLOCK, SMEM, ST>>>(__VA_ARGS__); \
+    else KERNEL<float><<<GRID, BLOCK, SMEM, ST>>>(__VA_ARGS__);                         \
+    MAU_LAUNCHED();                                                                     \
+  } while (0)
+
+int op_nchw_to_nhwc(int dt, const float* x, int B, int C, int H, int W, const View& y, cudaStream_t st) {
+  const int P = H * W;
+  const long long tiles = (long long)B * ceil_div(P, 32) * ceil_div(C, 32);
+  MAU_DISPATCH(dt, nchw_to_nhwc_kernel, grid_for(tiles, 1, 16), 256, 0, st, x, B, C, P, dv(y));
+  return 0;
+}
+int op_nhwc_to_nchw(int dt, const View& x, float* y, cudaStream_t st) {
+  const int P = x.H * x.W;
+  const long long tiles = (long long)x.B * ceil_div(P, 32) * ceil_div(x.C, 32);
+  MAU_DISPATCH(dt, nhwc_to_nchw_kernel, grid_for(tiles, 1, 16), 256, 0, st, dv(x), y, P);
+  return 0;
+}
+int op_maxpool(int dt, const View& x, const View& y, cudaStream_t st) {
+  if (!vec_ok(x) || !vec_ok(y) || x.C != y.C || y.H != x.H / 2 || y.W != x.W / 2)
+    return fail("maxpool: bad views (C=%d/%d, %dx%d -> %dx%d)", x.C, y.C, x.H, x.W, y.H, y.W);
+  MAU_DISPATCH(dt, maxpool_kernel, grid_for(y.pixels() * (y.C / 8)), 256, 0, st, dv(x), dv(y));
+  return 0;
+}
+int op_maxpool_bwd(int dt, const View& x, const View& gy, const View* addend, const View& gx, cudaStream_t st) {
+  if (!vec_ok(x) || !vec_ok(gy) || !vec_ok(gx) || (addend && !vec_ok(*addend))) return fail("maxpool_bwd: bad views");
+  const long long items = (long long)x.B * ((x.H + 1) / 2) * ((x.W + 1) / 2) * (x.C / 8);
+  MAU_DISPATCH(dt, maxpool_bwd_kernel, grid_for(items), 256, 0, st, dv(x), dv(gy), addend ? dv(*addend) : dv(x),
+               addend ? 1 : 0, dv(gx));
+  return 0;
+}
+
+void bilinear_axis_tables(int in, int out, BilinearHost* h) {
+  // area_pixel_compute_scale / compute_source_index_and_lambda of ATen for align_corners=True, in fp32
+  h->i0.resize(out); h->i1.resize(out); h->l.resize(out);
+  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  std::vector<std::vector<std::pair<int, float>>> inv(in);
+  for (int o = 0; o < out; ++o) {
+    const float real = scale * (float)o;
+    int i0 = (int)real;
+    if (i0 > in - 1) i0 = in - 1;
+    const int i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    float l1 = real - (float)i0;
+    l1 = l1 < 0.f ? 0.f : (l1 > 1.f ? 1.f : l1);
+    h->i0[o] = i0; h->i1[o] = i1; h->l[o] = l1;
+    inv[i0].push_back({o, 1.f - l1});
+    inv[i1].push_back({o, l1});
+  }
+  h->t_off.assign(in + 1, 0);
+  h->t_idx.clear(); h->t_w.clear();
+  for (int i = 0; i < in; ++i) {
+    for (auto& e : inv[i]) { h->t_idx.push_back(e.first); h->t_w.push_back(e.second); }
+    h->t_off[i + 1] = (int)h->t_idx.size();
+  }
+}
+int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st) {
+  if (!vec_ok(x) || !vec_ok(y) || x.C != y.C || t.Hin != x.H || t.Win != x.W || t.Hout != y.H || t.Wout != y.W)
+    return fail("bilinear: bad views/tables");
+  MAU_DISPATCH(dt, bilinear_kernel, grid_for(y.pixels() * (y.C / 8)), 256, 0, st, dv(x), dv(y), t);
+  return 0;
+}
+int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables& t, int accumulate,
+                    cudaStream_t st) {
+  if (!vec_ok(gx) || !vec_ok(gy) || gx.C != gy.C || t.Hin != gx.H || t.Win != gx.W || t.Hout != gy.H ||
+      t.Wout != gy.W)
+    return fail("bilinear_bwd: bad views/tables");
+  MAU_DISPATCH(dt, bilinear_bwd_kernel, grid_for(gx.pixels() * (gx.C / 8)), 256, 0, st, dv(gy), dv(gx), t,
+               accumulate);
+  return 0;
+}
+int op_embed_broadcast(int dt, const float* emb, int emb_stride, const View& y, cudaStream_t st) {
+  if (!vec_ok(y)) return fail("embed_broadcast: bad view");
+  MAU_DISPATCH(dt, embed_broadcast_kernel, grid_for(y.pixels() * (y.C / 8)), 256, 0, st, emb, emb_stride, dv(y));
+  return 0;
+}
+int op_embed_reduce(int dt, const View& g, float* demb, int emb_stride, int accumulate, cudaStream_t st) {
+  if (!vec_ok(g) || g.C > 256) return fail("embed_reduce: bad view (C=%d)", g.C);
+  if (!accumulate) MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * (size_t)g.B * emb_stride, st));
+  const long long HW = (long long)g.H * g.W;
+  int chunks = (int)std::min<long long>(std::max<long long>(1, HW / 512), 148 * 4 / std::max(1, g.B) + 1);
+  dim3 grid((unsigned)chunks, (unsigned)g.B, 1);
+  MAU_DISPATCH(dt, embed_reduce_kernel, grid, 256, 256 * 8 * sizeof(float), st, dv(g), demb, emb_stride, chunks);
+  return 0;
+}
+int op_copy_slice(int dt, const View& src, const View& dst, int accumulate, cudaStream_t st) {
+  if (!vec_ok(src) || !vec_ok(dst) || src.C != dst.C || src.pixels() != dst.pixels()) return fail("copy_slice: bad views");
+  MAU_DISPATCH(dt, copy_slice_kernel, grid_for(src.pixels() * (src.C / 8)), 256, 0, st, dv(src), dv(dst), accumulate);
+  return 0;
+}
+static bool head_ok(const View& x, int OC) {
+  const int G = x.C / 8;
+  return x.C % 8 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && OC >= 1 && OC <= kMaxOC && x.cs % 8 == 0 &&
+         x.c0 % 8 == 0;
+}
+int op_head(int dt, const View& x, const float* w, const float* bias, int OC, int apply_tanh, float* out_nchw,
+            cudaStream_t st) {
+  if (!head_ok(x, OC)) return fail("head: needs C = 8*2^k <= 256 and out_channels <= 8 (C=%d, OC=%d)", x.C, OC);
+  const int per_block = 256 / (x.C / 8);
+  MAU_DISPATCH(dt, head_kernel, grid_for(x.pixels(), per_block), 256, OC * x.C * sizeof(float), st, dv(x), w, bias,
+               OC, apply_tanh, out_nchw);
+  return 0;
+}
+int op_head_bwd(int dt, const View& x, const float* w, int OC, int apply_tanh, const float* out_nchw,
+                const float* gout_nchw, const View& gx, float* dw, float* db, cudaStream_t st) {
+  if (!head_ok(x, OC) || !vec_ok(gx)) return fail("head_bwd: unsupported shape");
+  const int per_block = 256 / (x.C / 8);
+  const size_t smem = (2 * OC * x.C + OC) * sizeof(float);
+  MAU_DISPATCH(dt, head_bwd_kernel, grid_for(x.pixels(), per_block, 4), 256, smem, st, dv(x), w, OC, apply_tanh,
+               out_nchw, gout_nchw, dv(gx), dw, db);
+  return 0;
+}
+
+}  // namespace mau

@@ -1,0 +1,247 @@
+// norm.cu -- BatchNorm2d of the reference's VGGBlock (src/model.py:13,15) as bandwidth kernels:
+// eval-mode folding into the conv epilogue, training-mode batch statistics (biased variance for
+// normalisation, unbiased for the running update, momentum 0.1), the fused normalise+ReLU pass and
+// the two-pass backward.  Per-channel reductions: 8 channels per thread, pixel lanes reduced through
+// shared memory, one double-precision atomic per channel per block.
+#include "ops.h"
+#include "vec.cuh"
+
+namespace mau {
+namespace {
+
+inline DView dv(const View& v) { return DView{v.ptr, v.B, v.H, v.W, v.cs, v.c0, v.C}; }
+template <typename T>
+__device__ __forceinline__ T* at(const DView& v, long long pix, int c) {
+  return static_cast<T*>(v.ptr) + pix * v.cs + v.c0 + c;
+}
+
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                    const float* conv_bias, int C, float eps, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = gamma[c] / sqrtf(rv[c] + eps);
+  scale[c] = s;
+  shift[c] = ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * s + beta[c];
+}
+
+// block = 256 threads = G channel groups x L pixel lanes; block b handles pixels [b*per, (b+1)*per)
+template <typename T, int NQ, typename F>
+__device__ __forceinline__ void channel_reduce(const DView& ref, long long npix, double* out, F&& body) {
+  extern __shared__ float red[];  // [NQ][256][8]
+  const int G = ref.C / 8;
+  const int L = 256 / G;
+  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float acc[NQ][8];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+  if (pl < L)
+    for (long long p = p0 + pl; p < p1; p += L) body(p, gi * 8, acc);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[(q * 256 + threadIdx.x) * 8 + k] = acc[q][k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * ref.C; i += 256) {
+    const int q = i / ref.C, c = i - q * ref.C;
+    double s = 0.0;
+    for (int l = 0; l < L; ++l) s += (double)red[(q * 256 + l * G + (c >> 3)) * 8 + (c & 7)];
+    atomicAdd(&out[q * ref.C + c], s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(DView z, double* sums) {
+  const long long npix = (long long)z.B * z.H * z.W;
+  channel_reduce<T, 2>(z, npix, sums, [&](long long p, int c, float (&acc)[2][8]) {
+    float v[8];
+    V8<T>::load(at<T>(z, p, c), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc[0][k] += v[k]; acc[1][k] = fmaf(v[k], v[k], acc[1][k]); }
+  });
+}
+
+__global__ void bn_finalize_train_kernel(const double* sums, long long count, const float* gamma, const float* beta,
+                                         int C, float eps, float momentum, float* rm, float* rv, float* scale,
+                                         float* shift, float* save_mean, float* save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = (double)count;
+  const double mean = sums[c] / n;
+  double var = sums[C + c] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float s = gamma[c] * rstd;
+  scale[c] = s;
+  shift[c] = beta[c] - (float)mean * s;
+  save_mean[c] = (float)mean;
+  save_rstd[c] = rstd;
+  const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
+  rm[c] = (1.f - momentum) * rm[c] + momentum * (float)mean;
+  rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+}
+
+template <typename T>
+__global__ void bn_apply_relu_kernel(DView z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     DView y) {
+  const int G = z.C / 8;
+  const long long total = (long long)z.B * z.H * z.W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    float v[8];
+    V8<T>::load(at<T>(z, pix, g * 8), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], scale[g * 8 + k], shift[g * 8 + k]), 0.f);
+    V8<T>::store(at<T>(y, pix, g * 8), v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView y, DView z, const float* mean,
+                                                            const float* rstd, double* sums) {
+  const long long npix = (long long)z.B * z.H * z.W;
+  channel_reduce<T, 2>(z, npix, sums, [&](long long p, int c, float (&acc)[2][8]) {
+    float g[8], yy[8], zz[8];
+    V8<T>::load(at<T>(gy, p, c), g);
+    V8<T>::load(at<T>(y, p, c), yy);
+    V8<T>::load(at<T>(z, p, c), zz);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gt = yy[k] > 0.f ? g[k] : 0.f;
+      const float xh = (zz[k] - mean[c + k]) * rstd[c + k];
+      acc[0][k] += gt;
+      acc[1][k] = fmaf(gt, xh, acc[1][k]);
+    }
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView y, DView z, const float* gamma,
+                                                           const float* mean, const float* rstd, const double* sums,
+                                                           long long count, DView dz, double* dbias_sums) {
+  const long long npix = (long long)z.B * z.H * z.W;
+  const float inv_n = 1.f / (float)count;
+  const int C = z.C;
+  channel_reduce<T, 1>(z, npix, dbias_sums, [&](long long p, int c, float (&acc)[1][8]) {
+    float g[8], yy[8], zz[8], o[8];
+    V8<T>::load(at<T>(gy, p, c), g);
+    V8<T>::load(at<T>(y, p, c), yy);
+    V8<T>::load(at<T>(z, p, c), zz);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gt = yy[k] > 0.f ? g[k] : 0.f;
+      const float rs = rstd[c + k];
+      const float xh = (zz[k] - mean[c + k]) * rs;
+      const float m1 = (float)sums[c + k] * inv_n, m2 = (float)sums[C + c + k] * inv_n;
+      o[k] = gamma[c + k] * rs * (gt - m1 - xh * m2);
+      acc[0][k] += V8<T>::round(o[k]);
+    }
+    V8<T>::store(at<T>(dz, p, c), o);
+  });
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* sums, const double* dbias_sums, int C, float* dgamma,
+                                       float* dbeta, float* dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = (float)sums[c];
+  if (dgamma) dgamma[c] = (float)sums[C + c];
+  if (dbias) dbias[c] = (float)dbias_sums[c];
+}
+
+__global__ void bump_counters_kernel(long long* const* counters, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && counters[i]) *counters[i] += 1;
+}
+
+inline bool vec_ok(const View& v) { return v.cs % 8 == 0 && v.c0 % 8 == 0 && v.C % 8 == 0 && v.C <= 2048; }
+inline int reduce_blocks(long long npix, int C) {
+  // enough blocks to fill the machine, but at least ~64 pixels per lane-row of a block
+  const int L = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  long long b = npix / ((long long)L * 16);
+  if (b > 148 * 4) b = 148 * 4;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+int op_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                    const float* conv_bias, int C, float eps, float* scale, float* shift, cudaStream_t st) {
+  bn_fold_eval_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, rm, rv, conv_bias, C, eps, scale, shift);
+  MAU_LAUNCHED();
+  return 0;
+}
+
+int op_bn_stats(int dt, const View& z, double* sums, cudaStream_t st) {
+  if (!vec_ok(z)) return fail("bn_stats: bad view (C=%d cs=%d c0=%d)", z.C, z.cs, z.c0);
+  // sums layout [2][C]; with a single slab (C <= 2048) the kernel's [q*C + c] indexing matches
+  const size_t smem = 2 * 256 * 8 * sizeof(float);
+  const int blocks = reduce_blocks(z.pixels(), z.C);
+  if (dt == DT_BF16) bn_stats_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(DView{z.ptr, z.B, z.H, z.W, z.cs, z.c0, z.C}, sums);
+  else               bn_stats_kernel<float><<<blocks, 256, smem, st>>>(DView{z.ptr, z.B, z.H, z.W, z.cs, z.c0, z.C}, sums);
+  MAU_LAUNCHED();
+  return 0;
+}
+int op_bn_finalize_train(const double* sums, long long count, const float* gamma, const float* beta, int C,
+                         float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                         float* shift, float* save_mean, float* save_rstd, cudaStream_t st) {
+  bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, count, gamma, beta, C, eps, momentum,
+                                                            running_mean, running_var, scale, shift, save_mean,
+                                                            save_rstd);
+  MAU_LAUNCHED();
+  return 0;
+}
+int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shift, const View& y,
+                     cudaStream_t st) {
+  if (!vec_ok(z) || !vec_ok(y) || z.C != y.C || z.pixels() != y.pixels()) return fail("bn_apply: bad views");
+  const long long items = z.pixels() * (z.C / 8);
+  long long b = (items + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (dt == DT_BF16) bn_apply_relu_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(z), scale, shift, dv(y));
+  else               bn_apply_relu_kernel<float><<<(int)b, 256, 0, st>>>(dv(z), scale, shift, dv(y));
+  MAU_LAUNCHED();
+  return 0;
+}
+int op_bn_bwd_reduce(int dt, const View& gy, const View& y, const View& z, const float* mean, const float* rstd,
+                     double* sums, cudaStream_t st) {
+  if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(y)) return fail("bn_bwd_reduce: bad views");
+  const size_t smem = 2 * 256 * 8 * sizeof(float);
+  const int blocks = reduce_blocks(z.pixels(), z.C);
+  if (dt == DT_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), mean, rstd, sums);
+  else               bn_bwd_reduce_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), mean, rstd, sums);
+  MAU_LAUNCHED();
+  return 0;
+}
+int op_bn_bwd_apply(int dt, const View& gy, const View& y, const View& z, const float* gamma, const float* mean,
+                    const float* rstd, const double* sums, long long count, const View& dz_out,
+                    double* dbias_sums, cudaStream_t st) {
+  if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(y) || !vec_ok(dz_out)) return fail("bn_bwd_apply: bad views");
+  const size_t smem = 256 * 8 * sizeof(float);
+  const int blocks = reduce_blocks(z.pixels(), z.C);
+  if (dt == DT_BF16)
+    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
+  else
+    bn_bwd_apply_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
+  MAU_LAUNCHED();
+  return 0;
+}
+int op_bn_bwd_finalize(const double* sums, const double* dbias_sums, int C, float* dgamma, float* dbeta,
+                       float* dbias, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, dbias_sums, C, dgamma, dbeta, dbias);
+  MAU_LAUNCHED();
+  return 0;
+}
+int op_bump_counters(long long* const* counters_dev, int n, cudaStream_t st) {
+  bump_counters_kernel<<<ceil_div(n, 128), 128, 0, st>>>(counters_dev, n);
+  MAU_LAUNCHED();
+  return 0;
+}
+
+}  // namespace mau

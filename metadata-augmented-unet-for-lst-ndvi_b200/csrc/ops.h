@@ -1,0 +1,104 @@
+// ops.h -- host launchers of the bandwidth-bound kernels (elementwise.cu, norm.cu, encoders.cu,
+// loss.cu, metrics.cu).  Every function enqueues on `st` and returns 0 / non-zero.
+#pragma once
+#include <vector>
+#include "common.h"
+
+namespace mau {
+
+// ---- layout (elementwise.cu) ----------------------------------------------------------------
+int op_nchw_to_nhwc(int dt, const float* x, int B, int C, int H, int W, const View& y, cudaStream_t st);
+int op_nhwc_to_nchw(int dt, const View& x, float* y, cudaStream_t st);
+
+// ---- max-pool 2x2/2 floor mode (nn.MaxPool2d(2,2), reference src/model.py:218/58) -------------
+int op_maxpool(int dt, const View& x, const View& y, cudaStream_t st);
+// gx = (addend ? addend : 0) + route(gy) ; tie -> first max in row-major window order
+int op_maxpool_bwd(int dt, const View& x, const View& gy, const View* addend, const View& gx, cudaStream_t st);
+
+// ---- bilinear align_corners=True (reference src/model.py:121,219,245) --------------------------
+struct BilinearTables {          // device arrays owned by the plan
+  int Hin = 0, Win = 0, Hout = 0, Wout = 0;
+  int* y0 = nullptr; int* y1 = nullptr; float* ly = nullptr;   // [Hout]
+  int* x0 = nullptr; int* x1 = nullptr; float* lx = nullptr;   // [Wout]
+  // transposed (gather) form for the backward: CSR over input rows / cols
+  int* ty_off = nullptr; int* ty_idx = nullptr; float* ty_w = nullptr;
+  int* tx_off = nullptr; int* tx_idx = nullptr; float* tx_w = nullptr;
+};
+struct BilinearHost {            // host mirror used to build the tables
+  std::vector<int> i0, i1; std::vector<float> l;
+  std::vector<int> t_off, t_idx; std::vector<float> t_w;
+};
+void bilinear_axis_tables(int in, int out, BilinearHost* h);   // PyTorch's index / lambda rule in fp32
+int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st);
+int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables& t, int accumulate,
+                    cudaStream_t st);
+
+// ---- embedding broadcast / reduction (reference src/model.py:248-259, 98-108) -----------------
+// y[b,h,w,c] = emb[b*emb_stride + c]
+int op_embed_broadcast(int dt, const float* emb, int emb_stride, const View& y, cudaStream_t st);
+// demb[b*stride + c] (+)= sum_{h,w} g[b,h,w,c]
+int op_embed_reduce(int dt, const View& g, float* demb, int emb_stride, int accumulate, cudaStream_t st);
+
+// ---- dst (=|+=) src on channel-slice views ------------------------------------------------------
+int op_copy_slice(int dt, const View& src, const View& dst, int accumulate, cudaStream_t st);
+
+// ---- 1x1 head + tanh on channel 0 (reference src/model.py:284-292) -----------------------------
+int op_head(int dt, const View& x, const float* w, const float* bias, int OC, int apply_tanh, float* out_nchw,
+            cudaStream_t st);
+// gx = W^T (gout * act'), dW += ..., db += ... (dw/db must be zeroed by the caller)
+int op_head_bwd(int dt, const View& x, const float* w, int OC, int apply_tanh, const float* out_nchw,
+                const float* gout_nchw, const View& gx, float* dw, float* db, cudaStream_t st);
+
+// ---- BatchNorm (norm.cu; nn.BatchNorm2d of reference src/model.py:13,15) ------------------------
+// eval: scale = gamma / sqrt(rv + eps), shift = (conv_bias - rm) * scale + beta
+int op_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                    const float* conv_bias, int C, float eps, float* scale, float* shift, cudaStream_t st);
+// train: per-channel sum / sum of squares of z into sums[2*C] (double, zeroed by the caller)
+int op_bn_stats(int dt, const View& z, double* sums, cudaStream_t st);
+// mean/var -> scale, shift (for the apply pass), saved mean / rstd, running-stat update
+int op_bn_finalize_train(const double* sums, long long count, const float* gamma, const float* beta, int C,
+                         float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                         float* shift, float* save_mean, float* save_rstd, cudaStream_t st);
+// y = relu(z * scale + shift) into a (slice) view
+int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shift, const View& y,
+                     cudaStream_t st);
+// backward, pass 1: sums[0..C) = sum g~, sums[C..2C) = sum g~ * xhat, g~ = gy * (y > 0)
+int op_bn_bwd_reduce(int dt, const View& gy, const View& y, const View& z, const float* mean, const float* rstd,
+                     double* sums, cudaStream_t st);
+// backward, pass 2: dz = gamma*rstd*(g~ - s1/n - xhat*s2/n) written over dz_out (may alias z);
+// also dgamma = s2, dbeta = s1 and dbias_sums += sum dz (double, zeroed by the caller)
+int op_bn_bwd_apply(int dt, const View& gy, const View& y, const View& z, const float* gamma, const float* mean,
+                    const float* rstd, const double* sums, long long count, const View& dz_out,
+                    double* dbias_sums, cudaStream_t st);
+int op_bn_bwd_finalize(const double* sums, const double* dbias_sums, int C, float* dgamma, float* dbeta,
+                       float* dbias, cudaStream_t st);
+int op_bump_counters(long long* const* counters_dev, int n, cudaStream_t st);
+
+// ---- encoders (encoders.cu) ---------------------------------------------------------------------
+// MetadataEncoder: Linear(F,32) -> ReLU -> Linear(32,D)  (reference src/model.py:38-48); fp32
+int op_mlp_fwd(const float* md, int B, int F, const float* w0, const float* b0, const float* w2, const float* b2,
+               int D, float* hidden /*[B,32]*/, float* out, int out_stride, cudaStream_t st);
+int op_mlp_bwd(const float* md, int B, int F, const float* w0, const float* w2, int D, const float* hidden,
+               const float* gout, int gout_stride, float* dw0, float* db0, float* dw2, float* db2,
+               cudaStream_t st);
+// TemporalEncoder: LSTM(1,Hd) last hidden -> Linear(Hd,D)  (reference src/model.py:23-34); fp32
+// gates_save (nullable): [B,T,4*Hd] post-activation gates + [B,T,Hd] cell states for BPTT
+int op_lstm_fwd(const float* series, int B, int T, int Hd, const float* w_ih, const float* w_hh, const float* b_ih,
+                const float* b_hh, float* h_last, float* save /*nullable*/, cudaStream_t st);
+int op_lstm_bwd(const float* series, int B, int T, int Hd, const float* w_hh, const float* save,
+                const float* dh_last, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, float* scratch,
+                cudaStream_t st);
+size_t lstm_save_floats(int B, int T, int Hd);
+size_t lstm_bwd_scratch_floats(int B, int Hd);
+int op_linear_fwd(const float* x, int B, int K, const float* w, const float* b, int N, float* y, int y_stride,
+                  cudaStream_t st);
+int op_linear_bwd(const float* x, int B, int K, const float* w, int N, const float* gy, int gy_stride, float* gx,
+                  float* dw, float* db, cudaStream_t st);
+
+// ---- loss / metrics -----------------------------------------------------------------------------
+int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, int W, float lambda_grad,
+            float* losses, float* grad, cudaStream_t st);
+int op_eval_metrics(const float* maps, int maps_c, const float* pred, const float* tgt, int B, int C, int H, int W,
+                    float temp_mean, float temp_std, long long* dw_map, double* sums, cudaStream_t st);
+
+}  // namespace mau

@@ -1,0 +1,134 @@
+// plan.h -- the layer graph of one (variant, B, H, W, T, mode, precision) instance and its executor.
+// Mirrors the data flow of reference src/model.py:261-292 (U-Net) and :123-193 (U-Net++) on NHWC
+// buffers where every torch.cat is a channel slice of a pre-allocated level buffer.
+#pragma once
+#include <functional>
+#include <string>
+#include <vector>
+#include "../../include/mau_b200.h"
+#include "common.h"
+#include "conv_ffma.h"
+#include "conv_tc.h"
+#include "ops.h"
+
+namespace mau {
+
+struct StateInfo {
+  std::string name;
+  long long numel = 0;
+  int role = 0;   // 0 used param, 1 unused param, 2 running stat, 3 counter
+};
+
+struct TRef {      // a channel slice of an activation buffer
+  int buf = -1, c0 = 0, C = 0;
+};
+
+struct Buf {
+  std::string name;
+  void* ptr = nullptr;    // activation
+  void* gptr = nullptr;   // gradient twin (training, allocated lazily)
+  int H = 0, W = 0, C = 0, cs = 0;
+  size_t bytes = 0;
+  std::vector<char> ginit;   // per 8 channels: gradient slice already holds a contribution
+};
+
+struct Ctx {
+  void* const* state = nullptr;
+  void* const* grads = nullptr;
+  const float* maps = nullptr;
+  const float* series = nullptr;
+  const float* md = nullptr;
+  float* out = nullptr;
+  const float* gout = nullptr;
+  cudaStream_t st = nullptr;
+  const float* f(int i) const { return static_cast<const float*>(state[i]); }
+  float* fm(int i) const { return static_cast<float*>(state[i]); }
+  float* g(int i) const { return grads ? static_cast<float*>(grads[i]) : nullptr; }
+};
+
+struct Op {
+  std::string name;
+  std::function<int(Ctx&)> run;
+  int grad_first = -1, grad_last = -1;   // state gradients that are final after this (backward) op
+};
+
+struct ConvLayer {
+  std::string name;
+  int Cin = 0, Cout = 0, H = 0, W = 0;
+  int iw = -1, ib = -1, igamma = -1, ibeta = -1, irm = -1, irv = -1, inbt = -1;
+  int in_buf = -1, nseg = 0, seg_start[4] = {0, 0, 0, 0}, seg_len[4] = {0, 0, 0, 0};
+  int Kp = 0;
+  TRef out;                 // y = relu(bn(conv(x)))
+  int zbuf = -1;            // training: pre-BN conv output (later overwritten by dz)
+  bool input_needs_grad = true;
+  double flops = 0;
+  // device scratch
+  int* kmap = nullptr;
+  void* wpack = nullptr;
+  float* scale = nullptr; float* shift = nullptr; float* mean = nullptr; float* rstd = nullptr;
+  double* sums = nullptr;   // [2C] stats / backward sums
+  double* dbsum = nullptr;  // [C]
+  void* wpack_d[4] = {nullptr, nullptr, nullptr, nullptr};
+  int Kd = 0;
+  ConvTcOp tc; ConvFfmaParams ff;
+  ConvTcOp tc_d[4]; ConvFfmaParams ff_d[4];
+  WgradTcOp wg[4];
+};
+
+class Plan {
+ public:
+  mau_config cfg;
+  bool dry = false;          // describe-only: no CUDA calls
+  int dt = DT_BF16;
+  bool use_tc = true;
+  int conv_mode = MODE_ROW3;
+  std::vector<StateInfo> state;
+  std::vector<Buf> bufs;
+  std::vector<ConvLayer*> layers;
+  std::vector<Op> fwd, bwd;
+  std::vector<void*> allocs;
+  size_t ws_bytes = 0;
+  double fwd_flops = 0, bwd_flops = 0;
+  bool forward_done = false;
+  mau_grad_ready_fn hook = nullptr; void* hook_user = nullptr;
+  bool profiling = false;
+  std::vector<std::pair<std::string, float>> prof;
+  std::vector<long long*> counters_host; long long** counters_dev = nullptr;
+  std::string describe_json;
+  std::vector<void*> last_state; const float* last_series = nullptr; const float* last_md = nullptr;
+
+  ~Plan();
+  int build();
+  int run_forward(Ctx& c);
+  int run_backward(Ctx& c);
+
+ private:
+  // ---- construction helpers
+  int add_state(const std::string& name, long long numel, int role);
+  int new_buf(const std::string& name, int H, int W, int C);
+  void* alloc(size_t bytes);
+  View view(const TRef& t) const;
+  View whole(int buf) const;
+  int gview(const TRef& t, View* out);        // gradient twin view (allocates lazily)
+  int gcontrib(const TRef& t, int* accumulate);   // first contribution stores, later ones accumulate
+  struct BlockIdx { int c1w, c1b, g1, b1, rm1, rv1, n1, c2w, c2b, g2, b2, rm2, rv2, n2; };
+  BlockIdx add_block_state(const std::string& prefix, int cin, int cmid, int cout);
+  int add_encoder_state(int* lstm0, int* fc0, int* mlp0);
+  ConvLayer* add_conv(const std::string& name, int iw0, int in_buf, int nseg, const int* seg_start,
+                      const int* seg_len, TRef out, bool input_needs_grad);
+  int emit_conv_fwd(ConvLayer* L);
+  int emit_conv_bwd(ConvLayer* L);
+  int add_vgg(const std::string& name, const BlockIdx& bi, int in_buf, int nseg, const int* seg_start,
+              const int* seg_len, int cmid, TRef out, bool input_needs_grad, std::vector<ConvLayer*>* made);
+  int make_bilinear(int Hin, int Win, int Hout, int Wout, BilinearTables* t);
+  int build_unet();
+  int build_unetpp();
+  int build_encoders(int lstm0, int fc0, int mlp0, const TRef* t_dst, int n_t, const TRef* m_dst, int n_m);
+  std::vector<std::function<int()>> bwd_makers;   // run in reverse to emit backward ops
+  // encoder scratch
+  float* emb = nullptr; float* demb = nullptr; float* hidden = nullptr; float* hlast = nullptr;
+  float* dhlast = nullptr; float* lstm_save = nullptr;
+  int emb_dim = 0;
+};
+
+}  // namespace mau

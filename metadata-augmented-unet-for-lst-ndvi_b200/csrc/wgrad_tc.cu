@@ -1,0 +1,187 @@
+// wgrad_tc.cu -- weight gradient of the 3x3 convolution on the sm_100a tensor cores.
+//
+// Replaces: the dL/dW that autograd derives for nn.Conv2d(cin, cout, 3, padding=1)
+// (reference src/model.py:12,14; backward triggered at src/train.py:252).
+//
+//   dW[co][ci][r][s] = sum_{b,h,w} dY[b,h,w,co] * X[b,h+r-1,w+s-1,ci]
+//   GEMM view per filter tap: M = 128 output channels, N = 64 input channels, K = pixels.
+//
+// Both operands are NHWC bf16, i.e. the reduction dimension (pixels) is the *slow* one: the TMA
+// boxes {64 ch, 8 w, 8 h} land in SMEM as [64 pixel rows][128 B of channels] with 128-byte swizzle,
+// which is exactly the MN-major canonical UMMA layout (8-row K groups at SBO = 1024 B, 64-channel
+// MN groups at LBO = one box).  The X box of tap (r,s) is the dY box shifted by (r-1, s-1); the TMA
+// unit's out-of-bounds zero fill is the convolution padding.  One CTA owns one filter row r (three
+// fp32 accumulators of 128x64 in TMEM, 192 columns), one (co, ci) tile and one slice of the pixel
+// range (split-K); partial results are combined with fp32 atomics straight into the OIHW gradient.
+#include "conv_tc.h"
+#include "ptx.cuh"
+#include "tma.h"
+
+namespace mau {
+using namespace ptx;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kStages = 4;
+constexpr int kBox = 8192;               // one {64 ch, 8, 8} bf16 box
+constexpr int kStageBytes = 5 * kBox;    // 2 dY boxes (128 co) + 3 X boxes (s = 0,1,2)
+
+struct WgradParams {
+  int B, H, W;
+  int tiles_w, tiles_h;       // 8x8 pixel tiles per image
+  int Cout, Cin;              // extents of the dY view / X segment view
+  int ci_w0, Cin_w;           // placement inside the OIHW weight tensor
+  int tiles_per_split, total_tiles;
+};
+
+__global__ void __launch_bounds__(kThreads) wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmDy,
+                                                               const __grid_constant__ CUtensorMap tmX,
+                                                               const WgradParams p, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci0 = blockIdx.x * 64;
+  const int co0 = blockIdx.y * 128;
+  const int r = blockIdx.z % 3;
+  const int split = blockIdx.z / 3;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
+  const int tiles_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmDy);
+    prefetch_tensormap(&tmX);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int b = t / tiles_img;
+        const int rem = t - b * tiles_img;
+        const int h0 = (rem / p.tiles_w) * 8, w0 = (rem % p.tiles_w) * 8;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], kStageBytes);
+        uint8_t* s = smem + stage * kStageBytes;
+        tma_load_4d(s, &tmDy, &full[stage], co0, w0, h0, b);
+        tma_load_4d(s + kBox, &tmDy, &full[stage], co0 + 64, w0, h0, b);
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx)
+          tma_load_4d(s + (2 + sx) * kBox, &tmX, &full[stage], ci0, w0 + sx - 1, h0 + r - 1, b);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(128, 64, /*a MN-major*/ 1, /*b MN-major*/ 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+          const uint32_t sb = sa + (2 + sx) * kBox;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {   // 16 pixels (two 8-row K groups) per instruction
+            const uint64_t da = smem_desc_sw128(sa + kk * 2048, /*LBO: next 64 co*/ kBox, /*SBO*/ 1024, 0);
+            const uint64_t db = smem_desc_sw128(sb + kk * 2048, kBox, 1024, 0);
+            umma_bf16(tmem_base + sx * 64, da, db, idesc, (t > t_begin || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    if (t_end > t_begin) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+#pragma unroll 1
+      for (int sx = 0; sx < 3; ++sx) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + sx * 64 + half * 32, v);
+          tmem_ld_wait();
+          if (co < p.Cout) {
+            float* row = dw + ((long long)co * p.Cin_w + p.ci_w0 + ci0 + half * 32) * 9 + r * 3 + sx;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + half * 32 + j < p.Cin) atomicAdd(row + j * 9, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace
+
+int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0, int Cin_w) {
+  if (x_seg.B != dy.B || x_seg.H != dy.H || x_seg.W != dy.W) return fail("wgrad_tc: geometry mismatch");
+  if (x_seg.cs % 8 || x_seg.c0 % 8 || dy.cs % 8 || dy.c0 % 8) return fail("wgrad_tc: views must be 8-channel aligned");
+  op->B = dy.B; op->H = dy.H; op->W = dy.W;
+  op->Cout = dy.C; op->Cin = x_seg.C; op->ci_w0 = ci_w0; op->Cin_w = Cin_w;
+  op->n_tiles = ceil_div(x_seg.C, 64);
+  op->m_tiles = ceil_div(dy.C, 128);
+  const int total_tiles = dy.B * ceil_div(dy.H, 8) * ceil_div(dy.W, 8);
+  int want = ceil_div(148 * 2, op->n_tiles * op->m_tiles * 3);
+  if (want < 1) want = 1;
+  if (want > total_tiles) want = total_tiles;
+  op->tiles_per_split = ceil_div(total_tiles, want);
+  op->splits = ceil_div(total_tiles, op->tiles_per_split);
+  op->grid = dim3((unsigned)op->n_tiles, (unsigned)op->m_tiles, (unsigned)(3 * op->splits));
+  MAU_TRY(make_nhwc_map(&op->tmDy, DT_BF16, dy, 64, 8, 8));
+  MAU_TRY(make_nhwc_map(&op->tmX, DT_BF16, x_seg, 64, 8, 8));
+  return 0;
+}
+
+int wgrad_tc_launch(const WgradTcOp& op, float* dw_oihw, cudaStream_t st) {
+  constexpr size_t smem = 1024 + kStages * kStageBytes + 8 * (2 * kStages + 1) + 16;
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 15]) {
+    MAU_CUDA(cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 15] = true;
+  }
+  WgradParams p;
+  p.B = op.B; p.H = op.H; p.W = op.W;
+  p.tiles_w = ceil_div(op.W, 8); p.tiles_h = ceil_div(op.H, 8);
+  p.Cout = op.Cout; p.Cin = op.Cin; p.ci_w0 = op.ci_w0; p.Cin_w = op.Cin_w;
+  p.tiles_per_split = op.tiles_per_split;
+  p.total_tiles = op.B * p.tiles_w * p.tiles_h;
+  wgrad3x3_tc_kernel<<<op.grid, kThreads, smem, st>>>(op.tmDy, op.tmX, p, dw_oihw);
+  MAU_LAUNCHED();
+  return 0;
+}
+
+}  // namespace mau
