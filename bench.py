@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- tiles/s of the Metadata-Augmented U-Net hot path on B200 (and the CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--batch B]
+    python bench.py --impl reference ...        # the reference algorithm on the host CPU (oracle port)
+
+One "step" = one pass of the hot path over one batch of synthetic tiles (23x250x250).
+Default workload = BASELINE.json configs[1]: U-Net + metadata MLP, eval mode, bf16, per-GPU batch 16.
+`--workload train` = configs[2]: the same model, train mode, forward + L1 loss + backward.
+Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), tiles sharded across
+ranks (weak scaling); training adds the NCCL gradient all-reduce overlapped with backward.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE = 250
+CTOR = (23, 828, 64, 8, 64, 96, 2)           # conf/config.yaml:18-20,49-51; out_channels 2
+KW = dict(temporal_embeddings=False, metadata_embeddings=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (pynvml == nvidia-smi's source)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference(workload, batch, iters, warm=1):
+    """The reference algorithm on the host cores: oracle/unet_oracle.py (functional torch CPU fp32,
+    same ATen kernels the reference module dispatches to)."""
+    import torch
+    import mau_b200
+    from oracle import unet_oracle as O
+    torch.manual_seed(42)
+    m = mau_b200.UrbanPredictor("unet", *CTOR, **KW)
+    O.perturb_bn_stats(m.state_dict())
+    sd = m.state_dict()
+    x, ts, md, tgt = O.synthetic_batch(batch, TILE, TILE, seed=1002)
+    times = []
+    for i in range(warm + iters):
+        t0 = time.perf_counter()
+        if workload == "infer":
+            with torch.no_grad():
+                O.forward(sd, "unet", x, ts, md, training=False, **KW)
+        else:
+            O.train_step_grads(sd, "unet", x, ts, md, tgt, loss="l1", **KW)
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--batch", type=int, default=16, help="tiles per GPU per step (conf/config.yaml:45)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-layers", action="store_true", help="print per-layer device times to stderr")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "inference tiles/sec" if args.workload == "infer" else "training tiles/sec (fwd+bwd)"
+    workload_name = ("Metadata-Augmented U-Net (metadata MLP fused at bottleneck) inference, synthetic 23x250x250 tiles"
+                     if args.workload == "infer" else
+                     "Metadata-Augmented U-Net training fwd+L1+bwd, data-parallel, synthetic 23x250x250 tiles")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = 8 if args.workload == "infer" else 4
+        v, sec, threads = cpu_reference(args.workload, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name, "tile": [23, TILE, TILE], "batch_per_step": sample, "device": "cpu"},
+            "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} tiles per step, {max(1, args.steps)} timed steps, oracle/unet_oracle.py on torch CPU fp32"},
+            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mau_b200
+    from mau_b200 import engine
+    from oracle import unet_oracle as O   # synthetic inputs + CPU baseline leg only
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(42)
+    model = mau_b200.UrbanPredictor("unet", *CTOR, **KW)
+    O.perturb_bn_stats(model.state_dict())
+    model = model.to(dev)
+    train = args.workload == "train"
+    model.train(train)
+    if train and world > 1:
+        from mau_b200 import parallel
+        parallel.DataParallel(model)         # registers the overlapped all-reduce on the plan's grad hook
+    # several distinct input batches so that consecutive steps never re-read L2-resident inputs
+    nb = 4
+    host = [O.synthetic_batch(B, TILE, TILE, seed=1002 + 17 * rank + i) for i in range(nb)]
+    pinned = [tuple(t.pin_memory() for t in h) for h in host]
+    devb = [tuple(t.to(dev) for t in h) for h in host]
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3) if train else None
+
+    def step(i, batch):
+        x, ts, md, tgt = batch
+        if not train:
+            with torch.no_grad():
+                return model(x, ts, md)
+        out = model(x, ts, md)
+        loss = engine.compute_loss_l1_grad(out, tgt, 0.0)["total"]      # L1 via the fused loss kernel
+        loss.backward()
+        opt.zero_grad(set_to_none=True)      # optimizer step is reported separately
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i, devb[i % nb])
+    barrier()
+    launches0 = engine.lib().mau_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i, devb[i % nb])
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = engine.lib().mau_launch_count() - launches0
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end: host (pinned) inputs -> H2D -> plugin forward -> D2H result, every step
+    def e2e_step(i):
+        x, ts, md, tgt = pinned[i % nb]
+        xd, td, mdd = x.to(dev, non_blocking=True), ts.to(dev, non_blocking=True), md.to(dev, non_blocking=True)
+        if not train:
+            with torch.no_grad():
+                return model(xd, td, mdd).cpu()
+        tg = tgt.to(dev, non_blocking=True)
+        out = model(xd, td, mdd)
+        loss = engine.compute_loss_l1_grad(out, tg, 0.0)["total"]
+        loss.backward()
+        opt.zero_grad(set_to_none=True)
+        return loss.detach().cpu()
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+    x0, ts0, md0, tg0 = pinned[0]
+    h2d = sum(t_.numel() * 4 for t_ in ((x0, ts0, md0, tg0) if train else (x0, ts0, md0)))
+    d2h = 4 if train else B * 2 * TILE * TILE * 4
+
+    # ---- roofline of the dominant kernel (3x3 conv on the tensor pipe): per-layer CUDA-event times
+    plan = next(iter(model.model._plans.values()))
+    for p_ in model.model._plans.values():
+        if p_.cfg["training"] == int(train) and p_.cfg["batch"] == B:
+            plan = p_
+    plan.profile(True)
+    conv_ms, conv_n, all_ms = 0.0, 0, 0.0
+    reps = 3
+    for i in range(reps):
+        step(i, devb[i % nb])
+        torch.cuda.synchronize()
+        for name, t_ms in plan.profile_read():
+            all_ms += t_ms
+            if ".conv" in name:
+                conv_ms += t_ms
+                conv_n += 1
+            if args.profile_layers and i == reps - 1 and rank == 0:
+                print(f"{name:28s} {t_ms:8.3f} ms", file=sys.stderr)
+    plan.profile(False)
+    fwd_flops, bwd_flops = plan.flops()
+    pk = peaks()
+    conv_flops = (fwd_flops + (bwd_flops if train else 0.0))
+    achieved_tf = conv_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    roof = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": achieved_tf / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"],
+            "kernel": "conv3x3_tc_kernel (+wgrad3x3_tc_kernel in training)",
+            "conv_share_of_step": conv_ms / all_ms if all_ms else None,
+            "algorithmic_gflop_per_tile": conv_flops / B / 1e9}
+
+    out = {"metric": metric, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": workload_name, "tile": [23, TILE, TILE], "batch_per_gpu": B,
+                      "global_batch": B * world, "parallelism": f"dp{world}",
+                      "l2": "4 rotating input batches (368 MB) + ~2 GB of activations per step: working set > 126 MB L2"},
+           "clocks": sampler.summary(),
+           "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches), "roofline": roof,
+           "tflops_whole_step": (fwd_flops + (bwd_flops if train else 0)) / B * value / world / 1e12}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = 4 if not train else 2
+        v, sec, threads = cpu_reference(args.workload, sample, 3, 1)
+        out["cpu_baseline"] = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
+                               "sample": f"{sample} tiles x 3 timed steps (1 warm-up), oracle/unet_oracle.py, torch CPU fp32"}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -248,9 +248,9 @@ class HotPathFn(torch.autograd.Function):
     src/model.py:261-292 / :123-193 as recorded by PyTorch autograd)."""
 
     @staticmethod
-    def forward(ctx, plan: Plan, state, diff_idx, maps, series, md, *diff_params):
+    def forward(ctx, plan: Plan, state, diff_idx, dp, maps, series, md, *diff_params):
         out = plan.forward(state, maps, series, md)
-        ctx.plan, ctx.diff_idx, ctx.n_state = plan, diff_idx, len(state)
+        ctx.plan, ctx.diff_idx, ctx.n_state, ctx.dp = plan, diff_idx, len(state), dp
         ctx.shapes = [p.shape for p in diff_params]
         return out
 
@@ -258,6 +258,11 @@ class HotPathFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         plan: Plan = ctx.plan
         grad_out = grad_out.contiguous().float()
+        if ctx.dp is not None:        # data parallel: grads are views of one flat buffer, all-reduced
+            grads_full, outs = ctx.dp.make_grads(plan, ctx.diff_idx, ctx.shapes)   # from inside backward
+            plan.backward(grad_out, grads_full)
+            ctx.dp.finish(plan)
+            return (None, None, None, None, None, None, None, *outs)
         grads_full: List[Optional[torch.Tensor]] = [None] * ctx.n_state
         outs = []
         for i, shp in zip(ctx.diff_idx, ctx.shapes):
@@ -265,7 +270,7 @@ class HotPathFn(torch.autograd.Function):
             grads_full[i] = g
             outs.append(g)
         plan.backward(grad_out, grads_full)
-        return (None, None, None, None, None, None, *outs)
+        return (None, None, None, None, None, None, None, *outs)
 
 
 # ---------------------------------------------------------------------- #

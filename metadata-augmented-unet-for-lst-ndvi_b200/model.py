@@ -14,6 +14,7 @@ be built, otherwise a ``RuntimeError`` is raised.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -67,6 +68,7 @@ class _EngineNet(nn.Module):
     def _init_engine_state(self):
         # not registered as parameters/buffers -> invisible to state_dict()
         object.__setattr__(self, "_plans", {})
+        object.__setattr__(self, "_dp", None)
         object.__setattr__(self, "precision", engine.default_precision())
 
     # ------------------------------------------------------------------ #
@@ -82,6 +84,7 @@ class _EngineNet(nn.Module):
             cfg.update(batch=B, height=H, width=W, seq_len=T, training=int(training),
                        precision=engine.PRECISIONS[self.precision],
                        device=device.index if device.index is not None else torch.cuda.current_device())
+            cfg["flags"] = int(cfg.get("flags", 0)) | int(os.environ.get("MAU_FLAGS", "0"))   # debug knobs
             plan = engine.Plan(cfg)
             if len(self._plans) >= 8:           # bound the workspace held by stale shapes
                 self._plans.pop(next(iter(self._plans))).close()
@@ -119,8 +122,8 @@ class _EngineNet(nn.Module):
                                "call model.train() or wrap inference in torch.no_grad()")
         used = plan.used_state_indices()
         diff = [i for i in used if state[i].requires_grad]
-        out = engine.HotPathFn.apply(plan, state, diff, maps, temp_series, metadata,
-                                     *[state[i] for i in diff])
+        out = engine.HotPathFn.apply(plan, state, diff, getattr(self, "_dp", None), maps, temp_series,
+                                     metadata, *[state[i] for i in diff])
         return self._finish(out)
 
     def _finish(self, out):

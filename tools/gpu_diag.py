@@ -198,6 +198,7 @@ def _model_case(variant, small, training, precision, flags=0, B=2, HW=(37, 45), 
     out, lv, grads, new_stats = O.train_step_grads(sd_cpu, mt, x, ts, md, tgt, loss="l1", **kw)
     res = {"out": rel_err(y.detach().cpu(), out), "loss": abs(float(loss) - float(lv)) / abs(float(lv))}
     worst, worst_name = 0.0, ""
+    errs = []
     for n, p in m.named_parameters():
         gref = grads[n]
         if gref is None:
@@ -207,8 +208,12 @@ def _model_case(variant, small, training, precision, flags=0, B=2, HW=(37, 45), 
         e = float((p.grad.cpu() - gref).norm() / gref.norm().clamp_min(1e-6))
         if gref.norm() < 1e-5:   # conv biases in front of BN: analytically zero gradient
             e = float((p.grad.cpu() - gref).abs().max())
+        errs.append((e, n))
         if e > worst:
             worst, worst_name = e, n
+    errs.sort(reverse=True)
+    res["grad_top5"] = [(round(e, 4), n) for e, n in errs[:5]]
+    res["grad_median"] = errs[len(errs) // 2][0]
     res["grad_worst"] = worst
     res["grad_worst_name"] = worst_name
     sd = m.state_dict()
@@ -255,6 +260,12 @@ def run_group(name):
     if name == "model_eval": return g_model(False, "bf16", 0, 3e-2)
     if name == "model_train_ffma": return g_model(True, "fp32", 0, 1e-4)
     if name == "model_train": return g_model(True, "bf16", 0, 3e-2)
+    if name == "model_train_bf16_ffma": return g_model(True, "bf16", 4, 3e-2)
+    if name == "model_train_full":
+        return g_model(True, "bf16", 0, 3e-2, names=("unet_meta", "unetpp"), small=False, B=4, HW=(64, 64), T=60)
+    if name == "model_train_full_ffma":
+        return g_model(True, "bf16", 4, 3e-2, names=("unet_meta",), small=False, B=4, HW=(64, 64), T=60)
+    if name == "model_eval_halo": return g_model(False, "bf16", 512, 3e-2)
     if name == "model_full":
         return g_model(False, "bf16", 0, 3e-2, names=("unet_meta", "unetpp"), small=False, B=2, HW=(50, 50), T=60)
     raise SystemExit(f"unknown group {name}")
