@@ -59,7 +59,7 @@ typedef struct mau_config {
 #define MAU_FLAG_CONV_TAPLOAD  2  /* debug: force the 9-box-loads-per-chunk conv main loop        */
 #define MAU_FLAG_CONV_FFMA     4  /* debug: run bf16 plans on the FFMA convolution kernels         */
 #define MAU_FLAG_HALO_BASEOFF  256 /* debug: halo main loop fills the UMMA descriptor base_offset   */
-#define MAU_FLAG_CONV_HALO     512 /* single-halo-box conv main loop (1 A load per 64-channel chunk) */
+#define MAU_FLAG_CONV_ROW3     512 /* debug: three-row-box conv main loop instead of the halo kernel */
 
 typedef struct mau_plan mau_plan; /* opaque */
 
@@ -133,8 +133,8 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
 
 /* --- single operators on raw NHWC device buffers (used by the kernel-level parity tests) ----
  * dtype: 0 = bf16, 1 = fp32.  x [B,H,W,Cin_stride], w OIHW fp32 [Cout,Cin,3,3],
- * y [B,H,W,Cout_stride]; y = relu?(conv(x,w)*scale + shift).  impl: 0 = tcgen05 halo main loop,
- * 1 = tcgen05 tap-load main loop, 2 = FFMA. */
+ * y [B,H,W,Cout_stride]; y = relu?(conv(x,w)*scale + shift).  impl: 0 = tcgen05 persistent halo
+ * kernel (default), 1 = tcgen05 tap-load main loop, 3 = tcgen05 three-row-box main loop, 2 = FFMA. */
 int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
                    const float* w_oihw_dev, const float* scale_dev, const float* shift_dev, int relu,
                    int Cout, void* y_dev, int Cout_stride, void* stream);

@@ -162,7 +162,7 @@ int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, 
     else {
       MAU_CUDA(cudaMalloc(&wp, (size_t)2 * 9 * Kp * Cout));
       ConvTcOp op;
-      const int mode = (impl & 3) == 0 ? MODE_ROW3 : ((impl & 3) == 1 ? MODE_TAP : MODE_HALO);
+      const int mode = (impl & 3) == 0 ? MODE_HALO : ((impl & 3) == 1 ? MODE_TAP : MODE_ROW3);
       rc = conv_tc_pack_fwd(w_oihw_dev, Cout, Cin, kmap_dev, Kp, wp, st);
       if (!rc) rc = conv_tc_prepare(&op, x, 1, &zero, &Cin, wp, Kp, Cout, y, mode, scale_dev, shift_dev, relu, 0, (impl >> 2) & 1);
       if (!rc) rc = conv_tc_launch(op, st);

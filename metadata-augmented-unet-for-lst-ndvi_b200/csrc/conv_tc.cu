@@ -27,6 +27,7 @@
 #include "conv_tc.h"
 #include "ptx.cuh"
 #include "tma.h"
+#include <algorithm>
 
 namespace mau {
 using namespace ptx;
@@ -244,6 +245,253 @@ __global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_const
   }
 }
 
+// ==========================================================================================
+// v2: persistent, halo-reuse main loop with MT sub-tiles per B tile and a double-buffered TMEM
+// accumulator so that the epilogue of work item i overlaps the MMAs of item i+1.
+//
+//   work item = MT consecutive 128-pixel tiles (16 rows x 8 cols each, possibly from different
+//               images) x one BN-wide output-channel tile; MT * BN = 256 TMEM columns per buffer.
+//   per 64-channel chunk: MT halo boxes {64, 10, 18} (one TMA load each) feed 9 taps x MT
+//               sub-tiles; every B tile ({64, BN} of one tap) is used by MT MMAs groups, which
+//               divides the weight traffic from L2 by MT.
+// ==========================================================================================
+constexpr int kHaloBytes = 23040;    // 18 x 10 pixels x 128 B
+constexpr int kHaloStride = 23552;   // padded to a multiple of 1024 B (swizzle atom alignment)
+
+template <int BN, int MT, int NA, int NB, int NSTG>
+struct V2Smem {
+  static constexpr int A_STAGE = MT * kHaloStride;
+  static constexpr int B_STAGE = BN * 128;
+  static constexpr int STG = (BN / 64) * 16384;   // one 128-pixel sub-tile of bf16 outputs
+  static constexpr int kBars = 2 * NA + 2 * NB + 4;
+  static constexpr size_t kBytes = 1024 + (size_t)NA * A_STAGE + (size_t)NB * B_STAGE + (size_t)NSTG * STG + 8 * kBars +
+                                   16 + 2 * BN * sizeof(float);
+};
+
+template <int BN, int MT, int NA, int NB, int NSTG>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const __grid_constant__ CUtensorMap tmY,
+                                                                   const ConvTcParams p) {
+  using S = V2Smem<BN, MT, NA, NB, NSTG>;
+  static_assert(MT * BN == 256, "two accumulator buffers of 256 columns fill the 512 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NA * S::A_STAGE;
+  uint8_t* sStg = sB + NB * S::B_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + NSTG * S::STG);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + NA;
+  uint64_t* fullB = emptyA + NA;
+  uint64_t* emptyB = fullB + NB;
+  uint64_t* tmem_full = emptyB + NB;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_shift = s_scale + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_img = p.tiles_w * p.tiles_h;
+  const int total_pt = p.total_ptiles;
+  const int groups = (total_pt + MT - 1) / MT;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int total_items = groups * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA); prefetch_tensormap(&tmB); prefetch_tensormap(&tmY);
+    for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int total_chunks = 0;
+  for (int s = 0; s < p.nseg; ++s) total_chunks += p.seg_chunks[s];
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      Ring ra, rb;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        const int n0 = (it / groups) * BN;
+        const int pt0 = (it % groups) * MT;
+        const int nsub = min(MT, total_pt - pt0);
+        int kB = 0;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          for (int kc = 0; kc < p.seg_chunks[sg]; ++kc, kB += 64) {
+            const int cA = p.seg_start[sg] + kc * 64;
+            mbar_wait(&emptyA[ra.stage], ra.phase ^ 1);
+            mbar_expect_tx(&fullA[ra.stage], nsub * kHaloBytes);
+            for (int j = 0; j < nsub; ++j) {
+              const int pt = pt0 + j;
+              const int b = pt / tiles_img;
+              const int rem = pt - b * tiles_img;
+              const int th = rem / p.tiles_w;
+              tma_load_4d(sA + ra.stage * S::A_STAGE + j * kHaloStride, &tmA, &fullA[ra.stage], cA,
+                          (rem - th * p.tiles_w) * 8 - 1, th * 16 - 1, b);
+            }
+            ra.advance(NA);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&emptyB[rb.stage], rb.phase ^ 1);
+              mbar_expect_tx(&fullB[rb.stage], S::B_STAGE);
+              tma_load_3d(sB + rb.stage * S::B_STAGE, &tmB, &fullB[rb.stage], kB, n0, tap);
+              rb.advance(NB);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 0, 0);
+      Ring ra, rb;
+      int buf = 0;
+      uint32_t ephase[2] = {0, 0};
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        const int pt0 = (it % groups) * MT;
+        const int nsub = min(MT, total_pt - pt0);
+        mbar_wait(&tmem_empty[buf], ephase[buf] ^ 1);   // epilogue has drained this accumulator buffer
+        ephase[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * 256;
+        for (int chunk = 0; chunk < total_chunks; ++chunk) {
+          mbar_wait(&fullA[ra.stage], ra.phase);
+          const uint32_t a_stage = smem_u32(sA + ra.stage * S::A_STAGE);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap - r * 3;
+            mbar_wait(&fullB[rb.stage], rb.phase);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(sB + rb.stage * S::B_STAGE);
+            const uint32_t acc = (chunk | tap) ? 1u : 0u;
+            for (int j = 0; j < nsub; ++j) {
+              const uint32_t a_addr = a_stage + j * kHaloStride + (r * 10 + s) * 128;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = smem_desc_sw128(a_addr + k * 32, 16, 1280, 0);
+                const uint64_t db = smem_desc_sw128(b_addr + k * 32, 16, 1024, 0);
+                umma_bf16(d0 + j * BN, da, db, idesc, (acc | k) ? 1u : 0u);
+              }
+            }
+            umma_commit(&emptyB[rb.stage]);
+            rb.advance(NB);
+          }
+          umma_commit(&emptyA[ra.stage]);
+          ra.advance(NA);
+        }
+        umma_commit(&tmem_full[buf]);
+        buf ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int buf = 0, stg = 0, cur_n0 = -1;
+    uint32_t fphase[2] = {0, 0};
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int n0 = (it / groups) * BN;
+      const int pt0 = (it % groups) * MT;
+      const int nsub = min(MT, total_pt - pt0);
+      if (n0 != cur_n0) {
+        named_bar_sync(1, 128);           // previous users of s_scale are done
+        for (int i = et; i < BN; i += 128) {
+          const int c = n0 + i;
+          const bool ok = c < p.Cout;
+          s_scale[i] = ok ? (p.scale ? p.scale[c] : 1.f) : 0.f;
+          s_shift[i] = ok ? (p.shift ? p.shift[c] : 0.f) : 0.f;
+        }
+        named_bar_sync(1, 128);
+        cur_n0 = n0;
+      }
+      mbar_wait(&tmem_full[buf], fphase[buf]);
+      fphase[buf] ^= 1;
+      tc_fence_after();
+      for (int j = 0; j < nsub; ++j) {
+        uint8_t* sbuf = sStg + stg * S::STG;
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (et == 0) { if (NSTG == 1) tma_wait_group_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+        named_bar_sync(1, 128);
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + j * BN + cb * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int c = cb * 32 + 2 * jj;
+            float y0 = __uint_as_float(v[2 * jj]) * s_scale[c] + s_shift[c];
+            float y1 = __uint_as_float(v[2 * jj + 1]) * s_scale[c + 1] + s_shift[c + 1];
+            if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+            pk[jj] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint8_t* rowp = sbuf + (cb >> 1) * 16384 + m * 128;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int chunk16 = (cb & 1) * 4 + jj;
+            *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (m & 7)) << 4)) =
+                make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+        }
+        if (j == nsub - 1) tc_fence_before();   // all TMEM reads of this buffer are complete (wait::ld above)
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          if (j == nsub - 1) mbar_arrive(&tmem_empty[buf]);   // hand the accumulator buffer back to the MMA warp
+          const int pt = pt0 + j;
+          const int b = pt / tiles_img;
+          const int rem = pt - b * tiles_img;
+          const int th = rem / p.tiles_w;
+          const int w0 = (rem - th * p.tiles_w) * 8, h0 = th * 16;
+#pragma unroll 1
+          for (int g = 0; g < BN / 64; ++g) {
+            if (n0 + g * 64 < p.Cout) {
+              if (p.accumulate) tma_reduce_add_4d(&tmY, sbuf + g * 16384, n0 + g * 64, w0, h0, b);
+              else              tma_store_4d(&tmY, sbuf + g * 16384, n0 + g * 64, w0, h0, b);
+            }
+          }
+          tma_commit_group();
+        }
+        stg = (stg + 1) % NSTG;
+      }
+      buf ^= 1;
+    }
+    if (et == 0) tma_wait_group0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BN, int MT, int NA, int NB, int NSTG>
+int launch_v2(const ConvTcOp& op, cudaStream_t st) {
+  using S = V2Smem<BN, MT, NA, NB, NSTG>;
+  static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = conv3x3_tc_v2_kernel<BN, MT, NA, NB, NSTG>;
+  if (!attr_done[dev & 15]) {
+    MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    attr_done[dev & 15] = true;
+  }
+  kern<<<op.grid, kThreads, S::kBytes, st>>>(op.tmA, op.tmB, op.tmY, op.p);
+  MAU_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> [9][N][Kp] bf16
 // fwd : out[t][n][kp] = W[n][kmap[kp]][t]            (kmap = -1 -> 0)
@@ -296,6 +544,12 @@ int launch_inst(const ConvTcOp& op, cudaStream_t st) {
 }  // namespace
 
 int conv_tc_pick_bn(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
+// v2 tiles are 64 or 128 channels wide: 128 unless that would leave more than half of the last tile empty
+static int pick_bn_v2(int Cout) {
+  if (Cout <= 64) return 64;
+  const int rem = Cout % 128;
+  return (rem == 0 || rem > 64) ? 128 : 64;
+}
 
 int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
                     const void* wpacked, int Kp, int n_rows, const View& y, int mode, const float* scale,
@@ -308,7 +562,7 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   ConvTcParams& p = op->p;
   p = ConvTcParams();
   op->mode = mode;
-  op->bn = conv_tc_pick_bn(y.C);
+  op->bn = mode == MODE_HALO ? pick_bn_v2(y.C) : conv_tc_pick_bn(y.C);
   p.TW = (mode == MODE_TAP) ? 16 : 8;
   p.TH = 128 / p.TW;
   p.tiles_w = ceil_div(y.W, p.TW);
@@ -328,7 +582,16 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   p.halo_base_offset = halo_base_offset;
   p.scale = scale;
   p.shift = shift;
-  op->grid = dim3((unsigned)(y.B * p.tiles_w * p.tiles_h), (unsigned)ceil_div(y.C, op->bn), 1);
+  p.total_ptiles = y.B * p.tiles_w * p.tiles_h;
+  op->grid = dim3((unsigned)p.total_ptiles, (unsigned)ceil_div(y.C, op->bn), 1);
+  if (mode == MODE_HALO) {   // persistent: one CTA per SM (or fewer when there is less work)
+    const int mt = 256 / op->bn;
+    const int items = ceil_div(p.total_ptiles, mt) * ceil_div(y.C, op->bn);
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    op->grid = dim3((unsigned)std::min(items, sms), 1, 1);
+  }
   // A: whole input buffer {C, W, H, B}
   View xa = xbuf;
   int bw = p.TW, bh = p.TH;
@@ -356,10 +619,11 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
   MAU_INST(64, MODE_ROW3, 2, 6)
   MAU_INST(128, MODE_ROW3, 2, 4)
   MAU_INST(256, MODE_ROW3, 2, 3)
-  MAU_INST(64, MODE_HALO, 2, 6)
-  MAU_INST(128, MODE_HALO, 2, 4)
-  MAU_INST(256, MODE_HALO, 2, 4)
 #undef MAU_INST
+  if (op.mode == MODE_HALO) {
+    if (op.bn == 64) return launch_v2<64, 4, 2, 3, 1>(op, st);
+    if (op.bn == 128) return launch_v2<128, 2, 2, 4, 2>(op, st);
+  }
   return fail("conv_tc: no kernel instance for BN=%d mode=%d", op.bn, op.mode);
 }
 

@@ -11,6 +11,7 @@ enum ConvMode : int { MODE_TAP = 0, MODE_ROW3 = 1, MODE_HALO = 2 };
 struct ConvTcParams {
   int tiles_w = 0, tiles_h = 0;  // spatial tiles per image
   int TW = 16, TH = 8;           // tile = TH x TW = 128 output pixels
+  int total_ptiles = 0;          // B * tiles_w * tiles_h
   int Cout = 0;                  // valid output channels (N extent of the view)
   int nseg = 0;                  // channel segments of the input buffer feeding K
   int seg_start[4] = {0, 0, 0, 0};

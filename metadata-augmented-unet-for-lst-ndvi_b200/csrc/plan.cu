@@ -743,7 +743,7 @@ int Plan::build() {
   { const int g = cfg.filters[0] / 8; if (g & (g - 1)) return fail("filters[0] must be 8 * 2^k for the 1x1 head"); }
   dt = cfg.precision == MAU_PRECISION_FP32 ? DT_F32 : DT_BF16;
   use_tc = (dt == DT_BF16) && !(cfg.flags & MAU_FLAG_CONV_FFMA);
-  conv_mode = (cfg.flags & MAU_FLAG_CONV_TAPLOAD) ? MODE_TAP : (((cfg.flags >> 9) & 1) ? MODE_HALO : MODE_ROW3);
+  conv_mode = (cfg.flags & MAU_FLAG_CONV_TAPLOAD) ? MODE_TAP : ((cfg.flags & MAU_FLAG_CONV_ROW3) ? MODE_ROW3 : MODE_HALO);
   if (cfg.training && cfg.deep_supervision) return fail("deep supervision is forward-only in this engine");
   int rc = cfg.model_type == MAU_MODEL_UNET ? build_unet() : build_unetpp();
   if (rc) return rc;

@@ -1,0 +1,299 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against the CPU oracle and the golden vectors written
+by the real reference.  Tolerances: fp32 mode 1e-5 relative (max|d| / max|ref|), bf16 mode 1e-2
+(north_star); integer class maps bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mau_b200
+from mau_b200 import engine
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-5, "bf16": 1e-2}
+VARIANTS = {
+    "unet_noemb": ("unet", 828, dict(temporal_embeddings=False, metadata_embeddings=False)),
+    "unet_metaemb": ("unet", 828, dict(temporal_embeddings=False, metadata_embeddings=True)),
+    "unet_emb": ("unet", 60, dict(temporal_embeddings=True, metadata_embeddings=True)),
+    "unetpp_emb": ("unet++", 60, dict()),
+}
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def nhwc(x, dtype, cs=None):
+    B, C, H, W = x.shape
+    cs = cs or (C + 7) // 8 * 8
+    y = torch.zeros(B, H, W, cs, device=x.device, dtype=dtype)
+    y[..., :C] = x.permute(0, 2, 3, 1).to(dtype)
+    return y
+
+
+# ------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("impl,dt", [(0, 0), (1, 0), (3, 0), (2, 0), (2, 1)])
+@pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64), (1, 31, 31, 192, 256), (2, 33, 47, 23, 64), (1, 25, 25, 8, 8),
+                                   (3, 15, 15, 64, 192), (2, 125, 125, 64, 128)])
+def test_conv3x3_against_torch(impl, dt, shape):
+    """impl 0 = persistent tcgen05 halo kernel, 1 = tap loads, 3 = row boxes, 2 = FFMA."""
+    B, H, W, Cin, Cout = shape
+    torch.manual_seed(0)
+    dtype = torch.bfloat16 if dt == 0 else torch.float32
+    x = torch.randn(B, Cin, H, W, device="cuda"); w = torch.randn(Cout, Cin, 3, 3, device="cuda") / (3 * Cin ** 0.5)
+    scale = torch.rand(Cout, device="cuda") + 0.5; shift = torch.randn(Cout, device="cuda") * 0.1
+    xr, wr = (x.bfloat16().float(), w.bfloat16().float()) if dt == 0 else (x, w)
+    ref = F.relu(F.conv2d(xr.double(), wr.double(), padding=1).float() * scale[None, :, None, None] + shift[None, :, None, None])
+    cs_in = (Cin + 7) // 8 * 8
+    xh = nhwc(x, dtype, cs_in)
+    y = torch.zeros(B, H, W, Cout, device="cuda", dtype=dtype)
+    engine.check(engine.lib().mau_op_conv3x3(impl, dt, xh.data_ptr(), B, H, W, Cin, cs_in, w.data_ptr(), scale.data_ptr(),
+                                             shift.data_ptr(), 1, Cout, y.data_ptr(), Cout, None), "conv")
+    torch.cuda.synchronize()
+    assert rel(y.permute(0, 3, 1, 2), ref) < (6e-3 if dt == 0 else 1e-5)
+
+
+@pytest.mark.parametrize("impl,dt", [(0, 0), (2, 1)])
+@pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64), (2, 15, 15, 128, 256), (2, 33, 47, 24, 64), (1, 25, 25, 8, 8)])
+def test_wgrad_against_torch(impl, dt, shape):
+    B, H, W, Cin, Cout = shape
+    torch.manual_seed(2)
+    dtype = torch.bfloat16 if dt == 0 else torch.float32
+    x = torch.randn(B, Cin, H, W, device="cuda"); dy = torch.randn(B, Cout, H, W, device="cuda")
+    if dt == 0:
+        x, dy = x.bfloat16().float(), dy.bfloat16().float()
+    w = torch.zeros(Cout, Cin, 3, 3, device="cuda", dtype=torch.double, requires_grad=True)
+    (F.conv2d(x.double(), w, padding=1) * dy.double()).sum().backward()
+    dw = torch.zeros(Cout, Cin, 3, 3, device="cuda")
+    xh, dyh = nhwc(x, dtype), nhwc(dy, dtype)
+    engine.check(engine.lib().mau_op_conv3x3_wgrad(impl, dt, xh.data_ptr(), dyh.data_ptr(), B, H, W, Cin, Cin, Cout, Cout,
+                                                   dw.data_ptr(), None), "wgrad")
+    torch.cuda.synchronize()
+    assert rel(dw, w.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dt,tol", [(1, 1e-6), (0, 4e-3)])
+def test_layout_pool_bilinear(dt, tol):
+    L = engine.lib()
+    dtype = torch.float32 if dt == 1 else torch.bfloat16
+    torch.manual_seed(1)
+    x = torch.randn(2, 24, 21, 35, device="cuda")
+    xh = torch.zeros(2, 21, 35, 24, device="cuda", dtype=dtype)
+    engine.check(L.mau_op_nchw_to_nhwc(dt, x.data_ptr(), 2, 24, 21, 35, 24, xh.data_ptr(), None))
+    back = torch.zeros_like(x)
+    engine.check(L.mau_op_nhwc_to_nchw(dt, xh.data_ptr(), 2, 24, 21, 35, 24, back.data_ptr(), None))
+    assert rel(back, x) <= tol
+    xq = xh.float().permute(0, 3, 1, 2)
+    yp = torch.zeros(2, 10, 17, 24, device="cuda", dtype=dtype)
+    engine.check(L.mau_op_maxpool2x2(dt, xh.data_ptr(), 2, 21, 35, 24, yp.data_ptr(), None))
+    assert torch.equal(yp.float().permute(0, 3, 1, 2), F.max_pool2d(xq, 2, 2))       # odd extents drop last row/col
+    for ho, wo in ((42, 70), (43, 71), (22, 35)):
+        yb = torch.zeros(2, ho, wo, 24, device="cuda", dtype=dtype)
+        engine.check(L.mau_op_bilinear(dt, xh.data_ptr(), 2, 21, 35, 24, ho, wo, yb.data_ptr(), None))
+        want = F.interpolate(xq, size=(ho, wo), mode="bilinear", align_corners=True)
+        assert rel(yb.permute(0, 3, 1, 2), want) <= max(tol, 2e-7)
+
+
+@pytest.mark.parametrize("Hd,T,B", [(96, 828, 3), (32, 60, 2)])
+def test_lstm_last_hidden(Hd, T, B):
+    torch.manual_seed(3)
+    lstm = torch.nn.LSTM(1, Hd, batch_first=True).cuda()
+    s = torch.randn(B, T, device="cuda"); s[:, T - 7:] = 0.0       # runs over zero padding like the reference
+    with torch.no_grad():
+        _, (h, _) = lstm(s.unsqueeze(-1))
+    out = torch.zeros(B, Hd, device="cuda")
+    engine.check(engine.lib().mau_op_lstm_last_hidden(s.data_ptr(), B, T, Hd, lstm.weight_ih_l0.data_ptr(),
+                                                      lstm.weight_hh_l0.data_ptr(), lstm.bias_ih_l0.data_ptr(),
+                                                      lstm.bias_hh_l0.data_ptr(), out.data_ptr(), None), "lstm")
+    torch.cuda.synchronize()
+    assert rel(out, h[-1]) < 1e-4
+
+
+def test_loss_terms_against_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "loss_terms.npz"))
+    pred = torch.tensor(z["pred"]).cuda(); tgt = torch.tensor(z["tgt"]).cuda()
+    losses, grad = engine.loss_terms(pred, tgt, "l1", 0.1)
+    torch.cuda.synchronize()
+    assert abs(float(losses[1]) - float(z["l1"])) < 1e-6 and abs(float(losses[2]) - float(z["grad"])) < 1e-6
+    assert abs(float(losses[0]) - float(z["total_l1"])) < 1e-6
+    np.testing.assert_allclose(grad.cpu().numpy(), z["dpred_l1"], rtol=1e-5, atol=1e-9)
+    losses, grad = engine.loss_terms(pred, tgt, "mse", 0.1)
+    assert abs(float(losses[0]) - float(z["total_mse"])) < 1e-6
+    np.testing.assert_allclose(grad.cpu().numpy(), z["dpred_mse"], rtol=1e-5, atol=1e-9)
+    p2 = pred.clone().requires_grad_(True)
+    d = engine.compute_loss_l1_grad(p2, tgt, 0.1)
+    d["total"].backward()
+    np.testing.assert_allclose(p2.grad.cpu().numpy(), z["dpred_l1"], rtol=1e-5, atol=1e-9)
+
+
+def test_eval_metrics_bit_exact_class_map():
+    maps, _, _, tgt = O.synthetic_batch(3, 61, 47, T=8, seed=77)
+    maps[0, 3, 0, 2] = 1.0; maps[0, 6, 0, 2] = 0.5; maps[0, 0:3, 0, 2] = 0; maps[0, 4:6, 0, 2] = 0; maps[0, 7:9, 0, 2] = 0  # tie 3*1 == 6*.5
+    maps[1, 0:9, 5, 5] = 0.0; maps[1, 4, 5, 5] = -1.0                                  # negative product -> class 0
+    pred = torch.randn(3, 2, 61, 47)
+    want_dw, rows = O.eval_metrics(maps.numpy(), pred.numpy(), tgt.numpy(), temp_mean=14.5, temp_std=7.25)
+    dw, sums = engine.eval_metrics(maps.cuda(), pred.cuda(), tgt.cuda(), 14.5, 7.25)
+    torch.cuda.synchronize()
+    assert dw.dtype == torch.int64 and np.array_equal(dw.cpu().numpy(), want_dw)       # bit-exact indexing
+    s = sums.cpu().numpy()
+    for (i, ch, k, n, mae, rmse) in rows:
+        slot = 0 if k < 0 else 1 + k
+        assert int(s[i, ch, slot, 0]) == n
+        assert abs(s[i, ch, slot, 1] / n - mae) < 2e-5 * max(1.0, abs(mae))
+        assert abs(np.sqrt(s[i, ch, slot, 2] / n) - rmse) < 2e-5 * max(1.0, abs(rmse))
+    present = {(i, ch, k) for (i, ch, k, *_r) in rows}
+    for i in range(3):
+        for k in range(9):
+            if (i, 0, k) not in present:
+                assert s[i, 0, 1 + k, 0] == 0            # empty classes stay empty (reference skips them)
+
+
+# ------------------------------------------------------------------ whole model
+def _small(name, precision):
+    mt, _, kw = VARIANTS[name]
+    torch.manual_seed(123)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 23, 37, 45, generator=g); ts = torch.randn(3, 40, generator=g); md = torch.randn(3, 8, generator=g)
+    return mt, kw, m.cuda().set_precision(precision), x, ts, md
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_small_model_eval_against_reference_golden(name, precision, golden_dir):
+    """Odd sizes 37x45 (two-stage 4->8->9 / 18->36->37 resizes) against outputs of the real reference."""
+    mt, kw, m, x, ts, md = _small(name, precision)
+    want = np.load(os.path.join(golden_dir, f"small_{name}.npz"))["y_eval"]
+    m.eval()
+    with torch.no_grad():
+        y = m(x.cuda(), ts.cuda(), md.cuda())
+    assert rel(y, want) < TOL[precision]
+
+
+def test_deep_supervision_eval(golden_dir):
+    torch.manual_seed(123)
+    m = mau_b200.UrbanPredictor("unet++", 23, 828, 16, 8, 8, 32, 2, base_filters=8, deep_supervision=True).cuda()
+    m.set_precision("fp32").eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 23, 37, 45, generator=g); ts = torch.randn(3, 40, generator=g); md = torch.randn(3, 8, generator=g)
+    want = np.load(os.path.join(golden_dir, "small_unetpp_ds.npz"))["y_eval"]
+    with torch.no_grad():
+        ys = m(x.cuda(), ts.cuda(), md.cuda())
+    assert isinstance(ys, list) and len(ys) == 4
+    assert rel(torch.stack(ys), want) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["unet_noemb", "unet_metaemb", "unet_emb", "unetpp_emb"])
+def test_full_width_kat_eval(name, precision, golden_dir):
+    """SURVEY.md 8c known-answer vectors (64 base filters, 50x50, seed 42 / 7)."""
+    mt, T, kw = VARIANTS[name]
+    kat = np.load(os.path.join(golden_dir, f"kat_{name}.npz"))
+    torch.manual_seed(42)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 64, 8, 64, 96, 2, **kw).cuda().set_precision(precision)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 23, 50, 50, generator=g); ts = torch.randn(2, T, generator=g); md = torch.randn(2, 8, generator=g)
+    m.eval()
+    with torch.no_grad():
+        y = m(x.cuda(), ts.cuda(), md.cuda())
+    assert rel(y, kat["y_eval"]) < TOL[precision]
+    # determinism: the same call twice is bit-identical
+    with torch.no_grad():
+        y2 = m(x.cuda(), ts.cuda(), md.cuda())
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("name", ["unet_noemb", "unet_metaemb", "unet_emb", "unetpp_emb"])
+def test_full_width_kat_train_step_fp32(name, golden_dir):
+    """fwd (batch-stat BN) + loss + bwd in fp32 mode against the reference's own gradients."""
+    mt, T, kw = VARIANTS[name]
+    kat = np.load(os.path.join(golden_dir, f"kat_{name}.npz"))
+    torch.manual_seed(42)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 64, 8, 64, 96, 2, **kw).cuda().set_precision("fp32")
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 23, 50, 50, generator=g); ts = torch.randn(2, T, generator=g); md = torch.randn(2, 8, generator=g)
+    m.train()
+    y = m(x.cuda(), ts.cuda(), md.cuda())
+    assert rel(y.detach(), kat["y_train"]) < 2e-5
+    loss = y.abs().mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(kat["loss"])) < 1e-5
+    want = json.loads(str(kat["grad_norms"]))
+    total = 0.0
+    for n, p in m.named_parameters():
+        if want[n] is None:
+            assert p.grad is None, f"{n}: flag-disabled encoder must keep grad None"
+            continue
+        assert p.grad is not None, n
+        gn = float(p.grad.norm()); total += gn * gn
+        assert abs(gn - want[n]) <= 2e-3 * max(want[n], 1e-4) + 1e-6, (n, gn, want[n])
+    assert abs(total ** 0.5 - float(kat["grad_l2"])) < 1e-3 * float(kat["grad_l2"])
+    for k in kat.files:
+        if k.startswith("g::"):
+            got = dict(m.named_parameters())[k[3:]].grad.cpu().numpy()
+            np.testing.assert_allclose(got, kat[k], rtol=5e-3, atol=5e-6)
+    sd = m.state_dict()
+    np.testing.assert_allclose(sd["model.conv0_0.bn1.running_mean"].cpu().numpy(), kat["bn_rm"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(sd["model.conv0_0.bn1.running_var"].cpu().numpy(), kat["bn_rv"], rtol=1e-4, atol=1e-6)
+    assert int(sd["model.conv0_0.bn1.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("name", ["unet_metaemb", "unetpp_emb"])
+def test_train_step_bf16_tracks_fp32(name):
+    """bf16 tensor-core training against the fp32 oracle on conf-like synthetic tiles.  Train-mode
+    BatchNorm amplifies bf16 rounding (a CPU emulation of bf16 storage shows the same 5-10 % on the
+    output), so the check is on the loss and on the direction of the full gradient."""
+    mt, T, kw = VARIANTS[name]
+    torch.manual_seed(42)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 64, 8, 64, 96, 2, **kw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x, ts, md, tgt = O.synthetic_batch(4, 64, 64, T=T, seed=1003)
+    m = m.cuda().train()
+    out = m(x.cuda(), ts.cuda(), md.cuda())
+    loss = engine.compute_loss_l1_grad(out, tgt.cuda(), 0.1)["total"]
+    loss.backward()
+    torch.cuda.synchronize()
+    _, lref, grads, _ = O.train_step_grads(sd, mt, x, ts, md, tgt, loss="l1_grad", **kw)
+    assert abs(float(loss) - float(lref)) < 1e-2 * abs(float(lref))
+    a = torch.cat([p.grad.flatten().cpu() for n, p in m.named_parameters() if grads[n] is not None])
+    b = torch.cat([grads[n].flatten() for n, p in m.named_parameters() if grads[n] is not None])
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    assert cos > 0.9, cos
+    assert abs(float(a.norm() / b.norm()) - 1.0) < 0.15
+
+
+def test_full_size_properties():
+    """BASELINE tile size 23x250x250: eval outputs are per-tile (batch-independent) and deterministic;
+    NDVI channel is tanh-bounded."""
+    torch.manual_seed(42)
+    kw = dict(temporal_embeddings=False, metadata_embeddings=True)
+    m = mau_b200.UrbanPredictor("unet", 23, 828, 64, 8, 64, 96, 2, **kw)
+    O.perturb_bn_stats(m.state_dict())
+    m = m.cuda().eval()
+    x, ts, md, _ = O.synthetic_batch(3, 250, 250, seed=1002)
+    x, ts, md = x.cuda(), ts.cuda(), md.cuda()
+    with torch.no_grad():
+        y3 = m(x, ts, md)
+        y1 = m(x[1:2].contiguous(), ts[1:2].contiguous(), md[1:2].contiguous())
+    assert y3.shape == (3, 2, 250, 250) and torch.isfinite(y3).all()
+    assert torch.equal(y3[1:2], y1)
+    assert float(y3[:, 0].abs().max()) <= 1.0
+
+
+def test_state_dict_roundtrip_on_device(tmp_path):
+    kw = dict(temporal_embeddings=False, metadata_embeddings=True)
+    torch.manual_seed(5)
+    a = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw).cuda().eval()
+    torch.save({"model_state_dict": a.state_dict(), "model_type": "unet", "metadata_input_length": 8}, tmp_path / "c.pth")
+    ck = torch.load(tmp_path / "c.pth", weights_only=False)
+    b = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw).cuda().eval()
+    b.load_state_dict(ck["model_state_dict"], strict=True)
+    x, ts, md, _ = O.synthetic_batch(2, 40, 40, T=8, seed=9)
+    with torch.no_grad():
+        assert torch.equal(a(x.cuda(), ts.cuda(), md.cuda()), b(x.cuda(), ts.cuda(), md.cuda()))

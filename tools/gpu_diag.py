@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["elementwise", "conv_ffma", "conv_tap", "conv_row3", "conv_halo", "conv_halo_bo", "wgrad", "lstm",
+GROUPS = ["elementwise", "conv_ffma", "conv_tap", "conv_row3", "conv_halo", "wgrad", "lstm",
           "model_eval_fp32", "model_eval_ffma", "model_eval_tap", "model_eval", "model_train_ffma", "model_train",
           "model_full"]
 
@@ -58,6 +58,7 @@ def conv_cases():
     return [  # B, H, W, Cin, Cout
         (1, 16, 16, 64, 64), (2, 20, 24, 64, 64), (2, 15, 15, 128, 128), (1, 31, 31, 192, 256),
         (2, 33, 47, 23, 64), (1, 25, 25, 8, 8), (1, 62, 62, 320, 64), (2, 16, 16, 576, 512), (1, 50, 50, 64, 16),
+        (3, 15, 15, 64, 192), (16, 31, 31, 128, 64), (5, 125, 125, 64, 128), (2, 250, 250, 64, 64),
     ]
 
 
@@ -249,9 +250,8 @@ def run_group(name):
     if name == "elementwise": return g_elementwise()
     if name == "conv_ffma": return g_conv(2, 1, 1e-5) and g_conv(2, 0, 1e-2)
     if name == "conv_tap": return g_conv(1, 0, 1e-2)
-    if name == "conv_row3": return g_conv(0, 0, 1e-2)
-    if name == "conv_halo": return g_conv(3, 0, 1e-2)
-    if name == "conv_halo_bo": return g_conv(7, 0, 1e-2)
+    if name == "conv_row3": return g_conv(3, 0, 1e-2)
+    if name == "conv_halo": return g_conv(0, 0, 1e-2)
     if name == "wgrad": return g_wgrad()
     if name == "lstm": return g_lstm()
     if name == "model_eval_fp32": return g_model(False, "fp32", 0, 2e-5)
@@ -265,7 +265,7 @@ def run_group(name):
         return g_model(True, "bf16", 0, 3e-2, names=("unet_meta", "unetpp"), small=False, B=4, HW=(64, 64), T=60)
     if name == "model_train_full_ffma":
         return g_model(True, "bf16", 4, 3e-2, names=("unet_meta",), small=False, B=4, HW=(64, 64), T=60)
-    if name == "model_eval_halo": return g_model(False, "bf16", 512, 3e-2)
+    if name == "model_eval_row3": return g_model(False, "bf16", 512, 3e-2)
     if name == "model_full":
         return g_model(False, "bf16", 0, 3e-2, names=("unet_meta", "unetpp"), small=False, B=2, HW=(50, 50), T=60)
     raise SystemExit(f"unknown group {name}")
