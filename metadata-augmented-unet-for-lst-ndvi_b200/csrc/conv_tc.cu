@@ -262,7 +262,8 @@ template <int BN, int MT, int NA, int NB, int NSTG>
 struct V2Smem {
   static constexpr int A_STAGE = MT * kHaloStride;
   static constexpr int B_STAGE = BN * 128;
-  static constexpr int STG = (BN / 64) * 16384;   // one 128-pixel sub-tile of bf16 outputs
+  static constexpr int SU = BN < 128 ? BN : 128;   // columns staged per TMA-store round
+  static constexpr int STG = (SU / 64) * 16384;    // 128 pixels x SU bf16 channels
   static constexpr int kBars = 2 * NA + 2 * NB + 4;
   static constexpr size_t kBytes = 1024 + (size_t)NA * A_STAGE + (size_t)NB * B_STAGE + (size_t)NSTG * STG + 8 * kBars +
                                    16 + 2 * BN * sizeof(float);
@@ -415,53 +416,59 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
       fphase[buf] ^= 1;
       tc_fence_after();
       for (int j = 0; j < nsub; ++j) {
-        uint8_t* sbuf = sStg + stg * S::STG;
-        // the TMA store that last read this staging buffer must have finished reading it
-        if (et == 0) { if (NSTG == 1) tma_wait_group_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-        named_bar_sync(1, 128);
+        const int pt = pt0 + j;
+        const int b = pt / tiles_img;
+        const int rem = pt - b * tiles_img;
+        const int th = rem / p.tiles_w;
+        const int w0 = (rem - th * p.tiles_w) * 8, h0 = th * 16;
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + j * BN + cb * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const int c = cb * 32 + 2 * jj;
-            float y0 = __uint_as_float(v[2 * jj]) * s_scale[c] + s_shift[c];
-            float y1 = __uint_as_float(v[2 * jj + 1]) * s_scale[c + 1] + s_shift[c + 1];
-            if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
-            pk[jj] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          uint8_t* rowp = sbuf + (cb >> 1) * 16384 + m * 128;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int chunk16 = (cb & 1) * 4 + jj;
-            *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (m & 7)) << 4)) =
-                make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          }
-        }
-        if (j == nsub - 1) tc_fence_before();   // all TMEM reads of this buffer are complete (wait::ld above)
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (et == 0) {
-          if (j == nsub - 1) mbar_arrive(&tmem_empty[buf]);   // hand the accumulator buffer back to the MMA warp
-          const int pt = pt0 + j;
-          const int b = pt / tiles_img;
-          const int rem = pt - b * tiles_img;
-          const int th = rem / p.tiles_w;
-          const int w0 = (rem - th * p.tiles_w) * 8, h0 = th * 16;
+        for (int u = 0; u < BN / S::SU; ++u) {          // store rounds of SU columns
+          uint8_t* sbuf = sStg + stg * S::STG;
+          const bool last = (j == nsub - 1) && (u == BN / S::SU - 1);
+          // the TMA store that last read this staging buffer must have finished reading it
+          if (et == 0) { if (NSTG == 1) tma_wait_group_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+          named_bar_sync(1, 128);
 #pragma unroll 1
-          for (int g = 0; g < BN / 64; ++g) {
-            if (n0 + g * 64 < p.Cout) {
-              if (p.accumulate) tma_reduce_add_4d(&tmY, sbuf + g * 16384, n0 + g * 64, w0, h0, b);
-              else              tma_store_4d(&tmY, sbuf + g * 16384, n0 + g * 64, w0, h0, b);
+          for (int cb = 0; cb < S::SU / 32; ++cb) {
+            uint32_t v[32];
+            const int col = u * S::SU + cb * 32;
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + j * BN + col, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int c = col + 2 * jj;
+              float y0 = __uint_as_float(v[2 * jj]) * s_scale[c] + s_shift[c];
+              float y1 = __uint_as_float(v[2 * jj + 1]) * s_scale[c + 1] + s_shift[c + 1];
+              if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+              pk[jj] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            uint8_t* rowp = sbuf + (cb >> 1) * 16384 + m * 128;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int chunk16 = (cb & 1) * 4 + jj;
+              *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (m & 7)) << 4)) =
+                  make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
             }
           }
-          tma_commit_group();
+          if (last) tc_fence_before();   // all TMEM reads of this buffer are complete (wait::ld above)
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            if (last) mbar_arrive(&tmem_empty[buf]);   // hand the accumulator buffer back to the MMA warp
+#pragma unroll 1
+            for (int g = 0; g < S::SU / 64; ++g) {
+              const int c = n0 + u * S::SU + g * 64;
+              if (c < p.Cout) {
+                if (p.accumulate) tma_reduce_add_4d(&tmY, sbuf + g * 16384, c, w0, h0, b);
+                else              tma_store_4d(&tmY, sbuf + g * 16384, c, w0, h0, b);
+              }
+            }
+            tma_commit_group();
+          }
+          stg = (stg + 1) % NSTG;
         }
-        stg = (stg + 1) % NSTG;
       }
       buf ^= 1;
     }
@@ -546,9 +553,16 @@ int launch_inst(const ConvTcOp& op, cudaStream_t st) {
 int conv_tc_pick_bn(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
 // v2 tiles are 64 or 128 channels wide: 128 unless that would leave more than half of the last tile empty
 static int pick_bn_v2(int Cout) {
-  if (Cout <= 64) return 64;
-  const int rem = Cout % 128;
-  return (rem == 0 || rem > 64) ? 128 : 64;
+  // cost model: tiles x width / measured MMA efficiency of that instruction width (SMEM operand
+  // bandwidth: N = 64 and N = 128 instructions cannot keep the tensor pipe full from one CTA)
+  const int bn[3] = {256, 128, 64};
+  const double eff[3] = {1.0, 0.8, 0.55};
+  int best = 256; double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const double cost = (double)ceil_div(Cout, bn[i]) * bn[i] / eff[i];
+    if (cost < best_cost) { best_cost = cost; best = bn[i]; }
+  }
+  return best;
 }
 
 int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
@@ -623,6 +637,7 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
   if (op.mode == MODE_HALO) {
     if (op.bn == 64) return launch_v2<64, 4, 2, 3, 1>(op, st);
     if (op.bn == 128) return launch_v2<128, 2, 2, 4, 2>(op, st);
+    if (op.bn == 256) return launch_v2<256, 1, 2, 4, 1>(op, st);
   }
   return fail("conv_tc: no kernel instance for BN=%d mode=%d", op.bn, op.mode);
 }

@@ -157,30 +157,27 @@ __global__ void maxpool_bwd_kernel(DView x, DView gy, DView add, int has_add, DV
 }
 
 // ------------------------------------------------------------------ bilinear
+// grid: x over (ow, channel group) of one output row, y = b * Hout + oh
 template <typename T>
-__global__ void bilinear_kernel(DView x, DView y, BilinearTables t) {
-  const int G = y.C / 8;
-  const long long total = (long long)y.B * y.H * y.W * G;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    long long r = i / G;
-    const int ow = (int)(r % y.W); r /= y.W;
-    const int oh = (int)(r % y.H);
-    const int b = (int)(r / y.H);
-    const int y0 = t.y0[oh], y1 = t.y1[oh], x0 = t.x0[ow], x1 = t.x1[ow];
-    const float ly = t.ly[oh], lx = t.lx[ow];
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const long long base = (long long)b * x.H;
-    float a[8], bb[8], c[8], d[8], o[8];
-    V8<T>::load(at<T>(x, (base + y0) * x.W + x0, g * 8), a);
-    V8<T>::load(at<T>(x, (base + y0) * x.W + x1, g * 8), bb);
-    V8<T>::load(at<T>(x, (base + y1) * x.W + x0, g * 8), c);
-    V8<T>::load(at<T>(x, (base + y1) * x.W + x1, g * 8), d);
+__global__ void bilinear_kernel(DView x, DView y, BilinearTables t, FastDiv divG, FastDiv divH) {
+  const unsigned G = y.C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)y.W * G) return;
+  unsigned ow, g, b, oh;
+  divG.divmod(idx, ow, g);
+  divH.divmod(blockIdx.y, b, oh);
+  const int y0 = t.y0[oh], y1 = t.y1[oh], x0 = t.x0[ow], x1 = t.x1[ow];
+  const float ly = t.ly[oh], lx = t.lx[ow];
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const long long base = (long long)b * x.H;
+  float a[8], bb[8], c[8], d[8], o[8];
+  V8<T>::load(at<T>(x, (base + y0) * x.W + x0, g * 8), a);
+  V8<T>::load(at<T>(x, (base + y0) * x.W + x1, g * 8), bb);
+  V8<T>::load(at<T>(x, (base + y1) * x.W + x0, g * 8), c);
+  V8<T>::load(at<T>(x, (base + y1) * x.W + x1, g * 8), d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * bb[k]) + ly * (hx * c[k] + lx * d[k]);
-    V8<T>::store(at<T>(y, ((long long)b * y.H + oh) * y.W + ow, g * 8), o);
-  }
+  for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * bb[k]) + ly * (hx * c[k] + lx * d[k]);
+  V8<T>::store(at<T>(y, ((long long)b * y.H + oh) * y.W + ow, g * 8), o);
 }
 // gather form: gx[ih,iw] = sum_{(oh,wy) in rows(ih)} sum_{(ow,wx) in cols(iw)} wy*wx*gy[oh,ow]
 template <typename T>
@@ -466,7 +463,9 @@ void bilinear_axis_tables(int in, int out, BilinearHost* h) {
 int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st) {
   if (!vec_ok(x) || !vec_ok(y) || x.C != y.C || t.Hin != x.H || t.Win != x.W || t.Hout != y.H || t.Wout != y.W)
     return fail("bilinear: bad views/tables");
-  MAU_DISPATCH(dt, bilinear_kernel, grid_for(y.pixels() * (y.C / 8)), 256, 0, st, dv(x), dv(y), t);
+  if ((long long)y.B * y.H > 65535) return fail("bilinear: B*H too large for the row grid");
+  const dim3 grid((unsigned)ceil_div(y.W * (y.C / 8), 256), (unsigned)(y.B * y.H), 1);
+  MAU_DISPATCH(dt, bilinear_kernel, grid, 256, 0, st, dv(x), dv(y), t, FastDiv((unsigned)(y.C / 8)), FastDiv((unsigned)y.H));
   return 0;
 }
 int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables& t, int accumulate,

@@ -55,6 +55,22 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// exact unsigned division by a runtime constant for n < 2^31 (multiply-high + shift)
+struct FastDiv {
+  unsigned d = 1, mul = 0, shr = 0;
+  FastDiv() {}
+  explicit FastDiv(unsigned div) : d(div) {
+    if (div <= 1) { mul = 0; shr = 0; return; }
+    unsigned lg = 0;
+    while ((1u << lg) < div) ++lg;
+    const unsigned long long p = 31 + lg;
+    mul = (unsigned)(((1ull << p) + div - 1) / div);
+    shr = (unsigned)(p - 32);
+  }
+  __device__ __forceinline__ unsigned div(unsigned n) const { return d <= 1 ? n : (__umulhi(n, mul) >> shr); }
+  __device__ __forceinline__ void divmod(unsigned n, unsigned& q, unsigned& r) const { q = div(n); r = n - q * d; }
+};
+
 // device-side view (plain struct, passed by value)
 struct DView {
   void* ptr;

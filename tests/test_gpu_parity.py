@@ -237,7 +237,8 @@ def test_full_width_kat_train_step_fp32(name, golden_dir):
     for k in kat.files:
         if k.startswith("g::"):
             got = dict(m.named_parameters())[k[3:]].grad.cpu().numpy()
-            np.testing.assert_allclose(got, kat[k], rtol=5e-3, atol=5e-6)
+            err = float(np.linalg.norm(got - kat[k]))
+            assert err <= 1e-3 * float(np.linalg.norm(kat[k])) + 2e-6, (k, err, float(np.linalg.norm(kat[k])))
     sd = m.state_dict()
     np.testing.assert_allclose(sd["model.conv0_0.bn1.running_mean"].cpu().numpy(), kat["bn_rm"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(sd["model.conv0_0.bn1.running_var"].cpu().numpy(), kat["bn_rv"], rtol=1e-4, atol=1e-6)
