@@ -138,6 +138,9 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
 int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
                    const float* w_oihw_dev, const float* scale_dev, const float* shift_dev, int relu,
                    int Cout, void* y_dev, int Cout_stride, void* stream);
+/* timing helper (tools/conv_bench.py): bf16 tcgen05 conv, `iters` launches between CUDA events */
+int mau_op_conv3x3_bench(int impl, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
+                         const float* w_oihw_dev, int Cout, void* y_dev, int Cout_stride, int iters, float* ms_out);
 /* dW [Cout,Cin,3,3] fp32 = sum_pixels dy (x) x ; impl 0 = tcgen05, 2 = FFMA */
 int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_dev, int B, int H, int W,
                          int Cin, int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev,

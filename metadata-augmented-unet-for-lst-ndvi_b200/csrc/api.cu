@@ -174,6 +174,38 @@ int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, 
   return rc;
 }
 
+// timing helper for tools/conv_bench.py: prepares once, launches `iters` times between CUDA events
+int mau_op_conv3x3_bench(int impl, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
+                         const float* w_oihw_dev, int Cout, void* y_dev, int Cout_stride, int iters, float* ms_out) {
+  const int Kp = round_up(Cin, 64);
+  std::vector<int> kmap(Kp);
+  for (int i = 0; i < Kp; ++i) kmap[i] = i < Cin ? i : -1;
+  int* kmap_dev = nullptr; void* wp = nullptr;
+  MAU_CUDA(cudaMalloc(&kmap_dev, sizeof(int) * Kp));
+  MAU_CUDA(cudaMemcpy(kmap_dev, kmap.data(), sizeof(int) * Kp, cudaMemcpyHostToDevice));
+  MAU_CUDA(cudaMalloc(&wp, (size_t)2 * 9 * Kp * Cout));
+  const View x = mkview(x_dev, B, H, W, Cin, Cin_stride), y = mkview(y_dev, B, H, W, Cout, Cout_stride);
+  const int zero = 0;
+  ConvTcOp op;
+  const int mode = (impl & 3) == 0 ? MODE_HALO : ((impl & 3) == 1 ? MODE_TAP : MODE_ROW3);
+  int rc = conv_tc_pack_fwd(w_oihw_dev, Cout, Cin, kmap_dev, Kp, wp, 0);
+  if (!rc) rc = conv_tc_prepare(&op, x, 1, &zero, &Cin, wp, Kp, Cout, y, mode, nullptr, nullptr, 1, 0, 0);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 2 && !rc; ++i) rc = conv_tc_launch(op, 0);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < iters && !rc; ++i) rc = conv_tc_launch(op, 0);
+  cudaEventRecord(e1, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms / (iters > 0 ? iters : 1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(kmap_dev); cudaFree(wp);
+  if (!rc && e != cudaSuccess) rc = fail("conv bench failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
 int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_dev, int B, int H, int W, int Cin,
                          int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

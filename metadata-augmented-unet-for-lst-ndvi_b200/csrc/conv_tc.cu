@@ -28,6 +28,7 @@
 #include "ptx.cuh"
 #include "tma.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace mau {
 using namespace ptx;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_const
 constexpr int kHaloBytes = 23040;    // 18 x 10 pixels x 128 B
 constexpr int kHaloStride = 23552;   // padded to a multiple of 1024 B (swizzle atom alignment)
 
-template <int BN, int MT, int NA, int NB, int NSTG>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG>
 struct V2Smem {
   static constexpr int A_STAGE = MT * kHaloStride;
   static constexpr int B_STAGE = BN * 128;
@@ -269,13 +270,14 @@ struct V2Smem {
                                    16 + 2 * BN * sizeof(float);
 };
 
-template <int BN, int MT, int NA, int NB, int NSTG>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmY,
                                                                    const ConvTcParams p) {
-  using S = V2Smem<BN, MT, NA, NB, NSTG>;
-  static_assert(MT * BN == 256, "two accumulator buffers of 256 columns fill the 512 TMEM columns");
+  using S = V2Smem<BN, MT, NBUF, NA, NB, NSTG>;
+  static_assert(NBUF * MT * BN <= 512 && (NBUF == 1 || NBUF == 2), "accumulators must fit the 512 TMEM columns");
+  constexpr int kBufCols = MT * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
         mbar_wait(&tmem_empty[buf], ephase[buf] ^ 1);   // epilogue has drained this accumulator buffer
         ephase[buf] ^= 1;
         tc_fence_after();
-        const uint32_t d0 = tmem_base + buf * 256;
+        const uint32_t d0 = tmem_base + buf * kBufCols;
         for (int chunk = 0; chunk < total_chunks; ++chunk) {
           mbar_wait(&fullA[ra.stage], ra.phase);
           const uint32_t a_stage = smem_u32(sA + ra.stage * S::A_STAGE);
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
           ra.advance(NA);
         }
         umma_commit(&tmem_full[buf]);
-        buf ^= 1;
+        buf = (buf + 1) % NBUF;
       }
     }
   } else if (warp >= 4) {
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
           for (int cb = 0; cb < S::SU / 32; ++cb) {
             uint32_t v[32];
             const int col = u * S::SU + cb * 32;
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + j * BN + col, v);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBufCols + j * BN + col, v);
             tmem_ld_wait();
             uint32_t pk[16];
 #pragma unroll
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
           stg = (stg + 1) % NSTG;
         }
       }
-      buf ^= 1;
+      buf = (buf + 1) % NBUF;
     }
     if (et == 0) tma_wait_group0();
   }
@@ -482,14 +484,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   }
 }
 
-template <int BN, int MT, int NA, int NB, int NSTG>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG>
 int launch_v2(const ConvTcOp& op, cudaStream_t st) {
-  using S = V2Smem<BN, MT, NA, NB, NSTG>;
+  using S = V2Smem<BN, MT, NBUF, NA, NB, NSTG>;
   static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = conv3x3_tc_v2_kernel<BN, MT, NA, NB, NSTG>;
+  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG>;
   if (!attr_done[dev & 15]) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
@@ -577,6 +579,14 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   p = ConvTcParams();
   op->mode = mode;
   op->bn = mode == MODE_HALO ? pick_bn_v2(y.C) : conv_tc_pick_bn(y.C);
+  op->mt = op->bn == 64 ? 4 : (op->bn == 128 ? 2 : 2);
+  op->nbuf = op->bn == 256 ? 1 : 2;
+  if (mode == MODE_HALO) {
+    if (const char* e = getenv("MAU_CONV_CFG")) {      // experiment knob: "bn,mt,nbuf"
+      int a = 0, b = 0, c = 0;
+      if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) { op->bn = a; op->mt = b; op->nbuf = c; }
+    }
+  }
   p.TW = (mode == MODE_TAP) ? 16 : 8;
   p.TH = 128 / p.TW;
   p.tiles_w = ceil_div(y.W, p.TW);
@@ -599,8 +609,7 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   p.total_ptiles = y.B * p.tiles_w * p.tiles_h;
   op->grid = dim3((unsigned)p.total_ptiles, (unsigned)ceil_div(y.C, op->bn), 1);
   if (mode == MODE_HALO) {   // persistent: one CTA per SM (or fewer when there is less work)
-    const int mt = 256 / op->bn;
-    const int items = ceil_div(p.total_ptiles, mt) * ceil_div(y.C, op->bn);
+    const int items = ceil_div(p.total_ptiles, op->mt) * ceil_div(y.C, op->bn);
     int sms = 148;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -635,9 +644,16 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
   MAU_INST(256, MODE_ROW3, 2, 3)
 #undef MAU_INST
   if (op.mode == MODE_HALO) {
-    if (op.bn == 64) return launch_v2<64, 4, 2, 3, 1>(op, st);
-    if (op.bn == 128) return launch_v2<128, 2, 2, 4, 2>(op, st);
-    if (op.bn == 256) return launch_v2<256, 1, 2, 4, 1>(op, st);
+#define MAU_V2(BN_, MT_, NBUF_, NA_, NB_, NSTG_) \
+    if (op.bn == BN_ && op.mt == MT_ && op.nbuf == NBUF_) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_>(op, st);
+    MAU_V2(64, 4, 2, 2, 3, 1)
+    MAU_V2(64, 2, 2, 2, 4, 2)
+    MAU_V2(128, 2, 2, 2, 4, 2)
+    MAU_V2(128, 1, 2, 2, 4, 2)
+    MAU_V2(256, 1, 2, 2, 4, 1)
+    MAU_V2(256, 2, 1, 2, 3, 1)
+#undef MAU_V2
+    return fail("conv_tc: no v2 kernel instance for BN=%d MT=%d NBUF=%d", op.bn, op.mt, op.nbuf);
   }
   return fail("conv_tc: no kernel instance for BN=%d mode=%d", op.bn, op.mode);
 }

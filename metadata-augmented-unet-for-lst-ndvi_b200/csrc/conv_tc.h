@@ -29,6 +29,8 @@ struct ConvTcOp {
   dim3 grid;
   int bn = 0;
   int mode = 0;
+  int mt = 1;      // v2: 128-pixel sub-tiles per work item (share each B tile)
+  int nbuf = 2;    // v2: TMEM accumulator buffers
 };
 
 int conv_tc_pick_bn(int Cout);
