@@ -266,8 +266,9 @@ struct V2Smem {
   static constexpr int SU = BN < 128 ? BN : 128;   // columns staged per TMA-store round
   static constexpr int STG = (SU / 64) * 16384;    // 128 pixels x SU bf16 channels
   static constexpr int kBars = 2 * NA + 2 * NB + 4;
+  static constexpr int kHeadOC = 4;                 // fused 1x1 head: up to 4 output channels
   static constexpr size_t kBytes = 1024 + (size_t)NA * A_STAGE + (size_t)NB * B_STAGE + (size_t)NSTG * STG + 8 * kBars +
-                                   16 + 2 * BN * sizeof(float);
+                                   16 + (2 + (BN <= 128 ? kHeadOC : 0)) * BN * sizeof(float);
 };
 
 template <int BN, int MT, int NBUF, int NA, int NB, int NSTG>
@@ -293,6 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);
   float* s_shift = s_scale + BN;
+  float* s_hw = s_shift + BN;            // [kHeadOC][BN], only when BN <= 128
+  constexpr bool kCanHead = BN <= 128;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_img = p.tiles_w * p.tiles_h;
@@ -318,18 +321,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   for (int s = 0; s < p.nseg; ++s) total_chunks += p.seg_chunks[s];
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      Ring ra, rb;
-      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-        const int n0 = (it / groups) * BN;
-        const int pt0 = (it % groups) * MT;
-        const int nsub = min(MT, total_pt - pt0);
-        int kB = 0;
-        for (int sg = 0; sg < p.nseg; ++sg) {
-          for (int kc = 0; kc < p.seg_chunks[sg]; ++kc, kB += 64) {
-            const int cA = p.seg_start[sg] + kc * 64;
-            mbar_wait(&emptyA[ra.stage], ra.phase ^ 1);
+    // =========================== TMA producer (whole warp converged, one elected lane issues) ==========
+    Ring ra, rb;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int n0 = (it / groups) * BN;
+      const int pt0 = (it % groups) * MT;
+      const int nsub = min(MT, total_pt - pt0);
+      int kB = 0;
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        for (int kc = 0; kc < p.seg_chunks[sg]; ++kc, kB += 64) {
+          const int cA = p.seg_start[sg] + kc * 64;
+          mbar_wait(&emptyA[ra.stage], ra.phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&fullA[ra.stage], nsub * kHaloBytes);
             for (int j = 0; j < nsub; ++j) {
               const int pt = pt0 + j;
@@ -339,58 +342,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
               tma_load_4d(sA + ra.stage * S::A_STAGE + j * kHaloStride, &tmA, &fullA[ra.stage], cA,
                           (rem - th * p.tiles_w) * 8 - 1, th * 16 - 1, b);
             }
-            ra.advance(NA);
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&emptyB[rb.stage], rb.phase ^ 1);
+          }
+          __syncwarp();
+          ra.advance(NA);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&emptyB[rb.stage], rb.phase ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(&fullB[rb.stage], S::B_STAGE);
               tma_load_3d(sB + rb.stage * S::B_STAGE, &tmB, &fullB[rb.stage], kB, n0, tap);
-              rb.advance(NB);
             }
+            __syncwarp();
+            rb.advance(NB);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 0, 0);
-      Ring ra, rb;
-      int buf = 0;
-      uint32_t ephase[2] = {0, 0};
-      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-        const int pt0 = (it % groups) * MT;
-        const int nsub = min(MT, total_pt - pt0);
-        mbar_wait(&tmem_empty[buf], ephase[buf] ^ 1);   // epilogue has drained this accumulator buffer
-        ephase[buf] ^= 1;
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + buf * kBufCols;
-        for (int chunk = 0; chunk < total_chunks; ++chunk) {
-          mbar_wait(&fullA[ra.stage], ra.phase);
-          const uint32_t a_stage = smem_u32(sA + ra.stage * S::A_STAGE);
-          for (int tap = 0; tap < 9; ++tap) {
-            const int r = tap / 3, s = tap - r * 3;
-            mbar_wait(&fullB[rb.stage], rb.phase);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(sB + rb.stage * S::B_STAGE);
-            const uint32_t acc = (chunk | tap) ? 1u : 0u;
-            for (int j = 0; j < nsub; ++j) {
-              const uint32_t a_addr = a_stage + j * kHaloStride + (r * 10 + s) * 128;
+    // =========================== MMA issuer (whole warp converged, one elected lane issues) ============
+    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 0, 0);
+    // descriptor templates: only the 14-bit start-address field changes between MMAs
+    const uint64_t descA0 = smem_desc_sw128(0, 16, 1280, 0);
+    const uint64_t descB0 = smem_desc_sw128(0, 16, 1024, 0);
+    Ring ra, rb;
+    int buf = 0;
+    uint32_t ephase[2] = {0, 0};
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int pt0 = (it % groups) * MT;
+      const int nsub = min(MT, total_pt - pt0);
+      mbar_wait(&tmem_empty[buf], ephase[buf] ^ 1);   // epilogue has drained this accumulator buffer
+      ephase[buf] ^= 1;
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + buf * kBufCols;
+      for (int chunk = 0; chunk < total_chunks; ++chunk) {
+        mbar_wait(&fullA[ra.stage], ra.phase);
+        const uint32_t a_stage = smem_u32(sA + ra.stage * S::A_STAGE);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, s = tap - r * 3;
+          mbar_wait(&fullB[rb.stage], rb.phase);
+          tc_fence_after();
+          const uint64_t db = descB0 + (uint64_t)(smem_u32(sB + rb.stage * S::B_STAGE) >> 4);
+          const uint64_t da = descA0 + (uint64_t)((a_stage + (r * 10 + s) * 128) >> 4);
+          const uint32_t first = (chunk | tap) ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = smem_desc_sw128(a_addr + k * 32, 16, 1280, 0);
-                const uint64_t db = smem_desc_sw128(b_addr + k * 32, 16, 1024, 0);
-                umma_bf16(d0 + j * BN, da, db, idesc, (acc | k) ? 1u : 0u);
+            for (int j = 0; j < MT; ++j) {
+              if (j < nsub) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d0 + j * BN, da + (uint64_t)((j * kHaloStride + k * 32) >> 4), db + (uint64_t)((k * 32) >> 4),
+                            idesc, k ? 1u : first);
               }
             }
             umma_commit(&emptyB[rb.stage]);
-            rb.advance(NB);
+            if (tap == 8) umma_commit(&emptyA[ra.stage]);
+            if (tap == 8 && chunk == total_chunks - 1) umma_commit(&tmem_full[buf]);
           }
-          umma_commit(&emptyA[ra.stage]);
-          ra.advance(NA);
+          __syncwarp();
+          rb.advance(NB);
         }
-        umma_commit(&tmem_full[buf]);
-        buf = (buf + 1) % NBUF;
+        ra.advance(NA);
       }
+      buf = (buf + 1) % NBUF;
     }
   } else if (warp >= 4) {
     // =========================== epilogue ===========================
@@ -410,6 +423,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
           const bool ok = c < p.Cout;
           s_scale[i] = ok ? (p.scale ? p.scale[c] : 1.f) : 0.f;
           s_shift[i] = ok ? (p.shift ? p.shift[c] : 0.f) : 0.f;
+          if (kCanHead && p.head_out)
+            for (int o = 0; o < S::kHeadOC; ++o) s_hw[o * BN + i] = (ok && o < p.head_oc) ? p.head_w[o * p.Cout + c] : 0.f;
         }
         named_bar_sync(1, 128);
         cur_n0 = n0;
@@ -423,13 +438,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
         const int rem = pt - b * tiles_img;
         const int th = rem / p.tiles_w;
         const int w0 = (rem - th * p.tiles_w) * 8, h0 = th * 16;
+        float hacc[S::kHeadOC] = {0.f, 0.f, 0.f, 0.f};
+        const bool do_head = kCanHead && p.head_out != nullptr;
 #pragma unroll 1
         for (int u = 0; u < BN / S::SU; ++u) {          // store rounds of SU columns
           uint8_t* sbuf = sStg + stg * S::STG;
           const bool last = (j == nsub - 1) && (u == BN / S::SU - 1);
           // the TMA store that last read this staging buffer must have finished reading it
-          if (et == 0) { if (NSTG == 1) tma_wait_group_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-          named_bar_sync(1, 128);
+          if (p.store_y) {
+            if (et == 0) { if (NSTG == 1) tma_wait_group_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+            named_bar_sync(1, 128);
+          }
 #pragma unroll 1
           for (int cb = 0; cb < S::SU / 32; ++cb) {
             uint32_t v[32];
@@ -445,31 +464,53 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
               if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
               __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
               pk[jj] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            uint8_t* rowp = sbuf + (cb >> 1) * 16384 + m * 128;
+              if (kCanHead && do_head) {          // the head sees the bf16-rounded activation, like the unfused path
+                const float r0 = __low2float(h2), r1 = __high2float(h2);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int chunk16 = (cb & 1) * 4 + jj;
-              *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (m & 7)) << 4)) =
-                  make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+                for (int o = 0; o < S::kHeadOC; ++o)
+                  hacc[o] = fmaf(r1, s_hw[o * BN + c + 1], fmaf(r0, s_hw[o * BN + c], hacc[o]));
+              }
+            }
+            if (p.store_y) {
+              uint8_t* rowp = sbuf + (cb >> 1) * 16384 + m * 128;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int chunk16 = (cb & 1) * 4 + jj;
+                *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (m & 7)) << 4)) =
+                    make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+              }
             }
           }
           if (last) tc_fence_before();   // all TMEM reads of this buffer are complete (wait::ld above)
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          if (p.store_y) fence_proxy_async_smem();
+          if (p.store_y || last) named_bar_sync(1, 128);
           if (et == 0) {
             if (last) mbar_arrive(&tmem_empty[buf]);   // hand the accumulator buffer back to the MMA warp
+            if (p.store_y) {
 #pragma unroll 1
-            for (int g = 0; g < S::SU / 64; ++g) {
-              const int c = n0 + u * S::SU + g * 64;
-              if (c < p.Cout) {
-                if (p.accumulate) tma_reduce_add_4d(&tmY, sbuf + g * 16384, c, w0, h0, b);
-                else              tma_store_4d(&tmY, sbuf + g * 16384, c, w0, h0, b);
+              for (int g = 0; g < S::SU / 64; ++g) {
+                const int c = n0 + u * S::SU + g * 64;
+                if (c < p.Cout) {
+                  if (p.accumulate) tma_reduce_add_4d(&tmY, sbuf + g * 16384, c, w0, h0, b);
+                  else              tma_store_4d(&tmY, sbuf + g * 16384, c, w0, h0, b);
+                }
               }
+              tma_commit_group();
             }
-            tma_commit_group();
           }
-          stg = (stg + 1) % NSTG;
+          if (p.store_y) stg = (stg + 1) % NSTG;
+        }
+        if (kCanHead && do_head) {
+          const int h = h0 + (m >> 3), w = w0 + (m & 7);
+          if (h < p.H && w < p.W) {
+#pragma unroll
+            for (int o = 0; o < S::kHeadOC; ++o)
+              if (o < p.head_oc) {
+                float v = hacc[o] + p.head_b[o];
+                if (p.head_tanh && o == 0) v = tanhf(v);
+                p.head_out[(((long long)b * p.head_oc + o) * p.H + h) * p.W + w] = v;
+              }
+          }
         }
       }
       buf = (buf + 1) % NBUF;
@@ -606,6 +647,7 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   p.halo_base_offset = halo_base_offset;
   p.scale = scale;
   p.shift = shift;
+  p.H = y.H; p.W = y.W;
   p.total_ptiles = y.B * p.tiles_w * p.tiles_h;
   op->grid = dim3((unsigned)p.total_ptiles, (unsigned)ceil_div(y.C, op->bn), 1);
   if (mode == MODE_HALO) {   // persistent: one CTA per SM (or fewer when there is less work)

@@ -21,6 +21,10 @@ struct ConvTcParams {
   int halo_base_offset = 0;      // MODE_HALO: fill the descriptor base_offset field from the address
   const float* scale = nullptr;  // per output channel (nullptr -> 1)
   const float* shift = nullptr;  // per output channel (nullptr -> 0)
+  // optional fused 1x1 head (eval, single output-channel tile): out[b,o,h,w] = act(sum_c y[c]*head_w[o][c] + head_b[o])
+  const float* head_w = nullptr; const float* head_b = nullptr; float* head_out = nullptr;
+  int head_oc = 0, head_tanh = 0, H = 0, W = 0;
+  int store_y = 1;               // 0: skip the activation store (only the fused head output is needed)
 };
 
 struct ConvTcOp {

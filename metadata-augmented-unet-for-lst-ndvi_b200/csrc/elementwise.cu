@@ -24,30 +24,35 @@ __device__ __forceinline__ T* at(const DView& v, long long pix, int c) {
 }
 
 // ------------------------------------------------------------------ layout
-// x [B][C][P] fp32 -> y [B][P][cs] (T), P = H*W.  32x32 smem transpose tiles.
+// x [B][C][P] fp32 -> y [B][P][cs] (T), P = H*W.  Tiles of 64 pixels x 32 channels through shared
+// memory: coalesced 128-byte reads along P, 8-channel vector stores along C (pad channels up to the
+// view's 8-multiple are written as zeros).
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int P, DView y) {
-  __shared__ float tile[32][33];
-  const int p_tiles = (P + 31) / 32, c_tiles = (C + 31) / 32;
+  __shared__ float tile[32][65];
+  const int p_tiles = (P + 63) / 64, c_tiles = (C + 31) / 32;
   const long long total = (long long)B * p_tiles * c_tiles;
+  const int C8 = (C + 7) & ~7;
   for (long long t = blockIdx.x; t < total; t += gridDim.x) {
     const int ct = (int)(t % c_tiles);
     const long long r = t / c_tiles;
     const int pt = (int)(r % p_tiles);
     const int b = (int)(r / p_tiles);
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     __syncthreads();
-    for (int j = ty; j < 32; j += 8) {
-      const int c = ct * 32 + j, p = pt * 32 + tx;
-      tile[j][tx] = (c < C && p < P) ? x[((long long)b * C + c) * P + p] : 0.f;
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int j = i >> 6, px = i & 63;
+      const int c = ct * 32 + j, p = pt * 64 + px;
+      tile[j][px] = (c < C && p < P) ? x[((long long)b * C + c) * P + p] : 0.f;
     }
     __syncthreads();
-    for (int j = ty; j < 32; j += 8) {
-      const int p = pt * 32 + j, c = ct * 32 + tx;
-      if (p < P && c < C) {
-        T* dst = at<T>(y, (long long)b * P + p, c);
-        if constexpr (sizeof(T) == 2) *dst = __float2bfloat16_rn(tile[tx][j]);
-        else *dst = tile[tx][j];
+    {
+      const int px = threadIdx.x >> 2, cg = threadIdx.x & 3;     // 64 pixels x 4 groups of 8 channels
+      const int p = pt * 64 + px, c = ct * 32 + cg * 8;
+      if (p < P && c < C8 && c + 8 <= y.cs - y.c0) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = tile[cg * 8 + k][px];
+        V8<T>::store(at<T>(y, (long long)b * P + p, c), v);
       }
     }
   }
@@ -157,17 +162,26 @@ __global__ void maxpool_bwd_kernel(DView x, DView gy, DView add, int has_add, DV
 }
 
 // ------------------------------------------------------------------ bilinear
-// grid: x over (ow, channel group) of one output row, y = b * Hout + oh
+// grid: x over (ow, channel group) of one output row, y = b * Hout + oh.  Source index and lambda are
+// recomputed with the same fp32 operations ATen uses (scale * dst, truncation), so no table loads sit
+// in front of the data loads.
+__device__ __forceinline__ void src_index(float scale, int o, int in_size, int& i0, int& i1, float& l1) {
+  const float real = __fmul_rn(scale, (float)o);
+  i0 = min((int)real, in_size - 1);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = fminf(fmaxf(__fsub_rn(real, (float)i0), 0.f), 1.f);
+}
 template <typename T>
-__global__ void bilinear_kernel(DView x, DView y, BilinearTables t, FastDiv divG, FastDiv divH) {
+__global__ void bilinear_kernel(DView x, DView y, float sy, float sx, FastDiv divG, FastDiv divH) {
   const unsigned G = y.C / 8;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (unsigned)y.W * G) return;
   unsigned ow, g, b, oh;
   divG.divmod(idx, ow, g);
   divH.divmod(blockIdx.y, b, oh);
-  const int y0 = t.y0[oh], y1 = t.y1[oh], x0 = t.x0[ow], x1 = t.x1[ow];
-  const float ly = t.ly[oh], lx = t.lx[ow];
+  int y0, y1, x0, x1; float ly, lx;
+  src_index(sy, (int)oh, x.H, y0, y1, ly);
+  src_index(sx, (int)ow, x.W, x0, x1, lx);
   const float hy = 1.f - ly, hx = 1.f - lx;
   const long long base = (long long)b * x.H;
   float a[8], bb[8], c[8], d[8], o[8];
@@ -413,7 +427,8 @@ inline bool vec_ok(const View& v) { return v.cs % 8 == 0 && v.c0 % 8 == 0 && v.C
 
 int op_nchw_to_nhwc(int dt, const float* x, int B, int C, int H, int W, const View& y, cudaStream_t st) {
   const int P = H * W;
-  const long long tiles = (long long)B * ceil_div(P, 32) * ceil_div(C, 32);
+  if (y.cs % 8 || y.c0 % 8) return fail("nchw_to_nhwc: destination must be 8-channel aligned");
+  const long long tiles = (long long)B * ceil_div(P, 64) * ceil_div(C, 32);
   MAU_DISPATCH(dt, nchw_to_nhwc_kernel, grid_for(tiles, 1, 16), 256, 0, st, x, B, C, P, dv(y));
   return 0;
 }
@@ -465,7 +480,9 @@ int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, c
     return fail("bilinear: bad views/tables");
   if ((long long)y.B * y.H > 65535) return fail("bilinear: B*H too large for the row grid");
   const dim3 grid((unsigned)ceil_div(y.W * (y.C / 8), 256), (unsigned)(y.B * y.H), 1);
-  MAU_DISPATCH(dt, bilinear_kernel, grid, 256, 0, st, dv(x), dv(y), t, FastDiv((unsigned)(y.C / 8)), FastDiv((unsigned)y.H));
+  const float sy = y.H > 1 ? (float)(x.H - 1) / (float)(y.H - 1) : 0.f;     // area_pixel_compute_scale, align_corners
+  const float sx = y.W > 1 ? (float)(x.W - 1) / (float)(y.W - 1) : 0.f;
+  MAU_DISPATCH(dt, bilinear_kernel, grid, 256, 0, st, dv(x), dv(y), sy, sx, FastDiv((unsigned)(y.C / 8)), FastDiv((unsigned)y.H));
   return 0;
 }
 int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables& t, int accumulate,

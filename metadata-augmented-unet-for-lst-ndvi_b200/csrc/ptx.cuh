@@ -160,6 +160,18 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_major,
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// one elected lane of a fully converged warp (keeps the surrounding code warp-uniform so that ptxas
+// holds descriptors in uniform registers instead of wrapping every UTCHMMA / UTMALDG in an election loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -72,13 +72,14 @@ __global__ void __launch_bounds__(kThreads) wgrad3x3_tc_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int b = t / tiles_img;
-        const int rem = t - b * tiles_img;
-        const int h0 = (rem / p.tiles_w) * 8, w0 = (rem % p.tiles_w) * 8;
-        mbar_wait(&empty[stage], phase ^ 1);
+    // TMA producer: whole warp converged, one elected lane issues
+    int stage = 0; uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int b = t / tiles_img;
+      const int rem = t - b * tiles_img;
+      const int h0 = (rem / p.tiles_w) * 8, w0 = (rem % p.tiles_w) * 8;
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full[stage], kStageBytes);
         uint8_t* s = smem + stage * kStageBytes;
         tma_load_4d(s, &tmDy, &full[stage], co0, w0, h0, b);
@@ -86,32 +87,36 @@ __global__ void __launch_bounds__(kThreads) wgrad3x3_tc_kernel(const __grid_cons
 #pragma unroll
         for (int sx = 0; sx < 3; ++sx)
           tma_load_4d(s + (2 + sx) * kBox, &tmX, &full[stage], ci0, w0 + sx - 1, h0 + r - 1, b);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(128, 64, /*a MN-major*/ 1, /*b MN-major*/ 1);
-      int stage = 0; uint32_t phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+    // MMA issuer: whole warp converged, one elected lane issues
+    constexpr uint32_t idesc = idesc_bf16_f32(128, 64, /*a MN-major*/ 1, /*b MN-major*/ 1);
+    const uint64_t desc0 = smem_desc_sw128(0, /*LBO: next 64 channels*/ kBox, /*SBO*/ 1024, 0);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+      const uint64_t da = desc0 + (uint64_t)(sa >> 4);
+      const uint32_t first = t > t_begin ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
         for (int sx = 0; sx < 3; ++sx) {
-          const uint32_t sb = sa + (2 + sx) * kBox;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {   // 16 pixels (two 8-row K groups) per instruction
-            const uint64_t da = smem_desc_sw128(sa + kk * 2048, /*LBO: next 64 co*/ kBox, /*SBO*/ 1024, 0);
-            const uint64_t db = smem_desc_sw128(sb + kk * 2048, kBox, 1024, 0);
-            umma_bf16(tmem_base + sx * 64, da, db, idesc, (t > t_begin || kk > 0) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < 4; ++kk)   // 16 pixels (two 8-row K groups) per instruction
+            umma_bf16(tmem_base + sx * 64, da + (uint64_t)((kk * 2048) >> 4),
+                      da + (uint64_t)(((2 + sx) * kBox + kk * 2048) >> 4), idesc, kk ? 1u : first);
         }
         umma_commit(&empty[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (t == t_end - 1) umma_commit(tmem_full);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    if (t_end <= t_begin && elect_one()) umma_commit(tmem_full);
   } else if (warp >= 4) {
     if (t_end > t_begin) {
       mbar_wait(tmem_full, 0);

@@ -210,7 +210,10 @@ def test_full_width_kat_eval(name, precision, golden_dir):
 
 @pytest.mark.parametrize("name", ["unet_noemb", "unet_metaemb", "unet_emb", "unetpp_emb"])
 def test_full_width_kat_train_step_fp32(name, golden_dir):
-    """fwd (batch-stat BN) + loss + bwd in fp32 mode against the reference's own gradients."""
+    """fwd (batch-stat BN) + loss + bwd in fp32 mode against the reference's own gradients.  The golden
+    gradients come from another machine's oneDNN summation order and this 2x50x50 case has only 18
+    samples per channel at the bottleneck BatchNorm, so per-tensor agreement is asserted at 3e-2 here;
+    the tight (2e-3) gradient check is test_train_step_fp32_against_oracle, on the same machine."""
     mt, T, kw = VARIANTS[name]
     kat = np.load(os.path.join(golden_dir, f"kat_{name}.npz"))
     torch.manual_seed(42)
@@ -235,17 +238,52 @@ def test_full_width_kat_train_step_fp32(name, golden_dir):
         if want[n] < 1e-5:      # conv bias in front of BatchNorm: analytically zero, the reference holds round-off
             assert gn < 1e-4, (n, gn, want[n])
         else:
-            assert abs(gn - want[n]) <= 5e-3 * want[n], (n, gn, want[n])
+            assert abs(gn - want[n]) <= 3e-2 * want[n], (n, gn, want[n])
     assert abs(total ** 0.5 - float(kat["grad_l2"])) < 1e-3 * float(kat["grad_l2"])
     for k in kat.files:
         if k.startswith("g::"):
             got = dict(m.named_parameters())[k[3:]].grad.cpu().numpy()
             err = float(np.linalg.norm(got - kat[k]))
-            assert err <= 1e-3 * float(np.linalg.norm(kat[k])) + 2e-6, (k, err, float(np.linalg.norm(kat[k])))
+            assert err <= 3e-2 * float(np.linalg.norm(kat[k])) + 2e-6, (k, err, float(np.linalg.norm(kat[k])))
     sd = m.state_dict()
     np.testing.assert_allclose(sd["model.conv0_0.bn1.running_mean"].cpu().numpy(), kat["bn_rm"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(sd["model.conv0_0.bn1.running_var"].cpu().numpy(), kat["bn_rv"], rtol=1e-4, atol=1e-6)
     assert int(sd["model.conv0_0.bn1.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("small", [True, False])
+@pytest.mark.parametrize("name", ["unet_noemb", "unet_metaemb", "unet_emb", "unetpp_emb"])
+def test_train_step_fp32_against_oracle(name, small):
+    """Every parameter gradient, the loss, the training-mode output and the BatchNorm side effects of one
+    step, fp32 mode vs the oracle evaluated on this machine."""
+    mt, T, kw = VARIANTS[name]
+    if small:
+        torch.manual_seed(123)
+        m = mau_b200.UrbanPredictor(mt, 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw)
+        x, ts, md, tgt = O.synthetic_batch(3, 37, 45, T=40, seed=1004)
+    else:
+        torch.manual_seed(42)
+        m = mau_b200.UrbanPredictor(mt, 23, 828, 64, 8, 64, 96, 2, **kw)
+        x, ts, md, tgt = O.synthetic_batch(4, 64, 64, T=min(T, 120), seed=1005)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda().set_precision("fp32").train()
+    out = m(x.cuda(), ts.cuda(), md.cuda())
+    loss = engine.compute_loss_l1_grad(out, tgt.cuda(), 0.1)["total"]
+    loss.backward()
+    torch.cuda.synchronize()
+    oref, lref, grads, new_stats = O.train_step_grads(sd, mt, x, ts, md, tgt, loss="l1_grad", **kw)
+    assert rel(out.detach(), oref) < 2e-5
+    assert abs(float(loss) - float(lref)) < 1e-5 * abs(float(lref)) + 1e-7
+    for n, p in m.named_parameters():
+        if grads[n] is None:
+            assert p.grad is None, n
+            continue
+        gn = float(grads[n].norm())
+        err = float((p.grad.cpu() - grads[n]).norm())
+        assert err <= 2e-3 * gn + 1e-6, (n, err, gn)
+    sdn = m.state_dict()
+    for k, v in new_stats.items():
+        assert rel(sdn[k], v) < 1e-4 if v.is_floating_point() else int(sdn[k]) == int(v), k
 
 
 @pytest.mark.parametrize("name", ["unet_metaemb", "unetpp_emb"])
