@@ -95,6 +95,11 @@ int mau_plan_forward(mau_plan* plan, void* const* state_dev, const float* maps_d
                      const float* temp_series_dev, const float* metadata_dev, float* out_dev,
                      void* stream);
 
+/* optional eval-mode hint: a number that changes whenever any state tensor is modified (e.g. the sum
+ * of torch's tensor._version counters).  While it -- and every state pointer -- is unchanged between
+ * forwards, the packed bf16 weights and folded BatchNorm vectors are reused; 0 = always re-pack. */
+int mau_plan_set_state_version(mau_plan* plan, uint64_t version);
+
 /* --- backward: replaces `loss.backward()` through the model (src/train.py:252) -------------
  * grad_out_dev: dL/d out, same shape as out.  grads_dev[i]: where to write dL/d state[i]
  * (fp32, same shape), or NULL to skip; entries for unused / non-parameter state must be NULL.

@@ -90,6 +90,12 @@ int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* gr
   return plan->impl.run_backward(c);
 }
 
+int mau_plan_set_state_version(mau_plan* plan, uint64_t version) {
+  if (!plan) return fail("null plan");
+  plan->impl.state_version = version;
+  return 0;
+}
+
 int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user) {
   if (!plan) return fail("null plan");
   plan->impl.hook = fn; plan->impl.hook_user = user;

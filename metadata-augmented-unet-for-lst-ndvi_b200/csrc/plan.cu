@@ -172,16 +172,23 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
   const long long count = (long long)cfg.batch * L->H * L->W;
   op.run = [this, L, training, count](Ctx& c) -> int {
     const int C = L->Cout;
-    if (use_tc) MAU_TRY(conv_tc_pack_fwd(c.f(L->iw), C, L->Cin, L->kmap, L->Kp, L->wpack, c.st));
-    else MAU_TRY(conv_ffma_pack_fwd(c.f(L->iw), C, L->Cin, L->kmap, L->Kp, static_cast<float*>(L->wpack), c.st));
+    if (!skip_pack) {
+      if (use_tc) MAU_TRY(conv_tc_pack_fwd(c.f(L->iw), C, L->Cin, L->kmap, L->Kp, L->wpack, c.st));
+      else MAU_TRY(conv_ffma_pack_fwd(c.f(L->iw), C, L->Cin, L->kmap, L->Kp, static_cast<float*>(L->wpack), c.st));
+    }
     const float* scale = nullptr; const float* shift = c.f(L->ib); int relu = 0;
     if (!training) {
-      MAU_TRY(op_bn_fold_eval(c.f(L->igamma), c.f(L->ibeta), c.f(L->irm), c.f(L->irv), c.f(L->ib), C, kBnEps,
-                              L->scale, L->shift, c.st));
+      if (!skip_pack)
+        MAU_TRY(op_bn_fold_eval(c.f(L->igamma), c.f(L->ibeta), c.f(L->irm), c.f(L->irv), c.f(L->ib), C, kBnEps,
+                                L->scale, L->shift, c.st));
       scale = L->scale; shift = L->shift; relu = 1;
     }
     if (use_tc) {
       L->tc.p.scale = scale; L->tc.p.shift = shift; L->tc.p.relu = relu;
+      if (L->head_w >= 0) {       // fused 1x1 head: the activation itself is never stored
+        L->tc.p.head_w = c.f(L->head_w); L->tc.p.head_b = c.f(L->head_b); L->tc.p.head_out = c.out;
+        L->tc.p.head_oc = L->head_oc; L->tc.p.head_tanh = L->head_tanh; L->tc.p.store_y = 0;
+      }
       MAU_TRY(conv_tc_launch(L->tc, c.st));
     } else {
       L->ff.scale = scale; L->ff.shift = shift; L->ff.relu = relu;
@@ -506,6 +513,7 @@ int Plan::build_unet() {
   };
 
   const int zero = 0;
+  std::vector<ConvLayer*> last_block;
   // encoder
   for (int l = 0; l < 4; ++l) {
     const int src = l == 0 ? in0 : pooled[l];
@@ -525,13 +533,17 @@ int Plan::build_unet() {
     MAU_TRY(add_up(lower, TRef{cat[l], F[l], F[l + 1]}));
     const int cin = F[l] + F[l + 1];
     MAU_TRY(add_vgg("conv" + std::to_string(l) + "_1", dec[l], cat[l], 1, &zero, &cin, F[l], TRef{xdec[l], 0, F[l]}, true,
-                    nullptr));
+                    l == 0 ? &last_block : nullptr));
   }
   // head
   const TRef hx{xdec[0], 0, F[0]};
   const int OC = cfg.out_channels;
   fwd_flops += 2.0 * OC * F[0] * (double)Hs[0] * Ws[0] * B;
-  if (!dry) {
+  const bool fuse_head = !cfg.training && use_tc && conv_mode == MODE_HALO && OC <= 4 && F[0] <= 128 && !dry;
+  if (fuse_head) {
+    ConvLayer* L = last_block[1];
+    L->head_w = fw; L->head_b = fb; L->head_oc = OC; L->head_tanh = OC == 2;
+  } else if (!dry) {
     float* out_save = cfg.training ? static_cast<float*>(alloc(sizeof(float) * (size_t)B * OC * Hs[0] * Ws[0])) : nullptr;
     Op op; op.name = "head";
     const View vx = view(hx);
@@ -674,12 +686,13 @@ int Plan::build_unetpp() {
     if (l > 0) MAU_TRY(add_pool(xref(l - 1, 0), TRef{pooled[l], 0, F[l - 1]}));
     return add_vgg("conv" + std::to_string(l) + "_0", blk[l][0], src, 1, &zero, &cin, F[l], xref(l, 0), l > 0, nullptr);
   };
+  std::vector<ConvLayer*> last_block;
   auto node = [&](int l, int j) -> int {     // x_l_j, j >= 1
     MAU_TRY(add_up(xref(l + 1, j - 1), upref(l, j)));
     const int ss[3] = {0, upref(l, j).c0, embref(l).c0};
     const int sl[3] = {j * F[l], F[l + 1], E};
     return add_vgg("conv" + std::to_string(l) + "_" + std::to_string(j), blk[l][j], lv[l], 3, ss, sl, F[l], xref(l, j),
-                   true, nullptr);
+                   true, (l == 0 && j == 4) ? &last_block : nullptr);
   };
   // reference evaluation order, src/model.py:129-177
   MAU_TRY(encoder(0)); MAU_TRY(encoder(1)); MAU_TRY(node(0, 1));
@@ -690,7 +703,12 @@ int Plan::build_unetpp() {
   const int OC = cfg.out_channels;
   const size_t osz = (size_t)B * OC * Hs[0] * Ws[0];
   fwd_flops += nheads * 2.0 * OC * F[0] * (double)Hs[0] * Ws[0] * B;
-  if (!dry) {
+  const bool fuse_head = !cfg.training && !cfg.deep_supervision && use_tc && conv_mode == MODE_HALO && OC <= 4 &&
+                         F[0] <= 128 && !dry;
+  if (fuse_head) {
+    ConvLayer* L = last_block[1];
+    L->head_w = fw[0]; L->head_b = fb[0]; L->head_oc = OC; L->head_tanh = OC == 2;
+  } else if (!dry) {
     float* out_save = cfg.training ? static_cast<float*>(alloc(sizeof(float) * osz * nheads)) : nullptr;
     for (int i = 0; i < nheads; ++i) {
       const TRef hx = cfg.deep_supervision ? xref(0, i + 1) : xref(0, 4);
@@ -807,7 +825,9 @@ static int run_ops(Plan* P, std::vector<Op>& ops, Ctx& c, bool backward) {
 }
 
 int Plan::run_forward(Ctx& c) {
+  skip_pack = !cfg.training && state_version != 0 && state_version == packed_version && packed_state == last_state;
   MAU_TRY(run_ops(this, fwd, c, false));
+  if (!cfg.training) { packed_version = state_version; packed_state = last_state; }
   if (cfg.training && !counters_host.empty()) {
     std::vector<long long*> ptrs;
     for (long long* idx : counters_host) ptrs.push_back(static_cast<long long*>(c.state[(intptr_t)idx]));

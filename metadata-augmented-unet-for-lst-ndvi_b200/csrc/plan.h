@@ -62,6 +62,7 @@ struct ConvLayer {
   int zbuf = -1;            // training: pre-BN conv output (later overwritten by dz)
   bool input_needs_grad = true;
   double flops = 0;
+  int head_w = -1, head_b = -1, head_oc = 0, head_tanh = 0;   // eval: 1x1 head fused into this conv's epilogue
   // device scratch
   int* kmap = nullptr;
   void* wpack = nullptr;
@@ -96,6 +97,10 @@ class Plan {
   std::vector<long long*> counters_host; long long** counters_dev = nullptr;
   std::string describe_json;
   std::vector<void*> last_state; const float* last_series = nullptr; const float* last_md = nullptr;
+  // eval-mode weight cache: packed weights / folded BN are reused while the caller's state is unchanged
+  unsigned long long state_version = 0, packed_version = 0;
+  std::vector<void*> packed_state;
+  bool skip_pack = false;
 
   ~Plan();
   int build();

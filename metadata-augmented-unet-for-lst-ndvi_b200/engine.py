@@ -46,7 +46,7 @@ _lib_lock = threading.Lock()
 EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
-    "mau_plan_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook",
+    "mau_plan_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_state_version",
     "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics",
     "mau_op_conv3x3", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
@@ -81,6 +81,7 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.mau_plan_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         L.mau_plan_set_grad_hook.argtypes = [C.c_void_p, GRAD_HOOK, C.c_void_p]
+        L.mau_plan_set_state_version.argtypes = [C.c_void_p, C.c_uint64]
         L.mau_plan_profile.argtypes = [C.c_void_p, C.c_int]
         L.mau_plan_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_float),
                                             C.c_int, C.POINTER(C.c_int)]
@@ -209,6 +210,9 @@ class Plan:
 
     def forward(self, state, maps, series, md, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         self._check_state(state)
+        if not self.cfg.get("training"):
+            # 1 + sum of in-place modification counters: unchanged state => packed weights are reused
+            lib().mau_plan_set_state_version(self._h, 1 + sum(t._version for t in state))
         if out is None:
             out = torch.empty(self.out_shape, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):

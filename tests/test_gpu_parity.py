@@ -339,3 +339,25 @@ def test_state_dict_roundtrip_on_device(tmp_path):
     x, ts, md, _ = O.synthetic_batch(2, 40, 40, T=8, seed=9)
     with torch.no_grad():
         assert torch.equal(a(x.cuda(), ts.cuda(), md.cuda()), b(x.cuda(), ts.cuda(), md.cuda()))
+
+
+def test_eval_weight_cache_is_invalidated_by_inplace_updates():
+    """Packed weights are reused across eval forwards only while no state tensor was modified."""
+    kw = dict(temporal_embeddings=False, metadata_embeddings=True)
+    torch.manual_seed(5)
+    m = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw).cuda().eval()
+    x, ts, md, _ = O.synthetic_batch(2, 40, 40, T=8, seed=9)
+    x, ts, md = x.cuda(), ts.cuda(), md.cuda()
+    with torch.no_grad():
+        y0 = m(x, ts, md).clone()
+        y1 = m(x, ts, md).clone()                     # cached pack
+        assert torch.equal(y0, y1)
+        m.model.conv0_1.conv2.weight.mul_(1.5)        # in-place update (what an optimizer step does)
+        y2 = m(x, ts, md).clone()
+        assert not torch.equal(y0, y2)
+        m.model.conv0_1.conv2.weight.div_(1.5)
+        m.model.final.bias.add_(0.25)
+        y3 = m(x, ts, md)
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    ref = O.forward(sd, "unet", x.cpu(), ts.cpu(), md.cpu(), training=False, **kw)
+    assert rel(y3, ref) < 1e-2
