@@ -257,6 +257,9 @@ class HotPathFn(torch.autograd.Function):
     def forward(ctx, plan: Plan, state, diff_idx, dp, maps, series, md, *diff_params):
         out = plan.forward(state, maps, series, md)
         ctx.plan, ctx.diff_idx, ctx.n_state, ctx.dp = plan, diff_idx, len(state), dp
+        # backward re-reads the series (LSTM BPTT) and the metadata (MLP) through the raw pointers the
+        # plan kept from this forward: keep the tensors alive until then
+        ctx.keep_alive = (maps, series, md, state)
         ctx.shapes = [p.shape for p in diff_params]
         return out
 

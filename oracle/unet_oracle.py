@@ -266,6 +266,8 @@ def train_step_grads(sd, model_type, maps, series, md, tgt, loss="l1", lambda_gr
     out = forward(full, model_type, maps, series, md, training=True, new_stats=new_stats, **kw)
     if loss == "l1":
         lv = F.l1_loss(out, tgt)
+    elif loss == "mse":
+        lv = F.mse_loss(out, tgt)
     elif loss == "abs_mean":
         lv = out.abs().mean()
     elif loss == "l1_grad":

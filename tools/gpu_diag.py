@@ -213,7 +213,7 @@ def _model_case(variant, small, training, precision, flags=0, B=2, HW=(37, 45), 
         if e > worst:
             worst, worst_name = e, n
     errs.sort(reverse=True)
-    res["grad_top5"] = [(round(e, 4), n) for e, n in errs[:5]]
+    res["grad_top5"] = [(round(e, 5), n) for e, n in errs[:12]]
     res["grad_median"] = errs[len(errs) // 2][0]
     res["grad_worst"] = worst
     res["grad_worst_name"] = worst_name
@@ -260,6 +260,10 @@ def run_group(name):
     if name == "model_eval": return g_model(False, "bf16", 0, 3e-2)
     if name == "model_train_ffma": return g_model(True, "fp32", 0, 1e-4)
     if name == "model_train": return g_model(True, "bf16", 0, 3e-2)
+    if name == "model_train_full_fp32":
+        return g_model(True, "fp32", 0, 1e-4, names=("unet_noemb", "unet_meta", "unet_emb"), small=False, B=4, HW=(64, 64), T=60)
+    if name == "model_train_full_fp32_b2":
+        return g_model(True, "fp32", 0, 1e-4, names=("unet_meta",), small=False, B=2, HW=(50, 50), T=60)
     if name == "model_train_bf16_ffma": return g_model(True, "bf16", 4, 3e-2)
     if name == "model_train_full":
         return g_model(True, "bf16", 0, 3e-2, names=("unet_meta", "unetpp"), small=False, B=4, HW=(64, 64), T=60)
