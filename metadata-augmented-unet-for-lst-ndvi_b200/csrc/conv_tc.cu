@@ -620,8 +620,8 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   p = ConvTcParams();
   op->mode = mode;
   op->bn = mode == MODE_HALO ? pick_bn_v2(y.C) : conv_tc_pick_bn(y.C);
-  op->mt = op->bn == 64 ? 4 : (op->bn == 128 ? 2 : 2);
-  op->nbuf = op->bn == 256 ? 1 : 2;
+  op->mt = op->bn == 64 ? 4 : (op->bn == 128 ? 2 : 1);     // measured best per width (tools/conv_bench.py)
+  op->nbuf = 2;
   if (mode == MODE_HALO) {
     if (const char* e = getenv("MAU_CONV_CFG")) {      // experiment knob: "bn,mt,nbuf"
       int a = 0, b = 0, c = 0;
