@@ -5,6 +5,7 @@
 // shared memory, one double-precision atomic per channel per block.
 #include "ops.h"
 #include "vec.cuh"
+#include <algorithm>
 
 namespace mau {
 namespace {
@@ -85,27 +86,36 @@ __global__ void bn_finalize_train_kernel(const double* sums, long long count, co
   rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
 }
 
+// block = G channel groups x L pixel lanes (like channel_reduce); per-channel coefficients live in
+// registers for the whole pixel loop
 template <typename T>
-__global__ void bn_apply_relu_kernel(DView z, const float* __restrict__ scale, const float* __restrict__ shift,
-                                     DView y) {
+__global__ void __launch_bounds__(256) bn_apply_relu_kernel(DView z, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, DView y) {
   const int G = z.C / 8;
-  const long long total = (long long)z.B * z.H * z.W * G;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    const long long pix = i / G;
-    float v[8];
-    V8<T>::load(at<T>(z, pix, g * 8), v);
+  const int L = 256 / G;
+  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
+  if (pl >= L) return;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], scale[g * 8 + k], shift[g * 8 + k]), 0.f);
-    V8<T>::store(at<T>(y, pix, g * 8), v);
+  for (int k = 0; k < 8; ++k) { sc[k] = scale[gi * 8 + k]; sh[k] = shift[gi * 8 + k]; }
+  const long long npix = (long long)z.B * z.H * z.W;
+  for (long long p = (long long)blockIdx.x * L + pl; p < npix; p += (long long)gridDim.x * L) {
+    float v[8];
+    V8<T>::load(at<T>(z, p, gi * 8), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+    V8<T>::store(at<T>(y, p, gi * 8), v);
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView y, DView z, const float* mean,
-                                                            const float* rstd, double* sums) {
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView y, DView z, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, double* sums) {
   const long long npix = (long long)z.B * z.H * z.W;
+  const int gi8 = (threadIdx.x % (z.C / 8)) * 8;
+  float cm[8], cr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { cm[k] = mean[gi8 + k]; cr[k] = rstd[gi8 + k]; }
   channel_reduce<T, 2>(z, npix, sums, [&](long long p, int c, float (&acc)[2][8]) {
     float g[8], yy[8], zz[8];
     V8<T>::load(at<T>(gy, p, c), g);
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView y, D
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float gt = yy[k] > 0.f ? g[k] : 0.f;
-      const float xh = (zz[k] - mean[c + k]) * rstd[c + k];
+      const float xh = (zz[k] - cm[k]) * cr[k];
       acc[0][k] += gt;
       acc[1][k] = fmaf(gt, xh, acc[1][k]);
     }
@@ -122,12 +132,22 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView y, D
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView y, DView z, const float* gamma,
-                                                           const float* mean, const float* rstd, const double* sums,
-                                                           long long count, DView dz, double* dbias_sums) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView y, DView z, const float* __restrict__ gamma,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           const double* __restrict__ sums, long long count, DView dz,
+                                                           double* dbias_sums) {
   const long long npix = (long long)z.B * z.H * z.W;
   const float inv_n = 1.f / (float)count;
   const int C = z.C;
+  const int gi8 = (threadIdx.x % (C / 8)) * 8;
+  // per-channel coefficients hoisted out of the pixel loop (dz may alias z, so the compiler cannot do it)
+  float ca[8], cm[8], cr[8], m1[8], m2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    cr[k] = rstd[gi8 + k]; cm[k] = mean[gi8 + k]; ca[k] = gamma[gi8 + k] * cr[k];
+    m1[k] = (float)sums[gi8 + k] * inv_n; m2[k] = (float)sums[C + gi8 + k] * inv_n;
+  }
   channel_reduce<T, 1>(z, npix, dbias_sums, [&](long long p, int c, float (&acc)[1][8]) {
     float g[8], yy[8], zz[8], o[8];
     V8<T>::load(at<T>(gy, p, c), g);
@@ -136,10 +156,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView y, DV
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float gt = yy[k] > 0.f ? g[k] : 0.f;
-      const float rs = rstd[c + k];
-      const float xh = (zz[k] - mean[c + k]) * rs;
-      const float m1 = (float)sums[c + k] * inv_n, m2 = (float)sums[C + c + k] * inv_n;
-      o[k] = gamma[c + k] * rs * (gt - m1 - xh * m2);
+      const float xh = (zz[k] - cm[k]) * cr[k];
+      o[k] = ca[k] * (gt - m1[k] - xh * m2[k]);
       acc[0][k] += V8<T>::round(o[k]);
     }
     V8<T>::store(at<T>(dz, p, c), o);
@@ -201,8 +219,8 @@ int op_bn_finalize_train(const double* sums, long long count, const float* gamma
 int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shift, const View& y,
                      cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(y) || z.C != y.C || z.pixels() != y.pixels()) return fail("bn_apply: bad views");
-  const long long items = z.pixels() * (z.C / 8);
-  long long b = (items + 255) / 256;
+  const int L = std::max(1, 256 / (z.C / 8));
+  long long b = (z.pixels() + L - 1) / L;
   if (b > 148 * 8) b = 148 * 8;
   if (dt == DT_BF16) bn_apply_relu_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(z), scale, shift, dv(y));
   else               bn_apply_relu_kernel<float><<<(int)b, 256, 0, st>>>(dv(z), scale, shift, dv(y));
