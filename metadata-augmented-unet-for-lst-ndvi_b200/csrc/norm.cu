@@ -109,21 +109,23 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(DView z, const float
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView y, DView z, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView z, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, double* sums) {
   const long long npix = (long long)z.B * z.H * z.W;
   const int gi8 = (threadIdx.x % (z.C / 8)) * 8;
-  float cm[8], cr[8];
+  float cm[8], cr[8], sc[8], sh[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { cm[k] = mean[gi8 + k]; cr[k] = rstd[gi8 + k]; }
+  for (int k = 0; k < 8; ++k) { cm[k] = mean[gi8 + k]; cr[k] = rstd[gi8 + k]; sc[k] = scale[gi8 + k]; sh[k] = shift[gi8 + k]; }
   channel_reduce<T, 2>(z, npix, sums, [&](long long p, int c, float (&acc)[2][8]) {
-    float g[8], yy[8], zz[8];
+    float g[8], zz[8];
     V8<T>::load(at<T>(gy, p, c), g);
-    V8<T>::load(at<T>(y, p, c), yy);
     V8<T>::load(at<T>(z, p, c), zz);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float gt = yy[k] > 0.f ? g[k] : 0.f;
+      // ReLU mask recomputed exactly as the forward did (y = relu(fma(z, scale, shift))): no read of y
+      const float gt = fmaf(zz[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
       const float xh = (zz[k] - cm[k]) * cr[k];
       acc[0][k] += gt;
       acc[1][k] = fmaf(gt, xh, acc[1][k]);
@@ -132,7 +134,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView y, D
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView y, DView z, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView z, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ gamma,
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ rstd,
                                                            const double* __restrict__ sums, long long count, DView dz,
@@ -142,20 +146,20 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView y, DV
   const int C = z.C;
   const int gi8 = (threadIdx.x % (C / 8)) * 8;
   // per-channel coefficients hoisted out of the pixel loop (dz may alias z, so the compiler cannot do it)
-  float ca[8], cm[8], cr[8], m1[8], m2[8];
+  float ca[8], cm[8], cr[8], m1[8], m2[8], sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
+    sc[k] = scale[gi8 + k]; sh[k] = shift[gi8 + k];
     cr[k] = rstd[gi8 + k]; cm[k] = mean[gi8 + k]; ca[k] = gamma[gi8 + k] * cr[k];
     m1[k] = (float)sums[gi8 + k] * inv_n; m2[k] = (float)sums[C + gi8 + k] * inv_n;
   }
   channel_reduce<T, 1>(z, npix, dbias_sums, [&](long long p, int c, float (&acc)[1][8]) {
-    float g[8], yy[8], zz[8], o[8];
+    float g[8], zz[8], o[8];
     V8<T>::load(at<T>(gy, p, c), g);
-    V8<T>::load(at<T>(y, p, c), yy);
     V8<T>::load(at<T>(z, p, c), zz);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float gt = yy[k] > 0.f ? g[k] : 0.f;
+      const float gt = fmaf(zz[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
       const float xh = (zz[k] - cm[k]) * cr[k];
       o[k] = ca[k] * (gt - m1[k] - xh * m2[k]);
       acc[0][k] += V8<T>::round(o[k]);
@@ -227,26 +231,26 @@ int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shi
   MAU_LAUNCHED();
   return 0;
 }
-int op_bn_bwd_reduce(int dt, const View& gy, const View& y, const View& z, const float* mean, const float* rstd,
-                     double* sums, cudaStream_t st) {
-  if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(y)) return fail("bn_bwd_reduce: bad views");
+int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* mean,
+                     const float* rstd, double* sums, cudaStream_t st) {
+  if (!vec_ok(z) || !vec_ok(gy)) return fail("bn_bwd_reduce: bad views");
   const size_t smem = 2 * 256 * 8 * sizeof(float);
   const int blocks = reduce_blocks(z.pixels(), z.C);
-  if (dt == DT_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), mean, rstd, sums);
-  else               bn_bwd_reduce_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), mean, rstd, sums);
+  if (dt == DT_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, mean, rstd, sums);
+  else               bn_bwd_reduce_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, mean, rstd, sums);
   MAU_LAUNCHED();
   return 0;
 }
-int op_bn_bwd_apply(int dt, const View& gy, const View& y, const View& z, const float* gamma, const float* mean,
-                    const float* rstd, const double* sums, long long count, const View& dz_out,
+int op_bn_bwd_apply(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* gamma,
+                    const float* mean, const float* rstd, const double* sums, long long count, const View& dz_out,
                     double* dbias_sums, cudaStream_t st) {
-  if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(y) || !vec_ok(dz_out)) return fail("bn_bwd_apply: bad views");
+  if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(dz_out)) return fail("bn_bwd_apply: bad views");
   const size_t smem = 256 * 8 * sizeof(float);
   const int blocks = reduce_blocks(z.pixels(), z.C);
   if (dt == DT_BF16)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
   else
-    bn_bwd_apply_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(y), dv(z), gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
+    bn_bwd_apply_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
   MAU_LAUNCHED();
   return 0;
 }

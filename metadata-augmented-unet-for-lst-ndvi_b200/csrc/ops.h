@@ -62,13 +62,14 @@ int op_bn_finalize_train(const double* sums, long long count, const float* gamma
 // y = relu(z * scale + shift) into a (slice) view
 int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shift, const View& y,
                      cudaStream_t st);
-// backward, pass 1: sums[0..C) = sum g~, sums[C..2C) = sum g~ * xhat, g~ = gy * (y > 0)
-int op_bn_bwd_reduce(int dt, const View& gy, const View& y, const View& z, const float* mean, const float* rstd,
-                     double* sums, cudaStream_t st);
+// backward, pass 1: sums[0..C) = sum g~, sums[C..2C) = sum g~ * xhat, g~ = gy * (y > 0); the ReLU mask is
+// recomputed from z with the forward's scale / shift, so y is not read
+int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* mean,
+                     const float* rstd, double* sums, cudaStream_t st);
 // backward, pass 2: dz = gamma*rstd*(g~ - s1/n - xhat*s2/n) written over dz_out (may alias z);
 // also dgamma = s2, dbeta = s1 and dbias_sums += sum dz (double, zeroed by the caller)
-int op_bn_bwd_apply(int dt, const View& gy, const View& y, const View& z, const float* gamma, const float* mean,
-                    const float* rstd, const double* sums, long long count, const View& dz_out,
+int op_bn_bwd_apply(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* gamma,
+                    const float* mean, const float* rstd, const double* sums, long long count, const View& dz_out,
                     double* dbias_sums, cudaStream_t st);
 int op_bn_bwd_finalize(const double* sums, const double* dbias_sums, int C, float* dgamma, float* dbeta,
                        float* dbias, cudaStream_t st);

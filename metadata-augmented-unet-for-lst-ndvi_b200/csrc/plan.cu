@@ -260,8 +260,8 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
   op.run = [this, L, gy, y, z, count, C](Ctx& c) -> int {
     MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
     MAU_CUDA(cudaMemsetAsync(L->dbsum, 0, sizeof(double) * C, c.st));
-    MAU_TRY(op_bn_bwd_reduce(dt, gy, y, z, L->mean, L->rstd, L->sums, c.st));
-    MAU_TRY(op_bn_bwd_apply(dt, gy, y, z, c.f(L->igamma), L->mean, L->rstd, L->sums, count, z, L->dbsum, c.st));
+    MAU_TRY(op_bn_bwd_reduce(dt, gy, z, L->scale, L->shift, L->mean, L->rstd, L->sums, c.st));
+    MAU_TRY(op_bn_bwd_apply(dt, gy, z, L->scale, L->shift, c.f(L->igamma), L->mean, L->rstd, L->sums, count, z, L->dbsum, c.st));
     MAU_TRY(op_bn_bwd_finalize(L->sums, L->dbsum, C, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
     float* dw = c.g(L->iw);
     int ci_w0 = 0;
