@@ -67,9 +67,11 @@ class ClockSampler(threading.Thread):
 
 def cpu_reference(workload, batch, iters, warm=1):
     """The reference algorithm on the host cores: oracle/unet_oracle.py (functional torch CPU fp32,
-    same ATen kernels the reference module dispatches to)."""
+    same ATen kernels the reference module dispatches to).  Uses every host core: torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would otherwise pin the CPU arm to one thread."""
     import torch
     import mau_b200
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     from oracle import unet_oracle as O
     torch.manual_seed(42)
     m = mau_b200.UrbanPredictor("unet", *CTOR, **KW)
@@ -90,6 +92,16 @@ def cpu_reference(workload, batch, iters, warm=1):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: anything libraries print there (NCCL's version banner,
+    # loguru sinks) is routed to stderr; the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -113,14 +125,14 @@ def main():
             return
         sample = 8 if args.workload == "infer" else 4
         v, sec, threads = cpu_reference(args.workload, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": metric, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name, "tile": [23, TILE, TILE], "batch_per_step": sample, "device": "cpu"},
             "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} tiles per step, {max(1, args.steps)} timed steps, oracle/unet_oracle.py on torch CPU fp32"},
-            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -291,7 +303,7 @@ def main():
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -60,6 +60,7 @@ typedef struct mau_config {
 #define MAU_FLAG_CONV_FFMA     4  /* debug: run bf16 plans on the FFMA convolution kernels         */
 #define MAU_FLAG_HALO_BASEOFF  256 /* debug: halo main loop fills the UMMA descriptor base_offset   */
 #define MAU_FLAG_CONV_ROW3     512 /* debug: three-row-box conv main loop instead of the halo kernel */
+#define MAU_FLAG_WGRAD_V1      1024 /* debug: first-generation weight-gradient kernel (fp32 atomics)   */
 
 typedef struct mau_plan mau_plan; /* opaque */
 
@@ -114,6 +115,11 @@ int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* gr
 typedef void (*mau_grad_ready_fn)(void* user, int first_index, int last_index);
 int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user);
 
+/* SMs the persistent kernels leave free (default 0, or $MAU_SM_RESERVE): set it to the number of CTAs
+ * a concurrently running collective (NCCL all-reduce overlapped with backward) occupies, so that a
+ * persistent grid never spills into a second wave.  Applies to plans created afterwards. */
+int mau_set_sm_reserve(int n_sms);
+
 /* per-layer device timings of the last forward/backward (ms, CUDA events on `stream`);
  * enable, run, then read.  names: '\n'-separated, same order as ms[]. */
 int mau_plan_profile(mau_plan* plan, int enable);
@@ -146,10 +152,21 @@ int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, 
 /* timing helper (tools/conv_bench.py): bf16 tcgen05 conv, `iters` launches between CUDA events */
 int mau_op_conv3x3_bench(int impl, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
                          const float* w_oihw_dev, int Cout, void* y_dev, int Cout_stride, int iters, float* ms_out);
-/* dW [Cout,Cin,3,3] fp32 = sum_pixels dy (x) x ; impl 0 = tcgen05, 2 = FFMA */
+/* dW [Cout,Cin,3,3] fp32 = sum_pixels dy (x) x ; impl 0 = tcgen05 persistent split-K kernel (orientation
+ * chosen by the tile-padding cost model), 4 / 5 = the same with M = output / input channels forced,
+ * 1 = first-generation tcgen05 kernel (atomics), 2 = FFMA */
 int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_dev, int B, int H, int W,
                          int Cin, int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev,
                          void* stream);
+/* timing helper (tools/conv_bench.py): weight gradient incl. workspace memset + transpose */
+int mau_op_conv3x3_wgrad_bench(int impl, const void* x_dev, const void* dy_dev, int B, int H, int W, int Cin,
+                               int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev, int iters,
+                               float* ms_out);
+/* timing helper (tools/bw_bench.py): one bandwidth-bound kernel, rotating over `sets` copies of its tensors
+ * (sets * bytes > L2).  kind: 0 bn_stats, 1 bn_apply_relu, 2 bn_bwd_reduce, 3 bn_bwd_apply, 4 maxpool,
+ * 5 maxpool_bwd, 6 bilinear (H/2 -> H), 7 bilinear_bwd, 8 head, 9 head_bwd, 10 nchw_to_nhwc (23 ch),
+ * 11 embed_broadcast, 12 loss (L1 + gradient, fwd+bwd), 13 slice copy. */
+int mau_op_bw_bench(int kind, int dtype, int B, int H, int W, int C, int iters, int sets, float* ms_out);
 int mau_op_maxpool2x2(int dtype, const void* x_dev, int B, int H, int W, int C, void* y_dev, void* stream);
 int mau_op_bilinear(int dtype, const void* x_dev, int B, int Hin, int Win, int C, int Hout, int Wout,
                     void* y_dev, void* stream);

@@ -1,5 +1,7 @@
 // api.cu -- the extern "C" surface declared in include/mau_b200.h
+#include <algorithm>
 #include <cstring>
+#include <vector>
 #include <new>
 #include "plan.h"
 
@@ -14,6 +16,7 @@ extern "C" {
 const char* mau_last_error(void) { return last_error().c_str(); }
 int mau_version(void) { return 100; }
 int64_t mau_launch_count(void) { return (int64_t)g_launches.load(); }
+int mau_set_sm_reserve(int n_sms) { set_sm_reserve(n_sms); return 0; }
 
 int mau_plan_create(const mau_config* cfg, mau_plan** out) {
   if (!cfg || !out) return fail("mau_plan_create: null argument");
@@ -220,8 +223,138 @@ int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_
   if (impl == 2) return wgrad_ffma_launch(dtype, x, dy, 0, Cin, dw_oihw_dev, 1, st);
   if (dtype != DT_BF16) return fail("tcgen05 wgrad is bf16 only");
   WgradTcOp op;
-  MAU_TRY(wgrad_tc_prepare(&op, x, dy, 0, Cin));
-  return wgrad_tc_launch(op, dw_oihw_dev, st);
+  if (impl == 1) {
+    MAU_TRY(wgrad_tc_prepare(&op, x, dy, 0, Cin, nullptr, 0));
+    return wgrad_tc_launch(op, dw_oihw_dev, st);
+  }
+  const int swap = impl == 4 ? 0 : (impl == 5 ? 1 : wgrad_tc_pick_swap(Cout, 1, &Cin));
+  const size_t fl = wgrad_tc_workspace_floats(Cout, Cin, swap);
+  float* ws = nullptr;
+  MAU_CUDA(cudaMalloc(&ws, sizeof(float) * fl));
+  int rc = 0;
+  if (cudaMemsetAsync(ws, 0, sizeof(float) * fl, st) != cudaSuccess) rc = fail("wgrad workspace memset failed");
+  if (!rc) rc = wgrad_tc_prepare(&op, x, dy, 0, Cin, ws, swap);
+  if (!rc) rc = wgrad_tc_launch(op, dw_oihw_dev, st);
+  if (!rc) rc = wgrad_tc_finalize(ws, swap, Cout, Cin, dw_oihw_dev, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(ws);
+  if (!rc && e != cudaSuccess) rc = fail("wgrad execution failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// timing helper for tools/conv_bench.py: weight gradient, `iters` launches (memset + kernel + finalize) between events
+int mau_op_conv3x3_wgrad_bench(int impl, const void* x_dev, const void* dy_dev, int B, int H, int W, int Cin,
+                               int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev, int iters, float* ms_out) {
+  const View x = mkview(x_dev, B, H, W, Cin, Cin_stride), dy = mkview(dy_dev, B, H, W, Cout, Cout_stride);
+  WgradTcOp op;
+  const bool v1 = impl == 1;
+  const int swap = impl == 4 ? 0 : (impl == 5 ? 1 : wgrad_tc_pick_swap(Cout, 1, &Cin));
+  const size_t fl = wgrad_tc_workspace_floats(Cout, Cin, swap);
+  float* ws = nullptr;
+  if (!v1) MAU_CUDA(cudaMalloc(&ws, sizeof(float) * fl));
+  int rc = wgrad_tc_prepare(&op, x, dy, 0, Cin, ws, swap);
+  auto once = [&]() -> int {
+    if (v1) { if (cudaMemsetAsync(dw_oihw_dev, 0, sizeof(float) * (size_t)Cout * Cin * 9, 0) != cudaSuccess) return fail("memset"); }
+    else if (cudaMemsetAsync(ws, 0, sizeof(float) * fl, 0) != cudaSuccess) return fail("memset");
+    MAU_TRY(wgrad_tc_launch(op, dw_oihw_dev, 0));
+    if (!v1) MAU_TRY(wgrad_tc_finalize(ws, swap, Cout, Cin, dw_oihw_dev, 0));
+    return 0;
+  };
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 2 && !rc; ++i) rc = once();
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < iters && !rc; ++i) rc = once();
+  cudaEventRecord(e1, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms / (iters > 0 ? iters : 1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(ws);
+  if (!rc && e != cudaSuccess) rc = fail("wgrad bench failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// timing helper (tools/bw_bench.py): one bandwidth-bound kernel of the path, `iters` launches between CUDA
+// events.  Every tensor is allocated `sets` times (sets * bytes > L2) and launches rotate over the copies, so
+// no launch re-reads data a previous launch left in L2.  Returns ms per launch.
+int mau_op_bw_bench(int kind, int dtype, int B, int H, int W, int C, int iters, int sets, float* ms_out) {
+  if (sets < 1 || sets > 16 || iters < 1) return fail("bw_bench: bad sets/iters");
+  const size_t es = dtype_size(dtype);
+  const int H2 = H / 2, W2 = W / 2;
+  const size_t big = (size_t)B * H * W * C * es, small = (size_t)B * H2 * W2 * C * es;
+  const size_t plane = (size_t)B * H * W * sizeof(float);
+  std::vector<void*> allocs;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, bytes ? bytes : 16);
+    allocs.push_back(p);
+    return p;
+  };
+  struct Set { void *a, *b, *c, *s; float *f0, *f1; double* d; };
+  std::vector<Set> S(sets);
+  for (auto& s : S) {
+    s.a = dalloc(big); s.b = dalloc(big); s.c = dalloc(big); s.s = dalloc(small);
+    s.f0 = static_cast<float*>(dalloc(std::max(plane * 8, (size_t)B * 23 * H * W * 4)));
+    s.f1 = static_cast<float*>(dalloc(plane * 8));
+    s.d = static_cast<double*>(dalloc(sizeof(double) * 4 * (C + 64)));
+    if (!s.a || !s.b || !s.c || !s.s || !s.f0 || !s.f1 || !s.d) {
+      for (void* p : allocs) cudaFree(p);
+      return fail("bw_bench: out of device memory");
+    }
+  }
+  std::vector<float> ones(C, 1.f);
+  float* coef = static_cast<float*>(dalloc(sizeof(float) * C * 8));
+  for (int i = 0; i < 8; ++i) cudaMemcpy(coef + i * C, ones.data(), sizeof(float) * C, cudaMemcpyHostToDevice);
+  // bilinear tables (H2,W2) -> (H,W)
+  BilinearHost hy, hx;
+  bilinear_axis_tables(H2, H, &hy);
+  bilinear_axis_tables(W2, W, &hx);
+  BilinearTables t;
+  t.Hin = H2; t.Win = W2; t.Hout = H; t.Wout = W; t.max_fan_w = hx.max_fan;
+  auto up = [&](const void* src, size_t bytes) -> void* { void* d = dalloc(bytes); if (d) cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice); return d; };
+  t.ty_off = (int*)up(hy.t_off.data(), 4 * hy.t_off.size()); t.ty_idx = (int*)up(hy.t_idx.data(), 4 * hy.t_idx.size());
+  t.ty_w = (float*)up(hy.t_w.data(), 4 * hy.t_w.size());
+  t.tx_off = (int*)up(hx.t_off.data(), 4 * hx.t_off.size()); t.tx_idx = (int*)up(hx.t_idx.data(), 4 * hx.t_idx.size());
+  t.tx_w = (float*)up(hx.t_w.data(), 4 * hx.t_w.size());
+  auto run = [&](const Set& s) -> int {
+    const View a = mkview(s.a, B, H, W, C, C), b = mkview(s.b, B, H, W, C, C), c = mkview(s.c, B, H, W, C, C);
+    const View sm = mkview(s.s, B, H2, W2, C, C);
+    switch (kind) {
+      case 0: return op_bn_stats(dtype, a, s.d, 0);
+      case 1: return op_bn_apply_relu(dtype, a, coef, coef + C, b, 0);
+      case 2: return op_bn_bwd_reduce(dtype, a, b, coef, coef + C, coef + 2 * C, coef + 3 * C, s.d, 0);
+      case 3: return op_bn_bwd_apply(dtype, a, b, coef, coef + C, coef + 2 * C, coef + 3 * C, coef + 4 * C, s.d, (long long)B * H * W, b, s.d + 2 * C, 0);
+      case 4: return op_maxpool(dtype, a, sm, 0);
+      case 5: return op_maxpool_bwd(dtype, a, sm, nullptr, b, 0);
+      case 6: return op_bilinear(dtype, sm, a, t, 0);
+      case 7: return op_bilinear_bwd(dtype, a, sm, t, 0, 0);
+      case 8: return op_head(dtype, a, coef, coef + 2 * C, 2, 1, s.f0, 0);
+      case 9: return op_head_bwd(dtype, a, coef, 2, 1, s.f0, s.f1, b, coef + 5 * C, coef + 7 * C, 0);
+      case 10: return op_nchw_to_nhwc(dtype, s.f0, B, 23, H, W, mkview(s.a, B, H, W, 23, 24), 0);
+      case 11: return op_embed_broadcast(dtype, coef, 0, a, 0);
+      case 12: return op_loss(0, s.f0, s.f1, B, 2, H, W, 0.1f, reinterpret_cast<float*>(s.d), s.f0 + 4 * (size_t)B * H * W, 0);
+      case 13: return op_copy_slice(dtype, a, b, 0, 0);     // plain device copy through the same vector path (reference point)
+      default: return fail("bw_bench: unknown kind %d", kind);
+    }
+  };
+  int rc = 0;
+  for (int i = 0; i < sets && !rc; ++i) rc = run(S[i]);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < iters && !rc; ++i) rc = run(S[i % sets]);
+  cudaEventRecord(e1, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (void* p : allocs) cudaFree(p);
+  if (!rc && e != cudaSuccess) rc = fail("bw_bench failed: %s", cudaGetErrorString(e));
+  return rc;
 }
 
 int mau_op_maxpool2x2(int dtype, const void* x_dev, int B, int H, int W, int C, void* y_dev, void* stream) {

@@ -1,4 +1,5 @@
 #include "common.h"
+#include <cstdlib>
 namespace mau {
 std::atomic<long long> g_launches{0};
 std::string& last_error() {
@@ -13,5 +14,23 @@ int fail(const char* fmt, ...) {
   va_end(ap);
   last_error() = buf;
   return -1;
+}
+
+// SMs the persistent kernels of this library size their grids for.  MAU_SM_RESERVE (or mau_set_sm_reserve)
+// leaves SMs free for a concurrently running collective kernel: a persistent grid that does not fit
+// next to it would otherwise run its last CTAs as a second wave.
+static std::atomic<int> g_sm_reserve{-1};
+void set_sm_reserve(int n) { g_sm_reserve.store(n < 0 ? 0 : n); }
+int sm_budget() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int r = g_sm_reserve.load();
+  if (r < 0) {
+    const char* e = getenv("MAU_SM_RESERVE");
+    r = e ? atoi(e) : 0;
+    if (r < 0) r = 0;
+    g_sm_reserve.store(r);
+  }
+  return sms - r > 8 ? sms - r : 8;
 }
 }  // namespace mau

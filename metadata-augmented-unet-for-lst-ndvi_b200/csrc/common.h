@@ -51,6 +51,9 @@ struct View {
   long long pixels() const { return (long long)B * H * W; }
 };
 
+int sm_budget();              // SMs persistent kernels may occupy (device SM count - reserve)
+void set_sm_reserve(int n);   // SMs left free for concurrent collective kernels (data-parallel training)
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

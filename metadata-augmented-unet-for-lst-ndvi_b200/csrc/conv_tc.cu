@@ -652,10 +652,7 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   op->grid = dim3((unsigned)p.total_ptiles, (unsigned)ceil_div(y.C, op->bn), 1);
   if (mode == MODE_HALO) {   // persistent: one CTA per SM (or fewer when there is less work)
     const int items = ceil_div(p.total_ptiles, op->mt) * ceil_div(y.C, op->bn);
-    int sms = 148;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    op->grid = dim3((unsigned)std::min(items, sms), 1, 1);
+    op->grid = dim3((unsigned)std::min(items, sm_budget()), 1, 1);
   }
   // A: whole input buffer {C, W, H, B}
   View xa = xbuf;

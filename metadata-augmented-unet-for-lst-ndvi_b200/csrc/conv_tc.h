@@ -51,17 +51,25 @@ int conv_tc_pack_dgrad(const float* w_oihw, int Cout, int Cin, int ci0, int N, i
 
 // ---- weight gradient (wgrad_tc.cu): dW[co][ci][tap] = sum_pixels dY[p][co] * X[p + d(tap)][ci]
 struct WgradTcOp {
-  CUtensorMap tmDy, tmX;
+  CUtensorMap tmDy, tmX, tmWs;
   int B = 0, H = 0, W = 0;
   int Cout = 0, Cin = 0;         // extents of this launch (Cin = one input segment)
   int ci_w0 = 0;                 // first weight input-channel index of this segment
   int Cin_w = 0;                 // Cin of the full OIHW weight tensor
   int m_tiles = 0, n_tiles = 0, splits = 0, tiles_per_split = 0;
   int bn = 0;
+  float* ws = nullptr;           // v2: fp32 workspace [9][M dim][N dim] (nullptr selects the v1 atomics kernel)
+  int swap = 0;                  // v2: 1 = M side is the input-channel side (workspace [9][Cin][Cout])
   dim3 grid;
 };
-int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0, int Cin_w);
-// accumulates into dw (fp32 OIHW, must be zeroed by the caller before the first segment)
+// orientation that wastes less of the 128 x BN tiles for this layer (all segments share one workspace layout)
+int wgrad_tc_pick_swap(int Cout, int nseg, const int* seg_len);
+size_t wgrad_tc_workspace_floats(int Cout, int Cin_w, int swap);
+// ws != nullptr: v2 (persistent split-K/stream-K kernel, TMA reduce-add into ws, then wgrad_tc_finalize);
+// ws == nullptr: v1 (fp32 atomics straight into the zeroed OIHW gradient)
+int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0, int Cin_w, float* ws, int swap);
 int wgrad_tc_launch(const WgradTcOp& op, float* dw_oihw, cudaStream_t st);
+// ws [9][..][..] (zeroed before the segment launches) -> dw OIHW (overwrites)
+int wgrad_tc_finalize(const float* ws, int swap, int Cout, int Cin_w, float* dw_oihw, cudaStream_t st);
 
 }  // namespace mau

@@ -4,6 +4,7 @@
 // warp touches whole 128-byte lines; grids are sized in multiples of the SM count and grid-stride.
 #include "ops.h"
 #include "vec.cuh"
+#include <algorithm>
 
 namespace mau {
 namespace {
@@ -171,31 +172,107 @@ __device__ __forceinline__ void src_index(float scale, int o, int in_size, int& 
   i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
   l1 = fminf(fmaxf(__fsub_rn(real, (float)i0), 0.f), 1.f);
 }
+// One thread = one (output column, 8-channel group) for kRows consecutive output rows: all 4*kRows source
+// vectors are requested before the first is used (bytes in flight per thread, not occupancy, is what
+// buys bandwidth here); neighbouring rows share source rows, which L1 serves.
+constexpr int kRows = 4;
 template <typename T>
-__global__ void bilinear_kernel(DView x, DView y, float sy, float sx, FastDiv divG, FastDiv divH) {
+__global__ void __launch_bounds__(256) bilinear_kernel(DView x, DView y, float sy, float sx, FastDiv divG, FastDiv divQ) {
+  using Raw = typename V8<T>::Raw;
   const unsigned G = y.C / 8;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (unsigned)y.W * G) return;
-  unsigned ow, g, b, oh;
+  unsigned ow, g, b, q;
   divG.divmod(idx, ow, g);
-  divH.divmod(blockIdx.y, b, oh);
-  int y0, y1, x0, x1; float ly, lx;
-  src_index(sy, (int)oh, x.H, y0, y1, ly);
+  divQ.divmod(blockIdx.y, b, q);          // q = group of kRows output rows
+  int x0, x1; float lx;
   src_index(sx, (int)ow, x.W, x0, x1, lx);
-  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float hx = 1.f - lx;
   const long long base = (long long)b * x.H;
-  float a[8], bb[8], c[8], d[8], o[8];
-  V8<T>::load(at<T>(x, (base + y0) * x.W + x0, g * 8), a);
-  V8<T>::load(at<T>(x, (base + y0) * x.W + x1, g * 8), bb);
-  V8<T>::load(at<T>(x, (base + y1) * x.W + x0, g * 8), c);
-  V8<T>::load(at<T>(x, (base + y1) * x.W + x1, g * 8), d);
+  const int oh0 = (int)q * kRows;
+  Raw r[kRows][4];
+  float ly[kRows];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * bb[k]) + ly * (hx * c[k] + lx * d[k]);
-  V8<T>::store(at<T>(y, ((long long)b * y.H + oh) * y.W + ow, g * 8), o);
+  for (int i = 0; i < kRows; ++i) {
+    const int oh = oh0 + i;
+    if (oh < y.H) {
+      int y0, y1;
+      src_index(sy, oh, x.H, y0, y1, ly[i]);
+      r[i][0] = V8<T>::load_raw(at<T>(x, (base + y0) * x.W + x0, g * 8));
+      r[i][1] = V8<T>::load_raw(at<T>(x, (base + y0) * x.W + x1, g * 8));
+      r[i][2] = V8<T>::load_raw(at<T>(x, (base + y1) * x.W + x0, g * 8));
+      r[i][3] = V8<T>::load_raw(at<T>(x, (base + y1) * x.W + x1, g * 8));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kRows; ++i) {
+    const int oh = oh0 + i;
+    if (oh < y.H) {
+      float a[8], bb[8], c[8], d[8], o[8];
+      V8<T>::unpack(r[i][0], a); V8<T>::unpack(r[i][1], bb); V8<T>::unpack(r[i][2], c); V8<T>::unpack(r[i][3], d);
+      const float hy = 1.f - ly[i];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * bb[k]) + ly[i] * (hx * c[k] + lx * d[k]);
+      V8<T>::store(at<T>(y, ((long long)b * y.H + oh) * y.W + ow, g * 8), o);
+    }
+  }
 }
 // gather form: gx[ih,iw] = sum_{(oh,wy) in rows(ih)} sum_{(ow,wx) in cols(iw)} wy*wx*gy[oh,ow]
+// Fast path (every source column receives at most kMaxE contributions -- always true when up-sampling):
+// the column list is read once, then for every contributing output row the <= kMaxE gy vectors are
+// requested as one batch.
+constexpr int kMaxE = 6;
 template <typename T>
-__global__ void bilinear_bwd_kernel(DView gy, DView gx, BilinearTables t, int accumulate) {
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(DView gy, DView gx, BilinearTables t, int accumulate) {
+  using Raw = typename V8<T>::Raw;
+  const int G = gx.C / 8;
+  const long long total = (long long)gx.B * gx.H * gx.W * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int iw = (int)(r % gx.W); r /= gx.W;
+    const int ih = (int)(r % gx.H);
+    const int b = (int)(r / gx.H);
+    const int ra = t.ty_off[ih], rb = t.ty_off[ih + 1];
+    const int ca = t.tx_off[iw], nc = t.tx_off[iw + 1] - ca;
+    int ow[kMaxE];
+    float wx[kMaxE];
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      ow[e] = e < nc ? t.tx_idx[ca + e] : 0;
+      wx[e] = e < nc ? t.tx_w[ca + e] : 0.f;
+    }
+    float o[8];
+    const long long opix = ((long long)b * gx.H + ih) * gx.W + iw;
+    if (accumulate) V8<T>::load(at<T>(gx, opix, g * 8), o);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    }
+    for (int a = ra; a < rb; ++a) {        // same summation order as the general kernel: rows outer, columns inner
+      const long long rowbase = ((long long)b * gy.H + t.ty_idx[a]) * gy.W;
+      const float wy = t.ty_w[a];
+      Raw rv[kMaxE];
+#pragma unroll
+      for (int c = 0; c < kMaxE; ++c)
+        if (c < nc) rv[c] = V8<T>::load_raw(at<T>(gy, rowbase + ow[c], g * 8));
+#pragma unroll
+      for (int c = 0; c < kMaxE; ++c)
+        if (c < nc) {
+          float v[8];
+          V8<T>::unpack(rv[c], v);
+          const float wgt = wy * wx[c];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = fmaf(wgt, v[k], o[k]);
+        }
+    }
+    V8<T>::store(at<T>(gx, opix, g * 8), o);
+  }
+}
+// general form (any number of contributions per source index, e.g. down-sampling)
+template <typename T>
+__global__ void bilinear_bwd_general_kernel(DView gy, DView gx, BilinearTables t, int accumulate) {
   const int G = gx.C / 8;
   const long long total = (long long)gx.B * gx.H * gx.W * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -298,63 +375,75 @@ __global__ void copy_slice_kernel(DView src, DView dst, int accumulate) {
 }
 
 // ------------------------------------------------------------------ 1x1 head
-// 8 lanes per pixel (each 8 channels of up to 64), shuffle-reduce, lane 0 of the group writes NCHW.
+// G = C/8 lanes per pixel (each 8 channels), shuffle-reduce over the G lanes, lane 0 of the group writes
+// NCHW.  kHU pixels per thread are loaded before any is used.  OCT = compile-time bound on out_channels.
 constexpr int kMaxOC = 8;
-template <typename T>
-__global__ void head_kernel(DView x, const float* __restrict__ w, const float* __restrict__ bias, int OC,
-                            int apply_tanh, float* __restrict__ out) {
-  extern __shared__ float sw[];  // [OC][C]
-  for (int i = threadIdx.x; i < OC * x.C; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
+constexpr int kHU = 4;
+template <typename T, int OCT>
+__global__ void __launch_bounds__(256) head_kernel(DView x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                   int OC, int apply_tanh, float* __restrict__ out) {
+  using Raw = typename V8<T>::Raw;
   const int G = x.C / 8;           // lanes per pixel (power of two <= 32 assumed by the host)
+  const int sub = threadIdx.x % G, slot = threadIdx.x / G;
+  float wr[OCT][8];                // this lane's 8 weights of every output channel
+#pragma unroll
+  for (int o = 0; o < OCT; ++o)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[o][k] = o < OC ? w[o * x.C + sub * 8 + k] : 0.f;
   const long long P = (long long)x.H * x.W;
   const long long npix = (long long)x.B * P;
   const int per_block = blockDim.x / G;
-  const int sub = threadIdx.x % G, slot = threadIdx.x / G;
-  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += (long long)gridDim.x * per_block) {
-    const long long pix = base + slot;
-    float acc[kMaxOC];
+  const long long stride = (long long)gridDim.x * per_block;
+  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += kHU * stride) {
+    Raw r[kHU];
 #pragma unroll
-    for (int o = 0; o < kMaxOC; ++o) acc[o] = 0.f;
-    if (pix < npix) {
-      float v[8];
-      V8<T>::load(at<T>(x, pix, sub * 8), v);
-#pragma unroll
-      for (int o = 0; o < kMaxOC; ++o)
-        if (o < OC) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[o] = fmaf(v[k], sw[o * x.C + sub * 8 + k], acc[o]);
-        }
+    for (int u = 0; u < kHU; ++u) {
+      const long long pix = base + u * stride + slot;
+      if (pix < npix) r[u] = V8<T>::load_raw(at<T>(x, pix, sub * 8));
     }
 #pragma unroll
-    for (int o = 0; o < kMaxOC; ++o)
-      if (o < OC)
-        for (int off = G >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
-    if (pix < npix && sub == 0) {
-      const int b = (int)(pix / P);
-      const long long p = pix - (long long)b * P;
+    for (int u = 0; u < kHU; ++u) {
+      const long long pix = base + u * stride + slot;
+      float acc[OCT];
 #pragma unroll
-      for (int o = 0; o < kMaxOC; ++o)
-        if (o < OC) {
-          float v = acc[o] + bias[o];
-          if (apply_tanh && o == 0) v = tanhf(v);
-          out[((long long)b * OC + o) * P + p] = v;
-        }
+      for (int o = 0; o < OCT; ++o) acc[o] = 0.f;
+      if (pix < npix) {
+        float v[8];
+        V8<T>::unpack(r[u], v);
+#pragma unroll
+        for (int o = 0; o < OCT; ++o)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[o] = fmaf(v[k], wr[o][k], acc[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < OCT; ++o)
+        for (int off = G >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+      if (pix < npix && sub == 0) {
+        const int b = (int)(pix / P);
+        const long long p = pix - (long long)b * P;
+#pragma unroll
+        for (int o = 0; o < OCT; ++o)
+          if (o < OC) {
+            float v = acc[o] + bias[o];
+            if (apply_tanh && o == 0) v = tanhf(v);
+            out[((long long)b * OC + o) * P + p] = v;
+          }
+      }
     }
   }
 }
 
 // backward of the head: per pixel g_o = gout_o * (o==0 && tanh ? 1 - out_0^2 : 1);
 // gx[c] = sum_o g_o W[o][c];  dW[o][c] += g_o x[c];  db[o] += g_o
-template <typename T>
-__global__ void head_bwd_kernel(DView x, const float* __restrict__ w, int OC, int apply_tanh,
-                                const float* __restrict__ out, const float* __restrict__ gout, DView gx,
-                                float* __restrict__ dw, float* __restrict__ db) {
-  extern __shared__ float sm[];      // sw [OC][C] | sdw [OC][C] | sdb [OC]
-  float* sw = sm;
-  float* sdw = sm + OC * x.C;
+template <typename T, int OCT>
+__global__ void __launch_bounds__(256) head_bwd_kernel(DView x, const float* __restrict__ w, int OC, int apply_tanh,
+                                                       const float* __restrict__ out, const float* __restrict__ gout,
+                                                       DView gx, float* __restrict__ dw, float* __restrict__ db) {
+  using Raw = typename V8<T>::Raw;
+  extern __shared__ float sm[];      // sdw [OC][C] | sdb [OC]
+  float* sdw = sm;
   float* sdb = sdw + OC * x.C;
-  for (int i = threadIdx.x; i < OC * x.C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+  for (int i = threadIdx.x; i < OC * x.C; i += blockDim.x) sdw[i] = 0.f;
   if (threadIdx.x < OC) sdb[threadIdx.x] = 0.f;
   __syncthreads();
   const int G = x.C / 8;
@@ -362,48 +451,55 @@ __global__ void head_bwd_kernel(DView x, const float* __restrict__ w, int OC, in
   const long long npix = (long long)x.B * P;
   const int per_block = blockDim.x / G;
   const int sub = threadIdx.x % G, slot = threadIdx.x / G;
-  float dwl[kMaxOC][8];
-  float dbl[kMaxOC];
+  float wr[OCT][8], dwl[OCT][8], dbl[OCT];
 #pragma unroll
-  for (int o = 0; o < kMaxOC; ++o) {
+  for (int o = 0; o < OCT; ++o) {
     dbl[o] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dwl[o][k] = 0.f;
+    for (int k = 0; k < 8; ++k) { dwl[o][k] = 0.f; wr[o][k] = o < OC ? w[o * x.C + sub * 8 + k] : 0.f; }
   }
-  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += (long long)gridDim.x * per_block) {
-    const long long pix = base + slot;
-    if (pix >= npix) continue;
-    const int b = (int)(pix / P);
-    const long long p = pix - (long long)b * P;
-    float go[kMaxOC];
+  const long long stride = (long long)gridDim.x * per_block;
+  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += kHU * stride) {
+    Raw r[kHU];
+    float go[kHU][OCT];
 #pragma unroll
-    for (int o = 0; o < kMaxOC; ++o)
-      if (o < OC) {
-        float gval = gout[((long long)b * OC + o) * P + p];
-        if (apply_tanh && o == 0) {
+    for (int u = 0; u < kHU; ++u) {
+      const long long pix = base + u * stride + slot;
+      if (pix < npix) {
+        r[u] = V8<T>::load_raw(at<T>(x, pix, sub * 8));
+        const int b = (int)(pix / P);
+        const long long p = pix - (long long)b * P;
+#pragma unroll
+        for (int o = 0; o < OCT; ++o) go[u][o] = o < OC ? gout[((long long)b * OC + o) * P + p] : 0.f;
+        if (apply_tanh) {
           const float y = out[((long long)b * OC) * P + p];
-          gval *= (1.f - y * y);
+          go[u][0] *= (1.f - y * y);
         }
-        go[o] = gval;
-      } else go[o] = 0.f;
-    float v[8], r[8];
-    V8<T>::load(at<T>(x, pix, sub * 8), v);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = 0.f;
-#pragma unroll
-    for (int o = 0; o < kMaxOC; ++o)
-      if (o < OC) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          r[k] = fmaf(go[o], sw[o * x.C + sub * 8 + k], r[k]);
-          dwl[o][k] = fmaf(go[o], v[k], dwl[o][k]);
-        }
-        if (sub == 0) dbl[o] += go[o];
       }
-    V8<T>::store(at<T>(gx, pix, sub * 8), r);
+    }
+#pragma unroll
+    for (int u = 0; u < kHU; ++u) {
+      const long long pix = base + u * stride + slot;
+      if (pix < npix) {
+        float v[8], rr[8];
+        V8<T>::unpack(r[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rr[k] = 0.f;
+#pragma unroll
+        for (int o = 0; o < OCT; ++o) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            rr[k] = fmaf(go[u][o], wr[o][k], rr[k]);
+            dwl[o][k] = fmaf(go[u][o], v[k], dwl[o][k]);
+          }
+          if (sub == 0) dbl[o] += go[u][o];
+        }
+        V8<T>::store(at<T>(gx, pix, sub * 8), rr);
+      }
+    }
   }
 #pragma unroll
-  for (int o = 0; o < kMaxOC; ++o)
+  for (int o = 0; o < OCT; ++o)
     if (o < OC) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) atomicAdd(&sdw[o * x.C + sub * 8 + k], dwl[o][k]);
@@ -470,7 +566,9 @@ void bilinear_axis_tables(int in, int out, BilinearHost* h) {
   }
   h->t_off.assign(in + 1, 0);
   h->t_idx.clear(); h->t_w.clear();
+  h->max_fan = 0;
   for (int i = 0; i < in; ++i) {
+    h->max_fan = std::max(h->max_fan, (int)inv[i].size());
     for (auto& e : inv[i]) { h->t_idx.push_back(e.first); h->t_w.push_back(e.second); }
     h->t_off[i + 1] = (int)h->t_idx.size();
   }
@@ -478,11 +576,12 @@ void bilinear_axis_tables(int in, int out, BilinearHost* h) {
 int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st) {
   if (!vec_ok(x) || !vec_ok(y) || x.C != y.C || t.Hin != x.H || t.Win != x.W || t.Hout != y.H || t.Wout != y.W)
     return fail("bilinear: bad views/tables");
-  if ((long long)y.B * y.H > 65535) return fail("bilinear: B*H too large for the row grid");
-  const dim3 grid((unsigned)ceil_div(y.W * (y.C / 8), 256), (unsigned)(y.B * y.H), 1);
+  const int quads = ceil_div(y.H, kRows);
+  if ((long long)y.B * quads > 65535) return fail("bilinear: B*H too large for the row grid");
+  const dim3 grid((unsigned)ceil_div(y.W * (y.C / 8), 256), (unsigned)(y.B * quads), 1);
   const float sy = y.H > 1 ? (float)(x.H - 1) / (float)(y.H - 1) : 0.f;     // area_pixel_compute_scale, align_corners
   const float sx = y.W > 1 ? (float)(x.W - 1) / (float)(y.W - 1) : 0.f;
-  MAU_DISPATCH(dt, bilinear_kernel, grid, 256, 0, st, dv(x), dv(y), sy, sx, FastDiv((unsigned)(y.C / 8)), FastDiv((unsigned)y.H));
+  MAU_DISPATCH(dt, bilinear_kernel, grid, 256, 0, st, dv(x), dv(y), sy, sx, FastDiv((unsigned)(y.C / 8)), FastDiv((unsigned)quads));
   return 0;
 }
 int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables& t, int accumulate,
@@ -490,8 +589,11 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
   if (!vec_ok(gx) || !vec_ok(gy) || gx.C != gy.C || t.Hin != gx.H || t.Win != gx.W || t.Hout != gy.H ||
       t.Wout != gy.W)
     return fail("bilinear_bwd: bad views/tables");
-  MAU_DISPATCH(dt, bilinear_bwd_kernel, grid_for(gx.pixels() * (gx.C / 8)), 256, 0, st, dv(gy), dv(gx), t,
-               accumulate);
+  if (t.max_fan_w <= kMaxE)
+    MAU_DISPATCH(dt, bilinear_bwd_kernel, grid_for(gx.pixels() * (gx.C / 8)), 256, 0, st, dv(gy), dv(gx), t, accumulate);
+  else
+    MAU_DISPATCH(dt, bilinear_bwd_general_kernel, grid_for(gx.pixels() * (gx.C / 8)), 256, 0, st, dv(gy), dv(gx), t,
+                 accumulate);
   return 0;
 }
 int op_embed_broadcast(int dt, const float* emb, int emb_stride, const View& y, cudaStream_t st) {
@@ -518,21 +620,35 @@ static bool head_ok(const View& x, int OC) {
   return x.C % 8 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && OC >= 1 && OC <= kMaxOC && x.cs % 8 == 0 &&
          x.c0 % 8 == 0;
 }
+#define MAU_HEAD_DISPATCH(KERNEL, GRID, SMEM, ...)                                                        \
+  do {                                                                                                    \
+    if (dt == DT_BF16) {                                                                                  \
+      if (OC <= 2) KERNEL<__nv_bfloat16, 2><<<GRID, 256, SMEM, st>>>(__VA_ARGS__);                        \
+      else if (OC <= 4) KERNEL<__nv_bfloat16, 4><<<GRID, 256, SMEM, st>>>(__VA_ARGS__);                   \
+      else KERNEL<__nv_bfloat16, 8><<<GRID, 256, SMEM, st>>>(__VA_ARGS__);                                \
+    } else {                                                                                              \
+      if (OC <= 2) KERNEL<float, 2><<<GRID, 256, SMEM, st>>>(__VA_ARGS__);                                \
+      else if (OC <= 4) KERNEL<float, 4><<<GRID, 256, SMEM, st>>>(__VA_ARGS__);                           \
+      else KERNEL<float, 8><<<GRID, 256, SMEM, st>>>(__VA_ARGS__);                                        \
+    }                                                                                                     \
+    MAU_LAUNCHED();                                                                                       \
+  } while (0)
+
 int op_head(int dt, const View& x, const float* w, const float* bias, int OC, int apply_tanh, float* out_nchw,
             cudaStream_t st) {
   if (!head_ok(x, OC)) return fail("head: needs C = 8*2^k <= 256 and out_channels <= 8 (C=%d, OC=%d)", x.C, OC);
   const int per_block = 256 / (x.C / 8);
-  MAU_DISPATCH(dt, head_kernel, grid_for(x.pixels(), per_block), 256, OC * x.C * sizeof(float), st, dv(x), w, bias,
-               OC, apply_tanh, out_nchw);
+  const int grid = grid_for(ceil_div((int)std::min<long long>(x.pixels(), 1 << 30), kHU), per_block, 8);
+  MAU_HEAD_DISPATCH(head_kernel, grid, 0, dv(x), w, bias, OC, apply_tanh, out_nchw);
   return 0;
 }
 int op_head_bwd(int dt, const View& x, const float* w, int OC, int apply_tanh, const float* out_nchw,
                 const float* gout_nchw, const View& gx, float* dw, float* db, cudaStream_t st) {
   if (!head_ok(x, OC) || !vec_ok(gx)) return fail("head_bwd: unsupported shape");
   const int per_block = 256 / (x.C / 8);
-  const size_t smem = (2 * OC * x.C + OC) * sizeof(float);
-  MAU_DISPATCH(dt, head_bwd_kernel, grid_for(x.pixels(), per_block, 4), 256, smem, st, dv(x), w, OC, apply_tanh,
-               out_nchw, gout_nchw, dv(gx), dw, db);
+  const size_t smem = (OC * x.C + OC) * sizeof(float);
+  const int grid = grid_for(ceil_div((int)std::min<long long>(x.pixels(), 1 << 30), kHU), per_block, 4);
+  MAU_HEAD_DISPATCH(head_bwd_kernel, grid, smem, dv(x), w, OC, apply_tanh, out_nchw, gout_nchw, dv(gx), dw, db);
   return 0;
 }
 

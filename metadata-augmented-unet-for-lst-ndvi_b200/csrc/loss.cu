@@ -7,6 +7,10 @@
 // the gradient).  SSIM (piq, third party) is not part of this kernel.
 #include "ops.h"
 #include "vec.cuh"
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace mau {
 namespace {
@@ -87,22 +91,35 @@ __global__ void loss_finalize_kernel(const double* partials, int nblocks, double
 
 }  // namespace
 
+// per-(device, stream) partial-sum scratch, allocated once: a stream-ordered cudaMallocAsync/cudaFreeAsync
+// pair per call made the pool trim and re-grow at every synchronisation
+constexpr int kMaxLossBlocks = 148 * 8;
+static double* loss_scratch(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, double*> pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  double*& p = pool[{dev, st}];
+  if (!p && cudaMalloc(reinterpret_cast<void**>(&p), sizeof(double) * 3 * kMaxLossBlocks) != cudaSuccess) p = nullptr;
+  return p;
+}
+
 int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, int W, float lambda_grad,
             float* losses, float* grad, cudaStream_t st) {
   if (kind != 0 && kind != 1) return fail("loss: kind must be 0 (L1) or 1 (MSE)");
   const long long n = (long long)B * C * H * W;
   const long long ny = (long long)B * C * (H - 1) * W, nx = (long long)B * C * H * (W - 1);
   if (n <= 0 || ny <= 0 || nx <= 0) return fail("loss: empty tensor");
-  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-  double* partials = nullptr;
-  MAU_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partials), sizeof(double) * 3 * blocks, st));
+  int blocks = (int)std::min<long long>((n + 255) / 256, kMaxLossBlocks);
+  double* partials = loss_scratch(st);
+  if (!partials) return fail("loss: scratch allocation failed");
   loss_kernel<<<blocks, 256, 0, st>>>(kind, pred, tgt, B * C, H, W, 1.f / (float)n, 1.f / (float)ny, 1.f / (float)nx,
                                       lambda_grad, partials, grad);
   MAU_LAUNCHED();
   loss_finalize_kernel<<<1, 256, 0, st>>>(partials, blocks, 1.0 / (double)n, 1.0 / (double)ny, 1.0 / (double)nx,
                                           lambda_grad, losses);
   MAU_LAUNCHED();
-  MAU_CUDA(cudaFreeAsync(partials, st));
   return 0;
 }
 

@@ -25,10 +25,15 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
   shift[c] = ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * s + beta[c];
 }
 
-// block = 256 threads = G channel groups x L pixel lanes; block b handles pixels [b*per, (b+1)*per)
-template <typename T, int NQ, typename F>
-__device__ __forceinline__ void channel_reduce(const DView& ref, long long npix, double* out, F&& body) {
+// block = 256 threads = G channel groups x L pixel lanes; block b handles pixels [b*per, (b+1)*per).
+// Every thread keeps kU pixels' worth of 16-byte loads in flight (NT tensors each) before it touches any of
+// them: these kernels have no reuse, so achieved bandwidth is bytes-in-flight / latency.
+constexpr int kU = 4;
+template <typename T, int NQ, int NT, typename F>
+__device__ __forceinline__ void channel_reduce(const DView& ref, const DView& second, long long npix, double* out,
+                                               F&& body) {
   extern __shared__ float red[];  // [NQ][256][8]
+  using Raw = typename V8<T>::Raw;
   const int G = ref.C / 8;
   const int L = 256 / G;
   const int gi = threadIdx.x % G, pl = threadIdx.x / G;
@@ -40,8 +45,30 @@ __device__ __forceinline__ void channel_reduce(const DView& ref, long long npix,
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
-  if (pl < L)
-    for (long long p = p0 + pl; p < p1; p += L) body(p, gi * 8, acc);
+  if (pl < L) {
+    const int c = gi * 8;
+    for (long long p = p0 + pl; p < p1; p += (long long)kU * L) {
+      Raw r0[kU], r1[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const long long pu = p + (long long)u * L;
+        if (pu < p1) {
+          r0[u] = V8<T>::load_raw(at<T>(ref, pu, c));
+          if (NT > 1) r1[u] = V8<T>::load_raw(at<T>(second, pu, c));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const long long pu = p + (long long)u * L;
+        if (pu < p1) {
+          float a[8], b[8];
+          V8<T>::unpack(r0[u], a);
+          if (NT > 1) V8<T>::unpack(r1[u], b);
+          body(pu, c, a, b, acc);
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -58,9 +85,7 @@ __device__ __forceinline__ void channel_reduce(const DView& ref, long long npix,
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(DView z, double* sums) {
   const long long npix = (long long)z.B * z.H * z.W;
-  channel_reduce<T, 2>(z, npix, sums, [&](long long p, int c, float (&acc)[2][8]) {
-    float v[8];
-    V8<T>::load(at<T>(z, p, c), v);
+  channel_reduce<T, 2, 1>(z, z, npix, sums, [&](long long, int, const float (&v)[8], const float (&)[8], float (&acc)[2][8]) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { acc[0][k] += v[k]; acc[1][k] = fmaf(v[k], v[k], acc[1][k]); }
   });
@@ -87,10 +112,11 @@ __global__ void bn_finalize_train_kernel(const double* sums, long long count, co
 }
 
 // block = G channel groups x L pixel lanes (like channel_reduce); per-channel coefficients live in
-// registers for the whole pixel loop
+// registers for the whole pixel loop; kU loads in flight per thread
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_relu_kernel(DView z, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, DView y) {
+  using Raw = typename V8<T>::Raw;
   const int G = z.C / 8;
   const int L = 256 / G;
   const int gi = threadIdx.x % G, pl = threadIdx.x / G;
@@ -99,12 +125,21 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(DView z, const float
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sc[k] = scale[gi * 8 + k]; sh[k] = shift[gi * 8 + k]; }
   const long long npix = (long long)z.B * z.H * z.W;
-  for (long long p = (long long)blockIdx.x * L + pl; p < npix; p += (long long)gridDim.x * L) {
-    float v[8];
-    V8<T>::load(at<T>(z, p, gi * 8), v);
+  const long long stride = (long long)gridDim.x * L;
+  for (long long p = (long long)blockIdx.x * L + pl; p < npix; p += kU * stride) {
+    Raw r[kU];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
-    V8<T>::store(at<T>(y, p, gi * 8), v);
+    for (int u = 0; u < kU; ++u)
+      if (p + u * stride < npix) r[u] = V8<T>::load_raw(at<T>(z, p + u * stride, gi * 8));
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (p + u * stride < npix) {
+        float v[8];
+        V8<T>::unpack(r[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+        V8<T>::store(at<T>(y, p + u * stride, gi * 8), v);
+      }
   }
 }
 
@@ -118,10 +153,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView z, c
   float cm[8], cr[8], sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { cm[k] = mean[gi8 + k]; cr[k] = rstd[gi8 + k]; sc[k] = scale[gi8 + k]; sh[k] = shift[gi8 + k]; }
-  channel_reduce<T, 2>(z, npix, sums, [&](long long p, int c, float (&acc)[2][8]) {
-    float g[8], zz[8];
-    V8<T>::load(at<T>(gy, p, c), g);
-    V8<T>::load(at<T>(z, p, c), zz);
+  channel_reduce<T, 2, 2>(gy, z, npix, sums, [&](long long, int, const float (&g)[8], const float (&zz)[8], float (&acc)[2][8]) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       // ReLU mask recomputed exactly as the forward did (y = relu(fma(z, scale, shift))): no read of y
@@ -153,10 +185,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView z, co
     cr[k] = rstd[gi8 + k]; cm[k] = mean[gi8 + k]; ca[k] = gamma[gi8 + k] * cr[k];
     m1[k] = (float)sums[gi8 + k] * inv_n; m2[k] = (float)sums[C + gi8 + k] * inv_n;
   }
-  channel_reduce<T, 1>(z, npix, dbias_sums, [&](long long p, int c, float (&acc)[1][8]) {
-    float g[8], zz[8], o[8];
-    V8<T>::load(at<T>(gy, p, c), g);
-    V8<T>::load(at<T>(z, p, c), zz);
+  // all kU pixels of a batch are loaded before the first is stored (dz may alias z: each thread only ever
+  // touches its own pixels, so batching is safe)
+  channel_reduce<T, 1, 2>(gy, z, npix, dbias_sums, [&](long long p, int c, const float (&g)[8], const float (&zz)[8], float (&acc)[1][8]) {
+    float o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float gt = fmaf(zz[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;

@@ -23,10 +23,12 @@ struct BilinearTables {          // device arrays owned by the plan
   // transposed (gather) form for the backward: CSR over input rows / cols
   int* ty_off = nullptr; int* ty_idx = nullptr; float* ty_w = nullptr;
   int* tx_off = nullptr; int* tx_idx = nullptr; float* tx_w = nullptr;
+  int max_fan_w = 1 << 30;     // most contributions any source column receives (selects the batched backward)
 };
 struct BilinearHost {            // host mirror used to build the tables
   std::vector<int> i0, i1; std::vector<float> l;
   std::vector<int> t_off, t_idx; std::vector<float> t_w;
+  int max_fan = 0;
 };
 void bilinear_axis_tables(int in, int out, BilinearHost* h);   // PyTorch's index / lambda rule in fp32
 int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st);

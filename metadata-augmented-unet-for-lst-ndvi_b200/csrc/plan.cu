@@ -1,5 +1,6 @@
 // plan.cu -- builds and runs the layer graph (see plan.h).
 #include "plan.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <sstream>
@@ -232,9 +233,10 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
   int ci_w0 = 0;
   int dacc[4] = {0, 0, 0, 0};
   L->Kd = round_up(C, 64);
+  L->wg_swap = (use_tc && wgrad_ws) ? wgrad_tc_pick_swap(C, L->nseg, L->seg_len) : 0;
   for (int s = 0; s < L->nseg; ++s) {
     const TRef xin{L->in_buf, L->seg_start[s], L->seg_len[s]};
-    if (use_tc) MAU_TRY(wgrad_tc_prepare(&L->wg[s], view(xin), z, ci_w0, L->Cin));
+    if (use_tc) MAU_TRY(wgrad_tc_prepare(&L->wg[s], view(xin), z, ci_w0, L->Cin, wgrad_ws, L->wg_swap));
     if (L->input_needs_grad) {
       View gx;
       MAU_TRY(gview(xin, &gx));
@@ -265,7 +267,9 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
     MAU_TRY(op_bn_bwd_finalize(L->sums, L->dbsum, C, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
     float* dw = c.g(L->iw);
     int ci_w0 = 0;
-    if (dw) MAU_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * L->Cin * 9, c.st));
+    const bool ws_path = use_tc && wgrad_ws != nullptr;      // v2 wgrad: reduce into the workspace, then transpose
+    if (dw && ws_path) MAU_CUDA(cudaMemsetAsync(wgrad_ws, 0, sizeof(float) * wgrad_tc_workspace_floats(C, L->Cin, L->wg_swap), c.st));
+    else if (dw) MAU_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * L->Cin * 9, c.st));
     for (int s = 0; s < L->nseg; ++s) {
       const TRef xin{L->in_buf, L->seg_start[s], L->seg_len[s]};
       if (dw) {
@@ -284,6 +288,7 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
       }
       ci_w0 += L->seg_len[s];
     }
+    if (dw && ws_path) MAU_TRY(wgrad_tc_finalize(wgrad_ws, L->wg_swap, C, L->Cin, dw, c.st));
     return 0;
   };
   bwd.push_back(op);
@@ -325,6 +330,7 @@ int Plan::make_bilinear(int Hin, int Win, int Hout, int Wout, BilinearTables* t)
   t->x0 = up_i(hx.i0); t->x1 = up_i(hx.i1); t->lx = up_f(hx.l);
   t->ty_off = up_i(hy.t_off); t->ty_idx = up_i(hy.t_idx); t->ty_w = up_f(hy.t_w);
   t->tx_off = up_i(hx.t_off); t->tx_idx = up_i(hx.t_idx); t->tx_w = up_f(hx.t_w);
+  t->max_fan_w = hx.max_fan;
   if (!t->tx_w || !t->ty_w) return -1;
   return 0;
 }
@@ -766,6 +772,14 @@ int Plan::build() {
   int rc = cfg.model_type == MAU_MODEL_UNET ? build_unet() : build_unetpp();
   if (rc) return rc;
   if (cfg.training) {
+    if (use_tc && !(cfg.flags & MAU_FLAG_WGRAD_V1)) {
+      // one fp32 workspace [9][Cout][Cin] shared by all layers (backward ops are serialised on one stream)
+      size_t fl = 0;
+      for (const ConvLayer* L : layers) fl = std::max(fl, (size_t)9 * round_up(L->Cout, 4) * round_up(L->Cin, 4));
+      wgrad_ws = static_cast<float*>(alloc(sizeof(float) * fl));
+      if (dry) wgrad_ws = reinterpret_cast<float*>(16);
+      else if (!wgrad_ws) return -1;
+    }
     for (auto it = bwd_makers.rbegin(); it != bwd_makers.rend(); ++it) MAU_TRY((*it)());
     if (!dry) {
       // counters (num_batches_tracked) are bumped by one tiny kernel per forward

@@ -74,6 +74,7 @@ struct ConvLayer {
   ConvTcOp tc; ConvFfmaParams ff;
   ConvTcOp tc_d[4]; ConvFfmaParams ff_d[4];
   WgradTcOp wg[4];
+  int wg_swap = 0;          // wgrad v2 orientation (see wgrad_tc.cu)
 };
 
 class Plan {
@@ -134,6 +135,7 @@ class Plan {
   float* emb = nullptr; float* demb = nullptr; float* hidden = nullptr; float* hlast = nullptr;
   float* dhlast = nullptr; float* lstm_save = nullptr;
   int emb_dim = 0;
+  float* wgrad_ws = nullptr;   // fp32 [9][Cout][Cin] scratch of the tcgen05 weight-gradient kernel
 };
 
 }  // namespace mau

@@ -9,6 +9,17 @@ namespace mau {
 template <typename T> struct V8;
 
 template <> struct V8<__nv_bfloat16> {
+  // raw 16-byte load (kept packed in 4 registers until it is needed: lets a thread keep many loads in flight)
+  struct Raw { uint4 u; };
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return Raw{*reinterpret_cast<const uint4*>(p)}; }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[8]) {
+    const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -32,6 +43,13 @@ template <> struct V8<__nv_bfloat16> {
 };
 
 template <> struct V8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+    return Raw{*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)};
+  }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[8]) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p);
     const float4 b = *reinterpret_cast<const float4*>(p + 4);

@@ -16,6 +16,8 @@
 #include "conv_tc.h"
 #include "ptx.cuh"
 #include "tma.h"
+#include <algorithm>
+#include <cstdlib>
 
 namespace mau {
 using namespace ptx;
@@ -171,37 +173,347 @@ int launch_wgrad(const WgradTcOp& op, const WgradParams& p, float* dw, cudaStrea
   return 0;
 }
 
+
+// ==========================================================================================
+// v2: persistent split-K / stream-K weight gradient with a TMA reduce-add epilogue.
+//
+//   pixel tile  = 16 wide x 4 high (64 pixels = one pipeline stage, K = 64): dY boxes {64 ch, 16, 4},
+//                 X halo boxes {64 ch, 18, 4} at (w0-1, h0+r-1).  One tcgen05.mma (K = 16) consumes one
+//                 tile row: the two 8-pixel K groups are 1024 B apart in both boxes; the horizontal tap s
+//                 is a start offset of s pixels into the halo row.
+//   work unit   = (128-wide M tile, BN-wide N tile, filter row r): three fp32 accumulators (one per
+//                 horizontal tap) of 128 x BN in TMEM.  M is the output-channel side and N the input-
+//                 channel side, or the other way round (SWAP) when that wastes less of the 128-row tile
+//                 (Cout = 64 layers): both operands are MN-major straight out of NHWC, so the roles are
+//                 interchangeable.
+//   scheduling  = the (unit, pixel-tile) space is cut into equal contiguous ranges, one per CTA.  With
+//                 few units every unit is split S ways (classic split-K: the CTAs of one split walk the
+//                 same pixels for different units at the same time, so dY / X are shared through L2);
+//                 with many units (small images, wide layers -- the activations fit L2) the ranges are
+//                 stream-K slices of the unit-major list over all SMs, a CTA may finish one unit and
+//                 start the next.  No wave quantisation either way.
+//   epilogue    = TMEM -> registers -> 128-byte-swizzled fp32 staging tile (128 x 32) -> TMA reduce-add
+//                 into a zeroed fp32 workspace [9][M dim][N dim]; wgrad_finalize_kernel transposes the
+//                 workspace into the caller's OIHW gradient.
+// ==========================================================================================
+constexpr int kDyBox2 = 8192;     // {64, 16, 4} bf16
+constexpr int kXBox2 = 9216;      // {64, 18, 4} bf16
+constexpr int kStgTile = 16384;   // 128 rows x 32 fp32
+
+struct WgradV2Params {
+  int tiles_w, tiles_h;      // 16x4 pixel tiles per image
+  int T;                     // pixel tiles in the whole batch
+  int m_tiles, n_tiles;      // units = m_tiles * n_tiles * 3
+  long long atoms;           // units * T
+  int ws_m0, ws_n0;          // workspace coordinates of this segment's first M / N channel
+};
+
+template <int BN, bool SWAP, int STAGES>
+struct WgradV2Smem {
+  static constexpr int NDY = SWAP ? BN / 64 : 2;
+  static constexpr int NX = SWAP ? 2 : BN / 64;
+  static constexpr int kStage = NDY * kDyBox2 + NX * kXBox2;
+  static constexpr size_t kBytes = 1024 + (size_t)STAGES * kStage + 2 * kStgTile + 8 * (2 * STAGES + 2) + 16;
+};
+
+struct UnitCoord { int m, n, r; };
+__device__ __forceinline__ UnitCoord decode_unit(int u, int n_tiles) {
+  UnitCoord c;
+  c.r = u % 3;
+  const int q = u / 3;
+  c.n = q % n_tiles;
+  c.m = q / n_tiles;
+  return c;
+}
+
+template <int BN, bool SWAP, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) wgrad3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmDy,
+                                                                    const __grid_constant__ CUtensorMap tmX,
+                                                                    const __grid_constant__ CUtensorMap tmWs,
+                                                                    const WgradV2Params p) {
+  using S = WgradV2Smem<BN, SWAP, STAGES>;
+  constexpr int kTmemCols = BN == 64 ? 256 : 512;        // 3 accumulators of BN columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sStg = smem + STAGES * S::kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * kStgTile);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long a0 = (long long)blockIdx.x * p.atoms / gridDim.x;
+  const long long a1 = (long long)(blockIdx.x + 1) * p.atoms / gridDim.x;
+  const int tiles_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmDy); prefetch_tensormap(&tmX); prefetch_tensormap(&tmWs);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    int stage = 0; uint32_t phase = 0;
+    for (long long a = a0; a < a1;) {
+      const int u = (int)(a / p.T);
+      const int t0 = (int)(a - (long long)u * p.T);
+      const int t1 = (int)min((long long)p.T, (long long)t0 + (a1 - a));
+      const UnitCoord uc = decode_unit(u, p.n_tiles);
+      const int co0 = SWAP ? uc.n * BN : uc.m * 128;
+      const int ci0 = SWAP ? uc.m * 128 : uc.n * BN;
+      for (int t = t0; t < t1; ++t) {
+        const int b = t / tiles_img;
+        const int rem = t - b * tiles_img;
+        const int th = rem / p.tiles_w;
+        const int h0 = th * 4, w0 = (rem - th * p.tiles_w) * 16;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], S::kStage);
+          uint8_t* s = smem + stage * S::kStage;
+#pragma unroll
+          for (int j = 0; j < S::NDY; ++j) tma_load_4d(s + j * kDyBox2, &tmDy, &full[stage], co0 + 64 * j, w0, h0, b);
+#pragma unroll
+          for (int j = 0; j < S::NX; ++j)
+            tma_load_4d(s + S::NDY * kDyBox2 + j * kXBox2, &tmX, &full[stage], ci0 + 64 * j, w0 - 1, h0 + uc.r - 1, b);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      a += t1 - t0;
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    // both operands MN-major: 64-channel groups at LBO = one box, 8-pixel K groups at SBO = 1024 B
+    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 1, 1);
+    const uint64_t descDy0 = smem_desc_sw128(0, kDyBox2, 1024, 0);
+    const uint64_t descX0 = smem_desc_sw128(0, kXBox2, 1024, 0);
+    int stage = 0; uint32_t phase = 0, ephase = 0;
+    for (long long a = a0; a < a1;) {
+      const int u = (int)(a / p.T);
+      const int t0 = (int)(a - (long long)u * p.T);
+      const int t1 = (int)min((long long)p.T, (long long)t0 + (a1 - a));
+      mbar_wait(tmem_empty, ephase ^ 1);       // the epilogue has drained the previous unit's accumulators
+      ephase ^= 1;
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * S::kStage);
+        const uint64_t dDy = descDy0 + (uint64_t)(sa >> 4);
+        const uint64_t dX = descX0 + (uint64_t)((sa + S::NDY * kDyBox2) >> 4);
+        const uint32_t first = t > t0 ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {     // one tile row (16 pixels) per instruction
+              const uint64_t ddy = dDy + (uint64_t)((h * 2048) >> 4);
+              const uint64_t dx = dX + (uint64_t)(((h * 18 + sx) * 128) >> 4);
+              umma_bf16(tmem_base + sx * BN, SWAP ? dx : ddy, SWAP ? ddy : dx, idesc, h ? 1u : first);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (t == t1 - 1) umma_commit(tmem_full);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      a += t1 - t0;
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t fphase = 0;
+    int sb = 0;
+    for (long long a = a0; a < a1;) {
+      const int u = (int)(a / p.T);
+      const int t0 = (int)(a - (long long)u * p.T);
+      const int t1 = (int)min((long long)p.T, (long long)t0 + (a1 - a));
+      const UnitCoord uc = decode_unit(u, p.n_tiles);
+      mbar_wait(tmem_full, fphase);
+      fphase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int sx = 0; sx < 3; ++sx) {
+#pragma unroll 1
+        for (int part = 0; part < BN / 32; ++part) {
+          uint8_t* stg = sStg + sb * kStgTile;
+          const bool last = sx == 2 && part == BN / 32 - 1;
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // staging tile sb is free again
+          named_bar_sync(1, 128);
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + sx * BN + part * 32, v);
+          tmem_ld_wait();
+          uint8_t* rowp = stg + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (last) tc_fence_before();
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            if (last) mbar_arrive(tmem_empty);
+            tma_reduce_add_3d(&tmWs, stg, p.ws_n0 + uc.n * BN + part * 32, p.ws_m0 + uc.m * 128, uc.r * 3 + sx);
+            tma_commit_group();
+          }
+          sb ^= 1;
+        }
+      }
+      a += t1 - t0;
+    }
+    if (et == 0) tma_wait_group0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// workspace [9][D1][ld0] -> OIHW.  normal: D1 = Cout, inner = ci; swapped: D1 = Cin, inner = co.
+__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, int swap, int Cout, int Cin, int ld0,
+                                      float* __restrict__ dw) {
+  const long long total = (long long)Cout * Cin;
+  const long long plane = (long long)(swap ? Cin : Cout) * ld0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int co, ci;
+    long long src;
+    if (!swap) { ci = (int)(i % Cin); co = (int)(i / Cin); src = (long long)co * ld0 + ci; }
+    else       { co = (int)(i % Cout); ci = (int)(i / Cout); src = (long long)ci * ld0 + co; }
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = ws[t * plane + src];
+    float* dst = dw + ((long long)co * Cin + ci) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) dst[t] = v[t];
+  }
+}
+
+template <int BN, bool SWAP, int STAGES>
+int launch_wgrad_v2(const WgradTcOp& op, const WgradV2Params& p, cudaStream_t st) {
+  using S = WgradV2Smem<BN, SWAP, STAGES>;
+  static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = wgrad3x3_tc_v2_kernel<BN, SWAP, STAGES>;
+  if (!attr_done[dev & 15]) {
+    MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    attr_done[dev & 15] = true;
+  }
+  kern<<<op.grid, kThreads, S::kBytes, st>>>(op.tmDy, op.tmX, op.tmWs, p);
+  MAU_LAUNCHED();
+  return 0;
+}
+
 }  // namespace
 
-int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0, int Cin_w) {
+// tile-padding cost of one orientation: sum over segments of (padded M x padded N), N = 64 instructions
+// discounted for their shared-memory operand bandwidth limit
+static double orient_cost(int Cout, int nseg, const int* seg_len, bool swap) {
+  double c = 0;
+  for (int s = 0; s < nseg; ++s) {
+    const int Md = swap ? seg_len[s] : Cout, Nd = swap ? Cout : seg_len[s];
+    const int bn = Nd <= 64 ? 64 : 128;
+    c += (double)ceil_div(Md, 128) * 128 * ceil_div(Nd, bn) * bn / (bn == 64 ? 0.67 : 1.0);
+  }
+  return c;
+}
+int wgrad_tc_pick_swap(int Cout, int nseg, const int* seg_len) {
+  if (const char* e = getenv("MAU_WGRAD_SWAP")) return atoi(e) != 0;
+  return orient_cost(Cout, nseg, seg_len, true) < orient_cost(Cout, nseg, seg_len, false) ? 1 : 0;
+}
+size_t wgrad_tc_workspace_floats(int Cout, int Cin_w, int swap) {
+  const int d0 = swap ? Cout : Cin_w, d1 = swap ? Cin_w : Cout;
+  return (size_t)9 * d1 * round_up(d0, 4);
+}
+
+int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0, int Cin_w, float* ws, int swap) {
   if (x_seg.B != dy.B || x_seg.H != dy.H || x_seg.W != dy.W) return fail("wgrad_tc: geometry mismatch");
   if (x_seg.cs % 8 || x_seg.c0 % 8 || dy.cs % 8 || dy.c0 % 8) return fail("wgrad_tc: views must be 8-channel aligned");
   op->B = dy.B; op->H = dy.H; op->W = dy.W;
   op->Cout = dy.C; op->Cin = x_seg.C; op->ci_w0 = ci_w0; op->Cin_w = Cin_w;
-  op->bn = x_seg.C <= 64 ? 64 : 128;
-  op->n_tiles = ceil_div(x_seg.C, op->bn);
-  op->m_tiles = ceil_div(dy.C, 128);
-  const int total_tiles = dy.B * ceil_div(dy.H, 8) * ceil_div(dy.W, 8);
-  int want = ceil_div(148 * 2, op->n_tiles * op->m_tiles * 3);
-  if (want < 1) want = 1;
-  if (want > total_tiles) want = total_tiles;
-  op->tiles_per_split = ceil_div(total_tiles, want);
-  op->splits = ceil_div(total_tiles, op->tiles_per_split);
-  op->grid = dim3((unsigned)op->n_tiles, (unsigned)op->m_tiles, (unsigned)(3 * op->splits));
-  MAU_TRY(make_nhwc_map(&op->tmDy, DT_BF16, dy, 64, 8, 8));
-  MAU_TRY(make_nhwc_map(&op->tmX, DT_BF16, x_seg, 64, 10, 8));
+  op->ws = ws; op->swap = swap;
+  if (!ws) {          // v1: one CTA per (tile, filter row, pixel split), atomics into the OIHW gradient
+    op->bn = x_seg.C <= 64 ? 64 : 128;
+    op->n_tiles = ceil_div(x_seg.C, op->bn);
+    op->m_tiles = ceil_div(dy.C, 128);
+    const int total_tiles = dy.B * ceil_div(dy.H, 8) * ceil_div(dy.W, 8);
+    int want = ceil_div(148 * 2, op->n_tiles * op->m_tiles * 3);
+    if (want < 1) want = 1;
+    if (want > total_tiles) want = total_tiles;
+    op->tiles_per_split = ceil_div(total_tiles, want);
+    op->splits = ceil_div(total_tiles, op->tiles_per_split);
+    op->grid = dim3((unsigned)op->n_tiles, (unsigned)op->m_tiles, (unsigned)(3 * op->splits));
+    MAU_TRY(make_nhwc_map(&op->tmDy, DT_BF16, dy, 64, 8, 8));
+    MAU_TRY(make_nhwc_map(&op->tmX, DT_BF16, x_seg, 64, 10, 8));
+    return 0;
+  }
+  const int Md = swap ? x_seg.C : dy.C, Nd = swap ? dy.C : x_seg.C;
+  op->bn = Nd <= 64 ? 64 : 128;
+  op->m_tiles = ceil_div(Md, 128);
+  op->n_tiles = ceil_div(Nd, op->bn);
+  const int T = dy.B * ceil_div(dy.H, 4) * ceil_div(dy.W, 16);
+  const int U = op->m_tiles * op->n_tiles * 3;
+  const int sms = sm_budget();
+  int G;
+  if (2 * U <= sms) G = U * std::min(sms / U, T);                                   // split-K, units in lock step
+  else G = (int)std::min<long long>(sms, (long long)U * T);                        // stream-K over all SMs
+  op->grid = dim3((unsigned)G, 1, 1);
+  MAU_TRY(make_nhwc_map(&op->tmDy, DT_BF16, dy, 64, 16, 4));
+  MAU_TRY(make_nhwc_map(&op->tmX, DT_BF16, x_seg, 64, 18, 4));
+  {   // workspace [9][D1][ld0] fp32, box {32, 128, 1}
+    const int d0 = swap ? dy.C : Cin_w, d1 = swap ? Cin_w : dy.C;
+    uint64_t dims[3] = {(uint64_t)d0, (uint64_t)d1, 9};
+    uint64_t str[2] = {(uint64_t)round_up(d0, 4) * 4, (uint64_t)round_up(d0, 4) * 4 * (uint64_t)d1};
+    uint32_t box[3] = {32, 128, 1};
+    MAU_TRY(make_tensor_map(&op->tmWs, DT_F32, 3, ws, dims, str, box, true));
+  }
   return 0;
 }
 
 int wgrad_tc_launch(const WgradTcOp& op, float* dw_oihw, cudaStream_t st) {
-  WgradParams p;
-  p.B = op.B; p.H = op.H; p.W = op.W;
-  p.tiles_w = ceil_div(op.W, 8); p.tiles_h = ceil_div(op.H, 8);
-  p.Cout = op.Cout; p.Cin = op.Cin; p.ci_w0 = op.ci_w0; p.Cin_w = op.Cin_w;
-  p.tiles_per_split = op.tiles_per_split;
-  p.total_tiles = op.B * p.tiles_w * p.tiles_h;
-  if (op.bn == 64) return launch_wgrad<64, 6>(op, p, dw_oihw, st);
-  return launch_wgrad<128, 5>(op, p, dw_oihw, st);
+  if (!op.ws) {
+    WgradParams p;
+    p.B = op.B; p.H = op.H; p.W = op.W;
+    p.tiles_w = ceil_div(op.W, 8); p.tiles_h = ceil_div(op.H, 8);
+    p.Cout = op.Cout; p.Cin = op.Cin; p.ci_w0 = op.ci_w0; p.Cin_w = op.Cin_w;
+    p.tiles_per_split = op.tiles_per_split;
+    p.total_tiles = op.B * p.tiles_w * p.tiles_h;
+    if (op.bn == 64) return launch_wgrad<64, 6>(op, p, dw_oihw, st);
+    return launch_wgrad<128, 5>(op, p, dw_oihw, st);
+  }
+  WgradV2Params p;
+  p.tiles_w = ceil_div(op.W, 16); p.tiles_h = ceil_div(op.H, 4);
+  p.T = op.B * p.tiles_w * p.tiles_h;
+  p.m_tiles = op.m_tiles; p.n_tiles = op.n_tiles;
+  p.atoms = (long long)op.m_tiles * op.n_tiles * 3 * p.T;
+  p.ws_m0 = op.swap ? op.ci_w0 : 0;
+  p.ws_n0 = op.swap ? 0 : op.ci_w0;
+  if (op.bn == 64) return op.swap ? launch_wgrad_v2<64, true, 6>(op, p, st) : launch_wgrad_v2<64, false, 6>(op, p, st);
+  return op.swap ? launch_wgrad_v2<128, true, 5>(op, p, st) : launch_wgrad_v2<128, false, 5>(op, p, st);
+}
+
+int wgrad_tc_finalize(const float* ws, int swap, int Cout, int Cin_w, float* dw_oihw, cudaStream_t st) {
+  const int d0 = swap ? Cout : Cin_w;
+  const long long total = (long long)Cout * Cin_w;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, swap, Cout, Cin_w, round_up(d0, 4), dw_oihw);
+  MAU_LAUNCHED();
+  return 0;
 }
 
 }  // namespace mau

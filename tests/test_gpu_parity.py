@@ -58,9 +58,13 @@ def test_conv3x3_against_torch(impl, dt, shape):
     assert rel(y.permute(0, 3, 1, 2), ref) < (6e-3 if dt == 0 else 1e-5)
 
 
-@pytest.mark.parametrize("impl,dt", [(0, 0), (2, 1)])
-@pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64), (2, 15, 15, 128, 256), (2, 33, 47, 24, 64), (1, 25, 25, 8, 8)])
+@pytest.mark.parametrize("impl,dt", [(0, 0), (4, 0), (5, 0), (1, 0), (2, 1)])
+@pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64), (2, 15, 15, 128, 256), (2, 33, 47, 24, 64), (1, 25, 25, 8, 8),
+                                   (2, 15, 15, 640, 640), (1, 31, 31, 192, 64), (3, 18, 50, 72, 200)])
 def test_wgrad_against_torch(impl, dt, shape):
+    """impl 0 = persistent split-K/stream-K tcgen05 kernel (auto orientation), 4 / 5 = M side forced to the
+    output / input channels, 1 = first-generation atomics kernel, 2 = FFMA.  (2,15,15,640,640) has more work
+    units than SMs/2 and runs the stream-K schedule (CTAs straddle units)."""
     B, H, W, Cin, Cout = shape
     torch.manual_seed(2)
     dtype = torch.bfloat16 if dt == 0 else torch.float32

@@ -50,5 +50,31 @@ def main():
         print(f"{name:11s} {H:3d} {Cin:4d}->{Cout:4d} | " + " | ".join(res), flush=True)
 
 
+def wgrad():
+    """weight gradient: v2 auto / forced orientations vs the first-generation atomics kernel"""
+    L = engine.lib()
+    B = int(os.environ.get("B", "16"))
+    only = [a for a in sys.argv[1:] if a != "wgrad"]
+    for name, H, Cin, Cout in LAYERS + [("conv0_0.1", 250, 24, 64), ("conv1_0.1", 125, 64, 128), ("conv4_0.1", 15, 576, 1024)]:
+        if name.startswith("dgrad") or (only and name not in only):
+            continue
+        x = torch.randn(B, H, H, Cin, device="cuda").bfloat16()
+        dy = torch.randn(B, H, H, Cout, device="cuda").bfloat16()
+        dw = torch.zeros(Cout, Cin, 3, 3, device="cuda")
+        flops = 2.0 * 9 * Cin * Cout * H * H * B
+        res = []
+        for label, impl in (("v2", 0), ("v2 M=co", 4), ("v2 M=ci", 5), ("v1", 1)):
+            ms = C.c_float()
+            rc = L.mau_op_conv3x3_wgrad_bench(impl, x.data_ptr(), dy.data_ptr(), B, H, H, Cin, Cin, Cout, Cout, dw.data_ptr(), 10, C.byref(ms))
+            if rc:
+                res.append(f"{label}: ERR {L.mau_last_error().decode()[:60]}")
+            else:
+                res.append(f"{label}: {ms.value*1e3:7.1f}us {flops/ms.value/1e9:6.0f}TF")
+        print(f"wgrad {name:11s} {H:3d} {Cin:4d}->{Cout:4d} | " + " | ".join(res), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "wgrad" in sys.argv[1:]:
+        wgrad()
+    else:
+        main()
