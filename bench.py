@@ -23,6 +23,17 @@ sys.path.insert(0, ROOT)
 TILE = 250
 CTOR = (23, 828, 64, 8, 64, 96, 2)           # conf/config.yaml:18-20,49-51; out_channels 2
 KW = dict(temporal_embeddings=False, metadata_embeddings=True)
+# BASELINE.json configs[] -> (model_type, ctor kwargs, workload, per-GPU batch, shared maps, description)
+CONFIGS = {
+    2: ("unet", dict(temporal_embeddings=False, metadata_embeddings=True), "infer", 16, False,
+        "Metadata-Augmented U-Net (metadata MLP fused at bottleneck) inference, synthetic 23x250x250 tiles"),
+    3: ("unet", dict(temporal_embeddings=False, metadata_embeddings=True), "train", 16, False,
+        "Metadata-Augmented U-Net training fwd+L1+bwd+AdamW, data-parallel, synthetic 23x250x250 tiles"),
+    4: ("unet++", dict(), "train", 16, False,
+        "U-Net++ (LSTM + metadata embeddings throughout the decoder) training fwd+L1+bwd+AdamW, synthetic 23x250x250 tiles"),
+    5: ("unet", dict(temporal_embeddings=True, metadata_embeddings=True), "infer", 50, True,
+        "U-Net + LSTM + metadata, metadata-sensitivity sweep: 50 rows share one tile and series (test/metadata_sensitivity.py:294-311)"),
+}
 
 
 def peaks():
@@ -65,7 +76,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference(workload, batch, iters, warm=1):
+def cpu_reference(workload, batch, iters, warm=1, mt="unet", kw=None, shared=False):
     """The reference algorithm on the host cores: oracle/unet_oracle.py (functional torch CPU fp32,
     same ATen kernels the reference module dispatches to).  Uses every host core: torchrun exports
     OMP_NUM_THREADS=1 to its workers, which would otherwise pin the CPU arm to one thread."""
@@ -73,19 +84,22 @@ def cpu_reference(workload, batch, iters, warm=1):
     import mau_b200
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     from oracle import unet_oracle as O
+    kw = KW if kw is None else kw
     torch.manual_seed(42)
-    m = mau_b200.UrbanPredictor("unet", *CTOR, **KW)
+    m = mau_b200.UrbanPredictor(mt, *CTOR, **kw)
     O.perturb_bn_stats(m.state_dict())
     sd = m.state_dict()
     x, ts, md, tgt = O.synthetic_batch(batch, TILE, TILE, seed=1002)
+    if shared:      # the reference materialises the repeated batch (test/metadata_sensitivity.py:294-307)
+        x, ts = x[:1].repeat(batch, 1, 1, 1), ts[:1].repeat(batch, 1)
     times = []
     for i in range(warm + iters):
         t0 = time.perf_counter()
         if workload == "infer":
             with torch.no_grad():
-                O.forward(sd, "unet", x, ts, md, training=False, **KW)
+                O.forward(sd, mt, x, ts, md, training=False, **kw)
         else:
-            O.train_step_grads(sd, "unet", x, ts, md, tgt, loss="l1", **KW)
+            O.train_step_grads(sd, mt, x, ts, md, tgt, loss="l1", **kw)
         if i >= warm:
             times.append(time.perf_counter() - t0)
     return batch * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads()
@@ -107,29 +121,34 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
-    ap.add_argument("--batch", type=int, default=16, help="tiles per GPU per step (conf/config.yaml:45)")
+    ap.add_argument("--workload", default=None, choices=["infer", "train"], help="shorthand: infer = --config 2, train = --config 3")
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE.json configs[] index (default 2)")
+    ap.add_argument("--batch", type=int, default=None, help="tiles per GPU per step (default: conf/config.yaml:45 = 16; 50 for the sweep)")
+    ap.add_argument("--comm-ctas", type=int, default=8, help="data-parallel training: CTAs NCCL may use (and SMs our persistent kernels leave free)")
+    ap.add_argument("--sync-bn", action="store_true", help="data-parallel training: SyncBN (global-batch statistics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="print per-layer device times to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_id = args.config if args.config is not None else (3 if args.workload == "train" else 2)
+    mt, kw, workload, def_batch, shared, workload_name = CONFIGS[cfg_id]
+    args.workload = workload
+    if args.batch is None:
+        args.batch = def_batch
     metric = "inference tiles/sec" if args.workload == "infer" else "training tiles/sec (fwd+bwd)"
-    workload_name = ("Metadata-Augmented U-Net (metadata MLP fused at bottleneck) inference, synthetic 23x250x250 tiles"
-                     if args.workload == "infer" else
-                     "Metadata-Augmented U-Net training fwd+L1+bwd, data-parallel, synthetic 23x250x250 tiles")
 
     if args.impl == "reference":
         if rank != 0:
             return
         sample = 8 if args.workload == "infer" else 4
-        v, sec, threads = cpu_reference(args.workload, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+        v, sec, threads = cpu_reference(args.workload, sample, max(1, args.steps), max(1, min(args.warmup, 1)), mt, kw, shared)
         emit({
             "impl": "reference", "metric": metric, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name, "tile": [23, TILE, TILE], "batch_per_step": sample, "device": "cpu"},
+            "config": {"workload": workload_name, "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_step": sample, "device": "cpu"},
             "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} tiles per step, {max(1, args.steps)} timed steps, oracle/unet_oracle.py on torch CPU fp32"},
             "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -143,34 +162,57 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    train = args.workload == "train"
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if train:
+            # the gradient all-reduce runs concurrently with the persistent conv / wgrad kernels: cap NCCL's
+            # CTA count and leave that many SMs out of our persistent grids (no second-wave cliff)
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = max(1, args.comm_ctas)
+            opts.config.min_ctas = 1
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+            engine.lib().mau_set_sm_reserve(max(0, args.comm_ctas))
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(42)
-    model = mau_b200.UrbanPredictor("unet", *CTOR, **KW)
+    model = mau_b200.UrbanPredictor(mt, *CTOR, **kw)
     O.perturb_bn_stats(model.state_dict())
     model = model.to(dev)
-    train = args.workload == "train"
     model.train(train)
     if train and world > 1:
         from mau_b200 import parallel
-        parallel.DataParallel(model)         # registers the overlapped all-reduce on the plan's grad hook
+        parallel.DataParallel(model, sync_bn=args.sync_bn)   # overlapped all-reduce on the plan's grad hook
     # several distinct input batches so that consecutive steps never re-read L2-resident inputs
     nb = 4
     host = [O.synthetic_batch(B, TILE, TILE, seed=1002 + 17 * rank + i) for i in range(nb)]
+    if shared:      # sweep: ONE tile and series per step (the reference repeats them on the device), B metadata rows
+        def sweep(h):
+            x, ts, md, tgt = h
+            md = md.clone()
+            md[:, 0] = torch.linspace(-2.0, 2.0, B)          # test/metadata_sensitivity.py:296-304
+            return x[:1].contiguous(), ts[:1].contiguous(), md, tgt
+        host = [sweep(h) for h in host]
     pinned = [tuple(t.pin_memory() for t in h) for h in host]
     devb = [tuple(t.to(dev) for t in h) for h in host]
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3) if train else None
+    # same optimizer as the reference (src/train.py:213-214, conf/config.yaml:41,52), one fused launch per step
+    opt = mau_b200.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-3) if train else None
+
+    def fwd(x, ts, md):
+        if shared:      # one tile + one series, B metadata rows (batch-expanded views select the sweep plan)
+            return model.forward_sweep(x, ts, md)
+        return model(x, ts, md)
 
     def step(i, batch):
         x, ts, md, tgt = batch
         if not train:
             with torch.no_grad():
-                return model(x, ts, md)
+                return fwd(x, ts, md)
         out = model(x, ts, md)
         loss = engine.compute_loss_l1_grad(out, tgt, 0.0)["total"]      # L1 via the fused loss kernel
         loss.backward()
-        opt.zero_grad(set_to_none=True)      # optimizer step is reported separately
+        opt.step()                            # fused AdamW: inside the timed region
+        opt.zero_grad(set_to_none=True)
         return loss
 
     def barrier():
@@ -227,11 +269,12 @@ def main():
                 t_.record_stream(main_s)
             if not train:
                 with torch.no_grad():
-                    res = model(xd, td, mdd)
+                    res = fwd(xd, td, mdd)
             else:
                 out_ = model(xd, td, mdd)
                 res = engine.compute_loss_l1_grad(out_, tg, 0.0)["total"]
                 res.backward()
+                opt.step()
                 opt.zero_grad(set_to_none=True)
                 res = res.detach()
             out_host[i % 2].copy_(res, non_blocking=True)          # D2H of the step's result
@@ -268,27 +311,37 @@ def main():
         step(i, devb[i % nb])
         torch.cuda.synchronize()
         for name, t_ms in plan.profile_read():
-            all_ms += t_ms
-            if ".conv" in name:
+            if name.startswith("k:"):        # CUDA events right around one conv / dgrad / wgrad kernel launch
                 conv_ms += t_ms
                 conv_n += 1
+            else:                            # per-op entries (a conv op also holds its BN / pack / memset launches)
+                all_ms += t_ms
             if args.profile_layers and i == reps - 1 and rank == 0:
-                print(f"{name:28s} {t_ms:8.3f} ms", file=sys.stderr)
+                print(f"{name:36s} {t_ms:8.3f} ms", file=sys.stderr)
     plan.profile(False)
-    fwd_flops, bwd_flops = plan.flops()
+    fwd_flops, bwd_flops = plan.flops()              # dense reference graph (SURVEY.md 8d numerators)
+    exec_fwd = plan.exec_conv_flops()                # what the conv kernels execute per forward
     pk = peaks()
-    conv_flops = (fwd_flops + (bwd_flops if train else 0.0))
-    achieved_tf = conv_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    # kernel roofline: FLOPs the timed kernels executed / their summed launch durations.  Training backward =
+    # dgrad + wgrad of every conv (no dgrad for the first layer) = bwd_flops of the plan.
+    kern_flops = exec_fwd + (bwd_flops if train else 0.0)
+    achieved_tf = kern_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # from the committed ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"config{cfg_id}", {}).get("dram_bytes_per_launch")
     roof = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved_tf / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"],
-            "kernel": "conv3x3_tc_kernel (+wgrad3x3_tc_kernel in training)",
+            "frac": achieved_tf / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["src"],
+            "kernel": "conv3x3_tc_v2_kernel (+wgrad3x3_tc_v2_kernel in training)",
+            "launches_timed": conv_n // reps, "avg_launch_us": conv_ms / max(conv_n, 1) * 1e3,
+            "flop_per_launch": kern_flops * reps / max(conv_n, 1),
             "conv_share_of_step": conv_ms / all_ms if all_ms else None,
-            "algorithmic_gflop_per_tile": conv_flops / B / 1e9}
+            "algorithmic_gflop_per_tile": (fwd_flops + (bwd_flops if train else 0.0)) / B / 1e9}
 
     out = {"metric": metric, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": workload_name, "tile": [23, TILE, TILE], "batch_per_gpu": B,
+           "config": {"workload": workload_name, "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_gpu": B,
                       "global_batch": B * world, "parallelism": f"dp{world}",
                       "l2": "4 rotating input batches (368 MB) + ~2 GB of activations per step: working set > 126 MB L2"},
            "clocks": sampler.summary(),
@@ -297,7 +350,7 @@ def main():
            "tflops_whole_step": (fwd_flops + (bwd_flops if train else 0)) / B * value / world / 1e12}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = 4 if not train else 2
-        v, sec, threads = cpu_reference(args.workload, sample, 3, 1)
+        v, sec, threads = cpu_reference(args.workload, sample, 3, 1, mt, kw, shared)
         out["cpu_baseline"] = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
                                "sample": f"{sample} tiles x 3 timed steps (1 warm-up), oracle/unet_oracle.py, torch CPU fp32"}
     elif rank == 0:

@@ -85,6 +85,9 @@ int    mau_plan_state_info(const mau_plan* plan, int i, int64_t* numel, int* rol
 int    mau_plan_describe_config(const mau_config* cfg, char* buf, size_t buflen);
 /* algorithmic work of one forward over the whole batch (dense reference graph) */
 int    mau_plan_flops(const mau_plan* plan, double* fwd_flops, double* bwd_flops);
+/* FLOPs the 3x3 convolution kernels of ONE forward actually execute (equals the dense conv FLOPs unless
+ * MAU_FLAG_SHARED_MAPS runs the encoder once for the whole batch) */
+int    mau_plan_exec_flops(const mau_plan* plan, double* conv_flops_per_forward);
 
 /* --- forward: replaces `model(maps, temp_series, metadata)` (src/model.py:328,
  *     called at src/train.py:245, test/evaluate.py:186, test/metadata_sensitivity.py:310) ---
@@ -115,6 +118,15 @@ int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* gr
 typedef void (*mau_grad_ready_fn)(void* user, int first_index, int last_index);
 int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user);
 
+/* optional SyncBN (new capability): when set, every training-mode BatchNorm calls fn with its
+ * device buffer of per-channel sums (double[n], n = 2*C: forward {sum z, sum z^2}, backward
+ * {sum g, sum g*xhat}) right after the local reduction; fn must all-reduce (SUM) the buffer in place
+ * across the world_size ranks, ordered on the stream the plan call was given.  Batch statistics, running
+ * statistics and dz then equal those of one process running the global batch (the reference semantics,
+ * src/model.py:13 on one device); dgamma / dbeta stay per-rank so that the gradient average is exact. */
+typedef void (*mau_stats_sync_fn)(void* user, void* sums_dev, int n_doubles);
+int mau_plan_set_stats_sync(mau_plan* plan, mau_stats_sync_fn fn, void* user, int world_size);
+
 /* SMs the persistent kernels leave free (default 0, or $MAU_SM_RESERVE): set it to the number of CTAs
  * a concurrently running collective (NCCL all-reduce overlapped with backward) occupies, so that a
  * persistent grid never spills into a second wave.  Applies to plans created afterwards. */
@@ -132,6 +144,15 @@ int mau_plan_profile_read(mau_plan* plan, char* names, size_t names_len, float* 
 int mau_loss_forward_backward(int kind, const float* pred_dev, const float* target_dev, int B, int C,
                               int H, int W, float lambda_grad, float* losses_dev, float* grad_dev,
                               void* stream);
+
+/* --- optimizer step: replaces torch.optim.AdamW(...).step() (src/train.py:213-214,255) -------
+ * One launch updates all n_tensors parameter tensors (fp32, contiguous) in place with decoupled weight
+ * decay; exp_avg / exp_avg_sq are the optimizer's state tensors (same layout as torch's, so
+ * optimizer.state_dict() stays interchangeable); step is the 1-based update count used for the
+ * bias corrections.  New capability on the path's "next" row. */
+int mau_adamw_step(int n_tensors, void* const* params_dev, void* const* grads_dev, void* const* exp_avg_dev,
+                   void* const* exp_avg_sq_dev, const int64_t* numels, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, int64_t step, void* stream);
 
 /* --- evaluation metrics: replaces the NumPy loop of test/evaluate.py:210-275 ---------------
  * dw_map_dev [B,H,W] int64 = argmax_c(maps[b,c]*c, c<9) (ties -> lowest index, bit-exact);

@@ -72,6 +72,12 @@ int mau_plan_flops(const mau_plan* plan, double* fwd_flops, double* bwd_flops) {
   return 0;
 }
 
+int mau_plan_exec_flops(const mau_plan* plan, double* conv_flops_per_forward) {
+  if (!plan || !conv_flops_per_forward) return fail("null argument");
+  *conv_flops_per_forward = plan->impl.exec_flops;
+  return 0;
+}
+
 int mau_plan_forward(mau_plan* plan, void* const* state_dev, const float* maps_dev, const float* temp_series_dev,
                      const float* metadata_dev, float* out_dev, void* stream) {
   if (!plan || !state_dev || !maps_dev || !out_dev) return fail("mau_plan_forward: null argument");
@@ -102,6 +108,13 @@ int mau_plan_set_state_version(mau_plan* plan, uint64_t version) {
 int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user) {
   if (!plan) return fail("null plan");
   plan->impl.hook = fn; plan->impl.hook_user = user;
+  return 0;
+}
+
+int mau_plan_set_stats_sync(mau_plan* plan, mau_stats_sync_fn fn, void* user, int world_size) {
+  if (!plan) return fail("null plan");
+  if (fn && world_size < 1) return fail("stats sync: world_size must be >= 1");
+  plan->impl.sync_fn = fn; plan->impl.sync_user = user; plan->impl.sync_world = fn ? world_size : 1;
   return 0;
 }
 
@@ -139,6 +152,17 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
   if (!maps_dev || !pred_dev || !target_dev || !dw_map_dev || !sums_dev) return fail("eval_metrics: null argument");
   return op_eval_metrics(maps_dev, maps_channels, pred_dev, target_dev, B, C, H, W, temp_mean, temp_std,
                          reinterpret_cast<long long*>(dw_map_dev), sums_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mau_adamw_step(int n_tensors, void* const* params_dev, void* const* grads_dev, void* const* exp_avg_dev,
+                   void* const* exp_avg_sq_dev, const int64_t* numels, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, void* stream) {
+  if (n_tensors < 0 || (n_tensors && (!params_dev || !grads_dev || !exp_avg_dev || !exp_avg_sq_dev || !numels)))
+    return fail("adamw: null argument");
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
+  return op_adamw_step(n_tensors, params_dev, grads_dev, exp_avg_dev, exp_avg_sq_dev,
+                       reinterpret_cast<const long long*>(numels), lr, beta1, beta2, eps, weight_decay, (long long)step,
+                       static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------- single operators (parity tests)

@@ -217,6 +217,68 @@ __global__ void __launch_bounds__(256) bilinear_kernel(DView x, DView y, float s
     }
   }
 }
+// Streaming form for up-sampling (Hin <= Hout): one thread owns one (output column, 8-channel group) and walks
+// down a strip of output rows keeping the two horizontally interpolated source rows it sits between in
+// registers.  Every source vector is loaded and unpacked once per strip and every horizontal lerp is computed
+// once (the per-row kernel above recomputes them for each of the ~2 output rows that share a source row pair):
+// ~2.4x fewer instructions, which is what bounded that kernel (ncu: 75 % issue-slot utilisation at 42 % of HBM
+// peak).  The next source row is requested one step before it is needed.
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_stream_kernel(DView x, DView y, float sy, float sx, FastDiv divG,
+                                                              int rows_per_strip) {
+  using Raw = typename V8<T>::Raw;
+  const unsigned G = y.C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)y.W * G) return;
+  unsigned ow, g;
+  divG.divmod(idx, ow, g);
+  const int b = blockIdx.z;
+  const int oh_begin = blockIdx.y * rows_per_strip;
+  const int oh_end = min(y.H, oh_begin + rows_per_strip);
+  int x0, x1; float lx;
+  src_index(sx, (int)ow, x.W, x0, x1, lx);
+  const float hx = 1.f - lx;
+  const T* xb = static_cast<const T*>(x.ptr) + (long long)b * x.H * x.W * x.cs + x.c0 + g * 8;
+  T* yb = static_cast<T*>(y.ptr) + ((long long)b * y.H * y.W + ow) * y.cs + y.c0 + g * 8;
+  const long long xrow = (long long)x.W * x.cs, yrow = (long long)y.W * y.cs;
+  const long long o0 = (long long)x0 * x.cs, o1 = (long long)x1 * x.cs;
+  auto hlerp = [&](const Raw& ra, const Raw& rb, float (&out)[8]) {
+    float a[8], bb[8];
+    V8<T>::unpack(ra, a); V8<T>::unpack(rb, bb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = hx * a[k] + lx * bb[k];
+  };
+  int y0, y1; float ly;
+  src_index(sy, oh_begin, x.H, y0, y1, ly);
+  float cur[8], nxt[8];
+  {
+    const Raw a0 = V8<T>::load_raw(xb + y0 * xrow + o0), a1 = V8<T>::load_raw(xb + y0 * xrow + o1);
+    const Raw b0 = V8<T>::load_raw(xb + y1 * xrow + o0), b1 = V8<T>::load_raw(xb + y1 * xrow + o1);
+    hlerp(a0, a1, cur);
+    hlerp(b0, b1, nxt);
+  }
+  int cy = y0;
+  Raw pa, pb;                                   // source row cy + 2, requested ahead of time
+  bool have = cy + 2 < x.H;
+  if (have) { pa = V8<T>::load_raw(xb + (cy + 2) * xrow + o0); pb = V8<T>::load_raw(xb + (cy + 2) * xrow + o1); }
+  for (int oh = oh_begin; oh < oh_end; ++oh) {
+    src_index(sy, oh, x.H, y0, y1, ly);         // block-uniform
+    if (y0 != cy) {                             // moved down by one source row (scale <= 1)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+      cy = y0;
+      if (have) hlerp(pa, pb, nxt);             // row cy + 1; at the last source row nxt keeps cur (weight ly = 0)
+      have = cy + 2 < x.H;
+      if (have) { pa = V8<T>::load_raw(xb + (cy + 2) * xrow + o0); pb = V8<T>::load_raw(xb + (cy + 2) * xrow + o1); }
+    }
+    const float hy = 1.f - ly;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = hy * cur[k] + ly * nxt[k];
+    V8<T>::store(yb + oh * yrow, o);
+  }
+}
+
 // gather form: gx[ih,iw] = sum_{(oh,wy) in rows(ih)} sum_{(ow,wx) in cols(iw)} wy*wx*gy[oh,ow]
 // Fast path (every source column receives at most kMaxE contributions -- always true when up-sampling):
 // the column list is read once, then for every contributing output row the <= kMaxE gy vectors are
@@ -270,6 +332,104 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(DView gy, DView gx, B
     V8<T>::store(at<T>(gx, opix, g * 8), o);
   }
 }
+// Streaming form of the backward for up-sampling (Hin <= Hout): one thread owns one (input column, 8-channel
+// group) and walks down the OUTPUT rows that touch its strip of input rows.  For every output row the column
+// gather hg = sum_c wx_c * gy[oh, ow_c] is formed once and scattered with the two vertical weights into two
+// sliding accumulators (input rows y0 and y0 + 1), so every gy vector is read twice in total instead of four
+// times, with block-uniform control flow and no per-row table walks.
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DView gx, BilinearTables t, float sy,
+                                                                  FastDiv divG, int rows_per_strip, int accumulate) {
+  using Raw = typename V8<T>::Raw;
+  const unsigned G = gx.C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)gx.W * G) return;
+  unsigned iw, g;
+  divG.divmod(idx, iw, g);
+  const int b = blockIdx.z;
+  const int ih_b = blockIdx.y * rows_per_strip;
+  const int ih_e = min(gx.H, ih_b + rows_per_strip);
+  const int ca = t.tx_off[iw], nc = t.tx_off[iw + 1] - ca;
+  long long off[kMaxE];
+  float wx[kMaxE];
+#pragma unroll
+  for (int e = 0; e < kMaxE; ++e) {
+    off[e] = (long long)(e < nc ? t.tx_idx[ca + e] : 0) * gy.cs;
+    wx[e] = e < nc ? t.tx_w[ca + e] : 0.f;
+  }
+  const T* gyb = static_cast<const T*>(gy.ptr) + (long long)b * gy.H * gy.W * gy.cs + gy.c0 + g * 8;
+  T* gxb = static_cast<T*>(gx.ptr) + ((long long)b * gx.H * gx.W + iw) * gx.cs + gx.c0 + g * 8;
+  const long long gyrow = (long long)gy.W * gy.cs, gxrow = (long long)gx.W * gx.cs;
+  // output rows touching input rows [ih_b, ih_e): the row lists are sorted by output row
+  const int oh_first = t.ty_idx[t.ty_off[ih_b]];
+  const int oh_last = t.ty_idx[t.ty_off[ih_e] - 1];
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+  int r = ih_b;                                  // input row acc0 belongs to (acc1: r + 1)
+  auto emit = [&](int row, const float (&a)[8]) {
+    float o[8];
+    if (accumulate) {
+      V8<T>::load(gxb + row * gxrow, o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += a[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = a[k];
+    }
+    V8<T>::store(gxb + row * gxrow, o);
+  };
+  for (int oh = oh_first; oh <= oh_last; ++oh) {
+    Raw rv[kMaxE];
+    const T* rowp = gyb + oh * gyrow;
+#pragma unroll
+    for (int c = 0; c < kMaxE; ++c)
+      if (c < nc) rv[c] = V8<T>::load_raw(rowp + off[c]);
+    int y0, y1; float ly;
+    src_index(sy, oh, gx.H, y0, y1, ly);         // block-uniform
+    while (y0 > r && r < ih_e) {                 // input row r is complete
+      emit(r, acc0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc0[k] = acc1[k]; acc1[k] = 0.f; }
+      ++r;
+    }
+    float hg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hg[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxE; ++c)
+      if (c < nc) {
+        float v[8];
+        V8<T>::unpack(rv[c], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hg[k] = fmaf(wx[c], v[k], hg[k]);
+      }
+    const float w0 = 1.f - ly;
+    if (y0 == r) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc0[k] = fmaf(w0, hg[k], acc0[k]);
+      if (y1 != y0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc1[k] = fmaf(ly, hg[k], acc1[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc0[k] = fmaf(ly, hg[k], acc0[k]);
+      }
+    } else if (y1 == r && y0 == r - 1) {         // first rows of the strip: only the lower neighbour is ours
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc0[k] = fmaf(ly, hg[k], acc0[k]);
+    }
+  }
+  if (r < ih_e) emit(r, acc0);
+  if (r + 1 < ih_e) emit(r + 1, acc1);
+  for (int row = r + 2; row < ih_e; ++row) {     // (cannot happen when up-sampling; keeps every row written)
+    float z[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z[k] = 0.f;
+    emit(row, z);
+  }
+}
+
 // general form (any number of contributions per source index, e.g. down-sampling)
 template <typename T>
 __global__ void bilinear_bwd_general_kernel(DView gy, DView gx, BilinearTables t, int accumulate) {
@@ -354,6 +514,22 @@ __global__ void embed_reduce_kernel(DView g, float* __restrict__ demb, int strid
   }
 }
 
+// dst[b, p, :] = src[0, p, :]: one 16-byte load, B stores
+template <typename T>
+__global__ void broadcast_batch_kernel(DView src, DView dst) {
+  using Raw = typename V8<T>::Raw;
+  const int G = src.C / 8;
+  const long long HW = (long long)src.H * src.W;
+  const long long total = HW * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    const Raw r = V8<T>::load_raw(at<T>(src, pix, g * 8));
+    for (int b = 0; b < dst.B; ++b) *reinterpret_cast<Raw*>(at<T>(dst, b * HW + pix, g * 8)) = r;
+  }
+}
+
 template <typename T>
 __global__ void copy_slice_kernel(DView src, DView dst, int accumulate) {
   const int G = src.C / 8;
@@ -390,24 +566,28 @@ __global__ void __launch_bounds__(256) head_kernel(DView x, const float* __restr
   for (int o = 0; o < OCT; ++o)
 #pragma unroll
     for (int k = 0; k < 8; ++k) wr[o][k] = o < OC ? w[o * x.C + sub * 8 + k] : 0.f;
-  const long long P = (long long)x.H * x.W;
-  const long long npix = (long long)x.B * P;
+  // grid.y = image: pixel indices stay 32-bit and no division sits in the loop (the 64-bit div/mod of the
+  // first version made this kernel issue-bound: ncu 73 % issue-slot utilisation at 35 % of HBM peak)
+  const int P = x.H * x.W;
+  const int b = blockIdx.y;
+  const T* xb = static_cast<const T*>(x.ptr) + (long long)b * P * x.cs + x.c0 + sub * 8;
+  float* ob = out + (long long)b * OC * P;
   const int per_block = blockDim.x / G;
-  const long long stride = (long long)gridDim.x * per_block;
-  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += kHU * stride) {
+  const int stride = gridDim.x * per_block;
+  for (int base = blockIdx.x * per_block; base < P; base += kHU * stride) {
     Raw r[kHU];
 #pragma unroll
     for (int u = 0; u < kHU; ++u) {
-      const long long pix = base + u * stride + slot;
-      if (pix < npix) r[u] = V8<T>::load_raw(at<T>(x, pix, sub * 8));
+      const int pix = base + u * stride + slot;
+      if (pix < P) r[u] = V8<T>::load_raw(xb + (long long)pix * x.cs);
     }
 #pragma unroll
     for (int u = 0; u < kHU; ++u) {
-      const long long pix = base + u * stride + slot;
+      const int pix = base + u * stride + slot;
       float acc[OCT];
 #pragma unroll
       for (int o = 0; o < OCT; ++o) acc[o] = 0.f;
-      if (pix < npix) {
+      if (pix < P) {
         float v[8];
         V8<T>::unpack(r[u], v);
 #pragma unroll
@@ -418,15 +598,13 @@ __global__ void __launch_bounds__(256) head_kernel(DView x, const float* __restr
 #pragma unroll
       for (int o = 0; o < OCT; ++o)
         for (int off = G >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
-      if (pix < npix && sub == 0) {
-        const int b = (int)(pix / P);
-        const long long p = pix - (long long)b * P;
+      if (pix < P && sub == 0) {
 #pragma unroll
         for (int o = 0; o < OCT; ++o)
           if (o < OC) {
             float v = acc[o] + bias[o];
             if (apply_tanh && o == 0) v = tanhf(v);
-            out[((long long)b * OC + o) * P + p] = v;
+            ob[(long long)o * P + pix] = v;
           }
       }
     }
@@ -447,10 +625,14 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(DView x, const float* __r
   if (threadIdx.x < OC) sdb[threadIdx.x] = 0.f;
   __syncthreads();
   const int G = x.C / 8;
-  const long long P = (long long)x.H * x.W;
-  const long long npix = (long long)x.B * P;
+  const int P = x.H * x.W;
+  const int b = blockIdx.y;
   const int per_block = blockDim.x / G;
   const int sub = threadIdx.x % G, slot = threadIdx.x / G;
+  const T* xb = static_cast<const T*>(x.ptr) + (long long)b * P * x.cs + x.c0 + sub * 8;
+  T* gxb = static_cast<T*>(gx.ptr) + (long long)b * P * gx.cs + gx.c0 + sub * 8;
+  const float* goutb = gout + (long long)b * OC * P;
+  const float* outb = out + (long long)b * OC * P;
   float wr[OCT][8], dwl[OCT][8], dbl[OCT];
 #pragma unroll
   for (int o = 0; o < OCT; ++o) {
@@ -458,29 +640,27 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(DView x, const float* __r
 #pragma unroll
     for (int k = 0; k < 8; ++k) { dwl[o][k] = 0.f; wr[o][k] = o < OC ? w[o * x.C + sub * 8 + k] : 0.f; }
   }
-  const long long stride = (long long)gridDim.x * per_block;
-  for (long long base = (long long)blockIdx.x * per_block; base < npix; base += kHU * stride) {
+  const int stride = gridDim.x * per_block;
+  for (int base = blockIdx.x * per_block; base < P; base += kHU * stride) {
     Raw r[kHU];
     float go[kHU][OCT];
 #pragma unroll
     for (int u = 0; u < kHU; ++u) {
-      const long long pix = base + u * stride + slot;
-      if (pix < npix) {
-        r[u] = V8<T>::load_raw(at<T>(x, pix, sub * 8));
-        const int b = (int)(pix / P);
-        const long long p = pix - (long long)b * P;
+      const int pix = base + u * stride + slot;
+      if (pix < P) {
+        r[u] = V8<T>::load_raw(xb + (long long)pix * x.cs);
 #pragma unroll
-        for (int o = 0; o < OCT; ++o) go[u][o] = o < OC ? gout[((long long)b * OC + o) * P + p] : 0.f;
+        for (int o = 0; o < OCT; ++o) go[u][o] = o < OC ? goutb[(long long)o * P + pix] : 0.f;
         if (apply_tanh) {
-          const float y = out[((long long)b * OC) * P + p];
+          const float y = outb[pix];
           go[u][0] *= (1.f - y * y);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < kHU; ++u) {
-      const long long pix = base + u * stride + slot;
-      if (pix < npix) {
+      const int pix = base + u * stride + slot;
+      if (pix < P) {
         float v[8], rr[8];
         V8<T>::unpack(r[u], v);
 #pragma unroll
@@ -494,7 +674,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(DView x, const float* __r
           }
           if (sub == 0) dbl[o] += go[u][o];
         }
-        V8<T>::store(at<T>(gx, pix, sub * 8), rr);
+        V8<T>::store(gxb + (long long)pix * gx.cs, rr);
       }
     }
   }
@@ -576,11 +756,19 @@ void bilinear_axis_tables(int in, int out, BilinearHost* h) {
 int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st) {
   if (!vec_ok(x) || !vec_ok(y) || x.C != y.C || t.Hin != x.H || t.Win != x.W || t.Hout != y.H || t.Wout != y.W)
     return fail("bilinear: bad views/tables");
-  const int quads = ceil_div(y.H, kRows);
-  if ((long long)y.B * quads > 65535) return fail("bilinear: B*H too large for the row grid");
-  const dim3 grid((unsigned)ceil_div(y.W * (y.C / 8), 256), (unsigned)(y.B * quads), 1);
   const float sy = y.H > 1 ? (float)(x.H - 1) / (float)(y.H - 1) : 0.f;     // area_pixel_compute_scale, align_corners
   const float sx = y.W > 1 ? (float)(x.W - 1) / (float)(y.W - 1) : 0.f;
+  const int colblocks = ceil_div(y.W * (y.C / 8), 256);
+  if (x.H <= y.H && y.B <= 65535 && x.H >= 2) {      // up-sampling rows: streaming kernel
+    int strip = 32;
+    while (strip > 8 && (long long)colblocks * y.B * ceil_div(y.H, strip) < 148 * 8) strip >>= 1;
+    const dim3 grid((unsigned)colblocks, (unsigned)ceil_div(y.H, strip), (unsigned)y.B);
+    MAU_DISPATCH(dt, bilinear_stream_kernel, grid, 256, 0, st, dv(x), dv(y), sy, sx, FastDiv((unsigned)(y.C / 8)), strip);
+    return 0;
+  }
+  const int quads = ceil_div(y.H, kRows);
+  if ((long long)y.B * quads > 65535) return fail("bilinear: B*H too large for the row grid");
+  const dim3 grid((unsigned)colblocks, (unsigned)(y.B * quads), 1);
   MAU_DISPATCH(dt, bilinear_kernel, grid, 256, 0, st, dv(x), dv(y), sy, sx, FastDiv((unsigned)(y.C / 8)), FastDiv((unsigned)quads));
   return 0;
 }
@@ -589,6 +777,16 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
   if (!vec_ok(gx) || !vec_ok(gy) || gx.C != gy.C || t.Hin != gx.H || t.Win != gx.W || t.Hout != gy.H ||
       t.Wout != gy.W)
     return fail("bilinear_bwd: bad views/tables");
+  if (t.max_fan_w <= kMaxE && gx.H <= gy.H && gx.H >= 2 && gx.B <= 65535) {
+    const float sy = gy.H > 1 ? (float)(gx.H - 1) / (float)(gy.H - 1) : 0.f;
+    const int colblocks = ceil_div(gx.W * (gx.C / 8), 256);
+    int strip = 16;
+    while (strip > 4 && (long long)colblocks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
+    const dim3 grid((unsigned)colblocks, (unsigned)ceil_div(gx.H, strip), (unsigned)gx.B);
+    MAU_DISPATCH(dt, bilinear_bwd_stream_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
+                 accumulate);
+    return 0;
+  }
   if (t.max_fan_w <= kMaxE)
     MAU_DISPATCH(dt, bilinear_bwd_kernel, grid_for(gx.pixels() * (gx.C / 8)), 256, 0, st, dv(gy), dv(gx), t, accumulate);
   else
@@ -608,6 +806,12 @@ int op_embed_reduce(int dt, const View& g, float* demb, int emb_stride, int accu
   int chunks = (int)std::min<long long>(std::max<long long>(1, HW / 512), 148 * 4 / std::max(1, g.B) + 1);
   dim3 grid((unsigned)chunks, (unsigned)g.B, 1);
   MAU_DISPATCH(dt, embed_reduce_kernel, grid, 256, 256 * 8 * sizeof(float), st, dv(g), demb, emb_stride, chunks);
+  return 0;
+}
+int op_broadcast_batch(int dt, const View& src, const View& dst, cudaStream_t st) {
+  if (!vec_ok(src) || !vec_ok(dst) || src.C != dst.C || src.B != 1 || src.H != dst.H || src.W != dst.W)
+    return fail("broadcast_batch: bad views");
+  MAU_DISPATCH(dt, broadcast_batch_kernel, grid_for((long long)src.H * src.W * (src.C / 8)), 256, 0, st, dv(src), dv(dst));
   return 0;
 }
 int op_copy_slice(int dt, const View& src, const View& dst, int accumulate, cudaStream_t st) {
@@ -638,7 +842,9 @@ int op_head(int dt, const View& x, const float* w, const float* bias, int OC, in
             cudaStream_t st) {
   if (!head_ok(x, OC)) return fail("head: needs C = 8*2^k <= 256 and out_channels <= 8 (C=%d, OC=%d)", x.C, OC);
   const int per_block = 256 / (x.C / 8);
-  const int grid = grid_for(ceil_div((int)std::min<long long>(x.pixels(), 1 << 30), kHU), per_block, 8);
+  if (x.B > 65535) return fail("head: batch too large for the per-image grid");
+  const int per_img = std::max(1, std::min(ceil_div(ceil_div(x.H * x.W, kHU), per_block), ceil_div(148 * 8, x.B)));
+  const dim3 grid((unsigned)per_img, (unsigned)x.B, 1);
   MAU_HEAD_DISPATCH(head_kernel, grid, 0, dv(x), w, bias, OC, apply_tanh, out_nchw);
   return 0;
 }
@@ -647,7 +853,9 @@ int op_head_bwd(int dt, const View& x, const float* w, int OC, int apply_tanh, c
   if (!head_ok(x, OC) || !vec_ok(gx)) return fail("head_bwd: unsupported shape");
   const int per_block = 256 / (x.C / 8);
   const size_t smem = (OC * x.C + OC) * sizeof(float);
-  const int grid = grid_for(ceil_div((int)std::min<long long>(x.pixels(), 1 << 30), kHU), per_block, 4);
+  if (x.B > 65535) return fail("head_bwd: batch too large for the per-image grid");
+  const int per_img = std::max(1, std::min(ceil_div(ceil_div(x.H * x.W, kHU), per_block), ceil_div(148 * 6, x.B)));
+  const dim3 grid((unsigned)per_img, (unsigned)x.B, 1);
   MAU_HEAD_DISPATCH(head_bwd_kernel, grid, smem, dv(x), w, OC, apply_tanh, out_nchw, gout_nchw, dv(gx), dw, db);
   return 0;
 }

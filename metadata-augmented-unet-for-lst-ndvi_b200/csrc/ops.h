@@ -41,6 +41,9 @@ int op_embed_broadcast(int dt, const float* emb, int emb_stride, const View& y, 
 // demb[b*stride + c] (+)= sum_{h,w} g[b,h,w,c]
 int op_embed_reduce(int dt, const View& g, float* demb, int emb_stride, int accumulate, cudaStream_t st);
 
+// ---- dst[b] = src[0] for every batch row b of dst (shared-maps sweep: one-tile tensor -> concat slice) ----
+int op_broadcast_batch(int dt, const View& src, const View& dst, cudaStream_t st);
+
 // ---- dst (=|+=) src on channel-slice views ------------------------------------------------------
 int op_copy_slice(int dt, const View& src, const View& dst, int accumulate, cudaStream_t st);
 
@@ -103,5 +106,10 @@ int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, 
             float* losses, float* grad, cudaStream_t st);
 int op_eval_metrics(const float* maps, int maps_c, const float* pred, const float* tgt, int B, int C, int H, int W,
                     float temp_mean, float temp_std, long long* dw_map, double* sums, cudaStream_t st);
+
+// ---- optimizer (optim.cu): torch.optim.AdamW step for every tensor in one launch ---------------------
+int op_adamw_step(int n_tensors, void* const* params, void* const* grads, void* const* exp_avg,
+                  void* const* exp_avg_sq, const long long* numels, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, long long step, cudaStream_t st);
 
 }  // namespace mau

@@ -10,6 +10,18 @@ namespace mau {
 static constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d default (reference src/model.py:13)
 static constexpr float kBnMomentum = 0.1f;
 
+void Plan::kbegin(const Ctx& c, const std::string& name) {
+  if (!profiling) return;
+  KTimer t; t.name = name;
+  cudaEventCreate(&t.e0); cudaEventCreate(&t.e1);
+  cudaEventRecord(t.e0, c.st);
+  ktimers.push_back(t);
+}
+void Plan::kend(const Ctx& c) {
+  if (!profiling || ktimers.empty()) return;
+  cudaEventRecord(ktimers.back().e1, c.st);
+}
+
 Plan::~Plan() {
   if (!dry) {
     for (void* p : allocs) cudaFree(p);
@@ -33,10 +45,10 @@ int Plan::add_state(const std::string& name, long long numel, int role) {
   return (int)state.size() - 1;
 }
 
-int Plan::new_buf(const std::string& name, int H, int W, int C) {
+int Plan::new_buf(const std::string& name, int H, int W, int C, int B) {
   Buf b;
-  b.name = name; b.H = H; b.W = W; b.C = C; b.cs = round_up(C, 8);
-  b.bytes = (size_t)cfg.batch * H * W * b.cs * dtype_size(dt);
+  b.name = name; b.B = B < 0 ? cfg.batch : B; b.H = H; b.W = W; b.C = C; b.cs = round_up(C, 8);
+  b.bytes = (size_t)b.B * H * W * b.cs * dtype_size(dt);
   b.ptr = alloc(b.bytes);
   b.ginit.assign(b.cs / 8, 0);
   bufs.push_back(b);
@@ -45,7 +57,7 @@ int Plan::new_buf(const std::string& name, int H, int W, int C) {
 
 View Plan::view(const TRef& t) const {
   const Buf& b = bufs[t.buf];
-  View v; v.ptr = b.ptr; v.B = cfg.batch; v.H = b.H; v.W = b.W; v.cs = b.cs; v.c0 = t.c0; v.C = t.C;
+  View v; v.ptr = b.ptr; v.B = b.B; v.H = b.H; v.W = b.W; v.cs = b.cs; v.c0 = t.c0; v.C = t.C;
   return v;
 }
 View Plan::whole(int buf) const { return view(TRef{buf, 0, bufs[buf].C}); }
@@ -129,7 +141,10 @@ ConvLayer* Plan::add_conv(const std::string& name, int iw0, int in_buf, int nseg
     L->Cin += seg_len[s];
   }
   L->Kp = (int)kmap.size();
+  L->B = bufs[in_buf].B;
+  if (bufs[out.buf].B != L->B) { fail("layer %s: input and output batch differ", name.c_str()); return nullptr; }
   L->flops = 2.0 * 9.0 * L->Cin * L->Cout * (double)L->H * L->W * cfg.batch;
+  exec_flops += L->flops / cfg.batch * L->B;
   if ((long long)L->Cout * L->Cin * 9 != state[iw0].numel) {
     fail("layer %s: weight numel mismatch (%d x %d)", name.c_str(), L->Cout, L->Cin);
     return nullptr;
@@ -143,7 +158,8 @@ ConvLayer* Plan::add_conv(const std::string& name, int iw0, int in_buf, int nseg
   L->rstd = static_cast<float*>(alloc(sizeof(float) * C));
   L->sums = static_cast<double*>(alloc(sizeof(double) * 2 * C));
   L->dbsum = static_cast<double*>(alloc(sizeof(double) * C));
-  if (cfg.training) L->zbuf = new_buf(name + ".z", L->H, L->W, C);
+  if (cfg.training) L->sums_local = static_cast<double*>(alloc(sizeof(double) * 2 * C));
+  if (cfg.training) L->zbuf = new_buf(name + ".z", L->H, L->W, C, L->B);
   if (dry) return L;
   if (!L->kmap || !L->wpack || !L->dbsum) return nullptr;
   if (cudaMemcpy(L->kmap, kmap.data(), sizeof(int) * kmap.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -170,7 +186,7 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
   Op op;
   op.name = L->name;
   const bool training = cfg.training != 0;
-  const long long count = (long long)cfg.batch * L->H * L->W;
+  const long long count = (long long)L->B * L->H * L->W;
   op.run = [this, L, training, count](Ctx& c) -> int {
     const int C = L->Cout;
     if (!skip_pack) {
@@ -190,16 +206,21 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
         L->tc.p.head_w = c.f(L->head_w); L->tc.p.head_b = c.f(L->head_b); L->tc.p.head_out = c.out;
         L->tc.p.head_oc = L->head_oc; L->tc.p.head_tanh = L->head_tanh; L->tc.p.store_y = 0;
       }
+      kbegin(c, "k:" + L->name + ":fwd");
       MAU_TRY(conv_tc_launch(L->tc, c.st));
+      kend(c);
     } else {
       L->ff.scale = scale; L->ff.shift = shift; L->ff.relu = relu;
-      MAU_TRY(conv_ffma_launch(dt, L->ff, cfg.batch, c.st));
+      kbegin(c, "k:" + L->name + ":fwd");
+      MAU_TRY(conv_ffma_launch(dt, L->ff, L->B, c.st));
+      kend(c);
     }
     if (training) {
       const View z = whole(L->zbuf);
       MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
       MAU_TRY(op_bn_stats(dt, z, L->sums, c.st));
-      MAU_TRY(op_bn_finalize_train(L->sums, count, c.f(L->igamma), c.f(L->ibeta), C, kBnEps, kBnMomentum,
+      if (sync_fn) sync_fn(sync_user, L->sums, 2 * C);       // SyncBN: sum / sum-of-squares over all ranks
+      MAU_TRY(op_bn_finalize_train(L->sums, count * sync_world, c.f(L->igamma), c.f(L->ibeta), C, kBnEps, kBnMomentum,
                                    c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, c.st));
       MAU_TRY(op_bn_apply_relu(dt, z, L->scale, L->shift, view(L->out), c.st));
     }
@@ -228,7 +249,7 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
   const int C = L->Cout;
   const View y = view(L->out);
   const View z = whole(L->zbuf);
-  const long long count = (long long)cfg.batch * L->H * L->W;
+  const long long count = (long long)L->B * L->H * L->W;
   // weight-gradient and data-gradient launches are prepared now (tensor maps need final pointers)
   int ci_w0 = 0;
   int dacc[4] = {0, 0, 0, 0};
@@ -263,8 +284,17 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
     MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
     MAU_CUDA(cudaMemsetAsync(L->dbsum, 0, sizeof(double) * C, c.st));
     MAU_TRY(op_bn_bwd_reduce(dt, gy, z, L->scale, L->shift, L->mean, L->rstd, L->sums, c.st));
-    MAU_TRY(op_bn_bwd_apply(dt, gy, z, L->scale, L->shift, c.f(L->igamma), L->mean, L->rstd, L->sums, count, z, L->dbsum, c.st));
-    MAU_TRY(op_bn_bwd_finalize(L->sums, L->dbsum, C, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
+    const double* param_sums = L->sums;
+    if (sync_fn) {
+      // SyncBN: dz needs the sums over every rank's pixels; dgamma / dbeta stay this rank's own sums (the
+      // data-parallel gradient average then yields the global-batch gradient, like torch SyncBatchNorm)
+      MAU_CUDA(cudaMemcpyAsync(L->sums_local, L->sums, sizeof(double) * 2 * C, cudaMemcpyDeviceToDevice, c.st));
+      sync_fn(sync_user, L->sums, 2 * C);
+      param_sums = L->sums_local;
+    }
+    MAU_TRY(op_bn_bwd_apply(dt, gy, z, L->scale, L->shift, c.f(L->igamma), L->mean, L->rstd, L->sums,
+                            count * sync_world, z, L->dbsum, c.st));
+    MAU_TRY(op_bn_bwd_finalize(param_sums, L->dbsum, C, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
     float* dw = c.g(L->iw);
     int ci_w0 = 0;
     const bool ws_path = use_tc && wgrad_ws != nullptr;      // v2 wgrad: reduce into the workspace, then transpose
@@ -273,17 +303,21 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
     for (int s = 0; s < L->nseg; ++s) {
       const TRef xin{L->in_buf, L->seg_start[s], L->seg_len[s]};
       if (dw) {
+        kbegin(c, "k:" + L->name + ":wgrad");
         if (use_tc) MAU_TRY(wgrad_tc_launch(L->wg[s], dw, c.st));
         else MAU_TRY(wgrad_ffma_launch(dt, view(xin), z, ci_w0, L->Cin, dw, 1, c.st));
+        kend(c);
       }
       if (L->input_needs_grad) {
         if (use_tc) {
           MAU_TRY(conv_tc_pack_dgrad(c.f(L->iw), C, L->Cin, ci_w0, L->seg_len[s], L->Kd, L->wpack_d[s], c.st));
+          kbegin(c, "k:" + L->name + ":dgrad");
           MAU_TRY(conv_tc_launch(L->tc_d[s], c.st));
+          kend(c);
         } else {
           MAU_TRY(conv_ffma_pack_dgrad(c.f(L->iw), C, L->Cin, ci_w0, L->seg_len[s], L->Kd,
                                        static_cast<float*>(L->wpack_d[s]), c.st));
-          MAU_TRY(conv_ffma_launch(dt, L->ff_d[s], cfg.batch, c.st));
+          MAU_TRY(conv_ffma_launch(dt, L->ff_d[s], L->B, c.st));
         }
       }
       ci_w0 += L->seg_len[s];
@@ -297,7 +331,7 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
 
 int Plan::add_vgg(const std::string& name, const BlockIdx& bi, int in_buf, int nseg, const int* seg_start,
                   const int* seg_len, int cmid, TRef out, bool input_needs_grad, std::vector<ConvLayer*>* made) {
-  const int mid = new_buf(name + ".mid", bufs[in_buf].H, bufs[in_buf].W, cmid);
+  const int mid = new_buf(name + ".mid", bufs[in_buf].H, bufs[in_buf].W, cmid, bufs[in_buf].B);
   ConvLayer* a = add_conv(name + ".conv1", bi.c1w, in_buf, nseg, seg_start, seg_len, TRef{mid, 0, cmid},
                           input_needs_grad);
   if (!a) return -1;
@@ -352,6 +386,8 @@ int Plan::build_encoders(int lstm0, int fc0, int mlp0, const TRef* t_dst, int n_
   if (me) fwd_flops += B * (2.0 * cfg.meta_features * 32 + 2.0 * 32 * md);
   if (dry) return 0;
   if (te && T < 1) return fail("temporal embeddings enabled but temp_series is empty");
+  const int Bt = shared ? 1 : B;                 // shared sweep: one LSTM run, row 0 broadcast to every tile
+  const int t_stride = shared ? 0 : emb_dim;
   std::vector<View> tv, mv;
   for (int i = 0; i < n_t; ++i) tv.push_back(view(t_dst[i]));
   for (int i = 0; i < n_m; ++i) mv.push_back(view(m_dst[i]));
@@ -360,10 +396,10 @@ int Plan::build_encoders(int lstm0, int fc0, int mlp0, const TRef* t_dst, int n_
   op.run = [=](Ctx& c) -> int {
     if (te) {
       if (!c.series) return fail("temp_series is required when temporal embeddings are enabled");
-      MAU_TRY(op_lstm_fwd(c.series, B, T, Hd, c.f(lstm0), c.f(lstm0 + 1), c.f(lstm0 + 2), c.f(lstm0 + 3), hlast,
+      MAU_TRY(op_lstm_fwd(c.series, Bt, T, Hd, c.f(lstm0), c.f(lstm0 + 1), c.f(lstm0 + 2), c.f(lstm0 + 3), hlast,
                           lstm_save, c.st));
-      MAU_TRY(op_linear_fwd(hlast, B, Hd, c.f(fc0), c.f(fc0 + 1), td, emb + t_off, emb_dim, c.st));
-      for (const View& v : tv) MAU_TRY(op_embed_broadcast(dt, emb + t_off, emb_dim, v, c.st));
+      MAU_TRY(op_linear_fwd(hlast, Bt, Hd, c.f(fc0), c.f(fc0 + 1), td, emb + t_off, emb_dim, c.st));
+      for (const View& v : tv) MAU_TRY(op_embed_broadcast(dt, emb + t_off, t_stride, v, c.st));
     }
     if (me) {
       if (!c.md) return fail("metadata is required when metadata embeddings are enabled");
@@ -436,11 +472,17 @@ int Plan::build_unet() {
   const int fw = add_state("model.final.weight", (long long)cfg.out_channels * F[0], 0);
   const int fb = add_state("model.final.bias", cfg.out_channels, 0);
 
-  // buffers
-  const int in0 = new_buf("maps_nhwc", Hs[0], Ws[0], cfg.spatial_channels);
-  int cat[4], pooled[5], xdec[4];
+  // buffers.  Shared-maps sweep (eval): everything up to the bottleneck input is batch-invariant and lives in
+  // one-tile buffers; the skip tensors are replicated over the batch rows of the concat buffers.
+  const int Be = shared ? 1 : B;
+  const int in0 = new_buf("maps_nhwc", Hs[0], Ws[0], cfg.spatial_channels, Be);
+  int cat[4], pooled[5], xdec[4], enc1[4] = {-1, -1, -1, -1};
   for (int l = 0; l < 4; ++l) cat[l] = new_buf("cat" + std::to_string(l), Hs[l], Ws[l], F[l] + F[l + 1]);
-  for (int l = 1; l < 4; ++l) pooled[l] = new_buf("pool" + std::to_string(l), Hs[l], Ws[l], F[l - 1]);
+  for (int l = 1; l < 4; ++l) pooled[l] = new_buf("pool" + std::to_string(l), Hs[l], Ws[l], F[l - 1], Be);
+  if (shared) {
+    for (int l = 0; l < 4; ++l) enc1[l] = new_buf("x" + std::to_string(l) + "_0.shared", Hs[l], Ws[l], F[l], 1);
+    pooled[4] = new_buf("pool4.shared", Hs[4], Ws[4], F[3], 1);
+  }
   const int bott = new_buf("bottleneck_in", Hs[4], Ws[4], F[3] + E);
   const int x4 = new_buf("x4_0", Hs[4], Ws[4], F[4]);
   for (int l = 0; l < 4; ++l) xdec[l] = new_buf("x" + std::to_string(l) + "_1", Hs[l], Ws[l], F[l]);
@@ -455,10 +497,18 @@ int Plan::build_unet() {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
     op.run = [=](Ctx& c) -> int {
-      return op_nchw_to_nhwc(dt, c.maps, B, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
+      return op_nchw_to_nhwc(dt, c.maps, Be, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
     };
     fwd.push_back(op);
   }
+  auto add_bcast = [&](TRef src, TRef dst) -> int {       // one-tile tensor -> every batch row of a slice
+    if (dry) return 0;
+    Op op; op.name = "bcast." + bufs[src.buf].name;
+    const View xs = view(src), yd = view(dst);
+    op.run = [=](Ctx& c) -> int { return op_broadcast_batch(dt, xs, yd, c.st); };
+    fwd.push_back(op);
+    return 0;
+  };
   auto add_pool = [&](TRef src, TRef dst) -> int {
     if (dry) return 0;
     Op op; op.name = "pool." + bufs[src.buf].name;
@@ -524,11 +574,18 @@ int Plan::build_unet() {
   for (int l = 0; l < 4; ++l) {
     const int src = l == 0 ? in0 : pooled[l];
     const int cin = l == 0 ? cfg.spatial_channels : F[l - 1];
-    if (l > 0) MAU_TRY(add_pool(TRef{cat[l - 1], 0, F[l - 1]}, TRef{pooled[l], 0, F[l - 1]}));
-    MAU_TRY(add_vgg("conv" + std::to_string(l) + "_0", enc[l], src, 1, &zero, &cin, F[l], TRef{cat[l], 0, F[l]}, l > 0,
-                    nullptr));
+    const TRef skip{cat[l], 0, F[l]};
+    const TRef xout = shared ? TRef{enc1[l], 0, F[l]} : skip;
+    if (l > 0) MAU_TRY(add_pool(shared ? TRef{enc1[l - 1], 0, F[l - 1]} : TRef{cat[l - 1], 0, F[l - 1]}, TRef{pooled[l], 0, F[l - 1]}));
+    MAU_TRY(add_vgg("conv" + std::to_string(l) + "_0", enc[l], src, 1, &zero, &cin, F[l], xout, l > 0, nullptr));
+    if (shared) MAU_TRY(add_bcast(xout, skip));
   }
-  MAU_TRY(add_pool(TRef{cat[3], 0, F[3]}, TRef{bott, 0, F[3]}));
+  if (shared) {
+    MAU_TRY(add_pool(TRef{enc1[3], 0, F[3]}, TRef{pooled[4], 0, F[3]}));
+    MAU_TRY(add_bcast(TRef{pooled[4], 0, F[3]}, TRef{bott, 0, F[3]}));
+  } else {
+    MAU_TRY(add_pool(TRef{cat[3], 0, F[3]}, TRef{bott, 0, F[3]}));
+  }
   {
     const int cin = F[3] + E;
     MAU_TRY(add_vgg("conv4_0", enc[4], bott, 1, &zero, &cin, F[4], TRef{x4, 0, F[4]}, true, nullptr));
@@ -609,14 +666,17 @@ int Plan::build_unetpp() {
   }
 
   // level buffers: [x_l_0 .. x_l_{n-1} | up_1 .. up_n | emb],  n = 4 - l  (every torch.cat is a slice)
-  const int in0 = new_buf("maps_nhwc", Hs[0], Ws[0], cfg.spatial_channels);
-  int lv[4], nn[4], pooled[5], xlast[5];
+  const int Be = shared ? 1 : B;
+  const int in0 = new_buf("maps_nhwc", Hs[0], Ws[0], cfg.spatial_channels, Be);
+  int lv[4], nn[4], pooled[5], xlast[5], enc1[5] = {-1, -1, -1, -1, -1};
+  if (shared)
+    for (int l = 0; l < 5; ++l) enc1[l] = new_buf("x" + std::to_string(l) + "_0.shared", Hs[l], Ws[l], F[l], 1);
   for (int l = 0; l < 4; ++l) {
     nn[l] = 4 - l;
     lv[l] = new_buf("level" + std::to_string(l), Hs[l], Ws[l], nn[l] * F[l] + nn[l] * F[l + 1] + E);
     xlast[l] = new_buf("x" + std::to_string(l) + "_" + std::to_string(nn[l]), Hs[l], Ws[l], F[l]);
   }
-  for (int l = 1; l < 5; ++l) pooled[l] = new_buf("pool" + std::to_string(l), Hs[l], Ws[l], F[l - 1]);
+  for (int l = 1; l < 5; ++l) pooled[l] = new_buf("pool" + std::to_string(l), Hs[l], Ws[l], F[l - 1], Be);
   xlast[4] = new_buf("x4_0", Hs[4], Ws[4], F[4]);
   auto xref = [&](int l, int j) -> TRef {      // where x_l_j lives
     if (l == 4) return TRef{xlast[4], 0, F[4]};
@@ -638,10 +698,18 @@ int Plan::build_unetpp() {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
     op.run = [=](Ctx& c) -> int {
-      return op_nchw_to_nhwc(dt, c.maps, B, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
+      return op_nchw_to_nhwc(dt, c.maps, Be, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
     };
     fwd.push_back(op);
   }
+  auto add_bcast = [&](TRef src, TRef dst) -> int {
+    if (dry) return 0;
+    Op op; op.name = "bcast." + bufs[src.buf].name;
+    const View xs = view(src), yd = view(dst);
+    op.run = [=](Ctx& c) -> int { return op_broadcast_batch(dt, xs, yd, c.st); };
+    fwd.push_back(op);
+    return 0;
+  };
   auto add_pool = [&](TRef src, TRef dst) -> int {
     if (dry) return 0;
     Op op; op.name = "pool." + bufs[dst.buf].name;
@@ -689,8 +757,11 @@ int Plan::build_unetpp() {
   auto encoder = [&](int l) -> int {
     const int src = l == 0 ? in0 : pooled[l];
     const int cin = l == 0 ? cfg.spatial_channels : F[l - 1];
-    if (l > 0) MAU_TRY(add_pool(xref(l - 1, 0), TRef{pooled[l], 0, F[l - 1]}));
-    return add_vgg("conv" + std::to_string(l) + "_0", blk[l][0], src, 1, &zero, &cin, F[l], xref(l, 0), l > 0, nullptr);
+    const TRef xout = shared ? TRef{enc1[l], 0, F[l]} : xref(l, 0);
+    if (l > 0) MAU_TRY(add_pool(shared ? TRef{enc1[l - 1], 0, F[l - 1]} : xref(l - 1, 0), TRef{pooled[l], 0, F[l - 1]}));
+    MAU_TRY(add_vgg("conv" + std::to_string(l) + "_0", blk[l][0], src, 1, &zero, &cin, F[l], xout, l > 0, nullptr));
+    if (shared) MAU_TRY(add_bcast(xout, xref(l, 0)));
+    return 0;
   };
   std::vector<ConvLayer*> last_block;
   auto node = [&](int l, int j) -> int {     // x_l_j, j >= 1
@@ -769,6 +840,8 @@ int Plan::build() {
   use_tc = (dt == DT_BF16) && !(cfg.flags & MAU_FLAG_CONV_FFMA);
   conv_mode = (cfg.flags & MAU_FLAG_CONV_TAPLOAD) ? MODE_TAP : ((cfg.flags & MAU_FLAG_CONV_ROW3) ? MODE_ROW3 : MODE_HALO);
   if (cfg.training && cfg.deep_supervision) return fail("deep supervision is forward-only in this engine");
+  shared = (cfg.flags & MAU_FLAG_SHARED_MAPS) != 0;
+  if (shared && cfg.training) return fail("MAU_FLAG_SHARED_MAPS is an inference-only fast path (BatchNorm batch statistics couple the rows in training)");
   int rc = cfg.model_type == MAU_MODEL_UNET ? build_unet() : build_unetpp();
   if (rc) return rc;
   if (cfg.training) {
@@ -834,6 +907,13 @@ static int run_ops(Plan* P, std::vector<Op>& ops, Ctx& c, bool backward) {
       P->prof.push_back({ops[i].name, ms});
     }
     for (auto& e : ev) cudaEventDestroy(e);
+    for (auto& t : P->ktimers) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, t.e0, t.e1);
+      P->prof.push_back({t.name, ms});
+      cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+    }
+    P->ktimers.clear();
   }
   return 0;
 }

@@ -27,7 +27,7 @@ struct Buf {
   std::string name;
   void* ptr = nullptr;    // activation
   void* gptr = nullptr;   // gradient twin (training, allocated lazily)
-  int H = 0, W = 0, C = 0, cs = 0;
+  int B = 0, H = 0, W = 0, C = 0, cs = 0;   // B = 1 for batch-invariant buffers of a shared-maps plan
   size_t bytes = 0;
   std::vector<char> ginit;   // per 8 channels: gradient slice already holds a contribution
 };
@@ -61,7 +61,8 @@ struct ConvLayer {
   TRef out;                 // y = relu(bn(conv(x)))
   int zbuf = -1;            // training: pre-BN conv output (later overwritten by dz)
   bool input_needs_grad = true;
-  double flops = 0;
+  double flops = 0;         // dense reference FLOPs (cfg.batch tiles)
+  int B = 0;                // tiles this layer actually runs on (1 for the shared encoder of a sweep plan)
   int head_w = -1, head_b = -1, head_oc = 0, head_tanh = 0;   // eval: 1x1 head fused into this conv's epilogue
   // device scratch
   int* kmap = nullptr;
@@ -69,6 +70,7 @@ struct ConvLayer {
   float* scale = nullptr; float* shift = nullptr; float* mean = nullptr; float* rstd = nullptr;
   double* sums = nullptr;   // [2C] stats / backward sums
   double* dbsum = nullptr;  // [C]
+  double* sums_local = nullptr;   // [2C] this rank's backward sums (dgamma / dbeta) when the BN sums are all-reduced
   void* wpack_d[4] = {nullptr, nullptr, nullptr, nullptr};
   int Kd = 0;
   ConvTcOp tc; ConvFfmaParams ff;
@@ -93,8 +95,15 @@ class Plan {
   double fwd_flops = 0, bwd_flops = 0;
   bool forward_done = false;
   mau_grad_ready_fn hook = nullptr; void* hook_user = nullptr;
+  mau_stats_sync_fn sync_fn = nullptr; void* sync_user = nullptr; int sync_world = 1;   // SyncBN across ranks
   bool profiling = false;
   std::vector<std::pair<std::string, float>> prof;
+  // kernel-level timers (profiling only): CUDA events right around the conv / dgrad / wgrad launches, reported as
+  // "k:<layer>:<fwd|dgrad|wgrad>" entries next to the per-op entries
+  struct KTimer { std::string name; cudaEvent_t e0, e1; };
+  std::vector<KTimer> ktimers;
+  void kbegin(const Ctx& c, const std::string& name);
+  void kend(const Ctx& c);
   std::vector<long long*> counters_host; long long** counters_dev = nullptr;
   std::string describe_json;
   std::vector<void*> last_state; const float* last_series = nullptr; const float* last_md = nullptr;
@@ -102,6 +111,8 @@ class Plan {
   unsigned long long state_version = 0, packed_version = 0;
   std::vector<void*> packed_state;
   bool skip_pack = false;
+  bool shared = false;       // MAU_FLAG_SHARED_MAPS: encoder and LSTM run once, results broadcast over the batch
+  double exec_flops = 0;     // FLOPs the convolution kernels execute per forward (== fwd conv FLOPs unless shared)
 
   ~Plan();
   int build();
@@ -111,7 +122,7 @@ class Plan {
  private:
   // ---- construction helpers
   int add_state(const std::string& name, long long numel, int role);
-  int new_buf(const std::string& name, int H, int W, int C);
+  int new_buf(const std::string& name, int H, int W, int C, int B = -1);   // B < 0: cfg.batch
   void* alloc(size_t bytes);
   View view(const TRef& t) const;
   View whole(int buf) const;

@@ -38,6 +38,7 @@ class MauConfig(C.Structure):
 
 
 GRAD_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)
+STATS_SYNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -46,9 +47,9 @@ _lib_lock = threading.Lock()
 EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
-    "mau_plan_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_state_version",
+    "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
     "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics",
-    "mau_op_conv3x3", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_op_maxpool2x2", "mau_op_bilinear",
+    "mau_op_conv3x3", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
 
@@ -77,11 +78,13 @@ def lib():
         L.mau_plan_state_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
         L.mau_plan_describe_config.argtypes = [C.POINTER(MauConfig), C.c_char_p, C.c_size_t]
         L.mau_plan_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.mau_plan_exec_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.mau_plan_forward.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.mau_plan_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         L.mau_plan_set_grad_hook.argtypes = [C.c_void_p, GRAD_HOOK, C.c_void_p]
         L.mau_plan_set_state_version.argtypes = [C.c_void_p, C.c_uint64]
+        L.mau_plan_set_stats_sync.argtypes = [C.c_void_p, STATS_SYNC, C.c_void_p, C.c_int]
         L.mau_plan_profile.argtypes = [C.c_void_p, C.c_int]
         L.mau_plan_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_float),
                                             C.c_int, C.POINTER(C.c_int)]
@@ -102,6 +105,9 @@ def lib():
                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                                  C.c_void_p]
         L.mau_set_sm_reserve.argtypes = [C.c_int]
+        L.mau_adamw_step.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_double, C.c_double, C.c_double,
+                                     C.c_double, C.c_double, C.c_int64, C.c_void_p]
         L.mau_op_bw_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p]
         L.mau_op_maxpool2x2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -145,6 +151,18 @@ def describe(cfg: Dict) -> Dict:
     buf = C.create_string_buffer(1 << 20)
     check(lib().mau_plan_describe_config(C.byref(c), buf, len(buf)), "describe")
     return json.loads(buf.value.decode())
+
+
+class _DevMem:
+    """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_alias(ptr: int, n: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    typestr = {torch.float64: "<f8", torch.float32: "<f4"}[dtype]
+    return torch.as_tensor(_DevMem(ptr, n, typestr), device=device)
 
 
 class Plan:
@@ -192,6 +210,12 @@ class Plan:
         f, b = C.c_double(), C.c_double()
         check(lib().mau_plan_flops(self._h, C.byref(f), C.byref(b)), "flops")
         return f.value, b.value
+
+    def exec_conv_flops(self) -> float:
+        """FLOPs the conv kernels execute per forward (dense conv FLOPs unless this is a shared-maps plan)."""
+        f = C.c_double()
+        check(lib().mau_plan_exec_flops(self._h, C.byref(f)), "exec_flops")
+        return f.value
 
     def used_state_indices(self) -> List[int]:
         return [i for i, r in enumerate(self.roles) if r == ROLE_PARAM]
@@ -242,6 +266,20 @@ class Plan:
             return
         self._hook_ref = GRAD_HOOK(lambda _u, a, b: fn(a, b))
         check(lib().mau_plan_set_grad_hook(self._h, self._hook_ref, None), "set_grad_hook")
+
+    def set_stats_sync(self, fn, world_size: int = 1):
+        """SyncBN: fn(tensor) must all-reduce (SUM) the float64 device tensor in place on the current stream;
+        it is called from inside forward / backward once per BatchNorm layer."""
+        if fn is None:
+            self._sync_ref = None
+            check(lib().mau_plan_set_stats_sync(self._h, C.cast(None, STATS_SYNC), None, 1), "set_stats_sync")
+            return
+        dev = self.device
+
+        def cb(_user, ptr, n):
+            fn(device_alias(ptr, n, torch.float64, dev))
+        self._sync_ref = STATS_SYNC(cb)
+        check(lib().mau_plan_set_stats_sync(self._h, self._sync_ref, None, int(world_size)), "set_stats_sync")
 
     def profile(self, enable=True):
         check(lib().mau_plan_profile(self._h, int(enable)), "profile")

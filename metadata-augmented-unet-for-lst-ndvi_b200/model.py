@@ -70,14 +70,15 @@ class _EngineNet(nn.Module):
         object.__setattr__(self, "_plans", {})
         object.__setattr__(self, "_dp", None)
         object.__setattr__(self, "precision", engine.default_precision())
+        object.__setattr__(self, "shared_maps", "auto")
 
     # ------------------------------------------------------------------ #
     def _state_tensors(self) -> List[torch.Tensor]:
         # state_dict order == registration order (parameters and buffers interleaved per module)
         return list(self.state_dict(keep_vars=True).values())
 
-    def _plan_for(self, B: int, H: int, W: int, T: int, training: bool, device: torch.device):
-        key = (B, H, W, T, bool(training), self.precision, device.index)
+    def _plan_for(self, B: int, H: int, W: int, T: int, training: bool, device: torch.device, shared: bool = False):
+        key = (B, H, W, T, bool(training), self.precision, device.index, bool(shared))
         plan = self._plans.get(key)
         if plan is None:
             cfg = dict(self._engine_config())
@@ -85,11 +86,22 @@ class _EngineNet(nn.Module):
                        precision=engine.PRECISIONS[self.precision],
                        device=device.index if device.index is not None else torch.cuda.current_device())
             cfg["flags"] = int(cfg.get("flags", 0)) | int(os.environ.get("MAU_FLAGS", "0"))   # debug knobs
+            if shared:
+                cfg["flags"] |= engine.FLAG_SHARED_MAPS
             plan = engine.Plan(cfg)
             if len(self._plans) >= 8:           # bound the workspace held by stale shapes
                 self._plans.pop(next(iter(self._plans))).close()
             self._plans[key] = plan
         return plan
+
+    def assume_shared_maps(self, mode="auto"):
+        """``True``: the caller guarantees that all rows of ``maps`` / ``temp_series`` are identical (the
+        metadata-sensitivity sweep) -- the encoder and the LSTM then run once per forward.  ``"auto"``
+        (default): only batch-expanded (stride-0) inputs are treated that way.  ``False``: never."""
+        if mode not in (True, False, "auto"):
+            raise ValueError("mode must be True, False or 'auto'")
+        object.__setattr__(self, "shared_maps", mode)
+        return self
 
     def release_plans(self):
         for p in self._plans.values():
@@ -106,10 +118,25 @@ class _EngineNet(nn.Module):
         if min(H, W) < 16:
             raise RuntimeError("tile edge must be >= 16 (four 2x2 poolings)")
         T = int(temp_series.shape[1]) if temp_series.dim() == 2 else 0
-        plan = self._plan_for(B, H, W, T, self.training, maps.device)
+        # Sensitivity sweep (reference test/metadata_sensitivity.py:294-311): every row carries the same tile
+        # and series, only the metadata differs.  Detected for free when the caller passes batch-expanded
+        # views (stride 0 on dim 0, e.g. ``x.expand(50, -1, -1, -1)``), or asserted by the caller with
+        # ``assume_shared_maps(True)`` for materialised ``.repeat()`` batches.  Eval mode only.
+        shared = False
+        if not self.training and B > 1 and self.shared_maps is not False:
+            expanded = maps.stride(0) == 0 and (temp_series.dim() != 2 or temp_series.stride(0) == 0
+                                                or not self._cfg["temporal_embeddings"])
+            shared = bool(self.shared_maps is True or expanded)
+        if shared:
+            maps, temp_series = maps[:1], temp_series[:1]
+        plan = self._plan_for(B, H, W, T, self.training, maps.device, shared)
+        if self.training and getattr(self, "_dp", None) is not None:
+            self._dp.prepare_plan(plan)          # SyncBN hook (data-parallel training)
         maps = maps.contiguous().float()
         temp_series = temp_series.contiguous().float()
         metadata = metadata.contiguous().float()
+        if metadata.dim() == 2 and metadata.shape[0] != B and plan.uses_metadata:
+            raise RuntimeError(f"metadata must have {B} rows, got {metadata.shape[0]}")
         uses_meta = plan.uses_metadata
         if uses_meta and (metadata.dim() != 2 or metadata.shape[1] != self._cfg["meta_features"]):
             raise RuntimeError(f"metadata must be [B,{self._cfg['meta_features']}], got {tuple(metadata.shape)}")
@@ -229,6 +256,17 @@ class UrbanPredictor(nn.Module):
         return self.model(maps, temp_series, metadata)
 
     # convenience (not part of the reference surface)
+    def forward_sweep(self, maps, temp_series, metadata):
+        """One tile, many metadata rows (reference test/metadata_sensitivity.py:294-311 builds this with
+        ``.repeat(50, ...)``): ``maps`` [1,C,H,W], ``temp_series`` [1,T], ``metadata`` [B,F] -> [B,out,H,W].
+        Identical to ``forward(maps.repeat(B,1,1,1), temp_series.repeat(B,1), metadata)`` in eval mode."""
+        B = metadata.shape[0]
+        return self.model(maps[:1].expand(B, -1, -1, -1), temp_series[:1].expand(B, -1), metadata)
+
+    def assume_shared_maps(self, mode="auto"):
+        self.model.assume_shared_maps(mode)
+        return self
+
     def set_precision(self, precision: str):
         """'bf16' (tcgen05 tensor-core path, default) or 'fp32' (FFMA path, 1e-5 parity mode)."""
         if precision not in engine.PRECISIONS:

@@ -4,8 +4,10 @@ launched from *inside* backward, layer by layer, as each layer's weight gradient
 (``mau_plan_set_grad_hook``), on a side stream so that it overlaps the remaining backward kernels.
 
 The reference is single-GPU (``CONFIG.device = "cuda:0"``, src/train.py:99); this is a new
-capability.  BatchNorm uses per-rank batch statistics (the throughput mode); running statistics
-can be averaged across ranks with :meth:`DataParallel.sync_buffers` before a checkpoint.
+capability.  BatchNorm uses per-rank batch statistics by default (the throughput mode; running statistics
+can be averaged across ranks with :meth:`DataParallel.sync_buffers` before a checkpoint).  With
+``sync_bn=True`` every BatchNorm all-reduces its per-channel sums (2*C doubles, forward and backward)
+so that an N-rank step equals the single-process step at the global batch -- the reference semantics.
 
 Inference needs none of this: tiles are independent in eval mode, shard them and run replicas.
 """
@@ -75,14 +77,29 @@ class DataParallel:
     """Wraps a :class:`mau_b200.UrbanPredictor`; the module itself (and therefore the reference's
     training loop, optimizer and checkpoint code) is used unchanged."""
 
-    def __init__(self, model, group=None, bucket_mb: float = 8.0, broadcast_init: bool = True):
+    def __init__(self, model, group=None, bucket_mb: float = 8.0, broadcast_init: bool = True,
+                 sync_bn: bool = False):
         self.model, self.group = model, group
         self.net = model.model
+        self.sync_bn = bool(sync_bn)
         self.bucket_numel = int(bucket_mb * (1 << 20) / 4)
         object.__setattr__(self.net, "_dp", self)   # picked up by the model's forward -> HotPathFn
         if broadcast_init and dist.is_initialized() and dist.get_world_size(group) > 1:
             for t in model.state_dict().values():
                 dist.broadcast(t, src=0, group=group)
+
+    def prepare_plan(self, plan: "engine.Plan"):
+        """Called by the model when it (re)uses a training plan: installs the SyncBN all-reduce if requested."""
+        if not self.sync_bn or getattr(plan, "_sync_installed", False):
+            return
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        group = self.group
+
+        def allreduce(t: torch.Tensor):
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        plan.set_stats_sync(allreduce, world)
+        plan._sync_installed = True
 
     # called by engine.HotPathFn.backward ---------------------------------------------------
     def make_grads(self, plan: "engine.Plan", diff_idx: List[int], shapes) -> Tuple[List[Optional[torch.Tensor]], list]:

@@ -368,3 +368,60 @@ def test_eval_weight_cache_is_invalidated_by_inplace_updates():
     sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
     ref = O.forward(sd, "unet", x.cpu(), ts.cpu(), md.cpu(), training=False, **kw)
     assert rel(y3, ref) < 1e-2
+
+
+def test_fused_adamw_matches_torch_adamw():
+    """mau_adamw_step vs torch.optim.AdamW: same parameters / state after several steps, None-grad parameters
+    untouched, interchangeable state_dict (reference src/train.py:213-214,255,309)."""
+    torch.manual_seed(11)
+    shapes = [(64, 23, 3, 3), (64,), (1024, 640, 3, 3), (2, 64, 1, 1), (2,), (384, 96), (7,)]
+    ref = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    kw = dict(lr=1e-2, weight_decay=1e-3)
+    o_ref, o_mine = torch.optim.AdamW(ref, **kw), mau_b200.FusedAdamW(mine, **kw)
+    for it in range(4):
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            if i == 3 and it < 2:        # a parameter without gradient in the first steps
+                a.grad = b.grad = None
+                continue
+            g = torch.randn_like(a) * (0.1 + it)
+            a.grad, b.grad = g.clone(), g.clone()
+        o_ref.step(); o_mine.step()
+    for a, b in zip(ref, mine):
+        assert rel(b, a) < 2e-6
+    sa, sb = o_ref.state_dict(), o_mine.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"])
+        assert rel(sb["state"][k]["exp_avg"], sa["state"][k]["exp_avg"]) < 2e-6
+        assert rel(sb["state"][k]["exp_avg_sq"], sa["state"][k]["exp_avg_sq"]) < 2e-6
+    o_ref.load_state_dict(sb)          # interchangeable checkpoints
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["unet_metaemb", "unet_emb", "unetpp_emb"])
+def test_shared_maps_sweep_is_bit_identical(name, precision):
+    """Config 5 (reference test/metadata_sensitivity.py:294-311): one tile repeated B times, only the metadata
+    rows differ.  The sweep plan (encoder + LSTM once, skips broadcast over the batch) must return exactly what
+    the dense forward on the materialised .repeat() batch returns, and the oracle on that batch must agree."""
+    mt, _, kw = VARIANTS[name]
+    torch.manual_seed(5)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw)
+    O.perturb_bn_stats(m.state_dict())
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda().set_precision(precision).eval()
+    g = torch.Generator().manual_seed(3)
+    B = 7
+    x1 = torch.randn(1, 23, 37, 45, generator=g); ts1 = torch.randn(1, 40, generator=g)
+    md = torch.randn(B, 8, generator=g); md[:, 0] = torch.linspace(-2, 2, B)
+    xr, tr = x1.repeat(B, 1, 1, 1), ts1.repeat(B, 1)
+    with torch.no_grad():
+        dense = m(xr.cuda(), tr.cuda(), md.cuda())                       # materialised batch: dense plan
+        sweep = m.forward_sweep(x1.cuda(), ts1.cuda(), md.cuda())        # expanded views: sweep plan
+        m.assume_shared_maps(True)
+        asserted = m(xr.cuda(), tr.cuda(), md.cuda())                    # caller-asserted on a .repeat() batch
+        m.assume_shared_maps("auto")
+    assert len(m.model._plans) == 2
+    assert torch.equal(sweep, dense) and torch.equal(asserted, dense)
+    ref = O.forward(sd, mt, xr, tr, md, training=False, **kw)
+    assert rel(dense, ref) < TOL[precision]

@@ -52,13 +52,18 @@ def main():
     if os.path.exists(pk):
         peak = json.load(open(pk))["hbm_gbs"]
     rows = []
+    iters = int(os.environ.get("BW_ITERS", "24"))
+    only = os.environ.get("BW_ONLY", "")
+    only = set(only.split(",")) if only else None
     for name, H, Cc in CASES:
+        if only and name not in only:
+            continue
         kind, fbytes = KINDS[name]
         by = fbytes(B, H, H, Cc, 2)
         sets = max(2, int(300e6 // max(by, 1)) + 1)
         sets = min(sets, 12)
         ms = C.c_float()
-        rc = L.mau_op_bw_bench(kind, 0, B, H, H, Cc, 24, sets, C.byref(ms))
+        rc = L.mau_op_bw_bench(kind, 0, B, H, H, Cc, iters, sets, C.byref(ms))
         if rc:
             print(f"{name:16s} {H:4d} C={Cc:4d}  ERR {L.mau_last_error().decode()[:80]}", flush=True)
             continue

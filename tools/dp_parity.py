@@ -1,0 +1,65 @@
+"""N-rank data-parallel training step vs the single-process oracle at the GLOBAL batch.
+
+    torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_parity.py
+
+With sync_bn=True the step must equal the reference semantics (one device, whole batch): loss, every
+parameter gradient (after the gradient average) and the BatchNorm running statistics.  fp32 mode.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import mau_b200  # noqa: E402
+from mau_b200 import parallel  # noqa: E402
+from oracle import unet_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok_all = True
+    for mt, kw in (("unet", dict(temporal_embeddings=False, metadata_embeddings=True)), ("unet++", dict())):
+        torch.manual_seed(7)
+        m = mau_b200.UrbanPredictor(mt, 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw)
+        sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+        per = 2
+        x, ts, md, tgt = O.synthetic_batch(per * world, 37, 45, T=24, seed=99)
+        m = m.to(dev).set_precision("fp32").train()
+        parallel.DataParallel(m, sync_bn=True)
+        sl = slice(rank * per, (rank + 1) * per)
+        out = m(x[sl].to(dev), ts[sl].to(dev), md[sl].to(dev))
+        loss = (out - tgt[sl].to(dev)).abs().mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        lsum = loss.detach().clone()
+        dist.all_reduce(lsum)
+        if rank == 0:
+            _, lref, grads, sd1 = O.train_step_grads(sd0, mt, x, ts, md, tgt, loss="l1", **kw)
+            worst, name_w = 0.0, ""
+            for k, p in m.named_parameters():
+                if p.grad is None:
+                    continue
+                g, r = p.grad.cpu(), grads[k]
+                e = float((g - r).norm() / r.norm().clamp_min(1e-12))
+                if r.norm() > 1e-6 and e > worst:
+                    worst, name_w = e, k
+            sd_now = m.state_dict()
+            rs = max(float((sd_now[k].cpu() - sd1[k]).abs().max()) for k in sd1 if "running" in k)
+            lerr = abs(float(lsum) / world - float(lref))
+            ok = worst < 2e-3 and rs < 1e-5 and lerr < 1e-5
+            ok_all &= ok
+            print(f"[dp_parity] {mt} world={world}: loss err {lerr:.2e}, worst grad rel L2 {worst:.2e} ({name_w}), "
+                  f"running-stat max err {rs:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok_all:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
