@@ -170,6 +170,11 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
 int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
                    const float* w_oihw_dev, const float* scale_dev, const float* shift_dev, int relu,
                    int Cout, void* y_dev, int Cout_stride, void* stream);
+/* dX[:, ci0 : ci0+n_ci] (=|+=) data gradient of the same convolution from dZ [B,H,W,Cout_stride] (bf16 NHWC);
+ * impl 0 = reads W^T MN-major out of the forward weight pack, 1 = transposed re-pack (first generation) */
+int mau_op_conv3x3_dgrad(int impl, const void* dz_dev, int B, int H, int W, int Cout, int Cout_stride,
+                         const float* w_oihw_dev, int Cin, int ci0, int n_ci, void* dx_dev, int dx_stride,
+                         int accumulate, void* stream);
 /* timing helper (tools/conv_bench.py): bf16 tcgen05 conv, `iters` launches between CUDA events */
 int mau_op_conv3x3_bench(int impl, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
                          const float* w_oihw_dev, int Cout, void* y_dev, int Cout_stride, int iters, float* ms_out);

@@ -207,6 +207,38 @@ int mau_op_conv3x3(int impl, int dtype, const void* x_dev, int B, int H, int W, 
   return rc;
 }
 
+// data gradient of the 3x3 convolution w.r.t. an input-channel range [ci0, ci0 + n_ci): dx = conv(dz, W^T flipped).
+// impl 0: tcgen05 halo kernel reading the forward pack MN-major; impl 1: same kernel on a transposed re-pack.
+int mau_op_conv3x3_dgrad(int impl, const void* dz_dev, int B, int H, int W, int Cout, int Cout_stride,
+                         const float* w_oihw_dev, int Cin, int ci0, int n_ci, void* dx_dev, int dx_stride, int accumulate,
+                         void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Kp = round_up(Cin, 64), Kd = round_up(Cout, 64);
+  std::vector<int> kmap(Kp);
+  for (int i = 0; i < Kp; ++i) kmap[i] = i < Cin ? i : -1;
+  int* kmap_dev = nullptr; void* wp = nullptr; void* wd = nullptr;
+  MAU_CUDA(cudaMalloc(&kmap_dev, sizeof(int) * Kp));
+  MAU_CUDA(cudaMemcpy(kmap_dev, kmap.data(), sizeof(int) * Kp, cudaMemcpyHostToDevice));
+  MAU_CUDA(cudaMalloc(&wp, (size_t)2 * 9 * Kp * Cout));
+  MAU_CUDA(cudaMalloc(&wd, (size_t)2 * 9 * Kd * n_ci));
+  const View dz = mkview(dz_dev, B, H, W, Cout, Cout_stride), dx = mkview(dx_dev, B, H, W, n_ci, dx_stride);
+  ConvTcOp op;
+  int rc = 0;
+  if (impl == 0) {
+    rc = conv_tc_pack_fwd(w_oihw_dev, Cout, Cin, kmap_dev, Kp, wp, st);
+    if (!rc) rc = conv_tc_prepare_dgrad(&op, dz, wp, Kp, ci0, dx, accumulate);
+  } else {
+    const int zero = 0;
+    rc = conv_tc_pack_dgrad(w_oihw_dev, Cout, Cin, ci0, n_ci, Kd, wd, st);
+    if (!rc) rc = conv_tc_prepare(&op, dz, 1, &zero, &Cout, wd, Kd, n_ci, dx, MODE_HALO, nullptr, nullptr, 0, accumulate, 0);
+  }
+  if (!rc) rc = conv_tc_launch(op, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(kmap_dev); cudaFree(wp); cudaFree(wd);
+  if (!rc && e != cudaSuccess) rc = fail("conv3x3 dgrad execution failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
 // timing helper for tools/conv_bench.py: prepares once, launches `iters` times between CUDA events
 int mau_op_conv3x3_bench(int impl, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
                          const float* w_oihw_dev, int Cout, void* y_dev, int Cout_stride, int iters, float* ms_out) {

@@ -271,7 +271,7 @@ struct V2Smem {
                                    16 + (2 + (BN <= 128 ? kHeadOC : 0)) * BN * sizeof(float);
 };
 
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmY,
@@ -349,7 +349,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
             mbar_wait(&emptyB[rb.stage], rb.phase ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&fullB[rb.stage], S::B_STAGE);
-              tma_load_3d(sB + rb.stage * S::B_STAGE, &tmB, &fullB[rb.stage], kB, n0, tap);
+              if (BT) {
+                // data gradient: B = W^T of the flipped tap, read MN-major straight from the FORWARD weight pack
+                // [9][Cout][Kp]: boxes {64 ci, 64 co} -> smem [64 k rows][128 B of n]; no transposed re-pack
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_3d(sB + rb.stage * S::B_STAGE + j * 8192, &tmB, &fullB[rb.stage], p.bt_col0 + n0 + 64 * j, kB, 8 - tap);
+              } else {
+                tma_load_3d(sB + rb.stage * S::B_STAGE, &tmB, &fullB[rb.stage], kB, n0, tap);
+              }
             }
             __syncwarp();
             rb.advance(NB);
@@ -359,10 +367,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (whole warp converged, one elected lane issues) ============
-    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 0, 0);
+    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 0, BT ? 1 : 0);
     // descriptor templates: only the 14-bit start-address field changes between MMAs
     const uint64_t descA0 = smem_desc_sw128(0, 16, 1280, 0);
-    const uint64_t descB0 = smem_desc_sw128(0, 16, 1024, 0);
+    // B K-major: rows of 128 B = 64 k of one n.  B MN-major (BT): rows of 128 B = 64 n of one k, 64-wide n groups
+    // at LBO = 8192 B, 8-row k groups at SBO = 1024 B; a K = 16 step advances 16 rows = 2048 B.
+    const uint64_t descB0 = BT ? smem_desc_sw128(0, 8192, 1024, 0) : smem_desc_sw128(0, 16, 1024, 0);
+    constexpr int kBStep = BT ? 2048 : 32;
     Ring ra, rb;
     int buf = 0;
     uint32_t ephase[2] = {0, 0};
@@ -390,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
               if (j < nsub) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(d0 + j * BN, da + (uint64_t)((j * kHaloStride + k * 32) >> 4), db + (uint64_t)((k * 32) >> 4),
+                  umma_bf16(d0 + j * BN, da + (uint64_t)((j * kHaloStride + k * 32) >> 4), db + (uint64_t)((k * kBStep) >> 4),
                             idesc, k ? 1u : first);
               }
             }
@@ -525,14 +536,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   }
 }
 
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT>
 int launch_v2(const ConvTcOp& op, cudaStream_t st) {
   using S = V2Smem<BN, MT, NBUF, NA, NB, NSTG>;
   static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG>;
+  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG, BT>;
   if (!attr_done[dev & 15]) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
@@ -546,18 +557,31 @@ int launch_v2(const ConvTcOp& op, cudaStream_t st) {
 // weight packing: OIHW fp32 -> [9][N][Kp] bf16
 // fwd : out[t][n][kp] = W[n][kmap[kp]][t]            (kmap = -1 -> 0)
 // dgrad: out[t][n][kp] = W[kp][ci0 + n][8 - t]       (kp >= Cout -> 0)
-__global__ void pack_w_fwd_kernel(const float* __restrict__ w, int Cout, int Cin, const int* __restrict__ kmap,
-                                  int Kp, __nv_bfloat16* __restrict__ out) {
-  const long long total = 9LL * Cout * Kp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int kp = (int)(i % Kp);
-    const long long r = i / Kp;
-    const int n = (int)(r % Cout);
-    const int t = (int)(r / Cout);
-    const int ci = kmap[kp];
-    const float v = ci >= 0 ? w[((long long)n * Cin + ci) * 9 + t] : 0.f;
-    out[i] = __float2bfloat16_rn(v);
+// one warp per (output channel n, 64-wide packed-K chunk): the 64 x 9 source floats of a chunk are contiguous
+// in OIHW when the chunk maps to consecutive input channels, so they are read as one coalesced 2304-byte run,
+// transposed through shared memory and written as nine 128-byte bf16 rows
+__global__ void __launch_bounds__(256) pack_w_fwd_kernel(const float* __restrict__ w, int Cout, int Cin,
+                                                         const int* __restrict__ kmap, int Kp,
+                                                         __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[8][9][65];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = Kp >> 6;
+  const long long total = (long long)Cout * chunks;
+  for (long long item = (long long)blockIdx.x * 8 + warp; item < total; item += (long long)gridDim.x * 8) {
+    const int n = (int)(item / chunks), kp0 = (int)(item % chunks) << 6;
+    const float* src = w + (long long)n * Cin * 9;
+    for (int e = lane; e < 576; e += 32) {
+      const int kl = e / 9, t = e - kl * 9;
+      const int ci = kmap[kp0 + kl];
+      tile[warp][t][kl] = ci >= 0 ? src[ci * 9 + t] : 0.f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const __nv_bfloat162 v = __floats2bfloat162_rn(tile[warp][t][2 * lane], tile[warp][t][2 * lane + 1]);
+      *reinterpret_cast<__nv_bfloat162*>(out + ((long long)t * Cout + n) * Kp + kp0 + 2 * lane) = v;
+    }
+    __syncwarp();
   }
 }
 __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int ci0, int N, int Kp,
@@ -608,9 +632,31 @@ static int pick_bn_v2(int Cout) {
   return best;
 }
 
+static int prepare_impl(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
+                        const void* wpacked, int Kp, int n_rows, const View& y, int mode, const float* scale,
+                        const float* shift, int relu, int accumulate, int halo_base_offset, int bt, int bt_col0,
+                        int bt_kp_fwd);
+
 int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
                     const void* wpacked, int Kp, int n_rows, const View& y, int mode, const float* scale,
                     const float* shift, int relu, int accumulate, int halo_base_offset) {
+  return prepare_impl(op, xbuf, nseg, seg_start, seg_len, wpacked, Kp, n_rows, y, mode, scale, shift, relu, accumulate,
+                      halo_base_offset, 0, 0, 0);
+}
+
+// data gradient of one input segment: dX[:, seg] = conv(dZ, W^T flipped), B operand read MN-major from the forward
+// pack wpack_fwd [9][Cout][Kp_fwd]; col0 = packed column of the segment's first input channel
+int conv_tc_prepare_dgrad(ConvTcOp* op, const View& dz, const void* wpack_fwd, int Kp_fwd, int col0, const View& gx,
+                          int accumulate) {
+  const int zero = 0, C = dz.C;
+  return prepare_impl(op, dz, 1, &zero, &C, wpack_fwd, round_up(C, 64), C, gx, MODE_HALO, nullptr, nullptr, 0, accumulate,
+                      0, 1, col0, Kp_fwd);
+}
+
+static int prepare_impl(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
+                        const void* wpacked, int Kp, int n_rows, const View& y, int mode, const float* scale,
+                        const float* shift, int relu, int accumulate, int halo_base_offset, int bt, int bt_col0,
+                        int bt_kp_fwd) {
   if (nseg < 1 || nseg > 4) return fail("conv_tc: 1..4 input segments supported, got %d", nseg);
   if (xbuf.cs % 8 || y.cs % 8 || y.c0 % 8 || Kp % 64)
     return fail("conv_tc: channel strides/offsets must be multiples of 8 (cs=%d, ycs=%d, yc0=%d, Kp=%d)", xbuf.cs,
@@ -660,8 +706,14 @@ int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_sta
   if (mode == MODE_ROW3) { bw = 8; bh = p.TH + 2; }
   if (mode == MODE_HALO) { bw = 10; bh = p.TH + 2; }
   MAU_TRY(make_nhwc_map(&op->tmA, DT_BF16, xa, 64, bw, bh));
-  // B: packed weights {Kp, n_rows, 9}
-  {
+  // B: packed weights {Kp, n_rows, 9}; dgrad (bt) reads {64 ci, 64 co} boxes of the forward pack instead
+  p.bt = bt; p.bt_col0 = bt_col0;
+  if (bt) {
+    uint64_t dims[3] = {(uint64_t)bt_kp_fwd, (uint64_t)n_rows, 9};
+    uint64_t str[2] = {(uint64_t)bt_kp_fwd * 2, (uint64_t)bt_kp_fwd * 2 * (uint64_t)n_rows};
+    uint32_t box[3] = {64, 64, 1};
+    MAU_TRY(make_tensor_map(&op->tmB, DT_BF16, 3, const_cast<void*>(wpacked), dims, str, box, true));
+  } else {
     uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)n_rows, 9};
     uint64_t str[2] = {(uint64_t)Kp * 2, (uint64_t)Kp * 2 * (uint64_t)n_rows};
     uint32_t box[3] = {64, (uint32_t)op->bn, 1};
@@ -683,8 +735,10 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
   MAU_INST(256, MODE_ROW3, 2, 3)
 #undef MAU_INST
   if (op.mode == MODE_HALO) {
-#define MAU_V2(BN_, MT_, NBUF_, NA_, NB_, NSTG_) \
-    if (op.bn == BN_ && op.mt == MT_ && op.nbuf == NBUF_) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_>(op, st);
+#define MAU_V2(BN_, MT_, NBUF_, NA_, NB_, NSTG_)                                                        \
+    if (op.bn == BN_ && op.mt == MT_ && op.nbuf == NBUF_)                                               \
+      return op.p.bt ? launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, true>(op, st)                        \
+                     : launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false>(op, st);
     MAU_V2(64, 4, 2, 2, 3, 1)
     MAU_V2(64, 2, 2, 2, 4, 2)
     MAU_V2(128, 2, 2, 2, 4, 2)
@@ -699,8 +753,8 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
 
 int conv_tc_pack_fwd(const float* w_oihw, int Cout, int Cin, const int* kmap_dev, int Kp, void* out,
                      cudaStream_t st) {
-  const long long total = 9LL * Cout * Kp;
-  int blocks = (int)((total + 255) / 256);
+  const long long items = (long long)Cout * (Kp / 64);
+  int blocks = (int)((items + 7) / 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_w_fwd_kernel<<<blocks, 256, 0, st>>>(w_oihw, Cout, Cin, kmap_dev, Kp, static_cast<__nv_bfloat16*>(out));
   MAU_LAUNCHED();

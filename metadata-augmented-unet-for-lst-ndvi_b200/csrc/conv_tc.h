@@ -25,6 +25,7 @@ struct ConvTcParams {
   const float* head_w = nullptr; const float* head_b = nullptr; float* head_out = nullptr;
   int head_oc = 0, head_tanh = 0, H = 0, W = 0;
   int store_y = 1;               // 0: skip the activation store (only the fused head output is needed)
+  int bt = 0, bt_col0 = 0;       // data gradient: B read MN-major from the forward weight pack, first packed column
 };
 
 struct ConvTcOp {
@@ -43,6 +44,9 @@ int conv_tc_pick_bn(int Cout);
 int conv_tc_prepare(ConvTcOp* op, const View& xbuf, int nseg, const int* seg_start, const int* seg_len,
                     const void* wpacked, int Kp, int n_rows, const View& y, int mode, const float* scale,
                     const float* shift, int relu, int accumulate, int halo_base_offset);
+// data gradient w.r.t. one input segment without a transposed weight pack (halo kernel only)
+int conv_tc_prepare_dgrad(ConvTcOp* op, const View& dz, const void* wpack_fwd, int Kp_fwd, int col0, const View& gx,
+                          int accumulate);
 int conv_tc_launch(const ConvTcOp& op, cudaStream_t st);
 int conv_tc_pack_fwd(const float* w_oihw, int Cout, int Cin, const int* kmap_dev, int Kp, void* out,
                      cudaStream_t st);

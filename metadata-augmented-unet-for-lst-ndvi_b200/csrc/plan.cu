@@ -263,7 +263,12 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
       MAU_TRY(gview(xin, &gx));
       MAU_TRY(gcontrib(xin, &dacc[s]));
       const int zero = 0;
-      if (use_tc) {
+      if (use_tc && conv_mode == MODE_HALO) {
+        // no transposed re-pack: the kernel reads W^T MN-major out of the forward pack (packed column of this segment)
+        int col0 = 0;
+        for (int q = 0; q < s; ++q) col0 += round_up(L->seg_len[q], 64);
+        MAU_TRY(conv_tc_prepare_dgrad(&L->tc_d[s], z, L->wpack, L->Kp, col0, gx, dacc[s]));
+      } else if (use_tc) {
         L->wpack_d[s] = alloc((size_t)9 * L->seg_len[s] * L->Kd * 2);
         if (!L->wpack_d[s]) return -1;
         MAU_TRY(conv_tc_prepare(&L->tc_d[s], z, 1, &zero, &C, L->wpack_d[s], L->Kd, L->seg_len[s], gx, conv_mode,
@@ -310,7 +315,8 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
       }
       if (L->input_needs_grad) {
         if (use_tc) {
-          MAU_TRY(conv_tc_pack_dgrad(c.f(L->iw), C, L->Cin, ci_w0, L->seg_len[s], L->Kd, L->wpack_d[s], c.st));
+          if (L->wpack_d[s])
+            MAU_TRY(conv_tc_pack_dgrad(c.f(L->iw), C, L->Cin, ci_w0, L->seg_len[s], L->Kd, L->wpack_d[s], c.st));
           kbegin(c, "k:" + L->name + ":dgrad");
           MAU_TRY(conv_tc_launch(L->tc_d[s], c.st));
           kend(c);

@@ -58,6 +58,32 @@ def test_conv3x3_against_torch(impl, dt, shape):
     assert rel(y.permute(0, 3, 1, 2), ref) < (6e-3 if dt == 0 else 1e-5)
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64, 0, 64), (1, 31, 31, 192, 256, 64, 128), (2, 33, 47, 24, 64, 0, 24),
+                                   (2, 15, 15, 320, 72, 128, 192), (1, 50, 50, 384, 128, 0, 384)])
+def test_conv3x3_dgrad_against_torch(impl, shape):
+    """Data gradient w.r.t. an input-channel segment [ci0, ci0+n): impl 0 reads W^T MN-major out of the FORWARD
+    weight pack (no transposed re-pack), impl 1 is the first-generation re-packed path; both against autograd."""
+    B, H, W, Cin, Cout, ci0, n = shape
+    torch.manual_seed(4)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / (3 * Cout ** 0.5)
+    dz = torch.randn(B, Cout, H, W, device="cuda").bfloat16().float()
+    wr = w.bfloat16().float()
+    x = torch.zeros(B, Cin, H, W, device="cuda", dtype=torch.double, requires_grad=True)
+    (F.conv2d(x, wr.double(), padding=1) * dz.double()).sum().backward()
+    want = x.grad[:, ci0:ci0 + n].float()
+    dzh = nhwc(dz, torch.bfloat16)
+    cs = (n + 7) // 8 * 8
+    base = torch.randn(B, H, W, cs, device="cuda").bfloat16()
+    for acc in (0, 1):
+        dx = base.clone() if acc else torch.zeros_like(base)
+        engine.check(engine.lib().mau_op_conv3x3_dgrad(impl, dzh.data_ptr(), B, H, W, Cout, dzh.shape[-1], w.data_ptr(), Cin, ci0, n,
+                                                       dx.data_ptr(), cs, acc, None), "dgrad")
+        torch.cuda.synchronize()
+        got = dx[..., :n].float().permute(0, 3, 1, 2) - (base[..., :n].float().permute(0, 3, 1, 2) if acc else 0)
+        assert rel(got, want) < (2e-2 if acc else 6e-3)
+
+
 @pytest.mark.parametrize("impl,dt", [(0, 0), (4, 0), (5, 0), (1, 0), (2, 1)])
 @pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64), (2, 15, 15, 128, 256), (2, 33, 47, 24, 64), (1, 25, 25, 8, 8),
                                    (2, 15, 15, 640, 640), (1, 31, 31, 192, 64), (3, 18, 50, 72, 200)])
