@@ -382,7 +382,7 @@ int mau_op_bw_bench(int kind, int dtype, int B, int H, int W, int C, int iters, 
       case 0: return op_bn_stats(dtype, a, s.d, 0);
       case 1: return op_bn_apply_relu(dtype, a, coef, coef + C, b, 0);
       case 2: return op_bn_bwd_reduce(dtype, a, b, coef, coef + C, coef + 2 * C, coef + 3 * C, s.d, 0);
-      case 3: return op_bn_bwd_apply(dtype, a, b, coef, coef + C, coef + 2 * C, coef + 3 * C, coef + 4 * C, s.d, (long long)B * H * W, b, s.d + 2 * C, 0);
+      case 3: return op_bn_bwd_apply(dtype, a, b, coef, coef + C, coef + 2 * C, coef + 3 * C, coef + 4 * C, s.d, (long long)B * H * W, b, nullptr, nullptr, nullptr, nullptr, 0);
       case 4: return op_maxpool(dtype, a, sm, 0);
       case 5: return op_maxpool_bwd(dtype, a, sm, nullptr, b, 0);
       case 6: return op_bilinear(dtype, sm, a, t, 0);

@@ -268,10 +268,12 @@ struct V2Smem {
   static constexpr int kBars = 2 * NA + 2 * NB + 4;
   static constexpr int kHeadOC = 4;                 // fused 1x1 head: up to 4 output channels
   static constexpr size_t kBytes = 1024 + (size_t)NA * A_STAGE + (size_t)NB * B_STAGE + (size_t)NSTG * STG + 8 * kBars +
-                                   16 + (2 + (BN <= 128 ? kHeadOC : 0)) * BN * sizeof(float);
+                                   32 + (2 + (BN <= 128 ? kHeadOC : 0)) * BN * sizeof(float);
 };
 
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT>
+// EM = epilogue mode: 0 none (data gradient), 1 + shift (training forward: bias), 2 * scale + shift (eval: folded
+// BatchNorm), 3 = 2 + fused 1x1 head.  A template parameter so that every instance carries one epilogue only.
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmY,
@@ -292,10 +294,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   uint64_t* tmem_full = emptyB + NB;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_scale = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~uintptr_t(15));   // float4 reads
   float* s_shift = s_scale + BN;
   float* s_hw = s_shift + BN;            // [kHeadOC][BN], only when BN <= 128
-  constexpr bool kCanHead = BN <= 128;
+  constexpr bool kCanHead = BN <= 128 && EM == 3;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_img = p.tiles_w * p.tiles_h;
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
     const int et = threadIdx.x - 128;
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    constexpr int emode = EM >= 2 ? 2 : EM;
     int buf = 0, stg = 0, cur_n0 = -1;
     uint32_t fphase[2] = {0, 0};
     for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
           const bool ok = c < p.Cout;
           s_scale[i] = ok ? (p.scale ? p.scale[c] : 1.f) : 0.f;
           s_shift[i] = ok ? (p.shift ? p.shift[c] : 0.f) : 0.f;
-          if (kCanHead && p.head_out)
+          if constexpr (kCanHead)
             for (int o = 0; o < S::kHeadOC; ++o) s_hw[o * BN + i] = (ok && o < p.head_oc) ? p.head_w[o * p.Cout + c] : 0.f;
         }
         named_bar_sync(1, 128);
@@ -450,7 +453,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
         const int th = rem / p.tiles_w;
         const int w0 = (rem - th * p.tiles_w) * 8, h0 = th * 16;
         float hacc[S::kHeadOC] = {0.f, 0.f, 0.f, 0.f};
-        const bool do_head = kCanHead && p.head_out != nullptr;
 #pragma unroll 1
         for (int u = 0; u < BN / S::SU; ++u) {          // store rounds of SU columns
           uint8_t* sbuf = sStg + stg * S::STG;
@@ -460,26 +462,60 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
             if (et == 0) { if (NSTG == 1) tma_wait_group_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
             named_bar_sync(1, 128);
           }
-#pragma unroll 1
-          for (int cb = 0; cb < S::SU / 32; ++cb) {
-            uint32_t v[32];
+          // TMEM -> registers is double-buffered: the load of column block cb + 1 is in flight while block cb is
+          // converted and staged.  Per-channel affine: mode 0 = none (data gradient), 1 = + shift (training forward:
+          // bias), 2 = * scale + shift (eval: folded BatchNorm); coefficients are read as float4 broadcasts.
+          constexpr int kCB = S::SU / 32;
+          uint32_t vv[2][32];
+          const uint32_t tcol0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBufCols + j * BN + u * S::SU;
+          tmem_ld_32x32(tcol0, vv[0]);
+#pragma unroll
+          for (int cb = 0; cb < kCB; ++cb) {
+            uint32_t (&v)[32] = vv[cb & 1];
             const int col = u * S::SU + cb * 32;
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBufCols + j * BN + col, v);
             tmem_ld_wait();
+            reg_fence32(v);
+            if (cb + 1 < kCB) tmem_ld_32x32(tcol0 + (cb + 1) * 32, vv[(cb + 1) & 1]);
             uint32_t pk[16];
+            if constexpr (emode == 0) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int c = col + 2 * jj;
-              float y0 = __uint_as_float(v[2 * jj]) * s_scale[c] + s_shift[c];
-              float y1 = __uint_as_float(v[2 * jj + 1]) * s_scale[c + 1] + s_shift[c + 1];
-              if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
-              pk[jj] = *reinterpret_cast<uint32_t*>(&h2);
-              if (kCanHead && do_head) {          // the head sees the bf16-rounded activation, like the unfused path
-                const float r0 = __low2float(h2), r1 = __high2float(h2);
+              for (int jj = 0; jj < 16; ++jj) {
+                float y0 = __uint_as_float(v[2 * jj]), y1 = __uint_as_float(v[2 * jj + 1]);
+                if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+                pk[jj] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+            } else if constexpr (emode == 1) {
 #pragma unroll
-                for (int o = 0; o < S::kHeadOC; ++o)
-                  hacc[o] = fmaf(r1, s_hw[o * BN + c + 1], fmaf(r0, s_hw[o * BN + c], hacc[o]));
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 sh = *reinterpret_cast<const float4*>(s_shift + col + 4 * j4);
+                float y0 = __uint_as_float(v[4 * j4]) + sh.x, y1 = __uint_as_float(v[4 * j4 + 1]) + sh.y;
+                float y2 = __uint_as_float(v[4 * j4 + 2]) + sh.z, y3 = __uint_as_float(v[4 * j4 + 3]) + sh.w;
+                if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+                __nv_bfloat162 ha = __floats2bfloat162_rn(y0, y1), hb = __floats2bfloat162_rn(y2, y3);
+                pk[2 * j4] = *reinterpret_cast<uint32_t*>(&ha);
+                pk[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&hb);
+              }
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const int c = col + 4 * j4;
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+                const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+                float y0 = fmaf(__uint_as_float(v[4 * j4]), sc.x, sh.x), y1 = fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y);
+                float y2 = fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), y3 = fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w);
+                if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+                __nv_bfloat162 ha = __floats2bfloat162_rn(y0, y1), hb = __floats2bfloat162_rn(y2, y3);
+                pk[2 * j4] = *reinterpret_cast<uint32_t*>(&ha);
+                pk[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&hb);
+                if constexpr (kCanHead) {           // the head sees the bf16-rounded activation, like the unfused path
+                  const float r0 = __low2float(ha), r1 = __high2float(ha), r2 = __low2float(hb), r3 = __high2float(hb);
+#pragma unroll
+                  for (int o = 0; o < S::kHeadOC; ++o) {
+                    const float4 hw = *reinterpret_cast<const float4*>(s_hw + o * BN + c);
+                    hacc[o] = fmaf(r3, hw.w, fmaf(r2, hw.z, fmaf(r1, hw.y, fmaf(r0, hw.x, hacc[o]))));
+                  }
+                }
               }
             }
             if (p.store_y) {
@@ -511,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
           }
           if (p.store_y) stg = (stg + 1) % NSTG;
         }
-        if (kCanHead && do_head) {
+        if constexpr (kCanHead) {
           const int h = h0 + (m >> 3), w = w0 + (m & 7);
           if (h < p.H && w < p.W) {
 #pragma unroll
@@ -536,14 +572,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   }
 }
 
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM>
 int launch_v2(const ConvTcOp& op, cudaStream_t st) {
   using S = V2Smem<BN, MT, NBUF, NA, NB, NSTG>;
   static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG, BT>;
+  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG, BT, EM>;
   if (!attr_done[dev & 15]) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
@@ -735,16 +771,20 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
   MAU_INST(256, MODE_ROW3, 2, 3)
 #undef MAU_INST
   if (op.mode == MODE_HALO) {
+    const int em = op.p.head_out ? 3 : (op.p.scale ? 2 : (op.p.shift ? 1 : 0));
+    if (op.p.bt && em != 0) return fail("conv_tc: the MN-major weight path has no epilogue affine");
+    if (em == 3 && op.bn > 128) return fail("conv_tc: fused head needs BN <= 128");
 #define MAU_V2(BN_, MT_, NBUF_, NA_, NB_, NSTG_)                                                        \
-    if (op.bn == BN_ && op.mt == MT_ && op.nbuf == NBUF_)                                               \
-      return op.p.bt ? launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, true>(op, st)                        \
-                     : launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false>(op, st);
+    if (op.bn == BN_ && op.mt == MT_ && op.nbuf == NBUF_) {                                             \
+      if (op.p.bt) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, true, 0>(op, st);                 \
+      if (em == 0) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 0>(op, st);                \
+      if (em == 1) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 1>(op, st);                \
+      if (em == 2) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 2>(op, st);                \
+      if constexpr (BN_ <= 128) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 3>(op, st);   \
+    }
     MAU_V2(64, 4, 2, 2, 3, 1)
-    MAU_V2(64, 2, 2, 2, 4, 2)
     MAU_V2(128, 2, 2, 2, 4, 2)
-    MAU_V2(128, 1, 2, 2, 4, 2)
     MAU_V2(256, 1, 2, 2, 4, 1)
-    MAU_V2(256, 2, 1, 2, 3, 1)
 #undef MAU_V2
     return fail("conv_tc: no v2 kernel instance for BN=%d MT=%d NBUF=%d", op.bn, op.mt, op.nbuf);
   }

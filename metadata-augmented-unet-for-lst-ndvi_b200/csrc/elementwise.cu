@@ -350,11 +350,11 @@ __global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DVie
   const int ih_b = blockIdx.y * rows_per_strip;
   const int ih_e = min(gx.H, ih_b + rows_per_strip);
   const int ca = t.tx_off[iw], nc = t.tx_off[iw + 1] - ca;
-  long long off[kMaxE];
+  int off[kMaxE];                                // element offsets inside one gy row (W * cs < 2^31)
   float wx[kMaxE];
 #pragma unroll
   for (int e = 0; e < kMaxE; ++e) {
-    off[e] = (long long)(e < nc ? t.tx_idx[ca + e] : 0) * gy.cs;
+    off[e] = (e < nc ? t.tx_idx[ca + e] : 0) * gy.cs;
     wx[e] = e < nc ? t.tx_w[ca + e] : 0.f;
   }
   const T* gyb = static_cast<const T*>(gy.ptr) + (long long)b * gy.H * gy.W * gy.cs + gy.c0 + g * 8;
@@ -379,12 +379,23 @@ __global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DVie
     }
     V8<T>::store(gxb + row * gxrow, o);
   };
-  for (int oh = oh_first; oh <= oh_last; ++oh) {
-    Raw rv[kMaxE];
-    const T* rowp = gyb + oh * gyrow;
+  Raw nx[kMaxE];                                 // gy vectors of the NEXT output row, requested one row ahead
+  {
+    const T* rowp = gyb + oh_first * gyrow;
 #pragma unroll
     for (int c = 0; c < kMaxE; ++c)
-      if (c < nc) rv[c] = V8<T>::load_raw(rowp + off[c]);
+      if (c < nc) nx[c] = V8<T>::load_raw(rowp + off[c]);
+  }
+  for (int oh = oh_first; oh <= oh_last; ++oh) {
+    Raw rv[kMaxE];
+#pragma unroll
+    for (int c = 0; c < kMaxE; ++c) rv[c] = nx[c];
+    if (oh < oh_last) {
+      const T* rowp = gyb + (oh + 1) * gyrow;
+#pragma unroll
+      for (int c = 0; c < kMaxE; ++c)
+        if (c < nc) nx[c] = V8<T>::load_raw(rowp + off[c]);
+    }
     int y0, y1; float ly;
     src_index(sy, oh, gx.H, y0, y1, ly);         // block-uniform
     while (y0 > r && r < ih_e) {                 // input row r is complete

@@ -143,6 +143,71 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(DView z, const float
   }
 }
 
+// training forward, one launch: every thread derives mean / rstd / scale / shift of its 8 channels from the
+// (already all-reduced, if SyncBN) double sums; block 0 also writes the saved statistics for the backward and
+// performs the running-stat update (momentum, unbiased variance) -- then the normalise + ReLU pass.
+template <typename T>
+__global__ void __launch_bounds__(256) bn_finalize_apply_relu_kernel(DView z, const double* __restrict__ sums, long long count,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float eps, float momentum,
+                                                                     float* __restrict__ rm, float* __restrict__ rv,
+                                                                     float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                     DView y) {
+  using Raw = typename V8<T>::Raw;
+  const int C = z.C;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const double n = (double)count;
+      const double mean = sums[c] / n;
+      double var = sums[C + c] / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float sc = gamma[c] * rstd;
+      scale_out[c] = sc;
+      shift_out[c] = beta[c] - (float)mean * sc;
+      mean_out[c] = (float)mean;
+      rstd_out[c] = rstd;
+      const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
+      rm[c] = (1.f - momentum) * rm[c] + momentum * (float)mean;
+      rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+    }
+  }
+  const int G = C / 8;
+  const int L = 256 / G;
+  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
+  if (pl >= L) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {       // same arithmetic as block 0 above, so every block uses identical coefficients
+    const int c = gi * 8 + k;
+    const double n = (double)count;
+    const double mean = sums[c] / n;
+    double var = sums[C + c] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sc[k] = gamma[c] * rstd;
+    sh[k] = beta[c] - (float)mean * sc[k];
+  }
+  const long long npix = (long long)z.B * z.H * z.W;
+  const long long stride = (long long)gridDim.x * L;
+  for (long long p = (long long)blockIdx.x * L + pl; p < npix; p += kU * stride) {
+    Raw r[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (p + u * stride < npix) r[u] = V8<T>::load_raw(at<T>(z, p + u * stride, gi * 8));
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (p + u * stride < npix) {
+        float v[8];
+        V8<T>::unpack(r[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+        V8<T>::store(at<T>(y, p + u * stride, gi * 8), v);
+      }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView z, const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
@@ -165,6 +230,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView z, c
   });
 }
 
+// dz = gamma*rstd*(g~ - mean(g~) - xhat*mean(g~*xhat)).  Pure element-wise pass (kU pixels in flight per thread;
+// dz may alias z: a thread only ever touches its own pixels).  The gradient of the convolution bias, sum(dz), is
+// identically zero under batch-statistics BatchNorm (the mean subtraction removes any constant), so it is not
+// reduced here: the reference's value is fp32 rounding noise around 0, ours is exactly 0.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView z, const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
@@ -172,12 +241,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView z, co
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ rstd,
                                                            const double* __restrict__ sums, long long count, DView dz,
-                                                           double* dbias_sums) {
-  const long long npix = (long long)z.B * z.H * z.W;
+                                                           const double* __restrict__ param_sums, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, float* __restrict__ dbias) {
+  using Raw = typename V8<T>::Raw;
   const float inv_n = 1.f / (float)count;
   const int C = z.C;
-  const int gi8 = (threadIdx.x % (C / 8)) * 8;
-  // per-channel coefficients hoisted out of the pixel loop (dz may alias z, so the compiler cannot do it)
+  if (blockIdx.x == 0 && param_sums) {      // dbeta = sum g~, dgamma = sum g~*xhat (this rank's sums), dbias = 0
+    for (int c = threadIdx.x; c < C; c += 256) {
+      if (dbeta) dbeta[c] = (float)param_sums[c];
+      if (dgamma) dgamma[c] = (float)param_sums[C + c];
+      if (dbias) dbias[c] = 0.f;
+    }
+  }
+  const int G = C / 8;
+  const int L = 256 / G;
+  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
+  if (pl >= L) return;
+  const int gi8 = gi * 8;
   float ca[8], cm[8], cr[8], m1[8], m2[8], sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -185,19 +265,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView z, co
     cr[k] = rstd[gi8 + k]; cm[k] = mean[gi8 + k]; ca[k] = gamma[gi8 + k] * cr[k];
     m1[k] = (float)sums[gi8 + k] * inv_n; m2[k] = (float)sums[C + gi8 + k] * inv_n;
   }
-  // all kU pixels of a batch are loaded before the first is stored (dz may alias z: each thread only ever
-  // touches its own pixels, so batching is safe)
-  channel_reduce<T, 1, 2>(gy, z, npix, dbias_sums, [&](long long p, int c, const float (&g)[8], const float (&zz)[8], float (&acc)[1][8]) {
-    float o[8];
+  const long long npix = (long long)z.B * z.H * z.W;
+  const long long stride = (long long)gridDim.x * L;
+  for (long long p = (long long)blockIdx.x * L + pl; p < npix; p += kU * stride) {
+    Raw rg[kU], rz[kU];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gt = fmaf(zz[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
-      const float xh = (zz[k] - cm[k]) * cr[k];
-      o[k] = ca[k] * (gt - m1[k] - xh * m2[k]);
-      acc[0][k] += V8<T>::round(o[k]);
-    }
-    V8<T>::store(at<T>(dz, p, c), o);
-  });
+    for (int u = 0; u < kU; ++u)
+      if (p + u * stride < npix) {
+        rg[u] = V8<T>::load_raw(at<T>(gy, p + u * stride, gi8));
+        rz[u] = V8<T>::load_raw(at<T>(z, p + u * stride, gi8));
+      }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (p + u * stride < npix) {
+        float g[8], zz[8], o[8];
+        V8<T>::unpack(rg[u], g);
+        V8<T>::unpack(rz[u], zz);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float gt = fmaf(zz[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+          const float xh = (zz[k] - cm[k]) * cr[k];
+          o[k] = ca[k] * (gt - m1[k] - xh * m2[k]);
+        }
+        V8<T>::store(at<T>(dz, p + u * stride, gi8), o);
+      }
+  }
 }
 
 __global__ void bn_bwd_finalize_kernel(const double* sums, const double* dbias_sums, int C, float* dgamma,
@@ -206,7 +298,7 @@ __global__ void bn_bwd_finalize_kernel(const double* sums, const double* dbias_s
   if (c >= C) return;
   if (dbeta) dbeta[c] = (float)sums[c];
   if (dgamma) dgamma[c] = (float)sums[C + c];
-  if (dbias) dbias[c] = (float)dbias_sums[c];
+  if (dbias) dbias[c] = dbias_sums ? (float)dbias_sums[c] : 0.f;
 }
 
 __global__ void bump_counters_kernel(long long* const* counters, int n) {
@@ -263,6 +355,24 @@ int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shi
   MAU_LAUNCHED();
   return 0;
 }
+int op_bn_finalize_apply_relu(int dt, const View& z, const double* sums, long long count, const float* gamma,
+                              const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                              float* scale, float* shift, float* save_mean, float* save_rstd, const View& y,
+                              cudaStream_t st) {
+  if (!vec_ok(z) || !vec_ok(y) || z.C != y.C || z.pixels() != y.pixels()) return fail("bn_finalize_apply: bad views");
+  const int L = std::max(1, 256 / (z.C / 8));
+  long long b = (z.pixels() + (long long)L * kU - 1) / ((long long)L * kU);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  if (dt == DT_BF16)
+    bn_finalize_apply_relu_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(z), sums, count, gamma, beta, eps, momentum, running_mean,
+                                                                       running_var, scale, shift, save_mean, save_rstd, dv(y));
+  else
+    bn_finalize_apply_relu_kernel<float><<<(int)b, 256, 0, st>>>(dv(z), sums, count, gamma, beta, eps, momentum, running_mean,
+                                                               running_var, scale, shift, save_mean, save_rstd, dv(y));
+  MAU_LAUNCHED();
+  return 0;
+}
 int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* mean,
                      const float* rstd, double* sums, cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(gy)) return fail("bn_bwd_reduce: bad views");
@@ -275,14 +385,16 @@ int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, 
 }
 int op_bn_bwd_apply(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* gamma,
                     const float* mean, const float* rstd, const double* sums, long long count, const View& dz_out,
-                    double* dbias_sums, cudaStream_t st) {
+                    const double* param_sums, float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(dz_out)) return fail("bn_bwd_apply: bad views");
-  const size_t smem = 256 * 8 * sizeof(float);
-  const int blocks = reduce_blocks(z.pixels(), z.C);
+  const int L = std::max(1, 256 / (z.C / 8));
+  long long b = (z.pixels() + (long long)L * kU - 1) / ((long long)L * kU);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
   if (dt == DT_BF16)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(gy), dv(z), scale, shift, gamma, mean, rstd, sums, count, dv(dz_out), param_sums, dgamma, dbeta, dbias);
   else
-    bn_bwd_apply_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, gamma, mean, rstd, sums, count, dv(dz_out), dbias_sums);
+    bn_bwd_apply_kernel<float><<<(int)b, 256, 0, st>>>(dv(gy), dv(z), scale, shift, gamma, mean, rstd, sums, count, dv(dz_out), param_sums, dgamma, dbeta, dbias);
   MAU_LAUNCHED();
   return 0;
 }

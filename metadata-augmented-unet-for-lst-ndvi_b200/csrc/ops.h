@@ -64,6 +64,11 @@ int op_bn_stats(int dt, const View& z, double* sums, cudaStream_t st);
 int op_bn_finalize_train(const double* sums, long long count, const float* gamma, const float* beta, int C,
                          float eps, float momentum, float* running_mean, float* running_var, float* scale,
                          float* shift, float* save_mean, float* save_rstd, cudaStream_t st);
+// op_bn_finalize_train + op_bn_apply_relu in one launch (every block derives the coefficients of its channels)
+int op_bn_finalize_apply_relu(int dt, const View& z, const double* sums, long long count, const float* gamma,
+                              const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                              float* scale, float* shift, float* save_mean, float* save_rstd, const View& y,
+                              cudaStream_t st);
 // y = relu(z * scale + shift) into a (slice) view
 int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shift, const View& y,
                      cudaStream_t st);
@@ -71,11 +76,13 @@ int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shi
 // recomputed from z with the forward's scale / shift, so y is not read
 int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* mean,
                      const float* rstd, double* sums, cudaStream_t st);
-// backward, pass 2: dz = gamma*rstd*(g~ - s1/n - xhat*s2/n) written over dz_out (may alias z);
-// also dgamma = s2, dbeta = s1 and dbias_sums += sum dz (double, zeroed by the caller)
+// backward, pass 2: dz = gamma*rstd*(g~ - s1/n - xhat*s2/n) written over dz_out (may alias z).  sum(dz), the
+// gradient of the convolution bias, is identically zero under batch statistics and is not reduced.
+// block 0 also writes dgamma = param_sums[C..2C), dbeta = param_sums[0..C), dbias = 0 when param_sums != nullptr
 int op_bn_bwd_apply(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* gamma,
                     const float* mean, const float* rstd, const double* sums, long long count, const View& dz_out,
-                    double* dbias_sums, cudaStream_t st);
+                    const double* param_sums, float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
+// dgamma = s2, dbeta = s1, dbias = dbias_sums (nullptr -> 0)
 int op_bn_bwd_finalize(const double* sums, const double* dbias_sums, int C, float* dgamma, float* dbeta,
                        float* dbias, cudaStream_t st);
 int op_bump_counters(long long* const* counters_dev, int n, cudaStream_t st);

@@ -217,12 +217,13 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
     }
     if (training) {
       const View z = whole(L->zbuf);
+      // (statistics fused into the conv epilogue were measured and dropped: the column-sum pass over the staged
+      //  tile lengthens the epilogue of the narrow layers by more than this separate 63 %-of-HBM-peak pass costs)
       MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
       MAU_TRY(op_bn_stats(dt, z, L->sums, c.st));
       if (sync_fn) sync_fn(sync_user, L->sums, 2 * C);       // SyncBN: sum / sum-of-squares over all ranks
-      MAU_TRY(op_bn_finalize_train(L->sums, count * sync_world, c.f(L->igamma), c.f(L->ibeta), C, kBnEps, kBnMomentum,
-                                   c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, c.st));
-      MAU_TRY(op_bn_apply_relu(dt, z, L->scale, L->shift, view(L->out), c.st));
+      MAU_TRY(op_bn_finalize_apply_relu(dt, z, L->sums, count * sync_world, c.f(L->igamma), c.f(L->ibeta), kBnEps, kBnMomentum,
+                                        c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, view(L->out), c.st));
     }
     return 0;
   };
@@ -287,7 +288,6 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
   op.grad_first = L->iw; op.grad_last = L->ibeta;
   op.run = [this, L, gy, y, z, count, C](Ctx& c) -> int {
     MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
-    MAU_CUDA(cudaMemsetAsync(L->dbsum, 0, sizeof(double) * C, c.st));
     MAU_TRY(op_bn_bwd_reduce(dt, gy, z, L->scale, L->shift, L->mean, L->rstd, L->sums, c.st));
     const double* param_sums = L->sums;
     if (sync_fn) {
@@ -298,8 +298,7 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
       param_sums = L->sums_local;
     }
     MAU_TRY(op_bn_bwd_apply(dt, gy, z, L->scale, L->shift, c.f(L->igamma), L->mean, L->rstd, L->sums,
-                            count * sync_world, z, L->dbsum, c.st));
-    MAU_TRY(op_bn_bwd_finalize(param_sums, L->dbsum, C, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
+                            count * sync_world, z, param_sums, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
     float* dw = c.g(L->iw);
     int ci_w0 = 0;
     const bool ws_path = use_tc && wgrad_ws != nullptr;      // v2 wgrad: reduce into the workspace, then transpose

@@ -384,21 +384,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_tc_v2_kernel(const __gri
 }
 
 // workspace [9][D1][ld0] -> OIHW.  normal: D1 = Cout, inner = ci; swapped: D1 = Cin, inner = co.
-__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, int swap, int Cout, int Cin, int ld0,
-                                      float* __restrict__ dw) {
+// A block owns 256 consecutive (co, ci) pairs of the OIHW tensor: nine coalesced plane reads into shared memory,
+// then one contiguous 256 x 9 float run written out (the direct version wrote 36-byte pieces per thread).
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ ws, int swap, int Cout, int Cin,
+                                                             int ld0, float* __restrict__ dw) {
+  __shared__ float tile[256 * 9 + 8];
   const long long total = (long long)Cout * Cin;
   const long long plane = (long long)(swap ? Cin : Cout) * ld0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int co, ci;
-    long long src;
-    if (!swap) { ci = (int)(i % Cin); co = (int)(i / Cin); src = (long long)co * ld0 + ci; }
-    else       { co = (int)(i % Cout); ci = (int)(i / Cout); src = (long long)ci * ld0 + co; }
-    float v[9];
+  for (long long base = (long long)blockIdx.x * 256; base < total; base += (long long)gridDim.x * 256) {
+    const long long i = base + threadIdx.x;
+    if (i < total) {
+      long long src;
+      if (!swap) { const int ci = (int)(i % Cin), co = (int)(i / Cin); src = (long long)co * ld0 + ci; }
+      else       { const int ci = (int)(i % Cin), co = (int)(i / Cin); src = (long long)ci * ld0 + co; }
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = ws[t * plane + src];
-    float* dst = dw + ((long long)co * Cin + ci) * 9;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) dst[t] = v[t];
+      for (int t = 0; t < 9; ++t) tile[threadIdx.x * 9 + t] = ws[t * plane + src];
+    }
+    __syncthreads();
+    const long long n = (total - base < 256 ? total - base : 256) * 9;
+    float* dst = dw + base * 9;
+    for (int e = threadIdx.x; e < n; e += 256) dst[e] = tile[e];
+    __syncthreads();
   }
 }
 
@@ -510,7 +516,7 @@ int wgrad_tc_launch(const WgradTcOp& op, float* dw_oihw, cudaStream_t st) {
 int wgrad_tc_finalize(const float* ws, int swap, int Cout, int Cin_w, float* dw_oihw, cudaStream_t st) {
   const int d0 = swap ? Cout : Cin_w;
   const long long total = (long long)Cout * Cin_w;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, swap, Cout, Cin_w, round_up(d0, 4), dw_oihw);
   MAU_LAUNCHED();
   return 0;
