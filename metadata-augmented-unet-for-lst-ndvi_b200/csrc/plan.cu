@@ -23,6 +23,7 @@ void Plan::kend(const Ctx& c) {
 }
 
 Plan::~Plan() {
+  if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
   if (!dry) {
     for (void* p : allocs) cudaFree(p);
   }
@@ -375,7 +376,29 @@ int Plan::make_bilinear(int Hin, int Win, int Hout, int Wout, BilinearTables* t)
 }
 
 // ------------------------------------------------------------------------------------------ encoders
-int Plan::build_encoders(int lstm0, int fc0, int mlp0, const TRef* t_dst, int n_t, const TRef* m_dst, int n_m) {
+// The LSTM is 828 strictly sequential steps (~0.6 ms forward, ~1.5 ms BPTT) on a handful of SMs.  It runs on a
+// plan-owned side stream: forward, it is launched first and joined right before the first consumer of the
+// embedding (the bottleneck of the U-Net, node x0_1 of the U-Net++), so it overlaps the encoder convolutions;
+// backward, the embedding gradient is complete right after that consumer's backward, the BPTT then overlaps the
+// encoder convolutions' backward and is joined at the end of the pass (where its gradients are reported ready).
+int Plan::side_fork(Ctx& c) {
+  if (!side) {
+    MAU_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    MAU_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    MAU_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  MAU_CUDA(cudaEventRecord(ev_fork, c.st));
+  MAU_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  return 0;
+}
+int Plan::side_join(Ctx& c) {
+  if (!side || !side_pending) return 0;
+  MAU_CUDA(cudaStreamWaitEvent(c.st, ev_join, 0));
+  side_pending = false;
+  return 0;
+}
+
+int Plan::build_encoders(int lstm0, int fc0, int mlp0) {
   const bool te = cfg.temporal_embeddings != 0, me = cfg.metadata_embeddings != 0;
   if (!te && !me) return 0;
   const int B = cfg.batch, Hd = cfg.lstm_dim, td = cfg.temporal_dim, md = cfg.meta_dim, T = cfg.seq_len;
@@ -389,29 +412,58 @@ int Plan::build_encoders(int lstm0, int fc0, int mlp0, const TRef* t_dst, int n_
   if (te && cfg.training) lstm_save = static_cast<float*>(alloc(sizeof(float) * lstm_save_floats(B, T, Hd)));
   if (te) fwd_flops += B * (2.0 * 4 * Hd * (Hd + 1) * T + 2.0 * Hd * td);
   if (me) fwd_flops += B * (2.0 * cfg.meta_features * 32 + 2.0 * 32 * md);
+  enc_lstm0 = lstm0; enc_fc0 = fc0; enc_mlp0 = mlp0;
   if (dry) return 0;
   if (te && T < 1) return fail("temporal embeddings enabled but temp_series is empty");
   const int Bt = shared ? 1 : B;                 // shared sweep: one LSTM run, row 0 broadcast to every tile
+  Op op;
+  op.name = "encoders";                          // launch only: the work runs on the side stream
+  op.run = [=](Ctx& c) -> int {
+    if (te && !c.series) return fail("temp_series is required when temporal embeddings are enabled");
+    if (me && !c.md) return fail("metadata is required when metadata embeddings are enabled");
+    MAU_TRY(side_fork(c));
+    if (te) {
+      MAU_TRY(op_lstm_fwd(c.series, Bt, T, Hd, c.f(lstm0), c.f(lstm0 + 1), c.f(lstm0 + 2), c.f(lstm0 + 3), hlast,
+                          lstm_save, side));
+      MAU_TRY(op_linear_fwd(hlast, Bt, Hd, c.f(fc0), c.f(fc0 + 1), td, emb + t_off, emb_dim, side));
+    }
+    if (me)
+      MAU_TRY(op_mlp_fwd(c.md, B, cfg.meta_features, c.f(mlp0), c.f(mlp0 + 1), c.f(mlp0 + 2), c.f(mlp0 + 3), md,
+                         hidden, emb + m_off, emb_dim, side));
+    MAU_CUDA(cudaEventRecord(ev_join, side));
+    side_pending = true;
+    return 0;
+  };
+  fwd.push_back(op);
+  if (cfg.training)
+    bwd_makers.push_back([=]() -> int {          // runs LAST in backward: join the side stream, gradients are final
+      Op b;
+      b.name = "encoders.bwd.join";
+      b.grad_first = std::min(lstm0, mlp0); b.grad_last = std::max(fc0 + 1, mlp0 + 3);
+      b.run = [=](Ctx& c) -> int { return side_join(c); };
+      bwd.push_back(b);
+      return 0;
+    });
+  return 0;
+}
+
+// placed right before the first consumer of the embedding slices
+int Plan::build_embed_broadcast(const TRef* t_dst, int n_t, const TRef* m_dst, int n_m) {
+  const bool te = cfg.temporal_embeddings != 0, me = cfg.metadata_embeddings != 0;
+  if ((!te && !me) || dry) return 0;
+  const int B = cfg.batch, Hd = cfg.lstm_dim, td = cfg.temporal_dim, md = cfg.meta_dim, T = cfg.seq_len;
+  const int t_off = 0, m_off = te ? td : 0;
   const int t_stride = shared ? 0 : emb_dim;
+  const int lstm0 = enc_lstm0, fc0 = enc_fc0, mlp0 = enc_mlp0;
   std::vector<View> tv, mv;
   for (int i = 0; i < n_t; ++i) tv.push_back(view(t_dst[i]));
   for (int i = 0; i < n_m; ++i) mv.push_back(view(m_dst[i]));
   Op op;
-  op.name = "encoders";
+  op.name = "emb.bcast";
   op.run = [=](Ctx& c) -> int {
-    if (te) {
-      if (!c.series) return fail("temp_series is required when temporal embeddings are enabled");
-      MAU_TRY(op_lstm_fwd(c.series, Bt, T, Hd, c.f(lstm0), c.f(lstm0 + 1), c.f(lstm0 + 2), c.f(lstm0 + 3), hlast,
-                          lstm_save, c.st));
-      MAU_TRY(op_linear_fwd(hlast, Bt, Hd, c.f(fc0), c.f(fc0 + 1), td, emb + t_off, emb_dim, c.st));
-      for (const View& v : tv) MAU_TRY(op_embed_broadcast(dt, emb + t_off, t_stride, v, c.st));
-    }
-    if (me) {
-      if (!c.md) return fail("metadata is required when metadata embeddings are enabled");
-      MAU_TRY(op_mlp_fwd(c.md, B, cfg.meta_features, c.f(mlp0), c.f(mlp0 + 1), c.f(mlp0 + 2), c.f(mlp0 + 3), md,
-                         hidden, emb + m_off, emb_dim, c.st));
-      for (const View& v : mv) MAU_TRY(op_embed_broadcast(dt, emb + m_off, emb_dim, v, c.st));
-    }
+    MAU_TRY(side_join(c));
+    if (te) for (const View& v : tv) MAU_TRY(op_embed_broadcast(dt, emb + t_off, t_stride, v, c.st));
+    if (me) for (const View& v : mv) MAU_TRY(op_embed_broadcast(dt, emb + m_off, emb_dim, v, c.st));
     return 0;
   };
   fwd.push_back(op);
@@ -422,30 +474,30 @@ int Plan::build_encoders(int lstm0, int fc0, int mlp0, const TRef* t_dst, int n_
       for (const TRef& t : tr) { View g; MAU_TRY(gview(t, &g)); gt.push_back(g); }
       for (const TRef& t : mr) { View g; MAU_TRY(gview(t, &g)); gm.push_back(g); }
       Op b;
-      b.name = "encoders.bwd";
-      b.grad_first = std::min(lstm0, mlp0); b.grad_last = std::max(fc0 + 1, mlp0 + 3);
+      b.name = "emb.bwd";                        // reduce on the main stream, encoder backward on the side stream
       b.run = [=](Ctx& c) -> int {
         MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * B * emb_dim, c.st));
+        if (te) for (const View& g : gt) MAU_TRY(op_embed_reduce(dt, g, demb + t_off, emb_dim, 1, c.st));
+        if (me) for (const View& g : gm) MAU_TRY(op_embed_reduce(dt, g, demb + m_off, emb_dim, 1, c.st));
+        MAU_TRY(side_fork(c));
         if (te) {
-          for (const View& g : gt) MAU_TRY(op_embed_reduce(dt, g, demb + t_off, emb_dim, 1, c.st));
           if (c.g(fc0))
             MAU_TRY(op_linear_bwd(hlast, B, Hd, c.f(fc0), td, demb + t_off, emb_dim, dhlast, c.g(fc0),
-                                  c.g(fc0 + 1), c.st));
+                                  c.g(fc0 + 1), side));
           if (c.g(lstm0)) {
-            MAU_CUDA(cudaMemsetAsync(c.g(lstm0), 0, sizeof(float) * 4 * Hd, c.st));
-            MAU_CUDA(cudaMemsetAsync(c.g(lstm0 + 1), 0, sizeof(float) * 4 * Hd * Hd, c.st));
-            MAU_CUDA(cudaMemsetAsync(c.g(lstm0 + 2), 0, sizeof(float) * 4 * Hd, c.st));
-            MAU_CUDA(cudaMemsetAsync(c.g(lstm0 + 3), 0, sizeof(float) * 4 * Hd, c.st));
+            MAU_CUDA(cudaMemsetAsync(c.g(lstm0), 0, sizeof(float) * 4 * Hd, side));
+            MAU_CUDA(cudaMemsetAsync(c.g(lstm0 + 1), 0, sizeof(float) * 4 * Hd * Hd, side));
+            MAU_CUDA(cudaMemsetAsync(c.g(lstm0 + 2), 0, sizeof(float) * 4 * Hd, side));
+            MAU_CUDA(cudaMemsetAsync(c.g(lstm0 + 3), 0, sizeof(float) * 4 * Hd, side));
             MAU_TRY(op_lstm_bwd(c.series, B, T, Hd, c.f(lstm0 + 1), lstm_save, dhlast, c.g(lstm0), c.g(lstm0 + 1),
-                                c.g(lstm0 + 2), c.g(lstm0 + 3), nullptr, c.st));
+                                c.g(lstm0 + 2), c.g(lstm0 + 3), nullptr, side));
           }
         }
-        if (me) {
-          for (const View& g : gm) MAU_TRY(op_embed_reduce(dt, g, demb + m_off, emb_dim, 1, c.st));
-          if (c.g(mlp0))
-            MAU_TRY(op_mlp_bwd(c.md, B, cfg.meta_features, c.f(mlp0), c.f(mlp0 + 2), md, hidden, demb + m_off,
-                               emb_dim, c.g(mlp0), c.g(mlp0 + 1), c.g(mlp0 + 2), c.g(mlp0 + 3), c.st));
-        }
+        if (me && c.g(mlp0))
+          MAU_TRY(op_mlp_bwd(c.md, B, cfg.meta_features, c.f(mlp0), c.f(mlp0 + 2), md, hidden, demb + m_off,
+                             emb_dim, c.g(mlp0), c.g(mlp0 + 1), c.g(mlp0 + 2), c.g(mlp0 + 3), side));
+        MAU_CUDA(cudaEventRecord(ev_join, side));
+        side_pending = true;
         return 0;
       };
       bwd.push_back(b);
@@ -494,8 +546,7 @@ int Plan::build_unet() {
 
   // encoders -> bottleneck slices (temporal first, then metadata: src/model.py:248-259)
   {
-    TRef tdst{bott, F[3], cfg.temporal_dim}, mdst{bott, F[3] + (te ? cfg.temporal_dim : 0), cfg.meta_dim};
-    MAU_TRY(build_encoders(lstm0, fc0, mlp0, &tdst, te ? 1 : 0, &mdst, me ? 1 : 0));
+    MAU_TRY(build_encoders(lstm0, fc0, mlp0));
   }
   // maps -> NHWC
   if (!dry) {
@@ -592,6 +643,8 @@ int Plan::build_unet() {
     MAU_TRY(add_pool(TRef{cat[3], 0, F[3]}, TRef{bott, 0, F[3]}));
   }
   {
+    TRef tdst{bott, F[3], cfg.temporal_dim}, mdst{bott, F[3] + (te ? cfg.temporal_dim : 0), cfg.meta_dim};
+    MAU_TRY(build_embed_broadcast(&tdst, te ? 1 : 0, &mdst, me ? 1 : 0));     // joins the side stream
     const int cin = F[3] + E;
     MAU_TRY(add_vgg("conv4_0", enc[4], bott, 1, &zero, &cin, F[4], TRef{x4, 0, F[4]}, true, nullptr));
   }
@@ -691,14 +744,12 @@ int Plan::build_unetpp() {
   auto upref = [&](int l, int j) -> TRef { return TRef{lv[l], nn[l] * F[l] + (j - 1) * F[l + 1], F[l + 1]}; };
   auto embref = [&](int l) -> TRef { return TRef{lv[l], nn[l] * F[l] + nn[l] * F[l + 1], E}; };
 
-  {
-    TRef tdst[4], mdst[4];
-    for (int l = 0; l < 4; ++l) {
-      tdst[l] = TRef{lv[l], embref(l).c0, cfg.temporal_dim};
-      mdst[l] = TRef{lv[l], embref(l).c0 + cfg.temporal_dim, cfg.meta_dim};
-    }
-    MAU_TRY(build_encoders(lstm0, fc0, mlp0, tdst, 4, mdst, 4));
+  TRef tdst[4], mdst[4];
+  for (int l = 0; l < 4; ++l) {
+    tdst[l] = TRef{lv[l], embref(l).c0, cfg.temporal_dim};
+    mdst[l] = TRef{lv[l], embref(l).c0 + cfg.temporal_dim, cfg.meta_dim};
   }
+  MAU_TRY(build_encoders(lstm0, fc0, mlp0));
   if (!dry) {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
@@ -777,7 +828,9 @@ int Plan::build_unetpp() {
                    true, (l == 0 && j == 4) ? &last_block : nullptr);
   };
   // reference evaluation order, src/model.py:129-177
-  MAU_TRY(encoder(0)); MAU_TRY(encoder(1)); MAU_TRY(node(0, 1));
+  MAU_TRY(encoder(0)); MAU_TRY(encoder(1));
+  MAU_TRY(build_embed_broadcast(tdst, 4, mdst, 4));       // first consumer of the embeddings is x0_1: join here
+  MAU_TRY(node(0, 1));
   MAU_TRY(encoder(2)); MAU_TRY(node(1, 1)); MAU_TRY(node(0, 2));
   MAU_TRY(encoder(3)); MAU_TRY(node(2, 1)); MAU_TRY(node(1, 2)); MAU_TRY(node(0, 3));
   MAU_TRY(encoder(4)); MAU_TRY(node(3, 1)); MAU_TRY(node(2, 2)); MAU_TRY(node(1, 3)); MAU_TRY(node(0, 4));
@@ -926,6 +979,7 @@ static int run_ops(Plan* P, std::vector<Op>& ops, Ctx& c, bool backward) {
 int Plan::run_forward(Ctx& c) {
   skip_pack = !cfg.training && state_version != 0 && state_version == packed_version && packed_state == last_state;
   MAU_TRY(run_ops(this, fwd, c, false));
+  MAU_TRY(side_join(c));
   if (!cfg.training) { packed_version = state_version; packed_state = last_state; }
   if (cfg.training && !counters_host.empty()) {
     std::vector<long long*> ptrs;
@@ -942,6 +996,7 @@ int Plan::run_backward(Ctx& c) {
   if (!cfg.training) return fail("backward requires a training-mode plan");
   if (!forward_done) return fail("backward called before forward");
   MAU_TRY(run_ops(this, bwd, c, true));
+  MAU_TRY(side_join(c));
   forward_done = false;
   return 0;
 }

@@ -140,7 +140,12 @@ class Plan {
   int make_bilinear(int Hin, int Win, int Hout, int Wout, BilinearTables* t);
   int build_unet();
   int build_unetpp();
-  int build_encoders(int lstm0, int fc0, int mlp0, const TRef* t_dst, int n_t, const TRef* m_dst, int n_m);
+  int build_encoders(int lstm0, int fc0, int mlp0);                                   // launch on the side stream
+  int build_embed_broadcast(const TRef* t_dst, int n_t, const TRef* m_dst, int n_m);  // join + broadcast into the slices
+  int side_fork(Ctx& c);
+  int side_join(Ctx& c);
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool side_pending = false;
+  int enc_lstm0 = -1, enc_fc0 = -1, enc_mlp0 = -1;
   std::vector<std::function<int()>> bwd_makers;   // run in reverse to emit backward ops
   // encoder scratch
   float* emb = nullptr; float* demb = nullptr; float* hidden = nullptr; float* hlast = nullptr;

@@ -1,6 +1,5 @@
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest_gpu13.log 2>&1; echo pytest rc=$?; tail -3 $O/pytest_gpu13.log
-for c in 2 3; do
-  timeout 600 python bench.py --config $c --steps 20 --warmup 5 --no-cpu-baseline --profile-layers > $O/bench_c${c}_v15.json 2> $O/layers_c${c}_v15.txt; echo config $c rc=$?; cut -c1-330 $O/bench_c${c}_v15.json
+timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest_gpu14.log 2>&1; echo pytest rc=$?; tail -3 $O/pytest_gpu14.log
+for c in 4 5 3; do
+  timeout 600 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_c${c}_v17.json 2> /dev/null; echo config $c rc=$?; cut -c1-230 $O/bench_c${c}_v17.json
 done
-grep "k:" $O/layers_c2_v15.txt | awk '{a+=$2; print} END {print a}'
