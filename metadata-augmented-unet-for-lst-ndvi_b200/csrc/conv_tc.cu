@@ -273,7 +273,10 @@ struct V2Smem {
 
 // EM = epilogue mode: 0 none (data gradient), 1 + shift (training forward: bias), 2 * scale + shift (eval: folded
 // BatchNorm), 3 = 2 + fused 1x1 head.  A template parameter so that every instance carries one epilogue only.
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM>
+// BRES = weights resident: when the whole packed weight tensor of the launch (9 taps x K chunks, one N tile) fits the
+// NB B stages it is loaded once per CTA instead of once per work item (the Cin <= 64, Cout <= 64 layers at 250x250:
+// 72 KB of weights against 46 KB of activations per item).
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM, bool BRES>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmY,
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
           __syncwarp();
           ra.advance(NA);
           for (int tap = 0; tap < 9; ++tap) {
+            if (BRES && it != (int)blockIdx.x) break;      // resident weights: loaded with the first item only
             mbar_wait(&emptyB[rb.stage], rb.phase ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&fullB[rb.stage], S::B_STAGE);
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int r = tap / 3, s = tap - r * 3;
-          mbar_wait(&fullB[rb.stage], rb.phase);
+          if (!BRES || it == (int)blockIdx.x) mbar_wait(&fullB[rb.stage], rb.phase);
           tc_fence_after();
           const uint64_t db = descB0 + (uint64_t)(smem_u32(sB + rb.stage * S::B_STAGE) >> 4);
           const uint64_t da = descA0 + (uint64_t)((a_stage + (r * 10 + s) * 128) >> 4);
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
                             idesc, k ? 1u : first);
               }
             }
-            umma_commit(&emptyB[rb.stage]);
+            if (!BRES) umma_commit(&emptyB[rb.stage]);
             if (tap == 8) umma_commit(&emptyA[ra.stage]);
             if (tap == 8 && chunk == total_chunks - 1) umma_commit(&tmem_full[buf]);
           }
@@ -572,14 +576,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   }
 }
 
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM, bool BRES = false>
 int launch_v2(const ConvTcOp& op, cudaStream_t st) {
   using S = V2Smem<BN, MT, NBUF, NA, NB, NSTG>;
   static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG, BT, EM>;
+  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES>;
   if (!attr_done[dev & 15]) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
@@ -710,6 +714,10 @@ static int prepare_impl(ConvTcOp* op, const View& xbuf, int nseg, const int* seg
       if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) { op->bn = a; op->mt = b; op->nbuf = c; }
     }
   }
+  op->bres = 0;
+  if (mode == MODE_HALO && op->bn == 64 && y.C <= 64 && Kp == 64 && !getenv("MAU_CONV_CFG") && !getenv("MAU_NO_BRES")) {
+    op->bres = 1; op->mt = 2; op->nbuf = 2;
+  }
   p.TW = (mode == MODE_TAP) ? 16 : 8;
   p.TH = 128 / p.TW;
   p.tiles_w = ceil_div(y.W, p.TW);
@@ -781,6 +789,13 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
       if (em == 1) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 1>(op, st);                \
       if (em == 2) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 2>(op, st);                \
       if constexpr (BN_ <= 128) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 3>(op, st);   \
+    }
+    if (op.bres) {          // 64-wide, K = 64: weights resident in 9 B stages, MT = 2
+      if (op.p.bt) return launch_v2<64, 2, 2, 2, 9, 2, true, 0, true>(op, st);
+      if (em == 0) return launch_v2<64, 2, 2, 2, 9, 2, false, 0, true>(op, st);
+      if (em == 1) return launch_v2<64, 2, 2, 2, 9, 2, false, 1, true>(op, st);
+      if (em == 2) return launch_v2<64, 2, 2, 2, 9, 2, false, 2, true>(op, st);
+      return launch_v2<64, 2, 2, 2, 9, 2, false, 3, true>(op, st);
     }
     MAU_V2(64, 4, 2, 2, 3, 1)
     MAU_V2(128, 2, 2, 2, 4, 2)
