@@ -45,35 +45,49 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons during the timed region (pynvml == nvidia-smi's source)."""
+    """Samples SM clock + throttle reasons during the timed region (pynvml == nvidia-smi's source).  NVML is
+    initialised before the timed region starts; the main thread adds one sample of its own inside the region
+    so that even a 20 ms run carries evidence."""
+
+    NAMES = None
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-
-    def run(self):
+        self.nv = self.h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-            while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.05)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                          nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                          nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                          nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, nm in self.names.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.005)
+
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
 
 
 def cpu_reference(workload, batch, iters, warm=1, mt="unet", kw=None, shared=False):
@@ -233,6 +247,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         step(i, devb[i % nb])
+    sampler.sample()          # the GPU is still executing the queued steps here
     e1.record()
     barrier()
     sampler.stop_flag = True

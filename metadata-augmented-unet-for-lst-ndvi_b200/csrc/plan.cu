@@ -921,23 +921,25 @@ int Plan::build() {
   bwd_makers.clear();
   // describe
   std::ostringstream js;
+  js.precision(15);
   js << "{\"model_type\":" << cfg.model_type << ",\"batch\":" << cfg.batch << ",\"height\":" << cfg.height
      << ",\"width\":" << cfg.width << ",\"training\":" << cfg.training << ",\"fwd_flops\":" << fwd_flops
-     << ",\"workspace_bytes\":" << ws_bytes << ",\"state\":[";
+     << ",\"exec_conv_flops\":" << exec_flops << ",\"workspace_bytes\":" << ws_bytes << ",\"state\":[";
   for (size_t i = 0; i < state.size(); ++i)
     js << (i ? "," : "") << "[\"" << state[i].name << "\"," << state[i].numel << "," << state[i].role << "]";
   js << "],\"layers\":[";
   for (size_t i = 0; i < layers.size(); ++i) {
     const ConvLayer* L = layers[i];
     js << (i ? "," : "") << "{\"name\":\"" << L->name << "\",\"cin\":" << L->Cin << ",\"cout\":" << L->Cout
-       << ",\"h\":" << L->H << ",\"w\":" << L->W << ",\"kp\":" << L->Kp << ",\"flops\":" << L->flops << ",\"segs\":[";
+       << ",\"h\":" << L->H << ",\"w\":" << L->W << ",\"kp\":" << L->Kp << ",\"flops\":" << L->flops << ",\"b\":" << L->B
+       << ",\"segs\":[";
     for (int s = 0; s < L->nseg; ++s) js << (s ? "," : "") << "[" << L->seg_start[s] << "," << L->seg_len[s] << "]";
     js << "],\"in\":\"" << bufs[L->in_buf].name << "\",\"out\":\"" << bufs[L->out.buf].name << "\",\"out_c0\":" << L->out.c0 << "}";
   }
   js << "],\"buffers\":[";
   for (size_t i = 0; i < bufs.size(); ++i)
     js << (i ? "," : "") << "{\"name\":\"" << bufs[i].name << "\",\"h\":" << bufs[i].H << ",\"w\":" << bufs[i].W
-       << ",\"c\":" << bufs[i].C << ",\"cs\":" << bufs[i].cs << "}";
+       << ",\"c\":" << bufs[i].C << ",\"cs\":" << bufs[i].cs << ",\"b\":" << bufs[i].B << "}";
   js << "]}";
   describe_json = js.str();
   return 0;

@@ -155,3 +155,51 @@ def test_plan_create_fails_loudly_without_gpu():
     h = C.c_void_p()
     rc = engine.lib().mau_plan_create(C.byref(c), C.byref(h))
     assert rc != 0 and b"no CUDA device" in engine.lib().mau_last_error()
+
+
+def test_shared_maps_plan_runs_the_encoder_once():
+    """MAU_FLAG_SHARED_MAPS (metadata-sensitivity sweep, reference test/metadata_sensitivity.py:294-311): every
+    buffer up to the bottleneck input holds ONE tile, the decoder the whole batch; executed conv FLOPs drop by
+    the encoder's share while the dense (reference) FLOPs stay the roofline numerator."""
+    B = 50
+    dense = engine.describe(_cfg(0, 1, 1, B=B))
+    cfg = _cfg(0, 1, 1, B=B)
+    cfg["flags"] = engine.FLAG_SHARED_MAPS
+    sweep = engine.describe(cfg)
+    assert sweep["fwd_flops"] == dense["fwd_flops"]
+    L = {l["name"]: l for l in sweep["layers"]}
+    for l in range(4):
+        assert L[f"conv{l}_0.conv1"]["b"] == 1 and L[f"conv{l}_0.conv2"]["b"] == 1
+    assert L["conv4_0.conv1"]["b"] == B and L["conv0_1.conv2"]["b"] == B
+    buf = {b["name"]: b for b in sweep["buffers"]}
+    assert buf["maps_nhwc"]["b"] == 1 and buf["x0_0.shared"]["b"] == 1 and buf["cat0"]["b"] == B
+    enc = sum(L[f"conv{l}_0.conv{k}"]["flops"] for l in range(4) for k in (1, 2))          # dense FLOPs, B tiles
+    assert abs(dense["exec_conv_flops"] - sweep["exec_conv_flops"] - enc * (B - 1) / B) < 1e-6 * dense["exec_conv_flops"]
+    assert sweep["workspace_bytes"] < dense["workspace_bytes"]
+    train = _cfg(0, 1, 1, B=4, training=1)
+    train["flags"] = engine.FLAG_SHARED_MAPS
+    with pytest.raises(RuntimeError, match="inference-only"):
+        engine.describe(train)
+
+
+def test_shared_maps_detection_is_host_logic():
+    """Batch-expanded (stride-0) inputs select the sweep plan; materialised batches do not unless asserted."""
+    m = mau_b200.UrbanPredictor("unet", *CTOR).eval()
+    x1 = torch.zeros(1, 23, 32, 32)
+    assert x1.expand(5, -1, -1, -1).stride(0) == 0 and x1.repeat(5, 1, 1, 1).stride(0) != 0
+    assert m.model.shared_maps == "auto"
+    m.assume_shared_maps(True)
+    assert m.model.shared_maps is True
+    with pytest.raises(ValueError):
+        m.assume_shared_maps("sometimes")
+
+
+def test_fused_adamw_has_no_cpu_fallback_and_torch_state_layout():
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = mau_b200.FusedAdamW([p], lr=1e-4, weight_decay=1e-3)
+    ref = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(4))], lr=1e-4, weight_decay=1e-3)
+    assert opt.state_dict()["param_groups"][0].keys() == ref.state_dict()["param_groups"][0].keys()
+    opt.step()                                    # no gradients: nothing to do, like the stock optimizer
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step()

@@ -54,3 +54,42 @@ def test_grad_reducer_single_process_is_noop():
     red = GradReducer(flat.clone(), bucket_numel=10)
     red.ready(50, 100); red.ready(0, 50); red.finish()
     assert torch.equal(red.flat, flat) and red.launched == 0
+
+
+def _dp_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import mau_b200
+    from mau_b200.parallel import DataParallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(1000 + rank)                      # different initial weights per rank
+    m = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 8, 32, 2, base_filters=8,
+                                temporal_embeddings=False, metadata_embeddings=True)
+    dp = DataParallel(m, sync_bn=True)                  # broadcasts rank 0's parameters and buffers
+    w = m.model.conv2_0.conv1.weight.detach().clone()
+    gathered = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(gathered, w)
+    same = all(torch.equal(g, gathered[0]) for g in gathered)
+    rm = m.state_dict()["model.conv0_0.bn1.running_mean"]
+    rm.fill_(float(rank))                               # ranks drift apart in local-BN mode ...
+    dp.sync_buffers()                                   # ... and are averaged before a checkpoint
+    ok = same and torch.allclose(rm, torch.full_like(rm, (world - 1) / 2)) and m.model._dp is dp and dp.sync_bn
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_broadcast_and_buffer_sync_gloo_world2():
+    """Host side of the data-parallel wrapper on CPU tensors: rank-0 broadcast at construction, running-stat
+    averaging, registration on the module (the kernels themselves need a GPU: tools/dp_parity.py)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

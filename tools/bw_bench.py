@@ -62,6 +62,7 @@ def main():
         by = fbytes(B, H, H, Cc, 2)
         sets = max(2, int(300e6 // max(by, 1)) + 1)
         sets = min(sets, 12)
+        sets = int(os.environ.get("BW_SETS", sets))
         ms = C.c_float()
         rc = L.mau_op_bw_bench(kind, 0, B, H, H, Cc, iters, sets, C.byref(ms))
         if rc:

@@ -82,3 +82,17 @@ for it in range(10):
     out = m(xd, td, mdd); loss = (out - tg).abs().mean(); loss.backward(); m.zero_grad(set_to_none=True)
 e1.record(); sync()
 print("steady-state step, torch L1 loss %.3f ms" % (e0.elapsed_time(e1) / 10))
+# torch-op loss (what the reference's own training loop does): per-phase device time
+tot = [0.0] * 4
+for it in range(6):
+    ev[0].record()
+    out = m(xd, td, mdd); ev[1].record()
+    loss = (out - tg).abs().mean(); ev[2].record()
+    loss.backward(); ev[3].record()
+    m.zero_grad(set_to_none=True); ev[4].record()
+    sync()
+    if it:
+        for k in range(4): tot[k] += ev[k].elapsed_time(ev[k + 1])
+print("torch L1 loss: device ms  fwd %.3f  loss %.3f  bwd %.3f  zero_grad %.3f" % tuple(t / 5 for t in tot))
+t0 = time.perf_counter(); out = m(xd, td, mdd); loss = (out - tg).abs().mean(); t1 = time.perf_counter(); loss.backward(); t2 = time.perf_counter(); sync(); t3 = time.perf_counter()
+print("torch L1 loss: host ms fwd+loss %.3f  backward() call %.3f  sync %.3f" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))

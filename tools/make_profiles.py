@@ -63,9 +63,13 @@ WANT = [("gpu__time_duration.sum", "us"), ("sm__pipe_tensor_cycles_active.avg.pc
 
 def full(path, out, title, note=""):
     rows = list(csv.reader(open(path)))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     cols = [(k, lab) for k, lab in WANT if k in idx]
+    # ncu picks one unit per column and per file: normalise bytes to MB and durations to us
+    SC = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6, "ns": 1e-3, "us": 1.0, "usecond": 1.0,
+          "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3, "s": 1e6, "second": 1e6}
+    scale = {k: SC.get(units[idx[k]], 1.0) for k, _ in cols}
     recs = []
     with open(out, "w") as f:
         f.write(f"# {title}\n\nSource: `{os.path.relpath(path, ROOT)}` = `ncu -i <report> --page raw --csv` of an "
@@ -78,7 +82,7 @@ def full(path, out, title, note=""):
             for k, lab in cols:
                 v = r[idx[k]].replace(",", "")
                 try:
-                    x = float(v)
+                    x = float(v) * scale[k]
                     vals.append(f"{x:.1f}" if lab != "regs" else f"{int(x)}")
                 except ValueError:
                     vals.append(v)
@@ -86,7 +90,7 @@ def full(path, out, title, note=""):
             rec = {"kernel": name}
             for k, lab in cols:
                 try:
-                    rec[lab] = float(r[idx[k]].replace(",", ""))
+                    rec[lab] = float(r[idx[k]].replace(",", "")) * scale[k]
                 except ValueError:
                     pass
             recs.append(rec)
@@ -102,19 +106,24 @@ def main():
         launches(lt, os.path.join(P, f"{tag}_launches_train.md"), f"{tag}: training step (config 3, B=16), every launch")
     if li:
         launches(li, os.path.join(P, f"{tag}_launches_infer.md"), f"{tag}: inference step (config 2, B=16), every launch")
-    pc, pw = latest("prof_conv*_raw.csv"), latest("prof_wgrad*_raw.csv")
+    pc, pw, pi = latest("prof_conv_raw.csv"), latest("prof_wgrad_raw.csv"), latest("prof_conv_infer_raw.csv")
+
+    def per_launch(recs):
+        n = len(recs)
+        by = sum(r.get("DRAM rd MB", 0) + r.get("DRAM wr MB", 0) for r in recs) * 1e6
+        return {"launches": n, "dram_bytes_per_launch": by / max(n, 1)}
+    if pi:
+        recs = full(pi, os.path.join(P, f"{tag}_ncu_conv_v2_infer.md"), f"{tag}: conv3x3_tc_v2_kernel, the 18 launches of one inference forward (config 2, B=16)",
+                    "Template arguments <BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES>; ")
+        traffic["conv_infer"] = per_launch(recs)
     if pc:
         recs = full(pc, os.path.join(P, f"{tag}_ncu_conv_v2.md"), f"{tag}: conv3x3_tc_v2_kernel (forward + dgrad launches of one training step)",
-                    "Template arguments <BN, MT, NBUF, NA, NB, NSTG>.")
-        n = len(recs)
-        by = sum(r.get("DRAM rd MB", 0) + r.get("DRAM wr MB", 0) for r in recs) * 1e6
-        traffic["conv_fwd_dgrad"] = {"launches": n, "dram_bytes_per_launch": by / max(n, 1)}
+                    "Template arguments <BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES>; ")
+        traffic["conv_fwd_dgrad"] = per_launch(recs)
     if pw:
-        recs = full(pw, os.path.join(P, f"{tag}_ncu_wgrad_v2.md"), f"{tag}: wgrad3x3_tc_v2_kernel (first 8 weight-gradient launches of one backward)",
-                    "Template arguments <BN, SWAP, STAGES>.")
-        n = len(recs)
-        by = sum(r.get("DRAM rd MB", 0) + r.get("DRAM wr MB", 0) for r in recs) * 1e6
-        traffic["wgrad"] = {"launches": n, "dram_bytes_per_launch": by / max(n, 1)}
+        recs = full(pw, os.path.join(P, f"{tag}_ncu_wgrad_v2.md"), f"{tag}: wgrad3x3_tc_v2_kernel (the 18 weight-gradient launches of one backward)",
+                    "Template arguments <BN, SWAP, STAGES>; ")
+        traffic["wgrad"] = per_launch(recs)
     for src in sorted(glob.glob(os.path.join(G, "prof_bw*_raw.csv"))):
         base = os.path.basename(src).replace("_raw.csv", "")
         full(src, os.path.join(P, f"{tag}_ncu_{base}.md"), f"{tag}: bandwidth-bound kernels ({base}), tools/bw_bench.py shapes at B=16")
@@ -128,13 +137,15 @@ def main():
         # bench.py's roofline.traffic: mean DRAM bytes per timed conv-family launch (config 2 times the forward convs,
         # config 3 forward + dgrad + wgrad).  The conv capture is of training-mode launches (same shapes as inference).
         out = {"source": f"profiles/{tag}_ncu_conv_v2.md, profiles/{tag}_ncu_wgrad_v2.md (dram__bytes_read.sum + dram__bytes_write.sum)"}
-        c, w = traffic.get("conv_fwd_dgrad"), traffic.get("wgrad")
-        if c:
-            out["config2"] = {"dram_bytes_per_launch": c["dram_bytes_per_launch"]}
-            out["config5"] = {"dram_bytes_per_launch": None}
+        c, w, ci = traffic.get("conv_fwd_dgrad"), traffic.get("wgrad"), traffic.get("conv_infer")
+        if ci:
+            out["config2"] = {"dram_bytes_per_launch": ci["dram_bytes_per_launch"], "launches": ci["launches"]}
+        elif c:
+            out["config2"] = {"dram_bytes_per_launch": c["dram_bytes_per_launch"], "launches": c["launches"]}
         if c and w:
             n = c["launches"] + w["launches"]
-            out["config3"] = {"dram_bytes_per_launch": (c["dram_bytes_per_launch"] * c["launches"] + w["dram_bytes_per_launch"] * w["launches"]) / n}
+            out["config3"] = {"dram_bytes_per_launch": (c["dram_bytes_per_launch"] * c["launches"] + w["dram_bytes_per_launch"] * w["launches"]) / n,
+                              "launches": n}
         json.dump(out, open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
     print("wrote", sorted(os.listdir(P)))
 
