@@ -265,8 +265,8 @@ def main():
     # standard PyTorch prefetch idiom); results land in pinned host buffers.
     copy_s = torch.cuda.Stream(device=dev)
     main_s = torch.cuda.current_stream(dev)
-    out_host = [torch.empty((B, 2, TILE, TILE), pin_memory=True) for _ in range(2)] if not train else \
-               [torch.empty((), pin_memory=True) for _ in range(2)]
+    out_host = [torch.empty((B, 2, TILE, TILE), pin_memory=True) for _ in range(3)] if not train else \
+               [torch.empty((), pin_memory=True) for _ in range(3)]
 
     def prefetch(i):
         with torch.cuda.stream(copy_s):
@@ -275,13 +275,16 @@ def main():
             ev.record(copy_s)
         return tens, ev
 
+    DEPTH = 3                      # input batches in flight ahead of the compute (keeps the H2D engine busy)
+    d2h_s = torch.cuda.Stream(device=dev)
+
     def e2e_run(n):
-        nxt = prefetch(0)
+        q = [prefetch(j) for j in range(min(DEPTH, n))]
         done = []
         for i in range(n):
-            (xd, td, mdd, tg), ev = nxt
-            if i + 1 < n:
-                nxt = prefetch(i + 1)
+            (xd, td, mdd, tg), ev = q.pop(0)
+            if i + DEPTH < n:
+                q.append(prefetch(i + DEPTH))
             main_s.wait_event(ev)
             for t_ in (xd, td, mdd, tg):
                 t_.record_stream(main_s)
@@ -295,13 +298,19 @@ def main():
                 opt.step()
                 opt.zero_grad(set_to_none=True)
                 res = res.detach()
-            out_host[i % 2].copy_(res, non_blocking=True)          # D2H of the step's result
-            e = torch.cuda.Event()
-            e.record(main_s)
+            ready = torch.cuda.Event()
+            ready.record(main_s)
+            with torch.cuda.stream(d2h_s):                         # D2H of the step's result off the compute stream
+                d2h_s.wait_event(ready)
+                res.record_stream(d2h_s)
+                out_host[i % len(out_host)].copy_(res, non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(d2h_s)
             done.append(e)
-            if i >= 1:
-                done[i - 1].synchronize()                          # the host has step i-1's result
-        done[-1].synchronize()
+            if i >= 2:
+                done[i - 2].synchronize()                          # the host has step i-2's result (ring of 3 buffers)
+        for e in done[-2:]:
+            e.synchronize()
 
     e2e_run(3)
     barrier()

@@ -610,10 +610,19 @@ __global__ void __launch_bounds__(256) pack_w_fwd_kernel(const float* __restrict
   for (long long item = (long long)blockIdx.x * 8 + warp; item < total; item += (long long)gridDim.x * 8) {
     const int n = (int)(item / chunks), kp0 = (int)(item % chunks) << 6;
     const float* src = w + (long long)n * Cin * 9;
-    for (int e = lane; e < 576; e += 32) {
-      const int kl = e / 9, t = e - kl * 9;
-      const int ci = kmap[kp0 + kl];
-      tile[warp][t][kl] = ci >= 0 ? src[ci * 9 + t] : 0.f;
+    int ci[18];
+    float v[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) ci[j] = kmap[kp0 + (lane + 32 * j) / 9];          // 18 index loads in flight ...
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {                                                 // ... then 18 weight loads in flight
+      const int e = lane + 32 * j, t = e - (e / 9) * 9;
+      v[j] = ci[j] >= 0 ? src[ci[j] * 9 + t] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+      const int e = lane + 32 * j, kl = e / 9;
+      tile[warp][e - kl * 9][kl] = v[j];
     }
     __syncwarp();
 #pragma unroll

@@ -29,26 +29,38 @@ __device__ __forceinline__ T* at(const DView& v, long long pix, int c) {
 // memory: coalesced 128-byte reads along P, 8-channel vector stores along C (pad channels up to the
 // view's 8-multiple are written as zeros).
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int P, DView y) {
-  __shared__ float tile[32][65];
-  const int p_tiles = (P + 63) / 64, c_tiles = (C + 31) / 32;
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int P, DView y) {
+  // tile = 128 pixels x 32 channels; plane rows are read as float4 (16 B) when P % 4 == 0
+  __shared__ float tile[32][129];
+  const int p_tiles = (P + 127) / 128, c_tiles = (C + 31) / 32;
   const long long total = (long long)B * p_tiles * c_tiles;
   const int C8 = (C + 7) & ~7;
+  const bool vec4 = (P & 3) == 0;
   for (long long t = blockIdx.x; t < total; t += gridDim.x) {
     const int ct = (int)(t % c_tiles);
     const long long r = t / c_tiles;
     const int pt = (int)(r % p_tiles);
     const int b = (int)(r / p_tiles);
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-      const int j = i >> 6, px = i & 63;
-      const int c = ct * 32 + j, p = pt * 64 + px;
-      tile[j][px] = (c < C && p < P) ? x[((long long)b * C + c) * P + p] : 0.f;
+    if (vec4) {
+      for (int i = threadIdx.x; i < 32 * 32; i += 256) {          // 32 channels x 32 float4
+        const int j = i >> 5, q = i & 31;
+        const int c = ct * 32 + j, p = pt * 128 + q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C && p < P) v = *reinterpret_cast<const float4*>(x + ((long long)b * C + c) * P + p);
+        tile[j][q * 4] = v.x; tile[j][q * 4 + 1] = v.y; tile[j][q * 4 + 2] = v.z; tile[j][q * 4 + 3] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+        const int j = i >> 7, px = i & 127;
+        const int c = ct * 32 + j, p = pt * 128 + px;
+        tile[j][px] = (c < C && p < P) ? x[((long long)b * C + c) * P + p] : 0.f;
+      }
     }
     __syncthreads();
-    {
-      const int px = threadIdx.x >> 2, cg = threadIdx.x & 3;     // 64 pixels x 4 groups of 8 channels
-      const int p = pt * 64 + px, c = ct * 32 + cg * 8;
+    for (int i = threadIdx.x; i < 128 * 4; i += 256) {            // 128 pixels x 4 groups of 8 channels
+      const int px = i >> 2, cg = i & 3;
+      const int p = pt * 128 + px, c = ct * 32 + cg * 8;
       if (p < P && c < C8 && c + 8 <= y.cs - y.c0) {
         float v[8];
 #pragma unroll
@@ -715,7 +727,7 @@ inline bool vec_ok(const View& v) { return v.cs % 8 == 0 && v.c0 % 8 == 0 && v.C
 int op_nchw_to_nhwc(int dt, const float* x, int B, int C, int H, int W, const View& y, cudaStream_t st) {
   const int P = H * W;
   if (y.cs % 8 || y.c0 % 8) return fail("nchw_to_nhwc: destination must be 8-channel aligned");
-  const long long tiles = (long long)B * ceil_div(P, 64) * ceil_div(C, 32);
+  const long long tiles = (long long)B * ceil_div(P, 128) * ceil_div(C, 32);
   MAU_DISPATCH(dt, nchw_to_nhwc_kernel, grid_for(tiles, 1, 16), 256, 0, st, x, B, C, P, dv(y));
   return 0;
 }

@@ -451,3 +451,53 @@ def test_shared_maps_sweep_is_bit_identical(name, precision):
     assert torch.equal(sweep, dense) and torch.equal(asserted, dense)
     ref = O.forward(sd, mt, xr, tr, md, training=False, **kw)
     assert rel(dense, ref) < TOL[precision]
+
+
+@pytest.mark.parametrize("case", ["unet_250", "unet_512_app", "unetpp_250"])
+def test_full_size_eval_against_oracle(case):
+    """BASELINE.json sizes against the CPU oracle on the same seeded inputs: the conf/config.yaml tile (250x250),
+    the app shape (512x512, conf/config.yaml:56) and the U-Net++ at 250x250; bf16 tolerance of north_star (1e-2,
+    max|d| / max|ref| per output channel)."""
+    mt, H, T, kw = {"unet_250": ("unet", 250, 828, dict(temporal_embeddings=False, metadata_embeddings=True)),
+                    "unet_512_app": ("unet", 512, 60, dict(temporal_embeddings=True, metadata_embeddings=True)),
+                    "unetpp_250": ("unet++", 250, 120, dict())}[case]
+    torch.manual_seed(42)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 64, 8, 64, 96, 2, **kw)
+    O.perturb_bn_stats(m.state_dict())
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x, ts, md, _ = O.synthetic_batch(1, H, H, T=T, seed=1002)
+    with torch.no_grad():
+        ref = O.forward(sd, mt, x, ts, md, training=False, **kw)
+        y = m.cuda().eval()(x.cuda(), ts.cuda(), md.cuda())
+    for ch in range(2):
+        assert rel(y[:, ch], ref[:, ch]) < TOL["bf16"], (case, ch)
+
+
+def test_full_size_training_step_properties():
+    """Training at the BASELINE batch (16 x 23x250x250): finite loss and gradients, gradients of flag-disabled
+    encoders stay None, BatchNorm counters advance, two identical steps give identical gradients (determinism of
+    everything except the fp32 TMA reduce-add order is not claimed: compare with a tolerance)."""
+    torch.manual_seed(42)
+    kw = dict(temporal_embeddings=False, metadata_embeddings=True)
+    m = mau_b200.UrbanPredictor("unet", 23, 828, 64, 8, 64, 96, 2, **kw).cuda().train()
+    x, ts, md, tgt = [t.cuda() for t in O.synthetic_batch(16, 250, 250, seed=1003)]
+    grads = []
+    for it in range(2):
+        m.zero_grad(set_to_none=True)
+        sd0 = {k: v.clone() for k, v in m.state_dict().items() if "running" in k}
+        out = m(x, ts, md)
+        loss = engine.compute_loss_l1_grad(out, tgt, 0.1)["total"]
+        loss.backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss)
+        for k, v in sd0.items():               # same batch statistics both times: undo the running-stat update
+            m.state_dict()[k].copy_(v)
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    assert int(m.state_dict()["model.conv0_0.bn1.num_batches_tracked"]) == 2
+    for k, p in m.named_parameters():
+        if "temporal_encoder" in k:
+            assert p.grad is None, k
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    for k in grads[0]:
+        assert rel(grads[1][k], grads[0][k]) < 1e-3 or float(grads[0][k].abs().max()) < 1e-6, k
