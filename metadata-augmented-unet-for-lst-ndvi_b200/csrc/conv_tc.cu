@@ -263,7 +263,7 @@ template <int BN, int MT, int NBUF, int NA, int NB, int NSTG>
 struct V2Smem {
   static constexpr int A_STAGE = MT * kHaloStride;
   static constexpr int B_STAGE = BN * 128;
-  static constexpr int SU = BN < 128 ? BN : 128;   // columns staged per TMA-store round
+  static constexpr int SU = BN % 128 == 0 ? 128 : 64;   // columns staged per TMA-store round (BN = 64, 192: 64)
   static constexpr int STG = (SU / 64) * 16384;    // 128 pixels x SU bf16 channels
   static constexpr int kBars = 2 * NA + 2 * NB + 4;
   static constexpr int kHeadOC = 4;                 // fused 1x1 head: up to 4 output channels
@@ -671,10 +671,10 @@ int conv_tc_pick_bn(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 25
 static int pick_bn_v2(int Cout) {
   // cost model: tiles x width / measured MMA efficiency of that instruction width (SMEM operand
   // bandwidth: N = 64 and N = 128 instructions cannot keep the tensor pipe full from one CTA)
-  const int bn[3] = {256, 128, 64};
-  const double eff[3] = {1.0, 0.8, 0.55};
+  const int bn[4] = {256, 192, 128, 64};
+  const double eff[4] = {1.0, 0.9, 0.8, 0.55};
   int best = 256; double best_cost = 1e30;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const double cost = (double)ceil_div(Cout, bn[i]) * bn[i] / eff[i];
     if (cost < best_cost) { best_cost = cost; best = bn[i]; }
   }
@@ -715,7 +715,7 @@ static int prepare_impl(ConvTcOp* op, const View& xbuf, int nseg, const int* seg
   p = ConvTcParams();
   op->mode = mode;
   op->bn = mode == MODE_HALO ? pick_bn_v2(y.C) : conv_tc_pick_bn(y.C);
-  op->mt = op->bn == 64 ? 4 : (op->bn == 128 ? 2 : 1);     // measured best per width (tools/conv_bench.py)
+  op->mt = op->bn == 64 ? 4 : (op->bn == 128 ? 2 : 1);     // measured best per width (tools/conv_bench.py); 192, 256: 1
   op->nbuf = 2;
   if (mode == MODE_HALO) {
     if (const char* e = getenv("MAU_CONV_CFG")) {      // experiment knob: "bn,mt,nbuf"
@@ -808,6 +808,7 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
     }
     MAU_V2(64, 4, 2, 2, 3, 1)
     MAU_V2(128, 2, 2, 2, 4, 2)
+    MAU_V2(192, 1, 2, 2, 4, 2)
     MAU_V2(256, 1, 2, 2, 4, 1)
 #undef MAU_V2
     return fail("conv_tc: no v2 kernel instance for BN=%d MT=%d NBUF=%d", op.bn, op.mt, op.nbuf);
