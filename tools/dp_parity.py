@@ -39,23 +39,41 @@ def main():
         lsum = loss.detach().clone()
         dist.all_reduce(lsum)
         if rank == 0:
+            # (1) the same engine, one process, the GLOBAL batch: differs from the N-rank run only by the order of the
+            #     SyncBN / gradient reductions -> tight tolerance
+            torch.manual_seed(7)
+            m1 = mau_b200.UrbanPredictor(mt, 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw)
+            m1.load_state_dict(sd0)
+            m1 = m1.to(dev).set_precision("fp32").train()
+            out1 = m1(x.to(dev), ts.to(dev), md.to(dev))
+            ((out1 - tgt.to(dev)) ** 2).mean().backward()
+            torch.cuda.synchronize()
+            g1 = {k: p.grad for k, p in m1.named_parameters() if p.grad is not None}
+            # (2) the CPU oracle at the global batch (train-mode BatchNorm makes single tiny-norm tensors ill-conditioned
+            #     in fp32 -- ReLU mask flips -- hence the absolute floor, as in tests/test_gpu_parity.py)
             _, lref, grads, sd1 = O.train_step_grads(sd0, mt, x, ts, md, tgt, loss="mse", **kw)
-            worst, name_w = 0.0, ""
+            worst1, name1, worst2, name2 = 0.0, "", 0.0, ""
+            ok = True
             for k, p in m.named_parameters():
                 if p.grad is None:
                     continue
-                g, r = p.grad.cpu(), grads[k]
-                e = float((g - r).norm() / r.norm().clamp_min(1e-12))
-                if r.norm() > 1e-6 and e > worst:
-                    worst, name_w = e, k
+                e1 = float((p.grad - g1[k]).norm() / g1[k].norm().clamp_min(1e-12))
+                if g1[k].norm() > 1e-7 and e1 > worst1:
+                    worst1, name1 = e1, k
+                r = grads[k]
+                err2, gn = float((p.grad.cpu() - r).norm()), float(r.norm())
+                ok &= err2 <= 2e-2 * gn + 2e-6
+                if gn > 1e-6 and err2 / gn > worst2:
+                    worst2, name2 = err2 / gn, k
             sd_now = m.state_dict()
             rs = max(float((sd_now[k].cpu() - sd1[k]).abs().max() / sd1[k].abs().max().clamp_min(1.0))
                      for k in sd1 if "running" in k)
             lerr = abs(float(lsum) / world - float(lref)) / max(abs(float(lref)), 1e-12)
-            ok = worst < 2e-3 and rs < 1e-4 and lerr < 1e-5
+            ok = ok and worst1 < 1e-3 and rs < 1e-4 and lerr < 1e-5
             ok_all &= ok
-            print(f"[dp_parity] {mt} world={world}: loss err {lerr:.2e}, worst grad rel L2 {worst:.2e} ({name_w}), "
-                  f"running-stat max err {rs:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+            print(f"[dp_parity] {mt} world={world}: loss err {lerr:.2e}; vs single-process engine at the global batch: worst grad rel L2 "
+                  f"{worst1:.2e} ({name1}); vs CPU oracle: worst {worst2:.2e} ({name2}), running-stat err {rs:.2e} -> "
+                  f"{'OK' if ok else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok_all:
