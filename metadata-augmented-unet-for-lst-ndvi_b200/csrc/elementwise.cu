@@ -391,23 +391,22 @@ __global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DVie
     }
     V8<T>::store(gxb + row * gxrow, o);
   };
-  Raw nx[kMaxE];                                 // gy vectors of the NEXT output row, requested one row ahead
-  {
-    const T* rowp = gyb + oh_first * gyrow;
+  // Output rows are processed in pairs with two statically named register buffers (the loads of row oh + 1 are in
+  // flight while row oh is consumed).  Most source columns receive at most 4 contributions: slots 4 and 5 are
+  // only touched when some lane of the warp needs them (warp-uniform branch, so the common case issues nothing).
+  const bool wide = __any_sync(__activemask(), nc > 4);   // lanes past the row end have already returned
+  auto load_row = [&](Raw (&buf)[kMaxE], int oh) {
+    const T* rowp = gyb + oh * gyrow;
 #pragma unroll
-    for (int c = 0; c < kMaxE; ++c)
-      if (c < nc) nx[c] = V8<T>::load_raw(rowp + off[c]);
-  }
-  for (int oh = oh_first; oh <= oh_last; ++oh) {
-    Raw rv[kMaxE];
+    for (int c = 0; c < 4; ++c)
+      if (c < nc) buf[c] = V8<T>::load_raw(rowp + off[c]);
+    if (wide) {
 #pragma unroll
-    for (int c = 0; c < kMaxE; ++c) rv[c] = nx[c];
-    if (oh < oh_last) {
-      const T* rowp = gyb + (oh + 1) * gyrow;
-#pragma unroll
-      for (int c = 0; c < kMaxE; ++c)
-        if (c < nc) nx[c] = V8<T>::load_raw(rowp + off[c]);
+      for (int c = 4; c < kMaxE; ++c)
+        if (c < nc) buf[c] = V8<T>::load_raw(rowp + off[c]);
     }
+  };
+  auto consume = [&](const Raw (&buf)[kMaxE], int oh) {
     int y0, y1; float ly;
     src_index(sy, oh, gx.H, y0, y1, ly);         // block-uniform
     while (y0 > r && r < ih_e) {                 // input row r is complete
@@ -420,13 +419,23 @@ __global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DVie
 #pragma unroll
     for (int k = 0; k < 8; ++k) hg[k] = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxE; ++c)
+    for (int c = 0; c < 4; ++c)
       if (c < nc) {
         float v[8];
-        V8<T>::unpack(rv[c], v);
+        V8<T>::unpack(buf[c], v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) hg[k] = fmaf(wx[c], v[k], hg[k]);
       }
+    if (wide) {
+#pragma unroll
+      for (int c = 4; c < kMaxE; ++c)
+        if (c < nc) {
+          float v[8];
+          V8<T>::unpack(buf[c], v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hg[k] = fmaf(wx[c], v[k], hg[k]);
+        }
+    }
     const float w0 = 1.f - ly;
     if (y0 == r) {
 #pragma unroll
@@ -442,6 +451,14 @@ __global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DVie
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc0[k] = fmaf(ly, hg[k], acc0[k]);
     }
+  };
+  Raw bufA[kMaxE], bufB[kMaxE];
+  load_row(bufA, oh_first);
+  for (int oh = oh_first; oh <= oh_last; oh += 2) {
+    if (oh + 1 <= oh_last) load_row(bufB, oh + 1);
+    consume(bufA, oh);
+    if (oh + 2 <= oh_last) load_row(bufA, oh + 2);
+    if (oh + 1 <= oh_last) consume(bufB, oh + 1);
   }
   if (r < ih_e) emit(r, acc0);
   if (r + 1 < ih_e) emit(r + 1, acc1);
@@ -489,21 +506,24 @@ __global__ void bilinear_bwd_general_kernel(DView gy, DView gx, BilinearTables t
 }
 
 // ------------------------------------------------------------------ embeddings
+// grid (chunks, B); block 256 = G channel groups x L pixel lanes: a thread converts its 8 embedding values once
+// and then only stores (16 B per pixel it owns)
 template <typename T>
-__global__ void embed_broadcast_kernel(const float* __restrict__ emb, int stride, DView y) {
+__global__ void __launch_bounds__(256) embed_broadcast_kernel(const float* __restrict__ emb, int stride, DView y) {
+  using Raw = typename V8<T>::Raw;
   const int G = y.C / 8;
-  const long long HW = (long long)y.H * y.W;
-  const long long total = (long long)y.B * HW * G;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    const long long pix = i / G;
-    const int b = (int)(pix / HW);
-    float o[8];
+  const int L = 256 / G;
+  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
+  if (pl >= L) return;
+  const int b = blockIdx.y;
+  const int HW = y.H * y.W;
+  float o[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = emb[(long long)b * stride + g * 8 + k];
-    V8<T>::store(at<T>(y, pix, g * 8), o);
-  }
+  for (int k = 0; k < 8; ++k) o[k] = emb[(long long)b * stride + gi * 8 + k];
+  T* base = static_cast<T*>(y.ptr) + (long long)b * HW * y.cs + y.c0 + gi * 8;
+  Raw r;
+  V8<T>::store(reinterpret_cast<T*>(&r), o);           // pack once
+  for (int p = blockIdx.x * L + pl; p < HW; p += gridDim.x * L) *reinterpret_cast<Raw*>(base + (long long)p * y.cs) = r;
 }
 // grid (chunks, B); block 256 = (C/8 groups) x (256 / groups pixel lanes)
 template <typename T>
@@ -631,6 +651,59 @@ __global__ void __launch_bounds__(256) head_kernel(DView x, const float* __restr
           }
       }
     }
+  }
+}
+
+// One thread per pixel: 8-channel vectors of the pixel are loaded four at a time, weights are float4 broadcasts
+// from shared memory, no cross-lane reduction, NCHW stores coalesced across the warp.  (The 8-lanes-per-pixel
+// version above spent 160 instructions per lane on shuffles, predicates and a divergent tanh: issue-bound at 44 %
+// of HBM peak.)
+template <typename T, int OCT>
+__global__ void __launch_bounds__(256) head_pix_kernel(DView x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       int OC, int apply_tanh, float* __restrict__ out) {
+  using Raw = typename V8<T>::Raw;
+  extern __shared__ float sw[];            // [OCT][C]
+  const int C = x.C;
+  for (int i = threadIdx.x; i < OCT * C; i += 256) sw[i] = (i / C) < OC ? w[i] : 0.f;
+  __syncthreads();
+  const int P = x.H * x.W;
+  const int b = blockIdx.y;
+  const T* xb = static_cast<const T*>(x.ptr) + (long long)b * P * x.cs + x.c0;
+  float* ob = out + (long long)b * OC * P;
+  const int G = C / 8;
+  for (int pix = blockIdx.x * 256 + threadIdx.x; pix < P; pix += gridDim.x * 256) {
+    const T* px = xb + (long long)pix * x.cs;
+    float acc[OCT];
+#pragma unroll
+    for (int o = 0; o < OCT; ++o) acc[o] = 0.f;
+    for (int g0 = 0; g0 < G; g0 += 4) {
+      Raw r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (g0 + u < G) r[u] = V8<T>::load_raw(px + (g0 + u) * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (g0 + u < G) {
+          float v[8];
+          V8<T>::unpack(r[u], v);
+#pragma unroll
+          for (int o = 0; o < OCT; ++o) {
+            const float4 wa = *reinterpret_cast<const float4*>(sw + o * C + (g0 + u) * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sw + o * C + (g0 + u) * 8 + 4);
+            acc[o] = fmaf(v[0], wa.x, acc[o]); acc[o] = fmaf(v[1], wa.y, acc[o]);
+            acc[o] = fmaf(v[2], wa.z, acc[o]); acc[o] = fmaf(v[3], wa.w, acc[o]);
+            acc[o] = fmaf(v[4], wb.x, acc[o]); acc[o] = fmaf(v[5], wb.y, acc[o]);
+            acc[o] = fmaf(v[6], wb.z, acc[o]); acc[o] = fmaf(v[7], wb.w, acc[o]);
+          }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < OCT; ++o)
+      if (o < OC) {
+        float v = acc[o] + bias[o];
+        if (apply_tanh && o == 0) v = tanhf(v);
+        ob[(long long)o * P + pix] = v;
+      }
   }
 }
 
@@ -818,8 +891,11 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
   return 0;
 }
 int op_embed_broadcast(int dt, const float* emb, int emb_stride, const View& y, cudaStream_t st) {
-  if (!vec_ok(y)) return fail("embed_broadcast: bad view");
-  MAU_DISPATCH(dt, embed_broadcast_kernel, grid_for(y.pixels() * (y.C / 8)), 256, 0, st, emb, emb_stride, dv(y));
+  if (!vec_ok(y) || y.C > 2048 || y.B > 65535) return fail("embed_broadcast: bad view");
+  const int L = std::max(1, 256 / (y.C / 8));
+  const int per_img = std::max(1, std::min(ceil_div(y.H * y.W, L * 4), ceil_div(148 * 8, y.B)));
+  const dim3 grid((unsigned)per_img, (unsigned)y.B, 1);
+  MAU_DISPATCH(dt, embed_broadcast_kernel, grid, 256, 0, st, emb, emb_stride, dv(y));
   return 0;
 }
 int op_embed_reduce(int dt, const View& g, float* demb, int emb_stride, int accumulate, cudaStream_t st) {
@@ -866,9 +942,11 @@ int op_head(int dt, const View& x, const float* w, const float* bias, int OC, in
   if (!head_ok(x, OC)) return fail("head: needs C = 8*2^k <= 256 and out_channels <= 8 (C=%d, OC=%d)", x.C, OC);
   const int per_block = 256 / (x.C / 8);
   if (x.B > 65535) return fail("head: batch too large for the per-image grid");
-  const int per_img = std::max(1, std::min(ceil_div(ceil_div(x.H * x.W, kHU), per_block), ceil_div(148 * 8, x.B)));
+  (void)per_block;
+  const int per_img = std::max(1, std::min(ceil_div(x.H * x.W, 256), ceil_div(148 * 8, x.B)));
   const dim3 grid((unsigned)per_img, (unsigned)x.B, 1);
-  MAU_HEAD_DISPATCH(head_kernel, grid, 0, dv(x), w, bias, OC, apply_tanh, out_nchw);
+  const size_t smem = sizeof(float) * (OC <= 2 ? 2 : (OC <= 4 ? 4 : 8)) * x.C;
+  MAU_HEAD_DISPATCH(head_pix_kernel, grid, smem, dv(x), w, bias, OC, apply_tanh, out_nchw);
   return 0;
 }
 int op_head_bwd(int dt, const View& x, const float* w, int OC, int apply_tanh, const float* out_nchw,

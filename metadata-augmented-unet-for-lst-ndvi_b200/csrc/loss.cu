@@ -22,22 +22,24 @@ __global__ void __launch_bounds__(256) loss_kernel(int kind, const float* __rest
                                                    int planes, int H, int W, float inv_n, float inv_ny, float inv_nx,
                                                    float lambda, double* __restrict__ partials,
                                                    float* __restrict__ grad) {
-  const long long HW = (long long)H * W;
-  const long long total = (long long)planes * HW;
-  double s_pix = 0.0, s_dy = 0.0, s_dx = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long hw = i % HW;
-    const int h = (int)(hw / W), w = (int)(hw - (long long)h * W);
+  // fp32 partial sums per thread (a thread sees at most a few hundred elements), fp64 only across threads:
+  // B200 issues FP64 adds at a small fraction of the FP32 rate and this loop was bound by them
+  float f_pix = 0.f, f_dy = 0.f, f_dx = 0.f;
+  // a block works on whole image rows (h known per row, w = thread offset): no division per element
+  const long long rows = (long long)planes * H;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x)
+  for (int w = threadIdx.x; w < W; w += blockDim.x) {
+    const int h = (int)(row % H);
+    const long long i = row * W + w;
     const float pc = p[i], tc = t[i];
     const float d = pc - tc;
     float g;
-    if (kind == 0) { s_pix += fabsf(d); g = sgn(d) * inv_n; }
-    else           { s_pix += (double)d * d; g = 2.f * d * inv_n; }
+    if (kind == 0) { f_pix += fabsf(d); g = sgn(d) * inv_n; }
+    else           { f_pix = fmaf(d, d, f_pix); g = 2.f * d * inv_n; }
     if (h + 1 < H) {   // pair (h, h+1): this pixel is the upper one
       const float a = p[i + W] - pc, b = t[i + W] - tc;
       const float u = fabsf(a) - fabsf(b);
-      s_dy += fabsf(u);
+      f_dy += fabsf(u);
       g -= lambda * inv_ny * sgn(u) * sgn(a);
     }
     if (h > 0) {       // pair (h-1, h): this pixel is the lower one
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(256) loss_kernel(int kind, const float* __rest
     if (w + 1 < W) {
       const float a = p[i + 1] - pc, b = t[i + 1] - tc;
       const float u = fabsf(a) - fabsf(b);
-      s_dx += fabsf(u);
+      f_dx += fabsf(u);
       g -= lambda * inv_nx * sgn(u) * sgn(a);
     }
     if (w > 0) {
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(256) loss_kernel(int kind, const float* __rest
     if (grad) grad[i] = g;
   }
   __shared__ double red[3][8];
+  double s_pix = (double)f_pix, s_dy = (double)f_dy, s_dx = (double)f_dx;
   s_pix = warp_sum(s_pix); s_dy = warp_sum(s_dy); s_dx = warp_sum(s_dx);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { red[0][warp] = s_pix; red[1][warp] = s_dy; red[2][warp] = s_dx; }
@@ -111,7 +114,7 @@ int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, 
   const long long n = (long long)B * C * H * W;
   const long long ny = (long long)B * C * (H - 1) * W, nx = (long long)B * C * H * (W - 1);
   if (n <= 0 || ny <= 0 || nx <= 0) return fail("loss: empty tensor");
-  int blocks = (int)std::min<long long>((n + 255) / 256, kMaxLossBlocks);
+  int blocks = (int)std::min<long long>((long long)B * C * H, kMaxLossBlocks);
   double* partials = loss_scratch(st);
   if (!partials) return fail("loss: scratch allocation failed");
   loss_kernel<<<blocks, 256, 0, st>>>(kind, pred, tgt, B * C, H, W, 1.f / (float)n, 1.f / (float)ny, 1.f / (float)nx,

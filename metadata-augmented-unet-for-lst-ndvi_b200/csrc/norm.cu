@@ -29,7 +29,7 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 // Every thread keeps kU pixels' worth of 16-byte loads in flight (NT tensors each) before it touches any of
 // them: these kernels have no reuse, so achieved bandwidth is bytes-in-flight / latency.
 constexpr int kU = 4;
-template <typename T, int NQ, int NT, typename F>
+template <typename T, int NQ, int NT, typename F, int U = (NT == 1 ? 8 : kU)>
 __device__ __forceinline__ void channel_reduce(const DView& ref, const DView& second, long long npix, double* out,
                                                F&& body) {
   extern __shared__ float red[];  // [NQ][256][8]
@@ -47,10 +47,10 @@ __device__ __forceinline__ void channel_reduce(const DView& ref, const DView& se
     for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
   if (pl < L) {
     const int c = gi * 8;
-    for (long long p = p0 + pl; p < p1; p += (long long)kU * L) {
-      Raw r0[kU], r1[kU];
+    for (long long p = p0 + pl; p < p1; p += (long long)U * L) {
+      Raw r0[U], r1[U];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long pu = p + (long long)u * L;
         if (pu < p1) {
           r0[u] = V8<T>::load_raw(at<T>(ref, pu, c));
@@ -58,7 +58,7 @@ __device__ __forceinline__ void channel_reduce(const DView& ref, const DView& se
         }
       }
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long pu = p + (long long)u * L;
         if (pu < p1) {
           float a[8], b[8];
@@ -329,7 +329,7 @@ int op_bn_stats(int dt, const View& z, double* sums, cudaStream_t st) {
   if (!vec_ok(z)) return fail("bn_stats: bad view (C=%d cs=%d c0=%d)", z.C, z.cs, z.c0);
   // sums layout [2][C]; with a single slab (C <= 2048) the kernel's [q*C + c] indexing matches
   const size_t smem = 2 * 256 * 8 * sizeof(float);
-  const int blocks = reduce_blocks(z.pixels(), z.C);
+  const int blocks = std::min(reduce_blocks(z.pixels(), z.C), 148 * 3);      // 80 registers: 3 resident blocks per SM, one wave
   if (dt == DT_BF16) bn_stats_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(DView{z.ptr, z.B, z.H, z.W, z.cs, z.c0, z.C}, sums);
   else               bn_stats_kernel<float><<<blocks, 256, smem, st>>>(DView{z.ptr, z.B, z.H, z.W, z.cs, z.c0, z.C}, sums);
   MAU_LAUNCHED();
