@@ -594,70 +594,12 @@ __global__ void copy_slice_kernel(DView src, DView dst, int accumulate) {
 }
 
 // ------------------------------------------------------------------ 1x1 head
-// G = C/8 lanes per pixel (each 8 channels), shuffle-reduce over the G lanes, lane 0 of the group writes
-// NCHW.  kHU pixels per thread are loaded before any is used.  OCT = compile-time bound on out_channels.
 constexpr int kMaxOC = 8;
 constexpr int kHU = 4;
-template <typename T, int OCT>
-__global__ void __launch_bounds__(256) head_kernel(DView x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                   int OC, int apply_tanh, float* __restrict__ out) {
-  using Raw = typename V8<T>::Raw;
-  const int G = x.C / 8;           // lanes per pixel (power of two <= 32 assumed by the host)
-  const int sub = threadIdx.x % G, slot = threadIdx.x / G;
-  float wr[OCT][8];                // this lane's 8 weights of every output channel
-#pragma unroll
-  for (int o = 0; o < OCT; ++o)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) wr[o][k] = o < OC ? w[o * x.C + sub * 8 + k] : 0.f;
-  // grid.y = image: pixel indices stay 32-bit and no division sits in the loop (the 64-bit div/mod of the
-  // first version made this kernel issue-bound: ncu 73 % issue-slot utilisation at 35 % of HBM peak)
-  const int P = x.H * x.W;
-  const int b = blockIdx.y;
-  const T* xb = static_cast<const T*>(x.ptr) + (long long)b * P * x.cs + x.c0 + sub * 8;
-  float* ob = out + (long long)b * OC * P;
-  const int per_block = blockDim.x / G;
-  const int stride = gridDim.x * per_block;
-  for (int base = blockIdx.x * per_block; base < P; base += kHU * stride) {
-    Raw r[kHU];
-#pragma unroll
-    for (int u = 0; u < kHU; ++u) {
-      const int pix = base + u * stride + slot;
-      if (pix < P) r[u] = V8<T>::load_raw(xb + (long long)pix * x.cs);
-    }
-#pragma unroll
-    for (int u = 0; u < kHU; ++u) {
-      const int pix = base + u * stride + slot;
-      float acc[OCT];
-#pragma unroll
-      for (int o = 0; o < OCT; ++o) acc[o] = 0.f;
-      if (pix < P) {
-        float v[8];
-        V8<T>::unpack(r[u], v);
-#pragma unroll
-        for (int o = 0; o < OCT; ++o)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[o] = fmaf(v[k], wr[o][k], acc[o]);
-      }
-#pragma unroll
-      for (int o = 0; o < OCT; ++o)
-        for (int off = G >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
-      if (pix < P && sub == 0) {
-#pragma unroll
-        for (int o = 0; o < OCT; ++o)
-          if (o < OC) {
-            float v = acc[o] + bias[o];
-            if (apply_tanh && o == 0) v = tanhf(v);
-            ob[(long long)o * P + pix] = v;
-          }
-      }
-    }
-  }
-}
-
 // One thread per pixel: 8-channel vectors of the pixel are loaded four at a time, weights are float4 broadcasts
-// from shared memory, no cross-lane reduction, NCHW stores coalesced across the warp.  (The 8-lanes-per-pixel
-// version above spent 160 instructions per lane on shuffles, predicates and a divergent tanh: issue-bound at 44 %
-// of HBM peak.)
+// from shared memory, no cross-lane reduction, NCHW stores coalesced across the warp.  (The first, 8-lanes-per-pixel
+// version spent 160 instructions per lane on shuffles, predicates and a divergent tanh: issue-bound at 44 % of HBM
+// peak; this one is bound by L1 tag throughput at the same level -- see DESIGN.md 6.)
 template <typename T, int OCT>
 __global__ void __launch_bounds__(256) head_pix_kernel(DView x, const float* __restrict__ w, const float* __restrict__ bias,
                                                        int OC, int apply_tanh, float* __restrict__ out) {

@@ -230,7 +230,7 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
   };
   fwd.push_back(op);
   if (training) {
-    counters_host.push_back(reinterpret_cast<long long*>((intptr_t)L->inbt));   // index, resolved at run time
+    counter_idx.push_back(L->inbt);     // state index of num_batches_tracked, resolved to a pointer at run time
     bwd_makers.push_back([this, L]() { return emit_conv_bwd(L); });
   }
   return 0;
@@ -914,7 +914,7 @@ int Plan::build() {
     for (auto it = bwd_makers.rbegin(); it != bwd_makers.rend(); ++it) MAU_TRY((*it)());
     if (!dry) {
       // counters (num_batches_tracked) are bumped by one tiny kernel per forward
-      counters_dev = static_cast<long long**>(alloc(sizeof(long long*) * std::max<size_t>(1, counters_host.size())));
+      counters_dev = static_cast<long long**>(alloc(sizeof(long long*) * std::max<size_t>(1, counter_idx.size())));
       if (!counters_dev) return -1;
     }
   }
@@ -983,9 +983,9 @@ int Plan::run_forward(Ctx& c) {
   MAU_TRY(run_ops(this, fwd, c, false));
   MAU_TRY(side_join(c));
   if (!cfg.training) { packed_version = state_version; packed_state = last_state; }
-  if (cfg.training && !counters_host.empty()) {
+  if (cfg.training && !counter_idx.empty()) {
     std::vector<long long*> ptrs;
-    for (long long* idx : counters_host) ptrs.push_back(static_cast<long long*>(c.state[(intptr_t)idx]));
+    for (int idx : counter_idx) ptrs.push_back(static_cast<long long*>(c.state[idx]));
     // pageable-host async copies are staged by the runtime before returning
     MAU_CUDA(cudaMemcpyAsync(counters_dev, ptrs.data(), sizeof(long long*) * ptrs.size(), cudaMemcpyHostToDevice, c.st));
     MAU_TRY(op_bump_counters(counters_dev, (int)ptrs.size(), c.st));

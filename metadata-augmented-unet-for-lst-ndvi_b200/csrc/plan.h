@@ -104,7 +104,7 @@ class Plan {
   std::vector<KTimer> ktimers;
   void kbegin(const Ctx& c, const std::string& name);
   void kend(const Ctx& c);
-  std::vector<long long*> counters_host; long long** counters_dev = nullptr;
+  std::vector<int> counter_idx; long long** counters_dev = nullptr;   // num_batches_tracked state indices / device pointer table
   std::string describe_json;
   std::vector<void*> last_state; const float* last_series = nullptr; const float* last_md = nullptr;
   // eval-mode weight cache: packed weights / folded BN are reused while the caller's state is unchanged
