@@ -147,11 +147,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    default_invocation = args.config is None and args.workload is None
     cfg_id = args.config if args.config is not None else (3 if args.workload == "train" else 2)
     mt, kw, workload, def_batch, shared, workload_name = CONFIGS[cfg_id]
     args.workload = workload
-    if args.batch is None:
-        args.batch = def_batch
     metric = "inference tiles/sec" if args.workload == "infer" else "training tiles/sec (fwd+bwd)"
 
     if args.impl == "reference":
@@ -177,211 +176,223 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    train = args.workload == "train"
     if args.comm_ctas is None:
         args.comm_ctas = 4 if world <= 2 else 8
     if world > 1:
-        if train:
-            # the gradient all-reduce runs concurrently with the persistent conv / wgrad kernels: cap NCCL's
-            # CTA count and leave that many SMs out of our persistent grids (no second-wave cliff)
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.config.max_ctas = max(1, args.comm_ctas)
-            opts.config.min_ctas = 1
-            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-            engine.lib().mau_set_sm_reserve(max(0, args.comm_ctas))
-        else:
-            dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    torch.manual_seed(42)
-    model = mau_b200.UrbanPredictor(mt, *CTOR, **kw)
-    O.perturb_bn_stats(model.state_dict())
-    model = model.to(dev)
-    model.train(train)
-    if train and world > 1:
-        from mau_b200 import parallel
-        parallel.DataParallel(model, sync_bn=args.sync_bn)   # overlapped all-reduce on the plan's grad hook
-    # several distinct input batches so that consecutive steps never re-read L2-resident inputs
-    nb = 4
-    host = [O.synthetic_batch(B, TILE, TILE, seed=1002 + 17 * rank + i) for i in range(nb)]
-    if shared:      # sweep: ONE tile and series per step (the reference repeats them on the device), B metadata rows
-        def sweep(h):
-            x, ts, md, tgt = h
-            md = md.clone()
-            md[:, 0] = torch.linspace(-2.0, 2.0, B)          # test/metadata_sensitivity.py:296-304
-            return x[:1].contiguous(), ts[:1].contiguous(), md, tgt
-        host = [sweep(h) for h in host]
-    pinned = [tuple(t.pin_memory() for t in h) for h in host]
-    devb = [tuple(t.to(dev) for t in h) for h in host]
-    # same optimizer as the reference (src/train.py:213-214, conf/config.yaml:41,52), one fused launch per step
-    opt = mau_b200.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-3) if train else None
+        # the gradient all-reduce of the training configs runs concurrently with the persistent conv / wgrad kernels:
+        # cap NCCL's CTA count (and, per training measurement, leave that many SMs out of our persistent grids)
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = max(1, args.comm_ctas)
+        opts.config.min_ctas = 1
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
-    def fwd(x, ts, md):
-        if shared:      # one tile + one series, B metadata rows (batch-expanded views select the sweep plan)
-            return model.forward_sweep(x, ts, md)
-        return model(x, ts, md)
+    def measure(cfg_id, steps, warmup, with_cpu_baseline):
+        mt, kw, workload, def_batch, shared, workload_name = CONFIGS[cfg_id]
+        metric = "inference tiles/sec" if workload == "infer" else "training tiles/sec (fwd+bwd)"
+        train = workload == "train"
+        engine.lib().mau_set_sm_reserve(max(0, args.comm_ctas) if (train and world > 1) else 0)
+        B = args.batch if args.batch is not None else def_batch
+        torch.manual_seed(42)
+        model = mau_b200.UrbanPredictor(mt, *CTOR, **kw)
+        O.perturb_bn_stats(model.state_dict())
+        model = model.to(dev)
+        model.train(train)
+        if train and world > 1:
+            from mau_b200 import parallel
+            parallel.DataParallel(model, sync_bn=args.sync_bn)   # overlapped all-reduce on the plan's grad hook
+        # several distinct input batches so that consecutive steps never re-read L2-resident inputs
+        nb = 4
+        host = [O.synthetic_batch(B, TILE, TILE, seed=1002 + 17 * rank + i) for i in range(nb)]
+        if shared:      # sweep: ONE tile and series per step (the reference repeats them on the device), B metadata rows
+            def sweep(h):
+                x, ts, md, tgt = h
+                md = md.clone()
+                md[:, 0] = torch.linspace(-2.0, 2.0, B)          # test/metadata_sensitivity.py:296-304
+                return x[:1].contiguous(), ts[:1].contiguous(), md, tgt
+            host = [sweep(h) for h in host]
+        pinned = [tuple(t.pin_memory() for t in h) for h in host]
+        devb = [tuple(t.to(dev) for t in h) for h in host]
+        # same optimizer as the reference (src/train.py:213-214, conf/config.yaml:41,52), one fused launch per step
+        opt = mau_b200.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-3) if train else None
 
-    def step(i, batch):
-        x, ts, md, tgt = batch
-        if not train:
-            with torch.no_grad():
-                return fwd(x, ts, md)
-        out = model(x, ts, md)
-        loss = engine.compute_loss_l1_grad(out, tgt, 0.0)["total"]      # L1 via the fused loss kernel
-        loss.backward()
-        opt.step()                            # fused AdamW: inside the timed region
-        opt.zero_grad(set_to_none=True)
-        return loss
+        def fwd(x, ts, md):
+            if shared:      # one tile + one series, B metadata rows (batch-expanded views select the sweep plan)
+                return model.forward_sweep(x, ts, md)
+            return model(x, ts, md)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        step(i, devb[i % nb])
-    barrier()
-    launches0 = engine.lib().mau_launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(i, devb[i % nb])
-    sampler.sample()          # the GPU is still executing the queued steps here
-    e1.record()
-    barrier()
-    sampler.stop_flag = True
-    ms = e0.elapsed_time(e1)
-    launches = engine.lib().mau_launch_count() - launches0
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * B * args.steps / (ms / 1e3)
-
-    # ---- end to end through the public nn.Module API with HOST buffers: every step's inputs are copied
-    # from pinned host memory (H2D) and every step's result is read back to the host (D2H), all inside the
-    # timed region.  Copies of step i+1 are prefetched on a side stream while step i computes (the
-    # standard PyTorch prefetch idiom); results land in pinned host buffers.
-    copy_s = torch.cuda.Stream(device=dev)
-    main_s = torch.cuda.current_stream(dev)
-    out_host = [torch.empty((B, 2, TILE, TILE), pin_memory=True) for _ in range(3)] if not train else \
-               [torch.empty((), pin_memory=True) for _ in range(3)]
-
-    def prefetch(i):
-        with torch.cuda.stream(copy_s):
-            tens = tuple(t_.to(dev, non_blocking=True) for t_ in pinned[i % nb])
-            ev = torch.cuda.Event()
-            ev.record(copy_s)
-        return tens, ev
-
-    DEPTH = 3                      # input batches in flight ahead of the compute (keeps the H2D engine busy)
-    d2h_s = torch.cuda.Stream(device=dev)
-
-    def e2e_run(n):
-        q = [prefetch(j) for j in range(min(DEPTH, n))]
-        done = []
-        for i in range(n):
-            (xd, td, mdd, tg), ev = q.pop(0)
-            if i + DEPTH < n:
-                q.append(prefetch(i + DEPTH))
-            main_s.wait_event(ev)
-            for t_ in (xd, td, mdd, tg):
-                t_.record_stream(main_s)
+        def step(i, batch):
+            x, ts, md, tgt = batch
             if not train:
                 with torch.no_grad():
-                    res = fwd(xd, td, mdd)
-            else:
-                out_ = model(xd, td, mdd)
-                res = engine.compute_loss_l1_grad(out_, tg, 0.0)["total"]
-                res.backward()
-                opt.step()
-                opt.zero_grad(set_to_none=True)
-                res = res.detach()
-            ready = torch.cuda.Event()
-            ready.record(main_s)
-            with torch.cuda.stream(d2h_s):                         # D2H of the step's result off the compute stream
-                d2h_s.wait_event(ready)
-                res.record_stream(d2h_s)
-                out_host[i % len(out_host)].copy_(res, non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(d2h_s)
-            done.append(e)
-            if i >= 2:
-                done[i - 2].synchronize()                          # the host has step i-2's result (ring of 3 buffers)
-        for e in done[-2:]:
-            e.synchronize()
+                    return fwd(x, ts, md)
+            out = model(x, ts, md)
+            loss = engine.compute_loss_l1_grad(out, tgt, 0.0)["total"]      # L1 via the fused loss kernel
+            loss.backward()
+            opt.step()                            # fused AdamW: inside the timed region
+            opt.zero_grad(set_to_none=True)
+            return loss
 
-    e2e_run(2 * DEPTH + 3)        # warm-up: lets the caching allocator reach its steady-state pool (no cudaMalloc in the timed run)
-    barrier()
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
-    x0, ts0, md0, tg0 = pinned[0]
-    h2d = sum(t_.numel() * 4 for t_ in ((x0, ts0, md0, tg0) if train else (x0, ts0, md0)))
-    d2h = 4 if train else B * 2 * TILE * TILE * 4
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
 
-    # ---- roofline of the dominant kernel (3x3 conv on the tensor pipe): per-layer CUDA-event times
-    plan = next(iter(model.model._plans.values()))
-    for p_ in model.model._plans.values():
-        if p_.cfg["training"] == int(train) and p_.cfg["batch"] == B:
-            plan = p_
-    plan.profile(True)
-    conv_ms, conv_n, all_ms = 0.0, 0, 0.0
-    reps = 3
-    for i in range(reps):
-        step(i, devb[i % nb])
-        torch.cuda.synchronize()
-        for name, t_ms in plan.profile_read():
-            if name.startswith("k:"):        # CUDA events right around one conv / dgrad / wgrad kernel launch
-                conv_ms += t_ms
-                conv_n += 1
-            else:                            # per-op entries (a conv op also holds its BN / pack / memset launches)
-                all_ms += t_ms
-            if args.profile_layers and i == reps - 1 and rank == 0:
-                print(f"{name:36s} {t_ms:8.3f} ms", file=sys.stderr)
-    plan.profile(False)
-    fwd_flops, bwd_flops = plan.flops()              # dense reference graph (SURVEY.md 8d numerators)
-    exec_fwd = plan.exec_conv_flops()                # what the conv kernels execute per forward
-    pk = peaks()
-    # kernel roofline: FLOPs the timed kernels executed / their summed launch durations.  Training backward =
-    # dgrad + wgrad of every conv (no dgrad for the first layer) = bwd_flops of the plan.
-    kern_flops = exec_fwd + (bwd_flops if train else 0.0)
-    achieved_tf = kern_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # from the committed ncu --set full captures
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"config{cfg_id}", {}).get("dram_bytes_per_launch")
-    roof = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved_tf / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["src"],
-            "kernel": "conv3x3_tc_v2_kernel (+wgrad3x3_tc_v2_kernel in training)",
-            "launches_timed": conv_n // reps, "avg_launch_us": conv_ms / max(conv_n, 1) * 1e3,
-            "flop_per_launch": kern_flops * reps / max(conv_n, 1),
-            "conv_share_of_step": conv_ms / all_ms if all_ms else None,
-            "algorithmic_gflop_per_tile": (fwd_flops + (bwd_flops if train else 0.0)) / B / 1e9}
+        for i in range(warmup):
+            step(i, devb[i % nb])
+        barrier()
+        launches0 = engine.lib().mau_launch_count()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i, devb[i % nb])
+        sampler.sample()          # the GPU is still executing the queued steps here
+        e1.record()
+        barrier()
+        sampler.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        launches = engine.lib().mau_launch_count() - launches0
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        value = world * B * steps / (ms / 1e3)
 
-    out = {"metric": metric, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": workload_name, "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_gpu": B,
-                      "global_batch": B * world, "parallelism": f"dp{world}",
-                      "l2": "4 rotating input batches (368 MB) + ~2 GB of activations per step: working set > 126 MB L2"},
-           "clocks": sampler.summary(),
-           "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-           "gpu_launches": int(launches), "roofline": roof,
-           "tflops_whole_step": (fwd_flops + (bwd_flops if train else 0)) / B * value / world / 1e12}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = 4 if not train else 2
-        v, sec, threads = cpu_reference(args.workload, sample, 3, 1, mt, kw, shared)
-        out["cpu_baseline"] = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
-                               "sample": f"{sample} tiles x 3 timed steps (1 warm-up), oracle/unet_oracle.py, torch CPU fp32"}
-    elif rank == 0:
-        out["cpu_baseline"] = None
+        # ---- end to end through the public nn.Module API with HOST buffers: every step's inputs are copied
+        # from pinned host memory (H2D) and every step's result is read back to the host (D2H), all inside the
+        # timed region.  Copies of step i+1 are prefetched on a side stream while step i computes (the
+        # standard PyTorch prefetch idiom); results land in pinned host buffers.
+        copy_s = torch.cuda.Stream(device=dev)
+        main_s = torch.cuda.current_stream(dev)
+        out_host = [torch.empty((B, 2, TILE, TILE), pin_memory=True) for _ in range(3)] if not train else \
+                   [torch.empty((), pin_memory=True) for _ in range(3)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_s):
+                tens = tuple(t_.to(dev, non_blocking=True) for t_ in pinned[i % nb])
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+            return tens, ev
+
+        DEPTH = 3                      # input batches in flight ahead of the compute (keeps the H2D engine busy)
+        d2h_s = torch.cuda.Stream(device=dev)
+
+        def e2e_run(n):
+            q = [prefetch(j) for j in range(min(DEPTH, n))]
+            done = []
+            for i in range(n):
+                (xd, td, mdd, tg), ev = q.pop(0)
+                if i + DEPTH < n:
+                    q.append(prefetch(i + DEPTH))
+                main_s.wait_event(ev)
+                for t_ in (xd, td, mdd, tg):
+                    t_.record_stream(main_s)
+                if not train:
+                    with torch.no_grad():
+                        res = fwd(xd, td, mdd)
+                else:
+                    out_ = model(xd, td, mdd)
+                    res = engine.compute_loss_l1_grad(out_, tg, 0.0)["total"]
+                    res.backward()
+                    opt.step()
+                    opt.zero_grad(set_to_none=True)
+                    res = res.detach()
+                ready = torch.cuda.Event()
+                ready.record(main_s)
+                with torch.cuda.stream(d2h_s):                         # D2H of the step's result off the compute stream
+                    d2h_s.wait_event(ready)
+                    res.record_stream(d2h_s)
+                    out_host[i % len(out_host)].copy_(res, non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(d2h_s)
+                done.append(e)
+                if i >= 2:
+                    done[i - 2].synchronize()                          # the host has step i-2's result (ring of 3 buffers)
+            for e in done[-2:]:
+                e.synchronize()
+
+        e2e_run(2 * DEPTH + 3)        # warm-up: lets the caching allocator reach its steady-state pool (no cudaMalloc in the timed run)
+        barrier()
+        e0.record()
+        e2e_run(steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * steps / (float(t.item()) / 1e3)
+        x0, ts0, md0, tg0 = pinned[0]
+        h2d = sum(t_.numel() * 4 for t_ in ((x0, ts0, md0, tg0) if train else (x0, ts0, md0)))
+        d2h = 4 if train else B * 2 * TILE * TILE * 4
+
+        # ---- roofline of the dominant kernel (3x3 conv on the tensor pipe): per-layer CUDA-event times
+        plan = next(iter(model.model._plans.values()))
+        for p_ in model.model._plans.values():
+            if p_.cfg["training"] == int(train) and p_.cfg["batch"] == B:
+                plan = p_
+        plan.profile(True)
+        conv_ms, conv_n, all_ms = 0.0, 0, 0.0
+        reps = 3
+        for i in range(reps):
+            step(i, devb[i % nb])
+            torch.cuda.synchronize()
+            for name, t_ms in plan.profile_read():
+                if name.startswith("k:"):        # CUDA events right around one conv / dgrad / wgrad kernel launch
+                    conv_ms += t_ms
+                    conv_n += 1
+                else:                            # per-op entries (a conv op also holds its BN / pack / memset launches)
+                    all_ms += t_ms
+                if args.profile_layers and i == reps - 1 and rank == 0:
+                    print(f"{name:36s} {t_ms:8.3f} ms", file=sys.stderr)
+        plan.profile(False)
+        fwd_flops, bwd_flops = plan.flops()              # dense reference graph (SURVEY.md 8d numerators)
+        exec_fwd = plan.exec_conv_flops()                # what the conv kernels execute per forward
+        pk = peaks()
+        # kernel roofline: FLOPs the timed kernels executed / their summed launch durations.  Training backward =
+        # dgrad + wgrad of every conv (no dgrad for the first layer) = bwd_flops of the plan.
+        kern_flops = exec_fwd + (bwd_flops if train else 0.0)
+        achieved_tf = kern_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # from the committed ncu --set full captures
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"config{cfg_id}", {}).get("dram_bytes_per_launch")
+        roof = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["src"],
+                "kernel": "conv3x3_tc_v2_kernel (+wgrad3x3_tc_v2_kernel in training)",
+                "launches_timed": conv_n // reps, "avg_launch_us": conv_ms / max(conv_n, 1) * 1e3,
+                "flop_per_launch": kern_flops * reps / max(conv_n, 1),
+                "conv_share_of_step": conv_ms / all_ms if all_ms else None,
+                "algorithmic_gflop_per_tile": (fwd_flops + (bwd_flops if train else 0.0)) / B / 1e9}
+
+        out = {"metric": metric, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": workload_name, "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_gpu": B,
+                          "global_batch": B * world, "parallelism": f"dp{world}",
+                          "l2": "4 rotating input batches (368 MB) + ~2 GB of activations per step: working set > 126 MB L2"},
+               "clocks": sampler.summary(),
+               "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": int(launches), "roofline": roof,
+               "tflops_whole_step": (fwd_flops + (bwd_flops if train else 0)) / B * value / world / 1e12}
+        if rank == 0 and world == 1 and with_cpu_baseline:
+            sample = 4 if not train else 2
+            v, sec, threads = cpu_reference(workload, sample, 3, 1, mt, kw, shared)
+            out["cpu_baseline"] = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
+                                   "sample": f"{sample} tiles x 3 timed steps (1 warm-up), oracle/unet_oracle.py, torch CPU fp32"}
+        elif rank == 0:
+            out["cpu_baseline"] = None
+        model.model.release_plans()
+        return out
+
+    steps, warmup = args.steps, args.warmup
+    out = measure(cfg_id, steps, warmup, not args.no_cpu_baseline)
+    if default_invocation:
+        # BASELINE.json's metric names two numbers: the line's value is the inference one (configs[1]); the training
+        # number (configs[2]: fwd + L1 + bwd + fused AdamW, data-parallel when N > 1) rides along in "training"
+        tr = measure(3, max(5, steps // 2), 3, False)
+        out["training"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches",
+                                              "roofline", "clocks", "config")}
     if rank == 0:
         emit(out)
     if world > 1:
