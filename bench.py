@@ -347,11 +347,12 @@ def main():
                     print(f"{name:36s} {t_ms:8.3f} ms", file=sys.stderr)
         plan.profile(False)
         fwd_flops, bwd_flops = plan.flops()              # dense reference graph (SURVEY.md 8d numerators)
-        exec_fwd = plan.exec_conv_flops()                # what the conv kernels execute per forward
+        exec_fwd, exec_bwd = plan.exec_flops()           # what the conv / dgrad / wgrad kernels execute per step
         pk = peaks()
         # kernel roofline: FLOPs the timed kernels executed / their summed launch durations.  Training backward =
-        # dgrad + wgrad of every conv (no dgrad for the first layer) = bwd_flops of the plan.
-        kern_flops = exec_fwd + (bwd_flops if train else 0.0)
+        # dgrad + wgrad of every conv (no dgrad for the first layer; the U-Net++ embedding planes' share is computed in
+        # closed form by other kernels and is not counted here).
+        kern_flops = exec_fwd + (exec_bwd if train else 0.0)
         achieved_tf = kern_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # from the committed ncu --set full captures

@@ -13,8 +13,10 @@
  *   - all pointers named *_dev are device pointers on the plan's device; the caller owns
  *     parameters, buffers, inputs, outputs and gradients; the plan owns only its
  *     workspace, packed weights and TMA descriptors.
- *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing is
- *     synchronised (the plan is stateful: one forward/backward in flight per plan).
+ *   - `stream` is a cudaStream_t passed as void*; all work is ordered on it and nothing is
+ *     synchronised with the host (the plan is stateful: one forward/backward in flight per plan).
+ *     A plan may run its LSTM / MLP encoder kernels on a private side stream; they are forked from
+ *     and joined back into `stream` with events inside the same call.
  *   - tensors crossing the ABI are contiguous fp32 NCHW exactly as the reference's
  *     callers hold them (src/dataset.py:99-106); counters are int64.
  */
@@ -61,6 +63,7 @@ typedef struct mau_config {
 #define MAU_FLAG_HALO_BASEOFF  256 /* debug: halo main loop fills the UMMA descriptor base_offset   */
 #define MAU_FLAG_CONV_ROW3     512 /* debug: three-row-box conv main loop instead of the halo kernel */
 #define MAU_FLAG_WGRAD_V1      1024 /* debug: first-generation weight-gradient kernel (fp32 atomics)   */
+#define MAU_FLAG_EMB_DENSE_BWD 2048 /* debug: U-Net++ embedding planes back-propagated densely (dgrad + wgrad launches) */
 
 typedef struct mau_plan mau_plan; /* opaque */
 
@@ -85,9 +88,10 @@ int    mau_plan_state_info(const mau_plan* plan, int i, int64_t* numel, int* rol
 int    mau_plan_describe_config(const mau_config* cfg, char* buf, size_t buflen);
 /* algorithmic work of one forward over the whole batch (dense reference graph) */
 int    mau_plan_flops(const mau_plan* plan, double* fwd_flops, double* bwd_flops);
-/* FLOPs the 3x3 convolution kernels of ONE forward actually execute (equals the dense conv FLOPs unless
- * MAU_FLAG_SHARED_MAPS runs the encoder once for the whole batch) */
-int    mau_plan_exec_flops(const mau_plan* plan, double* conv_flops_per_forward);
+/* FLOPs the 3x3 convolution kernels of ONE forward / ONE backward actually execute: the dense conv FLOPs unless
+ * MAU_FLAG_SHARED_MAPS runs the encoder once for the whole batch (forward) or the U-Net++ embedding planes are
+ * back-propagated in closed form (backward; 0 for eval plans) */
+int    mau_plan_exec_flops(const mau_plan* plan, double* conv_flops_per_forward, double* conv_flops_per_backward);
 
 /* --- forward: replaces `model(maps, temp_series, metadata)` (src/model.py:328,
  *     called at src/train.py:245, test/evaluate.py:186, test/metadata_sensitivity.py:310) ---

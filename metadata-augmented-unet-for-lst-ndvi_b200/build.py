@@ -9,7 +9,7 @@ SRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(SRC, "obj")
 LIB = os.path.join(HERE, "libmau_b200.so")
 SOURCES = ["common.cu", "tma.cu", "conv_tc.cu", "wgrad_tc.cu", "conv_ffma.cu", "elementwise.cu", "norm.cu",
-           "encoders.cu", "loss.cu", "metrics.cu", "optim.cu", "plan.cu", "api.cu"]
+           "encoders.cu", "loss.cu", "metrics.cu", "optim.cu", "embgrad.cu", "plan.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
          "-Xcompiler", "-fPIC", "-DNDEBUG"]

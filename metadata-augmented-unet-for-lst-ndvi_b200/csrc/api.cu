@@ -72,9 +72,10 @@ int mau_plan_flops(const mau_plan* plan, double* fwd_flops, double* bwd_flops) {
   return 0;
 }
 
-int mau_plan_exec_flops(const mau_plan* plan, double* conv_flops_per_forward) {
+int mau_plan_exec_flops(const mau_plan* plan, double* conv_flops_per_forward, double* conv_flops_per_backward) {
   if (!plan || !conv_flops_per_forward) return fail("null argument");
   *conv_flops_per_forward = plan->impl.exec_flops;
+  if (conv_flops_per_backward) *conv_flops_per_backward = plan->impl.exec_bwd_flops;
   return 0;
 }
 

@@ -114,6 +114,13 @@ int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, 
 int op_eval_metrics(const float* maps, int maps_c, const float* pred, const float* tgt, int B, int C, int H, int W,
                     float temp_mean, float temp_std, long long* dw_map, double* sums, cudaStream_t st);
 
+// ---- backward of a conv w.r.t. a spatially constant input segment (embgrad.cu; U-Net++ embedding planes) ------
+// dz: the conv's output gradient [B,H,W,Cout]; emb [B, emb_stride] holds the segment's E values per image at emb[b*stride + c].
+// dw_oihw[:, ci0:ci0+E, :, :] is overwritten, demb[b*stride + c] is accumulated.  scratch: emb_grad_scratch_floats(B, Cout).
+size_t emb_grad_scratch_floats(int B, int Cout);
+int op_emb_segment_grad(int dt, const View& dz, const float* w_oihw, int Cin, int ci0, int E, const float* emb,
+                        int emb_stride, float* dw_oihw, float* demb, float* scratch, cudaStream_t st);
+
 // ---- optimizer (optim.cu): torch.optim.AdamW step for every tensor in one launch ---------------------
 int op_adamw_step(int n_tensors, void* const* params, void* const* grads, void* const* exp_avg,
                   void* const* exp_avg_sq, const long long* numels, double lr, double beta1, double beta2, double eps,

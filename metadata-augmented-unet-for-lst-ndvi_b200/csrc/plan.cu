@@ -135,6 +135,7 @@ ConvLayer* Plan::add_conv(const std::string& name, int iw0, int in_buf, int nseg
   L->H = bufs[in_buf].H; L->W = bufs[in_buf].W;
   L->Cout = out.C;
   L->input_needs_grad = input_needs_grad;
+  L->emb_seg = next_emb_seg; next_emb_seg = -1;
   std::vector<int> kmap;
   for (int s = 0; s < nseg; ++s) {
     L->seg_start[s] = seg_start[s]; L->seg_len[s] = seg_len[s];
@@ -257,7 +258,18 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
   int dacc[4] = {0, 0, 0, 0};
   L->Kd = round_up(C, 64);
   L->wg_swap = (use_tc && wgrad_ws) ? wgrad_tc_pick_swap(C, L->nseg, L->seg_len) : 0;
+  if (L->emb_seg >= 0) {
+    emb_direct = true;
+    if (!embgrad_scratch && !dry) {
+      size_t fl = 0;
+      for (const ConvLayer* q : layers) fl = std::max(fl, emb_grad_scratch_floats(cfg.batch, q->Cout));
+      embgrad_scratch = static_cast<float*>(alloc(sizeof(float) * fl));
+      if (!embgrad_scratch) return -1;
+    }
+  }
   for (int s = 0; s < L->nseg; ++s) {
+    if (s == L->emb_seg) { ci_w0 += L->seg_len[s]; continue; }     // no wgrad / dgrad launches for the constant planes
+    exec_bwd_flops += 2.0 * 9.0 * L->seg_len[s] * C * (double)L->H * L->W * L->B * (L->input_needs_grad ? 2.0 : 1.0);
     const TRef xin{L->in_buf, L->seg_start[s], L->seg_len[s]};
     if (use_tc) MAU_TRY(wgrad_tc_prepare(&L->wg[s], view(xin), z, ci_w0, L->Cin, wgrad_ws, L->wg_swap));
     if (L->input_needs_grad) {
@@ -305,7 +317,9 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
     const bool ws_path = use_tc && wgrad_ws != nullptr;      // v2 wgrad: reduce into the workspace, then transpose
     if (dw && ws_path) MAU_CUDA(cudaMemsetAsync(wgrad_ws, 0, sizeof(float) * wgrad_tc_workspace_floats(C, L->Cin, L->wg_swap), c.st));
     else if (dw) MAU_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * L->Cin * 9, c.st));
+    int emb_ci0 = -1;
     for (int s = 0; s < L->nseg; ++s) {
+      if (s == L->emb_seg) { emb_ci0 = ci_w0; ci_w0 += L->seg_len[s]; continue; }
       const TRef xin{L->in_buf, L->seg_start[s], L->seg_len[s]};
       if (dw) {
         kbegin(c, "k:" + L->name + ":wgrad");
@@ -329,6 +343,9 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
       ci_w0 += L->seg_len[s];
     }
     if (dw && ws_path) MAU_TRY(wgrad_tc_finalize(wgrad_ws, L->wg_swap, C, L->Cin, dw, c.st));
+    if (emb_ci0 >= 0)      // dW of the constant planes' columns and their contribution to d emb, from nine sums of dz per image
+      MAU_TRY(op_emb_segment_grad(dt, z, c.f(L->iw), L->Cin, emb_ci0, L->seg_len[L->emb_seg], emb, emb_dim, dw, demb,
+                                  embgrad_scratch, c.st));
     return 0;
   };
   bwd.push_back(op);
@@ -476,9 +493,11 @@ int Plan::build_embed_broadcast(const TRef* t_dst, int n_t, const TRef* m_dst, i
       Op b;
       b.name = "emb.bwd";                        // reduce on the main stream, encoder backward on the side stream
       b.run = [=](Ctx& c) -> int {
-        MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * B * emb_dim, c.st));
-        if (te) for (const View& g : gt) MAU_TRY(op_embed_reduce(dt, g, demb + t_off, emb_dim, 1, c.st));
-        if (me) for (const View& g : gm) MAU_TRY(op_embed_reduce(dt, g, demb + m_off, emb_dim, 1, c.st));
+        if (!emb_direct) {     // (U-Net++: the decoder nodes have already accumulated d emb in closed form)
+          MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * B * emb_dim, c.st));
+          if (te) for (const View& g : gt) MAU_TRY(op_embed_reduce(dt, g, demb + t_off, emb_dim, 1, c.st));
+          if (me) for (const View& g : gm) MAU_TRY(op_embed_reduce(dt, g, demb + m_off, emb_dim, 1, c.st));
+        }
         MAU_TRY(side_fork(c));
         if (te) {
           if (c.g(fc0))
@@ -824,6 +843,7 @@ int Plan::build_unetpp() {
     MAU_TRY(add_up(xref(l + 1, j - 1), upref(l, j)));
     const int ss[3] = {0, upref(l, j).c0, embref(l).c0};
     const int sl[3] = {j * F[l], F[l + 1], E};
+    if (cfg.training && !(cfg.flags & MAU_FLAG_EMB_DENSE_BWD)) next_emb_seg = 2;   // constant planes: closed-form backward
     return add_vgg("conv" + std::to_string(l) + "_" + std::to_string(j), blk[l][j], lv[l], 3, ss, sl, F[l], xref(l, j),
                    true, (l == 0 && j == 4) ? &last_block : nullptr);
   };
@@ -997,6 +1017,7 @@ int Plan::run_forward(Ctx& c) {
 int Plan::run_backward(Ctx& c) {
   if (!cfg.training) return fail("backward requires a training-mode plan");
   if (!forward_done) return fail("backward called before forward");
+  if (emb_direct) MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * cfg.batch * emb_dim, c.st));
   MAU_TRY(run_ops(this, bwd, c, true));
   MAU_TRY(side_join(c));
   forward_done = false;

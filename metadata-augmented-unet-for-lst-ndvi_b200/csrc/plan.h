@@ -77,6 +77,7 @@ struct ConvLayer {
   ConvTcOp tc_d[4]; ConvFfmaParams ff_d[4];
   WgradTcOp wg[4];
   int wg_swap = 0;          // wgrad v2 orientation (see wgrad_tc.cu)
+  int emb_seg = -1;         // input segment that is constant over space (U-Net++ embedding planes): backward in closed form
 };
 
 class Plan {
@@ -113,6 +114,7 @@ class Plan {
   bool skip_pack = false;
   bool shared = false;       // MAU_FLAG_SHARED_MAPS: encoder and LSTM run once, results broadcast over the batch
   double exec_flops = 0;     // FLOPs the convolution kernels execute per forward (== fwd conv FLOPs unless shared)
+  double exec_bwd_flops = 0; // FLOPs the dgrad + wgrad kernels execute per backward (dense minus closed-form segments)
 
   ~Plan();
   int build();
@@ -146,6 +148,9 @@ class Plan {
   int side_join(Ctx& c);
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool side_pending = false;
   int enc_lstm0 = -1, enc_fc0 = -1, enc_mlp0 = -1;
+  int next_emb_seg = -1;            // consumed by the next add_conv
+  bool emb_direct = false;          // embedding gradient accumulated straight into demb by the decoder nodes (embgrad.cu)
+  float* embgrad_scratch = nullptr;
   std::vector<std::function<int()>> bwd_makers;   // run in reverse to emit backward ops
   // encoder scratch
   float* emb = nullptr; float* demb = nullptr; float* hidden = nullptr; float* hlast = nullptr;

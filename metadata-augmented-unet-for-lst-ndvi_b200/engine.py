@@ -78,7 +78,7 @@ def lib():
         L.mau_plan_state_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
         L.mau_plan_describe_config.argtypes = [C.POINTER(MauConfig), C.c_char_p, C.c_size_t]
         L.mau_plan_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        L.mau_plan_exec_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.mau_plan_exec_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.mau_plan_forward.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.mau_plan_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
@@ -215,9 +215,13 @@ class Plan:
 
     def exec_conv_flops(self) -> float:
         """FLOPs the conv kernels execute per forward (dense conv FLOPs unless this is a shared-maps plan)."""
-        f = C.c_double()
-        check(lib().mau_plan_exec_flops(self._h, C.byref(f)), "exec_flops")
-        return f.value
+        return self.exec_flops()[0]
+
+    def exec_flops(self):
+        """(forward, backward) FLOPs the conv / dgrad / wgrad kernels of this plan execute per step."""
+        f, b = C.c_double(), C.c_double()
+        check(lib().mau_plan_exec_flops(self._h, C.byref(f), C.byref(b)), "exec_flops")
+        return f.value, b.value
 
     def used_state_indices(self) -> List[int]:
         return [i for i, r in enumerate(self.roles) if r == ROLE_PARAM]

@@ -501,3 +501,26 @@ def test_full_size_training_step_properties():
             assert p.grad is not None and torch.isfinite(p.grad).all(), k
     for k in grads[0]:
         assert rel(grads[1][k], grads[0][k]) < 1e-3 or float(grads[0][k].abs().max()) < 1e-6, k
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_unetpp_embedding_backward_closed_form_equals_dense(precision, tol, monkeypatch):
+    """The U-Net++ concatenates spatially constant embedding planes into every decoder node (reference
+    src/model.py:98-108).  Their share of the backward is computed in closed form from nine sums of dz per image
+    (csrc/embgrad.cu) instead of a dense dgrad + wgrad; MAU_FLAG_EMB_DENSE_BWD (2048) keeps the dense launches.
+    Both must give the same gradients (the closed form removes bf16 roundings, hence the looser bf16 bound)."""
+    grads = {}
+    for flags in ("0", "2048"):
+        monkeypatch.setenv("MAU_FLAGS", flags)
+        torch.manual_seed(123)
+        m = mau_b200.UrbanPredictor("unet++", 23, 828, 16, 8, 8, 32, 2, base_filters=8).cuda().set_precision(precision).train()
+        x, ts, md, tgt = [t.cuda() for t in O.synthetic_batch(3, 37, 45, T=40, seed=1004)]
+        out = m(x, ts, md)
+        engine.compute_loss_mse_gradient(out, tgt, 0.0)["total"].backward()
+        torch.cuda.synchronize()
+        grads[flags] = {k: p.grad.clone() for k, p in m.named_parameters()}
+        m.model.release_plans()
+    for k, g in grads["0"].items():
+        d = grads["2048"][k]
+        gn = float(d.norm())
+        assert float((g - d).norm()) <= tol * gn + 1e-6, (k, float((g - d).norm()), gn)
