@@ -133,7 +133,8 @@ int mau_plan_set_stats_sync(mau_plan* plan, mau_stats_sync_fn fn, void* user, in
 
 /* SMs the persistent kernels leave free (default 0, or $MAU_SM_RESERVE): set it to the number of CTAs
  * a concurrently running collective (NCCL all-reduce overlapped with backward) occupies, so that a
- * persistent grid never spills into a second wave.  Applies to plans created afterwards. */
+ * persistent grid never spills into a second wave.  Applies to the BACKWARD launches (dgrad, wgrad) of
+ * plans created afterwards; forward launches always use every SM (no collective runs during forward). */
 int mau_set_sm_reserve(int n_sms);
 
 /* per-layer device timings of the last forward/backward (ms, CUDA events on `stream`);

@@ -20,10 +20,13 @@ int fail(const char* fmt, ...) {
 // leaves SMs free for a concurrently running collective kernel: a persistent grid that does not fit
 // next to it would otherwise run its last CTAs as a second wave.
 static std::atomic<int> g_sm_reserve{-1};
+static thread_local int t_reserve_override = -1;     // >= 0: used instead of the global reserve (plan build scopes)
+void set_sm_reserve_override(int n) { t_reserve_override = n; }
 void set_sm_reserve(int n) { g_sm_reserve.store(n < 0 ? 0 : n); }
 int sm_budget() {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (t_reserve_override >= 0) return sms - t_reserve_override > 8 ? sms - t_reserve_override : 8;
   int r = g_sm_reserve.load();
   if (r < 0) {
     const char* e = getenv("MAU_SM_RESERVE");

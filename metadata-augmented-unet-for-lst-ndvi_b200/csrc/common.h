@@ -53,6 +53,7 @@ struct View {
 
 int sm_budget();              // SMs persistent kernels may occupy (device SM count - reserve)
 void set_sm_reserve(int n);   // SMs left free for concurrent collective kernels (data-parallel training)
+void set_sm_reserve_override(int n);   // per-thread scope: >= 0 replaces the global reserve, -1 ends the scope
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -920,7 +920,11 @@ int Plan::build() {
   if (cfg.training && cfg.deep_supervision) return fail("deep supervision is forward-only in this engine");
   shared = (cfg.flags & MAU_FLAG_SHARED_MAPS) != 0;
   if (shared && cfg.training) return fail("MAU_FLAG_SHARED_MAPS is an inference-only fast path (BatchNorm batch statistics couple the rows in training)");
+  // the gradient all-reduce only runs during backward: forward launches may use every SM, backward launches are
+  // sized for (SMs - reserve)
+  set_sm_reserve_override(0);
   int rc = cfg.model_type == MAU_MODEL_UNET ? build_unet() : build_unetpp();
+  set_sm_reserve_override(-1);
   if (rc) return rc;
   if (cfg.training) {
     if (use_tc && !(cfg.flags & MAU_FLAG_WGRAD_V1)) {
