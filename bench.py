@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- tiles/s of the Metadata-Augmented U-Net hot path on B200 (and the CPU reference arm).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--batch B]
-    python bench.py --impl reference ...        # the reference algorithm on the host CPU (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5 | --workload infer|train] [--batch B]
+    python bench.py --impl reference ...        # the reference algorithm on the host CPU (oracle port, all cores)
 
 One "step" = one pass of the hot path over one batch of synthetic tiles (23x250x250).
-Default workload = BASELINE.json configs[1]: U-Net + metadata MLP, eval mode, bf16, per-GPU batch 16.
-`--workload train` = configs[2]: the same model, train mode, forward + L1 loss + backward.
-Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), tiles sharded across
-ranks (weak scaling); training adds the NCCL gradient all-reduce overlapped with backward.
+`--config` selects a BASELINE.json configs[] entry (1-based): 1 = no-embedding U-Net inference in the fp32 parity
+mode (B=8), 2 (default) = U-Net + metadata MLP inference, bf16, B=16 per GPU, 3 = the same model training (forward +
+L1 loss kernel + backward + fused AdamW), 4 = U-Net++ training, 5 = the B=50 metadata-sensitivity sweep.
+With no --config / --workload the line is config 2 and additionally carries config 3 under "training".
+Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), tiles sharded across ranks (weak
+scaling, no collective in inference); training adds the NCCL gradient all-reduce overlapped with backward.
+Timing: CUDA events around K steps after W warm-up steps, inputs rotate over 4 batches (working set >> L2),
+max over ranks; `e2e` repeats the measurement from pinned HOST buffers with H2D / D2H copies inside the timed
+region; `roofline` times the conv-family kernels with CUDA events right around their launches.
 """
 import argparse
 import json
@@ -25,6 +30,8 @@ CTOR = (23, 828, 64, 8, 64, 96, 2)           # conf/config.yaml:18-20,49-51; out
 KW = dict(temporal_embeddings=False, metadata_embeddings=True)
 # BASELINE.json configs[] -> (model_type, ctor kwargs, workload, per-GPU batch, shared maps, description)
 CONFIGS = {
+    1: ("unet", dict(temporal_embeddings=False, metadata_embeddings=False), "infer", 8, False,
+        "standard no-embedding U-Net inference, fp32 parity mode (FFMA convolutions), synthetic 23x250x250 tiles"),
     2: ("unet", dict(temporal_embeddings=False, metadata_embeddings=True), "infer", 16, False,
         "Metadata-Augmented U-Net (metadata MLP fused at bottleneck) inference, synthetic 23x250x250 tiles"),
     3: ("unet", dict(temporal_embeddings=False, metadata_embeddings=True), "train", 16, False,
@@ -196,6 +203,9 @@ def main():
         model = mau_b200.UrbanPredictor(mt, *CTOR, **kw)
         O.perturb_bn_stats(model.state_dict())
         model = model.to(dev)
+        fp32_mode = cfg_id == 1          # configs[0]: the reference's own fp32 case -> the 1e-5 parity mode of the engine
+        if fp32_mode:
+            model.set_precision("fp32")
         model.train(train)
         if train and world > 1:
             from mau_b200 import parallel
@@ -358,9 +368,12 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # from the committed ncu --set full captures
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(f"config{cfg_id}", {}).get("dram_bytes_per_launch")
-        roof = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["src"],
-                "kernel": "conv3x3_tc_v2_kernel (+wgrad3x3_tc_v2_kernel in training)",
+        peak_tf, peak_src, kname = pk["tf_sustained"], pk["src"], "conv3x3_tc_v2_kernel (+wgrad3x3_tc_v2_kernel in training)"
+        if fp32_mode:      # FFMA path: 148 SMs x 128 lanes x 2 FLOP x 1.965 GHz (nominal; no measured fp32 peak on file)
+            peak_tf, peak_src, kname = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA", "conv3x3_ffma_kernel"
+        roof = {"bound": "tensor" if not fp32_mode else "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                "kernel": kname,
                 "launches_timed": conv_n // reps, "avg_launch_us": conv_ms / max(conv_n, 1) * 1e3,
                 "flop_per_launch": kern_flops * reps / max(conv_n, 1),
                 "conv_share_of_step": conv_ms / all_ms if all_ms else None,
@@ -368,7 +381,7 @@ def main():
 
         out = {"metric": metric, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": steps,
                "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "vs_baseline": None, "dtype": "f32" if fp32_mode else "bf16", "data": "synthetic",
                "config": {"workload": workload_name, "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_gpu": B,
                           "global_batch": B * world, "parallelism": f"dp{world}",
                           "l2": "4 rotating input batches (368 MB) + ~2 GB of activations per step: working set > 126 MB L2"},
