@@ -143,11 +143,23 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(DView z, const float
   }
 }
 
+// mean / biased variance in double (the subtraction cancels), inverse standard deviation in fp32 like ATen's
+// batch_norm (FP64 divide / sqrt per thread were the dominant cost of the small late layers)
+__device__ __forceinline__ void bn_coeffs(const double* __restrict__ sums, int C, int c, double inv_n, float eps, float& mean,
+                                          float& var, float& rstd) {
+  const double m = sums[c] * inv_n;
+  double v = sums[C + c] * inv_n - m * m;
+  if (v < 0.0) v = 0.0;
+  mean = (float)m;
+  var = (float)v;
+  rstd = rsqrtf(var + eps);
+}
+
 // training forward, one launch: every thread derives mean / rstd / scale / shift of its 8 channels from the
 // (already all-reduced, if SyncBN) double sums; block 0 also writes the saved statistics for the backward and
 // performs the running-stat update (momentum, unbiased variance) -- then the normalise + ReLU pass.
 template <typename T>
-__global__ void __launch_bounds__(256) bn_finalize_apply_relu_kernel(DView z, const double* __restrict__ sums, long long count,
+__global__ void __launch_bounds__(256) bn_finalize_apply_relu_kernel(DView z, const double* __restrict__ sums, long long count, double inv_n,
                                                                      const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, float eps, float momentum,
                                                                      float* __restrict__ rm, float* __restrict__ rv,
@@ -157,20 +169,17 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_relu_kernel(DView z, co
   using Raw = typename V8<T>::Raw;
   const int C = z.C;
   if (blockIdx.x == 0) {
+    const float unbias = count > 1 ? (float)((double)count / ((double)count - 1.0)) : 1.f;
     for (int c = threadIdx.x; c < C; c += 256) {
-      const double n = (double)count;
-      const double mean = sums[c] / n;
-      double var = sums[C + c] / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      float mean, var, rstd;
+      bn_coeffs(sums, C, c, inv_n, eps, mean, var, rstd);
       const float sc = gamma[c] * rstd;
       scale_out[c] = sc;
-      shift_out[c] = beta[c] - (float)mean * sc;
-      mean_out[c] = (float)mean;
+      shift_out[c] = beta[c] - mean * sc;
+      mean_out[c] = mean;
       rstd_out[c] = rstd;
-      const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
-      rm[c] = (1.f - momentum) * rm[c] + momentum * (float)mean;
-      rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+      rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
+      rv[c] = (1.f - momentum) * rv[c] + momentum * (var * unbias);
     }
   }
   const int G = C / 8;
@@ -181,13 +190,10 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_relu_kernel(DView z, co
 #pragma unroll
   for (int k = 0; k < 8; ++k) {       // same arithmetic as block 0 above, so every block uses identical coefficients
     const int c = gi * 8 + k;
-    const double n = (double)count;
-    const double mean = sums[c] / n;
-    double var = sums[C + c] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float mean, var, rstd;
+    bn_coeffs(sums, C, c, inv_n, eps, mean, var, rstd);
     sc[k] = gamma[c] * rstd;
-    sh[k] = beta[c] - (float)mean * sc[k];
+    sh[k] = beta[c] - mean * sc[k];
   }
   const long long npix = (long long)z.B * z.H * z.W;
   const long long stride = (long long)gridDim.x * L;
@@ -361,14 +367,14 @@ int op_bn_finalize_apply_relu(int dt, const View& z, const double* sums, long lo
                               cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(y) || z.C != y.C || z.pixels() != y.pixels()) return fail("bn_finalize_apply: bad views");
   const int L = std::max(1, 256 / (z.C / 8));
-  long long b = (z.pixels() + (long long)L * kU - 1) / ((long long)L * kU);
+  long long b = (z.pixels() + (long long)L * 16 - 1) / ((long long)L * 16);     // >= 16 pixels per thread amortise the coefficient set-up
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
   if (dt == DT_BF16)
-    bn_finalize_apply_relu_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(z), sums, count, gamma, beta, eps, momentum, running_mean,
+    bn_finalize_apply_relu_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(z), sums, count, 1.0 / (double)count, gamma, beta, eps, momentum, running_mean,
                                                                        running_var, scale, shift, save_mean, save_rstd, dv(y));
   else
-    bn_finalize_apply_relu_kernel<float><<<(int)b, 256, 0, st>>>(dv(z), sums, count, gamma, beta, eps, momentum, running_mean,
+    bn_finalize_apply_relu_kernel<float><<<(int)b, 256, 0, st>>>(dv(z), sums, count, 1.0 / (double)count, gamma, beta, eps, momentum, running_mean,
                                                                running_var, scale, shift, save_mean, save_rstd, dv(y));
   MAU_LAUNCHED();
   return 0;
@@ -377,7 +383,7 @@ int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, 
                      const float* rstd, double* sums, cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(gy)) return fail("bn_bwd_reduce: bad views");
   const size_t smem = 2 * 256 * 8 * sizeof(float);
-  const int blocks = reduce_blocks(z.pixels(), z.C);
+  const int blocks = std::min(reduce_blocks(z.pixels(), z.C), 148 * 2);      // 96 registers: 2 resident blocks per SM, one wave
   if (dt == DT_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, mean, rstd, sums);
   else               bn_bwd_reduce_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, mean, rstd, sums);
   MAU_LAUNCHED();
@@ -388,7 +394,7 @@ int op_bn_bwd_apply(int dt, const View& gy, const View& z, const float* scale, c
                     const double* param_sums, float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(dz_out)) return fail("bn_bwd_apply: bad views");
   const int L = std::max(1, 256 / (z.C / 8));
-  long long b = (z.pixels() + (long long)L * kU - 1) / ((long long)L * kU);
+  long long b = (z.pixels() + (long long)L * 16 - 1) / ((long long)L * 16);     // >= 16 pixels per thread amortise the coefficient set-up
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
   if (dt == DT_BF16)
