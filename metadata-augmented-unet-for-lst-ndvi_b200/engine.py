@@ -311,6 +311,7 @@ class HotPathFn(torch.autograd.Function):
         # plan kept from this forward: keep the tensors alive until then
         ctx.keep_alive = (maps, series, md, state)
         ctx.shapes = [p.shape for p in diff_params]
+        ctx.params = diff_params if dp is not None else None
         return out
 
     @staticmethod
@@ -318,7 +319,7 @@ class HotPathFn(torch.autograd.Function):
         plan: Plan = ctx.plan
         grad_out = grad_out.contiguous().float()
         if ctx.dp is not None:        # data parallel: grads are views of one flat buffer, all-reduced
-            grads_full, outs = ctx.dp.make_grads(plan, ctx.diff_idx, ctx.shapes)   # from inside backward
+            grads_full, outs = ctx.dp.make_grads(plan, ctx.diff_idx, ctx.shapes, ctx.params)   # from inside backward
             plan.backward(grad_out, grads_full)
             ctx.dp.finish(plan)
             return (None, None, None, None, None, None, None, *outs)

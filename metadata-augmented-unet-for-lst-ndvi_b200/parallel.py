@@ -102,10 +102,19 @@ class DataParallel:
         plan._sync_installed = True
 
     # called by engine.HotPathFn.backward ---------------------------------------------------
-    def make_grads(self, plan: "engine.Plan", diff_idx: List[int], shapes) -> Tuple[List[Optional[torch.Tensor]], list]:
+    def make_grads(self, plan: "engine.Plan", diff_idx: List[int], shapes, params=None) -> Tuple[List[Optional[torch.Tensor]], list]:
         """Gradient tensors are views of one flat buffer laid out in state order, so a layer's
-        (weight, bias, gamma, beta) -- contiguous state indices -- is one contiguous slice."""
+        (weight, bias, gamma, beta) -- contiguous state indices -- is one contiguous slice.
+
+        Autograd may install such a view as ``param.grad`` without copying.  If a caller keeps gradients across
+        backward passes (gradient accumulation, ``zero_grad(set_to_none=False)``), the next pass would overwrite
+        them in place, so any ``.grad`` that still aliases the flat buffer is detached into its own storage first."""
         cache = getattr(plan, "_dp_cache", None)
+        if cache is not None and params is not None:
+            base = cache["flat"].untyped_storage().data_ptr()
+            for p in params:
+                if p.grad is not None and p.grad.untyped_storage().data_ptr() == base:
+                    p.grad = p.grad.clone()
         if cache is None or cache["idx"] != list(diff_idx):
             offs, total = {}, 0
             for i, shp in zip(diff_idx, shapes):

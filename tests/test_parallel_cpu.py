@@ -93,3 +93,29 @@ def test_data_parallel_broadcast_and_buffer_sync_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_flat_gradient_views_are_detached_before_reuse():
+    """DataParallel hands autograd views of one flat buffer; a gradient kept across backward passes must not be
+    overwritten by the next pass (host logic of make_grads, exercised with a stand-in plan on CPU)."""
+    import mau_b200  # noqa: F401
+    from mau_b200.parallel import DataParallel
+
+    class _Plan:
+        device = torch.device("cpu")
+        num_state = 3
+        def set_grad_hook(self, fn):
+            self.hook = fn
+
+    dp = DataParallel.__new__(DataParallel)
+    dp.group, dp.bucket_numel, dp.sync_bn = None, 1 << 20, False
+    plan = _Plan()
+    params = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(2, 3))]
+    full, outs = dp.make_grads(plan, [0, 2], [p.shape for p in params], params)
+    assert full[1] is None and outs[0].untyped_storage().data_ptr() == outs[1].untyped_storage().data_ptr()
+    outs[0].fill_(1.0); outs[1].fill_(2.0)
+    for p, g in zip(params, outs):
+        p.grad = g                                   # what autograd does when it steals the incoming gradient
+    full2, outs2 = dp.make_grads(plan, [0, 2], [p.shape for p in params], params)
+    outs2[0].fill_(5.0); outs2[1].fill_(7.0)         # the next backward writes into the flat buffer ...
+    assert torch.all(params[0].grad == 1.0) and torch.all(params[1].grad == 2.0)   # ... kept gradients survive
