@@ -524,3 +524,47 @@ def test_unetpp_embedding_backward_closed_form_equals_dense(precision, tol, monk
         d = grads["2048"][k]
         gn = float(d.norm())
         assert float((g - d).norm()) <= tol * gn + 1e-6, (k, float((g - d).norm()), gn)
+
+
+@pytest.mark.parametrize("case", [
+    # (model_type, base_filters, B, H, W, T, meta_features, out_channels, temporal_dim, meta_dim, lstm_dim, kwargs)
+    ("unet", 8, 1, 16, 16, 5, 4, 2, 16, 8, 32, dict(temporal_embeddings=True, metadata_embeddings=True)),     # minimum tile, legacy 4 features
+    ("unet", 8, 2, 17, 31, 1, 8, 1, 8, 8, 32, dict(temporal_embeddings=True, metadata_embeddings=False)),      # T = 1, one output channel (no tanh)
+    ("unet", 32, 5, 48, 20, 12, 8, 3, 16, 16, 64, dict(temporal_embeddings=False, metadata_embeddings=False)),  # H != W, three outputs
+    ("unet++", 8, 1, 16, 23, 3, 4, 2, 8, 8, 32, dict()),                                                       # U-Net++ at the minimum height
+    ("unet++", 16, 2, 40, 40, 9, 8, 1, 24, 8, 96, dict()),                                                     # uneven embedding widths
+])
+def test_unusual_shapes_eval_and_train_fp32(case):
+    """Edge cases of the module contract (H, W >= 16 arbitrary, B >= 1, T >= 1, meta_features in {4, 8},
+    any out_channels / dims): eval output and one training step in fp32 mode against the oracle, eval in bf16."""
+    mt, bf, B, H, W, T, mf, oc, td, md_, ld, kw = case
+    torch.manual_seed(31)
+    m = mau_b200.UrbanPredictor(mt, 23, 828, td, mf, md_, ld, oc, base_filters=bf, **kw)
+    O.perturb_bn_stats(m.state_dict())
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, 23, H, W, generator=g); ts = torch.randn(B, T, generator=g); md = torch.randn(B, mf, generator=g)
+    tgt = torch.randn(B, oc, H, W, generator=g)
+    ref = O.forward(sd, mt, x, ts, md, training=False, **kw)
+    m = m.cuda()
+    with torch.no_grad():
+        y32 = m.set_precision("fp32").eval()(x.cuda(), ts.cuda(), md.cuda())
+        y16 = m.set_precision("bf16").eval()(x.cuda(), ts.cuda(), md.cuda())
+    assert y32.shape == ref.shape
+    assert rel(y32, ref) < 2e-5 and rel(y16, ref) < 2e-2
+    if B * (H // 16) * (W // 16) < 8:
+        return               # a handful of values per channel at the bottleneck: train-mode BatchNorm is degenerate there
+    m.set_precision("fp32").train()
+    out = m(x.cuda(), ts.cuda(), md.cuda())
+    loss = engine.compute_loss_mse_gradient(out, tgt.cuda(), 0.0)["total"]
+    loss.backward()
+    torch.cuda.synchronize()
+    oref, lref, grads, _ = O.train_step_grads(sd, mt, x, ts, md, tgt, loss="mse", **kw)
+    assert rel(out.detach(), oref) < 1e-4
+    assert abs(float(loss) - float(lref)) < 1e-4 * abs(float(lref)) + 1e-7
+    for n, p in m.named_parameters():
+        if grads[n] is None:
+            assert p.grad is None, n
+            continue
+        gn = float(grads[n].norm())
+        assert float((p.grad.cpu() - grads[n]).norm()) <= 2e-2 * gn + 2e-6, n
