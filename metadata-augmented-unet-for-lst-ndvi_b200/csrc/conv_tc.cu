@@ -593,6 +593,281 @@ int launch_v2(const ConvTcOp& op, cudaStream_t st) {
   return 0;
 }
 
+// ==========================================================================================
+// v3 ("col3"): Cout = 64 layers.  An M = 128, N = 64 MMA reads 6 KB of shared memory for 32 clocks of tensor work
+// (192 B/clk against ~85 sustained): the v2 kernel runs those layers at 35-38 % tensor-pipe activity.  Here the
+// three HORIZONTAL taps of a filter row are folded into N: one MMA  D[128 px, 192] += A(row r) * [W(r,0)|W(r,1)|W(r,2)]
+// uses the same A window for all three, so A is read 3 instead of 9 times per chunk (10 KB per 96 clocks).  The
+// accumulator group s holds  D_s[h, w] = sum_{r,k} X[h+r-1, w] * W[k, co, (r,s)]  (input column = centre column), and
+//     Y[h, w] = D_0[h, w-1] + D_1[h, w] + D_2[h, w+1]
+// is formed in the epilogue with two lane shuffles (a tile is 8 rows x 16 columns, a warp owns two tile rows).
+// Columns 0 and 15 of a tile have no neighbour in the tile: tiles overlap by two columns (14 valid columns).  The A
+// operand needs no horizontal halo: TMA box {64 ch, 16, 10}, row pitch 2048 B, the three vertical taps are the
+// 1024-byte-aligned windows starting at halo rows 0, 1, 2.  With Cout = 64 the [9][64][Kp] weight pack *is*
+// [3][192][Kp], so no second pack exists.
+// ==========================================================================================
+constexpr int kC3ABytes = 160 * 128;      // {64, 16, 10} bf16
+constexpr int kC3BBytes = 192 * 128;      // 192 n x 64 k
+constexpr int kC3Stg = 16384;             // 112 valid pixels x 128 B (padded)
+
+template <int NA, int NB>
+struct V3Smem {
+  static constexpr int kBars = 2 * NA + 2 * NB + 4;
+  static constexpr size_t kBytes = 1024 + (size_t)NA * kC3ABytes + (size_t)NB * kC3BBytes + 2 * kC3Stg + 8 * kBars + 32 +
+                                   (2 + 4) * 64 * sizeof(float);
+};
+
+template <int NA, int NB, int EM>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                     const __grid_constant__ CUtensorMap tmY,
+                                                                     const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NA * kC3ABytes;
+  uint8_t* sStg = sB + NB * kC3BBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * kC3Stg);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + NA;
+  uint64_t* fullB = emptyA + NA;
+  uint64_t* emptyB = fullB + NB;
+  uint64_t* tmem_full = emptyB + NB;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_scale = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~uintptr_t(15));
+  float* s_shift = s_scale + 64;
+  float* s_hw = s_shift + 64;            // [4][64] fused head weights (EM == 3)
+  constexpr int kHeadOC = 4;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_img = p.tiles_w * p.tiles_h;
+  const int total_items = p.total_ptiles;
+  int total_chunks = 0;
+  for (int s = 0; s < p.nseg; ++s) total_chunks += p.seg_chunks[s];
+  const bool resident = 3 * total_chunks <= NB;     // all weight tiles fit the B stages: load them once per CTA
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA); prefetch_tensormap(&tmB); prefetch_tensormap(&tmY);
+    for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    Ring ra, rb;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int b = it / tiles_img;
+      const int rem = it - b * tiles_img;
+      const int th = rem / p.tiles_w;
+      const int w0 = (rem - th * p.tiles_w) * 14 - 1, h0 = th * 8 - 1;     // top-left of the input window
+      const bool load_b = !resident || it == (int)blockIdx.x;
+      int kB = 0;
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        for (int kc = 0; kc < p.seg_chunks[sg]; ++kc, kB += 64) {
+          const int cA = p.seg_start[sg] + kc * 64;
+          mbar_wait(&emptyA[ra.stage], ra.phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&fullA[ra.stage], kC3ABytes);
+            tma_load_4d(sA + ra.stage * kC3ABytes, &tmA, &fullA[ra.stage], cA, w0, h0, b);
+          }
+          __syncwarp();
+          ra.advance(NA);
+          if (load_b) {
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(&emptyB[rb.stage], rb.phase ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&fullB[rb.stage], kC3BBytes);
+                tma_load_3d(sB + rb.stage * kC3BBytes, &tmB, &fullB[rb.stage], kB, 0, r);
+              }
+              __syncwarp();
+              rb.advance(NB);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = idesc_bf16_f32(128, 192, 0, 0);
+    const uint64_t descA0 = smem_desc_sw128(0, 16, 1024, 0);
+    const uint64_t descB0 = smem_desc_sw128(0, 16, 1024, 0);
+    Ring ra, rb;
+    int buf = 0;
+    uint32_t ephase[2] = {0, 0};
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const bool wait_b = !resident || it == (int)blockIdx.x;
+      mbar_wait(&tmem_empty[buf], ephase[buf] ^ 1);
+      ephase[buf] ^= 1;
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + buf * 192;
+      if (resident) { rb.stage = 0; }
+      for (int chunk = 0; chunk < total_chunks; ++chunk) {
+        mbar_wait(&fullA[ra.stage], ra.phase);
+        const uint32_t a_stage = smem_u32(sA + ra.stage * kC3ABytes);
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+          if (wait_b) mbar_wait(&fullB[rb.stage], rb.phase);
+          tc_fence_after();
+          const uint64_t db = descB0 + (uint64_t)(smem_u32(sB + rb.stage * kC3BBytes) >> 4);
+          const uint64_t da = descA0 + (uint64_t)((a_stage + r * 2048) >> 4);      // halo rows r .. r+7
+          const uint32_t first = (chunk | r) ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d0, da + (uint64_t)((k * 32) >> 4), db + (uint64_t)((k * 32) >> 4), idesc, k ? 1u : first);
+            if (!resident) umma_commit(&emptyB[rb.stage]);
+            if (r == 2) umma_commit(&emptyA[ra.stage]);
+            if (r == 2 && chunk == total_chunks - 1) umma_commit(&tmem_full[buf]);
+          }
+          __syncwarp();
+          rb.advance(NB);
+        }
+        ra.advance(NA);
+      }
+      buf ^= 1;
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int hh = m >> 4, ww = m & 15;                 // position inside the 8 x 16 tile
+    const bool valid_col = ww >= 1 && ww <= 14;
+    const int ridx = hh * 14 + ww - 1;                  // row of the packed 8 x 14 staging tile
+    for (int i = et; i < 64; i += 128) {
+      const bool ok = i < p.Cout;
+      s_scale[i] = ok ? (p.scale ? p.scale[i] : 1.f) : 0.f;
+      s_shift[i] = ok ? (p.shift ? p.shift[i] : 0.f) : 0.f;
+      if (EM == 3)
+        for (int o = 0; o < kHeadOC; ++o) s_hw[o * 64 + i] = (ok && o < p.head_oc) ? p.head_w[o * p.Cout + i] : 0.f;
+    }
+    named_bar_sync(1, 128);
+    int buf = 0, stg = 0;
+    uint32_t fphase[2] = {0, 0};
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int b = it / tiles_img;
+      const int rem = it - b * tiles_img;
+      const int th = rem / p.tiles_w;
+      const int w0 = (rem - th * p.tiles_w) * 14, h0 = th * 8;            // first VALID output pixel of the tile
+      mbar_wait(&tmem_full[buf], fphase[buf]);
+      fphase[buf] ^= 1;
+      tc_fence_after();
+      uint8_t* sbuf = sStg + stg * kC3Stg;
+      if (p.store_y) {
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        named_bar_sync(1, 128);
+      }
+      float hacc[kHeadOC] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 192;
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v0[32], v1[32], v2[32];
+        tmem_ld_32x32(tcol + cb * 32, v0);
+        tmem_ld_32x32(tcol + 64 + cb * 32, v1);
+        tmem_ld_32x32(tcol + 128 + cb * 32, v2);
+        tmem_ld_wait();
+        reg_fence32(v0); reg_fence32(v1); reg_fence32(v2);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int c = cb * 32 + 4 * j4;
+          float y[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[4 * j4 + e]), 1);       // D_0[h, w-1]
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[4 * j4 + e]), 1);    // D_2[h, w+1]
+            y[e] = left + __uint_as_float(v1[4 * j4 + e]) + right;
+          }
+          if (EM == 1) {
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+            y[0] += sh.x; y[1] += sh.y; y[2] += sh.z; y[3] += sh.w;
+          } else if (EM >= 2) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+            y[0] = fmaf(y[0], sc.x, sh.x); y[1] = fmaf(y[1], sc.y, sh.y); y[2] = fmaf(y[2], sc.z, sh.z); y[3] = fmaf(y[3], sc.w, sh.w);
+          }
+          if (p.relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
+          __nv_bfloat162 ha = __floats2bfloat162_rn(y[0], y[1]), hb = __floats2bfloat162_rn(y[2], y[3]);
+          pk[2 * j4] = *reinterpret_cast<uint32_t*>(&ha);
+          pk[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&hb);
+          if (EM == 3) {
+            const float r0 = __low2float(ha), r1 = __high2float(ha), r2 = __low2float(hb), r3 = __high2float(hb);
+#pragma unroll
+            for (int o = 0; o < kHeadOC; ++o) {
+              const float4 hw = *reinterpret_cast<const float4*>(s_hw + o * 64 + c);
+              hacc[o] = fmaf(r3, hw.w, fmaf(r2, hw.z, fmaf(r1, hw.y, fmaf(r0, hw.x, hacc[o]))));
+            }
+          }
+        }
+        if (p.store_y && valid_col) {
+          uint8_t* rowp = sbuf + ridx * 128;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int chunk16 = cb * 4 + jj;
+            *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (ridx & 7)) << 4)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      if (p.store_y) fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        mbar_arrive(&tmem_empty[buf]);
+        if (p.store_y) {
+          tma_store_4d(&tmY, sbuf, 0, w0, h0, b);
+          tma_commit_group();
+        }
+      }
+      if (p.store_y) stg ^= 1;
+      if (EM == 3) {
+        const int h = h0 + hh, w = w0 + ww - 1;
+        if (valid_col && h < p.H && w < p.W) {
+#pragma unroll
+          for (int o = 0; o < kHeadOC; ++o)
+            if (o < p.head_oc) {
+              float v = hacc[o] + p.head_b[o];
+              if (p.head_tanh && o == 0) v = tanhf(v);
+              p.head_out[(((long long)b * p.head_oc + o) * p.H + h) * p.W + w] = v;
+            }
+        }
+      }
+      buf ^= 1;
+    }
+    if (et == 0) tma_wait_group0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NA, int NB, int EM>
+int launch_col3(const ConvTcOp& op, cudaStream_t st) {
+  using S = V3Smem<NA, NB>;
+  static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = conv3x3_tc_col3_kernel<NA, NB, EM>;
+  if (!attr_done[dev & 15]) {
+    MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    attr_done[dev & 15] = true;
+  }
+  kern<<<op.grid, kThreads, S::kBytes, st>>>(op.tmA, op.tmB, op.tmY, op.p);
+  MAU_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> [9][N][Kp] bf16
 // fwd : out[t][n][kp] = W[n][kmap[kp]][t]            (kmap = -1 -> 0)
@@ -724,13 +999,20 @@ static int prepare_impl(ConvTcOp* op, const View& xbuf, int nseg, const int* seg
     }
   }
   op->bres = 0;
-  if (mode == MODE_HALO && op->bn == 64 && y.C <= 64 && Kp == 64 && !getenv("MAU_CONV_CFG") && !getenv("MAU_NO_BRES")) {
+  op->col3 = 0;
+  // (measured: with a single K chunk the three-accumulator epilogue -- 3 tcgen05.ld + 2 shuffles per output -- costs
+  //  more than the saved operand traffic, 104 vs 96 us on the 64 -> 64 layers; from two chunks up col3 wins, 199 vs 240 us
+  //  at K = 192)
+  if (mode == MODE_HALO && !bt && y.C == 64 && Kp >= 128 && !accumulate && !getenv("MAU_CONV_CFG") && !getenv("MAU_NO_COL3")) {
+    op->col3 = 1; op->bn = 64; op->mt = 1; op->nbuf = 2;
+  } else if (mode == MODE_HALO && op->bn == 64 && y.C <= 64 && Kp == 64 && !getenv("MAU_CONV_CFG") && !getenv("MAU_NO_BRES")) {
     op->bres = 1; op->mt = 2; op->nbuf = 2;
   }
   p.TW = (mode == MODE_TAP) ? 16 : 8;
   p.TH = 128 / p.TW;
   p.tiles_w = ceil_div(y.W, p.TW);
   p.tiles_h = ceil_div(y.H, p.TH);
+  if (op->col3) { p.TW = 14; p.TH = 8; p.tiles_w = ceil_div(y.W, 14); p.tiles_h = ceil_div(y.H, 8); }
   p.Cout = y.C;
   p.nseg = nseg;
   int chunks = 0;
@@ -758,6 +1040,7 @@ static int prepare_impl(ConvTcOp* op, const View& xbuf, int nseg, const int* seg
   int bw = p.TW, bh = p.TH;
   if (mode == MODE_ROW3) { bw = 8; bh = p.TH + 2; }
   if (mode == MODE_HALO) { bw = 10; bh = p.TH + 2; }
+  if (op->col3) { bw = 16; bh = 10; }
   MAU_TRY(make_nhwc_map(&op->tmA, DT_BF16, xa, 64, bw, bh));
   // B: packed weights {Kp, n_rows, 9}; dgrad (bt) reads {64 ci, 64 co} boxes of the forward pack instead
   p.bt = bt; p.bt_col0 = bt_col0;
@@ -765,6 +1048,11 @@ static int prepare_impl(ConvTcOp* op, const View& xbuf, int nseg, const int* seg
     uint64_t dims[3] = {(uint64_t)bt_kp_fwd, (uint64_t)n_rows, 9};
     uint64_t str[2] = {(uint64_t)bt_kp_fwd * 2, (uint64_t)bt_kp_fwd * 2 * (uint64_t)n_rows};
     uint32_t box[3] = {64, 64, 1};
+    MAU_TRY(make_tensor_map(&op->tmB, DT_BF16, 3, const_cast<void*>(wpacked), dims, str, box, true));
+  } else if (op->col3) {     // [9][64][Kp] == [3][192][Kp]: one box per filter row holds its three horizontal taps
+    uint64_t dims[3] = {(uint64_t)Kp, 192, 3};
+    uint64_t str[2] = {(uint64_t)Kp * 2, (uint64_t)Kp * 2 * 192};
+    uint32_t box[3] = {64, 192, 1};
     MAU_TRY(make_tensor_map(&op->tmB, DT_BF16, 3, const_cast<void*>(wpacked), dims, str, box, true));
   } else {
     uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)n_rows, 9};
@@ -798,6 +1086,12 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
       if (em == 1) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 1>(op, st);                \
       if (em == 2) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 2>(op, st);                \
       if constexpr (BN_ <= 128) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 3>(op, st);   \
+    }
+    if (op.col3) {          // Cout == 64: three horizontal taps folded into N = 192
+      if (em == 0) return launch_col3<3, 4, 0>(op, st);
+      if (em == 1) return launch_col3<3, 4, 1>(op, st);
+      if (em == 2) return launch_col3<3, 4, 2>(op, st);
+      return launch_col3<3, 4, 3>(op, st);
     }
     if (op.bres) {          // 64-wide, K = 64: weights resident in 9 B stages, MT = 2
       if (op.p.bt) return launch_v2<64, 2, 2, 2, 9, 2, true, 0, true>(op, st);

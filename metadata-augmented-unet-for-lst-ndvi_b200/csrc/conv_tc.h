@@ -36,6 +36,7 @@ struct ConvTcOp {
   int mode = 0;
   int mt = 1;      // v2: 128-pixel sub-tiles per work item (share each B tile)
   int nbuf = 2;    // v2: TMEM accumulator buffers
+  int col3 = 0;    // v3: Cout == 64, the three horizontal taps folded into N = 192 (conv3x3_tc_col3_kernel)
   int bres = 0;    // v2: weights resident in shared memory for the whole launch (K = 64, one 64-wide N tile)
 };
 
