@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self.stop_flag:
             self.sample()
-            time.sleep(0.005)
+            time.sleep(0.02)      # NVML queries take milliseconds and contend with the launching thread: keep them sparse
 
     def summary(self):
         s = sorted(self.samples)
