@@ -118,6 +118,8 @@ class _EngineNet(nn.Module):
         if min(H, W) < 16:
             raise RuntimeError("tile edge must be >= 16 (four 2x2 poolings)")
         T = int(temp_series.shape[1]) if temp_series.dim() == 2 else 0
+        if not self._cfg["temporal_embeddings"]:
+            T = 0            # the series is ignored (src/model.py:263): do not key plans (and their workspaces) on its length
         # Sensitivity sweep (reference test/metadata_sensitivity.py:294-311): every row carries the same tile
         # and series, only the metadata differs.  Detected for free when the caller passes batch-expanded
         # views (stride 0 on dim 0, e.g. ``x.expand(50, -1, -1, -1)``), or asserted by the caller with
