@@ -245,7 +245,10 @@ class Plan:
                                    "(keep the module in fp32; precision is chosen by set_precision)")
 
     def forward(self, state, maps, series, md, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        self._check_state(state)
+        key = tuple(t.data_ptr() for t in state)
+        if key != getattr(self, "_validated", None):       # same memory as last time: shapes / dtypes were checked then
+            self._check_state(state)
+            self._validated = key
         if not self.cfg.get("training"):
             # 1 + sum of in-place modification counters: unchanged state => packed weights are reused
             lib().mau_plan_set_state_version(self._h, 1 + sum(t._version for t in state))

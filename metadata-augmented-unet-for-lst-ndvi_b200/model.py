@@ -74,8 +74,22 @@ class _EngineNet(nn.Module):
 
     # ------------------------------------------------------------------ #
     def _state_tensors(self) -> List[torch.Tensor]:
-        # state_dict order == registration order (parameters and buffers interleaved per module)
-        return list(self.state_dict(keep_vars=True).values())
+        """The tensors of ``state_dict()`` in its order (per module: parameters, persistent buffers, then the
+        sub-modules in registration order) without building the prefixed key dictionary (4x cheaper per call)."""
+        out: List[torch.Tensor] = []
+
+        def walk(mod):
+            for p in mod._parameters.values():
+                if p is not None:
+                    out.append(p)
+            for k, b in mod._buffers.items():
+                if b is not None and k not in mod._non_persistent_buffers_set:
+                    out.append(b)
+            for c in mod._modules.values():
+                if c is not None:
+                    walk(c)
+        walk(self)
+        return out
 
     def _plan_for(self, B: int, H: int, W: int, T: int, training: bool, device: torch.device, shared: bool = False):
         key = (B, H, W, T, bool(training), self.precision, device.index, bool(shared))

@@ -203,3 +203,14 @@ def test_fused_adamw_has_no_cpu_fallback_and_torch_state_layout():
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         opt.step()
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_state_tensor_walk_matches_state_dict_order(name):
+    """The engine receives the state as a pointer array in state_dict order; the module collects it with a direct
+    walk over parameters / persistent buffers: it must be the state_dict's tensors, in its order, by identity."""
+    mt, kw = VARIANTS[name]
+    m = mau_b200.UrbanPredictor(mt, 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw)
+    a = m.model._state_tensors()
+    b = list(m.model.state_dict(keep_vars=True).values())
+    assert len(a) == len(b) and all(x is y for x, y in zip(a, b))
