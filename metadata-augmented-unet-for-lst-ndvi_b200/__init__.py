@@ -6,5 +6,6 @@ constructor, ``forward(maps, temp_series, metadata)`` and ``state_dict`` layout)
 from .model import UrbanPredictor, UrbanPredictor_unet, UrbanPredictor_unetpp  # noqa: F401
 from . import engine  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
+from . import data  # noqa: F401  (mirror of reference src/dataset.py on the native tile reader)
 
-__all__ = ["UrbanPredictor", "UrbanPredictor_unet", "UrbanPredictor_unetpp", "engine", "FusedAdamW"]
+__all__ = ["UrbanPredictor", "UrbanPredictor_unet", "UrbanPredictor_unetpp", "engine", "FusedAdamW", "data"]

@@ -1,4 +1,5 @@
-"""Build libmau_b200.so in-tree with nvcc for sm_100a (no torch headers, no libcuda link)."""
+"""Build libmau_b200.so in-tree with nvcc for sm_100a (no torch headers, no libcuda link) and the host-only
+libmau_tiles.so (tile reader, g++ + zlib)."""
 import concurrent.futures as cf
 import os
 import subprocess
@@ -8,6 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(SRC, "obj")
 LIB = os.path.join(HERE, "libmau_b200.so")
+TILES_SRC = os.path.join(SRC, "tile_reader.cpp")
+TILES_LIB = os.path.join(HERE, "libmau_tiles.so")
+CXX = os.environ.get("CXX", "g++")
 SOURCES = ["common.cu", "tma.cu", "conv_tc.cu", "wgrad_tc.cu", "conv_ffma.cu", "elementwise.cu", "norm.cu",
            "encoders.cu", "loss.cu", "metrics.cu", "optim.cu", "embgrad.cu", "plan.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -48,7 +52,22 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_tiles(force=force)
     return LIB
+
+
+def build_tiles(force=False):
+    """Host-only tile reader (include/mau_tiles.h): g++ + zlib, no CUDA."""
+    hdr = os.path.join(HERE, "..", "include", "mau_tiles.h")
+    if force or _newer(TILES_SRC, TILES_LIB, [hdr]):
+        cmd = [CXX, "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-DNDEBUG", TILES_SRC, "-o", TILES_LIB,
+               "-lz", "-pthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {TILES_SRC}:\n{r.stdout}\n{r.stderr}")
+        if r.stderr.strip():
+            print(r.stderr, file=sys.stderr)
+    return TILES_LIB
 
 
 if __name__ == "__main__":

@@ -1,0 +1,733 @@
+// tile_reader.cpp -- native reader of the reference's per-sample .npz archives (include/mau_tiles.h).
+//
+// One sample = one ZIP written by np.savez_compressed (reference src/data/processing_10m/process.py:187)
+// with the members input.npy [23,H,W], target.npy [2,H,W], metadata.npy [4], temperature_serie.npy [T].
+// The reference reads it with np.load on the training thread (src/dataset.py:54-59) and stacks / pads the
+// batch in collate_fn (src/dataset.py:87-108).  Here a batch is decoded by a pool of worker threads straight
+// into the caller's (pinned) batch buffers: the archive is mmap'ed, the ZIP central directory gives the
+// member extents, each member is inflated directly into its slot of the batch (NPY header peeled off the
+// front of the same deflate stream), CRC-32 checked like zipfile does, optionally flipped in place.
+// Host-only: C++17, pthreads, zlib.
+#include "../../include/mau_tiles.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Fail {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Fail{code, buf};
+}
+
+inline uint16_t rd16(const uint8_t* p) { return uint16_t(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
+inline uint64_t rd64(const uint8_t* p) { return uint64_t(rd32(p)) | (uint64_t(rd32(p + 4)) << 32); }
+
+// ---- a read-only mapping of one archive ------------------------------------------------------------------
+struct Mapping {
+  const uint8_t* base = nullptr;
+  size_t size = 0;
+  std::string path;
+  explicit Mapping(const std::string& p) : path(p) {
+    int fd = ::open(p.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) fail(MAU_TILES_E_IO, "cannot open '%s': %s", p.c_str(), strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+      int e = errno;
+      ::close(fd);
+      fail(MAU_TILES_E_IO, "cannot stat '%s': %s", p.c_str(), strerror(e));
+    }
+    size = size_t(st.st_size);
+    if (size == 0) {
+      ::close(fd);
+      fail(MAU_TILES_E_FORMAT, "'%s' is empty (not a zip archive)", p.c_str());
+    }
+    void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    int e = errno;
+    ::close(fd);
+    if (m == MAP_FAILED) fail(MAU_TILES_E_IO, "cannot mmap '%s': %s", p.c_str(), strerror(e));
+    base = static_cast<const uint8_t*>(m);
+    madvise(m, size, MADV_SEQUENTIAL);
+  }
+  ~Mapping() {
+    if (base) munmap(const_cast<uint8_t*>(base), size);
+  }
+  Mapping(const Mapping&) = delete;
+  Mapping& operator=(const Mapping&) = delete;
+  const uint8_t* at(uint64_t off, uint64_t len) const {
+    if (off > size || len > size - off) fail(MAU_TILES_E_FORMAT, "'%s': truncated archive (need %llu bytes at %llu of %zu)", path.c_str(),
+                                             (unsigned long long)len, (unsigned long long)off, size);
+    return base + off;
+  }
+};
+
+// ---- ZIP central directory -------------------------------------------------------------------------------
+struct Member {
+  uint16_t method = 0;  // 0 stored, 8 deflate
+  uint32_t crc = 0;
+  uint64_t csize = 0, usize = 0;
+  const uint8_t* data = nullptr;  // first byte of the (compressed) payload
+  bool found = false;
+};
+
+enum { M_INPUT = 0, M_TARGET = 1, M_METADATA = 2, M_SERIES = 3, M_COUNT = 4 };
+const char* const kMemberNames[M_COUNT] = {"input.npy", "target.npy", "metadata.npy", "temperature_serie.npy"};
+
+void parse_zip(const Mapping& mp, Member out[M_COUNT]) {
+  const size_t n = mp.size;
+  if (n < 22) fail(MAU_TILES_E_FORMAT, "'%s' is not a zip archive (too short)", mp.path.c_str());
+  // end-of-central-directory record: last 22 bytes + up to 64 KiB of comment
+  size_t lo = n > 22 + 65535 ? n - 22 - 65535 : 0;
+  size_t eocd = size_t(-1);
+  for (size_t p = n - 22 + 1; p-- > lo;) {
+    if (rd32(mp.base + p) == 0x06054b50u) {
+      eocd = p;
+      break;
+    }
+  }
+  if (eocd == size_t(-1)) fail(MAU_TILES_E_FORMAT, "'%s' is not a zip archive (no end-of-central-directory record)", mp.path.c_str());
+  const uint8_t* e = mp.base + eocd;
+  uint64_t entries = rd16(e + 10), cd_size = rd32(e + 12), cd_off = rd32(e + 16);
+  if (entries == 0xFFFFu || cd_size == 0xFFFFFFFFu || cd_off == 0xFFFFFFFFu) {
+    // ZIP64: locator sits right in front of the EOCD record
+    if (eocd < 20 || rd32(mp.base + eocd - 20) != 0x07064b50u) fail(MAU_TILES_E_FORMAT, "'%s': zip64 locator missing", mp.path.c_str());
+    uint64_t z_off = rd64(mp.base + eocd - 20 + 8);
+    const uint8_t* z = mp.at(z_off, 56);
+    if (rd32(z) != 0x06064b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad zip64 end record", mp.path.c_str());
+    entries = rd64(z + 32);
+    cd_size = rd64(z + 40);
+    cd_off = rd64(z + 48);
+  }
+  const uint8_t* cd = mp.at(cd_off, cd_size);
+  uint64_t pos = 0;
+  for (uint64_t i = 0; i < entries; ++i) {
+    if (pos + 46 > cd_size || rd32(cd + pos) != 0x02014b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad central directory entry %llu", mp.path.c_str(), (unsigned long long)i);
+    const uint8_t* h = cd + pos;
+    uint16_t flags = rd16(h + 8), method = rd16(h + 10);
+    uint32_t crc = rd32(h + 16);
+    uint64_t csize = rd32(h + 20), usize = rd32(h + 24);
+    uint16_t nlen = rd16(h + 28), xlen = rd16(h + 30), clen = rd16(h + 32);
+    uint64_t lho = rd32(h + 42);
+    if (pos + 46 + uint64_t(nlen) + xlen + clen > cd_size) fail(MAU_TILES_E_FORMAT, "'%s': central directory overruns", mp.path.c_str());
+    const char* name = reinterpret_cast<const char*>(h + 46);
+    // zip64 extended information: present values in the order usize, csize, local header offset
+    const uint8_t* x = h + 46 + nlen;
+    for (uint32_t xp = 0; xp + 4 <= xlen;) {
+      uint16_t id = rd16(x + xp), sz = rd16(x + xp + 2);
+      if (xp + 4u + sz > xlen) break;
+      if (id == 0x0001) {
+        uint32_t q = xp + 4, qe = xp + 4 + sz;
+        if (usize == 0xFFFFFFFFu && q + 8 <= qe) { usize = rd64(x + q); q += 8; }
+        if (csize == 0xFFFFFFFFu && q + 8 <= qe) { csize = rd64(x + q); q += 8; }
+        if (lho == 0xFFFFFFFFu && q + 8 <= qe) { lho = rd64(x + q); q += 8; }
+      }
+      xp += 4u + sz;
+    }
+    for (int m = 0; m < M_COUNT; ++m) {
+      size_t L = strlen(kMemberNames[m]);
+      if (nlen == L && memcmp(name, kMemberNames[m], L) == 0) {
+        if (flags & 1) fail(MAU_TILES_E_FORMAT, "'%s': member %s is encrypted", mp.path.c_str(), kMemberNames[m]);
+        if (method != 0 && method != 8) fail(MAU_TILES_E_FORMAT, "'%s': member %s uses compression method %u (only stored/deflate)", mp.path.c_str(), kMemberNames[m], method);
+        const uint8_t* lh = mp.at(lho, 30);
+        if (rd32(lh) != 0x04034b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad local header of %s", mp.path.c_str(), kMemberNames[m]);
+        uint64_t start = lho + 30 + rd16(lh + 26) + rd16(lh + 28);
+        Member& M = out[m];  // duplicate names: zipfile keeps the last entry, so do we
+        M.method = method;
+        M.crc = crc;
+        M.csize = csize;
+        M.usize = usize;
+        M.data = mp.at(start, csize);
+        M.found = true;
+      }
+    }
+    pos += 46 + uint64_t(nlen) + xlen + clen;
+  }
+}
+
+// ---- sequential reader over one member (stored or raw deflate), CRC accumulated on the way ----------------
+class MemberStream {
+ public:
+  MemberStream(const Mapping& mp, const Member& m, const char* name, bool check_crc) : mp_(mp), m_(m), name_(name), check_crc_(check_crc) {
+    if (m.method == 8) {
+      memset(&z_, 0, sizeof z_);
+      if (inflateInit2(&z_, -15) != Z_OK) fail(MAU_TILES_E_FORMAT, "zlib inflateInit2 failed");
+      z_init_ = true;
+      in_left_ = m.csize;
+      z_.next_in = const_cast<Bytef*>(m.data);
+      z_.avail_in = 0;
+    }
+    crc_ = crc32(0L, Z_NULL, 0);
+  }
+  ~MemberStream() {
+    if (z_init_) inflateEnd(&z_);
+  }
+  MemberStream(const MemberStream&) = delete;
+  MemberStream& operator=(const MemberStream&) = delete;
+
+  void read(void* dst, uint64_t n) {
+    if (n > m_.usize - produced_) fail(MAU_TILES_E_FORMAT, "'%s': member %s is shorter than its NPY header says (%llu of %llu bytes)", mp_.path.c_str(), name_,
+                                       (unsigned long long)(m_.usize - produced_), (unsigned long long)n);
+    uint8_t* out = static_cast<uint8_t*>(dst);
+    if (m_.method == 0) {
+      memcpy(out, m_.data + produced_, n);
+    } else {
+      uint64_t left = n;
+      uint8_t* o = out;
+      while (left) {
+        if (z_.avail_in == 0 && in_left_) {
+          uInt take = uInt(std::min<uint64_t>(in_left_, 1u << 30));
+          z_.avail_in = take;
+          in_left_ -= take;
+        }
+        uInt want = uInt(std::min<uint64_t>(left, 1u << 30));
+        z_.next_out = o;
+        z_.avail_out = want;
+        int rc = inflate(&z_, Z_NO_FLUSH);
+        uInt got = want - z_.avail_out;
+        o += got;
+        left -= got;
+        if (rc == Z_STREAM_END) {
+          if (left) fail(MAU_TILES_E_FORMAT, "'%s': deflate stream of %s ends early", mp_.path.c_str(), name_);
+          break;
+        }
+        if (rc != Z_OK || (got == 0 && z_.avail_in == 0 && in_left_ == 0))
+          fail(MAU_TILES_E_FORMAT, "'%s': error while decompressing %s (%s)", mp_.path.c_str(), name_, z_.msg ? z_.msg : "truncated stream");
+      }
+    }
+    if (check_crc_) {
+      for (uint64_t p = 0; p < n;) {  // crc32() takes a 32-bit length
+        uInt c = uInt(std::min<uint64_t>(n - p, 1u << 30));
+        crc_ = crc32(crc_, out + p, c);
+        p += c;
+      }
+    }
+    produced_ += n;
+  }
+  void finish() {
+    if (produced_ != m_.usize) fail(MAU_TILES_E_FORMAT, "'%s': member %s holds %llu bytes, NPY header accounts for %llu", mp_.path.c_str(), name_,
+                                    (unsigned long long)m_.usize, (unsigned long long)produced_);
+    if (check_crc_ && uint32_t(crc_) != m_.crc) fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp_.path.c_str(), name_);
+  }
+
+ private:
+  const Mapping& mp_;
+  const Member& m_;
+  const char* name_;
+  bool check_crc_;
+  z_stream z_;
+  bool z_init_ = false;
+  uint64_t in_left_ = 0, produced_ = 0;
+  uLong crc_ = 0;
+};
+
+// ---- NPY header ------------------------------------------------------------------------------------------
+enum DType { F4, F8, F2, I1, U1, I2, U2, I4, U4, I8, U8, B1 };
+struct NpyHeader {
+  DType dtype = F4;
+  int itemsize = 4;
+  int ndim = 0;
+  int64_t shape[8] = {0};
+  int64_t count = 1;
+};
+
+bool find_key(const std::string& h, const char* key, size_t* value_pos) {
+  std::string k1 = std::string("'") + key + "'", k2 = std::string("\"") + key + "\"";
+  size_t p = h.find(k1);
+  if (p == std::string::npos) p = h.find(k2);
+  if (p == std::string::npos) return false;
+  p = h.find(':', p);
+  if (p == std::string::npos) return false;
+  ++p;
+  while (p < h.size() && (h[p] == ' ' || h[p] == '\t')) ++p;
+  *value_pos = p;
+  return true;
+}
+
+NpyHeader read_npy_header(MemberStream& s, const Mapping& mp, const char* name) {
+  uint8_t pre[12];
+  s.read(pre, 10);
+  if (memcmp(pre, "\x93NUMPY", 6) != 0) fail(MAU_TILES_E_FORMAT, "'%s': member %s is not an NPY array (object arrays / pickles are not supported)", mp.path.c_str(), name);
+  uint32_t hlen;
+  if (pre[6] == 1) {
+    hlen = rd16(pre + 8);
+  } else if (pre[6] == 2 || pre[6] == 3) {
+    s.read(pre + 10, 2);
+    hlen = rd32(pre + 8);
+  } else {
+    fail(MAU_TILES_E_FORMAT, "'%s': member %s has NPY format version %u.%u", mp.path.c_str(), name, pre[6], pre[7]);
+  }
+  if (hlen > (1u << 20)) fail(MAU_TILES_E_FORMAT, "'%s': member %s has an implausible NPY header (%u bytes)", mp.path.c_str(), name, hlen);
+  std::string h(hlen, '\0');
+  s.read(h.data(), hlen);
+  NpyHeader r;
+  size_t p;
+  if (!find_key(h, "descr", &p) || p >= h.size() || (h[p] != '\'' && h[p] != '"')) fail(MAU_TILES_E_DTYPE, "'%s': member %s: structured or missing dtype", mp.path.c_str(), name);
+  size_t q = h.find(h[p], p + 1);
+  if (q == std::string::npos) fail(MAU_TILES_E_FORMAT, "'%s': member %s: malformed descr", mp.path.c_str(), name);
+  std::string d = h.substr(p + 1, q - p - 1);
+  if (d.size() < 3) fail(MAU_TILES_E_DTYPE, "'%s': member %s has dtype '%s'", mp.path.c_str(), name, d.c_str());
+  char order = d[0];
+  std::string code = d.substr(1);
+  struct { const char* c; DType t; int sz; } table[] = {{"f4", F4, 4}, {"f8", F8, 8}, {"f2", F2, 2}, {"i1", I1, 1}, {"u1", U1, 1}, {"i2", I2, 2},
+                                                          {"u2", U2, 2}, {"i4", I4, 4}, {"u4", U4, 4}, {"i8", I8, 8}, {"u8", U8, 8}, {"b1", B1, 1}};
+  bool ok = false;
+  for (auto& t : table)
+    if (code == t.c) {
+      r.dtype = t.t;
+      r.itemsize = t.sz;
+      ok = true;
+    }
+  if (!ok || !(order == '<' || order == '|' || (order == '=') )) fail(MAU_TILES_E_DTYPE, "'%s': member %s has dtype '%s' (little-endian numeric types only)", mp.path.c_str(), name, d.c_str());
+  if (!find_key(h, "shape", &p) || p >= h.size() || h[p] != '(') fail(MAU_TILES_E_FORMAT, "'%s': member %s: malformed shape", mp.path.c_str(), name);
+  ++p;
+  while (p < h.size() && h[p] != ')') {
+    if (h[p] == ' ' || h[p] == ',') {
+      ++p;
+      continue;
+    }
+    if (h[p] < '0' || h[p] > '9' || r.ndim >= 8) fail(MAU_TILES_E_FORMAT, "'%s': member %s: malformed shape", mp.path.c_str(), name);
+    int64_t v = 0;
+    while (p < h.size() && h[p] >= '0' && h[p] <= '9') {
+      if (v > (int64_t(1) << 56)) fail(MAU_TILES_E_FORMAT, "'%s': member %s: shape overflow", mp.path.c_str(), name);
+      v = v * 10 + (h[p++] - '0');
+    }
+    if (p < h.size() && h[p] == 'L') ++p;  // Python 2 longs
+    r.shape[r.ndim++] = v;
+  }
+  if (p >= h.size()) fail(MAU_TILES_E_FORMAT, "'%s': member %s: malformed shape", mp.path.c_str(), name);
+  for (int i = 0; i < r.ndim; ++i) {
+    if (r.shape[i] && r.count > (int64_t(1) << 46) / std::max<int64_t>(r.shape[i], 1)) fail(MAU_TILES_E_FORMAT, "'%s': member %s: implausible shape", mp.path.c_str(), name);
+    r.count *= r.shape[i];
+  }
+  if (find_key(h, "fortran_order", &p) && h.compare(p, 4, "True") == 0 && r.ndim > 1)
+    fail(MAU_TILES_E_DTYPE, "'%s': member %s is Fortran-ordered", mp.path.c_str(), name);
+  return r;
+}
+
+inline float half_to_float(uint16_t h) {
+  uint32_t s = uint32_t(h & 0x8000u) << 16, e = (h >> 10) & 31u, m = h & 1023u, bits;
+  if (e == 0) {
+    if (m == 0) {
+      bits = s;
+    } else {  // subnormal
+      int sh = 0;
+      while (!(m & 1024u)) {
+        m <<= 1;
+        ++sh;
+      }
+      bits = s | ((113u - sh) << 23) | ((m & 1023u) << 13);
+    }
+  } else if (e == 31) {
+    bits = s | 0x7F800000u | (m << 13);
+  } else {
+    bits = s | ((e + 112u) << 23) | (m << 13);
+  }
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+
+template <typename T>
+void convert_run(const uint8_t* src, float* dst, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) {
+    T v;
+    memcpy(&v, src + i * sizeof(T), sizeof(T));
+    dst[i] = float(v);  // same rounding as Tensor.float(): round to nearest even
+  }
+}
+
+void convert(DType t, const uint8_t* src, float* dst, int64_t n) {
+  switch (t) {
+    case F4: memcpy(dst, src, size_t(n) * 4); break;
+    case F8: convert_run<double>(src, dst, n); break;
+    case F2:
+      for (int64_t i = 0; i < n; ++i) dst[i] = half_to_float(rd16(src + 2 * i));
+      break;
+    case I1: convert_run<int8_t>(src, dst, n); break;
+    case U1: convert_run<uint8_t>(src, dst, n); break;
+    case B1:
+      for (int64_t i = 0; i < n; ++i) dst[i] = src[i] ? 1.f : 0.f;
+      break;
+    case I2: convert_run<int16_t>(src, dst, n); break;
+    case U2: convert_run<uint16_t>(src, dst, n); break;
+    case I4: convert_run<int32_t>(src, dst, n); break;
+    case U4: convert_run<uint32_t>(src, dst, n); break;
+    case I8: convert_run<int64_t>(src, dst, n); break;
+    case U8: convert_run<uint64_t>(src, dst, n); break;
+  }
+}
+
+// payload of `count` elements -> fp32 at dst (direct inflate for f4, chunked conversion otherwise)
+void read_payload(MemberStream& s, const NpyHeader& h, float* dst) {
+  if (h.count == 0) return;
+  if (h.dtype == F4) {
+    s.read(dst, uint64_t(h.count) * 4);
+    return;
+  }
+  const int64_t chunk = 1 << 16;
+  std::vector<uint8_t> tmp(size_t(chunk) * h.itemsize);
+  for (int64_t done = 0; done < h.count;) {
+    int64_t n = std::min(chunk, h.count - done);
+    s.read(tmp.data(), uint64_t(n) * h.itemsize);
+    convert(h.dtype, tmp.data(), dst + done, n);
+    done += n;
+  }
+}
+
+void reverse_rows(float* p, int64_t rows, int64_t w) {  // np.flip(x, axis=2) of a [C,H,W] array, in place
+  for (int64_t r = 0; r < rows; ++r) std::reverse(p + r * w, p + (r + 1) * w);
+}
+
+// ---- the worker pool -------------------------------------------------------------------------------------
+class Pool {
+ public:
+  explicit Pool(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void push(std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      q_.push_back(std::move(f));
+    }
+    cv_.notify_one();
+  }
+  int size() const { return int(th_.size()); }
+
+ private:
+  void run() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;  // stop requested and drained
+        f = std::move(q_.front());
+        q_.pop_front();
+      }
+      f();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::deque<std::function<void()>> q_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  bool stop_ = false;
+};
+
+struct Batch {
+  std::vector<int64_t> idx;
+  std::vector<uint8_t> flip;
+  int64_t dims[8];
+  float *input, *target, *metadata, *series;
+  int64_t series_stride;
+  int64_t* series_len;
+  std::mutex mu;
+  std::condition_variable cv;
+  int64_t pending = 0;
+  int code = 0;
+  std::string msg;
+};
+
+}  // namespace
+
+struct mau_tiles {
+  std::vector<std::string> paths;
+  int flags = 0;
+  std::unique_ptr<Pool> pool;
+  std::mutex mu;
+  std::map<int64_t, std::shared_ptr<Batch>> inflight;
+  int64_t next_ticket = 1;
+  std::atomic<int64_t> payload_bytes{0}, archive_bytes{0}, samples{0};
+};
+
+namespace {
+
+// which members a task decodes: the `input` member is ~90 % of a sample, so it is its own task
+enum { PART_INPUT = 1, PART_REST = 2 };
+
+void decode_sample(mau_tiles* t, Batch* b, int64_t slot, int parts) {
+  const int64_t i = b->idx[size_t(slot)];
+  const bool flip = !b->flip.empty() && b->flip[size_t(slot)];
+  const bool crc = !(t->flags & MAU_TILES_FLAG_NO_CRC);
+  Mapping mp(t->paths[size_t(i)]);
+  Member mem[M_COUNT];
+  parse_zip(mp, mem);
+  int64_t bytes = 0;
+  auto need = [&](int m) -> const Member& {
+    if (!mem[m].found) fail(MAU_TILES_E_MEMBER, "'%s': '%.*s' is not a file in the archive", mp.path.c_str(), int(strlen(kMemberNames[m]) - 4), kMemberNames[m]);
+    return mem[m];
+  };
+  auto image = [&](int m, float* base, const int64_t* d) {
+    if (!base) return;
+    const Member& M = need(m);
+    MemberStream s(mp, M, kMemberNames[m], crc);
+    NpyHeader h = read_npy_header(s, mp, kMemberNames[m]);
+    if (h.ndim != 3 || h.shape[0] != d[0] || h.shape[1] != d[1] || h.shape[2] != d[2])
+      fail(MAU_TILES_E_SHAPE, "'%s': %s has shape (%lld,%lld,%lld)[ndim %d], the batch expects (%lld,%lld,%lld)", mp.path.c_str(), kMemberNames[m], (long long)h.shape[0],
+           (long long)h.shape[1], (long long)h.shape[2], h.ndim, (long long)d[0], (long long)d[1], (long long)d[2]);
+    float* dst = base + slot * h.count;
+    read_payload(s, h, dst);
+    s.finish();
+    if (flip) reverse_rows(dst, d[0] * d[1], d[2]);
+    bytes += h.count * h.itemsize;
+  };
+  if (parts & PART_INPUT) image(M_INPUT, b->input, b->dims);
+  if (parts & PART_REST) {
+    image(M_TARGET, b->target, b->dims + 3);
+    if (b->metadata) {
+      const Member& M = need(M_METADATA);
+      MemberStream s(mp, M, kMemberNames[M_METADATA], crc);
+      NpyHeader h = read_npy_header(s, mp, kMemberNames[M_METADATA]);
+      if (h.ndim != 1 || h.shape[0] != b->dims[6])
+        fail(MAU_TILES_E_SHAPE, "'%s': metadata has %lld values[ndim %d], the batch expects %lld", mp.path.c_str(), (long long)h.count, h.ndim, (long long)b->dims[6]);
+      read_payload(s, h, b->metadata + slot * b->dims[6]);
+      s.finish();
+      bytes += h.count * h.itemsize;
+    }
+    if (b->series) {
+      const Member& M = need(M_SERIES);
+      MemberStream s(mp, M, kMemberNames[M_SERIES], crc);
+      NpyHeader h = read_npy_header(s, mp, kMemberNames[M_SERIES]);
+      if (h.ndim != 1) fail(MAU_TILES_E_SHAPE, "'%s': temperature_serie has %d dimensions, expected 1", mp.path.c_str(), h.ndim);
+      if (h.count > b->series_stride) fail(MAU_TILES_E_CAPACITY, "'%s': temperature_serie has %lld values, buffer holds %lld", mp.path.c_str(), (long long)h.count, (long long)b->series_stride);
+      float* dst = b->series + slot * b->series_stride;
+      read_payload(s, h, dst);
+      s.finish();
+      std::fill(dst + h.count, dst + b->series_stride, 0.f);
+      if (b->series_len) b->series_len[slot] = h.count;
+      bytes += h.count * h.itemsize;
+    }
+    t->samples.fetch_add(1, std::memory_order_relaxed);
+    t->archive_bytes.fetch_add(int64_t(mp.size), std::memory_order_relaxed);
+  }
+  t->payload_bytes.fetch_add(bytes, std::memory_order_relaxed);
+}
+
+void run_task(mau_tiles* t, std::shared_ptr<Batch> b, int64_t slot, int parts) {
+  int code = 0;
+  std::string msg;
+  bool skip;
+  {
+    std::lock_guard<std::mutex> g(b->mu);
+    skip = b->code != 0;  // the batch already failed: do not spend time on its other samples
+  }
+  if (!skip) {
+    try {
+      decode_sample(t, b.get(), slot, parts);
+    } catch (const Fail& f) {
+      code = f.code;
+      msg = f.msg;
+    } catch (const std::exception& e) {
+      code = MAU_TILES_E_IO;
+      msg = e.what();
+    }
+  }
+  std::lock_guard<std::mutex> g(b->mu);
+  if (code && !b->code) {
+    b->code = code;
+    b->msg = msg;
+  }
+  if (--b->pending == 0) b->cv.notify_all();
+}
+
+int set_err(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+
+int guard(const std::function<int()>& f) {
+  try {
+    return f();
+  } catch (const Fail& e) {
+    return set_err(e.code, e.msg);
+  } catch (const std::exception& e) {
+    return set_err(MAU_TILES_E_IO, e.what());
+  } catch (...) {
+    return set_err(MAU_TILES_E_IO, "unknown error");
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mau_tiles_last_error(void) { return g_err.c_str(); }
+int mau_tiles_version(void) { return 1; }
+
+int mau_tiles_open(const char* const* paths, int64_t n, int threads, int flags, mau_tiles** out) {
+  return guard([&]() -> int {
+    if (!out || n < 0 || (n > 0 && !paths)) return set_err(MAU_TILES_E_ARG, "mau_tiles_open: null argument");
+    auto t = std::make_unique<mau_tiles>();
+    t->paths.reserve(size_t(n));
+    for (int64_t i = 0; i < n; ++i) {
+      if (!paths[i]) return set_err(MAU_TILES_E_ARG, "mau_tiles_open: null path");
+      t->paths.emplace_back(paths[i]);
+    }
+    t->flags = flags;
+    if (threads <= 0) {
+      long c = sysconf(_SC_NPROCESSORS_ONLN);
+      threads = c > 0 ? int(c) : 4;
+    }
+    t->pool = std::make_unique<Pool>(std::min(threads, 256));
+    *out = t.release();
+    return 0;
+  });
+}
+
+int mau_tiles_close(mau_tiles* t) {
+  return guard([&]() -> int {
+    if (!t) return 0;
+    t->pool.reset();  // drains the queue: buffers of in-flight batches are written before this returns
+    delete t;
+    return 0;
+  });
+}
+
+int64_t mau_tiles_count(const mau_tiles* t) { return t ? int64_t(t->paths.size()) : 0; }
+int mau_tiles_threads(const mau_tiles* t) { return t && t->pool ? t->pool->size() : 0; }
+
+int mau_tiles_probe(mau_tiles* t, int64_t idx, int64_t dims[8]) {
+  return guard([&]() -> int {
+    if (!t || !dims) return set_err(MAU_TILES_E_ARG, "mau_tiles_probe: null argument");
+    if (idx < 0 || idx >= int64_t(t->paths.size())) return set_err(MAU_TILES_E_ARG, "mau_tiles_probe: index out of range");
+    Mapping mp(t->paths[size_t(idx)]);
+    Member mem[M_COUNT];
+    parse_zip(mp, mem);
+    const int nd[M_COUNT] = {3, 3, 1, 1};
+    const int at[M_COUNT] = {0, 3, 6, 7};
+    for (int m = 0; m < M_COUNT; ++m) {
+      if (!mem[m].found) fail(MAU_TILES_E_MEMBER, "'%s': '%.*s' is not a file in the archive", mp.path.c_str(), int(strlen(kMemberNames[m]) - 4), kMemberNames[m]);
+      MemberStream s(mp, mem[m], kMemberNames[m], false);
+      NpyHeader h = read_npy_header(s, mp, kMemberNames[m]);
+      if (h.ndim != nd[m]) fail(MAU_TILES_E_SHAPE, "'%s': %s has %d dimensions, expected %d", mp.path.c_str(), kMemberNames[m], h.ndim, nd[m]);
+      for (int k = 0; k < nd[m]; ++k) dims[at[m] + k] = h.shape[k];
+    }
+    return 0;
+  });
+}
+
+int64_t mau_tiles_submit(mau_tiles* t, const int64_t* idx, int64_t n, const uint8_t* hflip, const int64_t dims[8], float* input, float* target,
+                         float* metadata, float* series, int64_t series_stride, int64_t* series_len) {
+  int rc = guard([&]() -> int {
+    if (!t || !dims || n < 0 || (n > 0 && !idx)) return set_err(MAU_TILES_E_ARG, "mau_tiles_submit: null argument");
+    if (series && series_stride <= 0) return set_err(MAU_TILES_E_ARG, "mau_tiles_submit: series_stride must be positive");
+    for (int k = 0; k < 7; ++k)
+      if (dims[k] < 0) return set_err(MAU_TILES_E_ARG, "mau_tiles_submit: negative dimension");
+    for (int64_t k = 0; k < n; ++k)
+      if (idx[k] < 0 || idx[k] >= int64_t(t->paths.size())) return set_err(MAU_TILES_E_ARG, "mau_tiles_submit: index " + std::to_string(idx[k]) + " out of range");
+    return 0;
+  });
+  if (rc) return -int64_t(rc);
+  auto b = std::make_shared<Batch>();
+  b->idx.assign(idx, idx + n);
+  if (hflip) b->flip.assign(hflip, hflip + n);
+  memcpy(b->dims, dims, sizeof b->dims);
+  b->input = input;
+  b->target = target;
+  b->metadata = metadata;
+  b->series = series;
+  b->series_stride = series_stride;
+  b->series_len = series_len;
+  const bool split = input != nullptr && (target || metadata || series);
+  b->pending = n * (split ? 2 : 1);
+  int64_t ticket;
+  {
+    std::lock_guard<std::mutex> g(t->mu);
+    ticket = t->next_ticket++;
+    t->inflight[ticket] = b;
+  }
+  for (int64_t s = 0; s < n; ++s) {
+    if (split) {
+      t->pool->push([t, b, s] { run_task(t, b, s, PART_INPUT); });
+      t->pool->push([t, b, s] { run_task(t, b, s, PART_REST); });
+    } else {
+      t->pool->push([t, b, s] { run_task(t, b, s, PART_INPUT | PART_REST); });
+    }
+  }
+  return ticket;
+}
+
+int mau_tiles_wait(mau_tiles* t, int64_t ticket) {
+  if (!t) return set_err(MAU_TILES_E_ARG, "mau_tiles_wait: null handle");
+  std::shared_ptr<Batch> b;
+  {
+    std::lock_guard<std::mutex> g(t->mu);
+    auto it = t->inflight.find(ticket);
+    if (it == t->inflight.end()) return set_err(MAU_TILES_E_ARG, "mau_tiles_wait: unknown ticket " + std::to_string(ticket));
+    b = it->second;
+    t->inflight.erase(it);
+  }
+  std::unique_lock<std::mutex> g(b->mu);
+  b->cv.wait(g, [&] { return b->pending == 0; });
+  if (b->code) return set_err(b->code, b->msg);
+  return 0;
+}
+
+int mau_tiles_done(mau_tiles* t, int64_t ticket) {
+  if (!t) return -set_err(MAU_TILES_E_ARG, "mau_tiles_done: null handle");
+  std::shared_ptr<Batch> b;
+  {
+    std::lock_guard<std::mutex> g(t->mu);
+    auto it = t->inflight.find(ticket);
+    if (it == t->inflight.end()) return -set_err(MAU_TILES_E_ARG, "mau_tiles_done: unknown ticket " + std::to_string(ticket));
+    b = it->second;
+  }
+  std::lock_guard<std::mutex> g(b->mu);
+  return b->pending == 0 ? 1 : 0;
+}
+
+int mau_tiles_read_batch(mau_tiles* t, const int64_t* idx, int64_t n, const uint8_t* hflip, const int64_t dims[8], float* input, float* target,
+                         float* metadata, float* series, int64_t series_stride, int64_t* series_len) {
+  int64_t ticket = mau_tiles_submit(t, idx, n, hflip, dims, input, target, metadata, series, series_stride, series_len);
+  if (ticket < 0) return int(-ticket);
+  return mau_tiles_wait(t, ticket);
+}
+
+int mau_tiles_stats(const mau_tiles* t, int64_t* payload_bytes, int64_t* archive_bytes, int64_t* samples) {
+  if (!t) return set_err(MAU_TILES_E_ARG, "mau_tiles_stats: null handle");
+  if (payload_bytes) *payload_bytes = t->payload_bytes.load();
+  if (archive_bytes) *archive_bytes = t->archive_bytes.load();
+  if (samples) *samples = t->samples.load();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+"""CPU: the native tile reader + loader (include/mau_tiles.h, mau_b200.data) against
+(a) the batches the REAL reference loader produced for tests/golden/tiles (oracle/gen_golden_tiles.py),
+(b) the NumPy restatement oracle/dataset_oracle.py on freshly written archives, bit-exact in both cases."""
+import os
+import struct
+import zipfile
+
+import numpy as np
+import pytest
+import torch
+
+import mau_b200  # noqa: F401
+from mau_b200 import data as D
+from oracle import dataset_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiles")
+KEYS = ("inputs", "metadatas", "series", "lengths", "t1", "t2", "targets")
+
+
+@pytest.fixture(scope="module")
+def expected():
+    return np.load(os.path.join(GOLD, "expected_batches.npz"))
+
+
+def assert_batches_equal(tag, expected, batches):
+    assert len(batches) == int(expected[f"{tag}_batches"])
+    for b, batch in enumerate(batches):
+        for k, t in zip(KEYS, batch):
+            ref = expected[f"{tag}_b{b}_{k}"]
+            assert tuple(t.shape) == ref.shape, (tag, b, k, t.shape, ref.shape)
+            assert str(t.dtype).replace("torch.", "") == str(ref.dtype), (tag, b, k, t.dtype, ref.dtype)
+            assert np.array_equal(t.numpy(), ref), (tag, b, k)
+
+
+# ---- the C ABI ---------------------------------------------------------------------------------------------
+def test_library_exports_every_symbol_of_the_header():
+    hdr = open(os.path.join(os.path.dirname(GOLD), "..", "..", "include", "mau_tiles.h")).read()
+    import re
+    declared = set(re.findall(r"\b(mau_tiles_[a-z_]+)\s*\(", hdr))
+    assert declared == set(D.EXPORTS), declared ^ set(D.EXPORTS)
+    L = D.lib()
+    assert all(hasattr(L, s) for s in D.EXPORTS)
+    assert L.mau_tiles_version() >= 1
+
+
+def test_probe_reports_npy_header_shapes():
+    ds = D.FuturePredictionDataset("train", processed_dir=GOLD, threads=2)
+    assert len(ds) == 6 and ds.threads == 2
+    for i, f in enumerate(ds.file_list):
+        with np.load(f) as z:
+            want = list(z["input"].shape) + list(z["target"].shape) + [z["metadata"].shape[0], z["temperature_serie"].shape[0]]
+        assert ds.probe(i) == want
+    with pytest.raises(IndexError):
+        ds.probe(6)
+
+
+# ---- golden batches of the real reference loader -----------------------------------------------------------
+def test_sequential_batches_equal_the_reference_loader(expected):
+    loader = D.create_dataloader("train", 4, False, "future", device="cpu", processed_dir=GOLD)
+    assert len(loader) == 2
+    assert_batches_equal("seq", expected, list(loader))
+
+
+def test_shuffled_batches_equal_the_reference_loader_under_the_same_torch_seed(expected):
+    torch.manual_seed(123)
+    loader = D.create_dataloader("train", 4, True, "future", device="cpu", processed_dir=GOLD)
+    assert_batches_equal("shuf", expected, list(loader))
+
+
+def test_random_flip_two_epochs_equal_the_reference_loader(expected):
+    torch.manual_seed(7)
+    loader = D.create_dataloader("train", 4, True, "future", transform=D.RandomFlip(42), device="cpu", processed_dir=GOLD,
+                                 prefetch=3)
+    assert_batches_equal("flip_e0", expected, list(loader))
+    assert_batches_equal("flip_e1", expected, list(loader))
+
+
+def test_generic_transform_callable_matches_random_flip_path(expected):
+    torch.manual_seed(7)
+    loader = D.create_dataloader("train", 4, True, "future", transform=O.RandomFlip(42), device="cpu", processed_dir=GOLD)
+    assert_batches_equal("flip_e0", expected, list(loader))
+
+
+def test_getitem_and_metadata_from_idx(expected):
+    ds = D.FuturePredictionDataset("train", processed_dir=GOLD)
+    for i in range(len(ds)):
+        got, ref = ds[i], O.load_sample(ds.file_list[i])
+        for a, b in zip(got, ref):
+            assert a.dtype == b.dtype and torch.equal(a, b)
+        assert repr(ds.get_metadata_from_idx(i)) == str(expected["meta_from_idx"][i])
+    assert torch.equal(ds[-1][0], ds[5][0])
+    with pytest.raises(IndexError):
+        ds[6]
+    # torch's own DataLoader over the dataset + our collate_fn is the reference arrangement verbatim
+    from torch.utils.data import DataLoader
+    batches = list(DataLoader(ds, batch_size=4, shuffle=False, collate_fn=lambda b: D.collate_fn(b, device="cpu")))
+    assert_batches_equal("seq", expected, batches)
+
+
+def test_collate_fn_empty_and_none_samples():
+    out = D.collate_fn([], device="cpu")
+    assert len(out) == 7 and all(t.numel() == 0 for t in out)
+    ds = D.FuturePredictionDataset("train", processed_dir=GOLD)
+    s = ds[0]
+    got = D.collate_fn([(None,) * 6, s], device="cpu")
+    ref = O.collate([(None,) * 6, s])
+    assert all(torch.equal(a, b) for a, b in zip(got, ref))
+
+
+# ---- fresh archives: oracle restatement vs native reader ----------------------------------------------------
+@pytest.fixture(scope="module")
+def synth(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("tiles"))
+    O.write_synthetic_split(root, "train", 11, 20, 28, seed=5, t_range=(30, 47))
+    O.write_synthetic_split(root, "val", 3, 20, 28, seed=6, t_range=(40, 40), compressed=False)
+    return root
+
+
+def test_oracle_restatement_equals_reference_golden(expected):
+    files = O.list_split(GOLD, "train")
+    batches = [O.collate([O.load_sample(f) for f in files[i:i + 4]]) for i in (0, 4)]
+    assert_batches_equal("seq", expected, batches)
+
+
+@pytest.mark.parametrize("split,batch", [("train", 4), ("train", 11), ("train", 1), ("val", 2)])
+def test_native_reader_equals_oracle_on_fresh_archives(synth, split, batch):
+    files = O.list_split(synth, split)
+    loader = D.create_dataloader(split, batch, False, "future", device="cpu", processed_dir=synth, num_workers=3)
+    got = list(loader)
+    assert len(got) == -(-len(files) // batch)
+    for b, g in enumerate(got):
+        ref = O.collate([O.load_sample(f) for f in files[b * batch:(b + 1) * batch]])
+        for a, r in zip(g, ref):
+            assert a.dtype == r.dtype and torch.equal(a, r)
+    st = loader.dataset.stats()
+    assert st["samples"] == len(files) and st["payload_bytes"] > 0
+
+
+def test_drop_last_and_len(synth):
+    loader = D.create_dataloader("train", 4, False, "future", device="cpu", processed_dir=synth, drop_last=True)
+    assert len(loader) == 2 and sum(b[0].shape[0] for b in loader) == 8
+
+
+def test_rank_slices_partition_the_global_batch(synth):
+    files = O.list_split(synth, "train")
+    per_rank = []
+    for r in range(2):
+        torch.manual_seed(99)
+        tf = D.RandomFlip(3)
+        loader = D.create_dataloader("train", 3, True, "future", transform=tf, device="cpu", processed_dir=synth, rank=r, world_size=2)
+        per_rank.append(list(loader))
+    torch.manual_seed(99)
+    whole = list(D.create_dataloader("train", 6, True, "future", transform=D.RandomFlip(3), device="cpu", processed_dir=synth))
+    assert len(per_rank[0]) == len(per_rank[1]) == len(whole) == 2
+    for b in range(2):
+        for k in range(7):      # incl. the series: every rank pads to the longest series of the global batch
+            assert torch.equal(torch.cat([per_rank[0][b][k], per_rank[1][b][k]]), whole[b][k]), (b, k)
+    assert len(files) == 11
+
+
+def test_other_dtypes_are_converted_like_tensor_float(tmp_path):
+    d = tmp_path / "train"
+    d.mkdir()
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((3, 4, 5))
+    np.savez_compressed(d / "A_1_0.5_0.25_2019_7_to_2023_7.npz", input=x, target=(x[:2] * 1000).astype(np.int64),
+                        metadata=np.arange(4, dtype=np.uint8), temperature_serie=rng.standard_normal(7).astype(np.float16))
+    ds = D.FuturePredictionDataset("train", processed_dir=str(tmp_path))
+    got, ref = ds[0], O.load_sample(ds.file_list[0])
+    for a, b in zip(got, ref):
+        assert a.dtype == torch.float32 and torch.equal(a, b)
+
+
+def test_series_longer_than_the_staging_capacity_grows_the_buffer(tmp_path):
+    d = tmp_path / "train"
+    d.mkdir()
+    rng = np.random.default_rng(2)
+    for i, n in enumerate((1500, 3)):
+        np.savez_compressed(d / f"B_{i}_0.5_0.25_2019_7_to_2023_7.npz", input=np.zeros((2, 2, 2), np.float32), target=np.zeros((1, 2, 2), np.float32),
+                            metadata=np.zeros(4, np.float32), temperature_serie=rng.standard_normal(n).astype(np.float32))
+    (batch,) = list(D.create_dataloader("train", 2, False, "future", device="cpu", processed_dir=str(tmp_path)))
+    ref = O.collate([O.load_sample(f) for f in O.list_split(str(tmp_path), "train")])
+    assert batch[2].shape == (2, 1500) and torch.equal(batch[2], ref[2]) and torch.equal(batch[3], ref[3])
+
+
+# ---- error behaviour ---------------------------------------------------------------------------------------
+def _one(tmp_path, name="C_1_0.5_0.25_2019_7_to_2023_7.npz", **arrays):
+    d = tmp_path / "train"
+    d.mkdir(exist_ok=True)
+    base = dict(input=np.ones((2, 3, 4), np.float32), target=np.ones((1, 3, 4), np.float32), metadata=np.ones(4, np.float32),
+                temperature_serie=np.ones(5, np.float32))
+    base.update(arrays)
+    base = {k: v for k, v in base.items() if v is not None}
+    np.savez_compressed(d / name, **base)
+    return str(d / name)
+
+
+def test_missing_split_directory_raises_file_not_found(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        D.FuturePredictionDataset("test", processed_dir=str(tmp_path))
+
+
+def test_missing_member_raises_key_error(tmp_path):
+    _one(tmp_path, temperature_serie=None)
+    ds = D.FuturePredictionDataset("train", processed_dir=str(tmp_path))
+    with pytest.raises(KeyError, match="temperature_serie"):
+        ds[0]
+
+
+def test_corrupt_archives_raise_instead_of_returning_garbage(tmp_path):
+    p = _one(tmp_path, input=np.random.default_rng(0).standard_normal((2, 30, 40)).astype(np.float32))
+    raw = bytearray(open(p, "rb").read())
+    with zipfile.ZipFile(p) as z:
+        info = z.getinfo("input.npy")
+    start = info.header_offset + 30 + len(info.filename) + len(info.extra or b"") + 20        # local extra may differ; stay inside the payload
+    raw[start + 400] ^= 0x55
+    open(p, "wb").write(bytes(raw))
+    ds = D.FuturePredictionDataset("train", processed_dir=str(tmp_path))
+    with pytest.raises(ValueError):
+        ds[0]
+    open(p, "wb").write(bytes(raw[:len(raw) // 2]))          # truncated: no end-of-central-directory record
+    with pytest.raises(ValueError):
+        ds[0]
+    open(p, "wb").write(b"")
+    with pytest.raises(ValueError):
+        ds[0]
+    os.remove(p)
+    with pytest.raises(FileNotFoundError):
+        ds[0]
+
+
+def test_crc_mismatch_is_detected_unless_disabled(tmp_path):
+    p = _one(tmp_path)
+    with zipfile.ZipFile(p) as z:
+        info = z.getinfo("metadata.npy")
+    raw = bytearray(open(p, "rb").read())
+    pos = 0                 # patch the CRC field of metadata.npy in the central directory
+    while True:
+        pos = raw.find(b"PK\x01\x02", pos)
+        assert pos >= 0
+        nlen = struct.unpack_from("<H", raw, pos + 28)[0]
+        if raw[pos + 46:pos + 46 + nlen] == b"metadata.npy":
+            struct.pack_into("<I", raw, pos + 16, (info.CRC + 1) & 0xFFFFFFFF)
+            break
+        pos += 4
+    open(p, "wb").write(bytes(raw))
+    with pytest.raises(ValueError, match="CRC"):
+        D.FuturePredictionDataset("train", processed_dir=str(tmp_path))[0]
+    ok = D.FuturePredictionDataset("train", processed_dir=str(tmp_path), verify_crc=False)[0]
+    assert torch.equal(ok[1], torch.ones(4))
+
+
+def test_shape_mismatch_inside_a_batch_raises_runtime_error(tmp_path):
+    _one(tmp_path, name="C_1_0.5_0.25_2019_7_to_2023_7.npz")
+    _one(tmp_path, name="C_2_0.5_0.25_2019_7_to_2023_7.npz", input=np.ones((2, 3, 5), np.float32))
+    loader = D.create_dataloader("train", 2, False, "future", device="cpu", processed_dir=str(tmp_path))
+    with pytest.raises(RuntimeError, match="shape"):
+        list(loader)
+
+
+def test_malformed_file_name_raises_like_int(tmp_path):
+    _one(tmp_path, name="C_1_0.5_0.25_2019_7_to_2023_x.npz")
+    with pytest.raises(ValueError):
+        D.FuturePredictionDataset("train", processed_dir=str(tmp_path))[0]
+    with pytest.raises(ValueError):
+        O.load_sample(O.list_split(str(tmp_path), "train")[0])
+
+
+def test_fortran_ordered_member_is_refused(tmp_path):
+    _one(tmp_path, input=np.asfortranarray(np.arange(24, dtype=np.float32).reshape(2, 3, 4)))
+    with pytest.raises(ValueError, match="Fortran"):
+        D.FuturePredictionDataset("train", processed_dir=str(tmp_path))[0]
+
+
+def test_async_tickets_out_of_order_and_abandoned_iteration(synth):
+    ds = D.FuturePredictionDataset("train", processed_dir=synth, threads=4)
+    sets = [ds.alloc_staging(3) for _ in range(3)]
+    tickets = [ds.submit([3 * k, 3 * k + 1, 3 * k + 2], None, sets[k]) for k in range(3)]
+    files = ds.file_list
+    for k in (2, 0, 1):
+        st = tickets[k].wait()
+        assert tickets[k].n == 3
+        ref = O.collate([O.load_sample(f) for f in files[3 * k:3 * k + 3]])
+        assert torch.equal(st["input"][:3], ref[0]) and torch.equal(st["target"][:3], ref[6])
+    L = D.lib()
+    assert L.mau_tiles_wait(ds._handle, 12345) == D.E_ARG and b"unknown ticket" in L.mau_tiles_last_error()
+    it = iter(D.TileLoader(ds, 2, False, device="cpu", prefetch=3))
+    next(it)
+    it.close()          # in-flight decodes are drained before their buffers are dropped
+    ds.close()
