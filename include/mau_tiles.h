@@ -40,6 +40,7 @@ extern "C" {
 #define MAU_TILES_E_DTYPE     7  /* dtype / memory order we do not convert                         */
 
 #define MAU_TILES_FLAG_NO_CRC 1  /* skip the CRC-32 check zipfile performs on every member read    */
+#define MAU_TILES_FLAG_ZLIB   2  /* inflate through zlib instead of the reader's own decoder (A/B switch) */
 
 typedef struct mau_tiles mau_tiles; /* opaque: a list of archive paths + the worker pool */
 
@@ -83,6 +84,14 @@ int     mau_tiles_wait(mau_tiles* t, int64_t ticket);
 /* 1 if every sample of the batch has been decoded (wait() will not block), 0 if not, -MAU_TILES_E_ARG for an
  * unknown ticket.  Does not retire the ticket. */
 int     mau_tiles_done(mau_tiles* t, int64_t ticket);
+
+/* The reader's DEFLATE decoder on its own (raw RFC 1951 stream `src` -> exactly dst_len bytes), decoded in two
+ * calls split at output offset `split` (0 <= split <= dst_len) to exercise the resumable path; `src` must be
+ * followed by 16 readable bytes.  Test / bench hook. */
+int     mau_tiles_inflate(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len, size_t split);
+
+/* The reader's CRC-32 (ZIP polynomial; zlib convention: pass 0 to start, the result to continue).  Test hook. */
+uint32_t mau_tiles_crc32(uint32_t crc, const void* data, size_t n);
 
 /* Bytes decoded (uncompressed NPY payload) and archive bytes consumed since open: loader bench. */
 int     mau_tiles_stats(const mau_tiles* t, int64_t* payload_bytes, int64_t* archive_bytes, int64_t* samples);

@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
 def build_tiles(force=False):
     """Host-only tile reader (include/mau_tiles.h): g++ + zlib, no CUDA."""
     hdr = os.path.join(HERE, "..", "include", "mau_tiles.h")
-    if force or _newer(TILES_SRC, TILES_LIB, [hdr]):
+    if force or _newer(TILES_SRC, TILES_LIB, [hdr, os.path.join(SRC, "inflate_fast.h")]):
         cmd = [CXX, "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-DNDEBUG", TILES_SRC, "-o", TILES_LIB,
                "-lz", "-pthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)

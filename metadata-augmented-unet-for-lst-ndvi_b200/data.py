@@ -37,12 +37,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmau_tiles.so")
 
 E_ARG, E_IO, E_FORMAT, E_MEMBER, E_SHAPE, E_CAPACITY, E_DTYPE = 1, 2, 3, 4, 5, 6, 7
-FLAG_NO_CRC = 1
+FLAG_NO_CRC, FLAG_ZLIB = 1, 2
 
 # every symbol include/mau_tiles.h declares (tests check the .so exports all of them)
 EXPORTS = ("mau_tiles_last_error", "mau_tiles_version", "mau_tiles_open", "mau_tiles_close", "mau_tiles_count",
            "mau_tiles_threads", "mau_tiles_probe", "mau_tiles_read_batch", "mau_tiles_submit", "mau_tiles_wait",
-           "mau_tiles_done", "mau_tiles_stats")
+           "mau_tiles_done", "mau_tiles_inflate", "mau_tiles_crc32", "mau_tiles_stats")
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -76,6 +76,9 @@ def lib():
         L.mau_tiles_wait.argtypes = [C.c_void_p, C.c_int64]
         L.mau_tiles_done.argtypes = [C.c_void_p, C.c_int64]
         L.mau_tiles_stats.argtypes = [C.c_void_p, p64, p64, p64]
+        L.mau_tiles_inflate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.mau_tiles_crc32.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
+        L.mau_tiles_crc32.restype = C.c_uint32
         _lib = L
     return _lib
 
@@ -158,12 +161,13 @@ class FuturePredictionDataset(Dataset):
 
     ``processed_dir`` replaces ``CONFIG.PROCESSED_IMAGE_DATASET`` when the reference's Hydra config is not
     importable; ``threads`` sizes the decode pool (default: all online cores); ``verify_crc=False`` skips the
-    CRC-32 check ``zipfile`` performs."""
+    CRC-32 check ``zipfile`` performs; ``use_zlib=True`` inflates through zlib instead of the reader's own
+    DEFLATE decoder (A/B switch for benchmarks)."""
 
     SERIES_CAPACITY = 1024      # >= conf/config.yaml:20 seq_len 828; grown on demand
 
     def __init__(self, split: str, transform: Optional[Callable] = None, processed_dir: Optional[str] = None,
-                 threads: int = 0, verify_crc: bool = True):
+                 threads: int = 0, verify_crc: bool = True, use_zlib: bool = False):
         self.processed_dir = _resolve_processed_dir(processed_dir)
         self.split = split
         self.transform = transform
@@ -173,7 +177,8 @@ class FuturePredictionDataset(Dataset):
         self.file_list = sorted(os.path.join(self.data_dir, f) for f in os.listdir(self.data_dir) if f.endswith(".npz"))
         self._handle = C.c_void_p()
         arr = (C.c_char_p * len(self.file_list))(*[os.fsencode(p) for p in self.file_list])
-        rc = lib().mau_tiles_open(arr, len(self.file_list), int(threads), 0 if verify_crc else FLAG_NO_CRC, C.byref(self._handle))
+        flags = (0 if verify_crc else FLAG_NO_CRC) | (FLAG_ZLIB if use_zlib else 0)
+        rc = lib().mau_tiles_open(arr, len(self.file_list), int(threads), flags, C.byref(self._handle))
         if rc:
             _raise(rc)
         self._dims: Optional[List[int]] = None

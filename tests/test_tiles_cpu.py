@@ -36,7 +36,7 @@ def assert_batches_equal(tag, expected, batches):
 def test_library_exports_every_symbol_of_the_header():
     hdr = open(os.path.join(os.path.dirname(GOLD), "..", "..", "include", "mau_tiles.h")).read()
     import re
-    declared = set(re.findall(r"\b(mau_tiles_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(mau_tiles_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(D.EXPORTS), declared ^ set(D.EXPORTS)
     L = D.lib()
     assert all(hasattr(L, s) for s in D.EXPORTS)
@@ -288,3 +288,112 @@ def test_async_tickets_out_of_order_and_abandoned_iteration(synth):
     next(it)
     it.close()          # in-flight decodes are drained before their buffers are dropped
     ds.close()
+
+
+# ---- the reader's own DEFLATE decoder and CRC-32 against zlib ------------------------------------------------
+def _deflate(data, level=6, strategy=0, flush_every=None, memlevel=8):
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, memlevel, strategy)
+    if not flush_every:
+        return c.compress(data) + c.flush()
+    out = b""
+    for k, i in enumerate(range(0, len(data), flush_every)):
+        out += c.compress(data[i:i + flush_every]) + c.flush(zlib.Z_FULL_FLUSH if k % 2 else zlib.Z_SYNC_FLUSH)
+    return out + c.flush()
+
+
+def _inflate(raw, n, split):
+    import ctypes as C
+    src = (C.c_uint8 * (len(raw) + 16)).from_buffer_copy(raw + b"\xAA" * 16)      # 16 readable bytes of slack
+    dst = (C.c_uint8 * max(n, 1))()
+    rc = D.lib().mau_tiles_inflate(src, len(raw), dst, n, split)
+    return rc, bytes(dst[:n])
+
+
+def _payloads():
+    rng = np.random.default_rng(0)
+    cls = rng.integers(0, 9, (40, 40))
+    yield b""
+    yield b"a"
+    yield bytes(70000)                                                              # distance-1 runs, length-258 matches
+    yield rng.integers(0, 256, 70000, dtype=np.uint8).tobytes()                     # incompressible: literals / stored blocks
+    yield (cls[None] == np.arange(9)[:, None, None]).astype(np.float32).tobytes()   # one-hot planes: distance-4 periods
+    yield rng.standard_normal(20000).astype(np.float32).tobytes()
+    yield b"0123456" * 9000 + b"abc" * 5000 + b"xy" * 7000 + b"12345" * 3000 + b"abcdef" * 3000   # periods 7, 3, 2, 5, 6
+    yield open(__file__, "rb").read() * 2
+
+
+def test_inflate_is_bit_identical_to_zlib_on_every_block_type():
+    import zlib
+    n_checked = 0
+    for data in _payloads():
+        for level in (0, 1, 6, 9):                    # 0 = stored blocks
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                for flush_every, memlevel in ((None, 8), (7001, 8), (None, 1)):
+                    raw = _deflate(data, level, strategy, flush_every, memlevel)
+                    assert zlib.decompress(raw, -15) == data
+                    for split in {0, len(data), len(data) // 2, min(len(data), 65536), min(len(data), 305), max(len(data) - 1, 0)}:
+                        rc, out = _inflate(raw, len(data), split)
+                        assert rc == 0 and out == data, (len(data), level, strategy, flush_every, memlevel, split)
+                        n_checked += 1
+    assert n_checked > 1500
+
+
+def test_inflate_resumes_at_every_output_offset():
+    data = open(__file__, "rb").read()[:2500] + bytes(400) + b"ab" * 300 + b"xyz" * 100
+    raw = _deflate(data)
+    for split in range(len(data) + 1):
+        rc, out = _inflate(raw, len(data), split)
+        assert rc == 0 and out == data, split
+
+
+def test_inflate_rejects_bad_streams_without_crashing():
+    rng = random_bytes = np.random.default_rng(3)
+    data = open(__file__, "rb").read()[:6000]
+    raw = _deflate(data)
+    assert _inflate(raw, len(data) - 1, 0)[0] == D.E_FORMAT          # more data than the directory entry says
+    assert _inflate(raw, len(data) + 1, 0)[0] == D.E_FORMAT          # stream ends early
+    assert _inflate(raw[:len(raw) // 2], len(data), 0)[0] == D.E_FORMAT
+    assert _inflate(b"\x07", 10, 0)[0] == D.E_FORMAT                # block type 3
+    wrong = 0
+    for _ in range(1500):                                            # bit flips: an error or different bytes, never a crash
+        b = bytearray(raw)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        rc, out = _inflate(bytes(b), len(data), int(rng.integers(0, len(data))))
+        wrong += rc != 0 or out != data
+    assert wrong > 1000
+    for _ in range(300):
+        _inflate(random_bytes.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8).tobytes(), int(rng.integers(0, 4000)), 0)
+
+
+def test_crc32_equals_zlib_for_all_lengths_and_continuations():
+    import zlib
+    buf = np.random.default_rng(1).integers(0, 256, 1 << 18, dtype=np.uint8).tobytes()
+    crc = D.lib().mau_tiles_crc32
+    for n in list(range(0, 200)) + [1000, 4095, 4096, 65537, (1 << 18) - 3]:
+        for off in (0, 1, 7):
+            d = buf[off:off + n]
+            assert crc(0, d, len(d)) == zlib.crc32(d), (n, off)
+            k = len(d) // 3
+            assert crc(crc(0, d[:k], k), d[k:], len(d) - k) == zlib.crc32(d)
+
+
+def test_zlib_switch_decodes_the_same_batches(synth):
+    a = list(D.TileLoader(D.FuturePredictionDataset("train", processed_dir=synth, use_zlib=True), 4, False, device="cpu"))
+    b = list(D.TileLoader(D.FuturePredictionDataset("train", processed_dir=synth), 4, False, device="cpu"))
+    assert len(a) == len(b) == 3
+    assert all(torch.equal(x, y) for ba, bb in zip(a, b) for x, y in zip(ba, bb))
+
+
+def test_members_larger_than_the_decoder_head_buffer(tmp_path):
+    # the first 64 KiB of a member are decoded into a scratch buffer (NPY header + start of the payload), the rest
+    # straight into the batch slot with the copied part as match history: 23 x 64 x 72 fp32 = 424 KB crosses that seam
+    root = str(tmp_path)
+    files = O.write_synthetic_split(root, "train", 5, 64, 72, seed=8, t_range=(100, 120))
+    for flip in (None, D.RandomFlip(1)):
+        got = list(D.create_dataloader("train", 3, False, "future", transform=flip, device="cpu", processed_dir=root, num_workers=2))
+        tf = O.RandomFlip(1) if flip else None
+        for b, g in enumerate(got):
+            ref = O.collate([O.load_sample(f, tf) for f in files[3 * b:3 * b + 3]])
+            assert all(torch.equal(a, r) for a, r in zip(g, ref))
