@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--device", default="cpu")
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--no-crc", action="store_true")
+    ap.add_argument("--zlib", action="store_true", help="inflate through zlib instead of the reader's own decoder")
     ap.add_argument("--stored", action="store_true", help="archives written with np.savez (stored members, no deflate)")
     a = ap.parse_args()
 
@@ -49,6 +50,10 @@ def main():
     archive = sum(os.path.getsize(f) for f in files)
     dev = torch.device(a.device)
 
+    for f in files:     # page cache warm for both paths
+        with open(f, "rb") as fh:
+            fh.read()
+    O.collate([O.load_sample(f) for f in files[:2]])
     # reference path: one thread, np.load per sample (src/dataset.py:43-73), collate (src/dataset.py:87-108)
     t0 = time.perf_counter()
     n_ref = 0
@@ -61,7 +66,7 @@ def main():
 
     rows = []
     for th in [int(x) for x in a.threads.split(",")]:
-        ds = D.FuturePredictionDataset("train", processed_dir=root, threads=th, verify_crc=not a.no_crc)
+        ds = D.FuturePredictionDataset("train", processed_dir=root, threads=th, verify_crc=not a.no_crc, use_zlib=a.zlib)
         loader = D.TileLoader(ds, a.batch, False, device=dev, prefetch=2)
         for _ in loader:        # warm-up epoch: page cache, staging ring
             pass
@@ -81,7 +86,7 @@ def main():
         ds.close()
     out = {"bench": "tile loader", "tile": [23, a.edge, a.edge], "tiles": len(files), "batch": a.batch, "device": str(dev),
            "archive_bytes_per_tile": archive // len(files), "payload_bytes_per_tile": (25 * a.edge * a.edge + 4 + 828) * 4,
-           "host_cores": os.cpu_count(), "crc": not a.no_crc, "members": "stored" if a.stored else "deflate",
+           "host_cores": os.cpu_count(), "crc": not a.no_crc, "members": "stored" if a.stored else "deflate", "inflate": "zlib" if a.zlib else "own decoder",
            "reference_path": {"tiles_per_s": round(n_ref / t_ref, 1), "threads": 1, "what": "oracle/dataset_oracle.py: np.load + stack + pad_sequence"},
            "native": rows}
     print(json.dumps(out))

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=3)
     ap.add_argument("--stored", action="store_true")
+    ap.add_argument("--zlib", action="store_true", help="inflate through zlib instead of the reader's own decoder")
     ap.add_argument("--edge", type=int, default=250)
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic tiles written (deflating them is slow); "
                     "the rest of --tiles are copies under other names -- the decode work per file is the same")
@@ -47,8 +48,8 @@ def main():
         torch.manual_seed(42)
         model = mau_b200.UrbanPredictor("unet", 23, 828, 64, 8, 64, 96, 2, temporal_embeddings=False, metadata_embeddings=True).to(dev).train()
         opt = mau_b200.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-3)
-        loader = D.create_dataloader("train", a.batch, True, "future", transform=D.RandomFlip(42), device=dev, processed_dir=root,
-                                     prefetch=a.prefetch, drop_last=True, threads=a.threads)
+        ds = D.FuturePredictionDataset("train", transform=D.RandomFlip(42), processed_dir=root, threads=a.threads, use_zlib=a.zlib)
+        loader = D.TileLoader(ds, a.batch, True, device=dev, prefetch=a.prefetch, drop_last=True)
 
         def train_step(batch, read_back=True):
             inputs, metadatas, series, lengths, t1, t2, targets = batch
@@ -82,7 +83,7 @@ def main():
         torch.cuda.synchronize()
         res["model_only_resident_inputs"] = steps * a.batch / (time.perf_counter() - t0)
         print(json.dumps({"bench": "training from .npz archives", "tile": [23, a.edge, a.edge], "batch": a.batch, "tiles": a.tiles,
-                          "members": "stored" if a.stored else "deflate", "decode_threads": loader.dataset.threads,
+                          "members": "stored" if a.stored else "deflate", "inflate": "zlib" if a.zlib else "own decoder", "decode_threads": loader.dataset.threads,
                           "host_cores": os.cpu_count(), "prefetch": a.prefetch,
                           "tiles_per_s": {k: round(v, 1) for k, v in res.items()}}))
     finally:
