@@ -13,6 +13,8 @@
 
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -563,7 +565,9 @@ NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool
 // ---- the worker pool -------------------------------------------------------------------------------------
 class Pool {
  public:
-  explicit Pool(int n) {
+  // `nice` > 0 lowers the workers' priority: the thread that launches the GPU step shares the cores with them
+  // and must not wait for a time slice behind 6 ms decode tasks
+  Pool(int n, int nice) : nice_(nice) {
     for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
   }
   ~Pool() {
@@ -585,6 +589,7 @@ class Pool {
 
  private:
   void run() {
+    if (nice_ > 0) setpriority(PRIO_PROCESS, id_t(syscall(SYS_gettid)), nice_);  // per-thread on Linux; failure is harmless
     for (;;) {
       std::function<void()> f;
       {
@@ -602,6 +607,7 @@ class Pool {
   std::mutex mu_;
   std::condition_variable cv_;
   bool stop_ = false;
+  int nice_ = 0;
 };
 
 struct Batch {
@@ -755,7 +761,7 @@ int mau_tiles_open(const char* const* paths, int64_t n, int threads, int flags, 
       long c = sysconf(_SC_NPROCESSORS_ONLN);
       threads = c > 0 ? int(c) : 4;
     }
-    t->pool = std::make_unique<Pool>(std::min(threads, 256));
+    t->pool = std::make_unique<Pool>(std::min(threads, 256), (flags & MAU_TILES_FLAG_NO_NICE) ? 0 : 10);
     *out = t.release();
     return 0;
   });
