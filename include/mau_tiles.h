@@ -40,8 +40,9 @@ extern "C" {
 #define MAU_TILES_E_DTYPE     7  /* dtype / memory order we do not convert                         */
 
 #define MAU_TILES_FLAG_NO_CRC 1  /* skip the CRC-32 check zipfile performs on every member read    */
-#define MAU_TILES_FLAG_NO_NICE 4 /* keep the decode threads at the caller's priority (default: niceness +10,
-                                    so that the thread launching the GPU step is never queued behind a decode)  */
+#define MAU_TILES_FLAG_NICE    4 /* run the decode threads at niceness +10 (for hosts where the thread launching
+                                    the GPU step would otherwise queue behind 6 ms decode tasks); measured
+                                    neutral-to-worse on the 16-core B200 boxes, so off by default             */
 #define MAU_TILES_FLAG_ZLIB   2  /* inflate through zlib instead of the reader's own decoder (A/B switch) */
 
 typedef struct mau_tiles mau_tiles; /* opaque: a list of archive paths + the worker pool */

@@ -565,8 +565,7 @@ NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool
 // ---- the worker pool -------------------------------------------------------------------------------------
 class Pool {
  public:
-  // `nice` > 0 lowers the workers' priority: the thread that launches the GPU step shares the cores with them
-  // and must not wait for a time slice behind 6 ms decode tasks
+  // `nice` > 0 lowers the workers' priority (MAU_TILES_FLAG_NICE)
   Pool(int n, int nice) : nice_(nice) {
     for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
   }
@@ -761,7 +760,7 @@ int mau_tiles_open(const char* const* paths, int64_t n, int threads, int flags, 
       long c = sysconf(_SC_NPROCESSORS_ONLN);
       threads = c > 0 ? int(c) : 4;
     }
-    t->pool = std::make_unique<Pool>(std::min(threads, 256), (flags & MAU_TILES_FLAG_NO_NICE) ? 0 : 10);
+    t->pool = std::make_unique<Pool>(std::min(threads, 256), (flags & MAU_TILES_FLAG_NICE) ? 10 : 0);
     *out = t.release();
     return 0;
   });
