@@ -15,9 +15,10 @@ What differs is how a batch is produced.  The reference inflates four ZIP member
 ``np.load`` on the training thread (``num_workers=0`` because its collate function moves tensors to the
 device, src/train.py:180).  Here the batch sampler's indices go to the native reader, which decodes the
 samples of a batch in parallel on a pool of host threads straight into pinned batch buffers (stack, pad
-and flip happen in that same pass); a staging thread keeps ``prefetch`` batches in the decode pool and issues
-the host->device copy of each batch on a side stream the moment it is decoded, so that decoding, PCIe and the
-GPU step overlap even when the training loop synchronises every step.  Batch order, flip decisions and
+and flip happen in that same pass); batches are prefetched ``prefetch`` deep and the host->device copies
+run on a side stream, so that decoding, PCIe and the GPU step overlap.  (A variant with a dedicated staging
+thread that issues each copy the moment its batch is decoded measured slower on the 16-core B200 box -- 842 vs
+1 210 training tiles/s from disk -- and was dropped.)  Batch order, flip decisions and
 values are identical to the reference loader under the same seeds (tests/test_tiles_cpu.py).
 
 There is no NumPy fallback: a missing ``libmau_tiles.so`` raises ``RuntimeError``.
@@ -26,7 +27,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import queue
 import random
 import threading
 from collections import deque
@@ -382,7 +382,6 @@ class TileLoader:
         self.dataset, self.batch_size, self.shuffle = dataset, int(batch_size), bool(shuffle)
         self.device = _resolve_device(device)
         self.prefetch = max(1, int(prefetch))
-        self.ahead = 2                # device batches the staging thread may hold ahead of the consumer
         self.rank, self.world_size = int(rank), int(world_size)
         self.sampler = RandomSampler(dataset, generator=generator) if shuffle else SequentialSampler(dataset)
         self.batch_sampler = BatchSampler(self.sampler, self.batch_size * self.world_size, drop_last)
@@ -411,88 +410,64 @@ class TileLoader:
 
     def __iter__(self):
         ds = self.dataset
-        if self._rings is None:       # `prefetch` sets being decoded + `ahead` + 1 whose host->device copy may be in flight
-            self._rings = [ds.alloc_staging(self.batch_size, pin=self._pin) for _ in range(self.prefetch + self.ahead + 1)]
-        rings = self._rings
+        if self._rings is None:       # prefetch + 2 staging sets: up to two being copied H2D, `prefetch` being decoded
+            self._rings = [ds.alloc_staging(self.batch_size, pin=self._pin) for _ in range(self.prefetch + 2)]
+        free = deque(self._rings)
+        busy = {}                     # id(staging set) -> event of its last H2D copy
+        inflight = deque()            # decode tickets, oldest first
+        staged = deque()              # (device batch, copy event) ahead of the consumer, at most one
         copy_stream = torch.cuda.Stream(device=self.device) if self._pin else None
-        # All randomness is consumed here, on the caller's thread, in the reference's order.  DataLoader's iterator
-        # draws its base seed from the default generator before the sampler draws the permutation seed
-        # (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__); replaying that draw keeps the batch order
-        # identical to the reference loader under the same torch.manual_seed.  Flip decisions: one random.random()
-        # per sample in sample order (src/dataset.py:61-62,139), drawn for the whole epoch up front.
+        # DataLoader's iterator draws its base seed from the default generator before the sampler draws the
+        # permutation seed (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__); replaying that draw keeps
+        # the batch order identical to the reference loader under the same torch.manual_seed
         torch.empty((), dtype=torch.int64).random_(generator=self.generator)
-        plan = [(gb, self._local(gb), self._flips(gb)) for gb in self.batch_sampler]
-        handoff: "queue.Queue" = queue.Queue(maxsize=self.ahead)
-        stop = threading.Event()
-        DONE = object()
+        it = iter(self.batch_sampler)
 
-        def put(item) -> bool:
-            while not stop.is_set():
-                try:
-                    handoff.put(item, timeout=0.05)
-                    return True
-                except queue.Full:
-                    pass
-            return False
-
-        def producer():
-            """Staging thread: keeps `prefetch` batches in the decode pool and starts the host->device copy of a
-            batch the moment it is decoded -- independently of the consumer, so the copy overlaps the running step
-            even when the training loop synchronises every step (loss.item(), src/train.py:258)."""
-            free, busy, inflight, nxt = deque(rings), {}, deque(), 0
-            try:
-                while not stop.is_set():
-                    while nxt < len(plan) and free and len(inflight) < self.prefetch:
-                        gb, local, flips = plan[nxt]
-                        nxt += 1
-                        # the reference pads every series to the longest of the batch and the LSTM runs over that
-                        # padding (src/dataset.py:106, src/model.py:29-33): ranks pad to the longest of the GLOBAL batch
-                        width = max(ds.probe(i)[7] for i in gb) if self.world_size > 1 else 0
-                        if width > ds._series_capacity:
-                            ds._series_capacity = 2 * width
-                            self._rings = None          # the next epoch allocates its staging sets at the new capacity
-                        st = free.popleft()
-                        ev = busy.pop(id(st), None)
-                        if ev is not None:
-                            ev.synchronize()            # the copy that last read this staging set has finished
-                        if st["series"].shape[1] < width:
-                            st["series"] = torch.empty((st["capacity"], ds._series_capacity), dtype=torch.float32, pin_memory=self._pin)
-                        inflight.append(ds.submit(local, flips, st, width))
-                    if not inflight:
-                        break
-                    st = inflight.popleft().wait()
-                    if copy_stream is not None:
-                        with torch.cuda.stream(copy_stream):
-                            out = _batch_from_staging(st, self.device, non_blocking=True)
-                            ev = torch.cuda.Event()
-                            ev.record(copy_stream)
-                        busy[id(st)] = ev
-                    else:
-                        out, ev = _batch_from_staging(st, self.device), None
-                    free.append(st)
-                    if not put((out, ev, None)):
-                        return
-                put(DONE)
-            except BaseException as e:       # delivered to the consumer in order, after the batches decoded before it
-                put((None, None, e))
-            finally:
-                while inflight:              # never leave the pool writing into buffers we are about to drop
-                    try:
-                        inflight.popleft().wait()
-                    except Exception:
-                        pass
-
-        th = threading.Thread(target=producer, name="mau-tile-stager", daemon=True)
-        th.start()
-        try:
-            while True:
-                item = handoff.get()
-                if item is DONE:
-                    break
-                out, ev, err = item
-                if err is not None:
-                    raise err
+        def top_up():
+            while free and len(inflight) < self.prefetch:
+                gb = next(it, None)
+                if gb is None:
+                    return
+                flips = self._flips(gb)
+                local = self._local(gb)
+                # the reference pads every series to the longest of the batch and the LSTM runs over that padding
+                # (src/dataset.py:106, src/model.py:29-33): ranks pad to the longest series of the *global* batch
+                width = max(ds.probe(i)[7] for i in gb) if self.world_size > 1 else 0
+                if width > ds._series_capacity:
+                    ds._series_capacity = 2 * width
+                    self._rings = None          # staging sets of the next epoch are allocated at the new capacity
+                st = free.popleft()
+                if st["series"].shape[1] < width:
+                    st["series"] = torch.empty((st["capacity"], ds._series_capacity), dtype=torch.float32, pin_memory=self._pin)
+                ev = busy.pop(id(st), None)
                 if ev is not None:
+                    ev.synchronize()          # the copy that last read this staging set has finished
+                inflight.append(ds.submit(local, flips, st, width))
+
+        def stage(block: bool) -> bool:
+            """Move the oldest decoded batch to the device (asynchronously on the copy stream)."""
+            if not inflight or (not block and not inflight[0].done()):
+                return False
+            st = inflight.popleft().wait()
+            if copy_stream is not None:
+                with torch.cuda.stream(copy_stream):
+                    out = _batch_from_staging(st, self.device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                busy[id(st)] = ev
+            else:
+                out, ev = _batch_from_staging(st, self.device), None
+            staged.append((out, ev))
+            free.append(st)
+            top_up()
+            return True
+
+        try:
+            top_up()
+            while staged or stage(True):
+                out, ev = staged.popleft()
+                stage(False)          # the next batch's H2D starts now if it is decoded: it overlaps this batch's step
+                if ev is not None:    # even when the caller synchronises every step (loss.item(), src/train.py:258)
                     cur = torch.cuda.current_stream(self.device)
                     cur.wait_event(ev)
                     for t in out:
@@ -500,8 +475,11 @@ class TileLoader:
                             t.record_stream(cur)
                 yield out
         finally:
-            stop.set()
-            th.join()
+            while inflight:           # never leave the pool writing into buffers we are about to drop
+                try:
+                    inflight.popleft().wait()
+                except Exception:
+                    pass
 
 
 def create_dataloader(split: str, batch_size: int, shuffle: bool, dataset_type: str, transform=None, num_workers: int = 0,
