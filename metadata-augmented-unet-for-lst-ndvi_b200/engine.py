@@ -339,10 +339,23 @@ class HotPathFn(torch.autograd.Function):
 # ---------------------------------------------------------------------- #
 # stand-alone operators of the path (loss terms, evaluation metrics)
 # ---------------------------------------------------------------------- #
+def _dev_f32(t: torch.Tensor, name: str, like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The kernels read raw device pointers: insist on a CUDA tensor (on the same device as ``like``) and hand back a
+    contiguous fp32 view of it (a no-op for the tensors the reference's callers hold)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"mau_b200: {name} must be a CUDA tensor (no CPU fallback), got device {t.device}")
+    if like is not None and t.device != like.device:
+        raise RuntimeError(f"Expected all tensors to be on the same device: {name} is on {t.device}, expected {like.device}")
+    return t.contiguous().float()
+
+
 def loss_terms(pred: torch.Tensor, target: torch.Tensor, kind: str = "l1", lambda_grad: float = 0.1,
                need_grad: bool = True):
     """L1|MSE + lambda * gradient-difference loss and its gradient w.r.t. pred in one pass
     (reference src/utils/losses.py:5-25,33,67-70).  Returns (losses[4] tensor, grad or None)."""
+    pred, target = _dev_f32(pred, "pred"), _dev_f32(target, "target", pred)
+    if pred.dim() != 4 or target.shape != pred.shape:
+        raise RuntimeError(f"pred and target must both be [B,C,H,W], got {tuple(pred.shape)} and {tuple(target.shape)}")
     B, Cc, H, W = pred.shape
     losses = torch.zeros(4, device=pred.device, dtype=torch.float32)
     grad = torch.empty_like(pred) if need_grad else None
@@ -383,6 +396,12 @@ def eval_metrics(maps: torch.Tensor, pred: torch.Tensor, target: torch.Tensor,
                  temp_mean: float = 0.0, temp_std: float = 0.0):
     """Device version of test/evaluate.py:210-275.  Returns (dw_map int64 [B,H,W],
     sums float64 [B,C,10,3] = {count, sum|d|, sum d^2} for overall + 9 DW classes)."""
+    pred = _dev_f32(pred, "pred")
+    target, maps = _dev_f32(target, "target", pred), _dev_f32(maps, "maps", pred)
+    if pred.dim() != 4 or target.shape != pred.shape or maps.dim() != 4 or maps.shape[0] != pred.shape[0] \
+            or maps.shape[2:] != pred.shape[2:] or maps.shape[1] < 9:
+        raise RuntimeError(f"eval_metrics expects maps [B,>=9,H,W] and pred / target [B,C,H,W], got {tuple(maps.shape)}, "
+                           f"{tuple(pred.shape)}, {tuple(target.shape)}")
     B, Cc, H, W = pred.shape
     dw = torch.empty(B, H, W, device=pred.device, dtype=torch.int64)
     sums = torch.zeros(B, Cc, 10, 3, device=pred.device, dtype=torch.float64)

@@ -148,9 +148,17 @@ class _EngineNet(nn.Module):
         plan = self._plan_for(B, H, W, T, self.training, maps.device, shared)
         if self.training and getattr(self, "_dp", None) is not None:
             self._dp.prepare_plan(plan)          # SyncBN hook (data-parallel training)
+        # the engine reads raw device pointers: an input left on the host (or on another GPU) must fail here, like
+        # PyTorch's "Expected all tensors to be on the same device", not as an illegal address inside a kernel
+        for name, t, used in (("temp_series", temp_series, plan.uses_series), ("metadata", metadata, plan.uses_metadata)):
+            if used and t.device != maps.device:
+                raise RuntimeError(f"Expected all tensors to be on the same device: maps is on {maps.device}, {name} on {t.device}")
+        if plan.uses_series and (temp_series.dim() != 2 or T < 1 or temp_series.shape[0] != (1 if shared else B)):
+            raise RuntimeError(f"temp_series must be [{B},T] with T >= 1, got {tuple(temp_series.shape)}")
         maps = maps.contiguous().float()
-        temp_series = temp_series.contiguous().float()
-        metadata = metadata.contiguous().float()
+        # an ignored argument (flag off, src/model.py:263-264) never crosses the ABI, wherever it lives
+        temp_series = temp_series.contiguous().float() if plan.uses_series else maps.new_empty(0)
+        metadata = metadata.contiguous().float() if plan.uses_metadata else maps.new_empty(0)
         if metadata.dim() == 2 and metadata.shape[0] != B and plan.uses_metadata:
             raise RuntimeError(f"metadata must have {B} rows, got {metadata.shape[0]}")
         uses_meta = plan.uses_metadata

@@ -568,3 +568,36 @@ def test_unusual_shapes_eval_and_train_fp32(case):
             continue
         gn = float(grads[n].norm())
         assert float((p.grad.cpu() - grads[n]).norm()) <= 2e-2 * gn + 2e-6, n
+
+
+def test_inputs_left_on_the_host_raise_instead_of_faulting():
+    """The engine reads raw device pointers; a tensor forgotten on the CPU must surface as PyTorch's usual
+    RuntimeError, not as an illegal address inside a kernel (which would poison the CUDA context)."""
+    kw = dict(temporal_embeddings=True, metadata_embeddings=True)
+    m = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 16, 32, 2, base_filters=16, **kw).cuda().eval()
+    x, ts, md, tgt = O.synthetic_batch(2, 32, 32, T=12, seed=3)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="same device"):
+            m(x.cuda(), ts.cuda(), md)
+        with pytest.raises(RuntimeError, match="same device"):
+            m(x.cuda(), ts, md.cuda())
+        with pytest.raises(RuntimeError, match="temp_series"):
+            m(x.cuda(), ts[:1].cuda(), md.cuda())
+        with pytest.raises(RuntimeError, match="temp_series"):
+            m(x.cuda(), ts.cuda()[:, :0], md.cuda())
+        with pytest.raises(RuntimeError):
+            m(x, ts, md)
+        y = m(x.cuda(), ts.cuda(), md.cuda())           # the context is still healthy
+    assert torch.isfinite(y).all()
+    # a model that ignores the series / metadata accepts them wherever they live (src/model.py:263-264)
+    m0 = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 16, 32, 2, base_filters=16, temporal_embeddings=False,
+                                 metadata_embeddings=False).cuda().eval()
+    with torch.no_grad():
+        assert torch.isfinite(m0(x.cuda(), ts, md)).all()
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        engine.eval_metrics(x, y, tgt.cuda())
+    with pytest.raises(RuntimeError, match="same device|CUDA tensor"):
+        engine.loss_terms(y, tgt)
+    with pytest.raises(RuntimeError, match=r"\[B,C,H,W\]"):
+        engine.loss_terms(y, tgt.cuda()[:, :1])
+    torch.cuda.synchronize()
