@@ -510,9 +510,13 @@ void reverse_rows(float* p, int64_t rows, int64_t w) {  // np.flip(x, axis=2) of
 // the first 64 KiB are decoded into a scratch buffer (header + the start of the payload), the rest straight into
 // the destination, whose first 64 KiB minus header then serve as the match history.  Stored members are copied
 // from the mapping.  Anything else (other dtypes under deflate, MAU_TILES_FLAG_ZLIB) streams through zlib.
+// `flip_w` > 0 additionally reverses every run of flip_w floats of the payload (np.flip over the last axis of a
+// C-ordered array whose last extent is flip_w).  On the fast path this happens chunk by chunk while the decoded bytes
+// are still in cache, as does the CRC: rows are reversed once they lie more than 32 KiB (the DEFLATE window) behind
+// the decode position, so the match history in front of the decoder stays in stream order.
 template <typename Place>
-NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool check_crc, bool force_zlib, Place&& place) {
-  constexpr size_t kHead = 65536;
+NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool check_crc, bool force_zlib, int64_t flip_w, Place&& place) {
+  constexpr size_t kHead = 65536, kChunk = 256 * 1024, kWindow = 32768;
   const uint8_t* map_end = mp.base + mp.size;
   auto check_size = [&](const NpyHeader& h, size_t header_total) {
     if (uint64_t(h.count) * h.itemsize + header_total != M.usize)
@@ -525,7 +529,16 @@ NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool
     NpyHeader h = read_npy_header_mem(M.data, M.usize, &header_total, mp, name);
     check_size(h, header_total);
     float* dst = place(h);
-    convert(h.dtype, M.data + header_total, dst, h.count);
+    if (flip_w > 0 && h.dtype == F4 && h.count % flip_w == 0) {  // one pass over the payload
+      const uint8_t* src = M.data + header_total;  // row by row: copy, then reverse while the row is in L1
+      for (int64_t r = 0; r < h.count; r += flip_w) {
+        memcpy(dst + r, src + 4 * r, size_t(flip_w) * 4);
+        std::reverse(dst + r, dst + r + flip_w);
+      }
+    } else {
+      convert(h.dtype, M.data + header_total, dst, h.count);
+      if (flip_w > 0) reverse_rows(dst, h.count / flip_w, flip_w);
+    }
     if (check_crc && crc32_update(0, M.data, M.usize) != M.crc) fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp.path.c_str(), name);
     return h;
   }
@@ -545,10 +558,26 @@ NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool
         const uint64_t payload = uint64_t(h.count) * 4;
         const size_t n0 = c0 - header_total;
         memcpy(dst, S + header_total, n0);
-        if (payload > n0 && inf.run(dst, dst + n0, dst + payload) != dst + payload) fail(MAU_TILES_E_FORMAT, "'%s': deflate stream of %s ends early", mp.path.c_str(), name);
+        uint32_t crc = check_crc ? crc32_update(0, S, c0) : 0;
+        const uint64_t row_bytes = uint64_t(flip_w) * 4;
+        uint64_t rows_done = 0;
+        auto flip_rows_before = [&](uint64_t limit) {  // rows that end at or before byte `limit` of the payload
+          if (flip_w <= 0) return;
+          for (uint64_t rows = limit / row_bytes; rows_done < rows; ++rows_done) {
+            float* r = reinterpret_cast<float*>(dst + rows_done * row_bytes);
+            std::reverse(r, r + flip_w);
+          }
+        };
+        for (uint64_t pos = n0; pos < payload;) {
+          const uint64_t stop = std::min<uint64_t>(payload, pos + kChunk);
+          if (inf.run(dst, dst + pos, dst + stop) != dst + stop) fail(MAU_TILES_E_FORMAT, "'%s': deflate stream of %s ends early", mp.path.c_str(), name);
+          if (check_crc) crc = crc32_update(crc, dst + pos, stop - pos);
+          pos = stop;
+          if (pos > kWindow) flip_rows_before(pos - kWindow);
+        }
         if (!inf.done()) fail(MAU_TILES_E_FORMAT, "'%s': member %s holds more data than its directory entry says", mp.path.c_str(), name);
-        if (check_crc && crc32_update(crc32_update(0, S, c0), dst + n0, payload - n0) != M.crc)
-          fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp.path.c_str(), name);
+        if (check_crc && crc != M.crc) fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp.path.c_str(), name);
+        flip_rows_before(payload);
         return h;
       }
     } catch (const mau_inflate::Error& e) {
@@ -557,8 +586,10 @@ NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool
   }
   MemberStream s(mp, M, name, check_crc);
   NpyHeader h = read_npy_header(s, mp, name);
-  read_payload(s, h, place(h));
+  float* dst = place(h);
+  read_payload(s, h, dst);
   s.finish();
+  if (flip_w > 0) reverse_rows(dst, h.count / flip_w, flip_w);
   return h;
 }
 
@@ -656,21 +687,19 @@ void decode_sample(mau_tiles* t, Batch* b, int64_t slot, int parts) {
   auto image = [&](int m, float* base, const int64_t* d) {
     if (!base) return;
     const Member& M = need(m);
-    float* dst = nullptr;
-    NpyHeader h = read_member(mp, M, kMemberNames[m], crc, zl, [&](const NpyHeader& hd) {
+    NpyHeader h = read_member(mp, M, kMemberNames[m], crc, zl, flip ? d[2] : 0, [&](const NpyHeader& hd) {
       if (hd.ndim != 3 || hd.shape[0] != d[0] || hd.shape[1] != d[1] || hd.shape[2] != d[2])
         fail(MAU_TILES_E_SHAPE, "'%s': %s has shape (%lld,%lld,%lld)[ndim %d], the batch expects (%lld,%lld,%lld)", mp.path.c_str(), kMemberNames[m], (long long)hd.shape[0],
              (long long)hd.shape[1], (long long)hd.shape[2], hd.ndim, (long long)d[0], (long long)d[1], (long long)d[2]);
-      return dst = base + slot * hd.count;
+      return base + slot * hd.count;
     });
-    if (flip) reverse_rows(dst, d[0] * d[1], d[2]);
     bytes += h.count * h.itemsize;
   };
   if (parts & PART_INPUT) image(M_INPUT, b->input, b->dims);
   if (parts & PART_REST) {
     image(M_TARGET, b->target, b->dims + 3);
     if (b->metadata) {
-      NpyHeader h = read_member(mp, need(M_METADATA), kMemberNames[M_METADATA], crc, zl, [&](const NpyHeader& hd) {
+      NpyHeader h = read_member(mp, need(M_METADATA), kMemberNames[M_METADATA], crc, zl, 0, [&](const NpyHeader& hd) {
         if (hd.ndim != 1 || hd.shape[0] != b->dims[6])
           fail(MAU_TILES_E_SHAPE, "'%s': metadata has %lld values[ndim %d], the batch expects %lld", mp.path.c_str(), (long long)hd.count, hd.ndim, (long long)b->dims[6]);
         return b->metadata + slot * b->dims[6];
@@ -679,7 +708,7 @@ void decode_sample(mau_tiles* t, Batch* b, int64_t slot, int parts) {
     }
     if (b->series) {
       float* dst = b->series + slot * b->series_stride;
-      NpyHeader h = read_member(mp, need(M_SERIES), kMemberNames[M_SERIES], crc, zl, [&](const NpyHeader& hd) {
+      NpyHeader h = read_member(mp, need(M_SERIES), kMemberNames[M_SERIES], crc, zl, 0, [&](const NpyHeader& hd) {
         if (hd.ndim != 1) fail(MAU_TILES_E_SHAPE, "'%s': temperature_serie has %d dimensions, expected 1", mp.path.c_str(), hd.ndim);
         if (hd.count > b->series_stride)
           fail(MAU_TILES_E_CAPACITY, "'%s': temperature_serie has %lld values, buffer holds %lld", mp.path.c_str(), (long long)hd.count, (long long)b->series_stride);

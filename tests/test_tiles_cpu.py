@@ -397,3 +397,25 @@ def test_members_larger_than_the_decoder_head_buffer(tmp_path):
         for b, g in enumerate(got):
             ref = O.collate([O.load_sample(f, tf) for f in files[3 * b:3 * b + 3]])
             assert all(torch.equal(a, r) for a, r in zip(g, ref))
+
+
+@pytest.mark.parametrize("compressed,use_zlib,dtype", [(False, False, np.float32), (True, True, np.float32), (True, False, np.float64),
+                                                       (False, False, np.float64), (True, False, np.float32)])
+def test_flip_on_every_decode_path(tmp_path, compressed, use_zlib, dtype):
+    # stored members (row-wise reversed copy), zlib streaming, converted dtypes and the chunked fast path all flip alike
+    d = tmp_path / "train"
+    d.mkdir()
+    rng = np.random.default_rng(4)
+    save = np.savez_compressed if compressed else np.savez
+    for i in range(3):
+        save(d / f"F_{i}_0.5_0.25_2019_7_to_2023_7.npz", input=rng.standard_normal((5, 130, 141)).astype(dtype),
+             target=rng.standard_normal((2, 130, 141)).astype(dtype), metadata=rng.standard_normal(4).astype(np.float32),
+             temperature_serie=rng.standard_normal(9).astype(np.float32))
+    ds = D.FuturePredictionDataset("train", processed_dir=str(tmp_path), use_zlib=use_zlib)
+    st = ds.read_batch([0, 1, 2], [True, False, True])
+    files = O.list_split(str(tmp_path), "train")
+    for k, flip in enumerate([True, False, True]):
+        x, md, ts, t1, t2, y = O.load_sample(files[k])
+        assert torch.equal(st["input"][k], x.flip(2) if flip else x)
+        assert torch.equal(st["target"][k], y.flip(2) if flip else y)
+        assert torch.equal(st["metadata"][k], md)
