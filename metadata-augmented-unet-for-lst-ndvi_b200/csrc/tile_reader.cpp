@@ -171,7 +171,9 @@ struct Mapping {
 // ---- ZIP central directory -------------------------------------------------------------------------------
 struct Member {
   uint16_t method = 0;  // 0 stored, 8 deflate
+  uint16_t flags = 0;   // general purpose bits (bit 0: encrypted)
   uint32_t crc = 0;
+  uint32_t dos_time_date = 0;
   uint64_t csize = 0, usize = 0;
   const uint8_t* data = nullptr;  // first byte of the (compressed) payload
   bool found = false;
@@ -180,7 +182,9 @@ struct Member {
 enum { M_INPUT = 0, M_TARGET = 1, M_METADATA = 2, M_SERIES = 3, M_COUNT = 4 };
 const char* const kMemberNames[M_COUNT] = {"input.npy", "target.npy", "metadata.npy", "temperature_serie.npy"};
 
-void parse_zip(const Mapping& mp, Member out[M_COUNT]) {
+// Walks the central directory and calls visit(name, name_len, member) for every entry (payload extent validated).
+template <typename Visit>
+void walk_zip(const Mapping& mp, Visit&& visit) {
   const size_t n = mp.size;
   if (n < 22) fail(MAU_TILES_E_FORMAT, "'%s' is not a zip archive (too short)", mp.path.c_str());
   // end-of-central-directory record: last 22 bytes + up to 64 KiB of comment
@@ -230,25 +234,41 @@ void parse_zip(const Mapping& mp, Member out[M_COUNT]) {
       }
       xp += 4u + sz;
     }
-    for (int m = 0; m < M_COUNT; ++m) {
-      size_t L = strlen(kMemberNames[m]);
-      if (nlen == L && memcmp(name, kMemberNames[m], L) == 0) {
-        if (flags & 1) fail(MAU_TILES_E_FORMAT, "'%s': member %s is encrypted", mp.path.c_str(), kMemberNames[m]);
-        if (method != 0 && method != 8) fail(MAU_TILES_E_FORMAT, "'%s': member %s uses compression method %u (only stored/deflate)", mp.path.c_str(), kMemberNames[m], method);
-        const uint8_t* lh = mp.at(lho, 30);
-        if (rd32(lh) != 0x04034b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad local header of %s", mp.path.c_str(), kMemberNames[m]);
-        uint64_t start = lho + 30 + rd16(lh + 26) + rd16(lh + 28);
-        Member& M = out[m];  // duplicate names: zipfile keeps the last entry, so do we
-        M.method = method;
-        M.crc = crc;
-        M.csize = csize;
-        M.usize = usize;
-        M.data = mp.at(start, csize);
-        M.found = true;
-      }
+    {
+      const uint8_t* lh = mp.at(lho, 30);
+      if (rd32(lh) != 0x04034b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad local header of %.*s", mp.path.c_str(), int(nlen), name);
+      uint64_t start = lho + 30 + rd16(lh + 26) + rd16(lh + 28);
+      Member M;
+      M.method = method;
+      M.flags = flags;
+      M.crc = crc;
+      M.dos_time_date = rd32(h + 12);
+      M.csize = csize;
+      M.usize = usize;
+      M.data = mp.at(start, csize);
+      M.found = true;
+      visit(name, size_t(nlen), M);
     }
     pos += 46 + uint64_t(nlen) + xlen + clen;
   }
+}
+
+void check_supported(const Mapping& mp, const Member& M, const char* name, size_t nlen) {
+  if (M.flags & 1) fail(MAU_TILES_E_FORMAT, "'%s': member %.*s is encrypted", mp.path.c_str(), int(nlen), name);
+  if (M.method != 0 && M.method != 8)
+    fail(MAU_TILES_E_FORMAT, "'%s': member %.*s uses compression method %u (only stored/deflate)", mp.path.c_str(), int(nlen), name, M.method);
+}
+
+// the four members of a sample (duplicate names: zipfile keeps the last entry, so do we)
+void parse_zip(const Mapping& mp, Member out[M_COUNT]) {
+  walk_zip(mp, [&](const char* name, size_t nlen, const Member& M) {
+    for (int m = 0; m < M_COUNT; ++m) {
+      if (nlen == strlen(kMemberNames[m]) && memcmp(name, kMemberNames[m], nlen) == 0) {
+        check_supported(mp, M, name, nlen);
+        out[m] = M;
+      }
+    }
+  });
 }
 
 // ---- sequential reader over one member (stored or raw deflate), CRC accumulated on the way ----------------
@@ -930,3 +950,137 @@ extern "C" int mau_tiles_inflate(const uint8_t* src, size_t src_len, uint8_t* ds
 }
 
 extern "C" uint32_t mau_tiles_crc32(uint32_t crc, const void* data, size_t n) { return crc32_update(crc, static_cast<const uint8_t*>(data), n); }
+
+// ---- repack: the same archive with stored (uncompressed) members ---------------------------------------------
+namespace {
+
+void put16(std::vector<uint8_t>& v, uint32_t x) {
+  v.push_back(uint8_t(x));
+  v.push_back(uint8_t(x >> 8));
+}
+void put32(std::vector<uint8_t>& v, uint32_t x) {
+  put16(v, x & 0xFFFFu);
+  put16(v, x >> 16);
+}
+
+// all bytes of one member, CRC verified
+void member_bytes(const Mapping& mp, const Member& M, const std::string& name, std::vector<uint8_t>& out) {
+  out.resize(size_t(M.usize));
+  const uint8_t* map_end = mp.base + mp.size;
+  if (M.method == 0) {
+    if (M.csize != M.usize) fail(MAU_TILES_E_FORMAT, "'%s': stored member %s has differing sizes", mp.path.c_str(), name.c_str());
+    if (M.usize) memcpy(out.data(), M.data, size_t(M.usize));
+  } else if (size_t(map_end - (M.data + M.csize)) >= 16) {
+    try {
+      auto inf = std::make_unique<mau_inflate::Inflater>();
+      inf->init(M.data, size_t(M.csize), map_end);
+      uint8_t* end = out.data() + out.size();
+      if (inf->run(out.data(), out.data(), end) != end || !inf->done())
+        fail(MAU_TILES_E_FORMAT, "'%s': member %s does not decode to the size its directory entry gives", mp.path.c_str(), name.c_str());
+    } catch (const mau_inflate::Error& e) {
+      fail(MAU_TILES_E_FORMAT, "'%s': error while decompressing %s (%s)", mp.path.c_str(), name.c_str(), e.what);
+    }
+  } else {
+    MemberStream s(mp, M, name.c_str(), false);
+    if (M.usize) s.read(out.data(), M.usize);
+  }
+  if (crc32_update(0, out.data(), out.size()) != M.crc) fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp.path.c_str(), name.c_str());
+}
+
+void write_all(int fd, const void* p, size_t n, const std::string& path) {
+  const uint8_t* q = static_cast<const uint8_t*>(p);
+  while (n) {
+    ssize_t w = ::write(fd, q, n);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      fail(MAU_TILES_E_IO, "cannot write '%s': %s", path.c_str(), strerror(errno));
+    }
+    q += w;
+    n -= size_t(w);
+  }
+}
+
+}  // namespace
+
+extern "C" int mau_tiles_repack(const char* src_path, const char* dst_path) {
+  return guard([&]() -> int {
+    if (!src_path || !dst_path) return set_err(MAU_TILES_E_ARG, "mau_tiles_repack: null path");
+    Mapping mp(src_path);
+    struct Item {
+      std::string name;
+      Member m;
+    };
+    std::vector<Item> items;
+    walk_zip(mp, [&](const char* name, size_t nlen, const Member& M) {
+      check_supported(mp, M, name, nlen);
+      if (M.usize >= 0xFFFFFFFFull) fail(MAU_TILES_E_FORMAT, "'%s': member %.*s is too large for a plain ZIP entry", mp.path.c_str(), int(nlen), name);
+      items.push_back(Item{std::string(name, nlen), M});
+    });
+    const std::string dst(dst_path), tmp = dst + ".tmp" + std::to_string(long(getpid())) + "." + std::to_string(long(syscall(SYS_gettid)));
+    int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+    if (fd < 0) fail(MAU_TILES_E_IO, "cannot create '%s': %s", tmp.c_str(), strerror(errno));
+    try {
+      std::vector<uint8_t> central, head, body;
+      uint64_t offset = 0;
+      for (const Item& it : items) {
+        member_bytes(mp, it.m, it.name, body);
+        if (offset + 30 + it.name.size() + body.size() >= 0xFFFFFFFFull) fail(MAU_TILES_E_FORMAT, "'%s': repacked archive would need ZIP64", mp.path.c_str());
+        head.clear();
+        put32(head, 0x04034b50u);
+        put16(head, 20);               // version needed
+        put16(head, 0);                // flags
+        put16(head, 0);                // method: stored
+        put32(head, it.m.dos_time_date);
+        put32(head, it.m.crc);
+        put32(head, uint32_t(body.size()));
+        put32(head, uint32_t(body.size()));
+        put16(head, uint32_t(it.name.size()));
+        put16(head, 0);                // no extra field
+        head.insert(head.end(), it.name.begin(), it.name.end());
+        write_all(fd, head.data(), head.size(), tmp);
+        write_all(fd, body.data(), body.size(), tmp);
+        put32(central, 0x02014b50u);
+        put16(central, 20);            // version made by
+        put16(central, 20);
+        put16(central, 0);
+        put16(central, 0);
+        put32(central, it.m.dos_time_date);
+        put32(central, it.m.crc);
+        put32(central, uint32_t(body.size()));
+        put32(central, uint32_t(body.size()));
+        put16(central, uint32_t(it.name.size()));
+        put16(central, 0);             // extra
+        put16(central, 0);             // comment
+        put16(central, 0);             // disk
+        put16(central, 0);             // internal attributes
+        put32(central, 0);             // external attributes
+        put32(central, uint32_t(offset));
+        central.insert(central.end(), it.name.begin(), it.name.end());
+        offset += head.size() + body.size();
+      }
+      if (items.size() >= 0xFFFFu) fail(MAU_TILES_E_FORMAT, "'%s': too many members", mp.path.c_str());
+      std::vector<uint8_t> eocd;
+      put32(eocd, 0x06054b50u);
+      put16(eocd, 0);
+      put16(eocd, 0);
+      put16(eocd, uint32_t(items.size()));
+      put16(eocd, uint32_t(items.size()));
+      put32(eocd, uint32_t(central.size()));
+      put32(eocd, uint32_t(offset));
+      put16(eocd, 0);
+      write_all(fd, central.data(), central.size(), tmp);
+      write_all(fd, eocd.data(), eocd.size(), tmp);
+      if (::close(fd) != 0) {
+        fd = -1;
+        fail(MAU_TILES_E_IO, "cannot close '%s': %s", tmp.c_str(), strerror(errno));
+      }
+      fd = -1;
+      if (::rename(tmp.c_str(), dst.c_str()) != 0) fail(MAU_TILES_E_IO, "cannot rename '%s' to '%s': %s", tmp.c_str(), dst.c_str(), strerror(errno));
+    } catch (...) {
+      if (fd >= 0) ::close(fd);
+      ::unlink(tmp.c_str());
+      throw;
+    }
+    return 0;
+  });
+}

@@ -44,7 +44,7 @@ FLAG_NO_CRC, FLAG_ZLIB, FLAG_NICE = 1, 2, 4
 # every symbol include/mau_tiles.h declares (tests check the .so exports all of them)
 EXPORTS = ("mau_tiles_last_error", "mau_tiles_version", "mau_tiles_open", "mau_tiles_close", "mau_tiles_count",
            "mau_tiles_threads", "mau_tiles_probe", "mau_tiles_read_batch", "mau_tiles_submit", "mau_tiles_wait",
-           "mau_tiles_done", "mau_tiles_inflate", "mau_tiles_crc32", "mau_tiles_stats")
+           "mau_tiles_done", "mau_tiles_repack", "mau_tiles_inflate", "mau_tiles_crc32", "mau_tiles_stats")
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -79,6 +79,7 @@ def lib():
         L.mau_tiles_done.argtypes = [C.c_void_p, C.c_int64]
         L.mau_tiles_stats.argtypes = [C.c_void_p, p64, p64, p64]
         L.mau_tiles_inflate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.mau_tiles_repack.argtypes = [C.c_char_p, C.c_char_p]
         L.mau_tiles_crc32.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
         L.mau_tiles_crc32.restype = C.c_uint32
         _lib = L
@@ -97,6 +98,26 @@ def _raise(code: int):
     if code == E_ARG:
         raise IndexError(msg) if "out of range" in msg else ValueError(msg)
     raise ValueError(msg)                         # BadZipFile / unpicklable member / dtype
+
+
+def repack_split(src_dir: str, dst_dir: str, workers: int = 0) -> int:
+    """Rewrites every ``*.npz`` of ``src_dir`` into ``dst_dir`` with stored (uncompressed) members -- the format
+    ``np.savez`` writes, still readable by ``np.load`` and by the reference's loader.  Decoding such archives is a
+    memcpy instead of an inflate: on hosts where the decode, not the GPU, bounds training from disk,
+    trade 3.5x the disk space for it once.  Returns the number of archives written."""
+    from concurrent.futures import ThreadPoolExecutor
+    names = sorted(f for f in os.listdir(src_dir) if f.endswith(".npz"))
+    os.makedirs(dst_dir, exist_ok=True)
+    L = lib()
+
+    def one(name):
+        rc = L.mau_tiles_repack(os.fsencode(os.path.join(src_dir, name)), os.fsencode(os.path.join(dst_dir, name)))
+        if rc:
+            _raise(rc)      # last_error is thread-local and this is the thread that made the call
+
+    with ThreadPoolExecutor(max_workers=workers or os.cpu_count() or 4) as ex:
+        list(ex.map(one, names))
+    return len(names)
 
 
 def parse_dates(filename: str):

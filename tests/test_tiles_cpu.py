@@ -419,3 +419,28 @@ def test_flip_on_every_decode_path(tmp_path, compressed, use_zlib, dtype):
         assert torch.equal(st["input"][k], x.flip(2) if flip else x)
         assert torch.equal(st["target"][k], y.flip(2) if flip else y)
         assert torch.equal(st["metadata"][k], md)
+
+
+def test_repack_to_stored_members_is_lossless_and_numpy_readable(synth, tmp_path):
+    import zipfile
+    src, dst = os.path.join(synth, "train"), str(tmp_path / "stored" / "train")
+    extra = os.path.join(src, "Extra Members_1_0.5_0.25_2019_7_to_2023_7.npz")
+    np.savez_compressed(extra, input=np.ones((23, 20, 28), np.float32), target=np.zeros((2, 20, 28), np.float32), metadata=np.zeros(4, np.float32),
+                        temperature_serie=np.ones(33, np.float32), note=np.arange(7), empty=np.zeros((0, 3)))
+    try:
+        assert D.repack_split(src, dst, workers=3) == 12
+        for name in sorted(os.listdir(src)):
+            with np.load(os.path.join(src, name)) as a, np.load(os.path.join(dst, name)) as b:
+                assert a.files == b.files
+                for k in a.files:
+                    assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k])
+            with zipfile.ZipFile(os.path.join(dst, name)) as z:
+                assert z.testzip() is None and all(i.compress_type == zipfile.ZIP_STORED for i in z.infolist())
+        a = list(D.create_dataloader("train", 5, False, "future", transform=D.RandomFlip(2), device="cpu", processed_dir=synth))
+        b = list(D.create_dataloader("train", 5, False, "future", transform=D.RandomFlip(2), device="cpu", processed_dir=str(tmp_path / "stored")))
+        assert len(a) == len(b) == 3 and all(torch.equal(x, y) for ba, bb in zip(a, b) for x, y in zip(ba, bb))
+        assert not [f for f in os.listdir(dst) if ".tmp" in f]
+    finally:
+        os.remove(extra)
+    with pytest.raises(FileNotFoundError):
+        D.lib().mau_tiles_repack(b"/nonexistent/a.npz", os.fsencode(str(tmp_path / "x.npz"))) and D._raise(D.E_IO)
