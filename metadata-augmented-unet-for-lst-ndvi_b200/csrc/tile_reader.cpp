@@ -4,9 +4,10 @@
 // with the members input.npy [23,H,W], target.npy [2,H,W], metadata.npy [4], temperature_serie.npy [T].
 // The reference reads it with np.load on the training thread (src/dataset.py:54-59) and stacks / pads the
 // batch in collate_fn (src/dataset.py:87-108).  Here a batch is decoded by a pool of worker threads straight
-// into the caller's (pinned) batch buffers: the archive is mmap'ed, the ZIP central directory gives the
+// into the caller's (pinned) batch buffers: the ZIP central directory (one pread of the file's tail) gives the
 // member extents, each member is inflated directly into its slot of the batch (NPY header peeled off the
-// front of the same deflate stream), CRC-32 checked like zipfile does, optionally flipped in place.
+// front of the same deflate stream) or, if stored, pread there; CRC-32 checked like zipfile does and rows flipped
+// while the decoded bytes are still in cache.
 // Host-only: C++17, pthreads, zlib.
 #include "../../include/mau_tiles.h"
 #include "inflate_fast.h"
@@ -130,41 +131,72 @@ uint32_t crc32_update(uint32_t crc, const uint8_t* p, uint64_t n) {
   return crc;
 }
 
-// ---- a read-only mapping of one archive ------------------------------------------------------------------
-struct Mapping {
-  const uint8_t* base = nullptr;
+// ---- one archive, read with pread ------------------------------------------------------------------------
+// The first version mmap'ed every archive in every task.  With 16 decode threads in one process that serialises on
+// the address-space lock (mmap / munmap take it exclusively, every munmap ends in TLB-shootdown interrupts on all
+// cores running our threads -- including the one launching the GPU step) and costs a page fault per 4 KiB read:
+// stored archives decoded at 819 tiles/s with all threads busy against 1 460 when throttled by the training step.
+// pread() into the destination (stored fp32 payloads: zero extra copies) or into a per-thread arena (compressed
+// members, the directory) has none of that.
+std::vector<uint8_t>& arena() {
+  thread_local std::vector<uint8_t> a;
+  return a;
+}
+
+struct Archive {
+  int fd = -1;
   size_t size = 0;
   std::string path;
-  explicit Mapping(const std::string& p) : path(p) {
-    int fd = ::open(p.c_str(), O_RDONLY | O_CLOEXEC);
+  explicit Archive(const std::string& p) : path(p) {
+    fd = ::open(p.c_str(), O_RDONLY | O_CLOEXEC);
     if (fd < 0) fail(MAU_TILES_E_IO, "cannot open '%s': %s", p.c_str(), strerror(errno));
     struct stat st;
     if (fstat(fd, &st) != 0) {
       int e = errno;
       ::close(fd);
+      fd = -1;
       fail(MAU_TILES_E_IO, "cannot stat '%s': %s", p.c_str(), strerror(e));
     }
     size = size_t(st.st_size);
     if (size == 0) {
       ::close(fd);
+      fd = -1;
       fail(MAU_TILES_E_FORMAT, "'%s' is empty (not a zip archive)", p.c_str());
     }
-    void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
-    int e = errno;
-    ::close(fd);
-    if (m == MAP_FAILED) fail(MAU_TILES_E_IO, "cannot mmap '%s': %s", p.c_str(), strerror(e));
-    base = static_cast<const uint8_t*>(m);
-    madvise(m, size, MADV_SEQUENTIAL);
   }
-  ~Mapping() {
-    if (base) munmap(const_cast<uint8_t*>(base), size);
+  ~Archive() {
+    if (fd >= 0) ::close(fd);
   }
-  Mapping(const Mapping&) = delete;
-  Mapping& operator=(const Mapping&) = delete;
-  const uint8_t* at(uint64_t off, uint64_t len) const {
+  Archive(const Archive&) = delete;
+  Archive& operator=(const Archive&) = delete;
+  void check_range(uint64_t off, uint64_t len) const {
     if (off > size || len > size - off) fail(MAU_TILES_E_FORMAT, "'%s': truncated archive (need %llu bytes at %llu of %zu)", path.c_str(),
                                              (unsigned long long)len, (unsigned long long)off, size);
-    return base + off;
+  }
+  // exactly len bytes at off -> dst
+  void read_at(void* dst, uint64_t off, uint64_t len) const {
+    check_range(off, len);
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    while (len) {
+      ssize_t r = ::pread(fd, d, size_t(std::min<uint64_t>(len, 1u << 30)), off_t(off));
+      if (r < 0) {
+        if (errno == EINTR) continue;
+        fail(MAU_TILES_E_IO, "cannot read '%s': %s", path.c_str(), strerror(errno));
+      }
+      if (r == 0) fail(MAU_TILES_E_FORMAT, "'%s': truncated archive (file shrank while reading)", path.c_str());
+      d += r;
+      off += uint64_t(r);
+      len -= uint64_t(r);
+    }
+  }
+  // the range copied into this thread's arena, followed by `slack` zero bytes; valid until the next fetch on this thread
+  const uint8_t* fetch(uint64_t off, uint64_t len, size_t slack = 0) const {
+    check_range(off, len);
+    std::vector<uint8_t>& a = arena();
+    if (a.size() < len + slack) a.resize(size_t(len + slack));
+    read_at(a.data(), off, len);
+    if (slack) memset(a.data() + len, 0, slack);
+    return a.data();
   }
 };
 
@@ -175,7 +207,7 @@ struct Member {
   uint32_t crc = 0;
   uint32_t dos_time_date = 0;
   uint64_t csize = 0, usize = 0;
-  const uint8_t* data = nullptr;  // first byte of the (compressed) payload
+  uint64_t data_off = 0;  // file offset of the first byte of the (compressed) payload
   bool found = false;
 };
 
@@ -184,32 +216,53 @@ const char* const kMemberNames[M_COUNT] = {"input.npy", "target.npy", "metadata.
 
 // Walks the central directory and calls visit(name, name_len, member) for every entry (payload extent validated).
 template <typename Visit>
-void walk_zip(const Mapping& mp, Visit&& visit) {
+void walk_zip(const Archive& mp, Visit&& visit) {
   const size_t n = mp.size;
   if (n < 22) fail(MAU_TILES_E_FORMAT, "'%s' is not a zip archive (too short)", mp.path.c_str());
-  // end-of-central-directory record: last 22 bytes + up to 64 KiB of comment
-  size_t lo = n > 22 + 65535 ? n - 22 - 65535 : 0;
-  size_t eocd = size_t(-1);
-  for (size_t p = n - 22 + 1; p-- > lo;) {
-    if (rd32(mp.base + p) == 0x06054b50u) {
-      eocd = p;
-      break;
+  // the tail of the file holds the end-of-central-directory record (last 22 bytes + up to 64 KiB of comment) and,
+  // for the small directories of these archives, the central directory itself: one pread gets both
+  thread_local std::vector<uint8_t> tail, spill;
+  size_t tail_len = 0, tail_off = 0, eocd = size_t(-1);
+  for (size_t want : {size_t(8192), size_t(22 + 65535)}) {
+    size_t len = std::min(n, want);
+    if (len == tail_len) break;
+    tail_len = len;
+    tail_off = n - len;
+    if (tail.size() < len) tail.resize(len);
+    mp.read_at(tail.data(), tail_off, len);
+    for (size_t p = len - 22 + 1; p-- > 0;) {
+      if (rd32(tail.data() + p) == 0x06054b50u) {
+        eocd = tail_off + p;
+        break;
+      }
     }
+    if (eocd != size_t(-1)) break;
   }
   if (eocd == size_t(-1)) fail(MAU_TILES_E_FORMAT, "'%s' is not a zip archive (no end-of-central-directory record)", mp.path.c_str());
-  const uint8_t* e = mp.base + eocd;
+  auto view = [&](uint64_t off, uint64_t len) -> const uint8_t* {  // bytes of the file: from the tail if inside, else read
+    mp.check_range(off, len);
+    if (off >= tail_off) return tail.data() + (off - tail_off);
+    if (spill.size() < len) spill.resize(size_t(len));
+    mp.read_at(spill.data(), off, len);
+    return spill.data();
+  };
+  const uint8_t* e = tail.data() + (eocd - tail_off);
   uint64_t entries = rd16(e + 10), cd_size = rd32(e + 12), cd_off = rd32(e + 16);
   if (entries == 0xFFFFu || cd_size == 0xFFFFFFFFu || cd_off == 0xFFFFFFFFu) {
     // ZIP64: locator sits right in front of the EOCD record
-    if (eocd < 20 || rd32(mp.base + eocd - 20) != 0x07064b50u) fail(MAU_TILES_E_FORMAT, "'%s': zip64 locator missing", mp.path.c_str());
-    uint64_t z_off = rd64(mp.base + eocd - 20 + 8);
-    const uint8_t* z = mp.at(z_off, 56);
+    if (eocd < 20) fail(MAU_TILES_E_FORMAT, "'%s': zip64 locator missing", mp.path.c_str());
+    uint8_t loc[20];
+    mp.read_at(loc, eocd - 20, 20);
+    if (rd32(loc) != 0x07064b50u) fail(MAU_TILES_E_FORMAT, "'%s': zip64 locator missing", mp.path.c_str());
+    uint8_t z[56];
+    mp.read_at(z, rd64(loc + 8), 56);
     if (rd32(z) != 0x06064b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad zip64 end record", mp.path.c_str());
     entries = rd64(z + 32);
     cd_size = rd64(z + 40);
     cd_off = rd64(z + 48);
   }
-  const uint8_t* cd = mp.at(cd_off, cd_size);
+  if (cd_size > (uint64_t(1) << 31)) fail(MAU_TILES_E_FORMAT, "'%s': implausible central directory", mp.path.c_str());
+  const uint8_t* cd = view(cd_off, cd_size);
   uint64_t pos = 0;
   for (uint64_t i = 0; i < entries; ++i) {
     if (pos + 46 > cd_size || rd32(cd + pos) != 0x02014b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad central directory entry %llu", mp.path.c_str(), (unsigned long long)i);
@@ -235,7 +288,8 @@ void walk_zip(const Mapping& mp, Visit&& visit) {
       xp += 4u + sz;
     }
     {
-      const uint8_t* lh = mp.at(lho, 30);
+      uint8_t lh[30];
+      mp.read_at(lh, lho, 30);
       if (rd32(lh) != 0x04034b50u) fail(MAU_TILES_E_FORMAT, "'%s': bad local header of %.*s", mp.path.c_str(), int(nlen), name);
       uint64_t start = lho + 30 + rd16(lh + 26) + rd16(lh + 28);
       Member M;
@@ -245,7 +299,8 @@ void walk_zip(const Mapping& mp, Visit&& visit) {
       M.dos_time_date = rd32(h + 12);
       M.csize = csize;
       M.usize = usize;
-      M.data = mp.at(start, csize);
+      mp.check_range(start, csize);
+      M.data_off = start;
       M.found = true;
       visit(name, size_t(nlen), M);
     }
@@ -253,14 +308,14 @@ void walk_zip(const Mapping& mp, Visit&& visit) {
   }
 }
 
-void check_supported(const Mapping& mp, const Member& M, const char* name, size_t nlen) {
+void check_supported(const Archive& mp, const Member& M, const char* name, size_t nlen) {
   if (M.flags & 1) fail(MAU_TILES_E_FORMAT, "'%s': member %.*s is encrypted", mp.path.c_str(), int(nlen), name);
   if (M.method != 0 && M.method != 8)
     fail(MAU_TILES_E_FORMAT, "'%s': member %.*s uses compression method %u (only stored/deflate)", mp.path.c_str(), int(nlen), name, M.method);
 }
 
 // the four members of a sample (duplicate names: zipfile keeps the last entry, so do we)
-void parse_zip(const Mapping& mp, Member out[M_COUNT]) {
+void parse_zip(const Archive& mp, Member out[M_COUNT]) {
   walk_zip(mp, [&](const char* name, size_t nlen, const Member& M) {
     for (int m = 0; m < M_COUNT; ++m) {
       if (nlen == strlen(kMemberNames[m]) && memcmp(name, kMemberNames[m], nlen) == 0) {
@@ -274,13 +329,17 @@ void parse_zip(const Mapping& mp, Member out[M_COUNT]) {
 // ---- sequential reader over one member (stored or raw deflate), CRC accumulated on the way ----------------
 class MemberStream {
  public:
-  MemberStream(const Mapping& mp, const Member& m, const char* name, bool check_crc) : mp_(mp), m_(m), name_(name), check_crc_(check_crc) {
+  // `max_in` bounds how much of a deflated member is fetched (the NPY header sits in the first few hundred bytes:
+  // probing a sample must not read its megabytes).  The compressed bytes live in this thread's arena: no other
+  // fetch on this thread while the stream is in use.
+  MemberStream(const Archive& mp, const Member& m, const char* name, bool check_crc, uint64_t max_in = ~uint64_t(0))
+      : mp_(mp), m_(m), name_(name), check_crc_(check_crc) {
     if (m.method == 8) {
       memset(&z_, 0, sizeof z_);
       if (inflateInit2(&z_, -15) != Z_OK) fail(MAU_TILES_E_FORMAT, "zlib inflateInit2 failed");
       z_init_ = true;
-      in_left_ = m.csize;
-      z_.next_in = const_cast<Bytef*>(m.data);
+      in_left_ = std::min(m.csize, max_in);
+      z_.next_in = const_cast<Bytef*>(mp.fetch(m.data_off, in_left_));
       z_.avail_in = 0;
     }
     crc_ = 0;
@@ -296,7 +355,7 @@ class MemberStream {
                                        (unsigned long long)(m_.usize - produced_), (unsigned long long)n);
     uint8_t* out = static_cast<uint8_t*>(dst);
     if (m_.method == 0) {
-      memcpy(out, m_.data + produced_, n);
+      mp_.read_at(out, m_.data_off + produced_, n);
     } else {
       uint64_t left = n;
       uint8_t* o = out;
@@ -331,7 +390,7 @@ class MemberStream {
   }
 
  private:
-  const Mapping& mp_;
+  const Archive& mp_;
   const Member& m_;
   const char* name_;
   bool check_crc_;
@@ -365,7 +424,7 @@ bool find_key(const std::string& h, const char* key, size_t* value_pos) {
 }
 
 // magic + version + header length: returns the dict length, *prefix = 10 (format 1.0) or 12 (2.0 / 3.0)
-uint32_t npy_prefix(const uint8_t* pre, size_t avail, size_t* prefix, const Mapping& mp, const char* name) {
+uint32_t npy_prefix(const uint8_t* pre, size_t avail, size_t* prefix, const Archive& mp, const char* name) {
   if (avail < 10 || memcmp(pre, "\x93NUMPY", 6) != 0)
     fail(MAU_TILES_E_FORMAT, "'%s': member %s is not an NPY array (object arrays / pickles are not supported)", mp.path.c_str(), name);
   uint32_t hlen;
@@ -383,9 +442,9 @@ uint32_t npy_prefix(const uint8_t* pre, size_t avail, size_t* prefix, const Mapp
   return hlen;
 }
 
-NpyHeader parse_npy_dict(const std::string& h, const Mapping& mp, const char* name);
+NpyHeader parse_npy_dict(const std::string& h, const Archive& mp, const char* name);
 
-NpyHeader read_npy_header(MemberStream& s, const Mapping& mp, const char* name) {
+NpyHeader read_npy_header(MemberStream& s, const Archive& mp, const char* name) {
   uint8_t pre[12];
   s.read(pre, 10);
   if (pre[6] == 2 || pre[6] == 3) s.read(pre + 10, 2);
@@ -397,7 +456,7 @@ NpyHeader read_npy_header(MemberStream& s, const Mapping& mp, const char* name) 
 }
 
 // header of an NPY image held in memory; *header_total = bytes in front of the payload
-NpyHeader read_npy_header_mem(const uint8_t* p, size_t avail, size_t* header_total, const Mapping& mp, const char* name) {
+NpyHeader read_npy_header_mem(const uint8_t* p, size_t avail, size_t* header_total, const Archive& mp, const char* name) {
   size_t prefix;
   uint32_t hlen = npy_prefix(p, avail, &prefix, mp, name);
   if (prefix + hlen > avail) fail(MAU_TILES_E_FORMAT, "'%s': member %s: truncated NPY header", mp.path.c_str(), name);
@@ -405,7 +464,7 @@ NpyHeader read_npy_header_mem(const uint8_t* p, size_t avail, size_t* header_tot
   return parse_npy_dict(std::string(reinterpret_cast<const char*>(p) + prefix, hlen), mp, name);
 }
 
-NpyHeader parse_npy_dict(const std::string& h, const Mapping& mp, const char* name) {
+NpyHeader parse_npy_dict(const std::string& h, const Archive& mp, const char* name) {
   NpyHeader r;
   size_t p;
   if (!find_key(h, "descr", &p) || p >= h.size() || (h[p] != '\'' && h[p] != '"')) fail(MAU_TILES_E_DTYPE, "'%s': member %s: structured or missing dtype", mp.path.c_str(), name);
@@ -535,9 +594,8 @@ void reverse_rows(float* p, int64_t rows, int64_t w) {  // np.flip(x, axis=2) of
 // are still in cache, as does the CRC: rows are reversed once they lie more than 32 KiB (the DEFLATE window) behind
 // the decode position, so the match history in front of the decoder stays in stream order.
 template <typename Place>
-NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool check_crc, bool force_zlib, int64_t flip_w, Place&& place) {
+NpyHeader read_member(const Archive& mp, const Member& M, const char* name, bool check_crc, bool force_zlib, int64_t flip_w, Place&& place) {
   constexpr size_t kHead = 65536, kChunk = 256 * 1024, kWindow = 32768;
-  const uint8_t* map_end = mp.base + mp.size;
   auto check_size = [&](const NpyHeader& h, size_t header_total) {
     if (uint64_t(h.count) * h.itemsize + header_total != M.usize)
       fail(MAU_TILES_E_FORMAT, "'%s': member %s holds %llu bytes, NPY header accounts for %llu", mp.path.c_str(), name, (unsigned long long)M.usize,
@@ -545,30 +603,54 @@ NpyHeader read_member(const Mapping& mp, const Member& M, const char* name, bool
   };
   if (M.method == 0) {
     if (M.csize != M.usize) fail(MAU_TILES_E_FORMAT, "'%s': stored member %s has differing sizes", mp.path.c_str(), name);
+    uint8_t hb[4096];
+    const uint8_t* hp = hb;
+    size_t hn = size_t(std::min<uint64_t>(M.usize, sizeof hb)), prefix;
+    mp.read_at(hb, M.data_off, hn);
+    const uint64_t hdr = uint64_t(npy_prefix(hb, hn, &prefix, mp, name)) + prefix;
+    if (hdr > hn) {  // an unusually long header dict
+      if (hdr > M.usize) fail(MAU_TILES_E_FORMAT, "'%s': member %s: truncated NPY header", mp.path.c_str(), name);
+      hp = mp.fetch(M.data_off, hdr);
+      hn = size_t(hdr);
+    }
     size_t header_total;
-    NpyHeader h = read_npy_header_mem(M.data, M.usize, &header_total, mp, name);
+    NpyHeader h = read_npy_header_mem(hp, hn, &header_total, mp, name);
     check_size(h, header_total);
     float* dst = place(h);
-    if (flip_w > 0 && h.dtype == F4 && h.count % flip_w == 0) {  // one pass over the payload
-      const uint8_t* src = M.data + header_total;  // row by row: copy, then reverse while the row is in L1
-      for (int64_t r = 0; r < h.count; r += flip_w) {
-        memcpy(dst + r, src + 4 * r, size_t(flip_w) * 4);
-        std::reverse(dst + r, dst + r + flip_w);
+    uint32_t crc = check_crc ? crc32_update(0, hp, header_total) : 0;
+    const uint64_t payload = uint64_t(h.count) * h.itemsize, at = M.data_off + header_total;
+    if (h.dtype == F4) {
+      // straight from the page cache into the batch slot, a chunk of whole rows at a time; CRC and flip while in cache
+      const uint64_t row_bytes = flip_w > 0 ? uint64_t(flip_w) * 4 : 0;
+      const uint64_t step = row_bytes ? std::max<uint64_t>(row_bytes, kChunk / row_bytes * row_bytes) : kChunk;
+      uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+      for (uint64_t pos = 0; pos < payload; pos += step) {
+        const uint64_t nb = std::min(step, payload - pos);
+        mp.read_at(d + pos, at + pos, nb);
+        if (check_crc) crc = crc32_update(crc, d + pos, nb);
+        if (row_bytes)
+          for (uint64_t r = 0; r + row_bytes <= nb; r += row_bytes) {
+            float* row = reinterpret_cast<float*>(d + pos + r);
+            std::reverse(row, row + flip_w);
+          }
       }
     } else {
-      convert(h.dtype, M.data + header_total, dst, h.count);
+      const uint8_t* src = mp.fetch(at, payload);
+      if (check_crc) crc = crc32_update(crc, src, payload);
+      convert(h.dtype, src, dst, h.count);
       if (flip_w > 0) reverse_rows(dst, h.count / flip_w, flip_w);
     }
-    if (check_crc && crc32_update(0, M.data, M.usize) != M.crc) fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp.path.c_str(), name);
+    if (check_crc && crc != M.crc) fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp.path.c_str(), name);
     return h;
   }
-  if (!force_zlib && size_t(map_end - (M.data + M.csize)) >= 16) {
+  if (!force_zlib) {
     thread_local std::vector<uint8_t> scratch(kHead + 16);
     thread_local mau_inflate::Inflater inf;
     try {
       const size_t c0 = size_t(std::min<uint64_t>(M.usize, kHead));
       uint8_t* S = scratch.data();
-      inf.init(M.data, M.csize, map_end);
+      const uint8_t* in = mp.fetch(M.data_off, M.csize, 16);  // + the 16 bytes of slack the decoder's 8-byte loads may touch
+      inf.init(in, M.csize, in + M.csize + 16);
       if (inf.run(S, S, S + c0) != S + c0) fail(MAU_TILES_E_FORMAT, "'%s': deflate stream of %s ends early", mp.path.c_str(), name);
       size_t header_total;
       NpyHeader h = read_npy_header_mem(S, c0, &header_total, mp, name);
@@ -695,7 +777,7 @@ void decode_sample(mau_tiles* t, Batch* b, int64_t slot, int parts) {
   const int64_t i = b->idx[size_t(slot)];
   const bool flip = !b->flip.empty() && b->flip[size_t(slot)];
   const bool crc = !(t->flags & MAU_TILES_FLAG_NO_CRC);
-  Mapping mp(t->paths[size_t(i)]);
+  Archive mp(t->paths[size_t(i)]);
   Member mem[M_COUNT];
   parse_zip(mp, mem);
   int64_t bytes = 0;
@@ -831,14 +913,14 @@ int mau_tiles_probe(mau_tiles* t, int64_t idx, int64_t dims[8]) {
   return guard([&]() -> int {
     if (!t || !dims) return set_err(MAU_TILES_E_ARG, "mau_tiles_probe: null argument");
     if (idx < 0 || idx >= int64_t(t->paths.size())) return set_err(MAU_TILES_E_ARG, "mau_tiles_probe: index out of range");
-    Mapping mp(t->paths[size_t(idx)]);
+    Archive mp(t->paths[size_t(idx)]);
     Member mem[M_COUNT];
     parse_zip(mp, mem);
     const int nd[M_COUNT] = {3, 3, 1, 1};
     const int at[M_COUNT] = {0, 3, 6, 7};
     for (int m = 0; m < M_COUNT; ++m) {
       if (!mem[m].found) fail(MAU_TILES_E_MEMBER, "'%s': '%.*s' is not a file in the archive", mp.path.c_str(), int(strlen(kMemberNames[m]) - 4), kMemberNames[m]);
-      MemberStream s(mp, mem[m], kMemberNames[m], false);
+      MemberStream s(mp, mem[m], kMemberNames[m], false, 16384);  // the header is in the first few hundred bytes
       NpyHeader h = read_npy_header(s, mp, kMemberNames[m]);
       if (h.ndim != nd[m]) fail(MAU_TILES_E_SHAPE, "'%s': %s has %d dimensions, expected %d", mp.path.c_str(), kMemberNames[m], h.ndim, nd[m]);
       for (int k = 0; k < nd[m]; ++k) dims[at[m] + k] = h.shape[k];
@@ -964,25 +1046,22 @@ void put32(std::vector<uint8_t>& v, uint32_t x) {
 }
 
 // all bytes of one member, CRC verified
-void member_bytes(const Mapping& mp, const Member& M, const std::string& name, std::vector<uint8_t>& out) {
+void member_bytes(const Archive& mp, const Member& M, const std::string& name, std::vector<uint8_t>& out) {
   out.resize(size_t(M.usize));
-  const uint8_t* map_end = mp.base + mp.size;
   if (M.method == 0) {
     if (M.csize != M.usize) fail(MAU_TILES_E_FORMAT, "'%s': stored member %s has differing sizes", mp.path.c_str(), name.c_str());
-    if (M.usize) memcpy(out.data(), M.data, size_t(M.usize));
-  } else if (size_t(map_end - (M.data + M.csize)) >= 16) {
+    if (M.usize) mp.read_at(out.data(), M.data_off, M.usize);
+  } else {
     try {
+      const uint8_t* in = mp.fetch(M.data_off, M.csize, 16);
       auto inf = std::make_unique<mau_inflate::Inflater>();
-      inf->init(M.data, size_t(M.csize), map_end);
+      inf->init(in, size_t(M.csize), in + M.csize + 16);
       uint8_t* end = out.data() + out.size();
       if (inf->run(out.data(), out.data(), end) != end || !inf->done())
         fail(MAU_TILES_E_FORMAT, "'%s': member %s does not decode to the size its directory entry gives", mp.path.c_str(), name.c_str());
     } catch (const mau_inflate::Error& e) {
       fail(MAU_TILES_E_FORMAT, "'%s': error while decompressing %s (%s)", mp.path.c_str(), name.c_str(), e.what);
     }
-  } else {
-    MemberStream s(mp, M, name.c_str(), false);
-    if (M.usize) s.read(out.data(), M.usize);
   }
   if (crc32_update(0, out.data(), out.size()) != M.crc) fail(MAU_TILES_E_FORMAT, "'%s': bad CRC-32 for member %s", mp.path.c_str(), name.c_str());
 }
@@ -1005,7 +1084,7 @@ void write_all(int fd, const void* p, size_t n, const std::string& path) {
 extern "C" int mau_tiles_repack(const char* src_path, const char* dst_path) {
   return guard([&]() -> int {
     if (!src_path || !dst_path) return set_err(MAU_TILES_E_ARG, "mau_tiles_repack: null path");
-    Mapping mp(src_path);
+    Archive mp(src_path);
     struct Item {
       std::string name;
       Member m;
