@@ -198,19 +198,36 @@ class FuturePredictionDataset(Dataset):
         if not os.path.isdir(self.data_dir):
             raise FileNotFoundError(f"Directory for split '{self.split}' not found at: {self.data_dir}")
         self.file_list = sorted(os.path.join(self.data_dir, f) for f in os.listdir(self.data_dir) if f.endswith(".npz"))
-        self._handle = C.c_void_p()
-        arr = (C.c_char_p * len(self.file_list))(*[os.fsencode(p) for p in self.file_list])
-        flags = (0 if verify_crc else FLAG_NO_CRC) | (FLAG_ZLIB if use_zlib else 0)
-        rc = lib().mau_tiles_open(arr, len(self.file_list), int(threads), flags, C.byref(self._handle))
-        if rc:
-            _raise(rc)
+        self._threads, self._flags = int(threads), (0 if verify_crc else FLAG_NO_CRC) | (FLAG_ZLIB if use_zlib else 0)
+        self._h, self._h_pid = None, None
         self._dims: Optional[List[int]] = None
         self._series_capacity = self.SERIES_CAPACITY
+        lib()                       # fail at construction if the reader is not built
 
     # -- plumbing ------------------------------------------------------------------------------------------
+    @property
+    def _handle(self):
+        """The native reader (file list + worker pool) of *this process*.  Opened on first use and re-opened after a
+        fork: threads do not survive ``fork()``, so a dataset handed to ``torch.utils.data.DataLoader(num_workers>0)``
+        gets a fresh pool in every worker instead of waiting on one that no longer exists."""
+        if self._h is None or self._h_pid != os.getpid():
+            h = C.c_void_p()
+            arr = (C.c_char_p * len(self.file_list))(*[os.fsencode(p) for p in self.file_list])
+            rc = lib().mau_tiles_open(arr, len(self.file_list), self._threads, self._flags, C.byref(h))
+            if rc:
+                _raise(rc)
+            self._h, self._h_pid = h, os.getpid()     # a handle inherited from the parent is abandoned, not closed:
+        return self._h                                # closing it would join threads that do not exist here
+
+    def __getstate__(self):          # spawn / forkserver workers, copy.deepcopy: the handle stays with its process
+        d = dict(self.__dict__)
+        d["_h"], d["_h_pid"] = None, None
+        return d
+
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
-        if h:
+        h, pid = getattr(self, "_h", None), getattr(self, "_h_pid", None)
+        self._h = self._h_pid = None
+        if h is not None and pid == os.getpid():
             try:
                 lib().mau_tiles_close(h)
             except Exception:
@@ -431,9 +448,13 @@ class TileLoader:
 
     def __iter__(self):
         ds = self.dataset
-        if self._rings is None:       # prefetch + 2 staging sets: up to two being copied H2D, `prefetch` being decoded
-            self._rings = [ds.alloc_staging(self.batch_size, pin=self._pin) for _ in range(self.prefetch + 2)]
-        free = deque(self._rings)
+        # prefetch + 2 staging sets: up to two being copied H2D, `prefetch` being decoded.  They are kept between epochs
+        # (pinning 100 MB buffers is slow) but owned by one iterator at a time: a second, concurrent iterator over the
+        # same loader finds none cached and allocates its own
+        rings, self._rings = self._rings, None
+        if rings is None or any(st["series"].shape[1] < ds._series_capacity for st in rings):
+            rings = [ds.alloc_staging(self.batch_size, pin=self._pin) for _ in range(self.prefetch + 2)]
+        free = deque(rings)
         busy = {}                     # id(staging set) -> event of its last H2D copy
         inflight = deque()            # decode tickets, oldest first
         staged = deque()              # (device batch, copy event) ahead of the consumer, at most one
@@ -455,14 +476,13 @@ class TileLoader:
                 # (src/dataset.py:106, src/model.py:29-33): ranks pad to the longest series of the *global* batch
                 width = max(ds.probe(i)[7] for i in gb) if self.world_size > 1 else 0
                 if width > ds._series_capacity:
-                    ds._series_capacity = 2 * width
-                    self._rings = None          # staging sets of the next epoch are allocated at the new capacity
+                    ds._series_capacity = 2 * width       # staging sets of the next epoch are allocated at this capacity
                 st = free.popleft()
-                if st["series"].shape[1] < width:
-                    st["series"] = torch.empty((st["capacity"], ds._series_capacity), dtype=torch.float32, pin_memory=self._pin)
                 ev = busy.pop(id(st), None)
                 if ev is not None:
                     ev.synchronize()          # the copy that last read this staging set has finished
+                if st["series"].shape[1] < width:
+                    st["series"] = torch.empty((st["capacity"], ds._series_capacity), dtype=torch.float32, pin_memory=self._pin)
                 inflight.append(ds.submit(local, flips, st, width))
 
         def stage(block: bool) -> bool:
@@ -501,6 +521,12 @@ class TileLoader:
                     inflight.popleft().wait()
                 except Exception:
                     pass
+            try:
+                for ev in busy.values():      # copies still reading the staging sets we hand back
+                    ev.synchronize()
+                self._rings = rings
+            except Exception:                 # e.g. a torn-down CUDA context at interpreter exit: just drop them
+                pass
 
 
 def create_dataloader(split: str, batch_size: int, shuffle: bool, dataset_type: str, transform=None, num_workers: int = 0,

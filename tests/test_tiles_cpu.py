@@ -444,3 +444,34 @@ def test_repack_to_stored_members_is_lossless_and_numpy_readable(synth, tmp_path
         os.remove(extra)
     with pytest.raises(FileNotFoundError):
         D.lib().mau_tiles_repack(b"/nonexistent/a.npz", os.fsencode(str(tmp_path / "x.npz"))) and D._raise(D.E_IO)
+
+
+def test_dataset_survives_fork_and_pickle_in_torch_dataloader_workers(expected):
+    # threads do not survive fork(): every DataLoader worker process must open its own reader
+    import pickle
+    from torch.utils.data import DataLoader
+    ds = D.FuturePredictionDataset("train", processed_dir=GOLD, threads=2)
+    ds[0]                                             # the parent's pool exists before the workers fork
+    collate = lambda b: D.collate_fn(b, device="cpu")  # noqa: E731
+    for ctx in ("fork", "spawn"):
+        kw = dict(collate_fn=collate) if ctx == "fork" else dict(collate_fn=_collate_cpu)
+        batches = list(DataLoader(ds, batch_size=4, shuffle=False, num_workers=2, multiprocessing_context=ctx, **kw))
+        assert_batches_equal("seq", expected, batches)
+    clone = pickle.loads(pickle.dumps(ds))
+    assert torch.equal(clone[3][0], ds[3][0])
+
+
+def _collate_cpu(batch):
+    return D.collate_fn(batch, device="cpu")
+
+
+def test_two_concurrent_iterators_over_one_loader_do_not_share_staging(synth):
+    loader = D.create_dataloader("train", 3, False, "future", device="cpu", processed_dir=synth)
+    ref = list(loader)
+    a, b = iter(loader), iter(loader)
+    got_a, got_b = [], []
+    for _ in range(len(ref)):
+        got_a.append(next(a))
+        got_b.append(next(b))
+    for g in (got_a, got_b):
+        assert all(torch.equal(x, y) for bg, br in zip(g, ref) for x, y in zip(bg, br))
