@@ -168,6 +168,14 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
                      const float* target_dev, int B, int C, int H, int W, float temp_mean,
                      float temp_std, int64_t* dw_map_dev, double* sums_dev, void* stream);
 
+/* Sharpness metric of the same evaluation loop (test/evaluate.py:241-242): np.var(scipy.ndimage.laplace(x)) of the
+ * un-normalised prediction and target of every (sample, channel).  sums_dev [B, C, 4] float64 =
+ * {sum L(pred), sum L(pred)^2, sum L(target), sum L(target)^2} with L = the 5-point Laplacian in scipy's default
+ * 'reflect' boundary mode, evaluated per axis in double and rounded to fp32 like scipy does;
+ * variance = sum2 / (H*W) - (sum / (H*W))^2 is formed by the caller. */
+int mau_laplacian_sums(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float temp_mean,
+                       float temp_std, double* sums_dev, void* stream);
+
 /* --- single operators on raw NHWC device buffers (used by the kernel-level parity tests) ----
  * dtype: 0 = bf16, 1 = fp32.  x [B,H,W,Cin_stride], w OIHW fp32 [Cout,Cin,3,3],
  * y [B,H,W,Cout_stride]; y = relu?(conv(x,w)*scale + shift).  impl: 0 = tcgen05 persistent halo

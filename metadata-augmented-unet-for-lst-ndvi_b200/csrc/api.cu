@@ -155,6 +155,12 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
                          reinterpret_cast<long long*>(dw_map_dev), sums_dev, static_cast<cudaStream_t>(stream));
 }
 
+int mau_laplacian_sums(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float temp_mean,
+                       float temp_std, double* sums_dev, void* stream) {
+  if (!pred_dev || !target_dev || !sums_dev) return fail("laplacian_sums: null argument");
+  return op_laplacian_sums(pred_dev, target_dev, B, C, H, W, temp_mean, temp_std, sums_dev, static_cast<cudaStream_t>(stream));
+}
+
 int mau_adamw_step(int n_tensors, void* const* params_dev, void* const* grads_dev, void* const* exp_avg_dev,
                    void* const* exp_avg_sq_dev, const int64_t* numels, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, void* stream) {

@@ -113,6 +113,9 @@ int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, 
             float* losses, float* grad, cudaStream_t st);
 int op_eval_metrics(const float* maps, int maps_c, const float* pred, const float* tgt, int B, int C, int H, int W,
                     float temp_mean, float temp_std, long long* dw_map, double* sums, cudaStream_t st);
+// per (sample, channel): {sum, sum of squares} of scipy.ndimage.laplace for pred and tgt -> out [B*C][4] (test/evaluate.py:241-242)
+int op_laplacian_sums(const float* pred, const float* tgt, int B, int C, int H, int W, float temp_mean, float temp_std,
+                      double* out, cudaStream_t st);
 
 // ---- backward of a conv w.r.t. a spatially constant input segment (embgrad.cu; U-Net++ embedding planes) ------
 // dz: the conv's output gradient [B,H,W,Cout]; emb [B, emb_stride] holds the segment's E values per image at emb[b*stride + c].

@@ -48,7 +48,7 @@ EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
     "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
-    "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics",
+    "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics", "mau_laplacian_sums",
     "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
@@ -93,6 +93,8 @@ def lib():
         L.mau_eval_metrics.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
+        L.mau_laplacian_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                         C.c_void_p, C.c_void_p]
         L.mau_op_conv3x3.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p]
@@ -410,3 +412,20 @@ def eval_metrics(maps: torch.Tensor, pred: torch.Tensor, target: torch.Tensor,
                                      B, Cc, H, W, temp_mean, temp_std, dw.data_ptr(), sums.data_ptr(),
                                      _stream_ptr()), "eval_metrics")
     return dw, sums
+
+
+def laplacian_variance(pred: torch.Tensor, target: torch.Tensor, temp_mean: float = 0.0, temp_std: float = 0.0) -> torch.Tensor:
+    """``np.var(scipy.ndimage.laplace(x))`` of the un-normalised prediction and target of every (sample, channel)
+    (test/evaluate.py:241-242: ``laplacian_var_pred`` / ``laplacian_var_gt``).  Returns float64 [B, C, 2]."""
+    pred = _dev_f32(pred, "pred")
+    target = _dev_f32(target, "target", pred)
+    if pred.dim() != 4 or target.shape != pred.shape:
+        raise RuntimeError(f"pred and target must both be [B,C,H,W], got {tuple(pred.shape)} and {tuple(target.shape)}")
+    B, Cc, H, W = pred.shape
+    sums = torch.empty(B, Cc, 4, device=pred.device, dtype=torch.float64)
+    with torch.cuda.device(pred.device):
+        check(lib().mau_laplacian_sums(pred.data_ptr(), target.data_ptr(), B, Cc, H, W, temp_mean, temp_std,
+                                       sums.data_ptr(), _stream_ptr()), "laplacian_sums")
+    n = float(H * W)
+    mean = sums[..., 0::2] / n
+    return sums[..., 1::2] / n - mean * mean

@@ -253,6 +253,33 @@ def eval_metrics(input_stack, pred, tgt, temp_mean=None, temp_std=None):
     return np.stack(maps), rows
 
 
+def laplacian_variance(pred, tgt, temp_mean=None, temp_std=None):
+    """``np.var(laplace(x))`` of every un-normalised (sample, channel) plane of pred and tgt
+    (test/evaluate.py:241-242; ``scipy.ndimage.laplace``, default mode 'reflect' = edge value
+    repeated).  Restated without scipy: per axis the second difference [1,-2,1] in double rounded
+    to fp32, the two axes added in fp32.  Returns float64 [B, C, 2] = (var_pred, var_gt).
+    Pinned against scipy itself in tests/test_oracle.py."""
+    import numpy as np
+    pred = np.array(pred, dtype=np.float32, copy=True)
+    tgt = np.array(tgt, dtype=np.float32, copy=True)
+    if temp_mean is not None and pred.shape[1] > 1:      # channel 1 is the temperature (conf/config.yaml:29)
+        pred[:, 1] = pred[:, 1] * np.float32(temp_std) + np.float32(temp_mean)
+        tgt[:, 1] = tgt[:, 1] * np.float32(temp_std) + np.float32(temp_mean)
+
+    def lap(a):
+        p = np.pad(a.astype(np.float64), 1, mode="edge")
+        d2y = (p[:-2, 1:-1] + p[2:, 1:-1] - 2.0 * p[1:-1, 1:-1]).astype(np.float32)
+        d2x = (p[1:-1, :-2] + p[1:-1, 2:] - 2.0 * p[1:-1, 1:-1]).astype(np.float32)
+        return d2y + d2x
+
+    out = np.zeros(pred.shape[:2] + (2,), np.float64)
+    for i in range(pred.shape[0]):
+        for ch in range(pred.shape[1]):
+            out[i, ch, 0] = np.var(lap(pred[i, ch]).astype(np.float64))
+            out[i, ch, 1] = np.var(lap(tgt[i, ch]).astype(np.float64))
+    return out
+
+
 # --------------------------------------------------------------------------- #
 # training step (src/train.py:244-256) -- gradients through torch autograd
 # --------------------------------------------------------------------------- #

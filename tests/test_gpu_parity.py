@@ -601,3 +601,19 @@ def test_inputs_left_on_the_host_raise_instead_of_faulting():
     with pytest.raises(RuntimeError, match=r"\[B,C,H,W\]"):
         engine.loss_terms(y, tgt.cuda()[:, :1])
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("shape,stats", [((3, 2, 61, 47), (14.5, 7.25)), ((2, 2, 250, 250), (0.0, 0.0)), ((1, 1, 16, 1), (3.0, 2.0)),
+                                         ((2, 3, 1, 33), (14.5, 7.25))])
+def test_laplacian_variance_against_scipy_restatement(shape, stats):
+    """test/evaluate.py:241-242: np.var(scipy.ndimage.laplace(x)) of the un-normalised prediction / target planes.
+    The oracle reproduces scipy's fp32 Laplacian element for element (tests/test_oracle.py); tolerance 2e-5 relative
+    (np.var sums in fp32, the kernel in double)."""
+    g = torch.Generator().manual_seed(shape[2] * 131 + shape[3])
+    pred = torch.randn(shape, generator=g)
+    tgt = torch.randn(shape, generator=g) * 3 + 1
+    want = O.laplacian_variance(pred.numpy(), tgt.numpy(), *(stats if stats[1] else (None, None)))
+    got = engine.laplacian_variance(pred.cuda(), tgt.cuda(), *stats)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.float64 and tuple(got.shape) == (shape[0], shape[1], 2)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-5, atol=1e-9)

@@ -104,3 +104,30 @@ def test_oracle_dw_map_known_answers():
     overall = [r for r in rows if r[2] == -1]
     assert all(abs(r[4] - 1.0) < 1e-7 and abs(r[5] - 1.0) < 1e-7 for r in overall)
     assert sorted({r[2] for r in rows}) == [-1, 0, 3, 5, 8]
+
+
+def test_oracle_laplacian_variance_equals_scipy():
+    """test/evaluate.py:241-242 calls scipy.ndimage.laplace directly; the restatement must reproduce it."""
+    from scipy.ndimage import laplace
+    rng = np.random.default_rng(0)
+    for shape in ((2, 2, 17, 23), (1, 2, 1, 9), (1, 1, 5, 1), (1, 2, 50, 50)):
+        pred = rng.standard_normal(shape).astype(np.float32)
+        tgt = (rng.standard_normal(shape) * 3 + 1).astype(np.float32)
+        for stats in ((None, None), (14.5, 7.25)):
+            got = O.laplacian_variance(pred, tgt, *stats)
+            p, g = pred.copy(), tgt.copy()
+            if stats[0] is not None and shape[1] > 1:
+                p[:, 1] = p[:, 1] * np.float32(stats[1]) + np.float32(stats[0])
+                g[:, 1] = g[:, 1] * np.float32(stats[1]) + np.float32(stats[0])
+            for i in range(shape[0]):
+                for ch in range(shape[1]):
+                    lp, lg = laplace(p[i, ch]), laplace(g[i, ch])
+                    assert lp.dtype == np.float32
+                    # element-wise identical Laplacian (fp32), variance within fp32 summation error of np.var
+                    pad = np.pad(p[i, ch].astype(np.float64), 1, mode="edge")
+                    mine = ((pad[:-2, 1:-1] + pad[2:, 1:-1] - 2 * pad[1:-1, 1:-1]).astype(np.float32)
+                            + (pad[1:-1, :-2] + pad[1:-1, 2:] - 2 * pad[1:-1, 1:-1]).astype(np.float32))
+                    assert np.array_equal(mine, lp)
+                    for k, ref in ((0, lp), (1, lg)):
+                        want = float(np.var(ref))
+                        assert abs(got[i, ch, k] - want) <= 2e-5 * max(abs(want), 1e-6), (shape, stats, i, ch, k)
