@@ -168,6 +168,16 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
                      const float* target_dev, int B, int C, int H, int W, float temp_mean,
                      float temp_std, int64_t* dw_map_dev, double* sums_dev, void* stream);
 
+/* SSIM term of the training loss, src/utils/losses.py:72-95: channel 0 scaled (x+1)/2, channel 1 clamped to [0,1],
+ * piq.ssim(..., data_range=1, reduction='none') -- 11x11 Gaussian window, sigma 1.5, valid filtering, k1 .01, k2 .03 --
+ * loss_dev[0] = 1 - mean SSIM over images, channels 0..1 and window positions; grad_dev (may be NULL) [B,C,H,W] =
+ * d loss / d pred (zero for channels >= 2).  work_dev: mau_ssim_work_floats(B,H,W) floats of scratch, acc_dev: one double.
+ * piq is a third-party dependency the reference does not pin: parity for this term is UNPINNED (see oracle/ssim_oracle.py).
+ * Tiles with min(H,W) >= 384 (which piq average-pools first) are refused. */
+int64_t mau_ssim_work_floats(int B, int H, int W);
+int mau_ssim_loss(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float* loss_dev,
+                  float* grad_dev, float* work_dev, double* acc_dev, void* stream);
+
 /* Sharpness metric of the same evaluation loop (test/evaluate.py:241-242): np.var(scipy.ndimage.laplace(x)) of the
  * un-normalised prediction and target of every (sample, channel).  sums_dev [B, C, 4] float64 =
  * {sum L(pred), sum L(pred)^2, sum L(target), sum L(target)^2} with L = the 5-point Laplacian in scipy's default

@@ -7,5 +7,6 @@ from .model import UrbanPredictor, UrbanPredictor_unet, UrbanPredictor_unetpp  #
 from . import engine  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from . import data  # noqa: F401  (mirror of reference src/dataset.py on the native tile reader)
+from . import losses  # noqa: F401  (mirror of reference src/utils/losses.py on the loss kernels)
 
-__all__ = ["UrbanPredictor", "UrbanPredictor_unet", "UrbanPredictor_unetpp", "engine", "FusedAdamW", "data"]
+__all__ = ["UrbanPredictor", "UrbanPredictor_unet", "UrbanPredictor_unetpp", "engine", "FusedAdamW", "data", "losses"]

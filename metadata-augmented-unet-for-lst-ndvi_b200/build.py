@@ -13,7 +13,7 @@ TILES_SRC = os.path.join(SRC, "tile_reader.cpp")
 TILES_LIB = os.path.join(HERE, "libmau_tiles.so")
 CXX = os.environ.get("CXX", "g++")
 SOURCES = ["common.cu", "tma.cu", "conv_tc.cu", "wgrad_tc.cu", "conv_ffma.cu", "elementwise.cu", "norm.cu",
-           "encoders.cu", "loss.cu", "metrics.cu", "optim.cu", "embgrad.cu", "plan.cu", "api.cu"]
+           "encoders.cu", "loss.cu", "ssim.cu", "metrics.cu", "optim.cu", "embgrad.cu", "plan.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
          "-Xcompiler", "-fPIC", "-DNDEBUG"]

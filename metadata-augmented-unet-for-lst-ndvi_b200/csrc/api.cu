@@ -161,6 +161,14 @@ int mau_laplacian_sums(const float* pred_dev, const float* target_dev, int B, in
   return op_laplacian_sums(pred_dev, target_dev, B, C, H, W, temp_mean, temp_std, sums_dev, static_cast<cudaStream_t>(stream));
 }
 
+int64_t mau_ssim_work_floats(int B, int H, int W) { return ssim_work_floats(B, H, W); }
+
+int mau_ssim_loss(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float* loss_dev, float* grad_dev,
+                  float* work_dev, double* acc_dev, void* stream) {
+  if (!pred_dev || !target_dev || !loss_dev || !work_dev || !acc_dev) return fail("ssim_loss: null argument");
+  return op_ssim_loss(pred_dev, target_dev, B, C, H, W, loss_dev, grad_dev, work_dev, acc_dev, static_cast<cudaStream_t>(stream));
+}
+
 int mau_adamw_step(int n_tensors, void* const* params_dev, void* const* grads_dev, void* const* exp_avg_dev,
                    void* const* exp_avg_sq_dev, const int64_t* numels, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, void* stream) {

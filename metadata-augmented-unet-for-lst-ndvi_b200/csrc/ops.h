@@ -116,6 +116,11 @@ int op_eval_metrics(const float* maps, int maps_c, const float* pred, const floa
 // per (sample, channel): {sum, sum of squares} of scipy.ndimage.laplace for pred and tgt -> out [B*C][4] (test/evaluate.py:241-242)
 int op_laplacian_sums(const float* pred, const float* tgt, int B, int C, int H, int W, float temp_mean, float temp_std,
                       double* out, cudaStream_t st);
+// SSIM term of the training loss (src/utils/losses.py:72-95): loss[0] = 1 - mean SSIM, grad = d loss / d pred (or null);
+// work holds ssim_work_floats(B, H, W) floats, acc one double
+long long ssim_work_floats(int B, int H, int W);
+int op_ssim_loss(const float* pred, const float* tgt, int B, int C, int H, int W, float* loss, float* grad, float* work,
+                 double* acc, cudaStream_t st);
 
 // ---- backward of a conv w.r.t. a spatially constant input segment (embgrad.cu; U-Net++ embedding planes) ------
 // dz: the conv's output gradient [B,H,W,Cout]; emb [B, emb_stride] holds the segment's E values per image at emb[b*stride + c].

@@ -48,7 +48,7 @@ EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
     "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
-    "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics", "mau_laplacian_sums",
+    "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss",
     "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
@@ -95,6 +95,10 @@ def lib():
                                        C.c_void_p]
         L.mau_laplacian_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                          C.c_void_p, C.c_void_p]
+        L.mau_ssim_work_floats.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.mau_ssim_work_floats.restype = C.c_int64
+        L.mau_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
         L.mau_op_conv3x3.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p]
@@ -429,3 +433,41 @@ def laplacian_variance(pred: torch.Tensor, target: torch.Tensor, temp_mean: floa
     n = float(H * W)
     mean = sums[..., 0::2] / n
     return sums[..., 1::2] / n - mean * mean
+
+
+def ssim_loss_terms(pred: torch.Tensor, target: torch.Tensor, need_grad: bool = True):
+    """``1 - piq.ssim(scaled pred, scaled target, data_range=1, reduction='none').mean()`` of
+    src/utils/losses.py:72-90 and its gradient w.r.t. ``pred``.  Returns (loss[1] tensor, grad or None)."""
+    pred = _dev_f32(pred, "pred")
+    target = _dev_f32(target, "target", pred)
+    if pred.dim() != 4 or target.shape != pred.shape:
+        raise RuntimeError(f"pred and target must both be [B,C,H,W], got {tuple(pred.shape)} and {tuple(target.shape)}")
+    B, Cc, H, W = pred.shape
+    n_work = int(lib().mau_ssim_work_floats(B, H, W))
+    work = torch.empty(max(n_work, 1), device=pred.device, dtype=torch.float32)
+    acc = torch.empty(1, device=pred.device, dtype=torch.float64)
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if need_grad else None
+    with torch.cuda.device(pred.device):
+        check(lib().mau_ssim_loss(pred.data_ptr(), target.data_ptr(), B, Cc, H, W, loss.data_ptr(),
+                                  grad.data_ptr() if need_grad else None, work.data_ptr(), acc.data_ptr(), _stream_ptr()),
+              "ssim_loss")
+    return loss, grad
+
+
+class _SsimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        loss, grad = ssim_loss_terms(pred, target, True)
+        ctx.save_for_backward(grad)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def ssim_loss(outputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """Differentiable scalar ``ssim_loss`` of src/utils/losses.py:88-89 (parity with piq unpinned)."""
+    return _SsimFn.apply(outputs, targets)

@@ -214,3 +214,21 @@ def test_state_tensor_walk_matches_state_dict_order(name):
     a = m.model._state_tensors()
     b = list(m.model.state_dict(keep_vars=True).values())
     assert len(a) == len(b) and all(x is y for x, y in zip(a, b))
+
+
+def test_losses_mirror_has_the_reference_names_and_refuses_cpu_tensors():
+    """mau_b200.losses mirrors src/utils/losses.py (same functions and arguments); like the model it has no CPU path."""
+    import inspect
+    from mau_b200 import losses
+    want = {"gradient_loss": ["pred", "target"], "compute_loss_mse": ["outputs", "targets"],
+            "compute_loss_mse_gradient": ["outputs", "targets", "lambda_grad"],
+            "compute_loss_l1_grad_ssim": ["outputs", "targets", "lambda_grad", "lambda_ssim"],
+            "compute_all_loss": ["outputs", "targets", "lambda_grad", "lambda_ssim"]}
+    for name, args in want.items():
+        assert list(inspect.signature(getattr(losses, name)).parameters) == args
+    assert inspect.signature(losses.compute_loss_l1_grad_ssim).parameters["lambda_ssim"].default == 0.5
+    x = torch.zeros(1, 2, 16, 16)
+    for fn in (losses.compute_loss_mse, losses.compute_loss_mse_gradient, losses.compute_loss_l1_grad_ssim, losses.compute_all_loss,
+               losses.gradient_loss):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn(x, x)

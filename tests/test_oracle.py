@@ -131,3 +131,34 @@ def test_oracle_laplacian_variance_equals_scipy():
                     for k, ref in ((0, lp), (1, lg)):
                         want = float(np.var(ref))
                         assert abs(got[i, ch, k] - want) <= 2e-5 * max(abs(want), 1e-6), (shape, stats, i, ch, k)
+
+
+def test_ssim_core_arithmetic_equals_torch_autograd(tmp_path):
+    """csrc/ssim_core.h (the header the CUDA kernels include) driven serially on the host (oracle/ssim_host.cpp)
+    against the torch restatement of piq's published SSIM: loss value and analytic gradient."""
+    import ctypes as C
+    import subprocess
+    from oracle import ssim_oracle as S
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "libssim_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", os.path.join(root, "oracle", "ssim_host.cpp"), "-o", lib])
+    L = C.CDLL(lib)
+    L.ssim_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    g = torch.Generator().manual_seed(0)
+    for shape in ((2, 2, 23, 31), (1, 2, 11, 11), (3, 2, 40, 17), (2, 3, 30, 30), (1, 2, 64, 250)):
+        out = (torch.randn(shape, generator=g) * 0.7).requires_grad_(True)
+        tgt = torch.randn(shape, generator=g) * 0.7
+        tgt[:, 0] = tgt[:, 0].clamp(-1, 1)                   # NDVI targets live in [-1, 1]
+        loss = S.ssim_loss(out, tgt)
+        loss.backward()
+        o, t = out.detach().contiguous().numpy(), tgt.contiguous().numpy()
+        grad, lv = np.zeros_like(o), C.c_double()
+        assert L.ssim_host(o.ctypes.data, t.ctypes.data, *shape, C.byref(lv), grad.ctypes.data) == 0
+        gref = out.grad.numpy()
+        assert abs(lv.value - float(loss.detach())) < 1e-6
+        assert np.abs(grad - gref).max() < 2e-5 * np.abs(gref).max()
+        if shape[1] > 2:
+            assert not grad[:, 2:].any() and not gref[:, 2:].any()      # only channels 0 and 1 enter the SSIM term
+    x = torch.rand(1, 2, 20, 20, generator=g)
+    assert abs(float(S.ssim_loss(x, x))) < 1e-6                          # identical maps: SSIM = 1
+    assert L.ssim_host(o.ctypes.data, t.ctypes.data, 1, 1, 20, 20, C.byref(lv), None) == 1     # needs both channels
