@@ -475,3 +475,36 @@ def test_two_concurrent_iterators_over_one_loader_do_not_share_staging(synth):
         got_b.append(next(b))
     for g in (got_a, got_b):
         assert all(torch.equal(x, y) for bg, br in zip(g, ref) for x, y in zip(bg, br))
+
+
+def test_reader_survives_corrupted_archives(tmp_path):
+    """Bytes of a good archive flipped anywhere (local headers, deflate streams, NPY headers, central directory, end
+    record): the reader must raise a Python exception or return data, never fault."""
+    d = tmp_path / "train"
+    d.mkdir()
+    rng = np.random.default_rng(12)
+    name = "Z_1_0.5_0.25_2019_7_to_2023_7.npz"
+    good = {}
+    for kind, save in (("deflate", np.savez_compressed), ("stored", np.savez)):
+        save(d / name, input=rng.standard_normal((3, 40, 50)).astype(np.float32), target=rng.standard_normal((2, 40, 50)).astype(np.float32),
+             metadata=rng.standard_normal(4).astype(np.float32), temperature_serie=rng.standard_normal(30).astype(np.float32))
+        good[kind] = open(d / name, "rb").read()
+    ds = D.FuturePredictionDataset("train", processed_dir=str(tmp_path), threads=2)
+    raised = 0
+    for kind, blob in good.items():
+        n = len(blob)
+        hot = list(range(0, 200)) + list(range(n - 600, n))            # headers and the directories at both ends
+        for trial in range(400):
+            b = bytearray(blob)
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.choice(hot)) if trial % 2 else int(rng.integers(0, n))
+                b[pos] = int(rng.integers(0, 256))
+            if trial % 50 == 0:
+                b = b[:int(rng.integers(1, n))]                         # truncation
+            open(d / name, "wb").write(bytes(b))
+            try:
+                ds.probe(0)
+                ds[0]
+            except (ValueError, KeyError, RuntimeError, OSError, IndexError):
+                raised += 1
+    assert raised > 100
