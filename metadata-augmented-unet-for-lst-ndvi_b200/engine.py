@@ -471,3 +471,37 @@ class _SsimFn(torch.autograd.Function):
 def ssim_loss(outputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
     """Differentiable scalar ``ssim_loss`` of src/utils/losses.py:88-89 (parity with piq unpinned)."""
     return _SsimFn.apply(outputs, targets)
+
+
+# Dynamic World class names, reference src/utils/visualization.py:5-8
+DW_CLASSES = {0: "water", 1: "trees", 2: "grass", 3: "flooded_vegetation", 4: "crops", 5: "shrub_and_scrub", 6: "built",
+              7: "bare", 8: "snow_and_ice"}
+
+
+def metric_rows(sums, lap_var=None, channel_names=("after_ndvi", "after_temp"), first_sample_idx: int = 0):
+    """The per-sample rows test/evaluate.py:239-275 appends, from the device reductions: ``sums`` [B,C,10,3] of
+    :func:`eval_metrics` and (optionally) ``lap_var`` [B,C,2] of :func:`laplacian_variance` (tensors on any device or
+    arrays).  One ``overall`` row per (sample, channel) followed by one row per Dynamic World class present in the
+    sample, in the reference's order; keys ``sample_idx, channel, dw_class, mae, rmse, laplacian_var_pred,
+    laplacian_var_gt`` (the caller adds its city / date columns).  One device-to-host copy of a few kilobytes replaces
+    the reference's copy of the full prediction, target and input tensors (test/evaluate.py:188)."""
+    import numpy as np
+    s = sums.detach().cpu().numpy() if isinstance(sums, torch.Tensor) else np.asarray(sums)
+    lv = None if lap_var is None else (lap_var.detach().cpu().numpy() if isinstance(lap_var, torch.Tensor) else np.asarray(lap_var))
+    B, Cc = s.shape[:2]
+    if len(channel_names) < Cc:
+        raise ValueError(f"{Cc} channels but only {len(channel_names)} channel names")
+    rows = []
+    for i in range(B):
+        for ch in range(Cc):
+            for slot in range(10):
+                n = s[i, ch, slot, 0]
+                if n <= 0:
+                    continue            # the reference skips classes absent from the sample (np.any(mask))
+                overall = slot == 0
+                rows.append({"sample_idx": first_sample_idx + i, "channel": channel_names[ch],
+                             "dw_class": "overall" if overall else DW_CLASSES[slot - 1],
+                             "mae": float(s[i, ch, slot, 1] / n), "rmse": float(np.sqrt(s[i, ch, slot, 2] / n)),
+                             "laplacian_var_pred": float(lv[i, ch, 0]) if overall and lv is not None else None,
+                             "laplacian_var_gt": float(lv[i, ch, 1]) if overall and lv is not None else None})
+    return rows

@@ -232,3 +232,36 @@ def test_losses_mirror_has_the_reference_names_and_refuses_cpu_tensors():
                losses.gradient_loss):
         with pytest.raises(RuntimeError, match="CUDA"):
             fn(x, x)
+
+
+def test_metric_rows_reproduce_the_reference_row_list():
+    """engine.metric_rows turns the device reductions into the rows of test/evaluate.py:239-275; here the reductions
+    are formed with NumPy from the oracle's own class map so that the host logic is checked without a GPU."""
+    import numpy as np
+    from oracle import unet_oracle as O
+    maps, _, _, tgt = O.synthetic_batch(2, 24, 20, T=4, seed=5)
+    maps[1, 0:9] = 0
+    maps[1, 6] = 1.0                                                     # sample 1: a single class present
+    pred = torch.randn(2, 2, 24, 20, generator=torch.Generator().manual_seed(1))
+    dw, ref_rows = O.eval_metrics(maps.numpy(), pred.numpy(), tgt.numpy(), temp_mean=14.5, temp_std=7.25)
+    lap = O.laplacian_variance(pred.numpy(), tgt.numpy(), 14.5, 7.25)
+    p, g = pred.numpy().copy(), tgt.numpy().copy()
+    p[:, 1] = p[:, 1] * np.float32(7.25) + np.float32(14.5)
+    g[:, 1] = g[:, 1] * np.float32(7.25) + np.float32(14.5)
+    sums = np.zeros((2, 2, 10, 3))
+    for i in range(2):
+        for ch in range(2):
+            d = (p[i, ch] - g[i, ch]).astype(np.float64)
+            for slot in range(10):
+                m = np.ones_like(dw[i], bool) if slot == 0 else dw[i] == slot - 1
+                sums[i, ch, slot] = [m.sum(), np.abs(d[m]).sum(), (d[m] ** 2).sum()]
+    rows = engine.metric_rows(torch.from_numpy(sums), torch.from_numpy(lap), first_sample_idx=40)
+    assert len(rows) == len(ref_rows)
+    for r, (i, ch, k, n, mae, rmse) in zip(rows, ref_rows):
+        assert r["sample_idx"] == 40 + i and r["channel"] == ("after_ndvi", "after_temp")[ch]
+        assert r["dw_class"] == ("overall" if k < 0 else engine.DW_CLASSES[k])
+        assert abs(r["mae"] - mae) < 1e-5 * max(1, abs(mae)) and abs(r["rmse"] - rmse) < 1e-5 * max(1, abs(rmse))
+        assert (r["laplacian_var_pred"] is not None) == (k < 0)
+        if k < 0:
+            assert r["laplacian_var_pred"] == lap[i, ch, 0] and r["laplacian_var_gt"] == lap[i, ch, 1]
+    assert [r["dw_class"] for r in rows if r["sample_idx"] == 41 and r["channel"] == "after_ndvi"] == ["overall", "built"]
