@@ -62,6 +62,11 @@ int     mau_tiles_threads(const mau_tiles* t);
  * (what data['input'].shape etc. would report, src/dataset.py:56-59) */
 int mau_tiles_probe(mau_tiles* t, int64_t idx, int64_t dims[8]);
 
+/* Lengths of the temperature series of n samples, read from the NPY headers on the worker pool (blocking).  A rank of a
+ * data-parallel job pads its slice to the longest series of the GLOBAL batch (the reference's LSTM runs over the padding,
+ * src/dataset.py:106, src/model.py:29-33) and needs the lengths of samples it does not decode. */
+int mau_tiles_series_lengths(mau_tiles* t, const int64_t* idx, int64_t n, int64_t* out);
+
 /* Decode n samples into batch-major buffers:
  *   input    [n, dims[0], dims[1], dims[2]]   (torch.stack(inputs),  src/dataset.py:99)
  *   target   [n, dims[3], dims[4], dims[5]]   (torch.stack(targets), src/dataset.py:101)

@@ -710,10 +710,12 @@ class Pool {
     cv_.notify_all();
     for (auto& t : th_) t.join();
   }
-  void push(std::function<void()> f) {
+  // `urgent` tasks (header-only reads a caller blocks on) go ahead of the queued decodes
+  void push(std::function<void()> f, bool urgent = false) {
     {
       std::lock_guard<std::mutex> g(mu_);
-      q_.push_back(std::move(f));
+      if (urgent) q_.push_front(std::move(f));
+      else q_.push_back(std::move(f));
     }
     cv_.notify_one();
   }
@@ -925,6 +927,55 @@ int mau_tiles_probe(mau_tiles* t, int64_t idx, int64_t dims[8]) {
       if (h.ndim != nd[m]) fail(MAU_TILES_E_SHAPE, "'%s': %s has %d dimensions, expected %d", mp.path.c_str(), kMemberNames[m], h.ndim, nd[m]);
       for (int k = 0; k < nd[m]; ++k) dims[at[m] + k] = h.shape[k];
     }
+    return 0;
+  });
+}
+
+int mau_tiles_series_lengths(mau_tiles* t, const int64_t* idx, int64_t n, int64_t* out) {
+  return guard([&]() -> int {
+    if (!t || n < 0 || (n > 0 && (!idx || !out))) return set_err(MAU_TILES_E_ARG, "mau_tiles_series_lengths: null argument");
+    for (int64_t k = 0; k < n; ++k)
+      if (idx[k] < 0 || idx[k] >= int64_t(t->paths.size())) return set_err(MAU_TILES_E_ARG, "mau_tiles_series_lengths: index " + std::to_string(idx[k]) + " out of range");
+    struct Job {
+      std::mutex mu;
+      std::condition_variable cv;
+      int64_t pending;
+      int code = 0;
+      std::string msg;
+    };
+    auto job = std::make_shared<Job>();
+    job->pending = n;
+    for (int64_t k = 0; k < n; ++k) {
+      t->pool->push([t, job, k, idx, out] {
+        int code = 0;
+        std::string msg;
+        try {
+          Archive mp(t->paths[size_t(idx[k])]);
+          Member mem[M_COUNT];
+          parse_zip(mp, mem);
+          if (!mem[M_SERIES].found) fail(MAU_TILES_E_MEMBER, "'%s': 'temperature_serie' is not a file in the archive", mp.path.c_str());
+          MemberStream s(mp, mem[M_SERIES], kMemberNames[M_SERIES], false, 16384);
+          NpyHeader h = read_npy_header(s, mp, kMemberNames[M_SERIES]);
+          if (h.ndim != 1) fail(MAU_TILES_E_SHAPE, "'%s': temperature_serie has %d dimensions, expected 1", mp.path.c_str(), h.ndim);
+          out[k] = h.shape[0];
+        } catch (const Fail& f) {
+          code = f.code;
+          msg = f.msg;
+        } catch (const std::exception& e) {
+          code = MAU_TILES_E_IO;
+          msg = e.what();
+        }
+        std::lock_guard<std::mutex> g(job->mu);
+        if (code && !job->code) {
+          job->code = code;
+          job->msg = msg;
+        }
+        if (--job->pending == 0) job->cv.notify_all();
+      }, /*urgent=*/true);
+    }
+    std::unique_lock<std::mutex> g(job->mu);   // idx / out belong to the caller: do not return before every task is done
+    job->cv.wait(g, [&] { return job->pending == 0; });
+    if (job->code) return set_err(job->code, job->msg);
     return 0;
   });
 }

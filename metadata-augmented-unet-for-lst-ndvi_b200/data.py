@@ -43,7 +43,7 @@ FLAG_NO_CRC, FLAG_ZLIB, FLAG_NICE = 1, 2, 4
 
 # every symbol include/mau_tiles.h declares (tests check the .so exports all of them)
 EXPORTS = ("mau_tiles_last_error", "mau_tiles_version", "mau_tiles_open", "mau_tiles_close", "mau_tiles_count",
-           "mau_tiles_threads", "mau_tiles_probe", "mau_tiles_read_batch", "mau_tiles_submit", "mau_tiles_wait",
+           "mau_tiles_threads", "mau_tiles_probe", "mau_tiles_series_lengths", "mau_tiles_read_batch", "mau_tiles_submit", "mau_tiles_wait",
            "mau_tiles_done", "mau_tiles_repack", "mau_tiles_inflate", "mau_tiles_crc32", "mau_tiles_stats")
 
 _lib = None
@@ -71,6 +71,7 @@ def lib():
         L.mau_tiles_count.restype = C.c_int64
         L.mau_tiles_threads.argtypes = [C.c_void_p]
         L.mau_tiles_probe.argtypes = [C.c_void_p, C.c_int64, p64]
+        L.mau_tiles_series_lengths.argtypes = [C.c_void_p, p64, C.c_int64, p64]
         batch = [C.c_void_p, p64, C.c_int64, pu8, p64, pf, pf, pf, pf, C.c_int64, C.c_void_p]
         L.mau_tiles_read_batch.argtypes = batch
         L.mau_tiles_submit.argtypes = batch
@@ -248,6 +249,19 @@ class FuturePredictionDataset(Dataset):
             _raise(rc)
         return list(d)
 
+    def series_lengths(self, indices: Sequence[int]) -> List[int]:
+        """Series lengths of ``indices`` from the NPY headers (decoded on the pool, cached: they never change)."""
+        cache = self.__dict__.setdefault("_series_len", {})
+        missing = [int(i) for i in dict.fromkeys(indices) if i not in cache]
+        if missing:
+            n = len(missing)
+            idx, out = (C.c_int64 * n)(*missing), (C.c_int64 * n)()
+            rc = lib().mau_tiles_series_lengths(self._handle, idx, n, out)
+            if rc:
+                _raise(rc)
+            cache.update(zip(missing, out))
+        return [cache[int(i)] for i in indices]
+
     def batch_dims(self) -> List[int]:
         """Shapes every batch is checked against: those of sample 0 (all samples of a processed dataset share them,
         src/data/processing_10m/process.py:165-187)."""
@@ -340,7 +354,7 @@ class _Ticket:
         rc = lib().mau_tiles_wait(self.ds._handle, self.ticket)
         if rc == E_CAPACITY:        # a series longer than the staging row: grow and decode this batch again
             ds, st = self.ds, self.st
-            longest = max(ds.probe(i)[7] for i in self.indices)
+            longest = max(ds.series_lengths(self.indices))
             ds._series_capacity = max(ds._series_capacity, 2 * longest)
             st["series"] = torch.empty((st["capacity"], ds._series_capacity), dtype=torch.float32,
                                        pin_memory=st["series"].is_pinned())
@@ -474,7 +488,7 @@ class TileLoader:
                 local = self._local(gb)
                 # the reference pads every series to the longest of the batch and the LSTM runs over that padding
                 # (src/dataset.py:106, src/model.py:29-33): ranks pad to the longest series of the *global* batch
-                width = max(ds.probe(i)[7] for i in gb) if self.world_size > 1 else 0
+                width = max(ds.series_lengths(gb)) if self.world_size > 1 else 0
                 if width > ds._series_capacity:
                     ds._series_capacity = 2 * width       # staging sets of the next epoch are allocated at this capacity
                 st = free.popleft()

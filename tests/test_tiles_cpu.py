@@ -508,3 +508,16 @@ def test_reader_survives_corrupted_archives(tmp_path):
             except (ValueError, KeyError, RuntimeError, OSError, IndexError):
                 raised += 1
     assert raised > 100
+
+
+def test_series_lengths_lookup_is_cached_and_reports_missing_members(synth, tmp_path):
+    ds = D.FuturePredictionDataset("train", processed_dir=synth, threads=3)
+    want = [int(np.load(f)["temperature_serie"].shape[0]) for f in ds.file_list]
+    assert ds.series_lengths(range(len(ds))) == want
+    assert ds.series_lengths([3, 3, 0]) == [want[3], want[3], want[0]]
+    assert set(ds._series_len) == set(range(len(ds)))
+    with pytest.raises(IndexError):
+        ds.series_lengths([len(ds)])
+    _one(tmp_path, temperature_serie=None)
+    with pytest.raises(KeyError, match="temperature_serie"):
+        D.FuturePredictionDataset("train", processed_dir=str(tmp_path)).series_lengths([0])
