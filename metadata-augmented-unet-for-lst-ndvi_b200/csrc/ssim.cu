@@ -6,7 +6,10 @@
 //   backward: one thread per prediction pixel gathers G^T * (a, b, c) over the <= 121 windows that contain it
 // 250 x 250 tiles, B = 16: 1.8 M windows x 121 taps x 5 moments = 1.1 GFLOP forward, 0.7 GFLOP backward -- fp32 FMA
 // work of ~0.1 ms next to an 8 ms step, so the direct (non-separable) form is kept for its simplicity.
-#include "ops.h"
+#ifndef MAU_KERNEL_ENV            // a test harness may supply the execution environment instead (it then defines this,
+#include "ops.h"                  // MAU_LAUNCH, MAU_CUDA, MAU_LAUNCHED, fail and ceil_div before including this file)
+#define MAU_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 #include "ssim_core.h"
 
 namespace mau {
@@ -91,13 +94,14 @@ int op_ssim_loss(const float* pred, const float* tgt, int B, int C, int H, int W
   mau_ssim::gaussian_window(win.g);
   float *a = work, *b = work + nwin, *c = work + 2 * nwin;
   MAU_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
-  ssim_forward_kernel<<<dim3((unsigned)ceil_div((int)nwin_plane, 256), (unsigned)(B * 2), 1), 256, 0, st>>>(pred, tgt, C, H, W, win, a, b, c, acc);
+  MAU_LAUNCH(ssim_forward_kernel, dim3((unsigned)ceil_div((int)nwin_plane, 256), (unsigned)(B * 2), 1), dim3(256), st, pred, tgt, C, H, W, win, a,
+             b, c, acc);
   MAU_LAUNCHED();
-  ssim_finalize_kernel<<<1, 1, 0, st>>>(acc, 1.0 / (double)nwin, loss);
+  MAU_LAUNCH(ssim_finalize_kernel, dim3(1), dim3(1), st, acc, 1.0 / (double)nwin, loss);
   MAU_LAUNCHED();
   if (grad) {
-    ssim_backward_kernel<<<dim3((unsigned)ceil_div(H * W, 256), (unsigned)(B * C), 1), 256, 0, st>>>(
-        pred, tgt, C, H, W, win, a, b, c, (float)(-1.0 / (double)nwin), grad);
+    MAU_LAUNCH(ssim_backward_kernel, dim3((unsigned)ceil_div(H * W, 256), (unsigned)(B * C), 1), dim3(256), st, pred, tgt, C, H, W, win, a, b, c,
+               (float)(-1.0 / (double)nwin), grad);
     MAU_LAUNCHED();
   }
   return 0;

@@ -162,3 +162,40 @@ def test_ssim_core_arithmetic_equals_torch_autograd(tmp_path):
     x = torch.rand(1, 2, 20, 20, generator=g)
     assert abs(float(S.ssim_loss(x, x))) < 1e-6                          # identical maps: SSIM = 1
     assert L.ssim_host(o.ctypes.data, t.ctypes.data, 1, 1, 20, 20, C.byref(lv), None) == 1     # needs both channels
+
+
+def test_ssim_kernel_source_under_cpu_emulation_equals_torch_autograd(tmp_path):
+    """csrc/ssim.cu itself -- the __global__ functions, their grid / block indexing, partial-block guards, the
+    shared-memory tree reduction with __syncthreads and the launch sequence of op_ssim_loss -- compiled for the CPU on
+    oracle/cuda_emu.h (256 real threads per block, barriers) and compared with torch autograd of the restatement.
+    Output buffers start as NaN: every element must have been written."""
+    import ctypes as C
+    import subprocess
+    from oracle import ssim_oracle as S
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "libssim_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", os.path.join(root, "oracle", "ssim_kernels_emu.cpp"), "-o", lib])
+    L = C.CDLL(lib)
+    L.emu_ssim_work_floats.restype = C.c_longlong
+    L.emu_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    g = torch.Generator().manual_seed(0)
+    for shape in ((2, 2, 23, 31), (1, 2, 11, 11), (3, 2, 40, 17), (2, 3, 30, 30)):      # 273 / 1 / 210 / 400 windows per plane
+        out = (torch.randn(shape, generator=g) * 0.7).requires_grad_(True)
+        tgt = torch.randn(shape, generator=g) * 0.7
+        tgt[:, 0] = tgt[:, 0].clamp(-1, 1)
+        loss = S.ssim_loss(out, tgt)
+        loss.backward()
+        o, t = out.detach().contiguous().numpy(), tgt.contiguous().numpy()
+        n = L.emu_ssim_work_floats(shape[0], shape[2], shape[3])
+        assert n == 3 * shape[0] * 2 * (shape[2] - 10) * (shape[3] - 10)
+        work, acc = np.full(n, np.nan, np.float32), np.full(1, np.nan, np.float64)
+        lv, grad = np.full(1, np.nan, np.float32), np.full_like(o, np.nan)
+        assert L.emu_ssim_loss(o.ctypes.data, t.ctypes.data, *shape, lv.ctypes.data, grad.ctypes.data, work.ctypes.data, acc.ctypes.data) == 0
+        gref = out.grad.numpy()
+        assert not np.isnan(grad).any() and not np.isnan(work).any()
+        assert abs(float(lv[0]) - float(loss.detach())) < 1e-6
+        assert np.abs(grad - gref).max() < 2e-5 * np.abs(gref).max()
+    # argument checks of the op: one channel only, tile smaller than the window, tile piq would down-sample first
+    z = np.zeros((1, 2, 400, 400), np.float32)
+    for shp in ((1, 1, 20, 20), (1, 2, 10, 30), (1, 2, 400, 400)):
+        assert L.emu_ssim_loss(z.ctypes.data, z.ctypes.data, *shp, lv.ctypes.data, None, work.ctypes.data, acc.ctypes.data) != 0
