@@ -325,14 +325,9 @@ class FuturePredictionDataset(Dataset):
         native_flip = isinstance(self.transform, RandomFlip)
         st = self.read_batch([idx], None, self.alloc_staging(1, dims=self.probe(idx)))
         n_series = int(st["series_len"][0])
-        x, y = st["input"][0], st["target"][0]
-        if self.transform is not None:
-            if native_flip:
-                if self.transform.decide():
-                    x, y = x.flip(2), y.flip(2)
-            else:
-                xa, ya = self.transform(x.numpy(), y.numpy())
-                x, y = torch.from_numpy(xa).float(), torch.from_numpy(ya).float()
+        x, y = st["input"][0], st["target"][0]      # an arbitrary transform has already run on the staging set (_Ticket.wait)
+        if native_flip and self.transform.decide():
+            x, y = x.flip(2), y.flip(2)
         return (x.contiguous(), st["metadata"][0].clone(), st["series"][0, :n_series].clone(),
                 torch.tensor([y1, m1]).float(), torch.tensor([y2, m2]).float(), y.contiguous())
 
@@ -465,6 +460,8 @@ class TileLoader:
         # prefetch + 2 staging sets: up to two being copied H2D, `prefetch` being decoded.  They are kept between epochs
         # (pinning 100 MB buffers is slow) but owned by one iterator at a time: a second, concurrent iterator over the
         # same loader finds none cached and allocates its own
+        if len(self.batch_sampler) == 0:      # an empty split yields nothing (and has no sample to take shapes from)
+            return
         rings, self._rings = self._rings, None
         if rings is None or any(st["series"].shape[1] < ds._series_capacity for st in rings):
             rings = [ds.alloc_staging(self.batch_size, pin=self._pin) for _ in range(self.prefetch + 2)]

@@ -521,3 +521,19 @@ def test_series_lengths_lookup_is_cached_and_reports_missing_members(synth, tmp_
     _one(tmp_path, temperature_serie=None)
     with pytest.raises(KeyError, match="temperature_serie"):
         D.FuturePredictionDataset("train", processed_dir=str(tmp_path)).series_lengths([0])
+
+
+def test_getitem_applies_a_transform_exactly_once(expected):
+    # torch DataLoader over the dataset (the reference arrangement) with the reference-style callable and with ours
+    from torch.utils.data import DataLoader
+    for make in (lambda: O.RandomFlip(42), lambda: D.RandomFlip(42)):
+        torch.manual_seed(7)
+        ds = D.FuturePredictionDataset("train", transform=make(), processed_dir=GOLD)
+        batches = list(DataLoader(ds, batch_size=4, shuffle=True, collate_fn=_collate_cpu))
+        assert_batches_equal("flip_e0", expected, batches)
+
+
+def test_empty_split_yields_nothing(tmp_path):
+    (tmp_path / "val").mkdir()
+    loader = D.create_dataloader("val", 4, False, "future", device="cpu", processed_dir=str(tmp_path))
+    assert len(loader) == 0 and list(loader) == []
