@@ -195,6 +195,13 @@ def test_ssim_kernel_source_under_cpu_emulation_equals_torch_autograd(tmp_path):
         assert not np.isnan(grad).any() and not np.isnan(work).any()
         assert abs(float(lv[0]) - float(loss.detach())) < 1e-6
         assert np.abs(grad - gref).max() < 2e-5 * np.abs(gref).max()
+    # the GPU check script itself (tools/ssim_gpu_check.py -> mau_b200.losses -> engine autograd wrappers), dry-run on the emulated kernels
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "ssim_dry_run.py"), lib], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["ok"] and len(d["cases"]) == 5 and all(c["ok"] for c in d["cases"]), d
     # argument checks of the op: one channel only, tile smaller than the window, tile piq would down-sample first
     z = np.zeros((1, 2, 400, 400), np.float32)
     for shp in ((1, 1, 20, 20), (1, 2, 10, 30), (1, 2, 400, 400)):
