@@ -458,8 +458,10 @@ def ssim_loss_terms(pred: torch.Tensor, target: torch.Tensor, need_grad: bool = 
 class _SsimFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
-        loss, grad = ssim_loss_terms(pred, target, True)
-        ctx.save_for_backward(grad)
+        need = bool(ctx.needs_input_grad[0])      # validation runs under no_grad (src/train.py:33): skip the backward kernel
+        loss, grad = ssim_loss_terms(pred, target, need)
+        if need:
+            ctx.save_for_backward(grad)
         return loss[0]
 
     @staticmethod

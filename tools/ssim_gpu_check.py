@@ -43,6 +43,9 @@ def main():
         ok &= good
         cases.append({"shape": list(shape), "ssim_abs_err": e_ssim, "total_abs_err": e_total, "grad_rel_err": e_grad,
                       "ssim_grad_rel_err": e_sgrad, "ok": good})
+    with torch.no_grad():      # validation path (src/train.py:33-42): values only, no backward kernel
+        val = losses.compute_all_loss(out.cuda(), tgt.cuda())
+    ok &= abs(float(val["ssim"]) - float(ref["ssim"])) < 2e-5 and set(val) == {"total", "mse", "gradient", "pixel", "ssim"}
     x = torch.rand(2, 2, 32, 32, generator=g)
     same = float(engine.ssim_loss(x.cuda(), x.cuda()))      # identical maps -> SSIM 1 -> loss 0
     ok &= abs(same) < 1e-6
