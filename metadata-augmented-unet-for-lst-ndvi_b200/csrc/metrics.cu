@@ -5,8 +5,11 @@
 // The host divides: MAE = sum|d|/count, RMSE = sqrt(sum d^2 / count).
 //   laplacian_sums: per (sample, channel) sum and sum of squares of scipy.ndimage.laplace(x) (mode 'reflect') for
 //   the prediction and the target (test/evaluate.py:241-242, np.var(laplace(.))); the host forms the variance.
+#ifndef MAU_KERNEL_ENV            // a test harness may supply the execution environment instead (oracle/cuda_emu.h)
 #include "ops.h"
 #include "vec.cuh"
+#define MAU_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 
 namespace mau {
 namespace {
@@ -108,7 +111,7 @@ int op_laplacian_sums(const float* pred, const float* tgt, int B, int C, int H, 
   if ((long long)B * C > 65535) return fail("laplacian_sums: B*C = %lld exceeds the grid limit 65535", (long long)B * C);
   MAU_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)B * C * 4, st));
   dim3 grid((unsigned)std::max(1, std::min(ceil_div(H * W, 256 * 4), 32)), (unsigned)(B * C), 1);
-  laplacian_sums_kernel<<<grid, 256, 0, st>>>(pred, tgt, C, H, W, temp_mean, temp_std, out);
+  MAU_LAUNCH(laplacian_sums_kernel, grid, dim3(256), st, pred, tgt, C, H, W, temp_mean, temp_std, out);
   MAU_LAUNCHED();
   return 0;
 }
@@ -120,7 +123,7 @@ int op_eval_metrics(const float* maps, int maps_c, const float* pred, const floa
   const int HW = H * W;
   MAU_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)B * C * 30, st));
   dim3 grid((unsigned)std::max(1, std::min(ceil_div(HW, 256 * 4), 64)), (unsigned)B, 1);
-  eval_metrics_kernel<<<grid, 256, 0, st>>>(maps, maps_c, pred, tgt, C, HW, temp_mean, temp_std, dw_map, sums);
+  MAU_LAUNCH(eval_metrics_kernel, grid, dim3(256), st, maps, maps_c, pred, tgt, C, HW, temp_mean, temp_std, dw_map, sums);
   MAU_LAUNCHED();
   return 0;
 }

@@ -206,3 +206,36 @@ def test_ssim_kernel_source_under_cpu_emulation_equals_torch_autograd(tmp_path):
     z = np.zeros((1, 2, 400, 400), np.float32)
     for shp in ((1, 1, 20, 20), (1, 2, 10, 30), (1, 2, 400, 400)):
         assert L.emu_ssim_loss(z.ctypes.data, z.ctypes.data, *shp, lv.ctypes.data, None, work.ctypes.data, acc.ctypes.data) != 0
+
+
+def test_emulation_shim_reproduces_kernels_that_are_verified_on_hardware(tmp_path):
+    """csrc/metrics.cu (class map, MAE / RMSE sums, Laplacian sums: all parity-green on a B200) under oracle/cuda_emu.h must
+    agree with the oracle as well -- the control experiment for the emulated check of the SSIM kernels."""
+    import ctypes as C
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "libmetrics_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-ffp-contract=off",
+                           os.path.join(root, "oracle", "metrics_kernels_emu.cpp"), "-o", lib])
+    L = C.CDLL(lib)
+    L.emu_eval_metrics.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p]
+    L.emu_laplacian_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    maps, _, _, tgt = O.synthetic_batch(2, 33, 29, T=4, seed=77)
+    maps[0, 3, 0, 2] = 1.0; maps[0, 6, 0, 2] = 0.5; maps[0, 0:3, 0, 2] = 0; maps[0, 4:6, 0, 2] = 0; maps[0, 7:9, 0, 2] = 0   # tie 3*1 == 6*.5
+    pred = torch.randn(2, 2, 33, 29, generator=torch.Generator().manual_seed(2))
+    m, p, t = maps.contiguous().numpy(), pred.contiguous().numpy(), tgt.contiguous().numpy()
+    want_dw, rows = O.eval_metrics(m, p, t, temp_mean=14.5, temp_std=7.25)
+    dw, sums = np.full((2, 33, 29), -1, np.int64), np.full((2, 2, 10, 3), np.nan)
+    assert L.emu_eval_metrics(m.ctypes.data, 23, p.ctypes.data, t.ctypes.data, 2, 2, 33, 29, 14.5, 7.25, dw.ctypes.data, sums.ctypes.data) == 0
+    assert np.array_equal(dw, want_dw)
+    for (i, ch, k, n, mae, rmse) in rows:
+        slot = 0 if k < 0 else 1 + k
+        assert int(sums[i, ch, slot, 0]) == n
+        assert abs(sums[i, ch, slot, 1] / n - mae) < 2e-5 * max(1.0, abs(mae))
+        assert abs(np.sqrt(sums[i, ch, slot, 2] / n) - rmse) < 2e-5 * max(1.0, abs(rmse))
+    lap = np.full((2, 2, 4), np.nan)
+    assert L.emu_laplacian_sums(p.ctypes.data, t.ctypes.data, 2, 2, 33, 29, 14.5, 7.25, lap.ctypes.data) == 0
+    n = 33 * 29
+    var = lap[..., 1::2] / n - (lap[..., 0::2] / n) ** 2
+    np.testing.assert_allclose(var, O.laplacian_variance(p, t, 14.5, 7.25), rtol=2e-5, atol=1e-9)
