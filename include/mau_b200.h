@@ -103,6 +103,12 @@ int mau_plan_forward(mau_plan* plan, void* const* state_dev, const float* maps_d
                      const float* temp_series_dev, const float* metadata_dev, float* out_dev,
                      void* stream);
 
+/* test / tooling access to the plan's own activation storage: device pointer of the NHWC buffer `name` (names, extents
+ * and channel strides are listed under "buffers" by mau_plan_describe_config; bf16 or fp32 elements according to the
+ * plan's precision).  which = 0: the activation, 1: its gradient twin (training plans; NULL until the plan has run a
+ * backward pass).  Used by the teacher-forced per-layer parity test (tests/test_bf16_layers_gpu.py). */
+int mau_plan_buffer_ptr(mau_plan* plan, const char* name, int which, void** ptr_dev, size_t* bytes);
+
 /* optional eval-mode hint: a number that changes whenever any state tensor is modified (e.g. the sum
  * of torch's tensor._version counters).  While it -- and every state pointer -- is unchanged between
  * forwards, the packed bf16 weights and folded BatchNorm vectors are reused; 0 = always re-pack. */
@@ -143,7 +149,7 @@ int mau_plan_profile(mau_plan* plan, int enable);
 int mau_plan_profile_read(mau_plan* plan, char* names, size_t names_len, float* ms, int max_n, int* n);
 
 /* --- training loss terms: replaces F.l1_loss / F.mse_loss / gradient_loss
- *     (src/utils/losses.py:5-25,33,67-70); SSIM (piq) is out of scope.
+ *     (src/utils/losses.py:5-25,33,67-70); the SSIM term is mau_ssim_loss below.
  * kind: 0 = L1 + lambda*grad, 1 = MSE + lambda*grad.  losses_dev[4] = {total, pixel, gradient, 0}.
  * grad_dev (nullable): dL_total/d pred, same shape as pred. */
 int mau_loss_forward_backward(int kind, const float* pred_dev, const float* target_dev, int B, int C,

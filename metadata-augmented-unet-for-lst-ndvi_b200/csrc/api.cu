@@ -100,6 +100,17 @@ int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* gr
   return plan->impl.run_backward(c);
 }
 
+int mau_plan_buffer_ptr(mau_plan* plan, const char* name, int which, void** ptr_dev, size_t* bytes) {
+  if (!plan || !name || !ptr_dev) return fail("mau_plan_buffer_ptr: null argument");
+  for (const Buf& b : plan->impl.bufs)
+    if (b.name == name) {
+      *ptr_dev = which ? b.gptr : b.ptr;
+      if (bytes) *bytes = b.bytes;
+      return 0;
+    }
+  return fail("mau_plan_buffer_ptr: no buffer named '%s'", name);
+}
+
 int mau_plan_set_state_version(mau_plan* plan, uint64_t version) {
   if (!plan) return fail("null plan");
   plan->impl.state_version = version;

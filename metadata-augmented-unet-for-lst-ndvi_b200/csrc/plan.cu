@@ -41,6 +41,16 @@ void* Plan::alloc(size_t bytes) {
   return p;
 }
 
+void Plan::note_op(const char* kind, const TRef* src, const TRef* dst, const std::string& extra) {
+  std::ostringstream o;
+  o << "{\"kind\":\"" << kind << "\"";
+  if (src) o << ",\"src\":[\"" << bufs[src->buf].name << "\"," << src->c0 << "," << src->C << "]";
+  if (dst) o << ",\"dst\":[\"" << bufs[dst->buf].name << "\"," << dst->c0 << "," << dst->C << "]";
+  if (!extra.empty()) o << "," << extra;
+  o << "}";
+  op_desc.push_back(o.str());
+}
+
 int Plan::add_state(const std::string& name, long long numel, int role) {
   state.push_back(StateInfo{name, numel, role});
   return (int)state.size() - 1;
@@ -467,6 +477,8 @@ int Plan::build_encoders(int lstm0, int fc0, int mlp0) {
 // placed right before the first consumer of the embedding slices
 int Plan::build_embed_broadcast(const TRef* t_dst, int n_t, const TRef* m_dst, int n_m) {
   const bool te = cfg.temporal_embeddings != 0, me = cfg.metadata_embeddings != 0;
+  if (te) for (int i = 0; i < n_t; ++i) note_op("emb", nullptr, &t_dst[i], "\"which\":\"temporal\"");
+  if (me) for (int i = 0; i < n_m; ++i) note_op("emb", nullptr, &m_dst[i], "\"which\":\"metadata\"");
   if ((!te && !me) || dry) return 0;
   const int B = cfg.batch, Hd = cfg.lstm_dim, td = cfg.temporal_dim, md = cfg.meta_dim, T = cfg.seq_len;
   const int t_off = 0, m_off = te ? td : 0;
@@ -568,6 +580,7 @@ int Plan::build_unet() {
     MAU_TRY(build_encoders(lstm0, fc0, mlp0));
   }
   // maps -> NHWC
+  { const TRef t{in0, 0, cfg.spatial_channels}; note_op("input", nullptr, &t); }
   if (!dry) {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
@@ -577,6 +590,7 @@ int Plan::build_unet() {
     fwd.push_back(op);
   }
   auto add_bcast = [&](TRef src, TRef dst) -> int {       // one-tile tensor -> every batch row of a slice
+    note_op("bcast", &src, &dst);
     if (dry) return 0;
     Op op; op.name = "bcast." + bufs[src.buf].name;
     const View xs = view(src), yd = view(dst);
@@ -585,6 +599,7 @@ int Plan::build_unet() {
     return 0;
   };
   auto add_pool = [&](TRef src, TRef dst) -> int {
+    note_op("pool", &src, &dst);
     if (dry) return 0;
     Op op; op.name = "pool." + bufs[src.buf].name;
     const View xs = view(src), yd = view(dst);
@@ -610,6 +625,8 @@ int Plan::build_unet() {
     const bool two = (2 * hs != ht) || (2 * wsrc != wt);
     TRef mid = src;
     if (two) mid = TRef{new_buf("up2x." + bufs[src.buf].name, 2 * hs, 2 * wsrc, src.C), 0, src.C};
+    if (two) { note_op("up", &src, &mid); note_op("up", &mid, &dst); }
+    else note_op("up", &src, &dst);
     BilinearTables t1, t2;
     if (two) { MAU_TRY(make_bilinear(hs, wsrc, 2 * hs, 2 * wsrc, &t1)); MAU_TRY(make_bilinear(2 * hs, 2 * wsrc, ht, wt, &t2)); }
     else MAU_TRY(make_bilinear(hs, wsrc, ht, wt, &t2));
@@ -677,6 +694,7 @@ int Plan::build_unet() {
   }
   // head
   const TRef hx{xdec[0], 0, F[0]};
+  note_op("head", &hx, nullptr, "\"w\":\"model.final.weight\",\"b\":\"model.final.bias\",\"index\":0");
   const int OC = cfg.out_channels;
   fwd_flops += 2.0 * OC * F[0] * (double)Hs[0] * Ws[0] * B;
   const bool fuse_head = !cfg.training && use_tc && conv_mode == MODE_HALO && OC <= 4 && F[0] <= 128 && !dry;
@@ -769,6 +787,7 @@ int Plan::build_unetpp() {
     mdst[l] = TRef{lv[l], embref(l).c0 + cfg.temporal_dim, cfg.meta_dim};
   }
   MAU_TRY(build_encoders(lstm0, fc0, mlp0));
+  { const TRef t{in0, 0, cfg.spatial_channels}; note_op("input", nullptr, &t); }
   if (!dry) {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
@@ -778,6 +797,7 @@ int Plan::build_unetpp() {
     fwd.push_back(op);
   }
   auto add_bcast = [&](TRef src, TRef dst) -> int {
+    note_op("bcast", &src, &dst);
     if (dry) return 0;
     Op op; op.name = "bcast." + bufs[src.buf].name;
     const View xs = view(src), yd = view(dst);
@@ -786,6 +806,7 @@ int Plan::build_unetpp() {
     return 0;
   };
   auto add_pool = [&](TRef src, TRef dst) -> int {
+    note_op("pool", &src, &dst);
     if (dry) return 0;
     Op op; op.name = "pool." + bufs[dst.buf].name;
     const View xs = view(src), yd = view(dst);
@@ -807,6 +828,7 @@ int Plan::build_unetpp() {
   };
   // _upsample_match: single-stage resize to the exact target size (src/model.py:111-121)
   auto add_up = [&](TRef src, TRef dst) -> int {
+    note_op("up", &src, &dst);
     BilinearTables t;
     MAU_TRY(make_bilinear(bufs[src.buf].H, bufs[src.buf].W, bufs[dst.buf].H, bufs[dst.buf].W, &t));
     if (dry) return 0;
@@ -858,6 +880,10 @@ int Plan::build_unetpp() {
   const int OC = cfg.out_channels;
   const size_t osz = (size_t)B * OC * Hs[0] * Ws[0];
   fwd_flops += nheads * 2.0 * OC * F[0] * (double)Hs[0] * Ws[0] * B;
+  for (int i = 0; i < nheads; ++i) {
+    const TRef hx = cfg.deep_supervision ? xref(0, i + 1) : xref(0, 4);
+    note_op("head", &hx, nullptr, "\"w\":\"" + state[fw[i]].name + "\",\"b\":\"" + state[fb[i]].name + "\",\"index\":" + std::to_string(i));
+  }
   const bool fuse_head = !cfg.training && !cfg.deep_supervision && use_tc && conv_mode == MODE_HALO && OC <= 4 &&
                          F[0] <= 128 && !dry;
   if (fuse_head) {
@@ -958,8 +984,12 @@ int Plan::build() {
        << ",\"h\":" << L->H << ",\"w\":" << L->W << ",\"kp\":" << L->Kp << ",\"flops\":" << L->flops << ",\"b\":" << L->B
        << ",\"segs\":[";
     for (int s = 0; s < L->nseg; ++s) js << (s ? "," : "") << "[" << L->seg_start[s] << "," << L->seg_len[s] << "]";
-    js << "],\"in\":\"" << bufs[L->in_buf].name << "\",\"out\":\"" << bufs[L->out.buf].name << "\",\"out_c0\":" << L->out.c0 << "}";
+    js << "],\"in\":\"" << bufs[L->in_buf].name << "\",\"out\":\"" << bufs[L->out.buf].name << "\",\"out_c0\":" << L->out.c0
+       << ",\"z\":\"" << (L->zbuf >= 0 ? bufs[L->zbuf].name : std::string()) << "\",\"emb_seg\":" << L->emb_seg
+       << ",\"input_needs_grad\":" << (L->input_needs_grad ? 1 : 0) << ",\"weight\":\"" << state[L->iw].name << "\"}";
   }
+  js << "],\"ops\":[";
+  for (size_t i = 0; i < op_desc.size(); ++i) js << (i ? "," : "") << op_desc[i];
   js << "],\"buffers\":[";
   for (size_t i = 0; i < bufs.size(); ++i)
     js << (i ? "," : "") << "{\"name\":\"" << bufs[i].name << "\",\"h\":" << bufs[i].H << ",\"w\":" << bufs[i].W

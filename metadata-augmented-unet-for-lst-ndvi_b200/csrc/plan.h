@@ -107,6 +107,8 @@ class Plan {
   void kend(const Ctx& c);
   std::vector<int> counter_idx; long long** counters_dev = nullptr;   // num_batches_tracked state indices / device pointer table
   std::string describe_json;
+  std::vector<std::string> op_desc;   // JSON objects of the non-conv ops (pool / up / bcast / emb / head), for describe
+  void note_op(const char* kind, const TRef* src, const TRef* dst, const std::string& extra = "");
   std::vector<void*> last_state; const float* last_series = nullptr; const float* last_md = nullptr;
   // eval-mode weight cache: packed weights / folded BN are reused while the caller's state is unchanged
   unsigned long long state_version = 0, packed_version = 0;

@@ -48,7 +48,7 @@ EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
     "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
-    "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss",
+    "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss",
     "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
@@ -84,6 +84,7 @@ def lib():
         L.mau_plan_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         L.mau_plan_set_grad_hook.argtypes = [C.c_void_p, GRAD_HOOK, C.c_void_p]
         L.mau_plan_set_state_version.argtypes = [C.c_void_p, C.c_uint64]
+        L.mau_plan_buffer_ptr.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.mau_plan_set_stats_sync.argtypes = [C.c_void_p, STATS_SYNC, C.c_void_p, C.c_int]
         L.mau_plan_profile.argtypes = [C.c_void_p, C.c_int]
         L.mau_plan_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_float),
@@ -132,6 +133,26 @@ def lib():
     return _lib
 
 
+# ---------------------------------------------------------------------- #
+# State epoch.  Eval plans keep packed bf16 weights / folded BatchNorm vectors while the caller's state is unchanged.
+# torch's per-tensor ``_version`` counters see every in-place torch op, but NOT writes through raw device pointers:
+# FusedAdamW.step (csrc/optim.cu) and the training forward's running_mean / running_var / num_batches_tracked updates.
+# Both bump this process-wide epoch, which is folded into the version handed to ``mau_plan_set_state_version``.
+# ---------------------------------------------------------------------- #
+_state_epoch = 0
+
+
+def bump_state_epoch() -> int:
+    """Call after writing parameters or buffers through raw device pointers (outside torch's version tracking)."""
+    global _state_epoch
+    _state_epoch += 1
+    return _state_epoch
+
+
+def state_epoch() -> int:
+    return _state_epoch
+
+
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = lib().mau_last_error()
@@ -169,6 +190,8 @@ class _DevMem:
 
 
 def device_alias(ptr: int, n: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    if dtype == torch.bfloat16:       # no bf16 in the array interface: alias as 16-bit words, reinterpret
+        return torch.as_tensor(_DevMem(ptr, n, "<i2"), device=device).view(torch.bfloat16)
     typestr = {torch.float64: "<f8", torch.float32: "<f4"}[dtype]
     return torch.as_tensor(_DevMem(ptr, n, typestr), device=device)
 
@@ -195,6 +218,7 @@ class Plan:
         self.uses_metadata = bool(cfg.get("metadata_embeddings", 1))
         self.uses_series = bool(cfg.get("temporal_embeddings", 1))
         self._hook_ref = None
+        self._pending = None        # token of the forward whose backward has not run yet (see HotPathFn)
         B, H, W = cfg["batch"], cfg["height"], cfg["width"]
         self.out_shape = ((4,) if cfg.get("deep_supervision") else ()) + (B, cfg["out_channels"], H, W)
 
@@ -209,6 +233,11 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+    @property
+    def pending(self) -> bool:
+        """True while an autograd graph still needs this plan's saved activations."""
+        return self._pending is not None
 
     @property
     def workspace_bytes(self) -> int:
@@ -256,8 +285,10 @@ class Plan:
             self._check_state(state)
             self._validated = key
         if not self.cfg.get("training"):
-            # 1 + sum of in-place modification counters: unchanged state => packed weights are reused
-            lib().mau_plan_set_state_version(self._h, 1 + sum(t._version for t in state))
+            # in-place modification counters + the epoch of raw-pointer writes: unchanged state => packed weights are reused
+            lib().mau_plan_set_state_version(self._h, 1 + sum(t._version for t in state) + (_state_epoch << 32))
+        else:
+            bump_state_epoch()          # this forward updates the BatchNorm running statistics through raw pointers
         if out is None:
             out = torch.empty(self.out_shape, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
@@ -271,6 +302,30 @@ class Plan:
         with torch.cuda.device(self.device):
             check(lib().mau_plan_backward(self._h, grad_out.data_ptr(), self._ptr_array(grads),
                                           _stream_ptr()), "backward")
+
+    def buffer(self, name: str, grad: bool = False) -> Optional[torch.Tensor]:
+        """Zero-copy [B, H, W, channel_stride] view of one of the plan's NHWC buffers (tests / tooling): the activation
+        or, with ``grad=True``, its gradient twin (``None`` before the first backward)."""
+        info = self._buffer_info().get(name)
+        if info is None:
+            raise KeyError(name)
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        check(lib().mau_plan_buffer_ptr(self._h, name.encode(), int(grad), C.byref(ptr), C.byref(nbytes)), "buffer_ptr")
+        if not ptr.value:
+            return None
+        dtype = torch.float32 if self.cfg.get("precision") == PRECISIONS["fp32"] else torch.bfloat16
+        n = info["b"] * info["h"] * info["w"] * info["cs"]
+        return device_alias(ptr.value, n, dtype, self.device).view(info["b"], info["h"], info["w"], info["cs"])
+
+    def _buffer_info(self):
+        if getattr(self, "_binfo", None) is None:
+            self._binfo = {b["name"]: b for b in self.describe()["buffers"]}
+        return self._binfo
+
+    def describe(self) -> Dict:
+        if getattr(self, "_desc", None) is None:
+            self._desc = describe(self.cfg)
+        return self._desc
 
     def set_grad_hook(self, fn):
         """fn(first_index, last_index) is called from inside backward when those state
@@ -308,13 +363,38 @@ class Plan:
         return list(zip(nm, [ms[i] for i in range(n.value)]))
 
 
+class _PendingToken:
+    """Marks a plan as holding the saved activations of a live autograd graph.  Released by backward, or when the graph
+    is dropped without a backward (the ctx, and with it this token, is garbage-collected)."""
+
+    __slots__ = ("plan", "__weakref__")
+
+    def __init__(self, plan: "Plan"):
+        self.plan = plan
+        plan._pending = self
+
+    def release(self):
+        if self.plan is not None and self.plan._pending is self:
+            self.plan._pending = None
+        self.plan = None
+
+    def __del__(self):  # pragma: no cover - exercised through gc
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class HotPathFn(torch.autograd.Function):
     """The single autograd node of the model (reference: the whole nn.Module graph of
     src/model.py:261-292 / :123-193 as recorded by PyTorch autograd)."""
 
     @staticmethod
     def forward(ctx, plan: Plan, state, diff_idx, dp, maps, series, md, *diff_params):
+        if plan.pending:
+            raise RuntimeError("mau_b200: this plan still holds the activations of a forward that awaits its backward")
         out = plan.forward(state, maps, series, md)
+        ctx.token = _PendingToken(plan)
         ctx.plan, ctx.diff_idx, ctx.n_state, ctx.dp = plan, diff_idx, len(state), dp
         # backward re-reads the series (LSTM BPTT) and the metadata (MLP) through the raw pointers the
         # plan kept from this forward: keep the tensors alive until then
@@ -326,11 +406,15 @@ class HotPathFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         plan: Plan = ctx.plan
+        if plan._pending is not ctx.token:
+            raise RuntimeError("mau_b200: backward() called twice on the same graph, or the plan's saved activations were "
+                               "released (a plan keeps the activations of exactly one forward)")
         grad_out = grad_out.contiguous().float()
         if ctx.dp is not None:        # data parallel: grads are views of one flat buffer, all-reduced
             grads_full, outs = ctx.dp.make_grads(plan, ctx.diff_idx, ctx.shapes, ctx.params)   # from inside backward
             plan.backward(grad_out, grads_full)
             ctx.dp.finish(plan)
+            ctx.token.release()
             return (None, None, None, None, None, None, None, *outs)
         grads_full: List[Optional[torch.Tensor]] = [None] * ctx.n_state
         outs = []
@@ -339,6 +423,7 @@ class HotPathFn(torch.autograd.Function):
             grads_full[i] = g
             outs.append(g)
         plan.backward(grad_out, grads_full)
+        ctx.token.release()
         return (None, None, None, None, None, None, None, *outs)
 
 

@@ -92,8 +92,18 @@ class _EngineNet(nn.Module):
         return out
 
     def _plan_for(self, B: int, H: int, W: int, T: int, training: bool, device: torch.device, shared: bool = False):
-        key = (B, H, W, T, bool(training), self.precision, device.index, bool(shared))
-        plan = self._plans.get(key)
+        """Plan cache.  A plan holds ONE set of saved activations, so a training plan whose forward still waits for its
+        backward (``l1 = crit(model(a)); l2 = crit(model(b)); (l1 + l2).backward()``) is never reused: the second forward
+        of that shape takes the next free slot (at most ``_MAX_PENDING`` graphs of one shape alive at a time)."""
+        base = (B, H, W, T, bool(training), self.precision, device.index, bool(shared))
+        for slot in range(self._MAX_PENDING):
+            plan = self._plans.get(base + (slot,))
+            if plan is None or not plan.pending:
+                break
+        else:
+            raise RuntimeError(f"mau_b200: {self._MAX_PENDING} forward passes of shape {(B, H, W)} are waiting for their "
+                               "backward; each holds a full set of saved activations -- call backward() or drop the outputs")
+        key = base + (slot,)
         if plan is None:
             cfg = dict(self._engine_config())
             cfg.update(batch=B, height=H, width=W, seq_len=T, training=int(training),
@@ -103,10 +113,15 @@ class _EngineNet(nn.Module):
             if shared:
                 cfg["flags"] |= engine.FLAG_SHARED_MAPS
             plan = engine.Plan(cfg)
-            if len(self._plans) >= 8:           # bound the workspace held by stale shapes
-                self._plans.pop(next(iter(self._plans))).close()
+            if len(self._plans) >= 8:           # bound the workspace held by stale shapes (never a plan autograd still needs)
+                for k in list(self._plans):
+                    if not self._plans[k].pending:
+                        self._plans.pop(k).close()
+                        break
             self._plans[key] = plan
         return plan
+
+    _MAX_PENDING = 4
 
     def assume_shared_maps(self, mode="auto"):
         """``True``: the caller guarantees that all rows of ``maps`` / ``temp_series`` are identical (the

@@ -62,4 +62,7 @@ class FusedAdamW(torch.optim.AdamW):
                     engine.check(L.mau_adamw_step(n, arrs[0], arrs[1], arrs[2], arrs[3], numels, lr, float(b1), float(b2),
                                                   float(group["eps"]), float(group["weight_decay"]), t,
                                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "adamw_step")
+        # the kernel wrote the parameters through raw pointers: torch's tensor._version did not move, so tell the
+        # engine that every cached weight pack (eval plans) is stale
+        engine.bump_state_epoch()
         return loss

@@ -14,6 +14,16 @@ the build container and writes ``tests/golden/*.npz``; ``tests/test_oracle.py``
 checks this restatement against those vectors.  The SSIM loss term
 (``piq.ssim``, third-party, unpinned, absent) is *not* restated: parity unpinned
 for that term only.
+
+``emulate_bf16=True`` (``forward`` / ``train_step_grads``) is the SAME graph with
+values rounded to bfloat16 exactly where the B200 engine stores bf16:
+the NHWC input, the packed convolution weights, every stored pre-BatchNorm output
+``z``, every stored activation ``y`` (BN+ReLU, bilinear stages, embedding planes),
+and -- in backward -- every stored gradient (``dz``, activation gradients).  All
+arithmetic between two stores stays fp32, like the kernels (fp32 accumulation in
+TMEM, fp32 BatchNorm coefficients, fp32 LSTM / MLP / head / loss).  With the flag off
+nothing changes, so the pin above also pins the graph of the emulation; the rounding
+points themselves are a statement about the engine, not about the reference.
 """
 from __future__ import annotations
 
@@ -26,6 +36,66 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 BN_EPS = 1e-5        # nn.BatchNorm2d default, src/model.py:13,15
 BN_MOMENTUM = 0.1    # nn.BatchNorm2d default
+
+
+# --------------------------------------------------------------------------- #
+# bf16 storage emulation (off by default)
+# --------------------------------------------------------------------------- #
+_EMULATE_BF16 = False
+
+
+class emulate_bf16_storage:
+    """Context manager: inside it the building blocks below round to bfloat16 where the engine stores bf16."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global _EMULATE_BF16
+        self.prev, _EMULATE_BF16 = _EMULATE_BF16, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _EMULATE_BF16
+        _EMULATE_BF16 = self.prev
+        return False
+
+
+def _bf16(x: Tensor) -> Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)      # round-to-nearest-even, like __float2bfloat16_rn
+
+
+class _StoreBf16(torch.autograd.Function):
+    """A tensor written to HBM as bf16: the value is rounded in forward, its gradient (also stored as bf16 by the
+    engine) is rounded in backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _PackBf16(torch.autograd.Function):
+    """Packed convolution weights: bf16 in forward; the weight gradient leaves the wgrad kernel in fp32."""
+
+    @staticmethod
+    def forward(ctx, w):
+        return _bf16(w)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _st(x: Tensor) -> Tensor:
+    return _StoreBf16.apply(x) if _EMULATE_BF16 else x
+
+
+def _pk(w: Tensor) -> Tensor:
+    return _PackBf16.apply(w) if _EMULATE_BF16 else w
 
 
 # --------------------------------------------------------------------------- #
@@ -51,10 +121,13 @@ def _bn(sd: Dict[str, Tensor], prefix: str, x: Tensor, training: bool,
 
 def vgg_block(sd, prefix: str, x: Tensor, training: bool, new_stats=None) -> Tensor:
     """VGGBlock.forward, src/model.py:18-21: relu(bn1(conv1(x))), relu(bn2(conv2(.)))."""
-    x = F.conv2d(x, sd[prefix + ".conv1.weight"], sd[prefix + ".conv1.bias"], padding=1)
-    x = F.relu(_bn(sd, prefix + ".bn1", x, training, new_stats))
-    x = F.conv2d(x, sd[prefix + ".conv2.weight"], sd[prefix + ".conv2.bias"], padding=1)
-    x = F.relu(_bn(sd, prefix + ".bn2", x, training, new_stats))
+    # bf16 emulation: training plans store the pre-BN output z and the activation y; eval plans fold BatchNorm into
+    # the convolution epilogue (fp32 accumulator -> scale/shift -> ReLU -> one bf16 store)
+    zst = _st if training else (lambda t: t)
+    x = zst(F.conv2d(x, _pk(sd[prefix + ".conv1.weight"]), sd[prefix + ".conv1.bias"], padding=1))
+    x = _st(F.relu(_bn(sd, prefix + ".bn1", x, training, new_stats)))
+    x = zst(F.conv2d(x, _pk(sd[prefix + ".conv2.weight"]), sd[prefix + ".conv2.bias"], padding=1))
+    x = _st(F.relu(_bn(sd, prefix + ".bn2", x, training, new_stats)))
     return x
 
 
@@ -91,7 +164,7 @@ def metadata_encoder(sd, prefix: str, md: Tensor) -> Tensor:
 
 def bilinear_ac(x: Tensor, size: Tuple[int, int]) -> Tensor:
     """Bilinear resize, align_corners=True (src/model.py:121, 219, 245)."""
-    return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+    return _st(F.interpolate(x, size=size, mode="bilinear", align_corners=True))
 
 
 def head(sd, prefix: str, x: Tensor) -> Tensor:
@@ -113,7 +186,7 @@ def unet_forward(sd, maps, series, md, *, temporal_embeddings=True, metadata_emb
     pool = lambda t: F.max_pool2d(t, 2, 2)
     blk = lambda name, t: vgg_block(sd, f"{p}.{name}", t, training, new_stats)
 
-    x0_0 = blk("conv0_0", maps)
+    x0_0 = blk("conv0_0", _st(maps))
     x1_0 = blk("conv1_0", pool(x0_0))
     x2_0 = blk("conv2_0", pool(x1_0))
     x3_0 = blk("conv3_0", pool(x2_0))
@@ -122,9 +195,9 @@ def unet_forward(sd, maps, series, md, *, temporal_embeddings=True, metadata_emb
     B, _, H, W = x4_0.shape
     cat = [x4_0]
     if t_emb is not None:
-        cat.append(t_emb[:, :, None, None].expand(B, t_emb.shape[1], H, W))
+        cat.append(_st(t_emb[:, :, None, None].expand(B, t_emb.shape[1], H, W)))
     if m_emb is not None:
-        cat.append(m_emb[:, :, None, None].expand(B, m_emb.shape[1], H, W))
+        cat.append(_st(m_emb[:, :, None, None].expand(B, m_emb.shape[1], H, W)))
     x4_0 = blk("conv4_0", torch.cat(cat, 1) if len(cat) > 1 else x4_0)
 
     def up_to(src, ref):
@@ -146,7 +219,7 @@ def unetpp_forward(sd, maps, series, md, *, deep_supervision=False, training=Fal
     """UrbanPredictor_unetpp.forward, src/model.py:123-193 (always both embeddings)."""
     t_emb = temporal_encoder(sd, p + ".temporal_encoder", series)
     m_emb = metadata_encoder(sd, p + ".meta_encoder", md)
-    emb = torch.cat([t_emb, m_emb], 1)                            # src/model.py:103
+    emb = _st(torch.cat([t_emb, m_emb], 1))                       # src/model.py:103 (bf16 planes in the level buffers)
     pool = lambda t: F.max_pool2d(t, 2, 2)
     blk = lambda name, t: vgg_block(sd, f"{p}.{name}", t, training, new_stats)
 
@@ -155,7 +228,7 @@ def unetpp_forward(sd, maps, series, md, *, deep_supervision=False, training=Fal
         e = emb[:, :, None, None].expand(emb.shape[0], emb.shape[1], H, W)
         return blk(name, torch.cat([*same_level, bilinear_ac(lower, (H, W)), e], 1))
 
-    x0_0 = blk("conv0_0", maps)
+    x0_0 = blk("conv0_0", _st(maps))
     x1_0 = blk("conv1_0", pool(x0_0))
     x0_1 = node("conv0_1", [x0_0], x1_0)
     x2_0 = blk("conv2_0", pool(x1_0))
@@ -176,8 +249,11 @@ def unetpp_forward(sd, maps, series, md, *, deep_supervision=False, training=Fal
     return head(sd, p + ".final", x0_4)
 
 
-def forward(sd, model_type: str, maps, series, md, **kw):
-    """UrbanPredictor.forward dispatch, src/model.py:295-329."""
+def forward(sd, model_type: str, maps, series, md, emulate_bf16: bool = False, **kw):
+    """UrbanPredictor.forward dispatch, src/model.py:295-329.  ``emulate_bf16``: see the module docstring."""
+    if emulate_bf16:
+        with emulate_bf16_storage(True):
+            return forward(sd, model_type, maps, series, md, **kw)
     if model_type == "unet":
         kw.pop("deep_supervision", None)
         return unet_forward(sd, maps, series, md, **kw)
@@ -283,8 +359,12 @@ def laplacian_variance(pred, tgt, temp_mean=None, temp_std=None):
 # --------------------------------------------------------------------------- #
 # training step (src/train.py:244-256) -- gradients through torch autograd
 # --------------------------------------------------------------------------- #
-def train_step_grads(sd, model_type, maps, series, md, tgt, loss="l1", lambda_grad=0.1, **kw):
-    """fwd (train-mode BN) + loss + bwd.  Returns (out, loss, grads{name}, new_stats)."""
+def train_step_grads(sd, model_type, maps, series, md, tgt, loss="l1", lambda_grad=0.1, emulate_bf16=False, **kw):
+    """fwd (train-mode BN) + loss + bwd.  Returns (out, loss, grads{name}, new_stats).  ``emulate_bf16``: the same step
+    with bf16 rounding at the engine's storage points (forward values and backward gradients), see the module docstring."""
+    if emulate_bf16:
+        with emulate_bf16_storage(True):      # autograd runs the custom backward functions inside lv.backward() below
+            return train_step_grads(sd, model_type, maps, series, md, tgt, loss=loss, lambda_grad=lambda_grad, **kw)
     params = {k: v.detach().clone().requires_grad_(True)
               for k, v in sd.items() if v.is_floating_point() and "running_" not in k}
     full = dict(sd)
