@@ -2,18 +2,25 @@
 """bench.py -- tiles/s of the Metadata-Augmented U-Net hot path on B200 (and the CPU reference arm).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5 | --workload infer|train] [--batch B]
-    python bench.py --impl reference ...        # the reference algorithm on the host CPU (oracle port, all cores)
+    python bench.py --impl reference ...        # the reference's own module on the host CPU (all cores)
 
 One "step" = one pass of the hot path over one batch of synthetic tiles (23x250x250).
 `--config` selects a BASELINE.json configs[] entry (1-based): 1 = no-embedding U-Net inference in the fp32 parity
-mode (B=8), 2 (default) = U-Net + metadata MLP inference, bf16, B=16 per GPU, 3 = the same model training (forward +
-L1 loss kernel + backward + fused AdamW), 4 = U-Net++ training, 5 = the B=50 metadata-sensitivity sweep.
-With no --config / --workload the line is config 2 and additionally carries config 3 under "training".
-Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), tiles sharded across ranks (weak
-scaling, no collective in inference); training adds the NCCL gradient all-reduce overlapped with backward.
-Timing: CUDA events around K steps after W warm-up steps, inputs rotate over 4 batches (working set >> L2),
-max over ranks; `e2e` repeats the measurement from pinned HOST buffers with H2D / D2H copies inside the timed
-region; `roofline` times the conv-family kernels with CUDA events right around their launches.
+mode (B=8), 2 = U-Net + metadata MLP inference, bf16, B=16 per GPU, 3 = the same model training (forward + L1 loss
+kernel + backward + fused AdamW, gradient all-reduce when N > 1), 4 = U-Net++ training, 5 = the B=50
+metadata-sensitivity sweep.
+
+Default invocation (no --config / --workload): the line is config 3 -- "training tiles/sec (fwd+bwd)", the first number
+BASELINE.json's metric names and the only one with a collective, so the driver's scaling efficiency measures the
+all-reduce -- and carries the inference number (config 2) under "inference" plus short runs of configs 1, 4 and 5 under
+"riders", at every N.
+
+Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), tiles sharded across ranks (weak scaling).
+Timing: CUDA events around K steps after W warm-up steps, inputs rotate over 4 batches (working set >> L2), max over
+ranks.  `sustained`: the same loop repeated for >= --sustain-s seconds with clocks / power sampled under that load.
+`e2e`: the same measurement from pinned HOST buffers with H2D / D2H copies inside the timed region.  `roofline`: the
+conv-family kernels timed with CUDA events right around their launches, once right after the sustained loop (against
+the measured sustained peak) and once cold in `roofline.burst` (against the measured burst peak) -- never mixed.
 """
 import argparse
 import json
@@ -27,7 +34,6 @@ sys.path.insert(0, ROOT)
 
 TILE = 250
 CTOR = (23, 828, 64, 8, 64, 96, 2)           # conf/config.yaml:18-20,49-51; out_channels 2
-KW = dict(temporal_embeddings=False, metadata_embeddings=True)
 # BASELINE.json configs[] -> (model_type, ctor kwargs, workload, per-GPU batch, shared maps, description)
 CONFIGS = {
     1: ("unet", dict(temporal_embeddings=False, metadata_embeddings=False), "infer", 8, False,
@@ -41,6 +47,18 @@ CONFIGS = {
     5: ("unet", dict(temporal_embeddings=True, metadata_embeddings=True), "infer", 50, True,
         "U-Net + LSTM + metadata, metadata-sensitivity sweep: 50 rows share one tile and series (test/metadata_sensitivity.py:294-311)"),
 }
+REF_MODULE = os.path.join(ROOT, "oracle", "_ref", "src", "model.py")     # built by oracle/build_ref.py from /root/reference
+
+
+def metric_name(workload):
+    return "inference tiles/sec" if workload == "infer" else "training tiles/sec (fwd+bwd)"
+
+
+def config_block(cfg_id, B, world):
+    """Identical for the B200 arm and the CPU reference arm of one invocation (the driver compares them)."""
+    return {"workload": CONFIGS[cfg_id][5], "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_gpu": B,
+            "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": "4 rotating input batches (368 MB) + ~2 GB of activations per step: working set > 126 MB L2"}
 
 
 def peaks():
@@ -48,19 +66,17 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons during the timed region (pynvml == nvidia-smi's source).  NVML is
-    initialised before the timed region starts; the main thread adds one sample of its own inside the region
-    so that even a 20 ms run carries evidence."""
-
-    NAMES = None
+    """Samples SM clock, power and throttle reasons during a timed region (pynvml == nvidia-smi's source).  NVML is
+    initialised before the region starts; the main thread adds one sample of its own inside the region so that even
+    a 20 ms run carries evidence."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.power, self.reasons, self.stop_flag, self.max_mhz = index, [], [], set(), False, None
         self.nv = self.h = None
         try:
             import pynvml as nv
@@ -79,6 +95,7 @@ class ClockSampler(threading.Thread):
             return
         try:
             self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
             for bit, nm in self.names.items():
                 if r & bit:
@@ -94,36 +111,75 @@ class ClockSampler(threading.Thread):
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "samples": len(s),
-                "reasons": sorted(self.reasons)}
+                "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference(workload, batch, iters, warm=1, mt="unet", kw=None, shared=False):
-    """The reference algorithm on the host cores: oracle/unet_oracle.py (functional torch CPU fp32,
-    same ATen kernels the reference module dispatches to).  Uses every host core: torchrun exports
-    OMP_NUM_THREADS=1 to its workers, which would otherwise pin the CPU arm to one thread."""
+def load_reference_module():
+    """The UNMODIFIED reference module (src/model.py of the reference repository), from the copy oracle/build_ref.py
+    places under oracle/_ref/ (git-ignored, travels to the GPU box).  None if that copy does not exist."""
+    if not os.path.exists(REF_MODULE):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mau_reference_model", REF_MODULE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference(cfg_id, batch, iters, warm=1):
+    """The reference's CPU path for one config on all host cores: the real `UrbanPredictor` of src/model.py when
+    oracle/_ref holds it (kind "reference"), else the oracle port (kind "port": oracle/unet_oracle.py, same ATen
+    kernels).  Training = forward + F.l1_loss + backward + torch.optim.AdamW step, like the B200 arm.
+    torchrun exports OMP_NUM_THREADS=1 to its workers, which would otherwise pin the CPU arm to one thread."""
     import torch
-    import mau_b200
+    import torch.nn.functional as F
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     from oracle import unet_oracle as O
-    kw = KW if kw is None else kw
-    torch.manual_seed(42)
-    m = mau_b200.UrbanPredictor(mt, *CTOR, **kw)
-    O.perturb_bn_stats(m.state_dict())
-    sd = m.state_dict()
+    mt, kw, workload, _, shared, _ = CONFIGS[cfg_id]
+    ref = load_reference_module()
     x, ts, md, tgt = O.synthetic_batch(batch, TILE, TILE, seed=1002)
     if shared:      # the reference materialises the repeated batch (test/metadata_sensitivity.py:294-307)
         x, ts = x[:1].repeat(batch, 1, 1, 1), ts[:1].repeat(batch, 1)
+    torch.manual_seed(42)
+    if ref is not None:
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the reference print()s at construction (src/model.py:203)
+            model = ref.UrbanPredictor(mt, *CTOR, **kw)
+        O.perturb_bn_stats(model.state_dict())
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3)       # src/train.py:213-214
+        model.train(workload == "train")
+
+        def step():
+            if workload == "infer":
+                with torch.no_grad():
+                    model(x, ts, md)
+            else:
+                loss = F.l1_loss(model(x, ts, md), tgt)
+                loss.backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+        kind, what = "reference", "the reference's UrbanPredictor (oracle/_ref/src/model.py, unmodified)"
+    else:
+        import mau_b200
+        m = mau_b200.UrbanPredictor(mt, *CTOR, **kw)
+        O.perturb_bn_stats(m.state_dict())
+        sd = m.state_dict()
+
+        def step():
+            if workload == "infer":
+                with torch.no_grad():
+                    O.forward(sd, mt, x, ts, md, training=False, **kw)
+            else:
+                O.train_step_grads(sd, mt, x, ts, md, tgt, loss="l1", **kw)
+        kind, what = "port", "oracle/unet_oracle.py (functional restatement, same ATen kernels)"
     times = []
     for i in range(warm + iters):
         t0 = time.perf_counter()
-        if workload == "infer":
-            with torch.no_grad():
-                O.forward(sd, mt, x, ts, md, training=False, **kw)
-        else:
-            O.train_step_grads(sd, mt, x, ts, md, tgt, loss="l1", **kw)
+        step()
         if i >= warm:
             times.append(time.perf_counter() - t0)
-    return batch * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads()
+    return dict(value=batch * len(times) / sum(times), sec=sum(times) / len(times), cores=torch.get_num_threads(), kind=kind,
+                what=what)
 
 
 def main():
@@ -143,42 +199,42 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=["infer", "train"], help="shorthand: infer = --config 2, train = --config 3")
-    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE.json configs[] index (default 2)")
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE.json configs[] index (default 3 + riders)")
     ap.add_argument("--batch", type=int, default=None, help="tiles per GPU per step (default: conf/config.yaml:45 = 16; 50 for the sweep)")
-    ap.add_argument("--comm-ctas", type=int, default=None, help="data-parallel training: CTAs NCCL may use (and SMs our persistent kernels leave free); "
-                    "default 4 at 2 GPUs, 8 beyond (measured: 9.29 / 9.44 ms per step at N=2, 9.88 / 9.09 ms at N=8)")
+    ap.add_argument("--comm-ctas", type=int, default=None, help="data-parallel training: CTAs NCCL may use (and SMs our persistent kernels leave free)")
     ap.add_argument("--sync-bn", action="store_true", help="data-parallel training: SyncBN (global-batch statistics)")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` block (0 = skip)")
+    ap.add_argument("--criterion", default="l1", choices=["l1", "l1-gradient-ssim"], help="training loss: L1 (default) or the reference's default criterion (conf/config.yaml:42)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-riders", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="print per-layer device times to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     default_invocation = args.config is None and args.workload is None
-    cfg_id = args.config if args.config is not None else (3 if args.workload == "train" else 2)
+    cfg_id = args.config if args.config is not None else (2 if args.workload == "infer" else 3)
     mt, kw, workload, def_batch, shared, workload_name = CONFIGS[cfg_id]
-    args.workload = workload
-    metric = "inference tiles/sec" if args.workload == "infer" else "training tiles/sec (fwd+bwd)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = 8 if args.workload == "infer" else 4
-        v, sec, threads = cpu_reference(args.workload, sample, max(1, args.steps), max(1, min(args.warmup, 1)), mt, kw, shared)
+        B = args.batch if args.batch is not None else def_batch          # the B200 arm's batch: same config
+        r = cpu_reference(cfg_id, B, max(1, args.steps), max(1, min(args.warmup, 1)))
         emit({
-            "impl": "reference", "metric": metric, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name, "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_step": sample, "device": "cpu"},
-            "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} tiles per step, {max(1, args.steps)} timed steps, oracle/unet_oracle.py on torch CPU fp32"},
-            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            "impl": "reference", "metric": metric_name(workload), "value": r["value"], "unit": "tiles/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(cfg_id, B, max(1, args.gpus)),
+            "device": "cpu",
+            "cpu_baseline": {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": f"{B} tiles per step, {max(1, args.steps)} timed steps (1 warm-up), {r['what']}, torch CPU fp32"},
+            "e2e": {"value": r["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
     import torch.distributed as dist
     import mau_b200
-    from mau_b200 import engine
+    from mau_b200 import engine, losses
     from oracle import unet_oracle as O   # synthetic inputs + CPU baseline leg only
 
     torch.cuda.set_device(local)
@@ -192,10 +248,10 @@ def main():
         opts.config.max_ctas = max(1, args.comm_ctas)
         opts.config.min_ctas = 1
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    pk = peaks()
 
-    def measure(cfg_id, steps, warmup, with_cpu_baseline):
+    def measure(cfg_id, steps, warmup, with_cpu_baseline, sustain_s=0.0, with_e2e=True):
         mt, kw, workload, def_batch, shared, workload_name = CONFIGS[cfg_id]
-        metric = "inference tiles/sec" if workload == "infer" else "training tiles/sec (fwd+bwd)"
         train = workload == "train"
         engine.lib().mau_set_sm_reserve(max(0, args.comm_ctas) if (train and world > 1) else 0)
         B = args.batch if args.batch is not None else def_batch
@@ -230,13 +286,17 @@ def main():
                 return model.forward_sweep(x, ts, md)
             return model(x, ts, md)
 
+        def criterion(out, tgt):
+            if args.criterion == "l1-gradient-ssim":              # the reference's default (conf/config.yaml:42, src/train.py:218-225)
+                return losses.compute_loss_l1_grad_ssim(out, tgt)["total"]
+            return engine.compute_loss_l1_grad(out, tgt, 0.0)["total"]      # L1 via the fused loss kernel
+
         def step(i, batch):
             x, ts, md, tgt = batch
             if not train:
                 with torch.no_grad():
                     return fwd(x, ts, md)
-            out = model(x, ts, md)
-            loss = engine.compute_loss_l1_grad(out, tgt, 0.0)["total"]      # L1 via the fused loss kernel
+            loss = criterion(model(x, ts, md), tgt)
             loss.backward()
             opt.step()                            # fused AdamW: inside the timed region
             opt.zero_grad(set_to_none=True)
@@ -247,166 +307,202 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
 
+        def reduce_max(ms):
+            t = torch.tensor([ms], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def timed(n, sampler=None):
+            barrier()
+            e0.record()
+            for i in range(n):
+                step(i, devb[i % nb])
+            if sampler is not None:
+                sampler.sample()          # the GPU is still executing the queued steps here
+            e1.record()
+            barrier()
+            return reduce_max(e0.elapsed_time(e1))
+
         for i in range(warmup):
             step(i, devb[i % nb])
         barrier()
         launches0 = engine.lib().mau_launch_count()
         sampler = ClockSampler(local)
         sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            step(i, devb[i % nb])
-        sampler.sample()          # the GPU is still executing the queued steps here
-        e1.record()
-        barrier()
+        ms = timed(steps, sampler)
         sampler.stop_flag = True
-        ms = e0.elapsed_time(e1)
         launches = engine.lib().mau_launch_count() - launches0
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         value = world * B * steps / (ms / 1e3)
+
+        plan = None
+        for p_ in model.model._plans.values():
+            if p_.cfg["training"] == int(train) and p_.cfg["batch"] == B:
+                plan = p_
+        fwd_flops, bwd_flops = plan.flops()              # dense reference graph (SURVEY.md 8d numerators)
+        exec_fwd, exec_bwd = plan.exec_flops()           # what the conv / dgrad / wgrad kernels execute per step
+        alg_flops_step = fwd_flops + (bwd_flops if train else 0.0)
+        kern_flops = exec_fwd + (exec_bwd if train else 0.0)
+
+        def kernel_pass(reps=3):
+            """CUDA events right around every conv / dgrad / wgrad launch (k: entries of mau_plan_profile)."""
+            plan.profile(True)
+            conv_ms, conv_n, all_ms = 0.0, 0, 0.0
+            for i in range(reps):
+                step(i, devb[i % nb])
+                torch.cuda.synchronize()
+                for name, t_ms in plan.profile_read():
+                    if name.startswith("k:"):
+                        conv_ms += t_ms
+                        conv_n += 1
+                    else:                            # per-op entries (a conv op also holds its BN / pack / memset launches)
+                        all_ms += t_ms
+                    if args.profile_layers and i == reps - 1 and rank == 0:
+                        print(f"{name:36s} {t_ms:8.3f} ms", file=sys.stderr)
+            plan.profile(False)
+            tf = kern_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+            return dict(tf=tf, launches=conv_n // reps, avg_us=conv_ms / max(conv_n, 1) * 1e3,
+                        flop_per_launch=kern_flops * reps / max(conv_n, 1), share=conv_ms / all_ms if all_ms else None)
+
+        burst = kernel_pass()            # cold chip, boost clocks: against the burst peak
+
+        # ---- sustained: the same step loop for >= sustain_s seconds, clocks and power sampled under that load; the
+        # kernel pass right after it (chip still at its sustained operating point) is the one held against the
+        # sustained peak
+        sustained, hot = None, None
+        if sustain_s > 0:
+            n_s = max(steps, int(sustain_s / (ms / steps / 1e3)) + 1)
+            s2 = ClockSampler(local)
+            s2.start()
+            ms_s = timed(n_s, s2)
+            s2.stop_flag = True
+            hot = kernel_pass()
+            tf_s = alg_flops_step * n_s / (ms_s / 1e3) / 1e12
+            sustained = {"seconds": ms_s / 1e3, "steps": n_s, "ms_per_step": ms_s / n_s, "value": world * B * n_s / (ms_s / 1e3),
+                         "unit": "tiles/s", "clocks": s2.summary(), "tflops_whole_step_per_gpu": tf_s,
+                         "whole_step_frac_of_sustained_peak": (tf_s / pk["tf_sustained"]) if not fp32_mode else None}
 
         # ---- end to end through the public nn.Module API with HOST buffers: every step's inputs are copied
         # from pinned host memory (H2D) and every step's result is read back to the host (D2H), all inside the
         # timed region.  Copies of step i+1 are prefetched on a side stream while step i computes (the
         # standard PyTorch prefetch idiom); results land in pinned host buffers.
-        copy_s = torch.cuda.Stream(device=dev)
-        main_s = torch.cuda.current_stream(dev)
-        out_host = [torch.empty((B, 2, TILE, TILE), pin_memory=True) for _ in range(3)] if not train else \
-                   [torch.empty((), pin_memory=True) for _ in range(3)]
+        e2e = None
+        if with_e2e:
+            copy_s = torch.cuda.Stream(device=dev)
+            main_s = torch.cuda.current_stream(dev)
+            out_host = [torch.empty((B, 2, TILE, TILE), pin_memory=True) for _ in range(3)] if not train else \
+                       [torch.empty((), pin_memory=True) for _ in range(3)]
 
-        def prefetch(i):
-            with torch.cuda.stream(copy_s):
-                tens = tuple(t_.to(dev, non_blocking=True) for t_ in pinned[i % nb])
-                ev = torch.cuda.Event()
-                ev.record(copy_s)
-            return tens, ev
+            def prefetch(i):
+                with torch.cuda.stream(copy_s):
+                    tens = tuple(t_.to(dev, non_blocking=True) for t_ in pinned[i % nb])
+                    ev = torch.cuda.Event()
+                    ev.record(copy_s)
+                return tens, ev
 
-        DEPTH = 3                      # input batches in flight ahead of the compute (keeps the H2D engine busy)
-        d2h_s = torch.cuda.Stream(device=dev)
+            DEPTH = 3                      # input batches in flight ahead of the compute (keeps the H2D engine busy)
+            d2h_s = torch.cuda.Stream(device=dev)
 
-        def e2e_run(n):
-            q = [prefetch(j) for j in range(min(DEPTH, n))]
-            done = []
-            for i in range(n):
-                (xd, td, mdd, tg), ev = q.pop(0)
-                if i + DEPTH < n:
-                    q.append(prefetch(i + DEPTH))
-                main_s.wait_event(ev)
-                for t_ in (xd, td, mdd, tg):
-                    t_.record_stream(main_s)
-                if not train:
-                    with torch.no_grad():
-                        res = fwd(xd, td, mdd)
-                else:
-                    out_ = model(xd, td, mdd)
-                    res = engine.compute_loss_l1_grad(out_, tg, 0.0)["total"]
-                    res.backward()
-                    opt.step()
-                    opt.zero_grad(set_to_none=True)
-                    res = res.detach()
-                ready = torch.cuda.Event()
-                ready.record(main_s)
-                with torch.cuda.stream(d2h_s):                         # D2H of the step's result off the compute stream
-                    d2h_s.wait_event(ready)
-                    res.record_stream(d2h_s)
-                    out_host[i % len(out_host)].copy_(res, non_blocking=True)
-                    e = torch.cuda.Event()
-                    e.record(d2h_s)
-                done.append(e)
-                if i >= 2:
-                    done[i - 2].synchronize()                          # the host has step i-2's result (ring of 3 buffers)
-            for e in done[-2:]:
-                e.synchronize()
+            def e2e_run(n):
+                q = [prefetch(j) for j in range(min(DEPTH, n))]
+                done = []
+                for i in range(n):
+                    (xd, td, mdd, tg), ev = q.pop(0)
+                    if i + DEPTH < n:
+                        q.append(prefetch(i + DEPTH))
+                    main_s.wait_event(ev)
+                    for t_ in (xd, td, mdd, tg):
+                        t_.record_stream(main_s)
+                    if not train:
+                        with torch.no_grad():
+                            res = fwd(xd, td, mdd)
+                    else:
+                        res = criterion(model(xd, td, mdd), tg)
+                        res.backward()
+                        opt.step()
+                        opt.zero_grad(set_to_none=True)
+                        res = res.detach()
+                    ready = torch.cuda.Event()
+                    ready.record(main_s)
+                    with torch.cuda.stream(d2h_s):                         # D2H of the step's result off the compute stream
+                        d2h_s.wait_event(ready)
+                        res.record_stream(d2h_s)
+                        out_host[i % len(out_host)].copy_(res, non_blocking=True)
+                        e = torch.cuda.Event()
+                        e.record(d2h_s)
+                    done.append(e)
+                    if i >= 2:
+                        done[i - 2].synchronize()                          # the host has step i-2's result (ring of 3 buffers)
+                for e in done[-2:]:
+                    e.synchronize()
 
-        e2e_run(2 * DEPTH + 3)        # warm-up: lets the caching allocator reach its steady-state pool (no cudaMalloc in the timed run)
-        barrier()
-        e0.record()
-        e2e_run(steps)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * B * steps / (float(t.item()) / 1e3)
-        x0, ts0, md0, tg0 = pinned[0]
-        h2d = sum(t_.numel() * 4 for t_ in ((x0, ts0, md0, tg0) if train else (x0, ts0, md0)))
-        d2h = 4 if train else B * 2 * TILE * TILE * 4
+            e2e_run(2 * DEPTH + 3)        # warm-up: lets the caching allocator reach its steady-state pool (no cudaMalloc in the timed run)
+            barrier()
+            e0.record()
+            e2e_run(steps)
+            e1.record()
+            barrier()
+            e2e_value = world * B * steps / (reduce_max(e0.elapsed_time(e1)) / 1e3)
+            x0, ts0, md0, tg0 = pinned[0]
+            h2d = sum(t_.numel() * 4 for t_ in ((x0, ts0, md0, tg0) if train else (x0, ts0, md0)))
+            d2h = 4 if train else B * 2 * TILE * TILE * 4
+            e2e = {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
-        # ---- roofline of the dominant kernel (3x3 conv on the tensor pipe): per-layer CUDA-event times
-        plan = next(iter(model.model._plans.values()))
-        for p_ in model.model._plans.values():
-            if p_.cfg["training"] == int(train) and p_.cfg["batch"] == B:
-                plan = p_
-        plan.profile(True)
-        conv_ms, conv_n, all_ms = 0.0, 0, 0.0
-        reps = 3
-        for i in range(reps):
-            step(i, devb[i % nb])
-            torch.cuda.synchronize()
-            for name, t_ms in plan.profile_read():
-                if name.startswith("k:"):        # CUDA events right around one conv / dgrad / wgrad kernel launch
-                    conv_ms += t_ms
-                    conv_n += 1
-                else:                            # per-op entries (a conv op also holds its BN / pack / memset launches)
-                    all_ms += t_ms
-                if args.profile_layers and i == reps - 1 and rank == 0:
-                    print(f"{name:36s} {t_ms:8.3f} ms", file=sys.stderr)
-        plan.profile(False)
-        fwd_flops, bwd_flops = plan.flops()              # dense reference graph (SURVEY.md 8d numerators)
-        exec_fwd, exec_bwd = plan.exec_flops()           # what the conv / dgrad / wgrad kernels execute per step
-        pk = peaks()
-        # kernel roofline: FLOPs the timed kernels executed / their summed launch durations.  Training backward =
-        # dgrad + wgrad of every conv (no dgrad for the first layer; the U-Net++ embedding planes' share is computed in
-        # closed form by other kernels and is not counted here).
-        kern_flops = exec_fwd + (exec_bwd if train else 0.0)
-        achieved_tf = kern_flops * reps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        # ---- roofline of the dominant kernel family (3x3 conv on the tensor pipe)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # from the committed ncu --set full captures
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(f"config{cfg_id}", {}).get("dram_bytes_per_launch")
-        peak_tf, peak_src, kname = pk["tf_sustained"], pk["src"], "conv3x3_tc_v2_kernel (+wgrad3x3_tc_v2_kernel in training)"
+        kname = "conv3x3_tc_* (+wgrad3x3_tc_* in training)"
         if fp32_mode:      # FFMA path: 148 SMs x 128 lanes x 2 FLOP x 1.965 GHz (nominal; no measured fp32 peak on file)
-            peak_tf, peak_src, kname = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA", "conv3x3_ffma_kernel"
-        roof = {"bound": "tensor" if not fp32_mode else "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                "kernel": kname,
-                "launches_timed": conv_n // reps, "avg_launch_us": conv_ms / max(conv_n, 1) * 1e3,
-                "flop_per_launch": kern_flops * reps / max(conv_n, 1),
-                "conv_share_of_step": conv_ms / all_ms if all_ms else None,
-                "algorithmic_gflop_per_tile": (fwd_flops + (bwd_flops if train else 0.0)) / B / 1e9}
+            fpk = 148 * 128 * 2 * 1.965e9 / 1e12
+            roof = {"bound": "fp32", "achieved": burst["tf"], "peak": fpk, "unit": "TFLOP/s", "frac": burst["tf"] / fpk,
+                    "traffic": traffic, "peak_source": "nominal fp32 FMA", "kernel": "conv3x3_ffma_kernel"}
+        else:
+            main_pass, peak, which = (hot, pk["tf_sustained"], "sustained") if hot is not None else (burst, pk["tf_burst"], "burst")
+            roof = {"bound": "tensor", "achieved": main_pass["tf"], "peak": peak, "unit": "TFLOP/s", "frac": main_pass["tf"] / peak,
+                    "traffic": traffic, "peak_source": f"{pk['src']} {which} cuBLAS bf16", "kernel": kname,
+                    "timed": f"CUDA events around each launch, 3 steps, {'right after the sustained loop' if hot is not None else 'cold chip'}",
+                    "burst": {"achieved": burst["tf"], "peak": pk["tf_burst"], "frac": burst["tf"] / pk["tf_burst"],
+                              "avg_launch_us": burst["avg_us"], "timed": "cold chip, boost clocks"}}
+            roof.update(launches_timed=main_pass["launches"], avg_launch_us=main_pass["avg_us"],
+                        flop_per_launch=main_pass["flop_per_launch"], conv_share_of_step=main_pass["share"])
+        roof["algorithmic_gflop_per_tile"] = alg_flops_step / B / 1e9
 
-        out = {"metric": metric, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": steps,
+        out = {"metric": metric_name(workload), "value": value, "unit": "tiles/s", "n_gpus": world, "steps": steps,
                "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32" if fp32_mode else "bf16", "data": "synthetic",
-               "config": {"workload": workload_name, "baseline_config": cfg_id, "tile": [23, TILE, TILE], "batch_per_gpu": B,
-                          "global_batch": B * world, "parallelism": f"dp{world}",
-                          "l2": "4 rotating input batches (368 MB) + ~2 GB of activations per step: working set > 126 MB L2"},
-               "clocks": sampler.summary(),
-               "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": int(launches), "roofline": roof,
-               "tflops_whole_step": (fwd_flops + (bwd_flops if train else 0)) / B * value / world / 1e12}
+               "config": config_block(cfg_id, B, world), "clocks": sampler.summary(), "e2e": e2e,
+               "gpu_launches": int(launches), "roofline": roof, "sustained": sustained,
+               "tflops_whole_step": alg_flops_step / B * value / world / 1e12}
+        if train:
+            out["criterion"] = args.criterion
         if rank == 0 and world == 1 and with_cpu_baseline:
-            sample = 4 if not train else 2
-            v, sec, threads = cpu_reference(workload, sample, 3, 1, mt, kw, shared)
-            out["cpu_baseline"] = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
-                                   "sample": f"{sample} tiles x 3 timed steps (1 warm-up), oracle/unet_oracle.py, torch CPU fp32"}
+            r = cpu_reference(cfg_id, B, 3, 1)
+            out["cpu_baseline"] = {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": r["kind"],
+                                   "sample": f"{B} tiles x 3 timed steps (1 warm-up), {r['what']}, torch CPU fp32"}
         elif rank == 0:
             out["cpu_baseline"] = None
         model.model.release_plans()
+        del model, opt, devb, pinned
+        torch.cuda.empty_cache()
         return out
 
     steps, warmup = args.steps, args.warmup
-    out = measure(cfg_id, steps, warmup, not args.no_cpu_baseline)
-    if default_invocation:
-        # BASELINE.json's metric names two numbers: the line's value is the inference one (configs[1]); the training
-        # number (configs[2]: fwd + L1 + bwd + fused AdamW, data-parallel when N > 1) rides along in "training"
-        tr = measure(3, max(5, steps // 2), 3, False)
-        out["training"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches",
-                                              "roofline", "clocks", "config")}
+    out = measure(cfg_id, steps, warmup, not args.no_cpu_baseline, sustain_s=args.sustain_s)
+    if default_invocation and not args.no_riders:
+        # BASELINE.json's metric names two numbers: the line is the training one (configs[2]); the inference number
+        # (configs[1]) rides along, and so do short runs of the other three configs so that the driver sees all five
+        keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "dtype", "e2e", "gpu_launches", "roofline", "clocks",
+                "config", "tflops_whole_step", "sustained")
+        inf = measure(2, steps, warmup, False, sustain_s=min(args.sustain_s, 1.0))
+        out["inference"] = {k: inf[k] for k in keep}
+        out["riders"] = {}
+        for cid in (1, 4, 5):
+            r = measure(cid, max(5, steps // 2), 3, False)
+            out["riders"][f"config{cid}"] = {k: r[k] for k in keep}
     if rank == 0:
         emit(out)
     if world > 1:

@@ -156,6 +156,15 @@ int mau_loss_forward_backward(int kind, const float* pred_dev, const float* targ
                               int H, int W, float lambda_grad, float* losses_dev, float* grad_dev,
                               void* stream);
 
+/* backward of the same terms for autograd (src/train.py:252 `batch_loss.backward()` reaches the criterion first):
+ * grad_dev = d(g_total*total + g_pixel*pixel + g_gradient*gradient)/d pred with total = pixel + lambda_total*gradient.
+ * The g_*_dev are nullable DEVICE scalars (the upstream gradients of the three dictionary entries), read by the kernel:
+ * no host synchronisation, no separate scaling pass.  All three entries of the reference's dictionaries stay
+ * differentiable this way (src/utils/losses.py:5-25 `gradient_loss` included). */
+int mau_loss_backward(int kind, const float* pred_dev, const float* target_dev, int B, int C, int H, int W,
+                      float lambda_total, const float* g_total_dev, const float* g_pixel_dev,
+                      const float* g_gradient_dev, float* grad_dev, void* stream);
+
 /* --- optimizer step: replaces torch.optim.AdamW(...).step() (src/train.py:213-214,255) -------
  * One launch updates all n_tensors parameter tensors (fp32, contiguous) in place with decoupled weight
  * decay; exp_avg / exp_avg_sq are the optimizer's state tensors (same layout as torch's, so

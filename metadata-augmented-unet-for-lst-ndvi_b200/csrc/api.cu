@@ -158,6 +158,14 @@ int mau_loss_forward_backward(int kind, const float* pred_dev, const float* targ
                  static_cast<cudaStream_t>(stream));
 }
 
+int mau_loss_backward(int kind, const float* pred_dev, const float* target_dev, int B, int C, int H, int W,
+                      float lambda_total, const float* g_total_dev, const float* g_pixel_dev, const float* g_grad_dev,
+                      float* grad_dev, void* stream) {
+  if (!pred_dev || !target_dev || !grad_dev) return fail("loss backward: null argument");
+  return op_loss_backward(kind, pred_dev, target_dev, B, C, H, W, lambda_total, g_total_dev, g_pixel_dev, g_grad_dev, grad_dev,
+                          static_cast<cudaStream_t>(stream));
+}
+
 int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred_dev, const float* target_dev, int B,
                      int C, int H, int W, float temp_mean, float temp_std, int64_t* dw_map_dev, double* sums_dev,
                      void* stream) {

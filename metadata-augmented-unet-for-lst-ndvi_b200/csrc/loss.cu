@@ -18,10 +18,21 @@ namespace {
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
 
 // partials: [gridDim.x][3] doubles
+// grad[i] = wp * d pixel / d p_i + wg * d gradient / d p_i with wp = wp_h + [*g_total] + [*g_pixel] and
+// wg = wg_h + [*g_total] * lambda_total + [*g_grad]: the device scalars are the upstream gradients autograd hands to the
+// backward of {total, pixel, gradient} (total = pixel + lambda_total * gradient), folded in here instead of a separate
+// element-wise multiply.  partials may be null (backward-only launch).
 __global__ void __launch_bounds__(256) loss_kernel(int kind, const float* __restrict__ p, const float* __restrict__ t,
                                                    int planes, int H, int W, float inv_n, float inv_ny, float inv_nx,
-                                                   float lambda, double* __restrict__ partials,
+                                                   float wp_h, float wg_h, float lambda_total,
+                                                   const float* __restrict__ g_total, const float* __restrict__ g_pixel,
+                                                   const float* __restrict__ g_grad, double* __restrict__ partials,
                                                    float* __restrict__ grad) {
+  float wp = wp_h, lambda = wg_h;
+  if (g_total) { const float g = *g_total; wp += g; lambda += g * lambda_total; }
+  if (g_pixel) wp += *g_pixel;
+  if (g_grad) lambda += *g_grad;
+  inv_n *= wp;        // only the gradient uses inv_n / lambda below; the sums are normalised by loss_finalize_kernel
   // fp32 partial sums per thread (a thread sees at most a few hundred elements), fp64 only across threads:
   // B200 issues FP64 adds at a small fraction of the FP32 rate and this loop was bound by them
   float f_pix = 0.f, f_dy = 0.f, f_dx = 0.f;
@@ -58,6 +69,7 @@ __global__ void __launch_bounds__(256) loss_kernel(int kind, const float* __rest
     }
     if (grad) grad[i] = g;
   }
+  if (!partials) return;
   __shared__ double red[3][8];
   double s_pix = (double)f_pix, s_dy = (double)f_dy, s_dx = (double)f_dx;
   s_pix = warp_sum(s_pix); s_dy = warp_sum(s_dy); s_dx = warp_sum(s_dx);
@@ -118,10 +130,24 @@ int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, 
   double* partials = loss_scratch(st);
   if (!partials) return fail("loss: scratch allocation failed");
   loss_kernel<<<blocks, 256, 0, st>>>(kind, pred, tgt, B * C, H, W, 1.f / (float)n, 1.f / (float)ny, 1.f / (float)nx,
-                                      lambda_grad, partials, grad);
+                                      1.f, lambda_grad, 0.f, nullptr, nullptr, nullptr, partials, grad);
   MAU_LAUNCHED();
   loss_finalize_kernel<<<1, 256, 0, st>>>(partials, blocks, 1.0 / (double)n, 1.0 / (double)ny, 1.0 / (double)nx,
                                           lambda_grad, losses);
+  MAU_LAUNCHED();
+  return 0;
+}
+
+int op_loss_backward(int kind, const float* pred, const float* tgt, int B, int C, int H, int W, float lambda_total,
+                     const float* g_total, const float* g_pixel, const float* g_grad, float* grad, cudaStream_t st) {
+  if (kind != 0 && kind != 1) return fail("loss: kind must be 0 (L1) or 1 (MSE)");
+  if (!grad) return fail("loss backward: null gradient");
+  const long long n = (long long)B * C * H * W;
+  const long long ny = (long long)B * C * (H - 1) * W, nx = (long long)B * C * H * (W - 1);
+  if (n <= 0 || ny <= 0 || nx <= 0) return fail("loss: empty tensor");
+  const int blocks = (int)std::min<long long>((long long)B * C * H, kMaxLossBlocks);
+  loss_kernel<<<blocks, 256, 0, st>>>(kind, pred, tgt, B * C, H, W, 1.f / (float)n, 1.f / (float)ny, 1.f / (float)nx,
+                                      0.f, 0.f, lambda_total, g_total, g_pixel, g_grad, nullptr, grad);
   MAU_LAUNCHED();
   return 0;
 }

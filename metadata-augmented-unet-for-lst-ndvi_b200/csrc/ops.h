@@ -111,6 +111,10 @@ int op_linear_bwd(const float* x, int B, int K, const float* w, int N, const flo
 // ---- loss / metrics -----------------------------------------------------------------------------
 int op_loss(int kind, const float* pred, const float* tgt, int B, int C, int H, int W, float lambda_grad,
             float* losses, float* grad, cudaStream_t st);
+// d(g_total*total + g_pixel*pixel + g_grad*gradient)/d pred with total = pixel + lambda_total*gradient; the g_* are
+// nullable DEVICE scalars (autograd's upstream gradients), so no host synchronisation and no separate scaling pass
+int op_loss_backward(int kind, const float* pred, const float* tgt, int B, int C, int H, int W, float lambda_total,
+                     const float* g_total, const float* g_pixel, const float* g_grad, float* grad, cudaStream_t st);
 int op_eval_metrics(const float* maps, int maps_c, const float* pred, const float* tgt, int B, int C, int H, int W,
                     float temp_mean, float temp_std, long long* dw_map, double* sums, cudaStream_t st);
 // per (sample, channel): {sum, sum of squares} of scipy.ndimage.laplace for pred and tgt -> out [B*C][4] (test/evaluate.py:241-242)

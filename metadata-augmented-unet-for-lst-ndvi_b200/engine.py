@@ -48,7 +48,7 @@ EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
     "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
-    "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss",
+    "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_loss_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss",
     "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
@@ -91,6 +91,8 @@ def lib():
                                             C.c_int, C.POINTER(C.c_int)]
         L.mau_loss_forward_backward.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                 C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mau_loss_backward.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mau_eval_metrics.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
@@ -457,30 +459,52 @@ def loss_terms(pred: torch.Tensor, target: torch.Tensor, kind: str = "l1", lambd
     return losses, grad
 
 
+def loss_backward_terms(pred, target, kind, lambda_total, g_total=None, g_pixel=None, g_grad=None) -> torch.Tensor:
+    """d(g_total*total + g_pixel*pixel + g_grad*gradient)/d pred (total = pixel + lambda_total*gradient); the g_* are 0-d
+    device tensors or None.  One launch of ``loss_kernel`` (csrc/loss.cu) with the scalars read on the device."""
+    pred, target = _dev_f32(pred, "pred"), _dev_f32(target, "target", pred)
+    B, Cc, H, W = pred.shape
+    grad = torch.empty_like(pred)
+    gs = [None if g is None else _dev_f32(g, "upstream gradient", pred) for g in (g_total, g_pixel, g_grad)]
+    with torch.cuda.device(pred.device):
+        check(lib().mau_loss_backward({"l1": 0, "mse": 1}[kind], pred.data_ptr(), target.data_ptr(), B, Cc, H, W,
+                                      float(lambda_total), *[None if g is None else g.data_ptr() for g in gs],
+                                      grad.data_ptr(), _stream_ptr()), "loss_backward")
+    return grad
+
+
 class _LossFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, pred, target, kind, lambda_grad):
-        losses, grad = loss_terms(pred.contiguous(), target.contiguous(), kind, lambda_grad, True)
-        ctx.save_for_backward(grad)
-        return losses
+    """(total, pixel, gradient) of src/utils/losses.py, each a differentiable 0-d tensor.  Forward: one pass for the three
+    sums.  Backward: one pass that folds autograd's upstream scalars (device-side, no host sync, no separate scaling
+    kernel) into d/d pred; entries nobody back-propagates through cost nothing (their upstream gradient arrives as None)."""
 
     @staticmethod
-    def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        return grad * g[0], None, None, None      # d total / d pred
+    def forward(ctx, pred, target, kind, lambda_grad):
+        pred_c, target_c = pred.contiguous(), target.contiguous()
+        losses, _ = loss_terms(pred_c, target_c, kind, lambda_grad, need_grad=False)
+        ctx.set_materialize_grads(False)
+        ctx.kind, ctx.lambda_grad = kind, float(lambda_grad)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(pred_c, target_c)
+        return losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, g_total, g_pixel, g_grad):
+        pred, target = ctx.saved_tensors
+        return loss_backward_terms(pred, target, ctx.kind, ctx.lambda_grad, g_total, g_pixel, g_grad), None, None, None
 
 
 def compute_loss_l1_grad(outputs, targets, lambda_grad=0.1):
     """{'total','pixel','gradient'} like the L1+gradient part of the reference's
-    compute_loss_l1_grad_ssim (src/utils/losses.py:59-99); 'total' carries the gradient."""
-    l = _LossFn.apply(outputs, targets, "l1", lambda_grad)
-    return {"total": l[0], "pixel": l[1].detach(), "gradient": l[2].detach()}
+    compute_loss_l1_grad_ssim (src/utils/losses.py:59-99); every entry is differentiable."""
+    total, pixel, grad = _LossFn.apply(outputs, targets, "l1", lambda_grad)
+    return {"total": total, "pixel": pixel, "gradient": grad}
 
 
 def compute_loss_mse_gradient(outputs, targets, lambda_grad=0.1):
     """src/utils/losses.py:41-57."""
-    l = _LossFn.apply(outputs, targets, "mse", lambda_grad)
-    return {"total": l[0], "mse": l[1].detach(), "gradient": l[2].detach()}
+    total, mse, grad = _LossFn.apply(outputs, targets, "mse", lambda_grad)
+    return {"total": total, "mse": mse, "gradient": grad}
 
 
 def eval_metrics(maps: torch.Tensor, pred: torch.Tensor, target: torch.Tensor,

@@ -1,5 +1,6 @@
 """Host-side mirror of the reference's ``src/utils/losses.py`` on the device kernels of the hot path: same function
-names, arguments and dictionary keys, every value a 0-d CUDA tensor, ``'total'`` differentiable w.r.t. ``outputs``.
+names, arguments and dictionary keys, every value a 0-d CUDA tensor, every entry differentiable w.r.t. ``outputs`` like
+the reference's (a caller may recombine components with its own weights).
 
 * pixel (L1 / MSE) and gradient-difference terms: ``loss_kernel`` (csrc/loss.cu), one pass forward + backward.
 * SSIM term: ``ssim_*_kernel`` (csrc/ssim.cu).  The reference calls ``piq.ssim`` (src/utils/losses.py:3,88), a
@@ -21,16 +22,15 @@ from . import engine
 
 
 def gradient_loss(pred: torch.Tensor, target: torch.Tensor) -> Dict[str, torch.Tensor]:
-    """src/utils/losses.py:5-25.  Value only (detached): the differentiable form is part of the combined losses below,
-    which is the only way the reference's training loop uses it."""
-    losses, _ = engine.loss_terms(pred.detach(), target.detach(), "l1", 0.0, need_grad=False)
-    return {"gradient": losses[2]}
+    """src/utils/losses.py:5-25 (differentiable w.r.t. ``pred``)."""
+    _, _, g = engine._LossFn.apply(pred, target, "l1", 0.0)
+    return {"gradient": g}
 
 
 def compute_loss_mse(outputs: torch.Tensor, targets: torch.Tensor) -> Dict[str, torch.Tensor]:
     """src/utils/losses.py:27-39."""
-    l = engine._LossFn.apply(outputs, targets, "mse", 0.0)
-    return {"total": l[0], "mse": l[1].detach()}
+    _, mse, _ = engine._LossFn.apply(outputs, targets, "mse", 0.0)
+    return {"total": mse, "mse": mse}
 
 
 def compute_loss_mse_gradient(outputs, targets, lambda_grad: float = 0.1) -> Dict[str, torch.Tensor]:
@@ -42,7 +42,7 @@ def compute_loss_l1_grad_ssim(outputs, targets, lambda_grad: float = 0.1, lambda
     """src/utils/losses.py:59-99: L1 + lambda_grad * gradient + lambda_ssim * (1 - mean SSIM)."""
     d = engine.compute_loss_l1_grad(outputs, targets, lambda_grad)
     ssim = engine.ssim_loss(outputs, targets)
-    return {"total": d["total"] + lambda_ssim * ssim, "pixel": d["pixel"], "gradient": d["gradient"], "ssim": ssim.detach()}
+    return {"total": d["total"] + lambda_ssim * ssim, "pixel": d["pixel"], "gradient": d["gradient"], "ssim": ssim}
 
 
 def compute_all_loss(outputs, targets, lambda_grad: float = 0.1, lambda_ssim: float = 0.5) -> Dict[str, torch.Tensor]:

@@ -46,8 +46,22 @@ def torch_loss_terms(pred, target, kind="l1", lambda_grad=0.1, need_grad=True):
     return torch.stack([tot.detach(), pix.detach(), (dy + dx).detach(), torch.zeros(())]), x.grad
 
 
+def torch_loss_backward_terms(pred, target, kind, lambda_total, g_total=None, g_pixel=None, g_grad=None):
+    with torch.enable_grad():
+        x = pred.detach().clone().requires_grad_(True)
+        pix = F.l1_loss(x, target) if kind == "l1" else F.mse_loss(x, target)
+        dy = ((x[:, :, 1:] - x[:, :, :-1]).abs() - (target[:, :, 1:] - target[:, :, :-1]).abs()).abs().mean()
+        dx = ((x[:, :, :, 1:] - x[:, :, :, :-1]).abs() - (target[:, :, :, 1:] - target[:, :, :, :-1]).abs()).abs().mean()
+        tot = pix + lambda_total * (dy + dx)
+        z = torch.zeros(())
+        ((g_total if g_total is not None else z) * tot + (g_pixel if g_pixel is not None else z) * pix
+         + (g_grad if g_grad is not None else z) * (dy + dx)).backward()
+    return x.grad
+
+
 engine.ssim_loss_terms = emulated_ssim_terms
 engine.loss_terms = torch_loss_terms
+engine.loss_backward_terms = torch_loss_backward_terms
 src = open(os.path.join(ROOT, "tools", "ssim_gpu_check.py")).read()
 assert "(16, 2, 250, 250)" in src
 exec(compile(src.replace("(16, 2, 250, 250)", "(1, 2, 40, 60)"), "ssim_gpu_check.py", "exec"))      # emulated blocks are real threads: keep it small
