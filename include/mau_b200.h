@@ -63,6 +63,9 @@ typedef struct mau_config {
 #define MAU_FLAG_HALO_BASEOFF  256 /* debug: halo main loop fills the UMMA descriptor base_offset   */
 #define MAU_FLAG_CONV_ROW3     512 /* debug: three-row-box conv main loop instead of the halo kernel */
 #define MAU_FLAG_WGRAD_V1      1024 /* debug: first-generation weight-gradient kernel (fp32 atomics)   */
+#define MAU_FLAG_BN_FUSED      4096 /* A-B: training BatchNorm as ONE cooperative launch per direction (statistics, grid barrier,
+                                      apply over the same block ranges in reverse).  Measured slower than the two plain launches
+                                      (8.41 vs 8.16 ms per training step, profiles/r02_bn_fused_ab.md): off by default */
 #define MAU_FLAG_EMB_DENSE_BWD 2048 /* debug: U-Net++ embedding planes back-propagated densely (dgrad + wgrad launches) */
 
 typedef struct mau_plan mau_plan; /* opaque */
@@ -173,6 +176,11 @@ int mau_loss_backward(int kind, const float* pred_dev, const float* target_dev, 
 int mau_adamw_step(int n_tensors, void* const* params_dev, void* const* grads_dev, void* const* exp_avg_dev,
                    void* const* exp_avg_sq_dev, const int64_t* numels, double lr, double beta1, double beta2,
                    double eps, double weight_decay, int64_t step, void* stream);
+
+/* fp32 gradient bucket <-> bf16 wire buffer of the data-parallel gradient all-reduce (new capability):
+ * halves the NVLink payload; max_blocks bounds the CTAs of the cast next to the backward kernels it overlaps (0 = default) */
+int mau_cast_f32_bf16(const float* src_dev, void* dst_bf16_dev, int64_t n, int max_blocks, void* stream);
+int mau_cast_bf16_f32(const void* src_bf16_dev, float* dst_dev, int64_t n, int max_blocks, void* stream);
 
 /* --- evaluation metrics: replaces the NumPy loop of test/evaluate.py:210-275 ---------------
  * dw_map_dev [B,H,W] int64 = argmax_c(maps[b,c]*c, c<9) (ties -> lowest index, bit-exact);

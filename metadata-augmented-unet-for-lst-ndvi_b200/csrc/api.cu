@@ -199,6 +199,15 @@ int mau_adamw_step(int n_tensors, void* const* params_dev, void* const* grads_de
                        static_cast<cudaStream_t>(stream));
 }
 
+int mau_cast_f32_bf16(const float* src_dev, void* dst_bf16_dev, int64_t n, int max_blocks, void* stream) {
+  if (!src_dev || !dst_bf16_dev) return fail("cast: null argument");
+  return op_cast_f32_bf16(src_dev, dst_bf16_dev, (long long)n, max_blocks, static_cast<cudaStream_t>(stream));
+}
+int mau_cast_bf16_f32(const void* src_bf16_dev, float* dst_dev, int64_t n, int max_blocks, void* stream) {
+  if (!src_bf16_dev || !dst_dev) return fail("cast: null argument");
+  return op_cast_bf16_f32(src_bf16_dev, dst_dev, (long long)n, max_blocks, static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------- single operators (parity tests)
 static View mkview(const void* p, int B, int H, int W, int C, int cs) {
   View v; v.ptr = const_cast<void*>(p); v.B = B; v.H = H; v.W = W; v.C = C; v.cs = cs; v.c0 = 0;

@@ -69,7 +69,54 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
 
 struct Scratch { void* dev = nullptr; size_t bytes = 0; };
 
+// gradient bucket <-> bf16 wire format of the data-parallel all-reduce (parallel.py, grad_dtype="bf16")
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) | (reinterpret_cast<uintptr_t>(dst) & 7)) == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (vec) {
+    for (long long i = t0; i < n4; i += stride) {
+      const float4 v = reinterpret_cast<const float4*>(src)[i];
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      reinterpret_cast<uint2*>(dst)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+    for (long long i = (n4 << 2) + t0; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+  } else {
+    for (long long i = t0; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) | (reinterpret_cast<uintptr_t>(src) & 7)) == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (vec) {
+    for (long long i = t0; i < n4; i += stride) {
+      const uint2 u = reinterpret_cast<const uint2*>(src)[i];
+      reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                                                      __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    }
+    for (long long i = (n4 << 2) + t0; i < n; i += stride) dst[i] = __bfloat162float(src[i]);
+  } else {
+    for (long long i = t0; i < n; i += stride) dst[i] = __bfloat162float(src[i]);
+  }
+}
+
 }  // namespace
+
+int op_cast_f32_bf16(const float* src, void* dst_bf16, long long n, int max_blocks, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int blocks = (int)std::min<long long>((n / 4 + 255) / 256 + 1, max_blocks > 0 ? max_blocks : 148 * 4);
+  cast_f32_bf16_kernel<<<blocks, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst_bf16), n);
+  MAU_LAUNCHED();
+  return 0;
+}
+int op_cast_bf16_f32(const void* src_bf16, float* dst, long long n, int max_blocks, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int blocks = (int)std::min<long long>((n / 4 + 255) / 256 + 1, max_blocks > 0 ? max_blocks : 148 * 4);
+  cast_bf16_f32_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src_bf16), dst, n);
+  MAU_LAUNCHED();
+  return 0;
+}
 
 int op_adamw_step(int n_tensors, void* const* params, void* const* grads, void* const* exp_avg,
                   void* const* exp_avg_sq, const long long* numels, double lr, double beta1, double beta2, double eps,

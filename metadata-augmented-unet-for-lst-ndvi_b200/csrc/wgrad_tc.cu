@@ -383,6 +383,213 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_tc_v2_kernel(const __gri
   }
 }
 
+
+// ==========================================================================================
+// v3 ("pair"): layers whose narrow side has <= 64 channels (every convolution at 250x250: Cout = 64; conv1_0.conv1:
+// Cin = 64).  The v2 kernel puts that side on a 128-row M tile of which half is padding (452 TFLOP/s on the 64 -> 64
+// layers).  Here the narrow side carries the filter-tap shift and TWO taps share one MMA: the M = 128 rows are
+// [64 channels of tap u | 64 channels of tap u+1].  Both operands are MN-major, so the second 64-row group of the A
+// operand is simply "the same halo box, LBO bytes further": LBO = 128 B (next pixel) for horizontally adjacent taps,
+// 2048 B for the (row end, next row start) pair.  Nine taps = five accumulators (the last one half used) instead of
+// nine, one work unit covers all three filter rows (one {64, 18, 6} halo box per 16 x 4 pixel tile instead of three
+// {64, 18, 4} boxes), and the other operand can be up to 96 channels wide (5 x 96 = 480 TMEM columns).
+//   shifted operand S = dY (PAIR_DY: Cout <= 64, window u at ((u/3) * 18 + u % 3) pixels, tap = 8 - u) or
+//                       X  (PAIR_X:  Cin  <= 64, same windows, tap = u);  the other operand O is the plain tile box.
+//   dW[co][ci][tap] = sum_q dY[q - d(tap)][co] * X[q][ci] = sum_p dY[p][co] * X[p + d(tap)][ci]
+// Epilogue: accumulator j holds rows [tap a | tap b]; each half is TMA-reduce-added (box {32, 64}) into the fp32
+// workspace [9][narrow side][wide side], which wgrad_finalize_kernel transposes into OIHW.
+// ==========================================================================================
+constexpr int kPairHalo = 14336;       // {64, 18, 6} bf16 = 13824 B, padded to a multiple of 1024
+constexpr int kPairOBox = 8192;        // {64, 16, 4} bf16
+
+struct WgradPairParams {
+  int tiles_w, tiles_h, T;   // 16 x 4 pixel tiles
+  int n_tiles;               // units (BN-wide tiles of the wide side)
+  long long atoms;           // n_tiles * T
+  int ws_n0;                 // workspace column of this segment's first wide-side channel
+  int ws_m0;                 // workspace row of this segment's first narrow-side channel
+  int tap_reversed;          // 1: window u is tap 8 - u (dY carries the shift)
+};
+
+template <int BN, int STAGES>
+struct WgradPairSmem {
+  static constexpr int NO = BN <= 64 ? 1 : 2;
+  static constexpr int kStage = kPairHalo + NO * kPairOBox;
+  static constexpr size_t kBytes = 1024 + (size_t)STAGES * kStage + 2 * kStgTile + 8 * (2 * STAGES + 2) + 16;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) wgrad3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmS,
+                                                                      const __grid_constant__ CUtensorMap tmO,
+                                                                      const __grid_constant__ CUtensorMap tmWs,
+                                                                      const WgradPairParams p) {
+  using S = WgradPairSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sStg = smem + STAGES * S::kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * kStgTile);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long a0 = (long long)blockIdx.x * p.atoms / gridDim.x;
+  const long long a1 = (long long)(blockIdx.x + 1) * p.atoms / gridDim.x;
+  const int tiles_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmS); prefetch_tensormap(&tmO); prefetch_tensormap(&tmWs);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    int stage = 0; uint32_t phase = 0;
+    for (long long a = a0; a < a1;) {
+      const int u = (int)(a / p.T);
+      const int t0 = (int)(a - (long long)u * p.T);
+      const int t1 = (int)min((long long)p.T, (long long)t0 + (a1 - a));
+      const int n0 = u * BN;
+      for (int t = t0; t < t1; ++t) {
+        const int b = t / tiles_img;
+        const int rem = t - b * tiles_img;
+        const int th = rem / p.tiles_w;
+        const int h0 = th * 4, w0 = (rem - th * p.tiles_w) * 16;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], 13824 + S::NO * kPairOBox);
+          uint8_t* s = smem + stage * S::kStage;
+          tma_load_4d(s, &tmS, &full[stage], 0, w0 - 1, h0 - 1, b);
+#pragma unroll
+          for (int j = 0; j < S::NO; ++j) tma_load_4d(s + kPairHalo + j * kPairOBox, &tmO, &full[stage], n0 + 64 * j, w0, h0, b);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      a += t1 - t0;
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = idesc_bf16_f32(128, BN, 1, 1);
+    // A = shifted operand: two 64-channel M groups LBO apart (the tap pair), 8-pixel K groups at SBO = 1024 B
+    const uint64_t descA_near = smem_desc_sw128(0, 128, 1024, 0);      // pair = horizontally adjacent windows
+    const uint64_t descA_wrap = smem_desc_sw128(0, 2048, 1024, 0);     // pair = (row end, next row start): 16 pixels apart
+    const uint64_t descB0 = smem_desc_sw128(0, kPairOBox, 1024, 0);
+    int stage = 0; uint32_t phase = 0, ephase = 0;
+    for (long long a = a0; a < a1;) {
+      const int u = (int)(a / p.T);
+      const int t0 = (int)(a - (long long)u * p.T);
+      const int t1 = (int)min((long long)p.T, (long long)t0 + (a1 - a));
+      mbar_wait(tmem_empty, ephase ^ 1);
+      ephase ^= 1;
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * S::kStage);
+        const uint32_t first = t > t0 ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int w = 2 * j;                                         // first window of the pair
+            const uint32_t woff = ((w / 3) * 18 + (w % 3)) * 128;
+            const uint64_t dA = (j == 1 ? descA_wrap : descA_near) + (uint64_t)((sa + woff) >> 4);
+            const uint64_t dB = descB0 + (uint64_t)((sa + kPairHalo) >> 4);
+#pragma unroll
+            for (int h = 0; h < 4; ++h)      // one tile row (16 pixels = K) per instruction
+              umma_bf16(tmem_base + j * BN, dA + (uint64_t)((h * 18 * 128) >> 4), dB + (uint64_t)((h * 2048) >> 4), idesc,
+                        h ? 1u : first);
+          }
+          umma_commit(&empty[stage]);
+          if (t == t1 - 1) umma_commit(tmem_full);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      a += t1 - t0;
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t fphase = 0;
+    int sb = 0;
+    for (long long a = a0; a < a1;) {
+      const int u = (int)(a / p.T);
+      const int t0 = (int)(a - (long long)u * p.T);
+      const int t1 = (int)min((long long)p.T, (long long)t0 + (a1 - a));
+      mbar_wait(tmem_full, fphase);
+      fphase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 5; ++j) {
+#pragma unroll 1
+        for (int part = 0; part < BN / 32; ++part) {
+          uint8_t* stg = sStg + sb * kStgTile;
+          const bool last = j == 4 && part == BN / 32 - 1;
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          named_bar_sync(1, 128);
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * BN + part * 32, v);
+          tmem_ld_wait();
+          uint8_t* rowp = stg + row * 128;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(rowp + ((k ^ (row & 7)) << 4)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          if (last) tc_fence_before();
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            if (last) mbar_arrive(tmem_empty);
+            const int wa = 2 * j, wb = 2 * j + 1;
+            const int col = p.ws_n0 + u * BN + part * 32;
+            tma_reduce_add_3d(&tmWs, stg, col, p.ws_m0, p.tap_reversed ? 8 - wa : wa);
+            if (wb < 9) tma_reduce_add_3d(&tmWs, stg + 8192, col, p.ws_m0, p.tap_reversed ? 8 - wb : wb);
+            tma_commit_group();
+          }
+          sb ^= 1;
+        }
+      }
+      a += t1 - t0;
+    }
+    if (et == 0) tma_wait_group0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BN, int STAGES>
+int launch_wgrad_pair(const WgradTcOp& op, const WgradPairParams& p, cudaStream_t st) {
+  using S = WgradPairSmem<BN, STAGES>;
+  static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = wgrad3x3_tc_pair_kernel<BN, STAGES>;
+  if (!attr_done[dev & 15]) {
+    MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    attr_done[dev & 15] = true;
+  }
+  kern<<<op.grid, kThreads, S::kBytes, st>>>(op.tmDy, op.tmX, op.tmWs, p);
+  MAU_LAUNCHED();
+  return 0;
+}
+
 // workspace [9][D1][ld0] -> OIHW.  normal: D1 = Cout, inner = ci; swapped: D1 = Cin, inner = co.
 // A block owns 256 consecutive (co, ci) pairs of the OIHW tensor: nine coalesced plane reads into shared memory,
 // then one contiguous 256 x 9 float run written out (the direct version wrote 36-byte pieces per thread).

@@ -11,6 +11,7 @@ import ctypes as C
 import json
 import os
 import threading
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -49,7 +50,7 @@ EXPORTS = (
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
     "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
     "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_loss_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss",
-    "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_op_maxpool2x2", "mau_op_bilinear",
+    "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_cast_f32_bf16", "mau_cast_bf16_f32", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
 
@@ -119,6 +120,8 @@ def lib():
         L.mau_adamw_step.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_int64, C.c_void_p]
+        L.mau_cast_f32_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.mau_cast_bf16_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         L.mau_op_bw_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p]
         L.mau_op_maxpool2x2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -239,7 +242,7 @@ class Plan:
     @property
     def pending(self) -> bool:
         """True while an autograd graph still needs this plan's saved activations."""
-        return self._pending is not None
+        return self._pending is not None and self._pending() is not None
 
     @property
     def workspace_bytes(self) -> int:
@@ -373,10 +376,10 @@ class _PendingToken:
 
     def __init__(self, plan: "Plan"):
         self.plan = plan
-        plan._pending = self
+        plan._pending = weakref.ref(self)      # weak: the graph (ctx) is the only owner, so dropping the graph frees the plan
 
     def release(self):
-        if self.plan is not None and self.plan._pending is self:
+        if self.plan is not None and self.plan._pending is not None and self.plan._pending() is self:
             self.plan._pending = None
         self.plan = None
 
@@ -408,7 +411,7 @@ class HotPathFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         plan: Plan = ctx.plan
-        if plan._pending is not ctx.token:
+        if plan._pending is None or plan._pending() is not ctx.token:
             raise RuntimeError("mau_b200: backward() called twice on the same graph, or the plan's saved activations were "
                                "released (a plan keeps the activations of exactly one forward)")
         grad_out = grad_out.contiguous().float()

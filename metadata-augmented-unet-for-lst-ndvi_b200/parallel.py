@@ -28,8 +28,13 @@ class GradReducer:
     ``ready(a, b)`` marks elements [a, b) final; ranges are merged while contiguous and flushed
     once ``bucket_numel`` elements are pending; ``finish()`` flushes the rest and waits."""
 
-    def __init__(self, flat: torch.Tensor, group=None, bucket_numel: int = 1 << 20):
+    def __init__(self, flat: torch.Tensor, group=None, bucket_numel: int = 1 << 20, grad_dtype: str = "fp32"):
+        if grad_dtype not in ("fp32", "bf16"):
+            raise ValueError("grad_dtype must be 'fp32' or 'bf16'")
         self.flat, self.group, self.bucket_numel = flat, group, bucket_numel
+        # bf16 wire format: the bucket is rounded to bf16, averaged in bf16 by the collective and widened back; halves
+        # the NVLink payload and the time the collective's CTAs compete with the backward kernels (fp32 = exact average)
+        self.wire = torch.empty(flat.numel(), dtype=torch.bfloat16, device=flat.device) if grad_dtype == "bf16" else None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.pending: List[Tuple[int, int]] = []
         self.cuda = flat.is_cuda
@@ -47,10 +52,24 @@ class GradReducer:
             ev.record(torch.cuda.current_stream(self.flat.device))
             self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group)
-        else:
+                if self.wire is None:
+                    dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group)
+                else:
+                    w = self.wire[a:b]
+                    st = torch.cuda.current_stream(self.flat.device).cuda_stream
+                    with torch.cuda.device(self.flat.device):
+                        engine.check(engine.lib().mau_cast_f32_bf16(sl.data_ptr(), w.data_ptr(), b - a, 16, st), "cast")
+                        dist.all_reduce(w, op=dist.ReduceOp.AVG, group=self.group)
+                        engine.check(engine.lib().mau_cast_bf16_f32(w.data_ptr(), sl.data_ptr(), b - a, 16, st), "cast")
+        elif self.wire is None:
             dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group)
             sl.div_(self.world)
+        else:                    # host / gloo path of the unit tests: same rounding points with torch ops
+            w = self.wire[a:b]
+            w.copy_(sl)
+            w32 = w.float()
+            dist.all_reduce(w32, op=dist.ReduceOp.SUM, group=self.group)
+            sl.copy_((w32 / self.world).to(torch.bfloat16))
 
     def ready(self, a: int, b: int):
         if self.pending and self.pending[-1][0] == b:          # extends the last range downwards
@@ -78,10 +97,11 @@ class DataParallel:
     training loop, optimizer and checkpoint code) is used unchanged."""
 
     def __init__(self, model, group=None, bucket_mb: float = 8.0, broadcast_init: bool = True,
-                 sync_bn: bool = False):
+                 sync_bn: bool = False, grad_dtype: str = "fp32"):
         self.model, self.group = model, group
         self.net = model.model
         self.sync_bn = bool(sync_bn)
+        self.grad_dtype = grad_dtype
         self.bucket_numel = int(bucket_mb * (1 << 20) / 4)
         object.__setattr__(self.net, "_dp", self)   # picked up by the model's forward -> HotPathFn
         if broadcast_init and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -125,7 +145,7 @@ class DataParallel:
                 total += n
             flat = torch.empty(total, device=plan.device, dtype=torch.float32)
             cache = {"idx": list(diff_idx), "offs": offs, "flat": flat,
-                     "reducer": GradReducer(flat, self.group, self.bucket_numel)}
+                     "reducer": GradReducer(flat, self.group, self.bucket_numel, getattr(self, "grad_dtype", "fp32"))}
             plan._dp_cache = cache
             red = cache["reducer"]
 

@@ -37,6 +37,12 @@ def _nchw(t):        # [B,H,W,C] -> [B,C,H,W]
     return t.permute(0, 3, 1, 2).contiguous()
 
 
+def _bn_name(conv_weight):
+    """'model.conv1_0.conv2.weight' -> 'model.conv1_0.bn2' (VGGBlock, src/model.py:12-15)."""
+    blk, cv, _ = conv_weight.rsplit(".", 2)
+    return f"{blk}.bn{cv[-1]}"
+
+
 def _nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
@@ -83,7 +89,7 @@ CASES = {
     "unet_small_odd": ("unet", dict(temporal_embeddings=True, metadata_embeddings=True), (23, 828, 16, 8, 8, 32, 2), 8, 3, 37, 45, 24),
     "unet_full_width": ("unet", dict(temporal_embeddings=False, metadata_embeddings=True), (23, 828, 64, 8, 64, 96, 2), 64, 2, 64, 64, 8),
     "unetpp_small_odd": ("unet++", dict(), (23, 828, 16, 8, 8, 32, 2), 8, 2, 37, 45, 24),
-    "unetpp_width32": ("unet++", dict(), (23, 828, 32, 8, 32, 48, 2), 32, 2, 48, 48, 16),
+    "unetpp_width32": ("unet++", dict(), (23, 828, 32, 8, 32, 32, 2), 32, 2, 48, 48, 16),
 }
 
 
@@ -154,10 +160,10 @@ def test_every_launch_of_a_training_step_teacher_forced(case, precision):
     for L in desc["layers"]:
         xin = torch.cat([fwd.get(L["in"], s0, n) for s0, n in L["segs"]], 1)
         w = rnd(sd[L["weight"]])
-        bias = sd[L["weight"].replace(".weight", ".bias")]
+        bias = sd[L["weight"][:-len("weight")] + "bias"]
         z = fwd.get(L["z"], 0, L["cout"])
         check(f"{L['name']} conv -> z", z, rnd(F.conv2d(xin, w, bias, padding=1)), tol_store)
-        bn = L["weight"].replace("conv1", "bn1").replace("conv2", "bn2").replace(".weight", "")
+        bn = _bn_name(L["weight"])
         gam, bet = sd[bn + ".weight"], sd[bn + ".bias"]
         y_ref = F.relu(F.batch_norm(z, None, None, gam, bet, True, 0.1, 1e-5))
         check(f"{L['name']} BN+ReLU -> y", fwd.get(L["out"], L["out_c0"], L["cout"]), rnd(y_ref), tol_store)
@@ -182,7 +188,7 @@ def test_every_launch_of_a_training_step_teacher_forced(case, precision):
             continue
         gy = gd.get(L["out"], L["out_c0"], cout)
         z = fwd.get(L["z"], 0, cout).requires_grad_(True)
-        bn = L["weight"].replace("conv1", "bn1").replace("conv2", "bn2").replace(".weight", "")
+        bn = _bn_name(L["weight"])
         gam = sd[bn + ".weight"].clone().requires_grad_(True)
         bet = sd[bn + ".bias"].clone().requires_grad_(True)
         F.relu(F.batch_norm(z, None, None, gam, bet, True, 0.1, 1e-5)).backward(gy)
@@ -190,7 +196,7 @@ def test_every_launch_of_a_training_step_teacher_forced(case, precision):
         check(f"{L['name']} BN+ReLU backward -> dz", dz_dev, rnd(z.grad), tol_store)
         check(f"{L['name']} dgamma", grads[bn + ".weight"], gam.grad, tol_f32)
         check(f"{L['name']} dbeta", grads[bn + ".bias"], bet.grad, tol_f32)
-        gb = grads[L["weight"].replace(".weight", ".bias")]
+        gb = grads[L["weight"][:-len("weight")] + "bias"]
         if float(gb.abs().max()) != 0.0:
             fails.append(f"{L['name']} conv bias gradient must be exactly 0 under batch-statistics BatchNorm")
         xin = torch.cat([fwd.get(L["in"], s0, n) for s0, n in L["segs"]], 1)

