@@ -201,6 +201,14 @@ int64_t mau_ssim_work_floats(int B, int H, int W);
 int mau_ssim_loss(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float* loss_dev,
                   float* grad_dev, float* work_dev, double* acc_dev, void* stream);
 
+/* The same in two calls for autograd: mau_ssim_forward leaves the per-window derivative maps in work_dev (keep it until the
+ * backward); mau_ssim_backward writes grad_dev = upstream * d loss / d pred, upstream_dev being a nullable DEVICE scalar
+ * (the gradient autograd hands to the term, e.g. lambda_ssim = 0.5, src/utils/losses.py:95) -- no host synchronisation. */
+int mau_ssim_forward(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float* loss_dev,
+                     float* work_dev, double* acc_dev, void* stream);
+int mau_ssim_backward(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, const float* work_dev,
+                      const float* upstream_dev, float* grad_dev, void* stream);
+
 /* Sharpness metric of the same evaluation loop (test/evaluate.py:241-242): np.var(scipy.ndimage.laplace(x)) of the
  * un-normalised prediction and target of every (sample, channel).  sums_dev [B, C, 4] float64 =
  * {sum L(pred), sum L(pred)^2, sum L(target), sum L(target)^2} with L = the 5-point Laplacian in scipy's default
@@ -225,7 +233,8 @@ int mau_op_conv3x3_dgrad(int impl, const void* dz_dev, int B, int H, int W, int 
 int mau_op_conv3x3_bench(int impl, const void* x_dev, int B, int H, int W, int Cin, int Cin_stride,
                          const float* w_oihw_dev, int Cout, void* y_dev, int Cout_stride, int iters, float* ms_out);
 /* dW [Cout,Cin,3,3] fp32 = sum_pixels dy (x) x ; impl 0 = tcgen05 persistent split-K kernel (orientation
- * chosen by the tile-padding cost model), 4 / 5 = the same with M = output / input channels forced,
+ * or tap-pair variant chosen by the cost model), 4 / 5 = split-K kernel with M = output / input channels forced,
+ * 6 / 7 = tap-pair kernel with the output / input side (<= 64 channels) carrying the tap shift,
  * 1 = first-generation tcgen05 kernel (atomics), 2 = FFMA */
 int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_dev, int B, int H, int W,
                          int Cin, int Cin_stride, int Cout, int Cout_stride, float* dw_oihw_dev,

@@ -188,6 +188,17 @@ int mau_ssim_loss(const float* pred_dev, const float* target_dev, int B, int C, 
   return op_ssim_loss(pred_dev, target_dev, B, C, H, W, loss_dev, grad_dev, work_dev, acc_dev, static_cast<cudaStream_t>(stream));
 }
 
+int mau_ssim_forward(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float* loss_dev, float* work_dev,
+                     double* acc_dev, void* stream) {
+  if (!pred_dev || !target_dev || !loss_dev || !work_dev || !acc_dev) return fail("ssim_forward: null argument");
+  return op_ssim_forward(pred_dev, target_dev, B, C, H, W, loss_dev, work_dev, acc_dev, static_cast<cudaStream_t>(stream));
+}
+int mau_ssim_backward(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, const float* work_dev,
+                      const float* upstream_dev, float* grad_dev, void* stream) {
+  if (!pred_dev || !target_dev || !work_dev || !grad_dev) return fail("ssim_backward: null argument");
+  return op_ssim_backward(pred_dev, target_dev, B, C, H, W, work_dev, upstream_dev, grad_dev, static_cast<cudaStream_t>(stream));
+}
+
 int mau_adamw_step(int n_tensors, void* const* params_dev, void* const* grads_dev, void* const* exp_avg_dev,
                    void* const* exp_avg_sq_dev, const int64_t* numels, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, void* stream) {
@@ -326,7 +337,7 @@ int mau_op_conv3x3_wgrad(int impl, int dtype, const void* x_dev, const void* dy_
     MAU_TRY(wgrad_tc_prepare(&op, x, dy, 0, Cin, nullptr, 0));
     return wgrad_tc_launch(op, dw_oihw_dev, st);
   }
-  const int swap = impl == 4 ? 0 : (impl == 5 ? 1 : wgrad_tc_pick_swap(Cout, 1, &Cin));
+  const int swap = impl == 4 ? 0 : (impl == 5 ? 1 : (impl == 6 ? 2 : (impl == 7 ? 3 : wgrad_tc_pick_swap(Cout, 1, &Cin))));
   const size_t fl = wgrad_tc_workspace_floats(Cout, Cin, swap);
   float* ws = nullptr;
   MAU_CUDA(cudaMalloc(&ws, sizeof(float) * fl));
@@ -347,7 +358,7 @@ int mau_op_conv3x3_wgrad_bench(int impl, const void* x_dev, const void* dy_dev, 
   const View x = mkview(x_dev, B, H, W, Cin, Cin_stride), dy = mkview(dy_dev, B, H, W, Cout, Cout_stride);
   WgradTcOp op;
   const bool v1 = impl == 1;
-  const int swap = impl == 4 ? 0 : (impl == 5 ? 1 : wgrad_tc_pick_swap(Cout, 1, &Cin));
+  const int swap = impl == 4 ? 0 : (impl == 5 ? 1 : (impl == 6 ? 2 : (impl == 7 ? 3 : wgrad_tc_pick_swap(Cout, 1, &Cin))));
   const size_t fl = wgrad_tc_workspace_floats(Cout, Cin, swap);
   float* ws = nullptr;
   if (!v1) MAU_CUDA(cudaMalloc(&ws, sizeof(float) * fl));

@@ -65,10 +65,12 @@ struct WgradTcOp {
   int m_tiles = 0, n_tiles = 0, splits = 0, tiles_per_split = 0;
   int bn = 0;
   float* ws = nullptr;           // v2: fp32 workspace [9][M dim][N dim] (nullptr selects the v1 atomics kernel)
-  int swap = 0;                  // v2: 1 = M side is the input-channel side (workspace [9][Cin][Cout])
+  int swap = 0;                  // v2: 1 = M side is the input-channel side (workspace [9][Cin][Cout]); 2 / 3 = tap-pair kernel
+                                 // with dY / X as the shifted 64-channel operand (workspace layouts of 0 / 1)
   dim3 grid;
 };
-// orientation that wastes less of the 128 x BN tiles for this layer (all segments share one workspace layout)
+// orientation that wastes less of the 128 x BN tiles for this layer (all segments share one workspace layout);
+// 2 / 3 select the tap-pair kernel when the output / input side has at most 64 channels
 int wgrad_tc_pick_swap(int Cout, int nseg, const int* seg_len);
 size_t wgrad_tc_workspace_floats(int Cout, int Cin_w, int swap);
 // ws != nullptr: v2 (persistent split-K/stream-K kernel, TMA reduce-add into ws, then wgrad_tc_finalize);

@@ -134,6 +134,12 @@ int op_laplacian_sums(const float* pred, const float* tgt, int B, int C, int H, 
 long long ssim_work_floats(int B, int H, int W);
 int op_ssim_loss(const float* pred, const float* tgt, int B, int C, int H, int W, float* loss, float* grad, float* work,
                  double* acc, cudaStream_t st);
+// the two halves separately (autograd): forward leaves the derivative maps in work; backward multiplies the nullable
+// DEVICE scalar `upstream` (d L / d ssim_loss) into the gradient
+int op_ssim_forward(const float* pred, const float* tgt, int B, int C, int H, int W, float* loss, float* work, double* acc,
+                    cudaStream_t st);
+int op_ssim_backward(const float* pred, const float* tgt, int B, int C, int H, int W, const float* work, const float* upstream,
+                     float* grad, cudaStream_t st);
 
 // ---- backward of a conv w.r.t. a spatially constant input segment (embgrad.cu; U-Net++ embedding planes) ------
 // dz: the conv's output gradient [B,H,W,Cout]; emb [B, emb_stride] holds the segment's E values per image at emb[b*stride + c].

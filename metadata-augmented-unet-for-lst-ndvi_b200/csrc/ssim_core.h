@@ -49,7 +49,28 @@ struct Point {
   float a, b, c;  // dS/d mu_x, dS/d (G*x^2), dS/d (G*xy)   (x = scaled prediction)
 };
 
+// SSIM of one window from its five Gaussian moments mx = G*x, my = G*y, q = G*x^2, qy = G*y^2, r = G*xy
+MAU_HD Point point_from_moments(float mx, float my, float q, float qy, float r) {
+  const float sxx = q - mx * mx, syy = qy - my * my, sxy = r - mx * my;
+  const float A1 = 2.f * mx * my + kC1, A2 = 2.f * sxy + kC2;
+  const float B1 = mx * mx + my * my + kC1, B2 = sxx + syy + kC2;
+  const float inv = 1.f / (B1 * B2);
+  Point p;
+  p.s = A1 * A2 * inv;
+  p.a = 2.f * my * (A2 - A1) * inv - 2.f * mx * p.s * (1.f / B1 - 1.f / B2);
+  p.b = -p.s / B2;
+  p.c = 2.f * A1 * inv;
+  return p;
+}
+
+// d (sum of S) / d raw prediction at one pixel from the three Gaussian-filtered derivative maps at that pixel
+MAU_HD float combine_grad(float sa, float sb, float sc, float x_raw, float y_raw, int ch) {
+  const float xv = scale_value(x_raw, ch), yv = scale_value(y_raw, ch);
+  return (sa + 2.f * xv * sb + yv * sc) * scale_slope(x_raw, ch);
+}
+
 // SSIM of the window whose top-left corner is (i, j) of one raw (unscaled) prediction / target plane of width W
+// (direct 121-tap form: the reference point the tiled, separable kernels of ssim.cu are checked against)
 MAU_HD Point window(const float* x, const float* y, int W, int i, int j, int ch, const float* g) {
   float mx = 0.f, my = 0.f, q = 0.f, qy = 0.f, r = 0.f;
   for (int ki = 0; ki < kWin; ++ki) {
@@ -65,18 +86,8 @@ MAU_HD Point window(const float* x, const float* y, int W, int i, int j, int ch,
       r += w * xv * yv;
     }
   }
-  const float sxx = q - mx * mx, syy = qy - my * my, sxy = r - mx * my;
-  const float A1 = 2.f * mx * my + kC1, A2 = 2.f * sxy + kC2;
-  const float B1 = mx * mx + my * my + kC1, B2 = sxx + syy + kC2;
-  const float inv = 1.f / (B1 * B2);
-  Point p;
-  p.s = A1 * A2 * inv;
-  p.a = 2.f * my * (A2 - A1) * inv - 2.f * mx * p.s * (1.f / B1 - 1.f / B2);
-  p.b = -p.s / B2;
-  p.c = 2.f * A1 * inv;
-  return p;
+  return point_from_moments(mx, my, q, qy, r);
 }
-
 // d (sum of S over all windows) / d raw prediction at pixel (yy, xx): gather over the windows that contain it.
 // a, b, c are the [Hv, Wv] maps written by the forward pass (Hv = H - 10, Wv = W - 10).
 MAU_HD float gather_grad(const float* a, const float* b, const float* c, int Hv, int Wv, const float* x, const float* y,
@@ -95,9 +106,7 @@ MAU_HD float gather_grad(const float* a, const float* b, const float* c, int Hv,
       sc += w * c[o];
     }
   }
-  const float xr = x[(long long)yy * W + xx];
-  const float xv = scale_value(xr, ch), yv = scale_value(y[(long long)yy * W + xx], ch);
-  return (sa + 2.f * xv * sb + yv * sc) * scale_slope(xr, ch);
+  return combine_grad(sa, sb, sc, x[(long long)yy * W + xx], y[(long long)yy * W + xx], ch);
 }
 
 }  // namespace mau_ssim

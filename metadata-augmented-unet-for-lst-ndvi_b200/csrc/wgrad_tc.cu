@@ -646,12 +646,22 @@ static double orient_cost(int Cout, int nseg, const int* seg_len, bool swap) {
   return c;
 }
 int wgrad_tc_pick_swap(int Cout, int nseg, const int* seg_len) {
-  if (const char* e = getenv("MAU_WGRAD_SWAP")) return atoi(e) != 0;
+  if (const char* e = getenv("MAU_WGRAD_SWAP")) return atoi(e);
+  // narrow side <= 64 channels: the tap-pair kernel (2 = dY carries the shift, 3 = X carries it); MAU_WGRAD_PAIR=0 disables
+  static const bool pair_ok = [] { const char* e = getenv("MAU_WGRAD_PAIR"); return !e || atoi(e) != 0; }();
+  if (pair_ok && Cout <= 64) return 2;
+  if (pair_ok && nseg == 1 && seg_len[0] <= 64) return 3;
   return orient_cost(Cout, nseg, seg_len, true) < orient_cost(Cout, nseg, seg_len, false) ? 1 : 0;
 }
 size_t wgrad_tc_workspace_floats(int Cout, int Cin_w, int swap) {
-  const int d0 = swap ? Cout : Cin_w, d1 = swap ? Cin_w : Cout;
+  const int d0 = (swap & 1) ? Cout : Cin_w, d1 = (swap & 1) ? Cin_w : Cout;
   return (size_t)9 * d1 * round_up(d0, 4);
+}
+// N tile of the pair kernel: 96 columns (5 x 96 = 480 TMEM columns) when that pads less than 64-wide tiles
+static int pair_bn(int Nd) {
+  if (Nd <= 64) return 64;
+  const double c96 = (double)ceil_div(Nd, 96) * 96, c64 = (double)ceil_div(Nd, 64) * 64 / 0.75;
+  return c96 <= c64 ? 96 : 64;
 }
 
 int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0, int Cin_w, float* ws, int swap) {
@@ -673,6 +683,28 @@ int wgrad_tc_prepare(WgradTcOp* op, const View& x_seg, const View& dy, int ci_w0
     op->grid = dim3((unsigned)op->n_tiles, (unsigned)op->m_tiles, (unsigned)(3 * op->splits));
     MAU_TRY(make_nhwc_map(&op->tmDy, DT_BF16, dy, 64, 8, 8));
     MAU_TRY(make_nhwc_map(&op->tmX, DT_BF16, x_seg, 64, 10, 8));
+    return 0;
+  }
+  if (swap >= 2) {      // tap-pair kernel: S = shifted narrow operand (halo box), O = the other operand
+    const bool dy_shift = swap == 2;
+    const View& sv = dy_shift ? dy : x_seg;
+    const View& ov = dy_shift ? x_seg : dy;
+    if (sv.C > 64) return fail("wgrad_tc pair: the shifted operand has %d > 64 channels", sv.C);
+    op->bn = pair_bn(ov.C);
+    op->m_tiles = 1;
+    op->n_tiles = ceil_div(ov.C, op->bn);
+    const int T = dy.B * ceil_div(dy.H, 4) * ceil_div(dy.W, 16);
+    const int U = op->n_tiles;
+    const int sms = sm_budget();
+    const int G = 2 * U <= sms ? U * std::min(sms / U, T) : (int)std::min<long long>(sms, (long long)U * T);
+    op->grid = dim3((unsigned)G, 1, 1);
+    MAU_TRY(make_nhwc_map(&op->tmDy, DT_BF16, sv, 64, 18, 6));
+    MAU_TRY(make_nhwc_map(&op->tmX, DT_BF16, ov, 64, 16, 4));
+    const int d0 = dy_shift ? Cin_w : dy.C, d1 = dy_shift ? dy.C : Cin_w;      // workspace [9][narrow][wide]
+    uint64_t dims[3] = {(uint64_t)d0, (uint64_t)d1, 9};
+    uint64_t str[2] = {(uint64_t)round_up(d0, 4) * 4, (uint64_t)round_up(d0, 4) * 4 * (uint64_t)d1};
+    uint32_t box[3] = {32, 64, 1};
+    MAU_TRY(make_tensor_map(&op->tmWs, DT_F32, 3, ws, dims, str, box, true));
     return 0;
   }
   const int Md = swap ? x_seg.C : dy.C, Nd = swap ? dy.C : x_seg.C;
@@ -709,6 +741,17 @@ int wgrad_tc_launch(const WgradTcOp& op, float* dw_oihw, cudaStream_t st) {
     if (op.bn == 64) return launch_wgrad<64, 6>(op, p, dw_oihw, st);
     return launch_wgrad<128, 5>(op, p, dw_oihw, st);
   }
+  if (op.swap >= 2) {
+    WgradPairParams p;
+    p.tiles_w = ceil_div(op.W, 16); p.tiles_h = ceil_div(op.H, 4);
+    p.T = op.B * p.tiles_w * p.tiles_h;
+    p.n_tiles = op.n_tiles;
+    p.atoms = (long long)op.n_tiles * p.T;
+    p.tap_reversed = op.swap == 2 ? 1 : 0;
+    p.ws_n0 = op.swap == 2 ? op.ci_w0 : 0;
+    p.ws_m0 = op.swap == 2 ? 0 : op.ci_w0;
+    return op.bn == 64 ? launch_wgrad_pair<64, 6>(op, p, st) : launch_wgrad_pair<96, 5>(op, p, st);
+  }
   WgradV2Params p;
   p.tiles_w = ceil_div(op.W, 16); p.tiles_h = ceil_div(op.H, 4);
   p.T = op.B * p.tiles_w * p.tiles_h;
@@ -721,6 +764,7 @@ int wgrad_tc_launch(const WgradTcOp& op, float* dw_oihw, cudaStream_t st) {
 }
 
 int wgrad_tc_finalize(const float* ws, int swap, int Cout, int Cin_w, float* dw_oihw, cudaStream_t st) {
+  swap &= 1;                // pair modes 2 / 3 use the layouts of 0 / 1
   const int d0 = swap ? Cout : Cin_w;
   const long long total = (long long)Cout * Cin_w;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);

@@ -49,7 +49,7 @@ EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
     "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
-    "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_loss_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss",
+    "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_loss_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss", "mau_ssim_forward", "mau_ssim_backward",
     "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_cast_f32_bf16", "mau_cast_bf16_f32", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
@@ -103,6 +103,10 @@ def lib():
         L.mau_ssim_work_floats.restype = C.c_int64
         L.mau_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mau_ssim_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+        L.mau_ssim_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
         L.mau_op_conv3x3.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p]
@@ -567,19 +571,49 @@ def ssim_loss_terms(pred: torch.Tensor, target: torch.Tensor, need_grad: bool = 
     return loss, grad
 
 
+def ssim_forward_terms(pred: torch.Tensor, target: torch.Tensor):
+    """Forward half: (loss[1], work) -- ``work`` holds the per-window derivative maps the backward half needs."""
+    pred = _dev_f32(pred, "pred")
+    target = _dev_f32(target, "target", pred)
+    if pred.dim() != 4 or target.shape != pred.shape:
+        raise RuntimeError(f"pred and target must both be [B,C,H,W], got {tuple(pred.shape)} and {tuple(target.shape)}")
+    B, Cc, H, W = pred.shape
+    work = torch.empty(max(int(lib().mau_ssim_work_floats(B, H, W)), 1), device=pred.device, dtype=torch.float32)
+    acc = torch.empty(1, device=pred.device, dtype=torch.float64)
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    with torch.cuda.device(pred.device):
+        check(lib().mau_ssim_forward(pred.data_ptr(), target.data_ptr(), B, Cc, H, W, loss.data_ptr(), work.data_ptr(),
+                                     acc.data_ptr(), _stream_ptr()), "ssim_forward")
+    return loss, work
+
+
+def ssim_backward_terms(pred: torch.Tensor, target: torch.Tensor, work: torch.Tensor, upstream: Optional[torch.Tensor]):
+    """Backward half: upstream * d loss / d pred (``upstream``: 0-d device tensor or None), one kernel launch."""
+    pred = _dev_f32(pred, "pred")
+    target = _dev_f32(target, "target", pred)
+    B, Cc, H, W = pred.shape
+    grad = torch.empty_like(pred)
+    up = None if upstream is None else _dev_f32(upstream, "upstream gradient", pred)
+    with torch.cuda.device(pred.device):
+        check(lib().mau_ssim_backward(pred.data_ptr(), target.data_ptr(), B, Cc, H, W, work.data_ptr(),
+                                      None if up is None else up.data_ptr(), grad.data_ptr(), _stream_ptr()), "ssim_backward")
+    return grad
+
+
 class _SsimFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
-        need = bool(ctx.needs_input_grad[0])      # validation runs under no_grad (src/train.py:33): skip the backward kernel
-        loss, grad = ssim_loss_terms(pred, target, need)
-        if need:
-            ctx.save_for_backward(grad)
+        pred_c, target_c = pred.contiguous(), target.contiguous()
+        loss, work = ssim_forward_terms(pred_c, target_c)
+        if ctx.needs_input_grad[0]:               # validation runs under no_grad (src/train.py:33): nothing is kept
+            ctx.save_for_backward(pred_c, target_c)
+            ctx.work = work
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        return grad * g, None
+        pred, target = ctx.saved_tensors
+        return ssim_backward_terms(pred, target, ctx.work, g), None
 
 
 def ssim_loss(outputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:

@@ -59,7 +59,19 @@ def torch_loss_backward_terms(pred, target, kind, lambda_total, g_total=None, g_
     return x.grad
 
 
+def emulated_ssim_forward(pred, target):
+    lv, _ = emulated_ssim_terms(pred, target, need_grad=False)
+    return lv, None
+
+
+def emulated_ssim_backward(pred, target, work, upstream):
+    _, g = emulated_ssim_terms(pred, target, need_grad=True)
+    return g if upstream is None else g * upstream
+
+
 engine.ssim_loss_terms = emulated_ssim_terms
+engine.ssim_forward_terms = emulated_ssim_forward
+engine.ssim_backward_terms = emulated_ssim_backward
 engine.loss_terms = torch_loss_terms
 engine.loss_backward_terms = torch_loss_backward_terms
 src = open(os.path.join(ROOT, "tools", "ssim_gpu_check.py")).read()

@@ -84,14 +84,19 @@ def test_conv3x3_dgrad_against_torch(impl, shape):
         assert rel(got, want) < (2e-2 if acc else 6e-3)
 
 
-@pytest.mark.parametrize("impl,dt", [(0, 0), (4, 0), (5, 0), (1, 0), (2, 1)])
+@pytest.mark.parametrize("impl,dt", [(0, 0), (4, 0), (5, 0), (6, 0), (7, 0), (1, 0), (2, 1)])
 @pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64), (2, 15, 15, 128, 256), (2, 33, 47, 24, 64), (1, 25, 25, 8, 8),
-                                   (2, 15, 15, 640, 640), (1, 31, 31, 192, 64), (3, 18, 50, 72, 200)])
+                                   (2, 15, 15, 640, 640), (1, 31, 31, 192, 64), (3, 18, 50, 72, 200), (2, 30, 30, 64, 128),
+                                   (1, 50, 37, 56, 256), (2, 61, 45, 320, 64)])
 def test_wgrad_against_torch(impl, dt, shape):
-    """impl 0 = persistent split-K/stream-K tcgen05 kernel (auto orientation), 4 / 5 = M side forced to the
-    output / input channels, 1 = first-generation atomics kernel, 2 = FFMA.  (2,15,15,640,640) has more work
-    units than SMs/2 and runs the stream-K schedule (CTAs straddle units)."""
+    """impl 0 = persistent tcgen05 kernel chosen by the cost model (split-K / stream-K, or the tap-pair kernel when one
+    side has <= 64 channels), 4 / 5 = split-K kernel with the M side forced to the output / input channels, 6 / 7 =
+    tap-pair kernel with the output / input side carrying the shift (two taps per MMA through the descriptor's LBO),
+    1 = first-generation atomics kernel, 2 = FFMA.  (2,15,15,640,640) has more work units than SMs/2 and runs the
+    stream-K schedule (CTAs straddle units)."""
     B, H, W, Cin, Cout = shape
+    if (impl == 6 and Cout > 64) or (impl == 7 and Cin > 64):
+        pytest.skip("tap-pair kernel needs <= 64 channels on the shifted side")
     torch.manual_seed(2)
     dtype = torch.bfloat16 if dt == 0 else torch.float32
     x = torch.randn(B, Cin, H, W, device="cuda"); dy = torch.randn(B, Cout, H, W, device="cuda")
