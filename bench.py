@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="tiles per GPU per step (default: conf/config.yaml:45 = 16; 50 for the sweep)")
     ap.add_argument("--comm-ctas", type=int, default=None, help="data-parallel training: CTAs NCCL may use (and SMs our persistent kernels leave free)")
     ap.add_argument("--sync-bn", action="store_true", help="data-parallel training: SyncBN (global-batch statistics)")
+    ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"], help="data-parallel training: wire format of the gradient all-reduce")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer measurement")
+    ap.add_argument("--no-kernel-pass", action="store_true", help="profiling runs only (ncu): skip the per-launch CUDA-event pass; no roofline block")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` block (0 = skip)")
     ap.add_argument("--criterion", default="l1", choices=["l1", "l1-gradient-ssim"], help="training loss: L1 (default) or the reference's default criterion (conf/config.yaml:42)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -265,7 +268,7 @@ def main():
         model.train(train)
         if train and world > 1:
             from mau_b200 import parallel
-            parallel.DataParallel(model, sync_bn=args.sync_bn)   # overlapped all-reduce on the plan's grad hook
+            parallel.DataParallel(model, sync_bn=args.sync_bn, grad_dtype=args.grad_dtype)   # overlapped all-reduce on the plan's grad hook
         # several distinct input batches so that consecutive steps never re-read L2-resident inputs
         nb = 4
         host = [O.synthetic_batch(B, TILE, TILE, seed=1002 + 17 * rank + i) for i in range(nb)]
@@ -366,6 +369,10 @@ def main():
             return dict(tf=tf, launches=conv_n // reps, avg_us=conv_ms / max(conv_n, 1) * 1e3,
                         flop_per_launch=kern_flops * reps / max(conv_n, 1), share=conv_ms / all_ms if all_ms else None)
 
+        if args.no_kernel_pass:          # ncu capture runs: nothing but the steps themselves
+            model.model.release_plans()
+            return {"metric": metric_name(workload), "value": value, "unit": "tiles/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                    "ms_per_step": ms / steps, "config": config_block(cfg_id, B, world), "gpu_launches": int(launches), "note": "profiling run"}
         burst = kernel_pass()            # cold chip, boost clocks: against the burst peak
 
         # ---- sustained: the same step loop for >= sustain_s seconds, clocks and power sampled under that load; the
@@ -389,7 +396,7 @@ def main():
         # timed region.  Copies of step i+1 are prefetched on a side stream while step i computes (the
         # standard PyTorch prefetch idiom); results land in pinned host buffers.
         e2e = None
-        if with_e2e:
+        if with_e2e and not args.no_e2e:
             copy_s = torch.cuda.Stream(device=dev)
             main_s = torch.cuda.current_stream(dev)
             out_host = [torch.empty((B, 2, TILE, TILE), pin_memory=True) for _ in range(3)] if not train else \

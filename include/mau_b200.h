@@ -66,6 +66,7 @@ typedef struct mau_config {
 #define MAU_FLAG_BN_FUSED      4096 /* A-B: training BatchNorm as ONE cooperative launch per direction (statistics, grid barrier,
                                       apply over the same block ranges in reverse).  Measured slower than the two plain launches
                                       (8.41 vs 8.16 ms per training step, profiles/r02_bn_fused_ab.md): off by default */
+#define MAU_FLAG_NO_WGRAD_OVERLAP 8192 /* A-B: weight-gradient kernels on the caller's stream (no second stream) */
 #define MAU_FLAG_EMB_DENSE_BWD 2048 /* debug: U-Net++ embedding planes back-propagated densely (dgrad + wgrad launches) */
 
 typedef struct mau_plan mau_plan; /* opaque */
@@ -130,6 +131,11 @@ int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* gr
  * single-GPU, src/train.py:99).  first_index..last_index is a contiguous state-index range. */
 typedef void (*mau_grad_ready_fn)(void* user, int first_index, int last_index);
 int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user);
+/* backward runs the weight-gradient kernels on a plan-owned second stream (they overlap the next layer's bandwidth-bound
+ * BatchNorm / pool / bilinear backward on `stream`); mau_plan_backward joins it before returning control of `stream`.
+ * A grad hook that launches work on ANOTHER stream (the all-reduce) calls this first: `stream` then waits for every
+ * weight-gradient launch enqueued so far, in addition to the event it records on the backward stream itself. */
+int mau_plan_wait_backward_streams(mau_plan* plan, void* stream);
 
 /* optional SyncBN (new capability): when set, every training-mode BatchNorm calls fn with its
  * device buffer of per-channel sums (double[n], n = 2*C: forward {sum z, sum z^2}, backward

@@ -117,6 +117,11 @@ int mau_plan_set_state_version(mau_plan* plan, uint64_t version) {
   return 0;
 }
 
+int mau_plan_wait_backward_streams(mau_plan* plan, void* stream) {
+  if (!plan) return fail("null plan");
+  return plan->impl.w_join(static_cast<cudaStream_t>(stream));
+}
+
 int mau_plan_set_grad_hook(mau_plan* plan, mau_grad_ready_fn fn, void* user) {
   if (!plan) return fail("null plan");
   plan->impl.hook = fn; plan->impl.hook_user = user;

@@ -24,6 +24,7 @@ void Plan::kend(const Ctx& c) {
 
 Plan::~Plan() {
   if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
+  if (wst) { cudaStreamSynchronize(wst); cudaStreamDestroy(wst); cudaEventDestroy(ev_w_fork); cudaEventDestroy(ev_w_join); }
   if (!dry) {
     for (void* p : allocs) cudaFree(p);
   }
@@ -336,17 +337,20 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
     float* dw = c.g(L->iw);
     int ci_w0 = 0;
     const bool ws_path = use_tc && wgrad_ws != nullptr;      // v2 wgrad: reduce into the workspace, then transpose
-    if (dw && ws_path) MAU_CUDA(cudaMemsetAsync(wgrad_ws, 0, sizeof(float) * wgrad_tc_workspace_floats(C, L->Cin, L->wg_swap), c.st));
-    else if (dw) MAU_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * L->Cin * 9, c.st));
+    cudaStream_t ws;                                         // weight-gradient stream (== c.st when the overlap is off)
+    MAU_TRY(w_fork(c, &ws));
+    Ctx cw = c; cw.st = ws;
+    if (dw && ws_path) MAU_CUDA(cudaMemsetAsync(wgrad_ws, 0, sizeof(float) * wgrad_tc_workspace_floats(C, L->Cin, L->wg_swap), ws));
+    else if (dw) MAU_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * L->Cin * 9, ws));
     int emb_ci0 = -1;
     for (int s = 0; s < L->nseg; ++s) {
       if (s == L->emb_seg) { emb_ci0 = ci_w0; ci_w0 += L->seg_len[s]; continue; }
       const TRef xin{L->in_buf, L->seg_start[s], L->seg_len[s]};
       if (dw) {
-        kbegin(c, "k:" + L->name + ":wgrad");
-        if (use_tc) MAU_TRY(wgrad_tc_launch(L->wg[s], dw, c.st));
-        else MAU_TRY(wgrad_ffma_launch(dt, view(xin), z, ci_w0, L->Cin, dw, 1, c.st));
-        kend(c);
+        kbegin(cw, "k:" + L->name + ":wgrad");
+        if (use_tc) MAU_TRY(wgrad_tc_launch(L->wg[s], dw, ws));
+        else MAU_TRY(wgrad_ffma_launch(dt, view(xin), z, ci_w0, L->Cin, dw, 1, ws));
+        kend(cw);
       }
       if (L->input_needs_grad) {
         if (use_tc) {
@@ -363,10 +367,10 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
       }
       ci_w0 += L->seg_len[s];
     }
-    if (dw && ws_path) MAU_TRY(wgrad_tc_finalize(wgrad_ws, L->wg_swap, C, L->Cin, dw, c.st));
+    if (dw && ws_path) MAU_TRY(wgrad_tc_finalize(wgrad_ws, L->wg_swap, C, L->Cin, dw, ws));
     if (emb_ci0 >= 0)      // dW of the constant planes' columns and their contribution to d emb, from nine sums of dz per image
       MAU_TRY(op_emb_segment_grad(dt, z, c.f(L->iw), L->Cin, emb_ci0, L->seg_len[L->emb_seg], emb, emb_dim, dw, demb,
-                                  embgrad_scratch, c.st));
+                                  embgrad_scratch, ws));
     return 0;
   };
   bwd.push_back(op);
@@ -433,6 +437,28 @@ int Plan::side_join(Ctx& c) {
   if (!side || !side_pending) return 0;
   MAU_CUDA(cudaStreamWaitEvent(c.st, ev_join, 0));
   side_pending = false;
+  return 0;
+}
+
+int Plan::w_fork(Ctx& c, cudaStream_t* out) {
+  *out = c.st;
+  if (!overlap_wgrad || profiling) return 0;
+  if (!wst) {
+    MAU_CUDA(cudaStreamCreateWithFlags(&wst, cudaStreamNonBlocking));
+    MAU_CUDA(cudaEventCreateWithFlags(&ev_w_fork, cudaEventDisableTiming));
+    MAU_CUDA(cudaEventCreateWithFlags(&ev_w_join, cudaEventDisableTiming));
+  }
+  MAU_CUDA(cudaEventRecord(ev_w_fork, c.st));
+  MAU_CUDA(cudaStreamWaitEvent(wst, ev_w_fork, 0));
+  w_pending = true;
+  *out = wst;
+  return 0;
+}
+// `waiter` waits for everything enqueued on the weight-gradient stream so far
+int Plan::w_join(cudaStream_t waiter) {
+  if (!wst || !w_pending) return 0;
+  MAU_CUDA(cudaEventRecord(ev_w_join, wst));
+  MAU_CUDA(cudaStreamWaitEvent(waiter, ev_w_join, 0));
   return 0;
 }
 
@@ -516,6 +542,7 @@ int Plan::build_embed_broadcast(const TRef* t_dst, int n_t, const TRef* m_dst, i
       Op b;
       b.name = "emb.bwd";                        // reduce on the main stream, encoder backward on the side stream
       b.run = [=](Ctx& c) -> int {
+        if (emb_direct) MAU_TRY(w_join(c.st));      // d emb was accumulated by the weight-gradient stream
         if (!emb_direct) {     // (U-Net++: the decoder nodes have already accumulated d emb in closed form)
           MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * B * emb_dim, c.st));
           if (te) for (const View& g : gt) MAU_TRY(op_embed_reduce(dt, g, demb + t_off, emb_dim, 1, c.st));
@@ -965,6 +992,7 @@ int Plan::build() {
   if (rc) return rc;
   if (cfg.training) {
     bn_fused = (cfg.flags & MAU_FLAG_BN_FUSED) != 0;
+    overlap_wgrad = !(cfg.flags & MAU_FLAG_NO_WGRAD_OVERLAP);
     bn_bar = static_cast<unsigned*>(alloc(sizeof(unsigned) * 4));      // zeroed; only ever counts up
     if (!dry && !bn_bar) return -1;
     if (use_tc && !(cfg.flags & MAU_FLAG_WGRAD_V1)) {
@@ -1068,6 +1096,8 @@ int Plan::run_backward(Ctx& c) {
   if (emb_direct) MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * cfg.batch * emb_dim, c.st));
   MAU_TRY(run_ops(this, bwd, c, true));
   MAU_TRY(side_join(c));
+  MAU_TRY(w_join(c.st));
+  w_pending = false;
   forward_done = false;
   return 0;
 }

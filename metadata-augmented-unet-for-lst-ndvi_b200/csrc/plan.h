@@ -148,6 +148,17 @@ class Plan {
   int build_embed_broadcast(const TRef* t_dst, int n_t, const TRef* m_dst, int n_m);  // join + broadcast into the slices
   int side_fork(Ctx& c);
   int side_join(Ctx& c);
+ public:
+  // Backward overlap: the weight-gradient launches of a layer (workspace memset, wgrad, transpose, closed-form embedding
+  // columns) run on a plan-owned second stream, forked after that layer's BatchNorm backward; the caller's stream goes
+  // on with the data gradient and the NEXT layer's bandwidth-bound BatchNorm / pool / bilinear backward, which then
+  // share the SMs with the tensor-bound wgrad kernel instead of waiting for it.  Joined at the end of backward (and
+  // by mau_plan_wait_backward_streams for a data-parallel bucket).  Off while profiling (per-op times stay additive).
+  bool overlap_wgrad = true;
+  cudaStream_t wst = nullptr; cudaEvent_t ev_w_fork = nullptr, ev_w_join = nullptr; bool w_pending = false;
+  int w_fork(Ctx& c, cudaStream_t* out);
+  int w_join(cudaStream_t waiter);
+ private:
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool side_pending = false;
   int enc_lstm0 = -1, enc_fc0 = -1, enc_mlp0 = -1;
   int next_emb_seg = -1;            // consumed by the next add_conv

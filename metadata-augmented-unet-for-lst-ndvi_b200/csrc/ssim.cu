@@ -29,7 +29,7 @@ constexpr int kIW = kTW + mau_ssim::kWin - 1;           // 42 input columns
 
 // grid (ceil(Wv / 32), ceil(Hv / 16), B * 2), block 256
 __global__ void __launch_bounds__(256) ssim_forward_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int C,
-                                                           int H, int W, Window win, float* __restrict__ a,
+                                                           int H, int W, int prescaled, Window win, float* __restrict__ a,
                                                            float* __restrict__ b, float* __restrict__ c,
                                                            double* __restrict__ acc) {
   __shared__ float sx[kIH][kIW], sy[kIH][kIW];
@@ -40,12 +40,13 @@ __global__ void __launch_bounds__(256) ssim_forward_kernel(const float* __restri
   const int i0 = blockIdx.y * kTH, j0 = blockIdx.x * kTW;
   const float* x = pred + ((long long)bi * C + ch) * H * W;
   const float* y = tgt + ((long long)bi * C + ch) * H * W;
+  const int sch = prescaled ? mau_ssim::kPrescaled : ch;
   for (int e = tid; e < kIH * kIW; e += 256) {
     const int r = e / kIW, q = e - r * kIW;
     const int gi = i0 + r, gj = j0 + q;
     const bool in = gi < H && gj < W;
-    sx[r][q] = in ? mau_ssim::scale_value(x[(long long)gi * W + gj], ch) : 0.f;
-    sy[r][q] = in ? mau_ssim::scale_value(y[(long long)gi * W + gj], ch) : 0.f;
+    sx[r][q] = in ? mau_ssim::scale_value(x[(long long)gi * W + gj], sch) : 0.f;
+    sy[r][q] = in ? mau_ssim::scale_value(y[(long long)gi * W + gj], sch) : 0.f;
   }
   __syncthreads();
   for (int e = tid; e < kIH * kTW; e += 256) {          // horizontal pass: five moments per (row, output column)
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) ssim_forward_kernel(const float* __restri
 
 // grid (ceil(W / 32), ceil(H / 16), B * C), block 256.  up (nullable): device scalar multiplied into the result.
 __global__ void __launch_bounds__(256) ssim_backward_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int C,
-                                                            int H, int W, Window win, const float* __restrict__ a,
+                                                            int H, int W, int prescaled, Window win, const float* __restrict__ a,
                                                             const float* __restrict__ b, const float* __restrict__ c,
                                                             float coef, const float* __restrict__ up, float* __restrict__ grad) {
   __shared__ float sm[3][kIH][kIW];
@@ -152,9 +153,50 @@ __global__ void __launch_bounds__(256) ssim_backward_kernel(const float* __restr
         t2 += w * hz[2][r + k][q];
       }
       const long long o = (long long)yy * W + xx;
-      gp[o] = scale * mau_ssim::combine_grad(t0, t1, t2, x[o], y[o], ch);
+      gp[o] = scale * mau_ssim::combine_grad(t0, t1, t2, x[o], y[o], prescaled ? mau_ssim::kPrescaled : ch);
     }
   }
+}
+
+// piq's down-sampling of large tiles: out[b, ch, i, j] = mean over the f x f block of the SCALED raw values (ch < 2);
+// xs / ys: [B, 2, Hp, Wp].  grid (ceil(Hp * Wp / 256), B * 2), block 256
+__global__ void __launch_bounds__(256) ssim_pool_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int C, int H,
+                                                        int W, int f, int Hp, int Wp, float* __restrict__ xs, float* __restrict__ ys) {
+  const int plane2 = blockIdx.y, bi = plane2 >> 1, ch = plane2 & 1;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= Hp * Wp) return;
+  const int i = o / Wp, j = o - i * Wp;
+  const float* x = pred + ((long long)bi * C + ch) * H * W;
+  const float* y = tgt + ((long long)bi * C + ch) * H * W;
+  float sx = 0.f, sy = 0.f;
+  for (int di = 0; di < f; ++di)
+    for (int dj = 0; dj < f; ++dj) {
+      const long long at = (long long)(i * f + di) * W + j * f + dj;
+      sx += mau_ssim::scale_value(x[at], ch);
+      sy += mau_ssim::scale_value(y[at], ch);
+    }
+  const float inv = 1.f / (float)(f * f);
+  xs[(long long)plane2 * Hp * Wp + o] = sx * inv;
+  ys[(long long)plane2 * Hp * Wp + o] = sy * inv;
+}
+
+// chain rule of the pooling and of the channel scaling: grad[b, ch, h, w] = up * gp[b, ch, h / f, w / f] / f^2 * slope
+// inside the pooled region, 0 outside it (rows / columns avg_pool2d drops) and for channels >= 2.
+// grid (ceil(H * W / 256), B * C), block 256
+__global__ void __launch_bounds__(256) ssim_unpool_kernel(const float* __restrict__ pred, int C, int H, int W, int f, int Hp, int Wp,
+                                                          const float* __restrict__ gpool, const float* __restrict__ up,
+                                                          float* __restrict__ grad) {
+  const int plane = blockIdx.y, bi = plane / C, ch = plane - bi * C;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int h = p / W, w = p - h * W;
+  float g = 0.f;
+  if (ch < 2 && h < Hp * f && w < Wp * f) {
+    const float scale = (up ? up[0] : 1.f) / (float)(f * f);
+    g = scale * gpool[((long long)(bi * 2 + ch) * Hp + h / f) * Wp + w / f] *
+        mau_ssim::scale_slope(pred[(long long)plane * H * W + p], ch);
+  }
+  grad[(long long)plane * H * W + p] = g;
 }
 
 __global__ void ssim_finalize_kernel(const double* __restrict__ acc, double inv_n, float* __restrict__ loss) {
@@ -165,16 +207,23 @@ int check_shape(int B, int C, int H, int W) {
   using mau_ssim::kWin;
   if (B < 1 || C < 2) return fail("ssim_loss: needs B >= 1 and the two target channels (NDVI, temperature), got B=%d C=%d", B, C);
   if (H < kWin || W < kWin) return fail("ssim_loss: Kernel size can't be greater than actual input size (%d x %d < %d)", H, W, kWin);
-  if ((H < W ? H : W) >= 384) return fail("ssim_loss: tiles of %d x %d are average-pooled by piq before SSIM; not implemented", H, W);
   if ((long long)B * C > 65535) return fail("ssim_loss: B*C = %lld exceeds the grid limit 65535", (long long)B * C);
   return 0;
 }
 
 }  // namespace
 
+static int g_force_pool = 0;      // tests: exercise the pooled path on small tiles (0 = piq's rule)
+void ssim_debug_force_pool(int f) { g_force_pool = f; }
+static int pool_f(int H, int W) { return g_force_pool > 0 ? g_force_pool : mau_ssim::pool_factor(H, W); }
+
+// a, b, c maps of the (pooled) planes; with pooling also the pooled scaled planes xs, ys and the pooled gradient
 long long ssim_work_floats(int B, int H, int W) {
-  const long long Hv = H - mau_ssim::kWin + 1, Wv = W - mau_ssim::kWin + 1;
-  return Hv > 0 && Wv > 0 ? 3ll * B * 2 * Hv * Wv : 0;
+  const int f = pool_f(H, W);
+  const long long Hp = H / f, Wp = W / f;
+  const long long Hv = Hp - mau_ssim::kWin + 1, Wv = Wp - mau_ssim::kWin + 1;
+  if (Hv <= 0 || Wv <= 0) return 0;
+  return 3ll * B * 2 * Hv * Wv + (f > 1 ? 3ll * B * 2 * Hp * Wp : 0);
 }
 
 // loss[0] = 1 - mean SSIM; work receives the derivative maps a, b, c the backward needs
@@ -182,14 +231,26 @@ int op_ssim_forward(const float* pred, const float* tgt, int B, int C, int H, in
                     cudaStream_t st) {
   using mau_ssim::kWin;
   if (int rc = check_shape(B, C, H, W)) return rc;
-  const int Hv = H - kWin + 1, Wv = W - kWin + 1;
+  const int f = pool_f(H, W);
+  const int Hp = H / f, Wp = W / f;
+  if (Hp < kWin || Wp < kWin) return fail("ssim_loss: Kernel size can't be greater than actual input size (%d x %d pooled by %d)", H, W, f);
+  const int Hv = Hp - kWin + 1, Wv = Wp - kWin + 1;
   const long long nwin = (long long)B * 2 * Hv * Wv;
   Window win;
   mau_ssim::gaussian_window(win.g);
   float *a = work, *b = work + nwin, *c = work + 2 * nwin;
+  const float *px = pred, *py = tgt;
+  int Cc = C, pres = 0;
+  if (f > 1) {
+    float* xs = work + 3 * nwin;
+    float* ys = xs + (long long)B * 2 * Hp * Wp;
+    MAU_LAUNCH(ssim_pool_kernel, dim3((unsigned)ceil_div(Hp * Wp, 256), (unsigned)(B * 2), 1), dim3(256), st, pred, tgt, C, H, W, f, Hp, Wp, xs, ys);
+    MAU_LAUNCHED();
+    px = xs; py = ys; Cc = 2; pres = 1;
+  }
   MAU_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
-  MAU_LAUNCH(ssim_forward_kernel, dim3((unsigned)ceil_div(Wv, kTW), (unsigned)ceil_div(Hv, kTH), (unsigned)(B * 2)), dim3(256), st, pred, tgt,
-             C, H, W, win, a, b, c, acc);
+  MAU_LAUNCH(ssim_forward_kernel, dim3((unsigned)ceil_div(Wv, kTW), (unsigned)ceil_div(Hv, kTH), (unsigned)(B * 2)), dim3(256), st, px, py,
+             Cc, Hp, Wp, pres, win, a, b, c, acc);
   MAU_LAUNCHED();
   MAU_LAUNCH(ssim_finalize_kernel, dim3(1), dim3(1), st, acc, 1.0 / (double)nwin, loss);
   MAU_LAUNCHED();
@@ -201,13 +262,29 @@ int op_ssim_backward(const float* pred, const float* tgt, int B, int C, int H, i
                      float* grad, cudaStream_t st) {
   using mau_ssim::kWin;
   if (int rc = check_shape(B, C, H, W)) return rc;
-  const int Hv = H - kWin + 1, Wv = W - kWin + 1;
+  const int f = pool_f(H, W);
+  const int Hp = H / f, Wp = W / f;
+  if (Hp < kWin || Wp < kWin) return fail("ssim_loss: Kernel size can't be greater than actual input size (%d x %d pooled by %d)", H, W, f);
+  const int Hv = Hp - kWin + 1, Wv = Wp - kWin + 1;
   const long long nwin = (long long)B * 2 * Hv * Wv;
   Window win;
   mau_ssim::gaussian_window(win.g);
   const float *a = work, *b = work + nwin, *c = work + 2 * nwin;
-  MAU_LAUNCH(ssim_backward_kernel, dim3((unsigned)ceil_div(W, kTW), (unsigned)ceil_div(H, kTH), (unsigned)(B * C)), dim3(256), st, pred, tgt, C,
-             H, W, win, a, b, c, (float)(-1.0 / (double)nwin), upstream, grad);
+  const float coef = (float)(-1.0 / (double)nwin);
+  if (f == 1) {
+    MAU_LAUNCH(ssim_backward_kernel, dim3((unsigned)ceil_div(W, kTW), (unsigned)ceil_div(H, kTH), (unsigned)(B * C)), dim3(256), st, pred, tgt, C,
+               H, W, 0, win, a, b, c, coef, upstream, grad);
+    MAU_LAUNCHED();
+    return 0;
+  }
+  const float* xs = work + 3 * nwin;
+  const float* ys = xs + (long long)B * 2 * Hp * Wp;
+  float* gpool = const_cast<float*>(ys) + (long long)B * 2 * Hp * Wp;
+  MAU_LAUNCH(ssim_backward_kernel, dim3((unsigned)ceil_div(Wp, kTW), (unsigned)ceil_div(Hp, kTH), (unsigned)(B * 2)), dim3(256), st, xs, ys, 2,
+             Hp, Wp, 1, win, a, b, c, coef, static_cast<const float*>(nullptr), gpool);
+  MAU_LAUNCHED();
+  MAU_LAUNCH(ssim_unpool_kernel, dim3((unsigned)ceil_div(H * W, 256), (unsigned)(B * C), 1), dim3(256), st, pred, C, H, W, f, Hp, Wp,
+             static_cast<const float*>(gpool), upstream, grad);
   MAU_LAUNCHED();
   return 0;
 }

@@ -8,7 +8,7 @@
 //     ssim_loss = 1 - mean(ssim_vals)
 // piq (third party, unpinned in requirements.txt:9, absent from the build image -- parity UNPINNED) publishes the
 // algorithm of Wang et al. 2004 as: an 11 x 11 Gaussian window (sigma 1.5, normalised), 'valid' filtering
-// (no padding), k1 = 0.01, k2 = 0.03, no down-sampling while min(H, W) < 384 (factor round(min(H,W)/256)),
+// (no padding), k1 = 0.01, k2 = 0.03, images average-pooled by f = round(min(H,W)/256) first when f > 1 (min(H,W) >= 384),
 //     mu_x = G*x, mu_y = G*y, s_xx = G*x^2 - mu_x^2, s_yy = G*y^2 - mu_y^2, s_xy = G*xy - mu_x mu_y
 //     S = (2 mu_x mu_y + c1)(2 s_xy + c2) / ((mu_x^2 + mu_y^2 + c1)(s_xx + s_yy + c2)),   c1 = k1^2, c2 = k2^2
 // per-image value = mean of S over the valid window positions and over the two channels.
@@ -39,10 +39,22 @@ inline void gaussian_window(float g[kWin]) {
   for (int i = 0; i < kWin; ++i) g[i] = (float)(t[i] / s);
 }
 
-// the reference scales the NDVI channel to [0,1] and clamps the (normalised) temperature channel to [0,1]
-MAU_HD float scale_value(float v, int ch) { return ch == 0 ? (v + 1.0f) * 0.5f : fminf(fmaxf(v, 0.0f), 1.0f); }
+// the reference scales the NDVI channel to [0,1] and clamps the (normalised) temperature channel to [0,1];
+// ch == kPrescaled: the plane already holds scaled values (the average-pooled planes of large tiles)
+constexpr int kPrescaled = 2;
+MAU_HD float scale_value(float v, int ch) {
+  return ch == 0 ? (v + 1.0f) * 0.5f : (ch == 1 ? fminf(fmaxf(v, 0.0f), 1.0f) : v);
+}
 // d scale / d v  (torch.clamp passes the gradient where 0 <= v <= 1, bounds included)
-MAU_HD float scale_slope(float v, int ch) { return ch == 0 ? 0.5f : ((v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f); }
+MAU_HD float scale_slope(float v, int ch) {
+  return ch == 0 ? 0.5f : (ch == 1 ? ((v >= 0.0f && v <= 1.0f) ? 1.0f : 0.0f) : 1.0f);
+}
+// piq.ssim(downsample=True): both images are average-pooled by f = max(1, round(min(H, W) / 256)) first
+// (Python's round: half to even -- nearbyint in the default rounding mode)
+inline int pool_factor(int H, int W) {
+  const int f = (int)nearbyint((double)(H < W ? H : W) / 256.0);
+  return f < 1 ? 1 : f;
+}
 
 struct Point {
   float s;        // SSIM of the window

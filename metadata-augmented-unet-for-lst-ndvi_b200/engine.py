@@ -48,7 +48,7 @@ _lib_lock = threading.Lock()
 EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
-    "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
+    "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_wait_backward_streams", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
     "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_loss_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss", "mau_ssim_forward", "mau_ssim_backward",
     "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_cast_f32_bf16", "mau_cast_bf16_f32", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
@@ -85,6 +85,7 @@ def lib():
         L.mau_plan_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         L.mau_plan_set_grad_hook.argtypes = [C.c_void_p, GRAD_HOOK, C.c_void_p]
         L.mau_plan_set_state_version.argtypes = [C.c_void_p, C.c_uint64]
+        L.mau_plan_wait_backward_streams.argtypes = [C.c_void_p, C.c_void_p]
         L.mau_plan_buffer_ptr.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.mau_plan_set_stats_sync.argtypes = [C.c_void_p, STATS_SYNC, C.c_void_p, C.c_int]
         L.mau_plan_profile.argtypes = [C.c_void_p, C.c_int]
@@ -345,6 +346,11 @@ class Plan:
             return
         self._hook_ref = GRAD_HOOK(lambda _u, a, b: fn(a, b))
         check(lib().mau_plan_set_grad_hook(self._h, self._hook_ref, None), "set_grad_hook")
+
+    def wait_backward_streams(self, stream_ptr: int):
+        """Make the CUDA stream ``stream_ptr`` wait for the weight-gradient launches enqueued so far on the plan's own
+        second stream (data-parallel: the communication stream calls this before reducing a bucket)."""
+        check(lib().mau_plan_wait_backward_streams(self._h, C.c_void_p(stream_ptr)), "wait_backward_streams")
 
     def set_stats_sync(self, fn, world_size: int = 1):
         """SyncBN: fn(tensor) must all-reduce (SUM) the float64 device tensor in place on the current stream;

@@ -41,6 +41,7 @@ class GradReducer:
         self.comm_stream = torch.cuda.Stream(device=flat.device) if self.cuda else None
         self.launched = 0
         self.use_avg = self.cuda          # NCCL has ReduceOp.AVG; gloo does not
+        self.extra_wait = None            # callable(stream_ptr): producers that run on streams torch does not know
 
     def _launch(self, a: int, b: int):
         if self.world == 1 or b <= a:
@@ -51,6 +52,8 @@ class GradReducer:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.flat.device))
             self.comm_stream.wait_event(ev)
+            if self.extra_wait is not None:       # the plan's weight-gradient stream (engine.Plan.wait_backward_streams)
+                self.extra_wait(self.comm_stream.cuda_stream)
             with torch.cuda.stream(self.comm_stream):
                 if self.wire is None:
                     dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group)
@@ -148,6 +151,8 @@ class DataParallel:
                      "reducer": GradReducer(flat, self.group, self.bucket_numel, getattr(self, "grad_dtype", "fp32"))}
             plan._dp_cache = cache
             red = cache["reducer"]
+            if hasattr(plan, "wait_backward_streams"):
+                red.extra_wait = plan.wait_backward_streams
 
             def hook(first: int, last: int, offs=offs, red=red):
                 lo = [offs[i][0] for i in range(first, last + 1) if i in offs]
