@@ -66,6 +66,7 @@ typedef struct mau_config {
 #define MAU_FLAG_BN_FUSED      4096 /* A-B: training BatchNorm as ONE cooperative launch per direction (statistics, grid barrier,
                                       apply over the same block ranges in reverse).  Measured slower than the two plain launches
                                       (8.41 vs 8.16 ms per training step, profiles/r02_bn_fused_ab.md): off by default */
+#define MAU_FLAG_NO_CONV_STATS 16384 /* A-B: BatchNorm statistics by a separate pass over z instead of inside the convolution */
 #define MAU_FLAG_NO_WGRAD_OVERLAP 8192 /* A-B: weight-gradient kernels on the caller's stream (no second stream) */
 #define MAU_FLAG_EMB_DENSE_BWD 2048 /* debug: U-Net++ embedding planes back-propagated densely (dgrad + wgrad launches) */
 
@@ -202,7 +203,8 @@ int mau_eval_metrics(const float* maps_dev, int maps_channels, const float* pred
  * loss_dev[0] = 1 - mean SSIM over images, channels 0..1 and window positions; grad_dev (may be NULL) [B,C,H,W] =
  * d loss / d pred (zero for channels >= 2).  work_dev: mau_ssim_work_floats(B,H,W) floats of scratch, acc_dev: one double.
  * piq is a third-party dependency the reference does not pin: parity for this term is UNPINNED (see oracle/ssim_oracle.py).
- * Tiles with min(H,W) >= 384 (which piq average-pools first) are refused. */
+ * Tiles with min(H,W) >= 384 are average-pooled by f = round(min(H,W)/256) first, like piq.ssim(downsample=True) does
+ * (the app's 512 x 512 tiles: f = 2). */
 int64_t mau_ssim_work_floats(int B, int H, int W);
 int mau_ssim_loss(const float* pred_dev, const float* target_dev, int B, int C, int H, int W, float* loss_dev,
                   float* grad_dev, float* work_dev, double* acc_dev, void* stream);

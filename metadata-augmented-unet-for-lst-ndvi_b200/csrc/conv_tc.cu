@@ -276,7 +276,36 @@ struct V2Smem {
 // BRES = weights resident: when the whole packed weight tensor of the launch (9 taps x K chunks, one N tile) fits the
 // NB B stages it is loaded once per CTA instead of once per work item (the Cin <= 64, Cout <= 64 layers at 250x250:
 // 72 KB of weights against 46 KB of activations per item).
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM, bool BRES>
+// named barriers of the statistics warps (STATS): staging buffer s "full" (128 epilogue threads arrive, 64 statistics
+// threads wait) and "free" (the reverse); id 0 is __syncthreads, id 1 the epilogue's own barrier
+constexpr int kBarFull = 2, kBarFree = 4, kStatThreads = 192;
+
+// per-channel sum / sum of squares of one 64-channel group of a staged bf16 tile (rows of 128 B, 16-byte chunks XOR-swizzled
+// by row & 7): lane l owns channels 2l, 2l + 1; valid(row) masks pixels outside the image
+template <typename F>
+__device__ __forceinline__ void stat_rows(const uint8_t* tile, int row0, int row1, int lane, F&& valid, float (&s)[2], float (&q)[2]) {
+  // eight rows per iteration, all eight loads issued before the first use (a one-row-at-a-time loop is bound by the
+  // shared-memory latency and made the epilogue wait for its staging buffer); row0 and row1 are multiples of 8, so the
+  // swizzle term of row r + i is i
+  float sa[2] = {0.f, 0.f}, sb[2] = {0.f, 0.f}, qa[2] = {0.f, 0.f}, qb[2] = {0.f, 0.f};
+  const uint8_t* base = tile + (lane & 3) * 4;
+  const int c16 = lane >> 2;
+  for (int r = row0; r < row1; r += 8) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = *reinterpret_cast<const uint32_t*>(base + (r + i) * 128 + ((c16 ^ i) << 4));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t x = valid(r + i) ? w[i] : 0u;
+      const float v0 = __uint_as_float(x << 16), v1 = __uint_as_float(x & 0xffff0000u);
+      if (i & 1) { sb[0] += v0; sb[1] += v1; qb[0] = fmaf(v0, v0, qb[0]); qb[1] = fmaf(v1, v1, qb[1]); }
+      else       { sa[0] += v0; sa[1] += v1; qa[0] = fmaf(v0, v0, qa[0]); qa[1] = fmaf(v1, v1, qa[1]); }
+    }
+  }
+  s[0] = sa[0] + sb[0]; s[1] = sa[1] + sb[1]; q[0] = qa[0] + qb[0]; q[1] = qa[1] + qb[1];
+}
+
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM, bool BRES, bool STATS = false>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmY,
@@ -422,6 +451,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
       }
       buf = (buf + 1) % NBUF;
     }
+  } else if (STATS && (warp == 2 || warp == 3)) {
+    // =========================== BatchNorm statistics (training forward) ===========================
+    // Mirrors the epilogue's iteration space; reads every staged tile once while the epilogue warps work on the next.
+    constexpr int NU = BN / S::SU;                  // store rounds per 128-pixel tile
+    constexpr int NG = S::SU / 64;                  // 64-channel groups per round: warp sw takes group sw (NG == 2) or half the rows
+    const int sw = warp - 2;
+    double as[NU][2], aq[NU][2];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) { as[u][0] = as[u][1] = aq[u][0] = aq[u][1] = 0.0; }
+    auto flush = [&](int n0) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int c = n0 + u * S::SU + (NG == 2 ? sw * 64 : 0) + 2 * lane;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (c + e < p.Cout) { atomicAdd(p.stats + c + e, as[u][e]); atomicAdd(p.stats + p.Cout + c + e, aq[u][e]); }
+        as[u][0] = as[u][1] = aq[u][0] = aq[u][1] = 0.0;
+      }
+    };
+    for (int s = 0; s < NSTG; ++s) named_bar_arrive(kBarFree + s, kStatThreads);      // every staging buffer starts free
+    int stg = 0, cur_n0 = -1;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int n0 = (it / groups) * BN;
+      const int pt0 = (it % groups) * MT;
+      const int nsub = min(MT, total_pt - pt0);
+      if (n0 != cur_n0) { if (cur_n0 >= 0) flush(cur_n0); cur_n0 = n0; }
+      for (int j = 0; j < nsub; ++j) {
+        const int pt = pt0 + j;
+        const int b = pt / tiles_img;
+        const int rem = pt - b * tiles_img;
+        const int th = rem / p.tiles_w;
+        const int w0 = (rem - th * p.tiles_w) * 8, h0 = th * 16;
+        auto valid = [&](int r) { return h0 + (r >> 3) < p.H && w0 + (r & 7) < p.W; };
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          named_bar_sync(kBarFull + stg, kStatThreads);
+          const uint8_t* tile = sStg + stg * S::STG + (NG == 2 ? sw * 16384 : 0);
+          float s2[2], q2[2];
+          stat_rows(tile, NG == 2 ? 0 : sw * 64, NG == 2 ? 128 : sw * 64 + 64, lane, valid, s2, q2);
+          named_bar_arrive(kBarFree + stg, kStatThreads);
+          as[u][0] += (double)s2[0]; as[u][1] += (double)s2[1]; aq[u][0] += (double)q2[0]; aq[u][1] += (double)q2[1];
+          stg = (stg + 1) % NSTG;
+        }
+      }
+    }
+    if (cur_n0 >= 0) flush(cur_n0);
   } else if (warp >= 4) {
     // =========================== epilogue ===========================
     const int et = threadIdx.x - 128;
@@ -466,6 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
             if (et == 0) { if (NSTG == 1) tma_wait_group_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
             named_bar_sync(1, 128);
           }
+          if constexpr (STATS) named_bar_sync(kBarFree + stg, kStatThreads);   // the statistics warps have read this buffer
           // TMEM -> registers is double-buffered: the load of column block cb + 1 is in flight while block cb is
           // converted and staged.  Per-channel affine: mode 0 = none (data gradient), 1 = + shift (training forward:
           // bias), 2 = * scale + shift (eval: folded BatchNorm); coefficients are read as float4 broadcasts.
@@ -533,6 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
             }
           }
           if (last) tc_fence_before();   // all TMEM reads of this buffer are complete (wait::ld above)
+          if constexpr (STATS) named_bar_arrive(kBarFull + stg, kStatThreads);   // this thread's part of the tile is staged
           if (p.store_y) fence_proxy_async_smem();
           if (p.store_y || last) named_bar_sync(1, 128);
           if (et == 0) {
@@ -576,14 +653,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
   }
 }
 
-template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM, bool BRES = false>
+template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM, bool BRES = false, bool STATS = false>
 int launch_v2(const ConvTcOp& op, cudaStream_t st) {
   using S = V2Smem<BN, MT, NBUF, NA, NB, NSTG>;
   static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES>;
+  auto kern = conv3x3_tc_v2_kernel<BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES, STATS>;
   if (!attr_done[dev & 15]) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
@@ -617,7 +694,7 @@ struct V3Smem {
                                    (2 + 4) * 64 * sizeof(float);
 };
 
-template <int NA, int NB, int EM>
+template <int NA, int NB, int EM, bool STATS = false>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmY,
@@ -734,6 +811,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __gr
       }
       buf ^= 1;
     }
+  } else if (STATS && (warp == 2 || warp == 3)) {
+    // =========================== BatchNorm statistics (training forward) ===========================
+    // the staged tile is the packed 8 x 14 block of valid outputs (112 rows of 64 channels); the two warps split the rows
+    const int sw = warp - 2;
+    double as[2] = {0.0, 0.0}, aq[2] = {0.0, 0.0};
+    for (int s = 0; s < 2; ++s) named_bar_arrive(kBarFree + s, kStatThreads);
+    int stg = 0;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int b = it / tiles_img;
+      const int rem = it - b * tiles_img;
+      const int th = rem / p.tiles_w;
+      const int w0 = (rem - th * p.tiles_w) * 14, h0 = th * 8;
+      auto valid = [&](int r) { const int hr = r / 14; return h0 + hr < p.H && w0 + (r - hr * 14) < p.W; };
+      named_bar_sync(kBarFull + stg, kStatThreads);
+      float s2[2], q2[2];
+      stat_rows(sStg + stg * kC3Stg, sw * 56, sw * 56 + 56, lane, valid, s2, q2);
+      named_bar_arrive(kBarFree + stg, kStatThreads);
+      as[0] += (double)s2[0]; as[1] += (double)s2[1]; aq[0] += (double)q2[0]; aq[1] += (double)q2[1];
+      stg ^= 1;
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (2 * lane + e < p.Cout) { atomicAdd(p.stats + 2 * lane + e, as[e]); atomicAdd(p.stats + p.Cout + 2 * lane + e, aq[e]); }
   } else if (warp >= 4) {
     // =========================== epilogue ===========================
     const int et = threadIdx.x - 128;
@@ -765,6 +865,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __gr
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         named_bar_sync(1, 128);
       }
+      if constexpr (STATS) named_bar_sync(kBarFree + stg, kStatThreads);    // the statistics warps have read this buffer
       float hacc[kHeadOC] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 192;
 #pragma unroll 1
@@ -817,6 +918,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __gr
         }
       }
       tc_fence_before();
+      if constexpr (STATS) named_bar_arrive(kBarFull + stg, kStatThreads);
       if (p.store_y) fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (et == 0) {
@@ -851,14 +953,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __gr
   }
 }
 
-template <int NA, int NB, int EM>
+template <int NA, int NB, int EM, bool STATS = false>
 int launch_col3(const ConvTcOp& op, cudaStream_t st) {
   using S = V3Smem<NA, NB>;
   static_assert(S::kBytes <= 232448, "shared memory budget exceeded");
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = conv3x3_tc_col3_kernel<NA, NB, EM>;
+  auto kern = conv3x3_tc_col3_kernel<NA, NB, EM, STATS>;
   if (!attr_done[dev & 15]) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
@@ -1083,12 +1185,14 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
     if (op.bn == BN_ && op.mt == MT_ && op.nbuf == NBUF_) {                                             \
       if (op.p.bt) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, true, 0>(op, st);                 \
       if (em == 0) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 0>(op, st);                \
+      if (em == 1 && op.p.stats) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 1, false, true>(op, st); \
       if (em == 1) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 1>(op, st);                \
       if (em == 2) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 2>(op, st);                \
       if constexpr (BN_ <= 128) return launch_v2<BN_, MT_, NBUF_, NA_, NB_, NSTG_, false, 3>(op, st);   \
     }
     if (op.col3) {          // Cout == 64: three horizontal taps folded into N = 192
       if (em == 0) return launch_col3<3, 4, 0>(op, st);
+      if (em == 1 && op.p.stats) return launch_col3<3, 4, 1, true>(op, st);
       if (em == 1) return launch_col3<3, 4, 1>(op, st);
       if (em == 2) return launch_col3<3, 4, 2>(op, st);
       return launch_col3<3, 4, 3>(op, st);
@@ -1096,6 +1200,7 @@ int conv_tc_launch(const ConvTcOp& op, cudaStream_t st) {
     if (op.bres) {          // 64-wide, K = 64: weights resident in 9 B stages, MT = 2
       if (op.p.bt) return launch_v2<64, 2, 2, 2, 9, 2, true, 0, true>(op, st);
       if (em == 0) return launch_v2<64, 2, 2, 2, 9, 2, false, 0, true>(op, st);
+      if (em == 1 && op.p.stats) return launch_v2<64, 2, 2, 2, 9, 2, false, 1, true, true>(op, st);
       if (em == 1) return launch_v2<64, 2, 2, 2, 9, 2, false, 1, true>(op, st);
       if (em == 2) return launch_v2<64, 2, 2, 2, 9, 2, false, 2, true>(op, st);
       return launch_v2<64, 2, 2, 2, 9, 2, false, 3, true>(op, st);

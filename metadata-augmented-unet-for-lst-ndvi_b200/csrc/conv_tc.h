@@ -26,6 +26,10 @@ struct ConvTcParams {
   int head_oc = 0, head_tanh = 0, H = 0, W = 0;
   int store_y = 1;               // 0: skip the activation store (only the fused head output is needed)
   int bt = 0, bt_col0 = 0;       // data gradient: B read MN-major from the forward weight pack, first packed column
+  // training forward: per-channel sum / sum of squares of the STORED (bf16-rounded) output, accumulated by the two
+  // otherwise idle warps from the staging tile while the epilogue warps convert the next one: double[2 * Cout], zeroed
+  // by the caller (replaces the separate bn_stats pass over z)
+  double* stats = nullptr;
 };
 
 struct ConvTcOp {

@@ -132,6 +132,7 @@ int op_laplacian_sums(const float* pred, const float* tgt, int B, int C, int H, 
 // SSIM term of the training loss (src/utils/losses.py:72-95): loss[0] = 1 - mean SSIM, grad = d loss / d pred (or null);
 // work holds ssim_work_floats(B, H, W) floats, acc one double
 long long ssim_work_floats(int B, int H, int W);
+void ssim_debug_force_pool(int f);     // tests: force piq's average-pool factor (0 = piq's rule, f = round(min(H,W)/256))
 int op_ssim_loss(const float* pred, const float* tgt, int B, int C, int H, int W, float* loss, float* grad, float* work,
                  double* acc, cudaStream_t st);
 // the two halves separately (autograd): forward leaves the derivative maps in work; backward multiplies the nullable

@@ -28,7 +28,7 @@ Plan::~Plan() {
   if (!dry) {
     for (void* p : allocs) cudaFree(p);
   }
-  for (ConvLayer* L : layers) delete L;
+  for (ConvLayer* L : layers) { if (L->ev_pack) cudaEventDestroy(L->ev_pack); delete L; }
 }
 
 void* Plan::alloc(size_t bytes) {
@@ -202,7 +202,9 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
   const long long count = (long long)L->B * L->H * L->W;
   op.run = [this, L, training, count](Ctx& c) -> int {
     const int C = L->Cout;
-    if (!skip_pack) {
+    if (packs_ahead) {
+      MAU_CUDA(cudaStreamWaitEvent(c.st, L->ev_pack, 0));      // packed by run_forward on the second stream
+    } else if (!skip_pack) {
       if (use_tc) MAU_TRY(conv_tc_pack_fwd(c.f(L->iw), C, L->Cin, L->kmap, L->Kp, L->wpack, c.st));
       else MAU_TRY(conv_ffma_pack_fwd(c.f(L->iw), C, L->Cin, L->kmap, L->Kp, static_cast<float*>(L->wpack), c.st));
     }
@@ -213,7 +215,12 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
                                 L->scale, L->shift, c.st));
       scale = L->scale; shift = L->shift; relu = 1;
     }
+    // training, tcgen05 halo kernels: the BatchNorm statistics are accumulated by the convolution itself (idle warps read
+    // each staged output tile), so z is not read again by a separate bn_stats pass
+    const bool fused_stats = training && use_tc && conv_mode == MODE_HALO && conv_stats;
+    if (training) MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
     if (use_tc) {
+      L->tc.p.stats = fused_stats ? L->sums : nullptr;
       L->tc.p.scale = scale; L->tc.p.shift = shift; L->tc.p.relu = relu;
       if (L->head_w >= 0) {       // fused 1x1 head: the activation itself is never stored
         L->tc.p.head_w = c.f(L->head_w); L->tc.p.head_b = c.f(L->head_b); L->tc.p.head_out = c.out;
@@ -232,13 +239,12 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
       const View z = whole(L->zbuf);
       // (statistics fused into the conv epilogue were measured and dropped: the column-sum pass over the staged
       //  tile lengthens the epilogue of the narrow layers by more than this separate 63 %-of-HBM-peak pass costs)
-      MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
-      if (!sync_fn && bn_fused) {
+      if (!sync_fn && bn_fused && !fused_stats) {
         // statistics + normalise + ReLU in one cooperative launch (second read of z from L2)
         MAU_TRY(op_bn_fwd_fused(dt, z, L->sums, bn_bar, &bn_bar_count, count, c.f(L->igamma), c.f(L->ibeta), kBnEps, kBnMomentum,
                                 c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, view(L->out), c.st));
       } else {
-        MAU_TRY(op_bn_stats(dt, z, L->sums, c.st));
+        if (!fused_stats) MAU_TRY(op_bn_stats(dt, z, L->sums, c.st));
         if (sync_fn) sync_fn(sync_user, L->sums, 2 * C);       // SyncBN: sum / sum-of-squares over all ranks
         MAU_TRY(op_bn_finalize_apply_relu(dt, z, L->sums, count * sync_world, c.f(L->igamma), c.f(L->ibeta), kBnEps, kBnMomentum,
                                           c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, view(L->out), c.st));
@@ -993,6 +999,7 @@ int Plan::build() {
   if (cfg.training) {
     bn_fused = (cfg.flags & MAU_FLAG_BN_FUSED) != 0;
     overlap_wgrad = !(cfg.flags & MAU_FLAG_NO_WGRAD_OVERLAP);
+    conv_stats = !(cfg.flags & MAU_FLAG_NO_CONV_STATS);
     bn_bar = static_cast<unsigned*>(alloc(sizeof(unsigned) * 4));      // zeroed; only ever counts up
     if (!dry && !bn_bar) return -1;
     if (use_tc && !(cfg.flags & MAU_FLAG_WGRAD_V1)) {
@@ -1076,6 +1083,20 @@ static int run_ops(Plan* P, std::vector<Op>& ops, Ctx& c, bool backward) {
 
 int Plan::run_forward(Ctx& c) {
   skip_pack = !cfg.training && state_version != 0 && state_version == packed_version && packed_state == last_state;
+  packs_ahead = false;
+  if (cfg.training && overlap_wgrad && !profiling) {
+    // training re-packs every weight tensor every step (the optimizer has just changed them): all 18 / 30 pack launches go
+    // to the second stream up front and hide behind the first convolutions; each convolution waits for its own event
+    cudaStream_t ws;
+    MAU_TRY(w_fork(c, &ws));
+    for (ConvLayer* L : layers) {
+      if (!L->ev_pack) MAU_CUDA(cudaEventCreateWithFlags(&L->ev_pack, cudaEventDisableTiming));
+      if (use_tc) MAU_TRY(conv_tc_pack_fwd(c.f(L->iw), L->Cout, L->Cin, L->kmap, L->Kp, L->wpack, ws));
+      else MAU_TRY(conv_ffma_pack_fwd(c.f(L->iw), L->Cout, L->Cin, L->kmap, L->Kp, static_cast<float*>(L->wpack), ws));
+      MAU_CUDA(cudaEventRecord(L->ev_pack, ws));
+    }
+    packs_ahead = true;
+  }
   MAU_TRY(run_ops(this, fwd, c, false));
   MAU_TRY(side_join(c));
   if (!cfg.training) { packed_version = state_version; packed_state = last_state; }

@@ -78,6 +78,7 @@ struct ConvLayer {
   WgradTcOp wg[4];
   int wg_swap = 0;          // wgrad v2 orientation (see wgrad_tc.cu)
   int emb_seg = -1;         // input segment that is constant over space (U-Net++ embedding planes): backward in closed form
+  cudaEvent_t ev_pack = nullptr;   // training: this layer's weight pack (launched ahead on the second stream) is complete
 };
 
 class Plan {
@@ -114,6 +115,7 @@ class Plan {
   unsigned long long state_version = 0, packed_version = 0;
   std::vector<void*> packed_state;
   bool skip_pack = false;
+  bool packs_ahead = false;  // this forward's weight packs were launched ahead on the second stream (training)
   bool shared = false;       // MAU_FLAG_SHARED_MAPS: encoder and LSTM run once, results broadcast over the batch
   double exec_flops = 0;     // FLOPs the convolution kernels execute per forward (== fwd conv FLOPs unless shared)
   double exec_bwd_flops = 0; // FLOPs the dgrad + wgrad kernels execute per backward (dense minus closed-form segments)
@@ -154,6 +156,7 @@ class Plan {
   // on with the data gradient and the NEXT layer's bandwidth-bound BatchNorm / pool / bilinear backward, which then
   // share the SMs with the tensor-bound wgrad kernel instead of waiting for it.  Joined at the end of backward (and
   // by mau_plan_wait_backward_streams for a data-parallel bucket).  Off while profiling (per-op times stay additive).
+  bool conv_stats = true;           // training forward: BatchNorm statistics accumulated inside the convolution kernel
   bool overlap_wgrad = true;
   cudaStream_t wst = nullptr; cudaEvent_t ev_w_fork = nullptr, ev_w_join = nullptr; bool w_pending = false;
   int w_fork(Ctx& c, cudaStream_t* out);

@@ -184,5 +184,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// producer side of a named barrier: counts this thread in without waiting (the consumers bar.sync on the same id)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 }}  // namespace mau::ptx

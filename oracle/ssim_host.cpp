@@ -50,3 +50,5 @@ extern "C" int ssim_host(const float* pred, const float* tgt, int B, int C, int 
   }
   return 0;
 }
+
+extern "C" int ssim_pool_factor(int H, int W) { return mau_ssim::pool_factor(H, W); }

@@ -10,3 +10,4 @@ extern "C" int emu_ssim_loss(const float* pred, const float* tgt, int B, int C, 
                              double* acc) {
   return mau::op_ssim_loss(pred, tgt, B, C, H, W, loss, grad, work, acc, nullptr);
 }
+extern "C" void emu_ssim_force_pool(int f) { mau::ssim_debug_force_pool(f); }

@@ -31,10 +31,11 @@ def gaussian_window(kernel_size: int = 11, sigma: float = 1.5) -> torch.Tensor:
 
 
 def ssim(x: torch.Tensor, y: torch.Tensor, kernel_size: int = 11, kernel_sigma: float = 1.5, data_range: float = 1.0,
-         k1: float = 0.01, k2: float = 0.03, downsample: bool = True) -> torch.Tensor:
-    """Per-image SSIM, [B] (piq.ssim(..., reduction='none'))."""
+         k1: float = 0.01, k2: float = 0.03, downsample: bool = True, force_pool: int = 0) -> torch.Tensor:
+    """Per-image SSIM, [B] (piq.ssim(..., reduction='none')).  ``force_pool`` (tests only) replaces piq's factor
+    f = max(1, round(min(H, W) / 256)) so that the pooled path can be exercised on small tiles."""
     x, y = x / float(data_range), y / float(data_range)
-    f = max(1, round(min(x.shape[-2:]) / 256))
+    f = force_pool if force_pool > 0 else max(1, round(min(x.shape[-2:]) / 256))
     if f > 1 and downsample:
         x, y = F.avg_pool2d(x, kernel_size=f), F.avg_pool2d(y, kernel_size=f)
     if x.shape[-1] < kernel_size or x.shape[-2] < kernel_size:
@@ -53,11 +54,11 @@ def ssim(x: torch.Tensor, y: torch.Tensor, kernel_size: int = 11, kernel_sigma: 
     return ss.mean(dim=(-1, -2)).mean(1)
 
 
-def ssim_loss(outputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+def ssim_loss(outputs: torch.Tensor, targets: torch.Tensor, force_pool: int = 0) -> torch.Tensor:
     """``1 - mean(ssim(scaled outputs, scaled targets))`` exactly as src/utils/losses.py:72-90 builds it."""
     t = torch.stack([(targets[:, 0] + 1.0) / 2.0, torch.clamp(targets[:, 1], 0.0, 1.0)], dim=1)
     o = torch.stack([(outputs[:, 0] + 1.0) / 2.0, torch.clamp(outputs[:, 1], 0.0, 1.0)], dim=1)
-    return 1 - ssim(o, t, data_range=1.0).mean()
+    return 1 - ssim(o, t, data_range=1.0, force_pool=force_pool).mean()
 
 
 def compute_loss_l1_grad_ssim(outputs, targets, lambda_grad=0.1, lambda_ssim=0.5):

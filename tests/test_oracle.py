@@ -161,6 +161,9 @@ def test_ssim_core_arithmetic_equals_torch_autograd(tmp_path):
             assert not grad[:, 2:].any() and not gref[:, 2:].any()      # only channels 0 and 1 enter the SSIM term
     x = torch.rand(1, 2, 20, 20, generator=g)
     assert abs(float(S.ssim_loss(x, x))) < 1e-6                          # identical maps: SSIM = 1
+    L.ssim_pool_factor.restype = C.c_int                                  # piq: f = max(1, round(min(H, W) / 256)), Python's half-to-even round
+    for m in list(range(11, 1300, 7)) + [383, 384, 385, 512, 639, 640, 641, 896, 1152]:
+        assert L.ssim_pool_factor(m, m + 3) == max(1, round(m / 256)), m
     assert L.ssim_host(o.ctypes.data, t.ctypes.data, 1, 1, 20, 20, C.byref(lv), None) == 1     # needs both channels
 
 
@@ -202,10 +205,32 @@ def test_ssim_kernel_source_under_cpu_emulation_equals_torch_autograd(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert d["ok"] and len(d["cases"]) == 5 and all(c["ok"] for c in d["cases"]), d
-    # argument checks of the op: one channel only, tile smaller than the window, tile piq would down-sample first
-    z = np.zeros((1, 2, 400, 400), np.float32)
-    for shp in ((1, 1, 20, 20), (1, 2, 10, 30), (1, 2, 400, 400)):
+    # argument checks of the op: one channel only, tile smaller than the window
+    z = np.zeros((1, 2, 40, 40), np.float32)
+    for shp in ((1, 1, 20, 20), (1, 2, 10, 30)):
         assert L.emu_ssim_loss(z.ctypes.data, z.ctypes.data, *shp, lv.ctypes.data, None, work.ctypes.data, acc.ctypes.data) != 0
+    # piq average-pools tiles with min(H, W) >= 384 by f = round(min / 256) before the SSIM (the app's 512 x 512 tiles: f = 2);
+    # the pooled path (pool -> SSIM on the pooled planes -> un-pool with the scaling's chain rule) is exercised on small
+    # tiles by forcing the factor, odd extents included (avg_pool2d drops the last row / column)
+    for f, shape in ((2, (2, 2, 45, 52)), (3, (1, 3, 40, 47))):
+        L.emu_ssim_force_pool(f)
+        try:
+            out = (torch.randn(shape, generator=g) * 0.7).requires_grad_(True)
+            tgt = torch.randn(shape, generator=g) * 0.7
+            loss = S.ssim_loss(out, tgt, force_pool=f)
+            loss.backward()
+            o, t = out.detach().contiguous().numpy(), tgt.contiguous().numpy()
+            n = L.emu_ssim_work_floats(shape[0], shape[2], shape[3])
+            work, acc = np.full(n, np.nan, np.float32), np.full(1, np.nan, np.float64)
+            lv, grad = np.full(1, np.nan, np.float32), np.full_like(o, np.nan)
+            assert L.emu_ssim_loss(o.ctypes.data, t.ctypes.data, *shape, lv.ctypes.data, grad.ctypes.data, work.ctypes.data, acc.ctypes.data) == 0
+            gref = out.grad.numpy()
+            assert not np.isnan(grad).any()
+            assert abs(float(lv[0]) - float(loss.detach())) < 1e-6
+            assert np.abs(grad - gref).max() < 2e-5 * np.abs(gref).max()
+        finally:
+            L.emu_ssim_force_pool(0)
+
 
 
 def test_emulation_shim_reproduces_kernels_that_are_verified_on_hardware(tmp_path):

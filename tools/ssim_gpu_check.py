@@ -18,7 +18,7 @@ from oracle import ssim_oracle as S  # noqa: E402
 def main():
     cases, ok = [], True
     g = torch.Generator().manual_seed(0)
-    for shape in ((2, 2, 23, 31), (1, 2, 11, 11), (3, 2, 40, 17), (2, 3, 30, 30), (16, 2, 250, 250)):
+    for shape in ((2, 2, 23, 31), (1, 2, 11, 11), (3, 2, 40, 17), (2, 3, 30, 30), (16, 2, 250, 250), (2, 2, 512, 512), (1, 2, 385, 400)):
         out = torch.randn(shape, generator=g) * 0.7
         tgt = torch.randn(shape, generator=g) * 0.7
         tgt[:, 0] = tgt[:, 0].clamp(-1, 1)
