@@ -243,7 +243,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if args.comm_ctas is None:
-        args.comm_ctas = 4 if world <= 2 else 8
+        args.comm_ctas = 8      # measured at N=2 (profiles/r02_multi_gpu.md): 7.20 ms per step with 8 CTAs, 7.50 with 4
     if world > 1:
         # the gradient all-reduce of the training configs runs concurrently with the persistent conv / wgrad kernels:
         # cap NCCL's CTA count (and, per training measurement, leave that many SMs out of our persistent grids)
@@ -510,6 +510,12 @@ def main():
         for cid in (1, 4, 5):
             r = measure(cid, max(5, steps // 2), 3, False)
             out["riders"][f"config{cid}"] = {k: r[k] for k in keep}
+        # config 3 once more with the reference's DEFAULT criterion (conf/config.yaml:42 `l1-gradient-ssim`: L1 + 0.1 gradient
+        # difference + 0.5 (1 - SSIM), src/utils/losses.py:59-99) instead of the plain L1 the headline line uses
+        crit, args.criterion = args.criterion, "l1-gradient-ssim"
+        r = measure(3, max(5, steps // 2), 3, False, with_e2e=False)
+        args.criterion = crit
+        out["riders"]["config3_l1_gradient_ssim"] = {k: r[k] for k in keep + ("criterion",)}
     if rank == 0:
         emit(out)
     if world > 1:

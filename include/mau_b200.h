@@ -63,9 +63,6 @@ typedef struct mau_config {
 #define MAU_FLAG_HALO_BASEOFF  256 /* debug: halo main loop fills the UMMA descriptor base_offset   */
 #define MAU_FLAG_CONV_ROW3     512 /* debug: three-row-box conv main loop instead of the halo kernel */
 #define MAU_FLAG_WGRAD_V1      1024 /* debug: first-generation weight-gradient kernel (fp32 atomics)   */
-#define MAU_FLAG_BN_FUSED      4096 /* A-B: training BatchNorm as ONE cooperative launch per direction (statistics, grid barrier,
-                                      apply over the same block ranges in reverse).  Measured slower than the two plain launches
-                                      (8.41 vs 8.16 ms per training step, profiles/r02_bn_fused_ab.md): off by default */
 #define MAU_FLAG_NO_CONV_STATS 16384 /* A-B: BatchNorm statistics by a separate pass over z instead of inside the convolution */
 #define MAU_FLAG_NO_WGRAD_OVERLAP 8192 /* A-B: weight-gradient kernels on the caller's stream (no second stream) */
 #define MAU_FLAG_EMB_DENSE_BWD 2048 /* debug: U-Net++ embedding planes back-propagated densely (dgrad + wgrad launches) */

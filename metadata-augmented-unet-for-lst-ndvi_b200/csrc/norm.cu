@@ -155,193 +155,6 @@ __device__ __forceinline__ void bn_coeffs(const double* __restrict__ sums, int C
   rstd = rsqrtf(var + eps);
 }
 
-// the same from sums other blocks of THIS launch have just accumulated: read through L2 (ld.global.cg), never L1 / nc
-__device__ __forceinline__ void bn_coeffs_cg(const double* sums, int C, int c, double inv_n, float eps, float& mean, float& var,
-                                             float& rstd) {
-  const double m = __ldcg(sums + c) * inv_n;
-  double v = __ldcg(sums + C + c) * inv_n - m * m;
-  if (v < 0.0) v = 0.0;
-  mean = (float)m;
-  var = (float)v;
-  rstd = rsqrtf(var + eps);
-}
-
-// ---- grid-wide barrier of a cooperative launch (all blocks co-resident).  `bar` only ever counts up: the host passes
-// the value it must reach (arrivals of all earlier launches + this grid), so it is never reset.  A bounded spin: if the
-// co-residency assumption were ever violated the kernel finishes with wrong numbers (caught by the parity tests)
-// instead of hanging the GPU.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    unsigned v, spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      if ((int)(v - target) >= 0) break;
-      __nanosleep(40);
-    } while (++spins < (1u << 26));
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// block-contiguous pixel ranges, shared by both phases of the fused kernels: block b owns [p0, p1)
-__device__ __forceinline__ void block_range(long long npix, long long& p0, long long& p1) {
-  const long long per = (npix + gridDim.x - 1) / gridDim.x;
-  p0 = blockIdx.x * per;
-  p1 = p0 + per < npix ? p0 + per : npix;
-  if (p0 > npix) p0 = npix;
-}
-
-// Training-mode BatchNorm + ReLU forward in ONE cooperative launch: (1) per-channel sum / sum of squares of z over the
-// block's own pixel range (ascending), grid barrier, (2) y = relu(z * scale + shift) over the same range DESCENDING.
-// All blocks sweep their ranges in lockstep, so the lines phase 2 asks for first are the ones phase 1 touched last:
-// the second read of z is served by the 126 MB L2 (completely for tensors <= ~60 MB, about half for the 128 MB
-// tensors of the 250x250 layers) instead of HBM, and the small late layers pay one launch latency instead of two.
-template <typename T>
-__global__ void __launch_bounds__(256) bn_fwd_fused_kernel(DView z, double* sums, unsigned* bar, unsigned target, long long count,
-                                                           double inv_n, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float eps, float momentum,
-                                                           float* __restrict__ rm, float* __restrict__ rv,
-                                                           float* __restrict__ scale_out, float* __restrict__ shift_out,
-                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out, DView y) {
-  using Raw = typename V8<T>::Raw;
-  const long long npix = (long long)z.B * z.H * z.W;
-  channel_reduce<T, 2, 1>(z, z, npix, sums, [&](long long, int, const float (&v)[8], const float (&)[8], float (&acc)[2][8]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { acc[0][k] += v[k]; acc[1][k] = fmaf(v[k], v[k], acc[1][k]); }
-  });
-  grid_barrier(bar, target);
-  const int C = z.C;
-  if (blockIdx.x == 0) {
-    const float unbias = count > 1 ? (float)((double)count / ((double)count - 1.0)) : 1.f;
-    for (int c = threadIdx.x; c < C; c += 256) {
-      float mean, var, rstd;
-      bn_coeffs_cg(sums, C, c, inv_n, eps, mean, var, rstd);
-      const float sc = gamma[c] * rstd;
-      scale_out[c] = sc;
-      shift_out[c] = beta[c] - mean * sc;
-      mean_out[c] = mean;
-      rstd_out[c] = rstd;
-      rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
-      rv[c] = (1.f - momentum) * rv[c] + momentum * (var * unbias);
-    }
-  }
-  const int G = C / 8;
-  const int L = 256 / G;
-  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
-  if (pl >= L) return;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = gi * 8 + k;
-    float mean, var, rstd;
-    bn_coeffs_cg(sums, C, c, inv_n, eps, mean, var, rstd);
-    sc[k] = gamma[c] * rstd;
-    sh[k] = beta[c] - mean * sc[k];
-  }
-  long long p0, p1;
-  block_range(npix, p0, p1);
-  const long long n_my = p1 - p0;
-  for (long long base = pl; base < n_my; base += (long long)kU * L) {
-    Raw r[kU];
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const long long idx = base + (long long)u * L;
-      if (idx < n_my) r[u] = V8<T>::load_raw(at<T>(z, p1 - 1 - idx, gi * 8));
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const long long idx = base + (long long)u * L;
-      if (idx < n_my) {
-        float v[8];
-        V8<T>::unpack(r[u], v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
-        V8<T>::store(at<T>(y, p1 - 1 - idx, gi * 8), v);
-      }
-    }
-  }
-}
-
-// Training-mode BatchNorm + ReLU backward in ONE cooperative launch: (1) sum g~, sum g~ * xhat over the block's range,
-// grid barrier, (2) dz over the same range descending (second read of gy / z from L2, see bn_fwd_fused_kernel); dz may
-// alias z.  The statistics of the forward (mean, rstd, scale, shift) come from the forward launch.
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(DView gy, DView z, const float* __restrict__ scale,
-                                                           const float* __restrict__ shift, const float* __restrict__ gamma,
-                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                           double* sums, unsigned* bar, unsigned target, long long count, DView dz,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           float* __restrict__ dbias) {
-  using Raw = typename V8<T>::Raw;
-  const long long npix = (long long)z.B * z.H * z.W;
-  const int C = z.C;
-  const int G = C / 8;
-  const int L = 256 / G;
-  const int gi = threadIdx.x % G, pl = threadIdx.x / G;
-  const int gi8 = gi * 8;
-  float cm[8], cr[8], sc[8], sh[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { cm[k] = mean[gi8 + k]; cr[k] = rstd[gi8 + k]; sc[k] = scale[gi8 + k]; sh[k] = shift[gi8 + k]; }
-  channel_reduce<T, 2, 2>(gy, z, npix, sums, [&](long long, int, const float (&g)[8], const float (&zz)[8], float (&acc)[2][8]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gt = fmaf(zz[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
-      const float xh = (zz[k] - cm[k]) * cr[k];
-      acc[0][k] += gt;
-      acc[1][k] = fmaf(gt, xh, acc[1][k]);
-    }
-  });
-  grid_barrier(bar, target);
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += 256) {
-      if (dbeta) dbeta[c] = (float)__ldcg(sums + c);
-      if (dgamma) dgamma[c] = (float)__ldcg(sums + C + c);
-      if (dbias) dbias[c] = 0.f;
-    }
-  }
-  if (pl >= L) return;
-  const float inv_n = 1.f / (float)count;
-  float ca[8], m1[8], m2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    ca[k] = gamma[gi8 + k] * cr[k];
-    m1[k] = (float)__ldcg(sums + gi8 + k) * inv_n; m2[k] = (float)__ldcg(sums + C + gi8 + k) * inv_n;
-  }
-  long long p0, p1;
-  block_range(npix, p0, p1);
-  const long long n_my = p1 - p0;
-  for (long long base = pl; base < n_my; base += (long long)kU * L) {
-    Raw rg[kU], rz[kU];
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const long long idx = base + (long long)u * L;
-      if (idx < n_my) {
-        rg[u] = V8<T>::load_raw(at<T>(gy, p1 - 1 - idx, gi8));
-        rz[u] = V8<T>::load_raw(at<T>(z, p1 - 1 - idx, gi8));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const long long idx = base + (long long)u * L;
-      if (idx < n_my) {
-        float g[8], zz[8], o[8];
-        V8<T>::unpack(rg[u], g);
-        V8<T>::unpack(rz[u], zz);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float gt = fmaf(zz[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
-          const float xh = (zz[k] - cm[k]) * cr[k];
-          o[k] = ca[k] * (gt - m1[k] - xh * m2[k]);
-        }
-        V8<T>::store(at<T>(dz, p1 - 1 - idx, gi8), o);
-      }
-    }
-  }
-}
-
 // training forward, one launch: every thread derives mean / rstd / scale / shift of its 8 channels from the
 // (already all-reduced, if SyncBN) double sums; block 0 also writes the saved statistics for the backward and
 // performs the running-stat update (momentum, unbiased variance) -- then the normalise + ReLU pass.
@@ -566,61 +379,6 @@ int op_bn_finalize_apply_relu(int dt, const View& z, const double* sums, long lo
   MAU_LAUNCHED();
   return 0;
 }
-// ---- cooperative launches --------------------------------------------------------------------------------------------
-// grid = (SMs the persistent kernels may use) x (resident blocks per SM, at most 2), never more blocks than pixels / 64
-template <typename K>
-static int coop_blocks(K kern, size_t smem, long long npix, int C) {
-  static int occ_cache[8] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) return 0;
-  (void)occ_cache;
-  const int L = std::max(1, 256 / (C / 8));
-  long long want = npix / ((long long)L * 16);
-  if (want < 1) want = 1;
-  const long long cap = (long long)sm_budget() * std::min(occ, 2);
-  return (int)std::min(want, cap);
-}
-
-int op_bn_fwd_fused(int dt, const View& z, double* sums, unsigned* bar, unsigned* bar_count, long long count, const float* gamma,
-                    const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                    float* save_mean, float* save_rstd, const View& y, cudaStream_t st) {
-  if (!vec_ok(z) || !vec_ok(y) || z.C != y.C || z.pixels() != y.pixels()) return fail("bn_fwd_fused: bad views");
-  const size_t smem = 2 * 256 * 8 * sizeof(float);
-  void* kern = dt == DT_BF16 ? (void*)bn_fwd_fused_kernel<__nv_bfloat16> : (void*)bn_fwd_fused_kernel<float>;
-  const int blocks = dt == DT_BF16 ? coop_blocks(bn_fwd_fused_kernel<__nv_bfloat16>, smem, z.pixels(), z.C)
-                                   : coop_blocks(bn_fwd_fused_kernel<float>, smem, z.pixels(), z.C);
-  if (blocks < 1) return fail("bn_fwd_fused: occupancy query failed");
-  *bar_count += (unsigned)blocks;
-  unsigned target = *bar_count;
-  DView dz_ = dv(z), dy_ = dv(y);
-  double inv_n = 1.0 / (double)count;
-  void* args[] = {&dz_, &sums, &bar, &target, &count, &inv_n, &gamma, &beta, &eps, &momentum, &running_mean, &running_var,
-                  &scale, &shift, &save_mean, &save_rstd, &dy_};
-  MAU_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, smem, st));
-  MAU_LAUNCHED();
-  return 0;
-}
-
-int op_bn_bwd_fused(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* gamma,
-                    const float* mean, const float* rstd, double* sums, unsigned* bar, unsigned* bar_count, long long count,
-                    const View& dz_out, float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
-  if (!vec_ok(z) || !vec_ok(gy) || !vec_ok(dz_out)) return fail("bn_bwd_fused: bad views");
-  const size_t smem = 2 * 256 * 8 * sizeof(float);
-  void* kern = dt == DT_BF16 ? (void*)bn_bwd_fused_kernel<__nv_bfloat16> : (void*)bn_bwd_fused_kernel<float>;
-  const int blocks = dt == DT_BF16 ? coop_blocks(bn_bwd_fused_kernel<__nv_bfloat16>, smem, z.pixels(), z.C)
-                                   : coop_blocks(bn_bwd_fused_kernel<float>, smem, z.pixels(), z.C);
-  if (blocks < 1) return fail("bn_bwd_fused: occupancy query failed");
-  *bar_count += (unsigned)blocks;
-  unsigned target = *bar_count;
-  DView g_ = dv(gy), z_ = dv(z), o_ = dv(dz_out);
-  void* args[] = {&g_, &z_, &scale, &shift, &gamma, &mean, &rstd, &sums, &bar, &target, &count, &o_, &dgamma, &dbeta, &dbias};
-  MAU_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, smem, st));
-  MAU_LAUNCHED();
-  return 0;
-}
-
 int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* mean,
                      const float* rstd, double* sums, cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(gy)) return fail("bn_bwd_reduce: bad views");

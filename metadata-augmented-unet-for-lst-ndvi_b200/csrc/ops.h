@@ -72,15 +72,6 @@ int op_bn_finalize_apply_relu(int dt, const View& z, const double* sums, long lo
 // y = relu(z * scale + shift) into a (slice) view
 int op_bn_apply_relu(int dt, const View& z, const float* scale, const float* shift, const View& y,
                      cudaStream_t st);
-// One cooperative launch for statistics + normalise + ReLU (and the running-stat update): the second read of z is
-// served from L2.  bar: device counter of the grid barrier (never reset), bar_count: host mirror of the arrivals so far.
-int op_bn_fwd_fused(int dt, const View& z, double* sums, unsigned* bar, unsigned* bar_count, long long count, const float* gamma,
-                    const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                    float* save_mean, float* save_rstd, const View& y, cudaStream_t st);
-// One cooperative launch for both backward passes (reduce, grid barrier, apply); also writes dgamma / dbeta / dbias = 0
-int op_bn_bwd_fused(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* gamma,
-                    const float* mean, const float* rstd, double* sums, unsigned* bar, unsigned* bar_count, long long count,
-                    const View& dz_out, float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
 // backward, pass 1: sums[0..C) = sum g~, sums[C..2C) = sum g~ * xhat, g~ = gy * (y > 0); the ReLU mask is
 // recomputed from z with the forward's scale / shift, so y is not read
 int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, const float* shift, const float* mean,

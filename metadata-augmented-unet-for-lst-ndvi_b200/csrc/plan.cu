@@ -239,16 +239,12 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
       const View z = whole(L->zbuf);
       // (statistics fused into the conv epilogue were measured and dropped: the column-sum pass over the staged
       //  tile lengthens the epilogue of the narrow layers by more than this separate 63 %-of-HBM-peak pass costs)
-      if (!sync_fn && bn_fused && !fused_stats) {
-        // statistics + normalise + ReLU in one cooperative launch (second read of z from L2)
-        MAU_TRY(op_bn_fwd_fused(dt, z, L->sums, bn_bar, &bn_bar_count, count, c.f(L->igamma), c.f(L->ibeta), kBnEps, kBnMomentum,
-                                c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, view(L->out), c.st));
-      } else {
-        if (!fused_stats) MAU_TRY(op_bn_stats(dt, z, L->sums, c.st));
-        if (sync_fn) sync_fn(sync_user, L->sums, 2 * C);       // SyncBN: sum / sum-of-squares over all ranks
-        MAU_TRY(op_bn_finalize_apply_relu(dt, z, L->sums, count * sync_world, c.f(L->igamma), c.f(L->ibeta), kBnEps, kBnMomentum,
-                                          c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, view(L->out), c.st));
-      }
+      // (a single cooperative launch -- statistics, grid barrier, apply over the same block ranges in reverse so that the
+      //  second read of z hits L2 -- was measured and dropped: 8.41 vs 8.16 ms per step, profiles/r02_training_step.md)
+      if (!fused_stats) MAU_TRY(op_bn_stats(dt, z, L->sums, c.st));
+      if (sync_fn) sync_fn(sync_user, L->sums, 2 * C);       // SyncBN: sum / sum-of-squares over all ranks
+      MAU_TRY(op_bn_finalize_apply_relu(dt, z, L->sums, count * sync_world, c.f(L->igamma), c.f(L->ibeta), kBnEps, kBnMomentum,
+                                        c.fm(L->irm), c.fm(L->irv), L->scale, L->shift, L->mean, L->rstd, view(L->out), c.st));
     }
     return 0;
   };
@@ -324,22 +320,17 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
   op.grad_first = L->iw; op.grad_last = L->ibeta;
   op.run = [this, L, gy, y, z, count, C](Ctx& c) -> int {
     MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
-    if (!sync_fn && bn_fused) {
-      MAU_TRY(op_bn_bwd_fused(dt, gy, z, L->scale, L->shift, c.f(L->igamma), L->mean, L->rstd, L->sums, bn_bar, &bn_bar_count,
-                              count, z, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
-    } else {
-      MAU_TRY(op_bn_bwd_reduce(dt, gy, z, L->scale, L->shift, L->mean, L->rstd, L->sums, c.st));
-      const double* param_sums = L->sums;
-      if (sync_fn) {
-        // SyncBN: dz needs the sums over every rank's pixels; dgamma / dbeta stay this rank's own sums (the
-        // data-parallel gradient average then yields the global-batch gradient, like torch SyncBatchNorm)
-        MAU_CUDA(cudaMemcpyAsync(L->sums_local, L->sums, sizeof(double) * 2 * C, cudaMemcpyDeviceToDevice, c.st));
-        sync_fn(sync_user, L->sums, 2 * C);
-        param_sums = L->sums_local;
-      }
-      MAU_TRY(op_bn_bwd_apply(dt, gy, z, L->scale, L->shift, c.f(L->igamma), L->mean, L->rstd, L->sums,
-                              count * sync_world, z, param_sums, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
+    MAU_TRY(op_bn_bwd_reduce(dt, gy, z, L->scale, L->shift, L->mean, L->rstd, L->sums, c.st));
+    const double* param_sums = L->sums;
+    if (sync_fn) {
+      // SyncBN: dz needs the sums over every rank's pixels; dgamma / dbeta stay this rank's own sums (the
+      // data-parallel gradient average then yields the global-batch gradient, like torch SyncBatchNorm)
+      MAU_CUDA(cudaMemcpyAsync(L->sums_local, L->sums, sizeof(double) * 2 * C, cudaMemcpyDeviceToDevice, c.st));
+      sync_fn(sync_user, L->sums, 2 * C);
+      param_sums = L->sums_local;
     }
+    MAU_TRY(op_bn_bwd_apply(dt, gy, z, L->scale, L->shift, c.f(L->igamma), L->mean, L->rstd, L->sums,
+                            count * sync_world, z, param_sums, c.g(L->igamma), c.g(L->ibeta), c.g(L->ib), c.st));
     float* dw = c.g(L->iw);
     int ci_w0 = 0;
     const bool ws_path = use_tc && wgrad_ws != nullptr;      // v2 wgrad: reduce into the workspace, then transpose
@@ -997,11 +988,8 @@ int Plan::build() {
   set_sm_reserve_override(-1);
   if (rc) return rc;
   if (cfg.training) {
-    bn_fused = (cfg.flags & MAU_FLAG_BN_FUSED) != 0;
     overlap_wgrad = !(cfg.flags & MAU_FLAG_NO_WGRAD_OVERLAP);
     conv_stats = !(cfg.flags & MAU_FLAG_NO_CONV_STATS);
-    bn_bar = static_cast<unsigned*>(alloc(sizeof(unsigned) * 4));      // zeroed; only ever counts up
-    if (!dry && !bn_bar) return -1;
     if (use_tc && !(cfg.flags & MAU_FLAG_WGRAD_V1)) {
       // one fp32 workspace [9][Cout][Cin] shared by all layers (backward ops are serialised on one stream)
       size_t fl = 0;

@@ -172,9 +172,6 @@ class Plan {
   float* emb = nullptr; float* demb = nullptr; float* hidden = nullptr; float* hlast = nullptr;
   float* dhlast = nullptr; float* lstm_save = nullptr;
   int emb_dim = 0;
-  bool bn_fused = false;            // MAU_FLAG_BN_FUSED: training BatchNorm as one cooperative launch per direction (norm.cu)
-  unsigned* bn_bar = nullptr;       // device counter of the fused kernels' grid barrier (monotonic)
-  unsigned bn_bar_count = 0;        // host mirror: arrivals of every launch so far
   float* wgrad_ws = nullptr;   // fp32 [9][Cout][Cin] scratch of the tcgen05 weight-gradient kernel
 };
 
