@@ -105,6 +105,14 @@ int mau_plan_forward(mau_plan* plan, void* const* state_dev, const float* maps_d
                      const float* temp_series_dev, const float* metadata_dev, float* out_dev,
                      void* stream);
 
+/* The same forward with the tiles already STAGED: maps_nhwc_dev is [B, H, W, round_up(spatial_channels, 8)] in the plan's
+ * activation type (bf16 for MAU_PRECISION_BF16, fp32 otherwise) -- what a loader produces when it converts while it decodes.
+ * Halves the host-to-device bytes of the reference's fp32 NCHW contract (48 MB instead of 92 MB per 16 tiles) and replaces
+ * the layout kernel by one device copy; values are identical to mau_plan_forward on the fp32 tiles rounded to nearest-even.
+ * (B = 1 for a MAU_FLAG_SHARED_MAPS plan.) */
+int mau_plan_forward_staged(mau_plan* plan, void* const* state_dev, const void* maps_nhwc_dev,
+                            const float* temp_series_dev, const float* metadata_dev, float* out_dev, void* stream);
+
 /* test / tooling access to the plan's own activation storage: device pointer of the NHWC buffer `name` (names, extents
  * and channel strides are listed under "buffers" by mau_plan_describe_config; bf16 or fp32 elements according to the
  * plan's precision).  which = 0: the activation, 1: its gradient twin (training plans; NULL until the plan has run a

@@ -90,6 +90,17 @@ int mau_plan_forward(mau_plan* plan, void* const* state_dev, const float* maps_d
   return plan->impl.run_forward(c);
 }
 
+int mau_plan_forward_staged(mau_plan* plan, void* const* state_dev, const void* maps_nhwc_dev, const float* temp_series_dev,
+                             const float* metadata_dev, float* out_dev, void* stream) {
+  if (!plan || !state_dev || !maps_nhwc_dev || !out_dev) return fail("mau_plan_forward_staged: null argument");
+  Ctx c;
+  c.state = state_dev; c.maps_staged = maps_nhwc_dev; c.series = temp_series_dev; c.md = metadata_dev; c.out = out_dev;
+  c.st = static_cast<cudaStream_t>(stream);
+  plan->impl.last_state.assign(state_dev, state_dev + plan->impl.state.size());
+  plan->impl.last_series = temp_series_dev; plan->impl.last_md = metadata_dev;
+  return plan->impl.run_forward(c);
+}
+
 int mau_plan_backward(mau_plan* plan, const float* grad_out_dev, void* const* grads_dev, void* stream) {
   if (!plan || !grad_out_dev || !grads_dev) return fail("mau_plan_backward: null argument");
   Ctx c;

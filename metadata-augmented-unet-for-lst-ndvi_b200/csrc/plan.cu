@@ -620,6 +620,11 @@ int Plan::build_unet() {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
     op.run = [=](Ctx& c) -> int {
+      if (c.maps_staged) {     // pre-staged NHWC tiles (mau_plan_forward_staged): one device copy instead of the layout kernel
+        MAU_CUDA(cudaMemcpyAsync(dst.ptr, c.maps_staged, (size_t)Be * cfg.height * cfg.width * dst.cs * dtype_size(dt),
+                                 cudaMemcpyDeviceToDevice, c.st));
+        return 0;
+      }
       return op_nchw_to_nhwc(dt, c.maps, Be, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
     };
     fwd.push_back(op);
@@ -827,6 +832,11 @@ int Plan::build_unetpp() {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
     op.run = [=](Ctx& c) -> int {
+      if (c.maps_staged) {     // pre-staged NHWC tiles (mau_plan_forward_staged): one device copy instead of the layout kernel
+        MAU_CUDA(cudaMemcpyAsync(dst.ptr, c.maps_staged, (size_t)Be * cfg.height * cfg.width * dst.cs * dtype_size(dt),
+                                 cudaMemcpyDeviceToDevice, c.st));
+        return 0;
+      }
       return op_nchw_to_nhwc(dt, c.maps, Be, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
     };
     fwd.push_back(op);

@@ -36,6 +36,7 @@ struct Ctx {
   void* const* state = nullptr;
   void* const* grads = nullptr;
   const float* maps = nullptr;
+  const void* maps_staged = nullptr;   // alternative input: maps already as NHWC in the plan's activation dtype, channel stride round_up(C, 8)
   const float* series = nullptr;
   const float* md = nullptr;
   float* out = nullptr;

@@ -48,7 +48,7 @@ _lib_lock = threading.Lock()
 EXPORTS = (
     "mau_last_error", "mau_version", "mau_launch_count", "mau_plan_create", "mau_plan_destroy",
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
-    "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_wait_backward_streams", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
+    "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_forward_staged", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_wait_backward_streams", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
     "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_loss_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss", "mau_ssim_forward", "mau_ssim_backward",
     "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_cast_f32_bf16", "mau_cast_bf16_f32", "mau_op_maxpool2x2", "mau_op_bilinear",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
@@ -82,6 +82,7 @@ def lib():
         L.mau_plan_exec_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.mau_plan_forward.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mau_plan_forward_staged.argtypes = L.mau_plan_forward.argtypes
         L.mau_plan_backward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         L.mau_plan_set_grad_hook.argtypes = [C.c_void_p, GRAD_HOOK, C.c_void_p]
         L.mau_plan_set_state_version.argtypes = [C.c_void_p, C.c_uint64]
@@ -192,6 +193,26 @@ def describe(cfg: Dict) -> Dict:
     return json.loads(buf.value.decode())
 
 
+def is_staged_maps(maps: torch.Tensor) -> bool:
+    """bf16 tensors are STAGED tiles: NHWC, channel stride a multiple of 8 (see :func:`stage_maps`)."""
+    return maps.dtype == torch.bfloat16
+
+
+def stage_maps(maps: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 NCHW tiles [B, C, H, W] (the reference's contract, src/dataset.py:99-106) -> the engine's bf16 NHWC input layout
+    [B, H, W, round_up(C, 8)] (pad channels zero), on whatever device ``maps`` lives on.  A producer that stages on the
+    HOST (into a pinned ``out``) halves the PCIe bytes per tile; ``model(staged, series, metadata)`` then skips the layout
+    kernel.  Round-to-nearest-even like the kernel, so outputs are bit-identical to passing the fp32 tiles."""
+    B, Cc, H, W = maps.shape
+    cs = (Cc + 7) // 8 * 8
+    if out is None:
+        out = torch.zeros((B, H, W, cs), dtype=torch.bfloat16, device=maps.device)
+    elif out.shape != (B, H, W, cs) or out.dtype != torch.bfloat16:
+        raise ValueError(f"out must be bf16 [{B},{H},{W},{cs}]")
+    out[..., :Cc].copy_(maps.permute(0, 2, 3, 1))
+    return out
+
+
 class _DevMem:
     """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
 
@@ -289,7 +310,7 @@ class Plan:
                 raise RuntimeError(f"mau_b200: state tensor {i} must be {want}, got {t.dtype} "
                                    "(keep the module in fp32; precision is chosen by set_precision)")
 
-    def forward(self, state, maps, series, md, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, state, maps, series, md, out: Optional[torch.Tensor] = None, staged: bool = False) -> torch.Tensor:
         key = tuple(t.data_ptr() for t in state)
         if key != getattr(self, "_validated", None):       # same memory as last time: shapes / dtypes were checked then
             self._check_state(state)
@@ -301,11 +322,10 @@ class Plan:
             bump_state_epoch()          # this forward updates the BatchNorm running statistics through raw pointers
         if out is None:
             out = torch.empty(self.out_shape, device=self.device, dtype=torch.float32)
+        fn = lib().mau_plan_forward_staged if staged else lib().mau_plan_forward
         with torch.cuda.device(self.device):
-            check(lib().mau_plan_forward(self._h, self._ptr_array(state), maps.data_ptr(),
-                                         series.data_ptr() if series.numel() else None,
-                                         md.data_ptr() if md.numel() else None, out.data_ptr(),
-                                         _stream_ptr()), "forward")
+            check(fn(self._h, self._ptr_array(state), maps.data_ptr(), series.data_ptr() if series.numel() else None,
+                     md.data_ptr() if md.numel() else None, out.data_ptr(), _stream_ptr()), "forward")
         return out
 
     def backward(self, grad_out: torch.Tensor, grads: Sequence[Optional[torch.Tensor]]):
@@ -408,7 +428,7 @@ class HotPathFn(torch.autograd.Function):
     def forward(ctx, plan: Plan, state, diff_idx, dp, maps, series, md, *diff_params):
         if plan.pending:
             raise RuntimeError("mau_b200: this plan still holds the activations of a forward that awaits its backward")
-        out = plan.forward(state, maps, series, md)
+        out = plan.forward(state, maps, series, md, staged=is_staged_maps(maps))
         ctx.token = _PendingToken(plan)
         ctx.plan, ctx.diff_idx, ctx.n_state, ctx.dp = plan, diff_idx, len(state), dp
         # backward re-reads the series (LSTM BPTT) and the metadata (MLP) through the raw pointers the
@@ -463,7 +483,7 @@ def loss_terms(pred: torch.Tensor, target: torch.Tensor, kind: str = "l1", lambd
     if pred.dim() != 4 or target.shape != pred.shape:
         raise RuntimeError(f"pred and target must both be [B,C,H,W], got {tuple(pred.shape)} and {tuple(target.shape)}")
     B, Cc, H, W = pred.shape
-    losses = torch.zeros(4, device=pred.device, dtype=torch.float32)
+    losses = torch.empty(4, device=pred.device, dtype=torch.float32)
     grad = torch.empty_like(pred) if need_grad else None
     with torch.cuda.device(pred.device):
         check(lib().mau_loss_forward_backward({"l1": 0, "mse": 1}[kind], pred.data_ptr(), target.data_ptr(),

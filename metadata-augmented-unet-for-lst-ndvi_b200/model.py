@@ -141,9 +141,18 @@ class _EngineNet(nn.Module):
         if not maps.is_cuda:
             raise RuntimeError("mau_b200: the hot path runs on a CUDA device only (no CPU fallback); "
                                "move the model and its inputs to cuda")
-        if maps.dim() != 4 or maps.shape[1] != self._cfg["spatial_channels"]:
-            raise RuntimeError(f"maps must be [B,{self._cfg['spatial_channels']},H,W], got {tuple(maps.shape)}")
-        B, _, H, W = maps.shape
+        staged = engine.is_staged_maps(maps)       # bf16 NHWC tiles produced by engine.stage_maps (halves the H2D bytes)
+        Cs = self._cfg["spatial_channels"]
+        if staged:
+            if maps.dim() != 4 or maps.shape[3] != (Cs + 7) // 8 * 8:
+                raise RuntimeError(f"staged maps must be bf16 [B,H,W,{(Cs + 7) // 8 * 8}], got {tuple(maps.shape)}")
+            if self.precision != "bf16":
+                raise RuntimeError("staged bf16 maps need the bf16 engine (set_precision('bf16'))")
+            B, H, W, _ = maps.shape
+        else:
+            if maps.dim() != 4 or maps.shape[1] != Cs:
+                raise RuntimeError(f"maps must be [B,{Cs},H,W], got {tuple(maps.shape)}")
+            B, _, H, W = maps.shape
         if min(H, W) < 16:
             raise RuntimeError("tile edge must be >= 16 (four 2x2 poolings)")
         T = int(temp_series.shape[1]) if temp_series.dim() == 2 else 0
@@ -170,7 +179,7 @@ class _EngineNet(nn.Module):
                 raise RuntimeError(f"Expected all tensors to be on the same device: maps is on {maps.device}, {name} on {t.device}")
         if plan.uses_series and (temp_series.dim() != 2 or T < 1 or temp_series.shape[0] != (1 if shared else B)):
             raise RuntimeError(f"temp_series must be [{B},T] with T >= 1, got {tuple(temp_series.shape)}")
-        maps = maps.contiguous().float()
+        maps = maps.contiguous() if staged else maps.contiguous().float()
         # an ignored argument (flag off, src/model.py:263-264) never crosses the ABI, wherever it lives
         temp_series = temp_series.contiguous().float() if plan.uses_series else maps.new_empty(0)
         metadata = metadata.contiguous().float() if plan.uses_metadata else maps.new_empty(0)
@@ -182,7 +191,7 @@ class _EngineNet(nn.Module):
         state = self._state_tensors()
         need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in state)
         if not need_grad:
-            return self._finish(plan.forward(state, maps, temp_series, metadata))
+            return self._finish(plan.forward(state, maps, temp_series, metadata, staged=staged))
         if not self.training:
             raise RuntimeError("mau_b200: backward through an eval()-mode forward is not supported; "
                                "call model.train() or wrap inference in torch.no_grad()")

@@ -589,6 +589,41 @@ def test_config3_full_size_training_against_oracle():
     assert abs(lgpu - float(F.l1_loss(ref32, tgt))) < 1e-2 * float(F.l1_loss(ref32, tgt))
 
 
+def test_staged_bf16_nhwc_maps_are_bit_identical_to_fp32_nchw_maps():
+    """engine.stage_maps (host side: fp32 NCHW -> bf16 NHWC, half the PCIe bytes) + mau_plan_forward_staged must give
+    exactly what the fp32 contract gives: the layout kernel rounds to nearest-even too.  Eval, the shared-maps sweep and
+    a training step (same loss, same gradients); the fp32 engine refuses staged tiles."""
+    kw = dict(temporal_embeddings=True, metadata_embeddings=True)
+    torch.manual_seed(5)
+    m = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 8, 32, 2, base_filters=8, **kw).cuda()
+    x, ts, md, tgt = O.synthetic_batch(3, 37, 45, T=12, seed=21)
+    xs = engine.stage_maps(x)                       # on the host
+    assert xs.shape == (3, 37, 45, 24) and xs.dtype == torch.bfloat16 and not xs.is_cuda
+    m.eval()
+    with torch.no_grad():
+        y_ref = m(x.cuda(), ts.cuda(), md.cuda())
+        y_st = m(xs.cuda(), ts.cuda(), md.cuda())
+        sweep_ref = m.forward_sweep(x[:1].cuda(), ts[:1].cuda(), md.cuda())
+        sweep_st = m.forward_sweep(xs[:1].cuda(), ts[:1].cuda(), md.cuda())
+    assert torch.equal(y_ref, y_st) and torch.equal(sweep_ref, sweep_st)
+    m.train()
+    grads = []
+    for inp in (x.cuda(), xs.cuda()):
+        m.zero_grad(set_to_none=True)
+        sd0 = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+        loss = engine.compute_loss_mse_gradient(m(inp, ts.cuda(), md.cuda()), tgt.cuda(), 0.1)["total"]
+        loss.backward()
+        torch.cuda.synchronize()
+        for k, v in sd0.items():
+            m.state_dict()[k].copy_(v)
+        grads.append((float(loss), {n: p.grad.clone() for n, p in m.named_parameters()}))
+    assert grads[0][0] == grads[1][0]
+    for n in grads[0][1]:
+        assert rel(grads[1][1][n], grads[0][1][n]) < 1e-5 or float(grads[0][1][n].abs().max()) < 1e-7, n   # fp32 atomics order only
+    with pytest.raises(RuntimeError, match="bf16 engine"):
+        m.set_precision("fp32")(xs.cuda(), ts.cuda(), md.cuda())
+
+
 def test_fused_adamw_matches_torch_adamw():
     """mau_adamw_step vs torch.optim.AdamW: same parameters / state after several steps, None-grad parameters
     untouched, interchangeable state_dict (reference src/train.py:213-214,255,309)."""

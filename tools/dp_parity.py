@@ -55,11 +55,14 @@ def main():
             #     in fp32 -- ReLU mask flips -- hence the absolute floor, as in tests/test_gpu_parity.py)
             _, lref, grads, sd1 = O.train_step_grads(sd0, mt, x, ts, md, tgt, loss="mse", **kw)
             worst1, name1, worst2, name2 = 0.0, "", 0.0, ""
+            all1 = []
             ok = True
             for k, p in m.named_parameters():
                 if p.grad is None:
                     continue
                 e1 = float((p.grad - g1[k]).norm() / g1[k].norm().clamp_min(1e-12))
+                if g1[k].norm() > 1e-7:
+                    all1.append(e1)
                 if g1[k].norm() > 1e-7 and e1 > worst1:
                     worst1, name1 = e1, k
                 r = grads[k]
@@ -71,9 +74,15 @@ def main():
             rs = max(float((sd_now[k].cpu() - sd1[k]).abs().max() / sd1[k].abs().max().clamp_min(1.0))
                      for k in sd1 if "running" in k)
             lerr = abs(float(lsum) / world - float(lref)) / max(abs(float(lref)), 1e-12)
-            ok = ok and worst1 < tol1 and rs < 1e-4 and lerr < 1e-5
+            # The N-rank run and the single-process run sum the BatchNorm statistics in a different order; an activation
+            # within rounding of zero can then fall on the other side of the ReLU, and ONE such element moves its
+            # channel's dbeta by ~1/sqrt(pixels) (16 x 37 x 45 pixels at 8 ranks: ~6e-3 of that channel).  So: the median
+            # over all tensors must be at rounding level, the worst tensor within a few mask flips.
+            all1.sort()
+            med1 = all1[len(all1) // 2] if all1 else 0.0
+            ok = ok and med1 < (2e-5 if grad_dtype == "fp32" else tol1) and worst1 < max(tol1, 5e-3) and rs < 1e-4 and lerr < 1e-5
             ok_all &= ok
-            print(f"[dp_parity] {mt} world={world} grads on the wire: {grad_dtype}: loss err {lerr:.2e}; vs single-process engine at the global batch: worst grad rel L2 "
+            print(f"[dp_parity] {mt} world={world} grads on the wire: {grad_dtype}: loss err {lerr:.2e}; vs single-process engine at the global batch: grad rel L2 median {med1:.2e}, worst "
                   f"{worst1:.2e} ({name1}); vs CPU oracle: worst {worst2:.2e} ({name2}), running-stat err {rs:.2e} -> "
                   f"{'OK' if ok else 'FAIL'}", flush=True)
     dist.barrier()
