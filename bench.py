@@ -243,7 +243,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if args.comm_ctas is None:
-        args.comm_ctas = 8      # measured at N=2 (profiles/r02_multi_gpu.md): 7.20 ms per step with 8 CTAs, 7.50 with 4
+        # measured (profiles/r02_multi_gpu.md): N=2: 7.20 ms per step with 8 CTAs, 7.50 with 4; N=8: 7.59 / 7.26 / 7.29 / 7.31 /
+        # 7.34 ms with 8 / 12 / 16 / 24 / 32 -- the ring moves 1.75x the bytes per GPU at 8 ranks and wants more CTAs
+        args.comm_ctas = 8 if world <= 2 else 12
     if world > 1:
         # the gradient all-reduce of the training configs runs concurrently with the persistent conv / wgrad kernels:
         # cap NCCL's CTA count (and, per training measurement, leave that many SMs out of our persistent grids)

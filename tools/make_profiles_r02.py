@@ -109,8 +109,9 @@ def main():
         f.write("\nOne GPU, same kernels: 7.07 ms/step (`r02_bench_c7_bench_c3.json`).  The bf16 wire format halves the payload but adds two cast launches per\n"
                 "bucket on the communication stream and loses; 8 CTAs beat 4 -- the all-reduce finishes earlier and the tail after the last\n"
                 "backward kernel shrinks.  Default: fp32 wire, 8 CTAs.\n\n## 8 GPUs\n\n| run | ms/step | tiles/s | sustained | e2e | |\n|---|---:|---:|---:|---:|---|\n")
-        f.write(row("default bench line (config 3 + riders), 8 GPUs", "r02n8_bench_default"))
-        f.write(row("config 3, 16 NCCL CTAs", "r02n8_bench_c3_ctas16"))
+        f.write(row("default bench line of that call (config 3 + riders, 8 NCCL CTAs), 8 GPUs", "r02n8_bench_default"))
+        for c in (12, 16, 24, 32):
+            f.write(row(f"config 3, {c} NCCL CTAs (second call, another box)", f"r02n8_bench_c3_ctas{c}"))
         d = bench("r02n8_bench_default")
         if d and "inference" in d:
             f.write(f"\nRiders of the 8-GPU line: inference {d['inference']['value']:.0f} tiles/s (e2e {d['inference']['e2e']['value']:.0f}); "
