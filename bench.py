@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--comm-ctas", type=int, default=None, help="data-parallel training: CTAs NCCL may use (and SMs our persistent kernels leave free)")
     ap.add_argument("--sync-bn", action="store_true", help="data-parallel training: SyncBN (global-batch statistics)")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"], help="data-parallel training: wire format of the gradient all-reduce")
+    ap.add_argument("--bucket-mb", type=float, default=8.0, help="data-parallel training: minimum all-reduce bucket (MB of fp32 gradients)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer measurement")
     ap.add_argument("--no-kernel-pass", action="store_true", help="profiling runs only (ncu): skip the per-launch CUDA-event pass; no roofline block")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` block (0 = skip)")
@@ -270,7 +271,7 @@ def main():
         model.train(train)
         if train and world > 1:
             from mau_b200 import parallel
-            parallel.DataParallel(model, sync_bn=args.sync_bn, grad_dtype=args.grad_dtype)   # overlapped all-reduce on the plan's grad hook
+            parallel.DataParallel(model, sync_bn=args.sync_bn, grad_dtype=args.grad_dtype, bucket_mb=args.bucket_mb)   # overlapped all-reduce on the plan's grad hook
         # several distinct input batches so that consecutive steps never re-read L2-resident inputs
         nb = 4
         host = [O.synthetic_batch(B, TILE, TILE, seed=1002 + 17 * rank + i) for i in range(nb)]

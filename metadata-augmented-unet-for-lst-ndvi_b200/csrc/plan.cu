@@ -169,7 +169,7 @@ ConvLayer* Plan::add_conv(const std::string& name, int iw0, int in_buf, int nseg
   L->shift = static_cast<float*>(alloc(sizeof(float) * C));
   L->mean = static_cast<float*>(alloc(sizeof(float) * C));
   L->rstd = static_cast<float*>(alloc(sizeof(float) * C));
-  L->sums = static_cast<double*>(alloc(sizeof(double) * 2 * C));
+  if (!cfg.training) L->sums = static_cast<double*>(alloc(sizeof(double) * 2 * C));    // training: carved from sums_all in build()
   L->dbsum = static_cast<double*>(alloc(sizeof(double) * C));
   if (cfg.training) L->sums_local = static_cast<double*>(alloc(sizeof(double) * 2 * C));
   if (cfg.training) L->zbuf = new_buf(name + ".z", L->H, L->W, C, L->B);
@@ -218,7 +218,6 @@ int Plan::emit_conv_fwd(ConvLayer* L) {
     // training, tcgen05 halo kernels: the BatchNorm statistics are accumulated by the convolution itself (idle warps read
     // each staged output tile), so z is not read again by a separate bn_stats pass
     const bool fused_stats = training && use_tc && conv_mode == MODE_HALO && conv_stats;
-    if (training) MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
     if (use_tc) {
       L->tc.p.stats = fused_stats ? L->sums : nullptr;
       L->tc.p.scale = scale; L->tc.p.shift = shift; L->tc.p.relu = relu;
@@ -319,7 +318,6 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
   op.name = L->name + ".bwd";
   op.grad_first = L->iw; op.grad_last = L->ibeta;
   op.run = [this, L, gy, y, z, count, C](Ctx& c) -> int {
-    MAU_CUDA(cudaMemsetAsync(L->sums, 0, sizeof(double) * 2 * C, c.st));
     MAU_TRY(op_bn_bwd_reduce(dt, gy, z, L->scale, L->shift, L->mean, L->rstd, L->sums, c.st));
     const double* param_sums = L->sums;
     if (sync_fn) {
@@ -620,10 +618,13 @@ int Plan::build_unet() {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
     op.run = [=](Ctx& c) -> int {
-      if (c.maps_staged) {     // pre-staged NHWC tiles (mau_plan_forward_staged): one device copy instead of the layout kernel
-        MAU_CUDA(cudaMemcpyAsync(dst.ptr, c.maps_staged, (size_t)Be * cfg.height * cfg.width * dst.cs * dtype_size(dt),
-                                 cudaMemcpyDeviceToDevice, c.st));
-        return 0;
+      if (c.maps_staged) {     // pre-staged NHWC tiles (mau_plan_forward_staged): a copy KERNEL instead of the layout kernel
+        // (a cudaMemcpyAsync would queue on the copy engines behind the caller's own H2D prefetches: measured, e2e 7.4k vs 8.0k tiles/s)
+        View src = dst;
+        src.ptr = const_cast<void*>(c.maps_staged);
+        View d8 = dst;
+        src.C = d8.C = dst.cs;      // whole 8-channel groups, pad channel included
+        return op_copy_slice(dt, src, d8, 0, c.st);
       }
       return op_nchw_to_nhwc(dt, c.maps, Be, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
     };
@@ -832,10 +833,13 @@ int Plan::build_unetpp() {
     Op op; op.name = "nchw_to_nhwc";
     const View dst = whole(in0);
     op.run = [=](Ctx& c) -> int {
-      if (c.maps_staged) {     // pre-staged NHWC tiles (mau_plan_forward_staged): one device copy instead of the layout kernel
-        MAU_CUDA(cudaMemcpyAsync(dst.ptr, c.maps_staged, (size_t)Be * cfg.height * cfg.width * dst.cs * dtype_size(dt),
-                                 cudaMemcpyDeviceToDevice, c.st));
-        return 0;
+      if (c.maps_staged) {     // pre-staged NHWC tiles (mau_plan_forward_staged): a copy KERNEL instead of the layout kernel
+        // (a cudaMemcpyAsync would queue on the copy engines behind the caller's own H2D prefetches: measured, e2e 7.4k vs 8.0k tiles/s)
+        View src = dst;
+        src.ptr = const_cast<void*>(c.maps_staged);
+        View d8 = dst;
+        src.C = d8.C = dst.cs;      // whole 8-channel groups, pad channel included
+        return op_copy_slice(dt, src, d8, 0, c.st);
       }
       return op_nchw_to_nhwc(dt, c.maps, Be, cfg.spatial_channels, cfg.height, cfg.width, dst, c.st);
     };
@@ -998,6 +1002,16 @@ int Plan::build() {
   set_sm_reserve_override(-1);
   if (rc) return rc;
   if (cfg.training) {
+    // the per-channel sums of every BatchNorm (forward statistics, then reused for the backward sums) live in ONE block that
+    // is zeroed once per pass: 36 tiny memsets per step were 36 stream operations on the critical chain
+    sums_bytes = 0;
+    for (const ConvLayer* L : layers) sums_bytes += sizeof(double) * 2 * L->Cout;
+    sums_all = static_cast<double*>(alloc(sums_bytes));
+    if (!dry && !sums_all) return -1;
+    {
+      double* p = sums_all;
+      for (ConvLayer* L : layers) { L->sums = dry ? nullptr : p; p += 2 * L->Cout; }
+    }
     overlap_wgrad = !(cfg.flags & MAU_FLAG_NO_WGRAD_OVERLAP);
     conv_stats = !(cfg.flags & MAU_FLAG_NO_CONV_STATS);
     if (use_tc && !(cfg.flags & MAU_FLAG_WGRAD_V1)) {
@@ -1082,6 +1096,7 @@ static int run_ops(Plan* P, std::vector<Op>& ops, Ctx& c, bool backward) {
 int Plan::run_forward(Ctx& c) {
   skip_pack = !cfg.training && state_version != 0 && state_version == packed_version && packed_state == last_state;
   packs_ahead = false;
+  if (cfg.training) MAU_CUDA(cudaMemsetAsync(sums_all, 0, sums_bytes, c.st));
   if (cfg.training && overlap_wgrad && !profiling) {
     // training re-packs every weight tensor every step (the optimizer has just changed them): all 18 / 30 pack launches go
     // to the second stream up front and hide behind the first convolutions; each convolution waits for its own event
@@ -1113,6 +1128,7 @@ int Plan::run_backward(Ctx& c) {
   if (!cfg.training) return fail("backward requires a training-mode plan");
   if (!forward_done) return fail("backward called before forward");
   if (emb_direct) MAU_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * cfg.batch * emb_dim, c.st));
+  MAU_CUDA(cudaMemsetAsync(sums_all, 0, sums_bytes, c.st));
   MAU_TRY(run_ops(this, bwd, c, true));
   MAU_TRY(side_join(c));
   MAU_TRY(w_join(c.st));

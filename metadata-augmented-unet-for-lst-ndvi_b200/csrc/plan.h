@@ -173,6 +173,7 @@ class Plan {
   float* emb = nullptr; float* demb = nullptr; float* hidden = nullptr; float* hlast = nullptr;
   float* dhlast = nullptr; float* lstm_save = nullptr;
   int emb_dim = 0;
+  double* sums_all = nullptr; size_t sums_bytes = 0;   // training: every layer's BatchNorm sums, one block, zeroed once per pass
   float* wgrad_ws = nullptr;   // fp32 [9][Cout][Cin] scratch of the tcgen05 weight-gradient kernel
 };
 
