@@ -276,9 +276,12 @@ struct V2Smem {
 // BRES = weights resident: when the whole packed weight tensor of the launch (9 taps x K chunks, one N tile) fits the
 // NB B stages it is loaded once per CTA instead of once per work item (the Cin <= 64, Cout <= 64 layers at 250x250:
 // 72 KB of weights against 46 KB of activations per item).
-// named barriers of the statistics warps (STATS): staging buffer s "full" (128 epilogue threads arrive, 64 statistics
-// threads wait) and "free" (the reverse); id 0 is __syncthreads, id 1 the epilogue's own barrier
-constexpr int kBarFull = 2, kBarFree = 4, kStatThreads = 192;
+// named barriers of the statistics warps (STATS): staging buffer s "full" (128 epilogue threads arrive, 128 statistics
+// threads wait) and "free" (the reverse); id 0 is __syncthreads, id 1 the epilogue's own barrier.  STATS instances run
+// with 384 threads: warps 8..11 are the statistics warps, one per SM sub-partition, so that each of the four epilogue
+// warps shares its issue slots with a quarter of the statistics work (two statistics warps on warps 2 / 3 slowed two of
+// the four epilogue warps -- and with them every tile -- twice as much)
+constexpr int kBarFull = 2, kBarFree = 4, kStatThreads = 256, kStatsBlock = 384;
 
 // per-channel sum / sum of squares of one 64-channel group of a staged bf16 tile (rows of 128 B, 16-byte chunks XOR-swizzled
 // by row & 7): lane l owns channels 2l, 2l + 1; valid(row) masks pixels outside the image
@@ -306,7 +309,7 @@ __device__ __forceinline__ void stat_rows(const uint8_t* tile, int row0, int row
 }
 
 template <int BN, int MT, int NBUF, int NA, int NB, int NSTG, bool BT, int EM, bool BRES, bool STATS = false>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(STATS ? kStatsBlock : kThreads, 1) conv3x3_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmY,
                                                                    const ConvTcParams p) {
@@ -451,19 +454,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
       }
       buf = (buf + 1) % NBUF;
     }
-  } else if (STATS && (warp == 2 || warp == 3)) {
+  } else if (STATS && warp >= 8) {
     // =========================== BatchNorm statistics (training forward) ===========================
     // Mirrors the epilogue's iteration space; reads every staged tile once while the epilogue warps work on the next.
     constexpr int NU = BN / S::SU;                  // store rounds per 128-pixel tile
-    constexpr int NG = S::SU / 64;                  // 64-channel groups per round: warp sw takes group sw (NG == 2) or half the rows
-    const int sw = warp - 2;
+    constexpr int NG = S::SU / 64;                  // 64-channel groups per round
+    const int sw = warp - 8;                        // NG == 2: group sw & 1, rows (sw >> 1) * 64 ..; NG == 1: rows sw * 32 ..
+    const int grp = NG == 2 ? (sw & 1) : 0;
+    const int r0 = NG == 2 ? (sw >> 1) * 64 : sw * 32, r1 = r0 + (NG == 2 ? 64 : 32);
     double as[NU][2], aq[NU][2];
 #pragma unroll
     for (int u = 0; u < NU; ++u) { as[u][0] = as[u][1] = aq[u][0] = aq[u][1] = 0.0; }
     auto flush = [&](int n0) {
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
-        const int c = n0 + u * S::SU + (NG == 2 ? sw * 64 : 0) + 2 * lane;
+        const int c = n0 + u * S::SU + grp * 64 + 2 * lane;
 #pragma unroll
         for (int e = 0; e < 2; ++e)
           if (c + e < p.Cout) { atomicAdd(p.stats + c + e, as[u][e]); atomicAdd(p.stats + p.Cout + c + e, aq[u][e]); }
@@ -487,9 +492,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
           named_bar_sync(kBarFull + stg, kStatThreads);
-          const uint8_t* tile = sStg + stg * S::STG + (NG == 2 ? sw * 16384 : 0);
           float s2[2], q2[2];
-          stat_rows(tile, NG == 2 ? 0 : sw * 64, NG == 2 ? 128 : sw * 64 + 64, lane, valid, s2, q2);
+          stat_rows(sStg + stg * S::STG + grp * 16384, r0, r1, lane, valid, s2, q2);
           named_bar_arrive(kBarFree + stg, kStatThreads);
           as[u][0] += (double)s2[0]; as[u][1] += (double)s2[1]; aq[u][0] += (double)q2[0]; aq[u][1] += (double)q2[1];
           stg = (stg + 1) % NSTG;
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_v2_kernel(const __grid
       }
     }
     if (cur_n0 >= 0) flush(cur_n0);
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // =========================== epilogue ===========================
     const int et = threadIdx.x - 128;
     const int q = warp & 3;
@@ -665,7 +669,7 @@ int launch_v2(const ConvTcOp& op, cudaStream_t st) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
   }
-  kern<<<op.grid, kThreads, S::kBytes, st>>>(op.tmA, op.tmB, op.tmY, op.p);
+  kern<<<op.grid, STATS ? kStatsBlock : kThreads, S::kBytes, st>>>(op.tmA, op.tmB, op.tmY, op.p);
   MAU_LAUNCHED();
   return 0;
 }
@@ -695,7 +699,7 @@ struct V3Smem {
 };
 
 template <int NA, int NB, int EM, bool STATS = false>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(STATS ? kStatsBlock : kThreads, 1) conv3x3_tc_col3_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmY,
                                                                      const ConvTcParams p) {
@@ -811,10 +815,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __gr
       }
       buf ^= 1;
     }
-  } else if (STATS && (warp == 2 || warp == 3)) {
+  } else if (STATS && warp >= 8) {
     // =========================== BatchNorm statistics (training forward) ===========================
-    // the staged tile is the packed 8 x 14 block of valid outputs (112 rows of 64 channels); the two warps split the rows
-    const int sw = warp - 2;
+    // the staged tile is the packed 8 x 14 block of valid outputs (112 rows of 64 channels), split 32 / 32 / 24 / 24 over four warps
+    const int sw = warp - 8;
+    const int r0 = sw < 2 ? sw * 32 : 64 + (sw - 2) * 24, r1 = r0 + (sw < 2 ? 32 : 24);
     double as[2] = {0.0, 0.0}, aq[2] = {0.0, 0.0};
     for (int s = 0; s < 2; ++s) named_bar_arrive(kBarFree + s, kStatThreads);
     int stg = 0;
@@ -826,7 +831,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __gr
       auto valid = [&](int r) { const int hr = r / 14; return h0 + hr < p.H && w0 + (r - hr * 14) < p.W; };
       named_bar_sync(kBarFull + stg, kStatThreads);
       float s2[2], q2[2];
-      stat_rows(sStg + stg * kC3Stg, sw * 56, sw * 56 + 56, lane, valid, s2, q2);
+      stat_rows(sStg + stg * kC3Stg, r0, r1, lane, valid, s2, q2);
       named_bar_arrive(kBarFree + stg, kStatThreads);
       as[0] += (double)s2[0]; as[1] += (double)s2[1]; aq[0] += (double)q2[0]; aq[1] += (double)q2[1];
       stg ^= 1;
@@ -834,7 +839,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_col3_kernel(const __gr
 #pragma unroll
     for (int e = 0; e < 2; ++e)
       if (2 * lane + e < p.Cout) { atomicAdd(p.stats + 2 * lane + e, as[e]); atomicAdd(p.stats + p.Cout + 2 * lane + e, aq[e]); }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // =========================== epilogue ===========================
     const int et = threadIdx.x - 128;
     const int q = warp & 3;
@@ -965,7 +970,7 @@ int launch_col3(const ConvTcOp& op, cudaStream_t st) {
     MAU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done[dev & 15] = true;
   }
-  kern<<<op.grid, kThreads, S::kBytes, st>>>(op.tmA, op.tmB, op.tmY, op.p);
+  kern<<<op.grid, STATS ? kStatsBlock : kThreads, S::kBytes, st>>>(op.tmA, op.tmB, op.tmY, op.p);
   MAU_LAUNCHED();
   return 0;
 }

@@ -332,8 +332,32 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
     float* dw = c.g(L->iw);
     int ci_w0 = 0;
     const bool ws_path = use_tc && wgrad_ws != nullptr;      // v2 wgrad: reduce into the workspace, then transpose
-    cudaStream_t ws;                                         // weight-gradient stream (== c.st when the overlap is off)
-    MAU_TRY(w_fork(c, &ws));
+    // Order on the device: the data gradient (on the dependency chain) first, the weight gradient after it -- forked from
+    // the caller's stream BEHIND the dgrad launches, so that the persistent wgrad CTAs never hold the SMs the chain's next
+    // tensor kernel is waiting for, and run while the next layer's BatchNorm backward streams.  (MAU_WGRAD_FORK_EARLY=1:
+    // fork right after the BatchNorm backward instead, both tensor kernels runnable at once.)
+    static const bool fork_early = [] { const char* e = getenv("MAU_WGRAD_FORK_EARLY"); return e && atoi(e) != 0; }();
+    cudaStream_t ws = c.st;                                  // weight-gradient stream (== c.st when the overlap is off)
+    if (fork_early) MAU_TRY(w_fork(c, &ws));
+    if (L->input_needs_grad) {
+      int ci0 = 0;
+      for (int s = 0; s < L->nseg; ++s) {
+        if (s == L->emb_seg) { ci0 += L->seg_len[s]; continue; }
+        if (use_tc) {
+          if (L->wpack_d[s])
+            MAU_TRY(conv_tc_pack_dgrad(c.f(L->iw), C, L->Cin, ci0, L->seg_len[s], L->Kd, L->wpack_d[s], c.st));
+          kbegin(c, "k:" + L->name + ":dgrad");
+          MAU_TRY(conv_tc_launch(L->tc_d[s], c.st));
+          kend(c);
+        } else {
+          MAU_TRY(conv_ffma_pack_dgrad(c.f(L->iw), C, L->Cin, ci0, L->seg_len[s], L->Kd,
+                                       static_cast<float*>(L->wpack_d[s]), c.st));
+          MAU_TRY(conv_ffma_launch(dt, L->ff_d[s], L->B, c.st));
+        }
+        ci0 += L->seg_len[s];
+      }
+    }
+    if (!fork_early) MAU_TRY(w_fork(c, &ws));
     Ctx cw = c; cw.st = ws;
     if (dw && ws_path) MAU_CUDA(cudaMemsetAsync(wgrad_ws, 0, sizeof(float) * wgrad_tc_workspace_floats(C, L->Cin, L->wg_swap), ws));
     else if (dw) MAU_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * L->Cin * 9, ws));
@@ -346,19 +370,6 @@ int Plan::emit_conv_bwd(ConvLayer* L) {
         if (use_tc) MAU_TRY(wgrad_tc_launch(L->wg[s], dw, ws));
         else MAU_TRY(wgrad_ffma_launch(dt, view(xin), z, ci_w0, L->Cin, dw, 1, ws));
         kend(cw);
-      }
-      if (L->input_needs_grad) {
-        if (use_tc) {
-          if (L->wpack_d[s])
-            MAU_TRY(conv_tc_pack_dgrad(c.f(L->iw), C, L->Cin, ci_w0, L->seg_len[s], L->Kd, L->wpack_d[s], c.st));
-          kbegin(c, "k:" + L->name + ":dgrad");
-          MAU_TRY(conv_tc_launch(L->tc_d[s], c.st));
-          kend(c);
-        } else {
-          MAU_TRY(conv_ffma_pack_dgrad(c.f(L->iw), C, L->Cin, ci_w0, L->seg_len[s], L->Kd,
-                                       static_cast<float*>(L->wpack_d[s]), c.st));
-          MAU_TRY(conv_ffma_launch(dt, L->ff_d[s], L->B, c.st));
-        }
       }
       ci_w0 += L->seg_len[s];
     }
