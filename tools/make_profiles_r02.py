@@ -59,6 +59,10 @@ def main():
         f.write(row("weight gradients on a second stream (overlap BatchNorm / pool / bilinear backward)", "r02c4_bench_c3", ""))
         f.write(row("`MAU_FLAGS=16384` (separate bn_stats pass)", "r02c7_bench_c3_nostats", "call 7"))
         f.write(row("BatchNorm statistics inside the convolution kernels (idle warps) + weight packs ahead on the second stream", "r02c7_bench_c3", ""))
+        f.write(row("call 9 (a slower box): `MAU_FLAGS=16384` (separate bn_stats pass)", "r02c9_bench_c3_nostats", "statistics on FOUR extra warps from here on (384-thread CTAs)"))
+        f.write(row("call 9: `MAU_WGRAD_FORK_LATE=1` (second stream forks behind the data gradient), run 1", "r02c9_bench_c3", "the weight gradients pile up and leave a tail: slower"))
+        f.write(row("call 9: the same, run 2", "r02c9_bench_c3_b", ""))
+        f.write(row("call 9: second stream forks right after the BatchNorm backward, data gradient enqueued first (final)", "r02c9_bench_c3_forkearly", "+ one memset for all BatchNorm sums"))
         f.write(row("the same with the reference's default criterion `l1-gradient-ssim` (separable SSIM kernels)", "r02c4_bench_c3_ssim",
                     "first version of the SSIM kernels (121 taps per window): +0.54 ms per step (`r02_bench_c1_bench_c3_ssim.json`)"))
         f.write(row("first SSIM kernels (direct 121-tap form), for reference", "r02c1_bench_c3_ssim", "call 1, on the round-1 step"))
@@ -112,6 +116,18 @@ def main():
         f.write(row("default bench line of that call (config 3 + riders, 8 NCCL CTAs), 8 GPUs", "r02n8_bench_default"))
         for c in (12, 16, 24, 32):
             f.write(row(f"config 3, {c} NCCL CTAs (second call, another box)", f"r02n8_bench_c3_ctas{c}"))
+        for nm, lab in (("base", "12 CTAs, third call"), ("simple", "12 CTAs, NCCL_PROTO=Simple"), ("bucket32", "12 CTAs, 32 MB buckets")):
+            f.write(row(f"config 3, {lab}", f"r02n8_bench_c3_{nm}"))
+        f.write("\n`NCCL_ALGO=NVLS` is refused by NCCL for this all-reduce (rc 1).  Neither the Simple protocol nor larger buckets change the step: the\n"
+                "all-reduce is hidden; what it costs is the SMs it takes from the persistent kernels.\n")
+        f.write("\n## Inference (config 2) through host buffers at 4 / 8 GPUs: the reference's fp32 NCHW contract vs tiles staged as bf16 NHWC\n\n"
+                "| GPUs | resident tiles/s | e2e, fp32 NCHW (92 MB per step and rank) | e2e, staged bf16 NHWC (48 MB) |\n|---:|---:|---:|---:|\n")
+        for n, nm in ((1, "r02c9_bench_c2"), (4, "r02n4_bench_c2"), (8, "r02n8_bench_c2")):
+            d2 = bench(nm)
+            if d2 and d2.get("e2e"):
+                shutil.copyfile(os.path.join(G, nm + ".json"), os.path.join(P, nm.replace("r02c", "r02_bench_c").replace("r02n", "r02_bench_n") + ".json"))
+                st = d2["e2e"].get("staged_bf16_nhwc", {}).get("value")
+                f.write(f"| {n} | {d2['value']:.0f} | {d2['e2e']['value']:.0f} | {st:.0f} |\n" if st else f"| {n} | {d2['value']:.0f} | {d2['e2e']['value']:.0f} | — |\n")
         d = bench("r02n8_bench_default")
         if d and "inference" in d:
             f.write(f"\nRiders of the 8-GPU line: inference {d['inference']['value']:.0f} tiles/s (e2e {d['inference']['e2e']['value']:.0f}); "
