@@ -59,7 +59,7 @@ def main():
         f.write(row("weight gradients on a second stream (overlap BatchNorm / pool / bilinear backward)", "r02c4_bench_c3", ""))
         f.write(row("`MAU_FLAGS=16384` (separate bn_stats pass)", "r02c7_bench_c3_nostats", "call 7"))
         f.write(row("BatchNorm statistics inside the convolution kernels (idle warps) + weight packs ahead on the second stream", "r02c7_bench_c3", ""))
-        f.write(row("call 9 (a slower box): `MAU_FLAGS=16384` (separate bn_stats pass)", "r02c9_bench_c3_nostats", "statistics on FOUR extra warps from here on (384-thread CTAs)"))
+        f.write(row("call 9 (a slower box), late fork: `MAU_FLAGS=16384` (separate bn_stats pass)", "r02c9_bench_c3_nostats", "statistics on FOUR extra warps from here on (384-thread CTAs)"))
         f.write(row("call 9: `MAU_WGRAD_FORK_LATE=1` (second stream forks behind the data gradient), run 1", "r02c9_bench_c3", "the weight gradients pile up and leave a tail: slower"))
         f.write(row("call 9: the same, run 2", "r02c9_bench_c3_b", ""))
         f.write(row("call 9: second stream forks right after the BatchNorm backward, data gradient enqueued first (final)", "r02c9_bench_c3_forkearly", "+ one memset for all BatchNorm sums"))
