@@ -118,7 +118,7 @@ def main():
             f.write(row(f"config 3, {c} NCCL CTAs (second call, another box)", f"r02n8_bench_c3_ctas{c}"))
         for nm, lab in (("base", "12 CTAs, third call"), ("simple", "12 CTAs, NCCL_PROTO=Simple"), ("bucket32", "12 CTAs, 32 MB buckets")):
             f.write(row(f"config 3, {lab}", f"r02n8_bench_c3_{nm}"))
-        f.write("\n`NCCL_ALGO=NVLS` is refused by NCCL for this all-reduce (rc 1).  Neither the Simple protocol nor larger buckets change the step: the\n"
+        f.write("\n`NCCL_ALGO=allreduce:nvls` is refused by NCCL here (\"no algorithm/protocol available for function AllReduce with datatype ncclFloat32\", with 4, 8 and 12 CTAs; fourth call, base 7.44 ms).  Neither the Simple protocol nor larger buckets change the step: the\n"
                 "all-reduce is hidden; what it costs is the SMs it takes from the persistent kernels.\n")
         f.write("\n## Inference (config 2) through host buffers at 4 / 8 GPUs: the reference's fp32 NCHW contract vs tiles staged as bf16 NHWC\n\n"
                 "| GPUs | resident tiles/s | e2e, fp32 NCHW (92 MB per step and rank) | e2e, staged bf16 NHWC (48 MB) |\n|---:|---:|---:|---:|\n")
