@@ -35,7 +35,11 @@ def launches(path, out, title, first_kernel="nchw_to_nhwc"):
     rows = list(csv.DictReader(lines))
     names = [clean(r["Kernel Name"]) for r in rows]
     starts = [i for i, n in enumerate(names) if n.startswith(first_kernel)]
-    a, b = (starts[-2], starts[-1]) if len(starts) >= 2 else (0, len(rows))     # one whole step
+    # one whole step: the LAST one (profiling runs end right after the timed step: --no-e2e --no-kernel-pass; the step before it
+    # is the warm-up step, which also creates the optimizer state)
+    a, b = (starts[-1], len(rows)) if starts else (0, len(rows))
+    while a > 0 and names[a - 1].startswith(("pack_w_fwd", "mlp_fwd", "lstm_fwd", "linear_fwd")):
+        a -= 1                                   # this step's weight packs / encoders are launched ahead of the layout kernel
     agg, tot = collections.OrderedDict(), 0.0
     for i in range(a, b):
         v = float(rows[i]["Metric Value"].replace(",", ""))
@@ -46,7 +50,7 @@ def launches(path, out, title, first_kernel="nchw_to_nhwc"):
         tot += v
     with open(out, "w") as f:
         f.write(f"# {title}\n\nSource: `{os.path.relpath(path, ROOT)}` -- `ncu --metrics gpu__time_duration.sum --clock-control none`, "
-                f"one whole step (launches {a}..{b - 1} of the capture).  Launches under ncu are serialised and cold-cache: compare "
+                f"the last whole step (launches {a}..{b - 1} of the capture).  Launches under ncu are serialised and cold-cache: compare "
                 f"SHARES, not absolutes.  Total {tot:.0f} us over {b - a} launches.\n\n"
                 "| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -113,16 +117,16 @@ def main():
         by = sum(r.get("DRAM rd MB", 0) + r.get("DRAM wr MB", 0) for r in recs) * 1e6
         return {"launches": n, "dram_bytes_per_launch": by / max(n, 1)}
     if pi:
-        recs = full(pi, os.path.join(P, f"{tag}_ncu_conv_v2_infer.md"), f"{tag}: conv3x3_tc_v2_kernel, the 18 launches of one inference forward (config 2, B=16)",
-                    "Template arguments <BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES>; ")
+        recs = full(pi, os.path.join(P, f"{tag}_ncu_conv_v2_infer.md"), f"{tag}: conv3x3_tc_v2 / conv3x3_tc_col3 kernels, the 18 launches of one inference forward (config 2, B=16)",
+                    "Template arguments v2 <BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES[, STATS]>, col3 <NA, NB, EM[, STATS]>; ")
         traffic["conv_infer"] = per_launch(recs)
     if pc:
-        recs = full(pc, os.path.join(P, f"{tag}_ncu_conv_v2.md"), f"{tag}: conv3x3_tc_v2_kernel (forward + dgrad launches of one training step)",
-                    "Template arguments <BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES>; ")
+        recs = full(pc, os.path.join(P, f"{tag}_ncu_conv_v2.md"), f"{tag}: conv3x3_tc_v2 / conv3x3_tc_col3 kernels (forward + dgrad launches of one training step; STATS = 1: forward with the statistics warps, 384 threads)",
+                    "Template arguments v2 <BN, MT, NBUF, NA, NB, NSTG, BT, EM, BRES[, STATS]>, col3 <NA, NB, EM[, STATS]>; ")
         traffic["conv_fwd_dgrad"] = per_launch(recs)
     if pw:
-        recs = full(pw, os.path.join(P, f"{tag}_ncu_wgrad_v2.md"), f"{tag}: wgrad3x3_tc_v2_kernel (the 18 weight-gradient launches of one backward)",
-                    "Template arguments <BN, SWAP, STAGES>; ")
+        recs = full(pw, os.path.join(P, f"{tag}_ncu_wgrad_v2.md"), f"{tag}: weight-gradient kernels (the 18 launches of one backward: wgrad3x3_tc_v2 split-K / stream-K, wgrad3x3_tc_pair for the <= 64-channel sides)",
+                    "Template arguments v2 <BN, SWAP, STAGES>, pair <BN, STAGES>; ")
         traffic["wgrad"] = per_launch(recs)
     for src in sorted(glob.glob(os.path.join(G, "prof_bw*_raw.csv"))):
         base = os.path.basename(src).replace("_raw.csv", "")

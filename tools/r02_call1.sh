@@ -1,3 +1,4 @@
+# (historical: MAU_FLAGS=4096 selected the cooperative one-launch BatchNorm of that commit; the path was measured slower and removed -- profiles/r02_training_step.md)
 # round 2, GPU call 1: parity suite, the new bench line (both arms), SSIM criterion, per-op profile of a training step,
 # fused (cooperative) BatchNorm A/B
 O=gpurun_out

@@ -1,3 +1,4 @@
+# (historical: MAU_FLAGS=4096 selected the cooperative one-launch BatchNorm of that commit; the path was measured slower and removed -- profiles/r02_training_step.md)
 O=gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > $O/r02c2_pytest.log 2>&1; echo "pytest rc=$?"
 tail -15 $O/r02c2_pytest.log

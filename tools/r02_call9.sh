@@ -1,3 +1,4 @@
+# (historical: at that commit the second stream forked BEHIND the data gradient by default and MAU_WGRAD_FORK_EARLY=1 selected the early fork, which won and is the default now; MAU_WGRAD_FORK_LATE=1 selects the late fork)
 O=gpurun_out
 timeout 600 python -m pytest tests -m gpu -q > $O/r02c9_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/r02c9_pytest.log
 B="python bench.py --config 3 --no-cpu-baseline --sustain-s 1 --no-e2e"
