@@ -88,6 +88,14 @@ int mau_tiles_read_batch(mau_tiles* t, const int64_t* idx, int64_t n, const uint
 int64_t mau_tiles_submit(mau_tiles* t, const int64_t* idx, int64_t n, const uint8_t* hflip, const int64_t dims[8],
                          float* input, float* target, float* metadata, float* series, int64_t series_stride,
                          int64_t* series_len);
+/* The same with the input tiles delivered a second time in the engine's staged layout (include/mau_b200.h,
+ * mau_plan_forward_staged): input_staged [n, dims[1], dims[2], staged_cs] bf16, NHWC, round-to-nearest-even, pad channels zero,
+ * staged_cs a multiple of 8 and >= dims[0].  Converted by the thread that has just decoded the tile; a loader that ships this
+ * buffer instead of `input` moves 2 * staged_cs instead of 4 * dims[0] bytes per pixel over PCIe (48 vs 92 bytes for the
+ * 23-channel tiles).  `input` is still required (it is the decode target); input_staged == NULL is mau_tiles_submit. */
+int64_t mau_tiles_submit_staged(mau_tiles* t, const int64_t* idx, int64_t n, const uint8_t* hflip, const int64_t dims[8],
+                                float* input, uint16_t* input_staged, int64_t staged_cs, float* target, float* metadata,
+                                float* series, int64_t series_stride, int64_t* series_len);
 int     mau_tiles_wait(mau_tiles* t, int64_t ticket);
 /* 1 if every sample of the batch has been decoded (wait() will not block), 0 if not, -MAU_TILES_E_ARG for an
  * unknown ticket.  Does not retire the ticket. */

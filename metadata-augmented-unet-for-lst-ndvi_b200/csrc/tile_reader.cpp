@@ -749,6 +749,8 @@ struct Batch {
   std::vector<uint8_t> flip;
   int64_t dims[8];
   float *input, *target, *metadata, *series;
+  uint16_t* input_staged = nullptr;   // optional: the input tiles once more as bf16 NHWC [n, H, W, staged_cs] (engine.stage_maps)
+  int64_t staged_cs = 0;
   int64_t series_stride;
   int64_t* series_len;
   std::mutex mu;
@@ -775,6 +777,29 @@ namespace {
 // which members a task decodes: the `input` member is ~90 % of a sample, so it is its own task
 enum { PART_INPUT = 1, PART_REST = 2 };
 
+// fp32 -> bf16, round to nearest even (what torch's .to(bfloat16) and the engine's layout kernel do); NaN -> 0x7FC0
+inline uint16_t to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7FC0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return uint16_t(u >> 16);
+}
+
+// one decoded tile, planar fp32 [C][H][W] -> the engine's input layout bf16 [H][W][cs] (pad channels zero), on the thread
+// that has just decoded it (the planes are still in its cache): the loader then ships 2 * cs instead of 4 * C bytes per pixel
+void stage_tile(const float* src, int64_t Cc, int64_t H, int64_t W, uint16_t* dst, int64_t cs) {
+  const int64_t HW = H * W;
+  for (int64_t h = 0; h < H; ++h) {
+    const float* row = src + h * W;
+    uint16_t* out = dst + h * W * cs;
+    for (int64_t w = 0; w < W; ++w, out += cs) {
+      for (int64_t c = 0; c < Cc; ++c) out[c] = to_bf16(row[c * HW + w]);
+      for (int64_t c = Cc; c < cs; ++c) out[c] = 0;
+    }
+  }
+}
+
 void decode_sample(mau_tiles* t, Batch* b, int64_t slot, int parts) {
   const int64_t i = b->idx[size_t(slot)];
   const bool flip = !b->flip.empty() && b->flip[size_t(slot)];
@@ -799,7 +824,13 @@ void decode_sample(mau_tiles* t, Batch* b, int64_t slot, int parts) {
     });
     bytes += h.count * h.itemsize;
   };
-  if (parts & PART_INPUT) image(M_INPUT, b->input, b->dims);
+  if (parts & PART_INPUT) {
+    image(M_INPUT, b->input, b->dims);
+    if (b->input && b->input_staged) {
+      const int64_t Cc = b->dims[0], H = b->dims[1], W = b->dims[2];
+      stage_tile(b->input + slot * Cc * H * W, Cc, H, W, b->input_staged + slot * H * W * b->staged_cs, b->staged_cs);
+    }
+  }
   if (parts & PART_REST) {
     image(M_TARGET, b->target, b->dims + 3);
     if (b->metadata) {
@@ -980,11 +1011,14 @@ int mau_tiles_series_lengths(mau_tiles* t, const int64_t* idx, int64_t n, int64_
   });
 }
 
-int64_t mau_tiles_submit(mau_tiles* t, const int64_t* idx, int64_t n, const uint8_t* hflip, const int64_t dims[8], float* input, float* target,
-                         float* metadata, float* series, int64_t series_stride, int64_t* series_len) {
+int64_t mau_tiles_submit_staged(mau_tiles* t, const int64_t* idx, int64_t n, const uint8_t* hflip, const int64_t dims[8], float* input,
+                                uint16_t* input_staged, int64_t staged_cs, float* target, float* metadata, float* series,
+                                int64_t series_stride, int64_t* series_len) {
   int rc = guard([&]() -> int {
     if (!t || !dims || n < 0 || (n > 0 && !idx)) return set_err(MAU_TILES_E_ARG, "mau_tiles_submit: null argument");
     if (series && series_stride <= 0) return set_err(MAU_TILES_E_ARG, "mau_tiles_submit: series_stride must be positive");
+    if (input_staged && (!input || staged_cs < dims[0] || staged_cs % 8))
+      return set_err(MAU_TILES_E_ARG, "mau_tiles_submit_staged: needs the fp32 input buffer too and a channel stride that is a multiple of 8 and >= C");
     for (int k = 0; k < 7; ++k)
       if (dims[k] < 0) return set_err(MAU_TILES_E_ARG, "mau_tiles_submit: negative dimension");
     for (int64_t k = 0; k < n; ++k)
@@ -997,6 +1031,8 @@ int64_t mau_tiles_submit(mau_tiles* t, const int64_t* idx, int64_t n, const uint
   if (hflip) b->flip.assign(hflip, hflip + n);
   memcpy(b->dims, dims, sizeof b->dims);
   b->input = input;
+  b->input_staged = input_staged;
+  b->staged_cs = staged_cs;
   b->target = target;
   b->metadata = metadata;
   b->series = series;
@@ -1019,6 +1055,11 @@ int64_t mau_tiles_submit(mau_tiles* t, const int64_t* idx, int64_t n, const uint
     }
   }
   return ticket;
+}
+
+int64_t mau_tiles_submit(mau_tiles* t, const int64_t* idx, int64_t n, const uint8_t* hflip, const int64_t dims[8], float* input, float* target,
+                         float* metadata, float* series, int64_t series_stride, int64_t* series_len) {
+  return mau_tiles_submit_staged(t, idx, n, hflip, dims, input, nullptr, 0, target, metadata, series, series_stride, series_len);
 }
 
 int mau_tiles_wait(mau_tiles* t, int64_t ticket) {

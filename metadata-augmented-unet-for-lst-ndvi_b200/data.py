@@ -43,7 +43,8 @@ FLAG_NO_CRC, FLAG_ZLIB, FLAG_NICE = 1, 2, 4
 
 # every symbol include/mau_tiles.h declares (tests check the .so exports all of them)
 EXPORTS = ("mau_tiles_last_error", "mau_tiles_version", "mau_tiles_open", "mau_tiles_close", "mau_tiles_count",
-           "mau_tiles_threads", "mau_tiles_probe", "mau_tiles_series_lengths", "mau_tiles_read_batch", "mau_tiles_submit", "mau_tiles_wait",
+           "mau_tiles_threads", "mau_tiles_probe", "mau_tiles_series_lengths", "mau_tiles_read_batch", "mau_tiles_submit", "mau_tiles_submit_staged",
+           "mau_tiles_wait",
            "mau_tiles_done", "mau_tiles_repack", "mau_tiles_inflate", "mau_tiles_crc32", "mau_tiles_stats")
 
 _lib = None
@@ -76,6 +77,8 @@ def lib():
         L.mau_tiles_read_batch.argtypes = batch
         L.mau_tiles_submit.argtypes = batch
         L.mau_tiles_submit.restype = C.c_int64
+        L.mau_tiles_submit_staged.argtypes = [C.c_void_p, p64, C.c_int64, pu8, p64, pf, C.c_void_p, C.c_int64, pf, pf, pf, C.c_int64, C.c_void_p]
+        L.mau_tiles_submit_staged.restype = C.c_int64
         L.mau_tiles_wait.argtypes = [C.c_void_p, C.c_int64]
         L.mau_tiles_done.argtypes = [C.c_void_p, C.c_int64]
         L.mau_tiles_stats.argtypes = [C.c_void_p, p64, p64, p64]
@@ -275,9 +278,15 @@ class FuturePredictionDataset(Dataset):
         return {"payload_bytes": a.value, "archive_bytes": b.value, "samples": c.value}
 
     # -- staging buffers -----------------------------------------------------------------------------------
-    def alloc_staging(self, n: int, pin: bool = False, dims: Optional[Sequence[int]] = None):
+    def alloc_staging(self, n: int, pin: bool = False, dims: Optional[Sequence[int]] = None, stage_bf16: bool = False):
         d = list(dims) if dims is not None else self.batch_dims()
         kw = dict(dtype=torch.float32, pin_memory=bool(pin))
+        st = self._alloc_staging(n, d, kw)
+        if stage_bf16:      # the input tiles a second time in the engine's staged layout (bf16 NHWC, channel stride padded to 8)
+            st["input_staged"] = torch.empty((n, d[1], d[2], (d[0] + 7) // 8 * 8), dtype=torch.bfloat16, pin_memory=bool(pin))
+        return st
+
+    def _alloc_staging(self, n, d, kw):
         return {
             "dims": d,
             "input": torch.empty((n, d[0], d[1], d[2]), **kw),
@@ -300,9 +309,15 @@ class FuturePredictionDataset(Dataset):
         idx = (C.c_int64 * n)(*[int(i) for i in indices])
         fl = (C.c_uint8 * n)(*[1 if f else 0 for f in flips]) if flips is not None else None
         dims = (C.c_int64 * 8)(*st["dims"])
-        ticket = lib().mau_tiles_submit(self._handle, idx, n, fl, dims, st["input"].data_ptr(), st["target"].data_ptr(),
-                                        st["metadata"].data_ptr(), st["series"].data_ptr(), st["series"].shape[1],
-                                        st["series_len"].data_ptr())
+        staged = st.get("input_staged")
+        if staged is not None and self.transform is not None and not isinstance(self.transform, RandomFlip):
+            raise ValueError("stage_bf16 converts the tiles inside the decode pass: only RandomFlip (applied there too) is "
+                             "supported as a transform, an arbitrary callable would run on the fp32 copy only")
+        ticket = lib().mau_tiles_submit_staged(self._handle, idx, n, fl, dims, st["input"].data_ptr(),
+                                               staged.data_ptr() if staged is not None else None,
+                                               staged.shape[3] if staged is not None else 0, st["target"].data_ptr(),
+                                               st["metadata"].data_ptr(), st["series"].data_ptr(), st["series"].shape[1],
+                                               st["series_len"].data_ptr())
         if ticket < 0:
             _raise(int(-ticket))
         return _Ticket(self, ticket, list(indices), list(flips) if flips is not None else None, st, n, min_width)
@@ -384,7 +399,8 @@ def _batch_from_staging(st, device: torch.device, non_blocking: bool = False):
     if width > st["series"].shape[1]:
         raise RuntimeError(f"series width {width} exceeds the staging row {st['series'].shape[1]}")
     to = dict(device=device, non_blocking=non_blocking)
-    inputs = st["input"][:n].to(**to)
+    # stage_bf16: ship the bf16 NHWC tiles (48 instead of 92 bytes per pixel); the model accepts them as `maps`
+    inputs = (st["input_staged"] if "input_staged" in st else st["input"])[:n].to(**to)
     metadatas = st["metadata"][:n].to(**to)
     targets = st["target"][:n].to(**to)
     dates = st["dates"][:n].to(**to)
@@ -423,12 +439,13 @@ class TileLoader:
     contiguous slice (all ranks must share the torch seed, as src/train.py:109 sets it)."""
 
     def __init__(self, dataset: FuturePredictionDataset, batch_size: int, shuffle: bool, device=None, prefetch: int = 2,
-                 drop_last: bool = False, rank: int = 0, world_size: int = 1, generator=None):
+                 drop_last: bool = False, rank: int = 0, world_size: int = 1, generator=None, stage_bf16: bool = False):
         if batch_size <= 0 or world_size <= 0 or not 0 <= rank < world_size:
             raise ValueError("batch_size and world_size must be positive, rank in [0, world_size)")
         self.dataset, self.batch_size, self.shuffle = dataset, int(batch_size), bool(shuffle)
         self.device = _resolve_device(device)
         self.prefetch = max(1, int(prefetch))
+        self.stage_bf16 = bool(stage_bf16)      # yield `inputs` as the engine's staged bf16 NHWC tiles (halves the PCIe bytes)
         self.rank, self.world_size = int(rank), int(world_size)
         self.sampler = RandomSampler(dataset, generator=generator) if shuffle else SequentialSampler(dataset)
         self.batch_sampler = BatchSampler(self.sampler, self.batch_size * self.world_size, drop_last)
@@ -464,7 +481,7 @@ class TileLoader:
             return
         rings, self._rings = self._rings, None
         if rings is None or any(st["series"].shape[1] < ds._series_capacity for st in rings):
-            rings = [ds.alloc_staging(self.batch_size, pin=self._pin) for _ in range(self.prefetch + 2)]
+            rings = [ds.alloc_staging(self.batch_size, pin=self._pin, stage_bf16=self.stage_bf16) for _ in range(self.prefetch + 2)]
         free = deque(rings)
         busy = {}                     # id(staging set) -> event of its last H2D copy
         inflight = deque()            # decode tickets, oldest first
@@ -542,11 +559,12 @@ class TileLoader:
 
 def create_dataloader(split: str, batch_size: int, shuffle: bool, dataset_type: str, transform=None, num_workers: int = 0,
                       *, device=None, processed_dir: Optional[str] = None, prefetch: int = 2, drop_last: bool = False,
-                      rank: int = 0, world_size: int = 1, threads: Optional[int] = None, generator=None) -> TileLoader:
+                      rank: int = 0, world_size: int = 1, threads: Optional[int] = None, generator=None,
+                      stage_bf16: bool = False) -> TileLoader:
     """src/dataset.py:110-131 with the same positional arguments.  ``num_workers`` sizes the native decode pool
     (0, the reference's value, means all online cores -- there are no worker *processes*)."""
     assert dataset_type == "future", "Only 'future' dataset_type is supported in create_dataloader."
     ds = FuturePredictionDataset(split=split, transform=transform, processed_dir=processed_dir,
                                  threads=int(threads if threads is not None else num_workers))
     return TileLoader(ds, batch_size, shuffle, device=device, prefetch=prefetch, drop_last=drop_last, rank=rank,
-                      world_size=world_size, generator=generator)
+                      world_size=world_size, generator=generator, stage_bf16=stage_bf16)

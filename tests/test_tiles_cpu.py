@@ -136,6 +136,30 @@ def test_native_reader_equals_oracle_on_fresh_archives(synth, split, batch):
     assert st["samples"] == len(files) and st["payload_bytes"] > 0
 
 
+@pytest.mark.parametrize("flip", [False, True])
+def test_stage_bf16_yields_the_engines_staged_layout_bit_exactly(synth, flip):
+    """create_dataloader(..., stage_bf16=True): `inputs` arrive as bf16 NHWC [B, H, W, 24] (converted inside the decode
+    pass, RandomFlip included) and must equal engine.stage_maps of the fp32 batches; everything else is unchanged.  An
+    arbitrary transform callable is refused (it would only see the fp32 copy)."""
+    from mau_b200 import engine
+
+    def loaders(**kw):
+        torch.manual_seed(7)
+        tf = D.RandomFlip(3) if flip else None
+        return D.create_dataloader("train", 4, True, "future", transform=tf, device="cpu", processed_dir=synth, num_workers=3, **kw)
+    plain, staged = list(loaders()), list(loaders(stage_bf16=True))
+    assert len(plain) == len(staged) > 0
+    for a, b in zip(plain, staged):
+        want = engine.stage_maps(a[0])
+        assert b[0].dtype == torch.bfloat16 and b[0].shape == want.shape == (a[0].shape[0], a[0].shape[2], a[0].shape[3], 24)
+        assert torch.equal(b[0].view(torch.int16), want.view(torch.int16))
+        for k in range(1, 7):
+            assert torch.equal(a[k], b[k]), k
+    with pytest.raises(ValueError, match="stage_bf16"):
+        list(D.create_dataloader("train", 4, False, "future", transform=lambda x, y: (x, y), device="cpu", processed_dir=synth,
+                                 stage_bf16=True))
+
+
 def test_drop_last_and_len(synth):
     loader = D.create_dataloader("train", 4, False, "future", device="cpu", processed_dir=synth, drop_last=True)
     assert len(loader) == 2 and sum(b[0].shape[0] for b in loader) == 8

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--no-crc", action="store_true")
     ap.add_argument("--zlib", action="store_true", help="inflate through zlib instead of the reader's own decoder")
     ap.add_argument("--stored", action="store_true", help="archives written with np.savez (stored members, no deflate)")
+    ap.add_argument("--stage-bf16", action="store_true", help="also convert every decoded tile to the engine's staged bf16 NHWC layout in the decode pass")
     a = ap.parse_args()
 
     root = a.dir or tempfile.mkdtemp(prefix="mau_tiles_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
@@ -67,7 +68,7 @@ def main():
     rows = []
     for th in [int(x) for x in a.threads.split(",")]:
         ds = D.FuturePredictionDataset("train", processed_dir=root, threads=th, verify_crc=not a.no_crc, use_zlib=a.zlib)
-        loader = D.TileLoader(ds, a.batch, False, device=dev, prefetch=2)
+        loader = D.TileLoader(ds, a.batch, False, device=dev, prefetch=2, stage_bf16=a.stage_bf16)
         for _ in loader:        # warm-up epoch: page cache, staging ring
             pass
         s0 = ds.stats()
@@ -86,7 +87,7 @@ def main():
         ds.close()
     out = {"bench": "tile loader", "tile": [23, a.edge, a.edge], "tiles": len(files), "batch": a.batch, "device": str(dev),
            "archive_bytes_per_tile": archive // len(files), "payload_bytes_per_tile": (25 * a.edge * a.edge + 4 + 828) * 4,
-           "host_cores": os.cpu_count(), "crc": not a.no_crc, "members": "stored" if a.stored else "deflate", "inflate": "zlib" if a.zlib else "own decoder",
+           "host_cores": os.cpu_count(), "crc": not a.no_crc, "members": "stored" if a.stored else "deflate", "inflate": "zlib" if a.zlib else "own decoder", "stage_bf16": a.stage_bf16,
            "reference_path": {"tiles_per_s": round(n_ref / t_ref, 1), "threads": 1, "what": "oracle/dataset_oracle.py: np.load + stack + pad_sequence"},
            "native": rows}
     print(json.dumps(out))
