@@ -64,3 +64,31 @@ def test_training_steps_fed_from_archives(synth):
         opt.zero_grad(set_to_none=True)
         losses.append(loss.item())                                       # src/train.py:258: one sync per step
     assert len(losses) == 3 and all(np.isfinite(losses))
+
+
+def test_staged_bf16_batches_drive_the_model_to_identical_outputs(synth):
+    """create_dataloader(..., stage_bf16=True) ships the tiles as bf16 NHWC (half the PCIe bytes); the model must return
+    exactly what it returns for the fp32 NCHW batches of the plain loader (eval forward, and the loss of a training step)."""
+    torch.manual_seed(0)
+    kw = dict(temporal_embeddings=True, metadata_embeddings=True)
+    model = mau_b200.UrbanPredictor("unet", 23, 828, 16, 8, 16, 32, 2, base_filters=16, **kw).to("cuda:0")
+
+    def batches(**opt):
+        torch.manual_seed(5)
+        return list(D.create_dataloader("train", 4, True, "future", transform=D.RandomFlip(9), device="cuda:0", processed_dir=synth,
+                                        drop_last=True, **opt))
+    plain, staged = batches(), batches(stage_bf16=True)
+    assert len(plain) == len(staged) == 3
+    for p, s in zip(plain, staged):
+        assert s[0].dtype == torch.bfloat16 and s[0].shape == (4, 48, 48, 24) and s[0].is_cuda
+        md = torch.cat([p[1], p[4], p[5]], dim=1)
+        model.eval()
+        with torch.no_grad():
+            assert torch.equal(model(p[0], p[2], md), model(s[0], s[2], md))
+        model.train()
+        sd0 = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "tracked" in k}
+        la = float((model(p[0], p[2], md) - p[6]).abs().mean())
+        for k, v in sd0.items():
+            model.state_dict()[k].copy_(v)
+        lb = float((model(s[0], s[2], md) - s[6]).abs().mean())
+        assert la == lb
