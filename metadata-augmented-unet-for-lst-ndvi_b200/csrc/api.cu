@@ -439,7 +439,7 @@ int mau_op_bw_bench(int kind, int dtype, int B, int H, int W, int C, int iters, 
   bilinear_axis_tables(H2, H, &hy);
   bilinear_axis_tables(W2, W, &hx);
   BilinearTables t;
-  t.Hin = H2; t.Win = W2; t.Hout = H; t.Wout = W; t.max_fan_w = hx.max_fan;
+  t.Hin = H2; t.Win = W2; t.Hout = H; t.Wout = W; t.max_fan_w = hx.max_fan; t.vh_tile = bilinear_vh_tile(hx);
   auto up = [&](const void* src, size_t bytes) -> void* { void* d = dalloc(bytes); if (d) cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice); return d; };
   t.ty_off = (int*)up(hy.t_off.data(), 4 * hy.t_off.size()); t.ty_idx = (int*)up(hy.t_idx.data(), 4 * hy.t_idx.size());
   t.ty_w = (float*)up(hy.t_w.data(), 4 * hy.t_w.size());
@@ -509,6 +509,36 @@ int mau_op_bilinear(int dtype, const void* x_dev, int B, int Hin, int Win, int C
   t.x0 = (int*)up(hx.i0.data(), 4 * hx.i0.size()); t.x1 = (int*)up(hx.i1.data(), 4 * hx.i1.size());
   t.lx = (float*)up(hx.l.data(), 4 * hx.l.size());
   int rc = op_bilinear(dtype, mkview(x_dev, B, Hin, Win, C, C), mkview(y_dev, B, Hout, Wout, C, C), t, st);
+  cudaStreamSynchronize(st);
+  for (void* p : tmp) cudaFree(p);
+  return rc;
+}
+
+int mau_op_bilinear_bwd(int dtype, const void* gy_dev, int B, int Hin, int Win, int C, int Hout, int Wout, void* gx_dev,
+                        int accumulate, int form, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (form < 0 || form > 2) return fail("bilinear_bwd: form must be 0, 1 or 2");
+  BilinearHost hy, hx;
+  bilinear_axis_tables(Hin, Hout, &hy);
+  bilinear_axis_tables(Win, Wout, &hx);
+  BilinearTables t;
+  t.Hin = Hin; t.Win = Win; t.Hout = Hout; t.Wout = Wout;
+  t.max_fan_w = form == 2 ? (1 << 30) : hx.max_fan;        // form 2: the table-driven general kernel
+  t.vh_tile = form == 0 ? bilinear_vh_tile(hx) : 0;
+  std::vector<void*> tmp;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(bytes, 4)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    tmp.push_back(d);
+    return d;
+  };
+  t.ty_off = (int*)up(hy.t_off.data(), 4 * hy.t_off.size()); t.ty_idx = (int*)up(hy.t_idx.data(), 4 * hy.t_idx.size());
+  t.ty_w = (float*)up(hy.t_w.data(), 4 * hy.t_w.size());
+  t.tx_off = (int*)up(hx.t_off.data(), 4 * hx.t_off.size()); t.tx_idx = (int*)up(hx.t_idx.data(), 4 * hx.t_idx.size());
+  t.tx_w = (float*)up(hx.t_w.data(), 4 * hx.t_w.size());
+  int rc = (t.ty_off && t.ty_idx && t.ty_w && t.tx_off && t.tx_idx && t.tx_w) ? 0 : fail("bilinear_bwd: table allocation failed");
+  if (!rc) rc = op_bilinear_bwd(dtype, mkview(gy_dev, B, Hout, Wout, C, C), mkview(gx_dev, B, Hin, Win, C, C), t, accumulate, st);
   cudaStreamSynchronize(st);
   for (void* p : tmp) cudaFree(p);
   return rc;

@@ -23,6 +23,15 @@ static std::atomic<int> g_sm_reserve{-1};
 static thread_local int t_reserve_override = -1;     // >= 0: used instead of the global reserve (plan build scopes)
 void set_sm_reserve_override(int n) { t_reserve_override = n; }
 void set_sm_reserve(int n) { g_sm_reserve.store(n < 0 ? 0 : n); }
+// MAU_WHOLE_WAVES=0 keeps the grids of the equal-work element-wise kernels as they were before they were rounded
+// down to whole waves of resident blocks (A/B measurements)
+bool whole_waves_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MAU_WHOLE_WAVES");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 int sm_budget() {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

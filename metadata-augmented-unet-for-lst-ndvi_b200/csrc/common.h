@@ -51,6 +51,7 @@ struct View {
   long long pixels() const { return (long long)B * H * W; }
 };
 
+bool whole_waves_enabled();   // grids of equal-work element-wise kernels rounded down to whole waves (MAU_WHOLE_WAVES=0: off)
 int sm_budget();              // SMs persistent kernels may occupy (device SM count - reserve)
 void set_sm_reserve(int n);   // SMs left free for concurrent collective kernels (data-parallel training)
 void set_sm_reserve_override(int n);   // per-thread scope: >= 0 replaces the global reserve, -1 ends the scope

@@ -5,6 +5,8 @@
 #include "ops.h"
 #include "vec.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace mau {
 namespace {
@@ -178,12 +180,7 @@ __global__ void maxpool_bwd_kernel(DView x, DView gy, DView add, int has_add, DV
 // grid: x over (ow, channel group) of one output row, y = b * Hout + oh.  Source index and lambda are
 // recomputed with the same fp32 operations ATen uses (scale * dst, truncation), so no table loads sit
 // in front of the data loads.
-__device__ __forceinline__ void src_index(float scale, int o, int in_size, int& i0, int& i1, float& l1) {
-  const float real = __fmul_rn(scale, (float)o);
-  i0 = min((int)real, in_size - 1);
-  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
-  l1 = fminf(fmaxf(__fsub_rn(real, (float)i0), 0.f), 1.f);
-}
+#include "bilinear_index.cuh"
 // One thread = one (output column, 8-channel group) for kRows consecutive output rows: all 4*kRows source
 // vectors are requested before the first is used (bytes in flight per thread, not occupancy, is what
 // buys bandwidth here); neighbouring rows share source rows, which L1 serves.
@@ -295,7 +292,7 @@ __global__ void __launch_bounds__(256) bilinear_stream_kernel(DView x, DView y, 
 // Fast path (every source column receives at most kMaxE contributions -- always true when up-sampling):
 // the column list is read once, then for every contributing output row the <= kMaxE gy vectors are
 // requested as one batch.
-constexpr int kMaxE = 6;
+constexpr int kMaxE = kBilinearMaxFan;
 template <typename T>
 __global__ void __launch_bounds__(256) bilinear_bwd_kernel(DView gy, DView gx, BilinearTables t, int accumulate) {
   using Raw = typename V8<T>::Raw;
@@ -469,6 +466,8 @@ __global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DVie
     emit(row, z);
   }
 }
+
+#include "bilinear_vh.cuh"
 
 // general form (any number of contributions per source index, e.g. down-sampling)
 template <typename T>
@@ -766,30 +765,13 @@ int op_maxpool_bwd(int dt, const View& x, const View& gy, const View* addend, co
   return 0;
 }
 
-void bilinear_axis_tables(int in, int out, BilinearHost* h) {
-  // area_pixel_compute_scale / compute_source_index_and_lambda of ATen for align_corners=True, in fp32
-  h->i0.resize(out); h->i1.resize(out); h->l.resize(out);
-  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
-  std::vector<std::vector<std::pair<int, float>>> inv(in);
-  for (int o = 0; o < out; ++o) {
-    const float real = scale * (float)o;
-    int i0 = (int)real;
-    if (i0 > in - 1) i0 = in - 1;
-    const int i1 = i0 + (i0 < in - 1 ? 1 : 0);
-    float l1 = real - (float)i0;
-    l1 = l1 < 0.f ? 0.f : (l1 > 1.f ? 1.f : l1);
-    h->i0[o] = i0; h->i1[o] = i1; h->l[o] = l1;
-    inv[i0].push_back({o, 1.f - l1});
-    inv[i1].push_back({o, l1});
-  }
-  h->t_off.assign(in + 1, 0);
-  h->t_idx.clear(); h->t_w.clear();
-  h->max_fan = 0;
-  for (int i = 0; i < in; ++i) {
-    h->max_fan = std::max(h->max_fan, (int)inv[i].size());
-    for (auto& e : inv[i]) { h->t_idx.push_back(e.first); h->t_w.push_back(e.second); }
-    h->t_off[i + 1] = (int)h->t_idx.size();
-  }
+// MAU_BILINEAR_BWD=stream selects the previous (input-column) streaming kernel, for A/B measurements
+static int bilinear_bwd_form() {
+  static const int form = [] {
+    const char* e = getenv("MAU_BILINEAR_BWD");
+    return (e && !strcmp(e, "stream")) ? 1 : 0;
+  }();
+  return form;
 }
 int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st) {
   if (!vec_ok(x) || !vec_ok(y) || x.C != y.C || t.Hin != x.H || t.Win != x.W || t.Hout != y.H || t.Wout != y.W)
@@ -817,6 +799,18 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
     return fail("bilinear_bwd: bad views/tables");
   if (t.max_fan_w <= kMaxE && gx.H <= gy.H && gx.H >= 2 && gx.B <= 65535) {
     const float sy = gy.H > 1 ? (float)(gx.H - 1) / (float)(gy.H - 1) : 0.f;
+    if (t.vh_tile > 0 && bilinear_bwd_form() == 0 && (long long)gy.H * gy.W * gy.cs < (1ll << 31)) {     // rows first, columns through shared memory (bilinear_vh.cuh)
+      const int G = gx.C / 8;
+      int cg_shift = 0;
+      while (cg_shift < 3 && G % (2 << cg_shift) == 0) ++cg_shift;
+      const int tiles = ceil_div(gx.W, t.vh_tile), chunks = G >> cg_shift;
+      int strip = 16;
+      while (strip > 4 && (long long)tiles * chunks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
+      const dim3 grid((unsigned)(tiles * chunks), (unsigned)ceil_div(gx.H, strip), (unsigned)gx.B);
+      MAU_DISPATCH(dt, bilinear_bwd_vh_kernel, grid, 32 << cg_shift, 0, st, dv(gy), dv(gx), t, sy, strip, t.vh_tile, cg_shift,
+                   accumulate);
+      return 0;
+    }
     const int colblocks = ceil_div(gx.W * (gx.C / 8), 256);
     int strip = 16;
     while (strip > 4 && (long long)colblocks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
@@ -879,6 +873,20 @@ static bool head_ok(const View& x, int OC) {
     MAU_LAUNCHED();                                                                                       \
   } while (0)
 
+template <typename K>
+static int head_occupancy(K kernel, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+  return n;
+}
+#define MAU_HEAD_OCCUPANCY(KERNEL, OUT, SMEM)                                                             \
+  do {                                                                                                    \
+    if (dt == DT_BF16) OUT = OC <= 2 ? head_occupancy(KERNEL<__nv_bfloat16, 2>, SMEM)                     \
+                           : (OC <= 4 ? head_occupancy(KERNEL<__nv_bfloat16, 4>, SMEM) : head_occupancy(KERNEL<__nv_bfloat16, 8>, SMEM)); \
+    else OUT = OC <= 2 ? head_occupancy(KERNEL<float, 2>, SMEM)                                           \
+             : (OC <= 4 ? head_occupancy(KERNEL<float, 4>, SMEM) : head_occupancy(KERNEL<float, 8>, SMEM)); \
+  } while (0)
+
 int op_head(int dt, const View& x, const float* w, const float* bias, int OC, int apply_tanh, float* out_nchw,
             cudaStream_t st) {
   if (!head_ok(x, OC)) return fail("head: needs C = 8*2^k <= 256 and out_channels <= 8 (C=%d, OC=%d)", x.C, OC);
@@ -897,7 +905,12 @@ int op_head_bwd(int dt, const View& x, const float* w, int OC, int apply_tanh, c
   const int per_block = 256 / (x.C / 8);
   const size_t smem = (OC * x.C + OC) * sizeof(float);
   if (x.B > 65535) return fail("head_bwd: batch too large for the per-image grid");
-  const int per_img = std::max(1, std::min(ceil_div(ceil_div(x.H * x.W, kHU), per_block), ceil_div(148 * 6, x.B)));
+  // one wave of equal blocks: blocks-per-image x batch must not exceed what is resident (80 registers -> 3 blocks per SM
+  // for bf16 / 2 outputs; 896 blocks on 444 slots ran as three waves, the last one on 8 SMs)
+  int occ = 0;
+  MAU_HEAD_OCCUPANCY(head_bwd_kernel, occ, smem);
+  const int cap = whole_waves_enabled() ? 148 * occ / x.B : ceil_div(148 * 6, x.B);
+  const int per_img = std::max(1, std::min(ceil_div(ceil_div(x.H * x.W, kHU), per_block), cap));
   const dim3 grid((unsigned)per_img, (unsigned)x.B, 1);
   MAU_HEAD_DISPATCH(head_bwd_kernel, grid, smem, dv(x), w, OC, apply_tanh, out_nchw, gout_nchw, dv(gx), dw, db);
   return 0;

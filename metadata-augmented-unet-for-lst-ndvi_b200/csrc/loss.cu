@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(256) loss_kernel(int kind, const float* __rest
     float g;
     if (kind == 0) { f_pix += fabsf(d); g = sgn(d) * inv_n; }
     else           { f_pix = fmaf(d, d, f_pix); g = 2.f * d * inv_n; }
+    if (!partials && lambda == 0.f) {       // backward-only launch without a gradient term (criterion "l1" / "mse"): no neighbours
+      grad[i] = g;
+      continue;
+    }
     if (h + 1 < H) {   // pair (h, h+1): this pixel is the upper one
       const float a = p[i + W] - pc, b = t[i + W] - tc;
       const float u = fabsf(a) - fabsf(b);

@@ -313,6 +313,19 @@ __global__ void bump_counters_kernel(long long* const* counters, int n) {
 }
 
 inline bool vec_ok(const View& v) { return v.cs % 8 == 0 && v.c0 % 8 == 0 && v.C % 8 == 0 && v.C <= 2048; }
+// Grid-stride element-wise kernels with equal work per block: a grid of 3.3 x the resident blocks ends in a tail wave
+// that leaves most SMs idle (bn_bwd_apply at 125^2: 977 blocks on 296 slots), so grids above one wave are rounded down
+// to whole waves.  Resident blocks per SM come from the occupancy calculator, once per kernel.
+template <typename K>
+int resident_per_sm(K kernel) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+  return n;
+}
+inline long long whole_waves(long long blocks, int per_sm) {
+  const long long slots = 148ll * per_sm;
+  return (blocks > slots && whole_waves_enabled()) ? blocks / slots * slots : blocks;
+}
 inline int reduce_blocks(long long npix, int C) {
   // enough blocks to fill the machine, but at least ~64 pixels per lane-row of a block
   const int L = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
@@ -370,6 +383,9 @@ int op_bn_finalize_apply_relu(int dt, const View& z, const double* sums, long lo
   long long b = (z.pixels() + (long long)L * 16 - 1) / ((long long)L * 16);     // >= 16 pixels per thread amortise the coefficient set-up
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
+  static const int occ_bf16 = resident_per_sm(bn_finalize_apply_relu_kernel<__nv_bfloat16>);
+  static const int occ_f32 = resident_per_sm(bn_finalize_apply_relu_kernel<float>);
+  b = whole_waves(b, dt == DT_BF16 ? occ_bf16 : occ_f32);
   if (dt == DT_BF16)
     bn_finalize_apply_relu_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(z), sums, count, 1.0 / (double)count, gamma, beta, eps, momentum, running_mean,
                                                                        running_var, scale, shift, save_mean, save_rstd, dv(y));
@@ -397,6 +413,9 @@ int op_bn_bwd_apply(int dt, const View& gy, const View& z, const float* scale, c
   long long b = (z.pixels() + (long long)L * 16 - 1) / ((long long)L * 16);     // >= 16 pixels per thread amortise the coefficient set-up
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
+  static const int occ_bf16 = resident_per_sm(bn_bwd_apply_kernel<__nv_bfloat16>);
+  static const int occ_f32 = resident_per_sm(bn_bwd_apply_kernel<float>);
+  b = whole_waves(b, dt == DT_BF16 ? occ_bf16 : occ_f32);
   if (dt == DT_BF16)
     bn_bwd_apply_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>(dv(gy), dv(z), scale, shift, gamma, mean, rstd, sums, count, dv(dz_out), param_sums, dgamma, dbeta, dbias);
   else

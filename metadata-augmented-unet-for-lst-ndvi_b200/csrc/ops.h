@@ -3,6 +3,7 @@
 #pragma once
 #include <vector>
 #include "common.h"
+#include "bilinear_tables.h"
 
 namespace mau {
 
@@ -16,21 +17,6 @@ int op_maxpool(int dt, const View& x, const View& y, cudaStream_t st);
 int op_maxpool_bwd(int dt, const View& x, const View& gy, const View* addend, const View& gx, cudaStream_t st);
 
 // ---- bilinear align_corners=True (reference src/model.py:121,219,245) --------------------------
-struct BilinearTables {          // device arrays owned by the plan
-  int Hin = 0, Win = 0, Hout = 0, Wout = 0;
-  int* y0 = nullptr; int* y1 = nullptr; float* ly = nullptr;   // [Hout]
-  int* x0 = nullptr; int* x1 = nullptr; float* lx = nullptr;   // [Wout]
-  // transposed (gather) form for the backward: CSR over input rows / cols
-  int* ty_off = nullptr; int* ty_idx = nullptr; float* ty_w = nullptr;
-  int* tx_off = nullptr; int* tx_idx = nullptr; float* tx_w = nullptr;
-  int max_fan_w = 1 << 30;     // most contributions any source column receives (selects the batched backward)
-};
-struct BilinearHost {            // host mirror used to build the tables
-  std::vector<int> i0, i1; std::vector<float> l;
-  std::vector<int> t_off, t_idx; std::vector<float> t_w;
-  int max_fan = 0;
-};
-void bilinear_axis_tables(int in, int out, BilinearHost* h);   // PyTorch's index / lambda rule in fp32
 int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st);
 int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables& t, int accumulate,
                     cudaStream_t st);

@@ -50,7 +50,7 @@ EXPORTS = (
     "mau_plan_workspace_bytes", "mau_plan_num_state", "mau_plan_state_info", "mau_plan_describe_config",
     "mau_plan_flops", "mau_plan_exec_flops", "mau_plan_forward", "mau_plan_forward_staged", "mau_plan_backward", "mau_plan_set_grad_hook", "mau_plan_wait_backward_streams", "mau_plan_set_stats_sync", "mau_plan_set_state_version",
     "mau_plan_buffer_ptr", "mau_plan_profile", "mau_plan_profile_read", "mau_loss_forward_backward", "mau_loss_backward", "mau_eval_metrics", "mau_laplacian_sums", "mau_ssim_work_floats", "mau_ssim_loss", "mau_ssim_forward", "mau_ssim_backward",
-    "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_cast_f32_bf16", "mau_cast_bf16_f32", "mau_op_maxpool2x2", "mau_op_bilinear",
+    "mau_op_conv3x3", "mau_op_conv3x3_dgrad", "mau_op_conv3x3_bench", "mau_op_conv3x3_wgrad", "mau_op_conv3x3_wgrad_bench", "mau_set_sm_reserve", "mau_op_bw_bench", "mau_adamw_step", "mau_cast_f32_bf16", "mau_cast_bf16_f32", "mau_op_maxpool2x2", "mau_op_bilinear", "mau_op_bilinear_bwd",
     "mau_op_nchw_to_nhwc", "mau_op_nhwc_to_nchw", "mau_op_lstm_last_hidden",
 )
 
@@ -134,6 +134,8 @@ def lib():
                                         C.c_void_p, C.c_void_p]
         L.mau_op_bilinear.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p]
+        L.mau_op_bilinear_bwd.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.mau_op_nchw_to_nhwc.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p]
         L.mau_op_nhwc_to_nchw.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -23,7 +23,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __shared__ static
-#define __launch_bounds__(n)
+#define __launch_bounds__(...)
 
 struct dim3 {
   unsigned x, y, z;

@@ -134,6 +134,33 @@ def test_layout_pool_bilinear(dt, tol):
         assert rel(yb.permute(0, 3, 1, 2), want) <= max(tol, 2e-7)
 
 
+@pytest.mark.parametrize("dt,tol", [(1, 4e-6), (0, 4e-3)])
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_bilinear_backward_every_kernel_form(dt, tol, form):
+    """mau_op_bilinear_bwd against torch autograd of F.interpolate(align_corners=True) (reference src/model.py:12-17):
+    form 0 = what the plan launches (rows-first kernel of csrc/bilinear_vh.cuh where it applies), 1 = the input-column
+    streaming kernel, 2 = the table-driven general kernel; x2, x2 + 1, + 1, identity, an odd ratio, down-sampling and a
+    ratio with more than six contributions per column (served by the general kernel in every form); = and +=."""
+    L = engine.lib()
+    dtype = torch.float32 if dt == 1 else torch.bfloat16
+    torch.manual_seed(11)
+    #         B  Hin Win  C   Hout Wout
+    shapes = [(2, 21, 35, 24, 42, 70), (2, 21, 35, 64, 43, 71), (1, 30, 30, 128, 31, 31), (2, 9, 11, 16, 9, 11),
+              (1, 12, 50, 8, 37, 125), (1, 2, 2, 8, 9, 9), (1, 19, 23, 8, 9, 11), (3, 62, 62, 256, 124, 124)]
+    for (B, Hin, Win, Cn, Hout, Wout) in shapes:
+        gy = torch.randn(B, Hout, Wout, Cn, device="cuda").to(dtype)
+        x = torch.zeros(B, Cn, Hin, Win, device="cuda", requires_grad=True)
+        F.interpolate(x, size=(Hout, Wout), mode="bilinear", align_corners=True).backward(gy.float().permute(0, 3, 1, 2))
+        want = x.grad.permute(0, 2, 3, 1)
+        for acc in (0, 1):
+            init = torch.randn(B, Hin, Win, Cn, device="cuda").to(dtype) if acc else torch.full((B, Hin, Win, Cn), float("nan"), device="cuda", dtype=dtype)
+            gx = init.clone()
+            engine.check(L.mau_op_bilinear_bwd(dt, gy.data_ptr(), B, Hin, Win, Cn, Hout, Wout, gx.data_ptr(), acc, form, None))
+            ref = want + init.float() if acc else want
+            assert not torch.isnan(gx).any()
+            assert rel(gx.float(), ref) <= tol, (B, Hin, Win, Cn, Hout, Wout, acc, form)
+
+
 @pytest.mark.parametrize("Hd,T,B", [(96, 828, 3), (32, 60, 2)])
 def test_lstm_last_hidden(Hd, T, B):
     torch.manual_seed(3)
