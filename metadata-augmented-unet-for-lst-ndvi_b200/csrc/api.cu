@@ -439,7 +439,7 @@ int mau_op_bw_bench(int kind, int dtype, int B, int H, int W, int C, int iters, 
   bilinear_axis_tables(H2, H, &hy);
   bilinear_axis_tables(W2, W, &hx);
   BilinearTables t;
-  t.Hin = H2; t.Win = W2; t.Hout = H; t.Wout = W; t.max_fan_w = hx.max_fan; t.vh_tile = bilinear_vh_tile(hx);
+  t.Hin = H2; t.Win = W2; t.Hout = H; t.Wout = W; t.max_fan_w = hx.max_fan;
   auto up = [&](const void* src, size_t bytes) -> void* { void* d = dalloc(bytes); if (d) cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice); return d; };
   t.ty_off = (int*)up(hy.t_off.data(), 4 * hy.t_off.size()); t.ty_idx = (int*)up(hy.t_idx.data(), 4 * hy.t_idx.size());
   t.ty_w = (float*)up(hy.t_w.data(), 4 * hy.t_w.size());
@@ -524,7 +524,7 @@ int mau_op_bilinear_bwd(int dtype, const void* gy_dev, int B, int Hin, int Win, 
   BilinearTables t;
   t.Hin = Hin; t.Win = Win; t.Hout = Hout; t.Wout = Wout;
   t.max_fan_w = form == 2 ? (1 << 30) : hx.max_fan;        // form 2: the table-driven general kernel
-  t.vh_tile = form == 0 ? bilinear_vh_tile(hx) : 0;
+  t.force_first_stream = form == 1;
   std::vector<void*> tmp;
   auto up = [&](const void* src, size_t bytes) -> void* {
     void* d = nullptr;

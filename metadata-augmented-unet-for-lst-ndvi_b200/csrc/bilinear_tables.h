@@ -1,7 +1,7 @@
 // bilinear_tables.h -- index / weight tables of the align_corners bilinear resize (reference src/model.py:12-17 and
-// 121 / 219 / 245: F.interpolate(..., mode="bilinear", align_corners=True)) and the tiling of its backward kernel.
-// Plain C++ (no CUDA headers): shared by elementwise.cu, plan.cu, api.cu and by oracle/bilinear_vh_emu.cpp, which runs
-// bilinear_vh.cuh on the CPU with exactly these tables.
+// 121 / 219 / 245: F.interpolate(..., mode="bilinear", align_corners=True)).
+// Plain C++ (no CUDA headers): shared by elementwise.cu, plan.cu, api.cu and by oracle/bilinear_bwd_emu.cpp, which runs
+// bilinear_bwd_lean.cuh on the CPU with exactly these tables.
 #pragma once
 #include <algorithm>
 #include <utility>
@@ -10,7 +10,6 @@
 namespace mau {
 
 constexpr int kBilinearMaxFan = 6;    // contributions per source index the batched backward kernels handle
-constexpr int kBilinearVhCols = 32;   // output columns per CTA of bilinear_bwd_vh_kernel
 
 struct BilinearTables {          // device arrays owned by the plan
   int Hin = 0, Win = 0, Hout = 0, Wout = 0;
@@ -20,7 +19,7 @@ struct BilinearTables {          // device arrays owned by the plan
   int* ty_off = nullptr; int* ty_idx = nullptr; float* ty_w = nullptr;
   int* tx_off = nullptr; int* tx_idx = nullptr; float* tx_w = nullptr;
   int max_fan_w = 1 << 30;     // most contributions any source column receives (selects the batched backward)
-  int vh_tile = 0;             // input columns per CTA of the rows-first backward (bilinear_vh_tile); 0 = not applicable
+  bool force_first_stream = false;   // tests / A-B runs: the first-generation streaming backward kernel
 };
 struct BilinearHost {            // host mirror used to build the tables
   std::vector<int> i0, i1; std::vector<float> l;
@@ -52,29 +51,6 @@ inline void bilinear_axis_tables(int in, int out, BilinearHost* h) {
     for (auto& e : inv[i]) { h->t_idx.push_back(e.first); h->t_w.push_back(e.second); }
     h->t_off[i + 1] = (int)h->t_idx.size();
   }
-}
-
-// Input columns per CTA of bilinear_bwd_vh_kernel: the widest tile (<= kBilinearVhCols) whose contributing output
-// columns span at most kBilinearVhCols for every tile, then evened out over the tiles.  0 when a source column has no
-// contribution (down-sampling) or more than kBilinearMaxFan of them.
-inline int bilinear_vh_tile(const BilinearHost& hx) {
-  const int in = (int)hx.t_off.size() - 1;
-  if (in < 1 || hx.max_fan > kBilinearMaxFan) return 0;
-  for (int i = 0; i < in; ++i)
-    if (hx.t_off[i + 1] <= hx.t_off[i]) return 0;
-  auto fits = [&](int w) {
-    for (int a = 0; a < in; a += w) {
-      const int b = std::min(in, a + w);
-      if (hx.t_idx[hx.t_off[b] - 1] - hx.t_idx[hx.t_off[a]] + 1 > kBilinearVhCols) return false;
-    }
-    return true;
-  };
-  int w = std::min(in, kBilinearVhCols);
-  while (w > 1 && !fits(w)) --w;
-  if (!fits(w)) return 0;
-  const int tiles = (in + w - 1) / w;
-  const int even = (in + tiles - 1) / tiles;     // same number of tiles, last one not much narrower than the others
-  return fits(even) ? even : w;
 }
 
 }  // namespace mau

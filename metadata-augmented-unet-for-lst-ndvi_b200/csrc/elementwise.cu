@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DVie
   }
 }
 
-#include "bilinear_vh.cuh"
+#include "bilinear_bwd_lean.cuh"
 
 // general form (any number of contributions per source index, e.g. down-sampling)
 template <typename T>
@@ -765,7 +765,7 @@ int op_maxpool_bwd(int dt, const View& x, const View& gy, const View* addend, co
   return 0;
 }
 
-// MAU_BILINEAR_BWD=stream selects the previous (input-column) streaming kernel, for A/B measurements
+// MAU_BILINEAR_BWD=stream selects the first-generation streaming kernel, for A/B measurements
 static int bilinear_bwd_form() {
   static const int form = [] {
     const char* e = getenv("MAU_BILINEAR_BWD");
@@ -799,24 +799,16 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
     return fail("bilinear_bwd: bad views/tables");
   if (t.max_fan_w <= kMaxE && gx.H <= gy.H && gx.H >= 2 && gx.B <= 65535) {
     const float sy = gy.H > 1 ? (float)(gx.H - 1) / (float)(gy.H - 1) : 0.f;
-    if (t.vh_tile > 0 && bilinear_bwd_form() == 0 && (long long)gy.H * gy.W * gy.cs < (1ll << 31)) {     // rows first, columns through shared memory (bilinear_vh.cuh)
-      const int G = gx.C / 8;
-      int cg_shift = 0;
-      while (cg_shift < 3 && G % (2 << cg_shift) == 0) ++cg_shift;
-      const int tiles = ceil_div(gx.W, t.vh_tile), chunks = G >> cg_shift;
-      int strip = 16;
-      while (strip > 4 && (long long)tiles * chunks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
-      const dim3 grid((unsigned)(tiles * chunks), (unsigned)ceil_div(gx.H, strip), (unsigned)gx.B);
-      MAU_DISPATCH(dt, bilinear_bwd_vh_kernel, grid, 32 << cg_shift, 0, st, dv(gy), dv(gx), t, sy, strip, t.vh_tile, cg_shift,
-                   accumulate);
-      return 0;
-    }
     const int colblocks = ceil_div(gx.W * (gx.C / 8), 256);
     int strip = 16;
     while (strip > 4 && (long long)colblocks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
     const dim3 grid((unsigned)colblocks, (unsigned)ceil_div(gx.H, strip), (unsigned)gx.B);
-    MAU_DISPATCH(dt, bilinear_bwd_stream_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
-                 accumulate);
+    if (t.force_first_stream || bilinear_bwd_form() == 1 || (long long)gy.H * gy.W * gy.cs >= (1ll << 31))
+      MAU_DISPATCH(dt, bilinear_bwd_stream_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
+                   accumulate);
+    else
+      MAU_DISPATCH(dt, bilinear_bwd_lean_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
+                   accumulate);
     return 0;
   }
   if (t.max_fan_w <= kMaxE)

@@ -419,7 +419,6 @@ int Plan::make_bilinear(int Hin, int Win, int Hout, int Wout, BilinearTables* t)
   t->ty_off = up_i(hy.t_off); t->ty_idx = up_i(hy.t_idx); t->ty_w = up_f(hy.t_w);
   t->tx_off = up_i(hx.t_off); t->tx_idx = up_i(hx.t_idx); t->tx_w = up_f(hx.t_w);
   t->max_fan_w = hx.max_fan;
-  t->vh_tile = bilinear_vh_tile(hx);
   if (!t->tx_w || !t->ty_w) return -1;
   return 0;
 }

@@ -138,15 +138,17 @@ def test_layout_pool_bilinear(dt, tol):
 @pytest.mark.parametrize("form", [0, 1, 2])
 def test_bilinear_backward_every_kernel_form(dt, tol, form):
     """mau_op_bilinear_bwd against torch autograd of F.interpolate(align_corners=True) (reference src/model.py:12-17):
-    form 0 = what the plan launches (rows-first kernel of csrc/bilinear_vh.cuh where it applies), 1 = the input-column
-    streaming kernel, 2 = the table-driven general kernel; x2, x2 + 1, + 1, identity, an odd ratio, down-sampling and a
-    ratio with more than six contributions per column (served by the general kernel in every form); = and +=."""
+    form 0 = what the plan launches (the streaming kernel of csrc/bilinear_bwd_lean.cuh where it applies), 1 = the
+    first-generation streaming kernel, 2 = the table-driven general kernel; x2, x2 + 1, + 1, identity, an odd ratio,
+    down-sampling, rows up / columns down, and a ratio with more than six contributions per column (served by the
+    general kernel in every form); = and +=."""
     L = engine.lib()
     dtype = torch.float32 if dt == 1 else torch.bfloat16
     torch.manual_seed(11)
     #         B  Hin Win  C   Hout Wout
     shapes = [(2, 21, 35, 24, 42, 70), (2, 21, 35, 64, 43, 71), (1, 30, 30, 128, 31, 31), (2, 9, 11, 16, 9, 11),
-              (1, 12, 50, 8, 37, 125), (1, 2, 2, 8, 9, 9), (1, 19, 23, 8, 9, 11), (3, 62, 62, 256, 124, 124)]
+              (1, 12, 50, 8, 37, 125), (1, 2, 2, 8, 9, 9), (1, 19, 23, 8, 9, 11), (1, 6, 20, 8, 12, 9), (3, 62, 62, 256, 124, 124),
+              (2, 124, 124, 64, 125, 125)]
     for (B, Hin, Win, Cn, Hout, Wout) in shapes:
         gy = torch.randn(B, Hout, Wout, Cn, device="cuda").to(dtype)
         x = torch.zeros(B, Cn, Hin, Win, device="cuda", requires_grad=True)

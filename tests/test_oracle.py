@@ -234,24 +234,26 @@ def test_ssim_kernel_source_under_cpu_emulation_equals_torch_autograd(tmp_path):
 
 
 def test_bilinear_backward_kernel_under_cpu_emulation_equals_torch_autograd(tmp_path):
-    """csrc/bilinear_vh.cuh (rows-first backward of the align_corners up-sampling: producer / owner roles, alternating
-    shared-memory buffers with one barrier per finished input row, strip and tile edges) with the host tiling of
-    csrc/bilinear_tables.h, compiled for the CPU on oracle/cuda_emu.h and compared with fp32 torch autograd of
-    F.interpolate (reference src/model.py:12-17).  gx starts as NaN (or as the addend): every element must be written."""
+    """csrc/bilinear_bwd_lean.cuh (streaming backward of the align_corners up-sampling: strip edges, sliding row window,
+    the 2 / 4 / 6-contribution variants, branch-free absent entries) with the tables of csrc/bilinear_tables.h, compiled
+    for the CPU on oracle/cuda_emu.h and compared with fp32 torch autograd of F.interpolate (reference src/model.py:12-17).
+    gx starts as NaN (or as the addend): every element must be written."""
     import ctypes as C
     import subprocess
     import torch.nn.functional as F
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    lib = str(tmp_path / "libbvh_emu.so")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", os.path.join(root, "oracle", "bilinear_vh_emu.cpp"), "-o", lib])
+    lib = str(tmp_path / "libbbl_emu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", os.path.join(root, "oracle", "bilinear_bwd_emu.cpp"), "-o", lib])
     L = C.CDLL(lib)
-    L.emu_bilinear_bwd_vh.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_int]
+    L.emu_bilinear_bwd_lean.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_int]
     g = torch.Generator().manual_seed(4)
     #        B  Hin Win  C  Hout Wout acc strip cs  c0
     cases = [(1, 5, 7, 8, 10, 14, 0, 4, 8, 0), (2, 13, 17, 16, 26, 35, 1, 8, 16, 0), (1, 31, 40, 24, 62, 80, 0, 16, 24, 0),
              (1, 30, 30, 8, 31, 31, 0, 8, 8, 0), (1, 15, 15, 64, 30, 30, 1, 4, 96, 16), (1, 20, 33, 8, 20, 33, 0, 16, 8, 0),
              (1, 12, 50, 8, 37, 125, 0, 5, 8, 0), (1, 2, 3, 8, 4, 6, 0, 4, 8, 0), (1, 9, 11, 128, 18, 22, 0, 4, 128, 0),
-             (2, 7, 9, 40, 15, 19, 0, 4, 48, 8), (1, 62, 62, 8, 125, 125, 0, 16, 8, 0), (1, 124, 124, 8, 125, 125, 1, 16, 8, 0)]
+             (2, 7, 9, 40, 15, 19, 0, 4, 48, 8), (1, 62, 62, 8, 125, 125, 0, 16, 8, 0), (1, 124, 124, 8, 125, 125, 1, 16, 8, 0),
+             (1, 6, 20, 8, 12, 9, 0, 4, 8, 0)]       # last: rows up-sampled, columns down-sampled (columns without a contribution)
+    fans = set()
     for (B, Hin, Win, Cn, Hout, Wout, acc, strip, cs, c0) in cases:
         gy_full = torch.randn(B, Hout, Wout, cs, generator=g)
         x = torch.zeros(B, Cn, Hin, Win, requires_grad=True)
@@ -259,15 +261,17 @@ def test_bilinear_backward_kernel_under_cpu_emulation_equals_torch_autograd(tmp_
         want = x.grad.permute(0, 2, 3, 1)
         init = torch.randn(B, Hin, Win, Cn, generator=g) if acc else torch.full((B, Hin, Win, Cn), float("nan"))
         gx = init.clone()
-        tile = L.emu_bilinear_bwd_vh(gy_full.data_ptr(), B, Hin, Win, Cn, Hout, Wout, cs, c0, gx.data_ptr(), acc, strip)
-        assert 1 <= tile <= 32
+        fan = L.emu_bilinear_bwd_lean(gy_full.data_ptr(), B, Hin, Win, Cn, Hout, Wout, cs, c0, gx.data_ptr(), acc, strip)
+        assert 1 <= fan <= 6
+        fans.add(fan)
         ref = want + init if acc else want
         assert not torch.isnan(gx).any()
         assert (gx - ref).abs().max() < 4e-6, (B, Hin, Win, Cn, Hout, Wout)
+    assert min(fans) <= 2 and any(3 <= f <= 4 for f in fans) and max(fans) >= 5      # every unrolling of the kernel was exercised
     # shapes the kernel does not serve are reported as such (the product then takes the table-driven kernels)
     z = torch.zeros(1, 9, 9, 8)
-    assert L.emu_bilinear_bwd_vh(z.data_ptr(), 1, 2, 2, 8, 9, 9, 8, 0, z.data_ptr(), 0, 4) == 0      # 9 contributions per column
-    assert L.emu_bilinear_bwd_vh(z.data_ptr(), 1, 9, 9, 8, 4, 4, 8, 0, z.data_ptr(), 0, 4) == 0      # down-sampling
+    assert L.emu_bilinear_bwd_lean(z.data_ptr(), 1, 2, 2, 8, 9, 9, 8, 0, z.data_ptr(), 0, 4) == 0      # 9 contributions per column
+    assert L.emu_bilinear_bwd_lean(z.data_ptr(), 1, 9, 9, 8, 4, 4, 8, 0, z.data_ptr(), 0, 4) == 0      # rows down-sampled
 
 
 def test_emulation_shim_reproduces_kernels_that_are_verified_on_hardware(tmp_path):
