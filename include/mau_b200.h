@@ -266,7 +266,9 @@ int mau_op_bilinear(int dtype, const void* x_dev, int B, int Hin, int Win, int C
                     void* y_dev, void* stream);
 /* backward of mau_op_bilinear: gx [B,Hin,Win,C] (=|+=) the transposed resize of gy [B,Hout,Wout,C] (autograd of
  * F.interpolate(..., mode="bilinear", align_corners=True), reference src/model.py:12-17).  form: 0 = the kernel the plan
- * picks for this shape, 1 = the first-generation streaming kernel (A/B), 2 = the table-driven general kernel. */
+ * picks for this shape (the streaming kernel when rows are up-sampled), 1 = the batched per-pixel gather kernel (what
+ * the plan uses when rows are down-sampled and no source column receives more than six contributions), 2 = the
+ * table-driven general kernel. */
 int mau_op_bilinear_bwd(int dtype, const void* gy_dev, int B, int Hin, int Win, int C, int Hout, int Wout,
                         void* gx_dev, int accumulate, int form, void* stream);
 int mau_op_nchw_to_nhwc(int dtype, const float* x_dev, int B, int C, int H, int W, int Cstride,

@@ -524,7 +524,7 @@ int mau_op_bilinear_bwd(int dtype, const void* gy_dev, int B, int Hin, int Win, 
   BilinearTables t;
   t.Hin = Hin; t.Win = Win; t.Hout = Hout; t.Wout = Wout;
   t.max_fan_w = form == 2 ? (1 << 30) : hx.max_fan;        // form 2: the table-driven general kernel
-  t.force_first_stream = form == 1;
+  t.no_stream = form == 1;
   std::vector<void*> tmp;
   auto up = [&](const void* src, size_t bytes) -> void* {
     void* d = nullptr;

@@ -7,16 +7,20 @@
 //
 // One thread owns one (input column, 8-channel group) and walks down the OUTPUT rows that touch its strip of input rows:
 // for every output row the column gather hg = sum_c wx_c * gy[oh, ow_c] is formed once and scattered with the two
-// vertical weights into two sliding accumulators (input rows y0 and y0 + 1).  Same data flow as the first streaming
-// kernel (bilinear_bwd_stream_kernel, which ncu showed issue-bound: 63 % issue-slot utilisation at 51 % of HBM peak,
-// ~350 instructions per thread and output row of which ~100 are loads, unpacks and FMAs); what changed is the
-// bookkeeping around it:
+// vertical weights into two sliding accumulators (input rows y0 and y0 + 1), so every gy vector is read twice in total
+// instead of four times, with block-uniform control flow and no per-row table walks.  The first version of this kernel
+// was issue-bound (ncu: 63 % issue-slot utilisation at 51 % of HBM peak, ~350 instructions per thread and output row of
+// which ~100 are loads, unpacks and FMAs); this one keeps the data flow and trims the bookkeeping (96.4 -> 84.2 us at
+// 16 x 250^2 x 128, 56.0 -> 51.4 us at 16 x 124^2 x 256; profiles/r02_training_step.md):
 //   * the number of column contributions NC is a template parameter chosen per WARP (2 / 4 / 6: the widest lane decides);
 //     lanes with fewer contributions repeat their first one with weight 0, so the loop body has no per-lane predicates
 //     (the old body kept every load and FMA group under `c < nc`: 36 branches and 24 convergence barriers per two rows);
 //   * one 64-bit pointer per contribution, set up once; inside the loop a load address is pointer + 32-bit row offset
 //     (one IMAD.WIDE instead of a 64-bit multiply-add chain per load);
 //   * the first term of every sum is a multiply, not an add to a zeroed register.
+// A rows-first variant (one thread per OUTPUT column, each gy vector loaded once, columns meeting in shared memory with
+// one barrier per finished input row) halved the instruction count again but was no faster alone (96.4 us) and 0.1 ms
+// slower inside the training step (the barrier serialises the load latency of all warps of a block); it was dropped.
 template <typename T, int NC>
 __device__ __forceinline__ void bilinear_bwd_lean_rows(const DView& gy, const DView& gx, const BilinearTables& t, float sy,
                                                        int b, int iw, int g, int ih_b, int ih_e, int accumulate) {

@@ -19,7 +19,7 @@ struct BilinearTables {          // device arrays owned by the plan
   int* ty_off = nullptr; int* ty_idx = nullptr; float* ty_w = nullptr;
   int* tx_off = nullptr; int* tx_idx = nullptr; float* tx_w = nullptr;
   int max_fan_w = 1 << 30;     // most contributions any source column receives (selects the batched backward)
-  bool force_first_stream = false;   // tests / A-B runs: the first-generation streaming backward kernel
+  bool no_stream = false;      // tests: skip the streaming backward kernel (exercises the per-pixel gather kernels)
 };
 struct BilinearHost {            // host mirror used to build the tables
   std::vector<int> i0, i1; std::vector<float> l;

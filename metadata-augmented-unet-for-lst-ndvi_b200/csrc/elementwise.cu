@@ -5,8 +5,6 @@
 #include "ops.h"
 #include "vec.cuh"
 #include <algorithm>
-#include <cstdlib>
-#include <cstring>
 
 namespace mau {
 namespace {
@@ -341,132 +339,7 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(DView gy, DView gx, B
     V8<T>::store(at<T>(gx, opix, g * 8), o);
   }
 }
-// Streaming form of the backward for up-sampling (Hin <= Hout): one thread owns one (input column, 8-channel
-// group) and walks down the OUTPUT rows that touch its strip of input rows.  For every output row the column
-// gather hg = sum_c wx_c * gy[oh, ow_c] is formed once and scattered with the two vertical weights into two
-// sliding accumulators (input rows y0 and y0 + 1), so every gy vector is read twice in total instead of four
-// times, with block-uniform control flow and no per-row table walks.
-template <typename T>
-__global__ void __launch_bounds__(256) bilinear_bwd_stream_kernel(DView gy, DView gx, BilinearTables t, float sy,
-                                                                  FastDiv divG, int rows_per_strip, int accumulate) {
-  using Raw = typename V8<T>::Raw;
-  const unsigned G = gx.C / 8;
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (unsigned)gx.W * G) return;
-  unsigned iw, g;
-  divG.divmod(idx, iw, g);
-  const int b = blockIdx.z;
-  const int ih_b = blockIdx.y * rows_per_strip;
-  const int ih_e = min(gx.H, ih_b + rows_per_strip);
-  const int ca = t.tx_off[iw], nc = t.tx_off[iw + 1] - ca;
-  int off[kMaxE];                                // element offsets inside one gy row (W * cs < 2^31)
-  float wx[kMaxE];
-#pragma unroll
-  for (int e = 0; e < kMaxE; ++e) {
-    off[e] = (e < nc ? t.tx_idx[ca + e] : 0) * gy.cs;
-    wx[e] = e < nc ? t.tx_w[ca + e] : 0.f;
-  }
-  const T* gyb = static_cast<const T*>(gy.ptr) + (long long)b * gy.H * gy.W * gy.cs + gy.c0 + g * 8;
-  T* gxb = static_cast<T*>(gx.ptr) + ((long long)b * gx.H * gx.W + iw) * gx.cs + gx.c0 + g * 8;
-  const long long gyrow = (long long)gy.W * gy.cs, gxrow = (long long)gx.W * gx.cs;
-  // output rows touching input rows [ih_b, ih_e): the row lists are sorted by output row
-  const int oh_first = t.ty_idx[t.ty_off[ih_b]];
-  const int oh_last = t.ty_idx[t.ty_off[ih_e] - 1];
-  float acc0[8], acc1[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
-  int r = ih_b;                                  // input row acc0 belongs to (acc1: r + 1)
-  auto emit = [&](int row, const float (&a)[8]) {
-    float o[8];
-    if (accumulate) {
-      V8<T>::load(gxb + row * gxrow, o);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] += a[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = a[k];
-    }
-    V8<T>::store(gxb + row * gxrow, o);
-  };
-  // Output rows are processed in pairs with two statically named register buffers (the loads of row oh + 1 are in
-  // flight while row oh is consumed).  Most source columns receive at most 4 contributions: slots 4 and 5 are
-  // only touched when some lane of the warp needs them (warp-uniform branch, so the common case issues nothing).
-  const bool wide = __any_sync(__activemask(), nc > 4);   // lanes past the row end have already returned
-  auto load_row = [&](Raw (&buf)[kMaxE], int oh) {
-    const T* rowp = gyb + oh * gyrow;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c < nc) buf[c] = V8<T>::load_raw(rowp + off[c]);
-    if (wide) {
-#pragma unroll
-      for (int c = 4; c < kMaxE; ++c)
-        if (c < nc) buf[c] = V8<T>::load_raw(rowp + off[c]);
-    }
-  };
-  auto consume = [&](const Raw (&buf)[kMaxE], int oh) {
-    int y0, y1; float ly;
-    src_index(sy, oh, gx.H, y0, y1, ly);         // block-uniform
-    while (y0 > r && r < ih_e) {                 // input row r is complete
-      emit(r, acc0);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { acc0[k] = acc1[k]; acc1[k] = 0.f; }
-      ++r;
-    }
-    float hg[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) hg[k] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c < nc) {
-        float v[8];
-        V8<T>::unpack(buf[c], v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) hg[k] = fmaf(wx[c], v[k], hg[k]);
-      }
-    if (wide) {
-#pragma unroll
-      for (int c = 4; c < kMaxE; ++c)
-        if (c < nc) {
-          float v[8];
-          V8<T>::unpack(buf[c], v);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) hg[k] = fmaf(wx[c], v[k], hg[k]);
-        }
-    }
-    const float w0 = 1.f - ly;
-    if (y0 == r) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc0[k] = fmaf(w0, hg[k], acc0[k]);
-      if (y1 != y0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc1[k] = fmaf(ly, hg[k], acc1[k]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc0[k] = fmaf(ly, hg[k], acc0[k]);
-      }
-    } else if (y1 == r && y0 == r - 1) {         // first rows of the strip: only the lower neighbour is ours
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc0[k] = fmaf(ly, hg[k], acc0[k]);
-    }
-  };
-  Raw bufA[kMaxE], bufB[kMaxE];
-  load_row(bufA, oh_first);
-  for (int oh = oh_first; oh <= oh_last; oh += 2) {
-    if (oh + 1 <= oh_last) load_row(bufB, oh + 1);
-    consume(bufA, oh);
-    if (oh + 2 <= oh_last) load_row(bufA, oh + 2);
-    if (oh + 1 <= oh_last) consume(bufB, oh + 1);
-  }
-  if (r < ih_e) emit(r, acc0);
-  if (r + 1 < ih_e) emit(r + 1, acc1);
-  for (int row = r + 2; row < ih_e; ++row) {     // (cannot happen when up-sampling; keeps every row written)
-    float z[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) z[k] = 0.f;
-    emit(row, z);
-  }
-}
-
+// Streaming form of the backward for up-sampling (Hin <= Hout): bilinear_bwd_lean.cuh
 #include "bilinear_bwd_lean.cuh"
 
 // general form (any number of contributions per source index, e.g. down-sampling)
@@ -765,14 +638,6 @@ int op_maxpool_bwd(int dt, const View& x, const View& gy, const View* addend, co
   return 0;
 }
 
-// MAU_BILINEAR_BWD=stream selects the first-generation streaming kernel, for A/B measurements
-static int bilinear_bwd_form() {
-  static const int form = [] {
-    const char* e = getenv("MAU_BILINEAR_BWD");
-    return (e && !strcmp(e, "stream")) ? 1 : 0;
-  }();
-  return form;
-}
 int op_bilinear(int dt, const View& x, const View& y, const BilinearTables& t, cudaStream_t st) {
   if (!vec_ok(x) || !vec_ok(y) || x.C != y.C || t.Hin != x.H || t.Win != x.W || t.Hout != y.H || t.Wout != y.W)
     return fail("bilinear: bad views/tables");
@@ -797,18 +662,15 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
   if (!vec_ok(gx) || !vec_ok(gy) || gx.C != gy.C || t.Hin != gx.H || t.Win != gx.W || t.Hout != gy.H ||
       t.Wout != gy.W)
     return fail("bilinear_bwd: bad views/tables");
-  if (t.max_fan_w <= kMaxE && gx.H <= gy.H && gx.H >= 2 && gx.B <= 65535) {
+  if (!t.no_stream && t.max_fan_w <= kMaxE && gx.H <= gy.H && gx.H >= 2 && gx.B <= 65535 &&
+      (long long)gy.H * gy.W * gy.cs < (1ll << 31)) {
     const float sy = gy.H > 1 ? (float)(gx.H - 1) / (float)(gy.H - 1) : 0.f;
     const int colblocks = ceil_div(gx.W * (gx.C / 8), 256);
     int strip = 16;
     while (strip > 4 && (long long)colblocks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
     const dim3 grid((unsigned)colblocks, (unsigned)ceil_div(gx.H, strip), (unsigned)gx.B);
-    if (t.force_first_stream || bilinear_bwd_form() == 1 || (long long)gy.H * gy.W * gy.cs >= (1ll << 31))
-      MAU_DISPATCH(dt, bilinear_bwd_stream_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
-                   accumulate);
-    else
-      MAU_DISPATCH(dt, bilinear_bwd_lean_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
-                   accumulate);
+    MAU_DISPATCH(dt, bilinear_bwd_lean_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
+                 accumulate);
     return 0;
   }
   if (t.max_fan_w <= kMaxE)

@@ -139,7 +139,7 @@ def test_layout_pool_bilinear(dt, tol):
 def test_bilinear_backward_every_kernel_form(dt, tol, form):
     """mau_op_bilinear_bwd against torch autograd of F.interpolate(align_corners=True) (reference src/model.py:12-17):
     form 0 = what the plan launches (the streaming kernel of csrc/bilinear_bwd_lean.cuh where it applies), 1 = the
-    first-generation streaming kernel, 2 = the table-driven general kernel; x2, x2 + 1, + 1, identity, an odd ratio,
+    batched per-pixel gather kernel, 2 = the table-driven general kernel; x2, x2 + 1, + 1, identity, an odd ratio,
     down-sampling, rows up / columns down, and a ratio with more than six contributions per column (served by the
     general kernel in every form); = and +=."""
     L = engine.lib()
