@@ -103,8 +103,8 @@ __device__ __forceinline__ void bilinear_bwd_lean_rows(const DView& gy, const DV
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2) bilinear_bwd_lean_kernel(DView gy, DView gx, BilinearTables t, float sy, FastDiv divG,
-                                                                  int rows_per_strip, int accumulate) {
+__device__ __forceinline__ void bilinear_bwd_lean_body(const DView& gy, const DView& gx, const BilinearTables& t, float sy,
+                                                       const FastDiv& divG, int rows_per_strip, int accumulate) {
   const unsigned G = gx.C / 8;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (unsigned)gx.W * G) return;
@@ -119,4 +119,17 @@ __global__ void __launch_bounds__(256, 2) bilinear_bwd_lean_kernel(DView gy, DVi
   if (__any_sync(lanes, nc > 4)) bilinear_bwd_lean_rows<T, 6>(gy, gx, t, sy, b, (int)iw, (int)g, ih_b, ih_e, accumulate);
   else if (__any_sync(lanes, nc > 2)) bilinear_bwd_lean_rows<T, 4>(gy, gx, t, sy, b, (int)iw, (int)g, ih_b, ih_e, accumulate);
   else bilinear_bwd_lean_rows<T, 2>(gy, gx, t, sy, b, (int)iw, (int)g, ih_b, ih_e, accumulate);
+}
+// Three resident blocks per SM (80 registers): the 2- and 4-contribution paths fit, the rare 6-contribution path (the two
+// or three warps of a row whose source column is fed by five output columns) spills 80 bytes.  The 127-register build
+// (two resident blocks) is kept next to it for the A/B (MAU_BILINEAR_OCC=2).
+template <typename T>
+__global__ void __launch_bounds__(256, 3) bilinear_bwd_lean_kernel(DView gy, DView gx, BilinearTables t, float sy, FastDiv divG,
+                                                                  int rows_per_strip, int accumulate) {
+  bilinear_bwd_lean_body<T>(gy, gx, t, sy, divG, rows_per_strip, accumulate);
+}
+template <typename T>
+__global__ void __launch_bounds__(256, 2) bilinear_bwd_lean2_kernel(DView gy, DView gx, BilinearTables t, float sy, FastDiv divG,
+                                                                   int rows_per_strip, int accumulate) {
+  bilinear_bwd_lean_body<T>(gy, gx, t, sy, divG, rows_per_strip, accumulate);
 }

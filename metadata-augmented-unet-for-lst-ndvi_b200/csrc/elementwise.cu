@@ -5,6 +5,7 @@
 #include "ops.h"
 #include "vec.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace mau {
 namespace {
@@ -669,8 +670,13 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
     int strip = 16;
     while (strip > 4 && (long long)colblocks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
     const dim3 grid((unsigned)colblocks, (unsigned)ceil_div(gx.H, strip), (unsigned)gx.B);
-    MAU_DISPATCH(dt, bilinear_bwd_lean_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
-                 accumulate);
+    static const bool occ2 = [] { const char* e = getenv("MAU_BILINEAR_OCC"); return e && e[0] == '2'; }();
+    if (occ2)
+      MAU_DISPATCH(dt, bilinear_bwd_lean2_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
+                   accumulate);
+    else
+      MAU_DISPATCH(dt, bilinear_bwd_lean_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
+                   accumulate);
     return 0;
   }
   if (t.max_fan_w <= kMaxE)
