@@ -11,7 +11,7 @@
 // instead of four times, with block-uniform control flow and no per-row table walks.  The first version of this kernel
 // was issue-bound (ncu: 63 % issue-slot utilisation at 51 % of HBM peak, ~350 instructions per thread and output row of
 // which ~100 are loads, unpacks and FMAs); this one keeps the data flow and trims the bookkeeping (96.4 -> 84.2 us at
-// 16 x 250^2 x 128, 56.0 -> 51.4 us at 16 x 124^2 x 256; profiles/r02_training_step.md):
+// 16 x 250^2 x 128, 56.0 -> 51.4 us at 16 x 124^2 x 256 before the occupancy change below; profiles/r02_training_step.md):
 //   * the number of column contributions NC is a template parameter chosen per WARP (2 / 4 / 6: the widest lane decides);
 //     lanes with fewer contributions repeat their first one with weight 0, so the loop body has no per-lane predicates
 //     (the old body kept every load and FMA group under `c < nc`: 36 branches and 24 convergence barriers per two rows);
@@ -121,15 +121,11 @@ __device__ __forceinline__ void bilinear_bwd_lean_body(const DView& gy, const DV
   else bilinear_bwd_lean_rows<T, 2>(gy, gx, t, sy, b, (int)iw, (int)g, ih_b, ih_e, accumulate);
 }
 // Three resident blocks per SM (80 registers): the 2- and 4-contribution paths fit, the rare 6-contribution path (the two
-// or three warps of a row whose source column is fed by five output columns) spills 80 bytes.  The 127-register build
-// (two resident blocks) is kept next to it for the A/B (MAU_BILINEAR_OCC=2).
+// or three warps of a row whose source column is fed by five output columns) spills 80 bytes.  Against the 127-register
+// build (two resident blocks): 84.0 -> 75.5 us at 16 x 250^2 x 128, 49.8 -> 41.1 us at 16 x 124^2 x 256 -- with the issue
+// slots freed by the lean loop the kernel was latency-bound (ncu: 52 % issue, 23 % warps active, 45 % DRAM).
 template <typename T>
 __global__ void __launch_bounds__(256, 3) bilinear_bwd_lean_kernel(DView gy, DView gx, BilinearTables t, float sy, FastDiv divG,
                                                                   int rows_per_strip, int accumulate) {
-  bilinear_bwd_lean_body<T>(gy, gx, t, sy, divG, rows_per_strip, accumulate);
-}
-template <typename T>
-__global__ void __launch_bounds__(256, 2) bilinear_bwd_lean2_kernel(DView gy, DView gx, BilinearTables t, float sy, FastDiv divG,
-                                                                   int rows_per_strip, int accumulate) {
   bilinear_bwd_lean_body<T>(gy, gx, t, sy, divG, rows_per_strip, accumulate);
 }

@@ -5,7 +5,6 @@
 #include "ops.h"
 #include "vec.cuh"
 #include <algorithm>
-#include <cstdlib>
 
 namespace mau {
 namespace {
@@ -524,8 +523,13 @@ __global__ void __launch_bounds__(256) head_pix_kernel(DView x, const float* __r
 
 // backward of the head: per pixel g_o = gout_o * (o==0 && tanh ? 1 - out_0^2 : 1);
 // gx[c] = sum_o g_o W[o][c];  dW[o][c] += g_o x[c];  db[o] += g_o
+#ifdef MAU_HEAD_BWD_OCC4      // bf16 / two outputs compiled for four resident blocks per SM (64 registers)
+#define MAU_HEAD_BWD_BOUNDS __launch_bounds__(256, (sizeof(T) == 2 && OCT == 2) ? 4 : 1)
+#else
+#define MAU_HEAD_BWD_BOUNDS __launch_bounds__(256)
+#endif
 template <typename T, int OCT>
-__global__ void __launch_bounds__(256) head_bwd_kernel(DView x, const float* __restrict__ w, int OC, int apply_tanh,
+__global__ void MAU_HEAD_BWD_BOUNDS head_bwd_kernel(DView x, const float* __restrict__ w, int OC, int apply_tanh,
                                                        const float* __restrict__ out, const float* __restrict__ gout,
                                                        DView gx, float* __restrict__ dw, float* __restrict__ db) {
   using Raw = typename V8<T>::Raw;
@@ -670,13 +674,8 @@ int op_bilinear_bwd(int dt, const View& gy, const View& gx, const BilinearTables
     int strip = 16;
     while (strip > 4 && (long long)colblocks * gx.B * ceil_div(gx.H, strip) < 148 * 8) strip >>= 1;
     const dim3 grid((unsigned)colblocks, (unsigned)ceil_div(gx.H, strip), (unsigned)gx.B);
-    static const bool occ2 = [] { const char* e = getenv("MAU_BILINEAR_OCC"); return e && e[0] == '2'; }();
-    if (occ2)
-      MAU_DISPATCH(dt, bilinear_bwd_lean2_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
-                   accumulate);
-    else
-      MAU_DISPATCH(dt, bilinear_bwd_lean_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
-                   accumulate);
+    MAU_DISPATCH(dt, bilinear_bwd_lean_kernel, grid, 256, 0, st, dv(gy), dv(gx), t, sy, FastDiv((unsigned)(gx.C / 8)), strip,
+                 accumulate);
     return 0;
   }
   if (t.max_fan_w <= kMaxE)

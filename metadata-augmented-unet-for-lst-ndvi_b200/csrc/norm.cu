@@ -214,8 +214,15 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_relu_kernel(DView z, co
   }
 }
 
+// MAU_BN_BWD_MIN_BLOCKS: resident blocks per SM the two backward kernels are compiled for (register cap 65536 / 256 / n);
+// undefined = no cap (a second __launch_bounds__ argument of 1 is NOT the same: it changes ptxas' allocation)
+#ifdef MAU_BN_BWD_MIN_BLOCKS
+#define MAU_BN_BWD_BOUNDS __launch_bounds__(256, MAU_BN_BWD_MIN_BLOCKS)
+#else
+#define MAU_BN_BWD_BOUNDS __launch_bounds__(256)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView z, const float* __restrict__ scale,
+__global__ void MAU_BN_BWD_BOUNDS bn_bwd_reduce_kernel(DView gy, DView z, const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, double* sums) {
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DView gy, DView z, c
 // identically zero under batch-statistics BatchNorm (the mean subtraction removes any constant), so it is not
 // reduced here: the reference's value is fp32 rounding noise around 0, ours is exactly 0.
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DView gy, DView z, const float* __restrict__ scale,
+__global__ void MAU_BN_BWD_BOUNDS bn_bwd_apply_kernel(DView gy, DView z, const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ mean,
@@ -317,9 +324,9 @@ inline bool vec_ok(const View& v) { return v.cs % 8 == 0 && v.c0 % 8 == 0 && v.C
 // that leaves most SMs idle (bn_bwd_apply at 125^2: 977 blocks on 296 slots), so grids above one wave are rounded down
 // to whole waves.  Resident blocks per SM come from the occupancy calculator, once per kernel.
 template <typename K>
-int resident_per_sm(K kernel) {
+int resident_per_sm(K kernel, size_t dyn_smem = 0) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, dyn_smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
   return n;
 }
 inline long long whole_waves(long long blocks, int per_sm) {
@@ -399,7 +406,9 @@ int op_bn_bwd_reduce(int dt, const View& gy, const View& z, const float* scale, 
                      const float* rstd, double* sums, cudaStream_t st) {
   if (!vec_ok(z) || !vec_ok(gy)) return fail("bn_bwd_reduce: bad views");
   const size_t smem = 2 * 256 * 8 * sizeof(float);
-  const int blocks = std::min(reduce_blocks(z.pixels(), z.C), 148 * 2);      // 96 registers: 2 resident blocks per SM, one wave
+  static const int occ_bf16 = resident_per_sm(bn_bwd_reduce_kernel<__nv_bfloat16>, smem);
+  static const int occ_f32 = resident_per_sm(bn_bwd_reduce_kernel<float>, smem);
+  const int blocks = std::min(reduce_blocks(z.pixels(), z.C), 148 * (dt == DT_BF16 ? occ_bf16 : occ_f32));      // one wave of resident blocks
   if (dt == DT_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, mean, rstd, sums);
   else               bn_bwd_reduce_kernel<float><<<blocks, 256, smem, st>>>(dv(gy), dv(z), scale, shift, mean, rstd, sums);
   MAU_LAUNCHED();
