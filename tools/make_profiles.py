@@ -137,6 +137,11 @@ def main():
             f.write(f"# {tag}: achieved HBM bandwidth per bandwidth-bound kernel\n\nSource: `{os.path.relpath(bw, ROOT)}` (`python tools/bw_bench.py`): "
                     "algorithmic bytes / CUDA-event time, tensors rotated over > L2-sized copies, B = 16, against the measured copy "
                     "bandwidth in MEASURED_PEAKS.json.\n\n```\n" + open(bw).read() + "```\n")
+            later = os.path.join(G, "r02o_bw_occ3.txt")
+            if tag == "r02" and os.path.exists(later):
+                f.write("\nThe table above is from the call before the last change to `bilinear_bwd_lean_kernel` (80 registers, three resident "
+                        "blocks per SM instead of 127 / two).  The final kernel, measured in the next call (`tools/r02_occ.sh`):\n\n```\n"
+                        + open(later).read() + "```\n")
     if traffic:
         # bench.py's roofline.traffic: mean DRAM bytes per timed conv-family launch (config 2 times the forward convs,
         # config 3 forward + dgrad + wgrad).  The conv capture is of training-mode launches (same shapes as inference).

@@ -33,7 +33,7 @@ def row(label, name, extra=""):
     d = bench(name)
     if d is None:
         return f"| {label} | — | — | — | — | `{name}.json` missing |\n"
-    shutil.copyfile(os.path.join(G, name + ".json"), os.path.join(P, name.replace("r02c", "r02_bench_c").replace("r02n", "r02_bench_n") + ".json"))
+    shutil.copyfile(os.path.join(G, name + ".json"), os.path.join(P, name.replace("r02c", "r02_bench_c").replace("r02n", "r02_bench_n").replace("r02g_", "r02_bench_final_").replace("r02o_", "r02_bench_occ_").replace("r02p_", "r02_bench_last_") + ".json"))
     s = d.get("sustained") or {}
     e = d.get("e2e") or {}
     return (f"| {label} | {d['ms_per_step']:.3f} | {d['value']:.0f} | {('%.3f' % s['ms_per_step']) if s.get('ms_per_step') else '—'} | "
@@ -66,6 +66,24 @@ def main():
         f.write(row("the same with the reference's default criterion `l1-gradient-ssim` (separable SSIM kernels)", "r02c4_bench_c3_ssim",
                     "first version of the SSIM kernels (121 taps per window): +0.54 ms per step (`r02_bench_c1_bench_c3_ssim.json`)"))
         f.write(row("first SSIM kernels (direct 121-tap form), for reference", "r02c1_bench_c3_ssim", "call 1, on the round-1 step"))
+        f.write(row("call 10 (a faster box): the step as of call 9 (`MAU_BILINEAR_BWD=stream MAU_WHOLE_WAVES=0` at that commit), run 1", "r02c10_c3_old_a", "boxes differ: compare within calls 10 / final / occupancy"))
+        f.write(row("call 10: the same, run 2", "r02c10_c3_old_b", ""))
+        f.write(row("call 10: rows-first bilinear backward (one thread per OUTPUT column, columns meet in shared memory, one barrier per input row) + whole-wave grids, run 1", "r02c10_c3_new_a",
+                    "bilinear_bwd alone 96.4 us either way; in the step +0.1 ms (the barrier serialises the load latency of a block) -> the rows-first kernel was dropped"))
+        f.write(row("call 10: the same, run 2", "r02c10_c3_new_b", ""))
+        f.write(row("call 10: rows-first bilinear backward without the whole-wave grids", "r02c10_c3_vh_only",
+                    "whole-wave grids: head_bwd 97.9 -> 74.3 us, bn_bwd_apply @62^2 28.8 -> 23.3 us alone (`tools/bw_bench.py`); below the noise of the step"))
+        f.write(row("final call: first-generation streaming bilinear backward (`MAU_BILINEAR_BWD=stream` at that commit), run 1", "r02g_c3_first_a", ""))
+        f.write(row("final call: the same, run 2", "r02g_c3_first_b", ""))
+        f.write(row("final call: lean streaming bilinear backward (warp-uniform 2/4/6 unrolling, no per-lane predicates, pointer + 32-bit offset), run 1", "r02g_c3_lean_a",
+                    "bilinear_bwd alone: 96.4 -> 84.2 us (16 x 250^2 x 128), 56.0 -> 51.4 us (16 x 124^2 x 256)"))
+        f.write(row("final call: the same, run 2", "r02g_c3_lean_b", ""))
+        f.write(row("occupancy call: lean kernel, 127 registers / two resident blocks (`MAU_BILINEAR_OCC=2` at that commit)", "r02o_c3_occ2", ""))
+        f.write(row("occupancy call: lean kernel compiled for three resident blocks (80 registers; only the rare 6-contribution path spills) (final)", "r02o_c3_occ3",
+                    "bilinear_bwd alone: 84.0 -> 75.5 us, 49.8 -> 41.1 us"))
+        f.write(row("last call: default build (= final)", "r02p_c3_default", ""))
+        f.write(row("last call: BatchNorm backward kernels compiled for three resident blocks (80 registers, spills in the loop), head backward for four", "r02p_c3_occ",
+                    "bn_bwd_reduce @250^2 51.1 -> 83.8 us, bn_bwd_apply 70.9 -> 105.0 us, head_bwd 73.6 -> 72.2 us: spilled coefficients cost more than the extra warps hide -> not adopted"))
         f.write("\nU-Net++ (config 4, B = 16):\n\n| change | ms/step | tiles/s | sustained | e2e | note |\n|---|---:|---:|---:|---:|---|\n")
         f.write(row("`MAU_FLAGS=8192`", "r02c4_bench_c4_nooverlap", "call 4"))
         f.write(row("second-stream weight gradients", "r02c4_bench_c4", ""))
@@ -75,6 +93,10 @@ def main():
             f.write("\nPer-launch times of the weight-gradient kernels with the tap-pair kernel (CUDA events around each launch, call 3):\n\n```\n")
             f.write("".join(l for l in open(lay) if "wgrad" in l and l.startswith("k:")))
             f.write("```\n")
+    # the default bench line of the final call (the driver's form) next to the CPU reference arm of the previous final run
+    for src, dst in (("r02g_bench_default.json", "r02_bench_default.json"),):
+        if os.path.exists(os.path.join(G, src)):
+            shutil.copyfile(os.path.join(G, src), os.path.join(P, dst))
     # timelines
     with open(os.path.join(P, "r02_timeline.md"), "w") as f:
         f.write("# r02: kernel timeline of one training step (CUPTI through torch.profiler; nsys is not in the image)\n\n"
