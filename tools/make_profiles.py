@@ -130,7 +130,11 @@ def main():
         traffic["wgrad"] = per_launch(recs)
     for src in sorted(glob.glob(os.path.join(G, "prof_bw*_raw.csv"))):
         base = os.path.basename(src).replace("_raw.csv", "")
-        full(src, os.path.join(P, f"{tag}_ncu_{base}.md"), f"{tag}: bandwidth-bound kernels ({base}), tools/bw_bench.py shapes at B=16")
+        what = base
+        if base == "prof_bw3":
+            what = ("touched at the end of round 2 (prof_bw3: bilinear_bwd_lean at 127 registers -- the 80-register build came one call "
+                    "later --, head_bwd and bn_bwd_apply with whole-wave grids)")
+        full(src, os.path.join(P, f"{tag}_ncu_{base}.md"), f"{tag}: bandwidth-bound kernels {what if base == 'prof_bw3' else '(' + what + ')'}, tools/bw_bench.py shapes at B=16")
     bw = latest("bw_bench*.txt")
     if bw:
         with open(os.path.join(P, f"{tag}_bw_bench.md"), "w") as f:
