@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2, call 10: rows-first bilinear backward (csrc/bilinear_vh.cuh) + whole-wave grids (head_bwd, BN apply kernels):
 # GPU tests, per-kernel bandwidth A/B, training-step A/B (new / old interleaved, same box)
+# (historical record of the call: csrc/bilinear_vh.cuh and the MAU_BILINEAR_BWD switch existed for one commit of this round -- the rows-first kernel lost and was removed; MAU_WHOLE_WAVES=0 still works)
 O=gpurun_out; mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -q > $O/r02c10_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/r02c10_pytest.log
 timeout 200 python tools/bw_bench.py > $O/r02c10_bw_new.txt 2>&1; echo "bw new rc=$?"

@@ -2,6 +2,8 @@
 # last 1-GPU call of round 2: lean bilinear backward (csrc/bilinear_bwd_lean.cuh) against the first-generation kernel
 # (MAU_BILINEAR_BWD=stream), kernel level and step level, interleaved on one box; then -- with whichever won -- smoke, the
 # default bench line, the bandwidth table and the launch list of one training step.
+# (historical record of the call: MAU_BILINEAR_BWD=stream selected the first-generation kernel at that commit; it was removed
+# after this call, the switch no longer exists)
 O=gpurun_out; mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -q > $O/r02g_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r02g_pytest.log
 BW_ONLY=bilinear_bwd timeout 100 python tools/bw_bench.py > $O/r02g_bw_lean.txt 2>&1

@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2, last experiment: lean bilinear backward at three resident blocks per SM (80 registers) against the
 # 127-register build (MAU_BILINEAR_OCC=2): tests on the default, kernel level and step level A/B, smoke
+# (historical record of the call: the 127-register build and MAU_BILINEAR_OCC existed at that commit only)
 O=gpurun_out; mkdir -p $O
 timeout 400 python -m pytest tests -m gpu -q > $O/r02o_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r02o_pytest.log
 BW_ONLY=bilinear_bwd timeout 100 python tools/bw_bench.py > $O/r02o_bw_occ3.txt 2>&1

@@ -2,6 +2,8 @@
 # round 2, last call: BatchNorm backward kernels compiled for three resident blocks per SM (80 registers, some spills) and
 # the head backward for four (64 registers) -- a second library built with -DMAU_BN_BWD_MIN_BLOCKS=3 -DMAU_HEAD_BWD_OCC4 --
 # against the default build: per-kernel bandwidth, training step, then tests + smoke ON THE VARIANT.
+# (the variant library is not part of the build: nvcc ... -DMAU_BN_BWD_MIN_BLOCKS=3 -DMAU_HEAD_BWD_OCC4 -c norm.cu / elementwise.cu,
+# linked with the other objects of csrc/obj into metadata-augmented-unet-for-lst-ndvi_b200/libmau_b200_occ.so; it lost -- see profiles/r02_training_step.md)
 O=gpurun_out; mkdir -p $O; P=metadata-augmented-unet-for-lst-ndvi_b200
 export BW_ONLY=bn_bwd_reduce,bn_bwd_apply,head_bwd
 B="python bench.py --config 3 --no-cpu-baseline --sustain-s 1 --no-e2e --no-riders"
