@@ -152,6 +152,19 @@ int mau_plan_wait_backward_streams(mau_plan* plan, void* stream);
 typedef void (*mau_stats_sync_fn)(void* user, void* sums_dev, int n_doubles);
 int mau_plan_set_stats_sync(mau_plan* plan, mau_stats_sync_fn fn, void* user, int world_size);
 
+/* Environment switches read by the library (all optional; measurement / A-B knobs, none changes results beyond rounding order):
+ *   MAU_SM_RESERVE=n        default of mau_set_sm_reserve (below)
+ *   MAU_WHOLE_WAVES=0       equal-work element-wise kernels (BatchNorm apply passes, head backward) keep the grids they
+ *                           had before they were rounded down to whole waves of resident blocks
+ *   MAU_WGRAD_PAIR=0        weight gradients of the <= 64-channel sides on the split-K kernel instead of the tap-pair kernel
+ *   MAU_WGRAD_SWAP=0..3     force the weight-gradient form (0 / 1: split-K kernel, operand orientation; 2 / 3: tap-pair kernel
+ *                           with dY / X carrying the tap shift)
+ *   MAU_WGRAD_FORK_LATE=1   second (weight-gradient) stream forks behind the data gradient instead of behind the BatchNorm
+ *                           backward
+ *   MAU_NO_COL3=1, MAU_NO_BRES=1, MAU_CONV_CFG=bn,mt,nbuf   convolution tile selection (column-folded N = 192 form, resident
+ *                           weights, explicit tile shape)
+ * The Python layer adds MAU_PRECISION (bf16 | fp32) and MAU_FLAGS (MAU_FLAG_* bits or-ed into every plan). */
+
 /* SMs the persistent kernels leave free (default 0, or $MAU_SM_RESERVE): set it to the number of CTAs
  * a concurrently running collective (NCCL all-reduce overlapped with backward) occupies, so that a
  * persistent grid never spills into a second wave.  Applies to the BACKWARD launches (dgrad, wgrad) of
